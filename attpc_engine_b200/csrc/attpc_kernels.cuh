@@ -1,0 +1,952 @@
+// Device code of the AT-TPC detector-simulation hot path for B200 (sm_100a).
+//
+// Stages (one kernel each, all launched on the handle's stream; see DESIGN.md for the data layout):
+//   track_kernel      Lorentz force + energy loss, Dormand-Prince 5(4) on the reference's 0.1 ns grid, one lane
+//                     per track with a dynamic work cursor; fused Fano electrons, >=1 mask, gain, z -> time bucket
+//                     (detector/solver.py:19-76, 243-305, 308-347, 386-398).
+//   replay_kernel     the same electron/mask/gain/time arithmetic from GIVEN trajectory rows and normals, in the
+//                     reference's exact operation order (parity part (a)).
+//   deposit_kernel    one warp per active point: sigma_t, 10x10 mesh, pad lookup, bivariate-normal share, Szudzik
+//                     key, accumulate into the event's open-addressing table kept L2-resident
+//                     (detector/transporter.py:11-41, 78-120, 123-249, 252-317; detector/pairing.py:6-28).
+//   collect/scan/emit TB wiggle, 0 <= tb < 512 mask, canonical (ascending-key) order, CSR compaction
+//                     (detector/simulator.py:19-49, 104-115); optional Spyral rows (detector/writer.py:61-112).
+//
+// Arithmetic that decides a pad id, a time bucket or an integer charge is written with the _rn intrinsics so that
+// nvcc cannot contract it into FMAs: it must round exactly like the reference's numpy/numba code.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "philox.cuh"
+
+namespace attpc {
+
+constexpr int MAX_SPECIES = 8;
+constexpr int MAX_TRACKS_PER_EVENT = 16;
+constexpr int GRID_POINTS = 10001;        // detector/solver.py:16
+constexpr double GRID_DT = 1.0e-10;       // s
+constexpr double C_LIGHT = 299792458.0;   // detector/constants.py
+constexpr double KE_LIMIT = 1.0e-6;       // MeV, detector/solver.py:14
+constexpr double Z_HI = 1.0, Z_LO = 0.0, RHO_MAX = 0.292;  // detector/solver.py:160,200,240
+constexpr int MESH_N = 10;                // detector/transporter.py:8
+constexpr int NUM_TB = 512;               // detector/constants.py:23
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+struct SpeciesDev {
+    double mass;     // MeV/c^2
+    double qm_c;     // Z e / (m_kg c)  [1/(T s)]
+    int32_t z;
+    int32_t table;   // offset (in doubles) of this species' deceleration table
+};
+
+// Scalars every kernel reads; passed by value as a __grid_constant__ parameter.
+struct SimParams {
+    double length, dv, mm_edge, win_edge, diffusion, efield, fano, ev_per_w;
+    double B, E;  // negated fields, detector/solver.py:298-299
+    long long gain;
+    double grid_low, grid_high;
+    int32_t lut_origin, lut_n;
+    double adc_threshold;
+    double rtol, atol, freeze_ke;
+    int32_t lm, e_min, n_oct, n_nodes;
+    int32_t n_species, n_pads, n_response, pad0;
+    SpeciesDev sp[MAX_SPECIES];
+    const int16_t* lut;
+    const double* tables;  // [n_species][n_nodes]: dE/dx * MEV_2_JOULE * density * 100 / (m_kg c)  -> d(gamma beta)/dt
+    const double* pad_xy;
+    const double* pad_scale;
+    const double* response;
+    const double* resp_sorted;   // response sorted descending
+    const double* resp_prefix;   // prefix sums of resp_sorted, [n_response + 1]
+    double resp_max;
+};
+
+// Active track points (>= 1 electron), appended per event group by the track kernels.
+struct PointBuf {
+    double* x;
+    double* y;
+    double* t;          // exact time bucket (float), detector/solver.py:396-398
+    long long* q;       // electrons after mpgd_gain
+    int32_t* ev;        // event slot inside the launch batch
+    int32_t* rank;      // position of the track in `indices`
+    unsigned* count;    // [n_groups]
+    int64_t group_cap;  // points per group
+    int32_t group_events;
+};
+
+struct Counters {
+    unsigned long long track_cursor;
+    unsigned long long traj_points, active_points, primary_electrons, deposits, keys;
+    unsigned long long out_points, out_rows;   // running CSR totals
+    int overflow_points, overflow_hash, overflow_out, replay_miss;
+};
+
+struct HashEntry {
+    unsigned key1;   // Szudzik key + 1, 0 = empty
+    unsigned rank;   // highest track rank that touched the key (label precedence, transporter.py:247-249)
+    unsigned long long charge;
+};
+
+// ----------------------------------------------------------------------------------------------- stopping power
+struct TableView {
+    const double* t;
+    double ke_min, inv_ke_min;
+    int32_t hi_min, shift, last;
+    double frac_scale;
+};
+
+__device__ __forceinline__ TableView make_table_view(const SimParams& P, const double* base) {
+    TableView v;
+    v.t = base;
+    v.shift = 52 - P.lm;
+    v.hi_min = (1023 + P.e_min) << P.lm;
+    v.last = P.n_nodes - 1;
+    v.ke_min = __longlong_as_double((long long)(1023 + P.e_min) << 52);
+    v.inv_ke_min = 1.0 / v.ke_min;
+    v.frac_scale = __longlong_as_double((long long)(1023 - v.shift) << 52);  // 2^-shift
+    return v;
+}
+
+// attpc_engine_b200/target.py:DedxTable.__call__ on the pre-scaled table.
+__device__ __forceinline__ double table_eval(const TableView& v, double ke) {
+    if (!(ke >= v.ke_min)) return ke > 0.0 ? v.t[0] * sqrt(ke * v.inv_ke_min) : 0.0;
+    const long long bits = __double_as_longlong(ke);
+    const int i = (int)(bits >> v.shift) - v.hi_min;
+    if (i >= v.last) return v.t[v.last];
+    const double f = (double)(bits & ((1LL << v.shift) - 1)) * v.frac_scale;
+    const double lo = v.t[i];
+    return fma(f, v.t[i + 1] - lo, lo);
+}
+
+// -------------------------------------------------------------------------------------------- equation of motion
+struct State {
+    double x, y, z, ux, uy, uz;
+};
+
+struct TrackConst {
+    double mass, qmB, qmE;  // qm_c * B, qm_c * E
+    TableView tab;
+};
+
+__device__ __forceinline__ double kinetic_energy(const TrackConst& c, double ux, double uy, double uz) {
+    const double g2 = ux * ux + uy * uy + uz * uz;
+    return c.mass * g2 / (sqrt(1.0 + g2) + 1.0);  // m (gamma - 1) without the cancellation
+}
+
+// detector/solver.py:52-76 with u = gamma*beta:  v = u c / gamma,  du/dt = (q/m (v x B + E) - a u_hat) / c
+__device__ __forceinline__ State rhs(const TrackConst& c, const State& s) {
+    const double g2 = s.ux * s.ux + s.uy * s.uy + s.uz * s.uz;
+    const double gamma = sqrt(1.0 + g2);
+    const double ke = c.mass * g2 / (gamma + 1.0);
+    const double a = table_eval(c.tab, ke);
+    const double c_over_gamma = C_LIGHT / gamma;
+    const double drag = g2 > 0.0 ? a * rsqrt(g2) : 0.0;
+    State d;
+    d.x = s.ux * c_over_gamma;
+    d.y = s.uy * c_over_gamma;
+    d.z = s.uz * c_over_gamma;
+    d.ux = c.qmB * d.y - drag * s.ux;
+    d.uy = -c.qmB * d.x - drag * s.uy;
+    d.uz = c.qmE - drag * s.uz;
+    return d;
+}
+
+#define ATTPC_COMBINE(dst, base, h, expr)   \
+    dst.x = base.x + (h) * (expr(x));       \
+    dst.y = base.y + (h) * (expr(y));       \
+    dst.z = base.z + (h) * (expr(z));       \
+    dst.ux = base.ux + (h) * (expr(ux));    \
+    dst.uy = base.uy + (h) * (expr(uy));    \
+    dst.uz = base.uz + (h) * (expr(uz));
+
+// One Dormand-Prince 5(4) step of size h from (y, k1 = f(y)).  Returns the scaled RMS error (<= 1 accepts).
+__device__ __forceinline__ double dopri5_step(const TrackConst& c, const State& y, const State& k1, double h,
+                                              double rtol, double atol, State& ynew, State& knew) {
+    State t, k2, k3, k4, k5, k6;
+#define E2(f) (0.2 * k1.f)
+    ATTPC_COMBINE(t, y, h, E2)
+    k2 = rhs(c, t);
+#define E3(f) (3.0 / 40.0 * k1.f + 9.0 / 40.0 * k2.f)
+    ATTPC_COMBINE(t, y, h, E3)
+    k3 = rhs(c, t);
+#define E4(f) (44.0 / 45.0 * k1.f - 56.0 / 15.0 * k2.f + 32.0 / 9.0 * k3.f)
+    ATTPC_COMBINE(t, y, h, E4)
+    k4 = rhs(c, t);
+#define E5(f) (19372.0 / 6561.0 * k1.f - 25360.0 / 2187.0 * k2.f + 64448.0 / 6561.0 * k3.f - 212.0 / 729.0 * k4.f)
+    ATTPC_COMBINE(t, y, h, E5)
+    k5 = rhs(c, t);
+#define E6(f)                                                                                              \
+    (9017.0 / 3168.0 * k1.f - 355.0 / 33.0 * k2.f + 46732.0 / 5247.0 * k3.f + 49.0 / 176.0 * k4.f - \
+     5103.0 / 18656.0 * k5.f)
+    ATTPC_COMBINE(t, y, h, E6)
+    k6 = rhs(c, t);
+#define E7(f) \
+    (35.0 / 384.0 * k1.f + 500.0 / 1113.0 * k3.f + 125.0 / 192.0 * k4.f - 2187.0 / 6784.0 * k5.f + 11.0 / 84.0 * k6.f)
+    ATTPC_COMBINE(ynew, y, h, E7)
+    knew = rhs(c, ynew);
+#define EE(f)                                                                                                  \
+    (71.0 / 57600.0 * k1.f - 71.0 / 16695.0 * k3.f + 71.0 / 1920.0 * k4.f - 17253.0 / 339200.0 * k5.f + \
+     22.0 / 525.0 * k6.f - 1.0 / 40.0 * knew.f)
+    double acc = 0.0;
+#define ERRTERM(f)                                                              \
+    {                                                                           \
+        const double sc = atol + rtol * fmax(fabs(y.f), fabs(ynew.f));          \
+        const double e = h * (EE(f)) / sc;                                      \
+        acc += e * e;                                                           \
+    }
+    ERRTERM(x) ERRTERM(y) ERRTERM(z) ERRTERM(ux) ERRTERM(uy) ERRTERM(uz)
+#undef E2
+#undef E3
+#undef E4
+#undef E5
+#undef E6
+#undef E7
+#undef EE
+#undef ERRTERM
+    return sqrt(acc * (1.0 / 6.0));
+}
+
+// Advance one 0.1 ns grid cell with error-controlled sub-steps (nsub halves/doubles adaptively).
+__device__ __forceinline__ void advance_cell(const TrackConst& c, State& y, State& k, int& nsub, double rtol,
+                                             double atol) {
+    const State y0 = y, k0 = k;
+    while (true) {
+        const double h = GRID_DT / (double)nsub;
+        bool ok = true;
+        double worst = 0.0;
+        for (int s = 0; s < nsub; ++s) {
+            State yn, kn;
+            const double err = dopri5_step(c, y, k, h, rtol, atol, yn, kn);
+            if (!(err <= 1.0) && nsub < 4096) {
+                ok = false;
+                break;
+            }
+            worst = fmax(worst, err);
+            y = yn;
+            k = kn;
+        }
+        if (ok) {
+            if (nsub > 1 && worst < 0.01) nsub >>= 1;
+            return;
+        }
+        nsub <<= 1;
+        y = y0;
+        k = k0;
+    }
+}
+
+// scipy's event rule (scipy/integrate/_ivp/ivp.py: find_active_events) applied per grid cell, with the
+// reference's directions (detector/solver.py:276-283).
+__device__ __forceinline__ bool crossed_up(double g0, double g1) { return g0 <= 0.0 && g1 >= 0.0; }
+__device__ __forceinline__ bool crossed_down(double g0, double g1) { return g0 >= 0.0 && g1 <= 0.0; }
+
+__device__ __forceinline__ bool terminal_event(const TrackConst& c, const State& a, const State& b, double ke_a,
+                                               double ke_b) {
+    return crossed_down(ke_a - KE_LIMIT, ke_b - KE_LIMIT) || crossed_up(a.z - Z_HI, b.z - Z_HI) ||
+           crossed_down(a.z - Z_LO, b.z - Z_LO) ||
+           crossed_up(hypot(a.x, a.y) - RHO_MAX, hypot(b.x, b.y) - RHO_MAX);
+}
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Warp-aggregated append of one active point per emitting lane into the lane's event-group region.
+__device__ __forceinline__ void append_point(const PointBuf& pb, Counters* ctr, bool emit, int ev, int rank,
+                                             double x, double y, double t, long long q) {
+    if (!emit) return;
+    const int g = ev / pb.group_events;
+    const unsigned pos = atomicAdd(&pb.count[g], 1u);
+    if ((int64_t)pos >= pb.group_cap) {
+        ctr->overflow_points = 1;
+        return;
+    }
+    const int64_t i = (int64_t)g * pb.group_cap + pos;
+    pb.x[i] = x;
+    pb.y[i] = y;
+    pb.t[i] = t;
+    pb.q[i] = q;
+    pb.ev[i] = ev;
+    pb.rank[i] = rank;
+}
+
+struct TrackBatch {
+    const double* momenta;   // [n_events, n_nuclei, 4]
+    const double* vertices;  // [n_events, 3]
+    int64_t n_events;
+    int32_t n_nuclei, n_tracks_per_event;
+    int32_t nucleus[MAX_TRACKS_PER_EVENT];
+    int32_t species[MAX_TRACKS_PER_EVENT];
+    uint64_t seed;
+    int64_t first_event;  // global id of event slot 0
+    // trajectory recording (attpc_trajectories): one track per "event", rows to rec_points
+    const int32_t* rec_species;  // [n_events]
+    double* rec_points;          // [n_events, rec_max, 6]
+    int32_t* rec_counts;         // [n_events]
+    int32_t rec_stride, rec_max;
+};
+
+constexpr int TRACK_THREADS = 128;
+
+// One lane integrates one track at a time and pulls the next from a global cursor when it finishes, so short
+// (exiting) tracks do not wait for the long (stopping) tracks of the same warp.
+template <bool TAB_SMEM, bool RECORD>
+__global__ void __launch_bounds__(TRACK_THREADS)
+track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackBatch tb, PointBuf pb, Counters* ctr) {
+    extern __shared__ double s_tab[];
+    if (TAB_SMEM) {
+        const int n = P.n_species * P.n_nodes;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_tab[i] = P.tables[i];
+        __syncthreads();
+    }
+    const double* tab_base = TAB_SMEM ? s_tab : P.tables;
+    const int64_t n_tracks = tb.n_events * tb.n_tracks_per_event;
+
+    bool have = false, done = false;
+    TrackConst c;
+    State y, k;
+    double ke = 0.0;
+    int step = 0, nsub = 1, ev = 0, rank = 0, nucleus = 0;
+    int64_t track = 0;
+    unsigned long long n_traj = 0, n_active = 0, n_prim = 0;
+
+    while (true) {
+        if (!have && !done) {
+            track = (int64_t)atomicAdd(&ctr->track_cursor, 1ULL);
+            if (track >= n_tracks) {
+                done = true;
+            } else {
+                ev = (int)(track / tb.n_tracks_per_event);
+                rank = (int)(track % tb.n_tracks_per_event);
+                const int sp = RECORD ? tb.rec_species[track] : tb.species[rank];
+                nucleus = RECORD ? 0 : tb.nucleus[rank];
+                if (sp >= 0) {
+                    const SpeciesDev& S = P.sp[sp];
+                    const double* m4 = tb.momenta + ((int64_t)ev * tb.n_nuclei + nucleus) * 4;
+                    const double* vx = tb.vertices + (int64_t)ev * 3;
+                    c.mass = S.mass;
+                    c.qmB = S.qm_c * P.B;
+                    c.qmE = S.qm_c * P.E;
+                    c.tab = make_table_view(P, tab_base + S.table);
+                    y.x = vx[0];
+                    y.y = vx[1];
+                    y.z = vx[2];
+                    y.ux = m4[0] / S.mass;  // detector/solver.py:270-273
+                    y.uy = m4[1] / S.mass;
+                    y.uz = m4[2] / S.mass;
+                    k = rhs(c, y);
+                    ke = kinetic_energy(c, y.ux, y.uy, y.uz);
+                    step = 0;
+                    nsub = 1;
+                    have = true;
+                    n_traj += 1;  // grid point 0 (never active: detector/solver.py:338-339)
+                    if (RECORD && tb.rec_max > 0) {
+                        double* o = tb.rec_points + (int64_t)track * tb.rec_max * 6;
+                        o[0] = y.x; o[1] = y.y; o[2] = y.z; o[3] = y.ux; o[4] = y.uy; o[5] = y.uz;
+                    }
+                } else if (RECORD) {
+                    tb.rec_counts[track] = 0;
+                }
+            }
+        }
+        if (__all_sync(FULL, done)) break;
+
+        bool emit = false;
+        double ex = 0.0, ey = 0.0, et = 0.0;
+        long long eq = 0;
+        if (have) {
+            const State y_prev = y;
+            const double ke_prev = ke;
+            advance_cell(c, y, k, nsub, P.rtol, P.atol);
+            ke = kinetic_energy(c, y.ux, y.uy, y.uz);
+            bool finished = terminal_event(c, y_prev, y, ke_prev, ke);
+            if (!finished) {
+                step += 1;
+                n_traj += 1;
+                if (RECORD) {
+                    if (step % tb.rec_stride == 0 && step / tb.rec_stride < tb.rec_max) {
+                        double* o = tb.rec_points + ((int64_t)track * tb.rec_max + step / tb.rec_stride) * 6;
+                        o[0] = y.x; o[1] = y.y; o[2] = y.z; o[3] = y.ux; o[4] = y.uy; o[5] = y.uz;
+                    }
+                } else {
+                    // detector/solver.py:338-346: mean = |dKE| / W, Gaussian with variance F * mean, truncation
+                    const double mean = fabs(ke - ke_prev) * P.ev_per_w;
+                    const double spread = sqrt(P.fano * mean);
+                    if (mean + spread * NORMAL_ABS_MAX >= 1.0) {
+                        const double zn = philox_normal(tb.seed, (uint64_t)(tb.first_event + ev), (uint32_t)nucleus,
+                                                        (uint32_t)step);
+                        const long long n_e = (long long)(mean + spread * zn);
+                        if (n_e >= 1) {  // detector/solver.py:387
+                            emit = true;
+                            ex = y.x;
+                            ey = y.y;
+                            et = (P.length - y.z) / P.dv + P.mm_edge;  // detector/solver.py:396-398
+                            eq = n_e * P.gain;                          // detector/solver.py:392
+                            n_active += 1;
+                            n_prim += (unsigned long long)n_e;
+                        }
+                    }
+                }
+                if (step >= GRID_POINTS - 1 || ke < P.freeze_ke) finished = true;
+            }
+            if (finished) {
+                have = false;
+                if (RECORD) tb.rec_counts[track] = step + 1;
+            }
+        }
+        if (!RECORD) append_point(pb, ctr, emit, ev, rank, ex, ey, et, eq);
+    }
+    // per-warp statistics
+    for (int o = 16; o > 0; o >>= 1) {
+        n_traj += __shfl_xor_sync(FULL, n_traj, o);
+        n_active += __shfl_xor_sync(FULL, n_active, o);
+        n_prim += __shfl_xor_sync(FULL, n_prim, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&ctr->traj_points, n_traj);
+        atomicAdd(&ctr->active_points, n_active);
+        atomicAdd(&ctr->primary_electrons, n_prim);
+    }
+}
+
+// --------------------------------------------------------------------------------------------------- replay
+struct ReplayBatch {
+    const int64_t* track_offsets;  // [n_tracks + 1]
+    const double* rows;            // [n_rows, 6]
+    const double* normals;         // [n_rows]
+    const int32_t* track_event;
+    const int32_t* track_rank;
+    const int32_t* track_species;
+    int64_t n_tracks, n_rows;
+    long long* electrons_out;      // may be null
+};
+
+// detector/solver.py:332-335 in numpy's operation order (norm = sqrt((a*a + b*b) + c*c)).
+__device__ __forceinline__ double reference_ke(const double* r, double mass) {
+    const double gv =
+        __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(r[3], r[3]), __dmul_rn(r[4], r[4])), __dmul_rn(r[5], r[5])));
+    const double g2 = __dmul_rn(gv, gv);
+    const double beta = __dsqrt_rn(__ddiv_rn(g2, __dadd_rn(1.0, g2)));
+    const double gamma = __ddiv_rn(gv, beta);
+    return __dmul_rn(mass, __dsub_rn(gamma, 1.0));
+}
+
+__global__ void __launch_bounds__(256)
+replay_kernel(const __grid_constant__ SimParams P, ReplayBatch rb, PointBuf pb, Counters* ctr) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rb.n_rows) return;
+    // locate the track of row r
+    int64_t lo = 0, hi = rb.n_tracks;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (rb.track_offsets[mid] <= r) lo = mid; else hi = mid;
+    }
+    const int64_t t = lo;
+    const int sp = rb.track_species[t];
+    long long n_e = 0;
+    if (sp >= 0) {
+        const double mass = P.sp[sp].mass;
+        double mean = 0.0;  // row 0 of a track: electrons[0] = 0 (detector/solver.py:338-339)
+        if (r > rb.track_offsets[t]) {
+            const double ke1 = reference_ke(rb.rows + r * 6, mass);
+            const double ke0 = reference_ke(rb.rows + (r - 1) * 6, mass);
+            mean = __dmul_rn(fabs(__dsub_rn(ke1, ke0)), P.ev_per_w);
+        }
+        // rng.normal(mean, sqrt(F mean)) == mean + sqrt(F mean) * standard_normal  (numpy legacy-free Generator)
+        const double draw = __dadd_rn(mean, __dmul_rn(__dsqrt_rn(__dmul_rn(P.fano, mean)), rb.normals[r]));
+        n_e = (long long)draw;  // C truncation, like ndarray.astype(int64)
+        atomicAdd(&ctr->traj_points, 1ULL);
+    }
+    if (rb.electrons_out) rb.electrons_out[r] = n_e;
+    if (n_e >= 1) {
+        const double* row = rb.rows + r * 6;
+        const double time = __dadd_rn(__ddiv_rn(__dsub_rn(P.length, row[2]), P.dv), P.mm_edge);
+        append_point(pb, ctr, true, rb.track_event[t], rb.track_rank[t], row[0], row[1], time, n_e * P.gain);
+        atomicAdd(&ctr->active_points, 1ULL);
+        atomicAdd(&ctr->primary_electrons, (unsigned long long)n_e);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- pad lookup
+// detector/transporter.py:78-120 then pad_grid[ix, iy] and the beam-pad veto (:165, :237), all folded into the
+// 1 mm lookup table built by the host (engine.build_pad_lut).  Returns -1 for "no deposit".
+__device__ __forceinline__ int lookup_pad(const SimParams& P, double x_m, double y_m) {
+    const double fx = floor(__dmul_rn(x_m, 1000.0));
+    const double fy = floor(__dmul_rn(y_m, 1000.0));
+    if (fx >= P.grid_high || fy >= P.grid_high) return -1;
+    if (fx < P.grid_low || fy < P.grid_low) return -1;
+    if (!(fx == fx) || !(fy == fy)) return -1;  // NaN positions never index the table
+    const int ix = (int)fx - P.lut_origin, iy = (int)fy - P.lut_origin;
+    if ((unsigned)ix >= (unsigned)P.lut_n || (unsigned)iy >= (unsigned)P.lut_n) return -1;
+    return (int)__ldg(P.lut + (int64_t)ix * P.lut_n + iy);
+}
+
+__global__ void lookup_kernel(const __grid_constant__ SimParams P, const double* xy, int64_t n, int32_t* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lookup_pad(P, xy[2 * i], xy[2 * i + 1]);
+}
+
+// detector/pairing.py:6-28
+__device__ __forceinline__ unsigned szudzik_pair(unsigned tb, unsigned pad) {
+    return tb >= pad ? tb * tb + tb + pad : pad * pad + tb;
+}
+
+// detector/pairing.py:31-55 in integers
+__device__ __forceinline__ void szudzik_unpair(unsigned key, unsigned& tb, unsigned& pad) {
+    unsigned s = (unsigned)sqrt((double)key);
+    while (s * s > key) --s;
+    while ((s + 1) * (s + 1) <= key) ++s;
+    const unsigned rem = key - s * s;
+    if (rem < s) {
+        tb = rem;
+        pad = s;
+    } else {
+        tb = s;
+        pad = rem - s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- accumulate
+__device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) { return (key * 2654435761u >> 7) & mask; }
+
+// points[id] = (charge + q, label) of detector/transporter.py:166-169, 247-249: integer adds commute and the label
+// is "last track in indices order", i.e. the maximum rank, so the result does not depend on thread order.
+__device__ __forceinline__ void table_add(HashEntry* tab, unsigned mask, unsigned key, long long q, unsigned rank,
+                                          Counters* ctr) {
+    const unsigned key1 = key + 1u;
+    unsigned slot = hash_slot(key, mask);
+    for (unsigned probe = 0; probe <= mask; ++probe) {
+        unsigned k = __ldcg(&tab[slot].key1);
+        if (k == 0u) {
+            k = atomicCAS(&tab[slot].key1, 0u, key1);
+            if (k == 0u) k = key1;
+        }
+        if (k == key1) {
+            if (q != 0) atomicAdd(&tab[slot].charge, (unsigned long long)q);
+            if (__ldcg(&tab[slot].rank) < rank) atomicMax(&tab[slot].rank, rank);
+            return;
+        }
+        slot = (slot + 1u) & mask;
+    }
+    ctr->overflow_hash = 1;
+}
+
+struct GroupView {
+    int32_t first_slot;   // first event slot of the group inside the launch batch
+    int32_t n_events;     // events in this group
+    int32_t group;        // group index (selects the PointBuf region)
+    int32_t hash_cap;     // slots per event (power of two)
+    HashEntry* tables;    // [group_events][hash_cap]
+};
+
+constexpr int DEPOSIT_THREADS = 256;
+
+// One warp per active point; lanes cover the 10x10 mesh (pixel = lane + 32 r).
+__global__ void __launch_bounds__(DEPOSIT_THREADS)
+deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, Counters* ctr) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_points = min((int64_t)pb.count[gv.group], pb.group_cap);
+    const int64_t base = (int64_t)gv.group * pb.group_cap;
+    const unsigned mask = (unsigned)gv.hash_cap - 1u;
+    unsigned long long n_dep = 0;
+
+    for (int64_t p = warp; p < n_points; p += n_warps) {
+        const double cx = pb.x[base + p], cy = pb.y[base + p], time = pb.t[base + p];
+        const long long q = pb.q[base + p];
+        const int ev = pb.ev[base + p] - gv.first_slot;
+        const unsigned rank = (unsigned)pb.rank[base + p];
+        HashEntry* tab = gv.tables + (int64_t)ev * gv.hash_cap;
+        // detector/transporter.py:301, evaluated left to right
+        const double sigma =
+            __dsqrt_rn(__ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, P.diffusion), P.dv), time), P.efield));
+        const int tb = (int)time;  // detector/transporter.py:165, 238
+        if (tb < 0 || !(sigma == sigma)) continue;  // never reached for z <= length + mm_edge * dv
+        if (sigma == 0.0) {  // detector/transporter.py:123-169
+            if (lane == 0) {
+                const int pad = lookup_pad(P, cx, cy);
+                if (pad >= 0) {
+                    table_add(tab, mask, szudzik_pair((unsigned)tb, (unsigned)pad), q, rank, ctr);
+                    n_dep += 1;
+                }
+            }
+            continue;
+        }
+        // detector/transporter.py:217-226 with numba's linspace (numba/np/arrayobj.py: linspace)
+        const double three_sigma = __dmul_rn(3.0, sigma);
+        const double lo_x = __dsub_rn(cx, three_sigma), hi_x = __dadd_rn(cx, three_sigma);
+        const double lo_y = __dsub_rn(cy, three_sigma), hi_y = __dadd_rn(cy, three_sigma);
+        const double dx = __ddiv_rn(__dsub_rn(hi_x, lo_x), (double)(MESH_N - 1));
+        const double dy = __ddiv_rn(__dsub_rn(hi_y, lo_y), (double)(MESH_N - 1));
+        const double cell = __ddiv_rn(__dmul_rn(6.0, sigma), (double)(MESH_N - 1));
+        const double cell2 = __dmul_rn(cell, cell);
+        const double s2 = __dmul_rn(sigma, sigma);
+        const double norm = __ddiv_rn(__ddiv_rn(0.5, 3.141592653589793), s2);  // 1 / 2 / pi / sigma**2
+        const double c2 = __ddiv_rn(-0.5, s2);                                 // -1 / 2 / sigma**2
+        const double qd = (double)q;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int pix = lane + 32 * r;
+            if (pix >= MESH_N * MESH_N) break;
+            const int i = pix / MESH_N, j = pix - i * MESH_N;
+            const double px = (i == MESH_N - 1) ? hi_x : __dadd_rn(lo_x, __dmul_rn((double)i, dx));
+            const double py = (j == MESH_N - 1) ? hi_y : __dadd_rn(lo_y, __dmul_rn((double)j, dy));
+            const int pad = lookup_pad(P, px, py);
+            if (pad < 0) continue;
+            // detector/transporter.py:36-41, 240-246
+            const double ddx = __dsub_rn(px, cx), ddy = __dsub_rn(py, cy);
+            const double arg = __dmul_rn(c2, __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
+            const double pdf = __dmul_rn(norm, exp(arg));
+            const long long share = (long long)__dmul_rn(__dmul_rn(pdf, cell2), qd);
+            table_add(tab, mask, szudzik_pair((unsigned)tb, (unsigned)pad), share, rank, ctr);
+            n_dep += 1;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) n_dep += __shfl_xor_sync(FULL, n_dep, o);
+    if (lane == 0 && n_dep) atomicAdd(&ctr->deposits, n_dep);
+}
+
+// ---------------------------------------------------------------------------------------------------- finalize
+struct ReplayUniforms {
+    const int64_t* offsets;  // [n_events + 1] or null
+    const int64_t* keys;
+    const double* vals;
+};
+
+struct FinalizeArgs {
+    uint64_t seed;
+    int64_t first_event;      // global id of event slot 0 of the launch batch
+    uint32_t flags;
+    int32_t n_tracks_per_event;
+    int32_t label_of_rank[MAX_TRACKS_PER_EVENT];
+    const int32_t* label_of_event_rank;  // replay: [n_events, n_tracks_per_event] or null
+    ReplayUniforms replay;
+    uint64_t* sort_items;     // [group_events][hash_cap] scratch: (order key << 32) | slot
+    unsigned* kept;           // [launch events] rows kept per event
+    int64_t* offsets;         // [launch events + 1] CSR offsets (global across groups of the launch)
+    double* cloud;            // [out_cap, 3]
+    int64_t* labels;          // [out_cap]
+    int64_t out_cap;
+};
+
+constexpr uint32_t F_KEEP_ALL_TB = 1u, F_SPYRAL = 2u, F_NO_WIGGLE = 4u;
+
+__device__ __forceinline__ double wiggle_of(const FinalizeArgs& fa, int slot_event, unsigned key, Counters* ctr) {
+    if (fa.flags & F_NO_WIGGLE) return 0.0;
+    if (fa.replay.offsets) {
+        int64_t lo = fa.replay.offsets[slot_event], hi = fa.replay.offsets[slot_event + 1];
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            const int64_t k = fa.replay.keys[mid];
+            if (k == (int64_t)key) return fa.replay.vals[mid];
+            if (k < (int64_t)key) lo = mid + 1; else hi = mid;
+        }
+        ctr->replay_miss = 1;
+        return 0.0;
+    }
+    return philox_uniform(fa.seed, (uint64_t)(fa.first_event + slot_event), STREAM_WIGGLE, key);
+}
+
+constexpr int FINALIZE_THREADS = 256;
+constexpr int SORT_SMEM_ITEMS = 8192;  // 64 KB of shared memory
+
+__device__ __forceinline__ void bitonic_sort(uint64_t* a, int n_pow2) {
+    for (int k = 2; k <= n_pow2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const uint64_t x = a[i], y = a[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        a[i] = y;
+                        a[l] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA per event: gather the occupied slots that survive the time-bucket mask and sort them by key.
+__global__ void __launch_bounds__(FINALIZE_THREADS)
+collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView gv,
+               Counters* ctr) {
+    extern __shared__ uint64_t s_items[];
+    __shared__ unsigned s_n, s_keys;
+    const int e = blockIdx.x;
+    const int slot_event = gv.first_slot + e;
+    const HashEntry* tab = gv.tables + (int64_t)e * gv.hash_cap;
+    uint64_t* items = fa.sort_items + (int64_t)e * gv.hash_cap;
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        s_keys = 0;
+    }
+    __syncthreads();
+    unsigned occupied = 0;
+    for (int i = threadIdx.x; i < gv.hash_cap; i += blockDim.x) {
+        const unsigned key1 = tab[i].key1;
+        if (key1 == 0u) continue;
+        const unsigned key = key1 - 1u;
+        occupied += 1;
+        unsigned tb, pad;
+        szudzik_unpair(key, tb, pad);
+        const double tbf = (double)tb + wiggle_of(fa, slot_event, key, ctr);  // detector/simulator.py:108
+        if ((fa.flags & F_KEEP_ALL_TB) || (0.0 <= tbf && tbf < (double)NUM_TB)) {      // detector/simulator.py:111
+            const unsigned pos = atomicAdd(&s_n, 1u);
+            items[pos] = ((uint64_t)key << 32) | (uint64_t)i;
+        }
+    }
+    if (occupied) atomicAdd(&s_keys, occupied);
+    __syncthreads();
+    const int n = (int)s_n;
+    if (threadIdx.x == 0) {
+        fa.kept[slot_event] = (unsigned)n;
+        atomicAdd(&ctr->keys, (unsigned long long)s_keys);
+    }
+    if (n <= 1) return;
+    int n2 = 1;
+    while (n2 < n) n2 <<= 1;
+    if (n2 <= SORT_SMEM_ITEMS) {
+        for (int i = threadIdx.x; i < n2; i += blockDim.x) s_items[i] = i < n ? items[i] : ~0ULL;
+        __syncthreads();
+        bitonic_sort(s_items, n2);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) items[i] = s_items[i];
+    } else {  // rare, very dense events: sort in the (L2-resident) scratch itself; hash_cap is a power of two >= n2
+        for (int i = n + threadIdx.x; i < n2; i += blockDim.x) items[i] = ~0ULL;
+        __syncthreads();
+        bitonic_sort(items, n2);
+    }
+}
+
+// Exclusive scan of the kept counts of one group onto the running CSR total (single CTA).
+__global__ void __launch_bounds__(1024)
+scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr) {
+    __shared__ unsigned long long s_part[1024];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_base = ctr->out_points;
+    __syncthreads();
+    for (int start = 0; start < gv.n_events; start += 1024) {
+        const int i = start + tid;
+        const unsigned long long v = i < gv.n_events ? fa.kept[gv.first_slot + i] : 0ULL;
+        s_part[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned long long add = tid >= o ? s_part[tid - o] : 0ULL;
+            __syncthreads();
+            s_part[tid] += add;
+            __syncthreads();
+        }
+        if (i < gv.n_events) fa.offsets[gv.first_slot + i] = (int64_t)(s_base + s_part[tid] - v);
+        __syncthreads();
+        if (tid == 0) s_base += s_part[1023];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        fa.offsets[gv.first_slot + gv.n_events] = (int64_t)s_base;
+        ctr->out_points = s_base;
+        if ((int64_t)s_base > fa.out_cap) ctr->overflow_out = 1;
+    }
+}
+
+// One CTA per event: write [pad, tb + u, electrons] rows and labels in ascending-key order
+// (detector/simulator.py:19-49, 104-115).
+__global__ void __launch_bounds__(FINALIZE_THREADS)
+emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView gv,
+            Counters* ctr) {
+    const int e = blockIdx.x;
+    const int slot_event = gv.first_slot + e;
+    const int n = (int)fa.kept[slot_event];
+    const int64_t off = fa.offsets[slot_event];
+    if (off + n > fa.out_cap) return;
+    const HashEntry* tab = gv.tables + (int64_t)e * gv.hash_cap;
+    const uint64_t* items = fa.sort_items + (int64_t)e * gv.hash_cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t it = items[i];
+        const unsigned key = (unsigned)(it >> 32);
+        const HashEntry en = tab[(unsigned)it];
+        unsigned tb, pad;
+        szudzik_unpair(key, tb, pad);
+        const double tbf = (double)tb + wiggle_of(fa, slot_event, key, ctr);
+        double* row = fa.cloud + (off + i) * 3;
+        row[0] = (double)pad;
+        row[1] = tbf;
+        row[2] = (double)(long long)en.charge;
+        fa.labels[off + i] = fa.label_of_event_rank
+                                 ? (int64_t)fa.label_of_event_rank[(int64_t)slot_event * fa.n_tracks_per_event + en.rank]
+                                 : (int64_t)fa.label_of_rank[en.rank];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ Spyral rows
+struct SpyralArgs {
+    const int64_t* offsets;   // [n_events + 1] input cloud CSR
+    const double* cloud;      // [n, 3]
+    const int64_t* labels;    // [n]
+    int64_t n_events;
+    unsigned* kept;           // [n_events]
+    int64_t* row_offsets;     // [n_events + 1]
+    double* rows;             // [n, 8] (capacity = input points)
+    int64_t* row_labels;
+    uint64_t* sort_keys;      // [n] scratch (order-preserving bits of z)
+    uint32_t* sort_idx;       // [n] scratch
+};
+
+// detector/response.py:35-57: amplitude = max(min(r_i e, 4095)), integral = sum(min(r_i e, 4095)).
+// max commutes with the monotone map r -> min(fl(r e), 4095), so amplitude = min(fl(r_max e), 4095) exactly.  The
+// integral uses the descending-sorted response and its prefix sums: entries with r_i e > 4095 form a prefix.
+__device__ __forceinline__ void shaped(const SimParams& P, double electrons, double& amp, double& integral) {
+    amp = fmin(__dmul_rn(P.resp_max, electrons), 4095.0);
+    int lo = 0, hi = P.n_response;  // first index whose scaled response is <= 4095
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__dmul_rn(P.resp_sorted[mid], electrons) > 4095.0) lo = mid + 1; else hi = mid;
+    }
+    integral = 4095.0 * (double)lo + electrons * (P.resp_prefix[P.n_response] - P.resp_prefix[lo]);
+}
+
+__device__ __forceinline__ uint64_t orderable(double v) {
+    const uint64_t b = (uint64_t)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+// pass 1: per point amplitude/threshold (detector/writer.py:232), count kept rows per event
+__global__ void __launch_bounds__(256) spyral_count_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
+    const int e = blockIdx.x;
+    __shared__ unsigned s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int64_t a = sa.offsets[e], b = sa.offsets[e + 1];
+    unsigned mine = 0;
+    for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
+        const double amp = fmin(__dmul_rn(P.resp_max, sa.cloud[i * 3 + 2]), 4095.0);
+        if (amp > P.adc_threshold) mine += 1;
+    }
+    atomicAdd(&s_n, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) sa.kept[e] = s_n;
+}
+
+__global__ void __launch_bounds__(1024) spyral_scan_kernel(SpyralArgs sa) {
+    __shared__ unsigned long long s_part[1024];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int64_t start = 0; start < sa.n_events; start += 1024) {
+        const int64_t i = start + tid;
+        const unsigned long long v = i < sa.n_events ? sa.kept[i] : 0ULL;
+        s_part[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned long long add = tid >= o ? s_part[tid - o] : 0ULL;
+            __syncthreads();
+            s_part[tid] += add;
+            __syncthreads();
+        }
+        if (i < sa.n_events) sa.row_offsets[i] = (int64_t)(s_base + s_part[tid] - v);
+        __syncthreads();
+        if (tid == 0) s_base += s_part[1023];
+        __syncthreads();
+    }
+    if (tid == 0) sa.row_offsets[sa.n_events] = (int64_t)s_base;
+}
+
+__device__ __forceinline__ void bitonic_sort_kv(uint64_t* k, uint32_t* v, int n_pow2) {
+    for (int size = 2; size <= n_pow2; size <<= 1) {
+        for (int j = size >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const uint64_t ki = k[i], kl = k[l];
+                    const uint32_t vi = v[i], vl = v[l];
+                    const bool gt = ki > kl || (ki == kl && vi > vl);
+                    if (gt == ((i & size) == 0)) {
+                        k[i] = kl; k[l] = ki;
+                        v[i] = vl; v[l] = vi;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+constexpr int SPYRAL_SMEM_ITEMS = 8192;  // 96 KB: 8 B z-bits + 4 B point index each
+
+// pass 2: one CTA per event: keep rows above threshold, order by z (detector/writer.py:236; ties, which numpy's
+// unstable argsort leaves unspecified, are broken by input order), write the 8 columns of detector/writer.py:97-110.
+__global__ void __launch_bounds__(256)
+spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
+    extern __shared__ uint64_t s_k[];
+    uint32_t* s_v = (uint32_t*)(s_k + SPYRAL_SMEM_ITEMS);
+    const int e = blockIdx.x;
+    __shared__ unsigned s_n;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const int64_t a = sa.offsets[e], b = sa.offsets[e + 1];
+    const int64_t out0 = sa.row_offsets[e];
+    const int n = (int)sa.kept[e];
+    if (n == 0) return;
+    const bool in_smem = n <= SPYRAL_SMEM_ITEMS;
+    uint64_t* keys = in_smem ? s_k : sa.sort_keys + a;
+    uint32_t* idx = in_smem ? s_v : sa.sort_idx + a;
+    const double span = (double)(P.win_edge - P.mm_edge);
+    for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
+        const double amp = fmin(__dmul_rn(P.resp_max, sa.cloud[i * 3 + 2]), 4095.0);
+        if (amp > P.adc_threshold) {
+            const unsigned pos = atomicAdd(&s_n, 1u);
+            // detector/writer.py:101-103: (window_edge - tb) / (window_edge - mm_edge) * length * 1000.0
+            const double z = __dmul_rn(
+                __dmul_rn(__ddiv_rn(__dsub_rn(P.win_edge, sa.cloud[i * 3 + 1]), span), P.length), 1000.0);
+            keys[pos] = orderable(z);
+            idx[pos] = (uint32_t)(i - a);
+        }
+    }
+    __syncthreads();
+    if (in_smem) {
+        int n2 = 1;
+        while (n2 < n) n2 <<= 1;
+        for (int i = n + threadIdx.x; i < n2; i += blockDim.x) {
+            keys[i] = ~0ULL;
+            idx[i] = 0xFFFFFFFFu;
+        }
+        __syncthreads();
+        bitonic_sort_kv(keys, idx, n2);
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        int rank = i;
+        const uint32_t id = idx[i];
+        if (!in_smem) {  // very dense events: rank by counting against the L2-resident scratch
+            const uint64_t k = keys[i];
+            rank = 0;
+            for (int j = 0; j < n; ++j) {
+                const uint64_t kj = keys[j];
+                rank += (kj < k) || (kj == k && idx[j] < id);
+            }
+        }
+        const int64_t src = a + id;
+        const double padf = sa.cloud[src * 3 + 0], tbf = sa.cloud[src * 3 + 1], el = sa.cloud[src * 3 + 2];
+        const int pad = (int)padf;
+        double amp, integral;
+        shaped(P, el, amp, integral);
+        double* row = sa.rows + (out0 + rank) * 8;
+        row[0] = P.pad_xy[2 * pad];
+        row[1] = P.pad_xy[2 * pad + 1];
+        row[2] = __dmul_rn(__dmul_rn(__ddiv_rn(__dsub_rn(P.win_edge, tbf), span), P.length), 1000.0);
+        row[3] = amp;
+        row[4] = integral;
+        row[5] = padf;
+        row[6] = tbf;
+        row[7] = P.pad_scale[pad];
+        sa.row_labels[out0 + rank] = sa.labels[src];
+    }
+}
+
+}  // namespace attpc
