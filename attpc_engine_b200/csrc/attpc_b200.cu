@@ -1,0 +1,924 @@
+// libattpc_b200.so -- host side of the C ABI declared in include/attpc_b200.h.
+//
+// One AttpcSim per GPU.  A call to attpc_simulate* walks the batch in "launches" (many events, so the
+// latency-bound track integrator has tens of thousands of lanes in flight) and each launch in "groups" of a few
+// hundred events whose accumulation tables (hash_cap x 16 B per event) fit the 126 MB L2 together: the deposit
+// and finalize kernels of a group therefore never touch HBM except for the compact CSR they emit.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/attpc_b200.h"
+#include "attpc_kernels.cuh"
+
+using namespace attpc;
+
+namespace {
+
+thread_local std::string g_create_error = "";
+
+constexpr double E_CHARGE = 1.602176634e-19;
+constexpr double MEV_2_JOULE = E_CHARGE * 1.0e6;
+constexpr double MEV_2_KG = (E_CHARGE / (C_LIGHT * C_LIGHT)) * 1.0e6;
+
+template <typename T>
+struct DevArray {
+    T* p = nullptr;
+    int64_t n = 0;
+    cudaError_t reserve(int64_t want, bool keep = false, cudaStream_t s = 0) {
+        if (want <= n) return cudaSuccess;
+        T* q = nullptr;
+        cudaError_t e = cudaMalloc((void**)&q, (size_t)want * sizeof(T));
+        if (e != cudaSuccess) return e;
+        if (keep && p && n > 0) {
+            e = cudaMemcpyAsync(q, p, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        }
+        if (p) cudaFree(p);
+        p = q;
+        n = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+template <typename T>
+struct PinnedArray {
+    T* p = nullptr;
+    int64_t n = 0;
+    cudaError_t reserve(int64_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaHostAlloc((void**)&p, (size_t)want * sizeof(T), cudaHostAllocDefault);
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace
+
+struct AttpcSim {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    SimParams P{};
+    AttpcConfig cfg{};
+    std::string error;
+    int sm_count = 148;
+    bool tables_in_smem = true;
+    size_t table_smem_bytes = 0;
+
+    // constants
+    DevArray<int16_t> lut;
+    DevArray<double> pad_xy, pad_scale, response, resp_sorted, resp_prefix, tables;
+
+    // sizing
+    int32_t launch_events = 16384;
+    int32_t group_events = 512;
+    int32_t hash_cap = 8192;
+    int64_t group_point_cap = 0;
+
+    // work buffers
+    DevArray<double> px, py, pt;
+    DevArray<long long> pq;
+    DevArray<int32_t> pev, prank;
+    DevArray<unsigned> group_count;
+    DevArray<HashEntry> hash;
+    DevArray<uint64_t> sort_items;
+    DevArray<Counters> counters;
+    DevArray<unsigned> kept;
+    DevArray<double> in_momenta, in_vertices;
+
+    // outputs
+    DevArray<int64_t> offsets_dev, labels_dev, row_offsets_dev, row_labels_dev;
+    DevArray<double> cloud_dev, rows_dev;
+    DevArray<unsigned> row_kept;
+    DevArray<uint64_t> row_sort_keys;
+    DevArray<uint32_t> row_sort_idx;
+    PinnedArray<int64_t> offsets_host, labels_host, row_offsets_host, row_labels_host;
+    PinnedArray<double> cloud_host, rows_host;
+    PinnedArray<Counters> counters_host;
+
+    std::vector<cudaEvent_t> events;
+    size_t events_used = 0;
+    int launches = 0;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        error = buf;
+        return code;
+    }
+    cudaEvent_t mark() {
+        if (events_used == events.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            events.push_back(e);
+        }
+        cudaEvent_t e = events[events_used++];
+        cudaEventRecord(e, stream);
+        return e;
+    }
+};
+
+#define CU(call)                                                                                           \
+    do {                                                                                                   \
+        cudaError_t _e = (call);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return sim->fail(ATTPC_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, \
+                             __LINE__);                                                                    \
+    } while (0)
+
+namespace {
+
+int next_pow2(int64_t v) {
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return (int)p;
+}
+
+int ensure_work_buffers(AttpcSim* sim, int64_t launch_events) {
+    const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
+    if (sim->group_point_cap == 0) sim->group_point_cap = (int64_t)sim->group_events * 1024;
+    const int64_t pts = n_groups * sim->group_point_cap;
+    CU(sim->px.reserve(pts));
+    CU(sim->py.reserve(pts));
+    CU(sim->pt.reserve(pts));
+    CU(sim->pq.reserve(pts));
+    CU(sim->pev.reserve(pts));
+    CU(sim->prank.reserve(pts));
+    CU(sim->group_count.reserve(n_groups));
+    CU(sim->hash.reserve((int64_t)sim->group_events * sim->hash_cap));
+    CU(sim->sort_items.reserve((int64_t)sim->group_events * sim->hash_cap));
+    CU(sim->counters.reserve(1));
+    CU(sim->counters_host.reserve(1));
+    return ATTPC_OK;
+}
+
+int ensure_out_buffers(AttpcSim* sim, int64_t n_events, int64_t n_points, bool keep) {
+    CU(sim->offsets_dev.reserve(n_events + 1, keep, sim->stream));
+    CU(sim->kept.reserve(n_events + 1, keep, sim->stream));
+    CU(sim->cloud_dev.reserve(n_points * 3, keep, sim->stream));
+    CU(sim->labels_dev.reserve(n_points, keep, sim->stream));
+    return ATTPC_OK;
+}
+
+PointBuf point_buf(AttpcSim* sim) {
+    PointBuf pb;
+    pb.x = sim->px.p;
+    pb.y = sim->py.p;
+    pb.t = sim->pt.p;
+    pb.q = sim->pq.p;
+    pb.ev = sim->pev.p;
+    pb.rank = sim->prank.p;
+    pb.count = sim->group_count.p;
+    pb.group_cap = sim->group_point_cap;
+    pb.group_events = sim->group_events;
+    return pb;
+}
+
+template <bool RECORD>
+int launch_tracks(AttpcSim* sim, const TrackBatch& tb, int64_t n_tracks) {
+    const int threads = TRACK_THREADS;
+    int64_t blocks64 = (n_tracks + threads - 1) / threads;
+    const int max_blocks = sim->sm_count * 4;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(blocks64, max_blocks));
+    PointBuf pb = point_buf(sim);
+    if (sim->tables_in_smem) {
+        auto kern = track_kernel<true, RECORD>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim->table_smem_bytes));
+        kern<<<blocks, threads, sim->table_smem_bytes, sim->stream>>>(sim->P, tb, pb, sim->counters.p);
+    } else {
+        track_kernel<false, RECORD><<<blocks, threads, 0, sim->stream>>>(sim->P, tb, pb, sim->counters.p);
+    }
+    sim->launches += 1;
+    CU(cudaGetLastError());
+    return ATTPC_OK;
+}
+
+// deposit + finalize of every group of one launch; the track/replay kernel has already filled the point buffers.
+int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, float* ms_deposit, float* ms_finalize,
+               std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& dep_marks,
+               std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& fin_marks) {
+    (void)ms_deposit;
+    (void)ms_finalize;
+    PointBuf pb = point_buf(sim);
+    const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
+    fa.sort_items = sim->sort_items.p;
+    const size_t sort_smem = (size_t)SORT_SMEM_ITEMS * sizeof(uint64_t);
+    CU(cudaFuncSetAttribute(collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    for (int64_t g = 0; g < n_groups; ++g) {
+        GroupView gv;
+        gv.first_slot = (int32_t)(g * sim->group_events);
+        gv.n_events = (int32_t)std::min<int64_t>(sim->group_events, launch_events - gv.first_slot);
+        gv.group = (int32_t)g;
+        gv.hash_cap = sim->hash_cap;
+        gv.tables = sim->hash.p;
+        cudaEvent_t d0 = sim->mark();
+        CU(cudaMemsetAsync(sim->hash.p, 0, (size_t)gv.n_events * sim->hash_cap * sizeof(HashEntry), sim->stream));
+        deposit_kernel<<<sim->sm_count * 8, DEPOSIT_THREADS, 0, sim->stream>>>(sim->P, pb, gv, sim->counters.p);
+        cudaEvent_t d1 = sim->mark();
+        collect_kernel<<<gv.n_events, FINALIZE_THREADS, sort_smem, sim->stream>>>(sim->P, fa, gv, sim->counters.p);
+        scan_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, sim->counters.p);
+        emit_kernel<<<gv.n_events, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, sim->counters.p);
+        cudaEvent_t f1 = sim->mark();
+        sim->launches += 4;
+        dep_marks.push_back({d0, d1});
+        fin_marks.push_back({d1, f1});
+    }
+    CU(cudaGetLastError());
+    return ATTPC_OK;
+}
+
+float sum_ms(const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& marks) {
+    float total = 0.f;
+    for (auto& m : marks) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, m.first, m.second) == cudaSuccess) total += ms;
+    }
+    return total;
+}
+
+int run_spyral(AttpcSim* sim, int64_t n_events, int64_t n_points, AttpcResult* res, bool copy_host,
+               bool keep_all = false) {
+    CU(sim->row_kept.reserve(n_events + 1));
+    CU(sim->row_offsets_dev.reserve(n_events + 1));
+    CU(sim->rows_dev.reserve(std::max<int64_t>(1, n_points) * 8));
+    CU(sim->row_labels_dev.reserve(std::max<int64_t>(1, n_points)));
+    CU(sim->row_sort_keys.reserve(std::max<int64_t>(1, n_points)));
+    CU(sim->row_sort_idx.reserve(std::max<int64_t>(1, n_points)));
+    SpyralArgs sa;
+    sa.offsets = sim->offsets_dev.p;
+    sa.cloud = sim->cloud_dev.p;
+    sa.labels = sim->labels_dev.p;
+    sa.n_events = n_events;
+    sa.kept = sim->row_kept.p;
+    sa.row_offsets = sim->row_offsets_dev.p;
+    sa.rows = sim->rows_dev.p;
+    sa.row_labels = sim->row_labels_dev.p;
+    sa.sort_keys = sim->row_sort_keys.p;
+    sa.sort_idx = sim->row_sort_idx.p;
+    sa.keep_all = keep_all ? 1 : 0;
+    const size_t smem = (size_t)SPYRAL_SMEM_ITEMS * (sizeof(uint64_t) + sizeof(uint32_t));
+    CU(cudaFuncSetAttribute(spyral_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (n_events > 0) {
+        spyral_count_kernel<<<(unsigned)n_events, 256, 0, sim->stream>>>(sim->P, sa);
+        spyral_scan_kernel<<<1, 1024, 0, sim->stream>>>(sa);
+        spyral_rows_kernel<<<(unsigned)n_events, 256, smem, sim->stream>>>(sim->P, sa);
+        sim->launches += 3;
+        CU(cudaGetLastError());
+    } else {
+        CU(cudaMemsetAsync(sim->row_offsets_dev.p, 0, sizeof(int64_t), sim->stream));
+    }
+    CU(sim->row_offsets_host.reserve(n_events + 1));
+    CU(cudaMemcpyAsync(sim->row_offsets_host.p, sim->row_offsets_dev.p, (size_t)(n_events + 1) * sizeof(int64_t),
+                       cudaMemcpyDeviceToHost, sim->stream));
+    CU(cudaStreamSynchronize(sim->stream));
+    const int64_t n_rows = sim->row_offsets_host.p[n_events];
+    res->n_rows = n_rows;
+    res->row_offsets = sim->row_offsets_host.p;
+    if (copy_host) {
+        CU(sim->rows_host.reserve(std::max<int64_t>(1, n_rows) * 8));
+        CU(sim->row_labels_host.reserve(std::max<int64_t>(1, n_rows)));
+        if (n_rows > 0) {
+            CU(cudaMemcpyAsync(sim->rows_host.p, sim->rows_dev.p, (size_t)n_rows * 8 * sizeof(double),
+                               cudaMemcpyDeviceToHost, sim->stream));
+            CU(cudaMemcpyAsync(sim->row_labels_host.p, sim->row_labels_dev.p, (size_t)n_rows * sizeof(int64_t),
+                               cudaMemcpyDeviceToHost, sim->stream));
+        }
+        CU(cudaStreamSynchronize(sim->stream));
+        res->rows = sim->rows_host.p;
+        res->row_labels = sim->row_labels_host.p;
+    }
+    return ATTPC_OK;
+}
+
+struct LaunchPlan {
+    // production
+    const double* momenta_dev = nullptr;
+    const double* vertices_dev = nullptr;
+    int32_t n_nuclei = 0;
+    const int32_t* track_nucleus = nullptr;
+    const int32_t* track_species = nullptr;
+    int32_t n_tracks_per_event = 0;
+    uint64_t seed = 0;
+    int64_t first_event = 0;
+    // replay
+    const ReplayBatch* replay = nullptr;
+    const int32_t* label_of_event_rank_dev = nullptr;
+    ReplayUniforms uniforms{nullptr, nullptr, nullptr};
+};
+
+// Shared driver of attpc_simulate / attpc_simulate_dev / attpc_simulate_replay.
+int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t flags, AttpcResult* res,
+              float ms_h2d) {
+    memset(res, 0, sizeof *res);
+    sim->events_used = 0;
+    sim->launches = 0;
+    res->n_events = n_events;
+    res->ms_h2d = ms_h2d;
+    int64_t out_cap = std::max<int64_t>(sim->labels_dev.n, std::max<int64_t>(n_events * 2048, 1 << 20));
+    int rc = ensure_out_buffers(sim, n_events, out_cap, false);
+    if (rc) return rc;
+    const int64_t launch_cap = plan.replay ? n_events : sim->launch_events;
+    rc = ensure_work_buffers(sim, std::min<int64_t>(std::max<int64_t>(n_events, 1), launch_cap));
+    if (rc) return rc;
+    CU(cudaMemsetAsync(sim->counters.p, 0, sizeof(Counters), sim->stream));
+    CU(cudaMemsetAsync(sim->offsets_dev.p, 0, sizeof(int64_t), sim->stream));
+    Counters snapshot;
+    memset(&snapshot, 0, sizeof snapshot);
+
+    cudaEvent_t t_begin = sim->mark();
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trk_marks, dep_marks, fin_marks;
+    int retries = 0;
+    for (int64_t b0 = 0; b0 < n_events;) {
+        const int64_t nb = std::min<int64_t>(launch_cap, n_events - b0);
+        rc = ensure_work_buffers(sim, nb);
+        if (rc) return rc;
+        const int64_t n_groups = (nb + sim->group_events - 1) / sim->group_events;
+        // restore the counters to the state before this launch (first attempt: no-op apart from the cursor)
+        snapshot.track_cursor = 0;
+        snapshot.overflow_points = snapshot.overflow_hash = snapshot.overflow_out = 0;
+        *sim->counters_host.p = snapshot;
+        CU(cudaMemcpyAsync(sim->counters.p, sim->counters_host.p, sizeof(Counters), cudaMemcpyHostToDevice,
+                           sim->stream));
+        CU(cudaMemsetAsync(sim->group_count.p, 0, (size_t)n_groups * sizeof(unsigned), sim->stream));
+
+        FinalizeArgs fa;
+        memset(&fa, 0, sizeof fa);
+        fa.seed = plan.seed;
+        fa.first_event = plan.first_event + b0;
+        fa.flags = flags;
+        fa.kept = sim->kept.p + b0;
+        fa.offsets = sim->offsets_dev.p + b0;
+        fa.cloud = sim->cloud_dev.p;
+        fa.labels = sim->labels_dev.p;
+        fa.out_cap = sim->labels_dev.n;
+        fa.replay = plan.uniforms;
+        if (fa.replay.offsets) fa.replay.offsets += b0;
+
+        cudaEvent_t k0 = sim->mark();
+        if (plan.replay) {
+            const ReplayBatch& rb = *plan.replay;
+            fa.n_tracks_per_event = plan.n_tracks_per_event;
+            fa.label_of_event_rank = plan.label_of_event_rank_dev;
+            if (rb.n_rows > 0) {
+                const int blocks = (int)((rb.n_rows + 255) / 256);
+                replay_kernel<<<blocks, 256, 0, sim->stream>>>(sim->P, rb, point_buf(sim), sim->counters.p);
+                sim->launches += 1;
+                CU(cudaGetLastError());
+            }
+        } else {
+            TrackBatch tb;
+            memset(&tb, 0, sizeof tb);
+            tb.momenta = plan.momenta_dev + b0 * plan.n_nuclei * 4;
+            tb.vertices = plan.vertices_dev + b0 * 3;
+            tb.n_events = nb;
+            tb.n_nuclei = plan.n_nuclei;
+            tb.n_tracks_per_event = plan.n_tracks_per_event;
+            fa.n_tracks_per_event = plan.n_tracks_per_event;
+            for (int t = 0; t < plan.n_tracks_per_event; ++t) {
+                tb.nucleus[t] = plan.track_nucleus[t];
+                tb.species[t] = plan.track_species[t];
+                fa.label_of_rank[t] = plan.track_nucleus[t];
+            }
+            tb.seed = plan.seed;
+            tb.first_event = plan.first_event + b0;
+            rc = launch_tracks<false>(sim, tb, nb * plan.n_tracks_per_event);
+            if (rc) return rc;
+        }
+        cudaEvent_t k1 = sim->mark();
+        const size_t dep_before = dep_marks.size(), fin_before = fin_marks.size();
+        rc = run_groups(sim, nb, fa, nullptr, nullptr, dep_marks, fin_marks);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(sim->counters_host.p, sim->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost,
+                           sim->stream));
+        CU(cudaStreamSynchronize(sim->stream));
+        const Counters now = *sim->counters_host.p;
+        if (now.replay_miss) return sim->fail(ATTPC_E_BADARG, "replay uniforms do not cover every (event, key)");
+        if (now.overflow_points || now.overflow_hash || now.overflow_out) {
+            dep_marks.resize(dep_before);
+            fin_marks.resize(fin_before);
+            if (++retries > 24) return sim->fail(ATTPC_E_CAPACITY, "buffers still too small after 24 retries");
+            if (now.overflow_points) {
+                sim->group_point_cap *= 2;
+                sim->px.release(); sim->py.release(); sim->pt.release();
+                sim->pq.release(); sim->pev.release(); sim->prank.release();
+            }
+            if (now.overflow_hash) {
+                if (sim->hash_cap >= (1 << 20)) return sim->fail(ATTPC_E_CAPACITY, "event needs > 2^20 hash slots");
+                sim->hash_cap *= 2;
+                sim->hash.release();
+                sim->sort_items.release();
+            }
+            if (now.overflow_out) {
+                out_cap = std::max<int64_t>(sim->labels_dev.n * 2, (int64_t)now.out_points + (1 << 20));
+                rc = ensure_out_buffers(sim, n_events, out_cap, true);
+                if (rc) return rc;
+            }
+            continue;  // redo this launch
+        }
+        trk_marks.push_back({k0, k1});
+        snapshot = now;
+        b0 += nb;
+    }
+    cudaEvent_t t_compute_end = sim->mark();
+
+    const int64_t n_points = (int64_t)snapshot.out_points;
+    res->n_points = n_points;
+    res->offsets_dev = sim->offsets_dev.p;
+    res->cloud_dev = sim->cloud_dev.p;
+    res->labels_dev = sim->labels_dev.p;
+    res->n_tracks = 0;
+    res->n_trajectory_points = (int64_t)snapshot.traj_points;
+    res->n_active_points = (int64_t)snapshot.active_points;
+    res->n_primary_electrons = (int64_t)snapshot.primary_electrons;
+    res->n_deposits = (int64_t)snapshot.deposits;
+    res->n_keys = (int64_t)snapshot.keys;
+    res->n_retries = retries;
+
+    const bool copy_host = !(flags & ATTPC_SKIP_HOST_COPY);
+    cudaEvent_t t_d2h0 = sim->mark();
+    if (copy_host) {
+        CU(sim->offsets_host.reserve(n_events + 1));
+        CU(sim->cloud_host.reserve(std::max<int64_t>(1, n_points) * 3));
+        CU(sim->labels_host.reserve(std::max<int64_t>(1, n_points)));
+        CU(cudaMemcpyAsync(sim->offsets_host.p, sim->offsets_dev.p, (size_t)(n_events + 1) * sizeof(int64_t),
+                           cudaMemcpyDeviceToHost, sim->stream));
+        if (n_points > 0) {
+            CU(cudaMemcpyAsync(sim->cloud_host.p, sim->cloud_dev.p, (size_t)n_points * 3 * sizeof(double),
+                               cudaMemcpyDeviceToHost, sim->stream));
+            CU(cudaMemcpyAsync(sim->labels_host.p, sim->labels_dev.p, (size_t)n_points * sizeof(int64_t),
+                               cudaMemcpyDeviceToHost, sim->stream));
+        }
+        res->offsets = sim->offsets_host.p;
+        res->cloud = sim->cloud_host.p;
+        res->labels = sim->labels_host.p;
+    }
+    if (flags & ATTPC_SPYRAL_ROWS) {
+        rc = run_spyral(sim, n_events, n_points, res, copy_host);
+        if (rc) return rc;
+    }
+    cudaEvent_t t_end = sim->mark();
+    CU(cudaStreamSynchronize(sim->stream));
+    res->ms_tracks = sum_ms(trk_marks);
+    res->ms_deposit = sum_ms(dep_marks);
+    res->ms_finalize = sum_ms(fin_marks);
+    cudaEventElapsedTime(&res->ms_d2h, t_d2h0, t_end);
+    float ms_compute = 0.f;
+    cudaEventElapsedTime(&ms_compute, t_begin, t_compute_end);
+    cudaEventElapsedTime(&res->ms_total, t_begin, t_end);
+    res->ms_total += ms_h2d;
+    res->n_kernel_launches = sim->launches;
+    return ATTPC_OK;
+}
+
+int check_tracks(AttpcSim* sim, int32_t n_nuclei, const int32_t* track_nucleus, const int32_t* track_species,
+                 int32_t n_tracks) {
+    if (!track_nucleus || !track_species) return sim->fail(ATTPC_E_BADARG, "null track arrays");
+    if (n_tracks <= 0 || n_tracks > MAX_TRACKS_PER_EVENT)
+        return sim->fail(ATTPC_E_BADARG, "n_tracks_per_event must be in 1..%d", MAX_TRACKS_PER_EVENT);
+    for (int t = 0; t < n_tracks; ++t) {
+        if (track_nucleus[t] < 0 || track_nucleus[t] >= n_nuclei)
+            return sim->fail(ATTPC_E_BADARG, "track_nucleus[%d]=%d outside 0..%d", t, track_nucleus[t], n_nuclei - 1);
+        if (track_species[t] >= sim->P.n_species)
+            return sim->fail(ATTPC_E_BADARG, "track_species[%d]=%d outside the %d species of this simulator", t,
+                             track_species[t], sim->P.n_species);
+    }
+    return ATTPC_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int attpc_abi_version(void) { return ATTPC_ABI_VERSION; }
+
+int attpc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return ATTPC_E_CUDA;
+    return n;
+}
+
+const char* attpc_last_error(const AttpcSim* sim) { return sim ? sim->error.c_str() : g_create_error.c_str(); }
+
+void attpc_destroy(AttpcSim* sim) {
+    if (!sim) return;
+    cudaSetDevice(sim->device);
+    if (sim->stream) cudaStreamSynchronize(sim->stream);
+    for (auto e : sim->events) cudaEventDestroy(e);
+    sim->lut.release(); sim->pad_xy.release(); sim->pad_scale.release(); sim->response.release();
+    sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release();
+    sim->px.release(); sim->py.release(); sim->pt.release(); sim->pq.release(); sim->pev.release();
+    sim->prank.release(); sim->group_count.release(); sim->hash.release(); sim->sort_items.release();
+    sim->counters.release(); sim->kept.release(); sim->in_momenta.release(); sim->in_vertices.release();
+    sim->offsets_dev.release(); sim->labels_dev.release(); sim->row_offsets_dev.release();
+    sim->row_labels_dev.release(); sim->cloud_dev.release(); sim->rows_dev.release(); sim->row_kept.release();
+    sim->row_sort_keys.release(); sim->row_sort_idx.release();
+    sim->offsets_host.release(); sim->labels_host.release(); sim->row_offsets_host.release();
+    sim->row_labels_host.release(); sim->cloud_host.release(); sim->rows_host.release();
+    sim->counters_host.release();
+    if (sim->stream) cudaStreamDestroy(sim->stream);
+    delete sim;
+}
+
+int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* pad_xy, const double* pad_scale,
+                 int32_t n_pads, const double* response, int32_t n_response, const AttpcSpecies* species,
+                 int32_t n_species, int32_t device, AttpcSim** out) {
+    if (!cfg || !pad_lut || !pad_xy || !pad_scale || !response || (!species && n_species > 0) || !out) {
+        g_create_error = "attpc_create: null argument";
+        return ATTPC_E_BADARG;
+    }
+    if (n_species < 0 || n_species > MAX_SPECIES || n_pads < 1 || n_response < 1 || cfg->lut_n < 1) {
+        g_create_error = "attpc_create: n_species must be 0..8, n_pads/n_response/lut_n positive";
+        return ATTPC_E_BADARG;
+    }
+    for (int s = 1; s < n_species; ++s)
+        if (species[s].lm != species[0].lm || species[s].e_min != species[0].e_min ||
+            species[s].n_oct != species[0].n_oct) {
+            g_create_error = "attpc_create: all species tables must share one grid (lm, e_min, n_oct)";
+            return ATTPC_E_BADARG;
+        }
+    if (cfg->windows_edge == cfg->micromegas_edge || !(cfg->drift_velocity > 0.0) || !(cfg->w_value > 0.0)) {
+        g_create_error = "attpc_create: windows_edge == micromegas_edge, drift_velocity <= 0 or w_value <= 0";
+        return ATTPC_E_BADARG;
+    }
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        return ATTPC_E_CUDA;
+    }
+    AttpcSim* sim = new AttpcSim();
+    sim->device = device;
+    sim->cfg = *cfg;
+    auto bail = [&](int code) {
+        g_create_error = sim->error;
+        attpc_destroy(sim);
+        return code;
+    };
+#define CUC(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            sim->fail(ATTPC_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e));                \
+            return bail(ATTPC_E_CUDA);                                                              \
+        }                                                                                           \
+    } while (0)
+    CUC(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
+    int sm = 0;
+    CUC(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    sim->sm_count = sm > 0 ? sm : 148;
+
+    SimParams& P = sim->P;
+    P.length = cfg->length;
+    P.dv = cfg->drift_velocity;
+    P.mm_edge = (double)cfg->micromegas_edge;
+    P.win_edge = (double)cfg->windows_edge;
+    P.diffusion = cfg->diffusion;
+    P.efield = cfg->efield;
+    P.fano = cfg->fano_factor;
+    P.ev_per_w = 1.0e6 / cfg->w_value;
+    P.B = cfg->bfield * -1.0;
+    P.E = cfg->efield * -1.0;
+    P.gain = cfg->mpgd_gain;
+    P.grid_low = cfg->grid_low_mm;
+    P.grid_high = cfg->grid_high_mm;
+    P.lut_origin = cfg->lut_origin_mm;
+    P.lut_n = cfg->lut_n;
+    P.adc_threshold = cfg->adc_threshold;
+    P.rtol = cfg->ode_rtol > 0 ? cfg->ode_rtol : 1e-8;
+    P.atol = cfg->ode_atol > 0 ? cfg->ode_atol : 1e-12;
+    P.freeze_ke = cfg->freeze_ke_mev;
+    P.lm = n_species ? species[0].lm : 0;
+    P.e_min = n_species ? species[0].e_min : 0;
+    P.n_oct = n_species ? species[0].n_oct : 0;
+    P.n_nodes = P.n_oct * (1 << P.lm) + 1;
+    P.n_species = n_species;
+    P.n_pads = n_pads;
+    P.n_response = n_response;
+    if (cfg->max_events_per_launch > 0) sim->launch_events = cfg->max_events_per_launch;
+    if (cfg->hash_capacity > 0) sim->hash_cap = next_pow2(cfg->hash_capacity);
+    sim->group_events = std::min(sim->group_events, sim->launch_events);
+
+    const int64_t lut_cells = (int64_t)cfg->lut_n * cfg->lut_n;
+    CUC(sim->lut.reserve(lut_cells));
+    CUC(cudaMemcpy(sim->lut.p, pad_lut, (size_t)lut_cells * sizeof(int16_t), cudaMemcpyHostToDevice));
+    CUC(sim->pad_xy.reserve((int64_t)n_pads * 2));
+    CUC(cudaMemcpy(sim->pad_xy.p, pad_xy, (size_t)n_pads * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    CUC(sim->pad_scale.reserve(n_pads));
+    CUC(cudaMemcpy(sim->pad_scale.p, pad_scale, (size_t)n_pads * sizeof(double), cudaMemcpyHostToDevice));
+    CUC(sim->response.reserve(n_response));
+    CUC(cudaMemcpy(sim->response.p, response, (size_t)n_response * sizeof(double), cudaMemcpyHostToDevice));
+    {
+        std::vector<double> sorted(response, response + n_response);
+        std::sort(sorted.begin(), sorted.end(), [](double a, double b) { return a > b; });
+        std::vector<double> prefix(n_response + 1, 0.0);
+        for (int i = 0; i < n_response; ++i) prefix[i + 1] = prefix[i] + sorted[i];
+        CUC(sim->resp_sorted.reserve(n_response));
+        CUC(cudaMemcpy(sim->resp_sorted.p, sorted.data(), (size_t)n_response * sizeof(double), cudaMemcpyHostToDevice));
+        CUC(sim->resp_prefix.reserve(n_response + 1));
+        CUC(cudaMemcpy(sim->resp_prefix.p, prefix.data(), (size_t)(n_response + 1) * sizeof(double),
+                       cudaMemcpyHostToDevice));
+        P.resp_max = sorted[0];
+    }
+    {
+        // deceleration tables: dE/dx [MeV/(g/cm^2)] * MEV_2_JOULE * density * 100 / m_kg / c  (detector/solver.py:64-76)
+        std::vector<double> scaled((size_t)n_species * P.n_nodes);
+        for (int s = 0; s < n_species; ++s) {
+            if (!species[s].dedx || !(species[s].mass > 0.0)) {
+                sim->fail(ATTPC_E_BADARG, "species %d: null table or non-positive mass", s);
+                return bail(ATTPC_E_BADARG);
+            }
+            const double mass_kg = species[s].mass * MEV_2_KG;
+            const double scale = MEV_2_JOULE * cfg->gas_density * 100.0 / mass_kg / C_LIGHT;
+            for (int i = 0; i < P.n_nodes; ++i) scaled[(size_t)s * P.n_nodes + i] = species[s].dedx[i] * scale;
+            P.sp[s].mass = species[s].mass;
+            P.sp[s].qm_c = (double)species[s].z * E_CHARGE / mass_kg / C_LIGHT;
+            P.sp[s].z = species[s].z;
+            P.sp[s].table = s * P.n_nodes;
+        }
+        CUC(sim->tables.reserve(std::max<int64_t>(1, (int64_t)scaled.size())));
+        if (!scaled.empty())
+            CUC(cudaMemcpy(sim->tables.p, scaled.data(), scaled.size() * sizeof(double), cudaMemcpyHostToDevice));
+        sim->table_smem_bytes = scaled.size() * sizeof(double);
+        sim->tables_in_smem = sim->table_smem_bytes <= 160 * 1024;
+    }
+    P.lut = sim->lut.p;
+    P.tables = sim->tables.p;
+    P.pad_xy = sim->pad_xy.p;
+    P.pad_scale = sim->pad_scale.p;
+    P.response = sim->response.p;
+    P.resp_sorted = sim->resp_sorted.p;
+    P.resp_prefix = sim->resp_prefix.p;
+#undef CUC
+    *out = sim;
+    return ATTPC_OK;
+}
+
+int attpc_simulate_dev(AttpcSim* sim, const double* momenta_dev, const double* vertices_dev, int64_t n_events,
+                       int32_t n_nuclei, const int32_t* track_nucleus, const int32_t* track_species,
+                       int32_t n_tracks_per_event, uint64_t seed, int64_t first_event, uint32_t flags,
+                       AttpcResult* result) {
+    if (!sim) return ATTPC_E_BADARG;
+    if (!result || n_events < 0 || n_nuclei <= 0 || (n_events > 0 && (!momenta_dev || !vertices_dev)))
+        return sim->fail(ATTPC_E_BADARG, "attpc_simulate: bad arguments");
+    int rc = check_tracks(sim, n_nuclei, track_nucleus, track_species, n_tracks_per_event);
+    if (rc) return rc;
+    CU(cudaSetDevice(sim->device));
+    LaunchPlan plan;
+    plan.momenta_dev = momenta_dev;
+    plan.vertices_dev = vertices_dev;
+    plan.n_nuclei = n_nuclei;
+    plan.track_nucleus = track_nucleus;
+    plan.track_species = track_species;
+    plan.n_tracks_per_event = n_tracks_per_event;
+    plan.seed = seed;
+    plan.first_event = first_event;
+    rc = run_batch(sim, plan, n_events, flags, result, 0.f);
+    if (rc == ATTPC_OK) {
+        int charged = 0;
+        for (int t = 0; t < n_tracks_per_event; ++t) charged += track_species[t] >= 0;
+        result->n_tracks = n_events * charged;
+    }
+    return rc;
+}
+
+int attpc_simulate(AttpcSim* sim, const double* momenta, const double* vertices, int64_t n_events, int32_t n_nuclei,
+                   const int32_t* track_nucleus, const int32_t* track_species, int32_t n_tracks_per_event,
+                   uint64_t seed, int64_t first_event, uint32_t flags, AttpcResult* result) {
+    if (!sim) return ATTPC_E_BADARG;
+    if (!result || n_events < 0 || n_nuclei <= 0 || (n_events > 0 && (!momenta || !vertices)))
+        return sim->fail(ATTPC_E_BADARG, "attpc_simulate: bad arguments");
+    CU(cudaSetDevice(sim->device));
+    CU(sim->in_momenta.reserve(std::max<int64_t>(1, n_events * n_nuclei * 4)));
+    CU(sim->in_vertices.reserve(std::max<int64_t>(1, n_events * 3)));
+    sim->events_used = 0;
+    cudaEvent_t h0 = sim->mark();
+    if (n_events > 0) {
+        CU(cudaMemcpyAsync(sim->in_momenta.p, momenta, (size_t)n_events * n_nuclei * 4 * sizeof(double),
+                           cudaMemcpyHostToDevice, sim->stream));
+        CU(cudaMemcpyAsync(sim->in_vertices.p, vertices, (size_t)n_events * 3 * sizeof(double),
+                           cudaMemcpyHostToDevice, sim->stream));
+    }
+    cudaEvent_t h1 = sim->mark();
+    CU(cudaStreamSynchronize(sim->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h0, h1);
+    int rc = attpc_simulate_dev(sim, sim->in_momenta.p, sim->in_vertices.p, n_events, n_nuclei, track_nucleus,
+                                track_species, n_tracks_per_event, seed, first_event, flags, result);
+    if (rc == ATTPC_OK) {
+        result->ms_h2d = ms;
+        result->ms_total += ms;
+    }
+    return rc;
+}
+
+int attpc_simulate_replay(AttpcSim* sim, const int64_t* track_offsets, const double* points, const double* normals,
+                          const int32_t* track_event, const int32_t* track_rank, const int32_t* track_label,
+                          const int32_t* track_species, int64_t n_tracks, int64_t n_events,
+                          const AttpcReplay* replay, uint32_t flags, int64_t* electrons_out, AttpcResult* result) {
+    if (!sim) return ATTPC_E_BADARG;
+    if (!result || n_tracks < 0 || n_events < 0 || !track_offsets ||
+        (n_tracks > 0 && (!points || !normals || !track_event || !track_rank || !track_label || !track_species)))
+        return sim->fail(ATTPC_E_BADARG, "attpc_simulate_replay: bad arguments");
+    CU(cudaSetDevice(sim->device));
+    const int64_t n_rows = track_offsets[n_tracks];
+    int32_t t_max = 1;
+    for (int64_t t = 0; t < n_tracks; ++t) {
+        if (track_event[t] < 0 || track_event[t] >= n_events)
+            return sim->fail(ATTPC_E_BADARG, "track_event[%lld] outside 0..n_events-1", (long long)t);
+        if (track_rank[t] < 0 || track_rank[t] >= MAX_TRACKS_PER_EVENT)
+            return sim->fail(ATTPC_E_BADARG, "track_rank[%lld] outside 0..%d", (long long)t, MAX_TRACKS_PER_EVENT - 1);
+        if (track_species[t] >= sim->P.n_species)
+            return sim->fail(ATTPC_E_BADARG, "track_species[%lld] outside the species of this simulator", (long long)t);
+        if (track_offsets[t + 1] < track_offsets[t]) return sim->fail(ATTPC_E_BADARG, "track_offsets not monotone");
+        t_max = std::max(t_max, track_rank[t] + 1);
+    }
+    std::vector<int32_t> label_map((size_t)std::max<int64_t>(1, n_events) * t_max, -1);
+    for (int64_t t = 0; t < n_tracks; ++t) label_map[(size_t)track_event[t] * t_max + track_rank[t]] = track_label[t];
+
+    DevArray<int64_t> d_off, d_ukeys, d_uoff;
+    DevArray<double> d_rows, d_norm, d_uvals;
+    DevArray<int32_t> d_ev, d_rank, d_sp, d_lab;
+    DevArray<long long> d_el;
+    auto cleanup = [&]() {
+        d_off.release(); d_ukeys.release(); d_uoff.release(); d_rows.release(); d_norm.release();
+        d_uvals.release(); d_ev.release(); d_rank.release(); d_sp.release(); d_lab.release(); d_el.release();
+    };
+#define CUR(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            cleanup();                                                                                 \
+            return sim->fail(ATTPC_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e));            \
+        }                                                                                              \
+    } while (0)
+    auto up = [&](auto& arr, const auto* src, int64_t n) -> cudaError_t {
+        cudaError_t e = arr.reserve(std::max<int64_t>(1, n));
+        if (e != cudaSuccess || n == 0) return e;
+        return cudaMemcpyAsync(arr.p, src, (size_t)n * sizeof(*src), cudaMemcpyHostToDevice, sim->stream);
+    };
+    CUR(up(d_off, track_offsets, n_tracks + 1));
+    CUR(up(d_rows, points, n_rows * 6));
+    CUR(up(d_norm, normals, n_rows));
+    CUR(up(d_ev, track_event, n_tracks));
+    CUR(up(d_rank, track_rank, n_tracks));
+    CUR(up(d_sp, track_species, n_tracks));
+    CUR(up(d_lab, label_map.data(), (int64_t)label_map.size()));
+    if (electrons_out) CUR(d_el.reserve(std::max<int64_t>(1, n_rows)));
+    LaunchPlan plan;
+    if (replay && replay->u_offsets) {
+        const int64_t nu = replay->u_offsets[n_events];
+        CUR(up(d_uoff, replay->u_offsets, n_events + 1));
+        CUR(up(d_ukeys, replay->u_keys, nu));
+        CUR(up(d_uvals, replay->u_vals, nu));
+        plan.uniforms = ReplayUniforms{d_uoff.p, d_ukeys.p, d_uvals.p};
+    }
+    ReplayBatch rb;
+    rb.track_offsets = d_off.p;
+    rb.rows = d_rows.p;
+    rb.normals = d_norm.p;
+    rb.track_event = d_ev.p;
+    rb.track_rank = d_rank.p;
+    rb.track_species = d_sp.p;
+    rb.n_tracks = n_tracks;
+    rb.n_rows = n_rows;
+    rb.electrons_out = electrons_out ? d_el.p : nullptr;
+    plan.replay = &rb;
+    plan.label_of_event_rank_dev = d_lab.p;
+    plan.n_tracks_per_event = t_max;
+    int rc = run_batch(sim, plan, n_events, flags, result, 0.f);
+    if (rc == ATTPC_OK && electrons_out && n_rows > 0) {
+        cudaError_t e = cudaMemcpy(electrons_out, d_el.p, (size_t)n_rows * sizeof(long long), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = sim->fail(ATTPC_E_CUDA, "electrons copy failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == ATTPC_OK) result->n_tracks = n_tracks;
+    cudaStreamSynchronize(sim->stream);
+    cleanup();
+#undef CUR
+    return rc;
+}
+
+int attpc_trajectories(AttpcSim* sim, const double* momenta, const double* vertices, const int32_t* species,
+                       int64_t n_tracks, int32_t stride, int32_t max_points, double* out_points, int32_t* out_counts) {
+    if (!sim) return ATTPC_E_BADARG;
+    if (n_tracks < 0 || stride < 1 || max_points < 1 || !out_points || !out_counts ||
+        (n_tracks > 0 && (!momenta || !vertices || !species)))
+        return sim->fail(ATTPC_E_BADARG, "attpc_trajectories: bad arguments");
+    if (n_tracks == 0) return ATTPC_OK;
+    for (int64_t t = 0; t < n_tracks; ++t)
+        if (species[t] >= sim->P.n_species) return sim->fail(ATTPC_E_BADARG, "species[%lld] out of range", (long long)t);
+    CU(cudaSetDevice(sim->device));
+    int rc = ensure_work_buffers(sim, 1);
+    if (rc) return rc;
+    DevArray<double> d_m, d_v, d_out;
+    DevArray<int32_t> d_sp, d_cnt;
+    auto cleanup = [&]() { d_m.release(); d_v.release(); d_out.release(); d_sp.release(); d_cnt.release(); };
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; return e == cudaSuccess; };
+    ok(d_m.reserve(n_tracks * 4)) && ok(d_v.reserve(n_tracks * 3)) && ok(d_sp.reserve(n_tracks)) &&
+        ok(d_cnt.reserve(n_tracks)) && ok(d_out.reserve(n_tracks * max_points * 6)) &&
+        ok(cudaMemcpyAsync(d_m.p, momenta, (size_t)n_tracks * 4 * sizeof(double), cudaMemcpyHostToDevice, sim->stream)) &&
+        ok(cudaMemcpyAsync(d_v.p, vertices, (size_t)n_tracks * 3 * sizeof(double), cudaMemcpyHostToDevice, sim->stream)) &&
+        ok(cudaMemcpyAsync(d_sp.p, species, (size_t)n_tracks * sizeof(int32_t), cudaMemcpyHostToDevice, sim->stream)) &&
+        ok(cudaMemsetAsync(d_out.p, 0, (size_t)n_tracks * max_points * 6 * sizeof(double), sim->stream)) &&
+        ok(cudaMemsetAsync(d_cnt.p, 0, (size_t)n_tracks * sizeof(int32_t), sim->stream)) &&
+        ok(cudaMemsetAsync(sim->counters.p, 0, sizeof(Counters), sim->stream));
+    if (e != cudaSuccess) {
+        cleanup();
+        return sim->fail(ATTPC_E_CUDA, "attpc_trajectories setup: %s", cudaGetErrorString(e));
+    }
+    TrackBatch tb;
+    memset(&tb, 0, sizeof tb);
+    tb.momenta = d_m.p;
+    tb.vertices = d_v.p;
+    tb.n_events = n_tracks;
+    tb.n_nuclei = 1;
+    tb.n_tracks_per_event = 1;
+    tb.rec_species = d_sp.p;
+    tb.rec_points = d_out.p;
+    tb.rec_counts = d_cnt.p;
+    tb.rec_stride = stride;
+    tb.rec_max = max_points;
+    rc = launch_tracks<true>(sim, tb, n_tracks);
+    if (rc == ATTPC_OK) {
+        ok(cudaMemcpyAsync(out_points, d_out.p, (size_t)n_tracks * max_points * 6 * sizeof(double),
+                           cudaMemcpyDeviceToHost, sim->stream)) &&
+            ok(cudaMemcpyAsync(out_counts, d_cnt.p, (size_t)n_tracks * sizeof(int32_t), cudaMemcpyDeviceToHost,
+                               sim->stream)) &&
+            ok(cudaStreamSynchronize(sim->stream));
+        if (e != cudaSuccess) rc = sim->fail(ATTPC_E_CUDA, "attpc_trajectories: %s", cudaGetErrorString(e));
+    }
+    cleanup();
+    return rc;
+}
+
+int attpc_convert_to_spyral(AttpcSim* sim, const int64_t* offsets, const double* cloud, const int64_t* labels,
+                            int64_t n_events, uint32_t flags, AttpcResult* result) {
+    if (!sim) return ATTPC_E_BADARG;
+    if (!result || n_events < 0 || !offsets) return sim->fail(ATTPC_E_BADARG, "attpc_convert_to_spyral: bad arguments");
+    const int64_t n_points = offsets[n_events];
+    if (n_points < 0 || (n_points > 0 && (!cloud || !labels)))
+        return sim->fail(ATTPC_E_BADARG, "attpc_convert_to_spyral: bad cloud");
+    CU(cudaSetDevice(sim->device));
+    memset(result, 0, sizeof *result);
+    sim->events_used = 0;
+    sim->launches = 0;
+    int rc = ensure_out_buffers(sim, n_events, std::max<int64_t>(1, n_points), false);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(sim->offsets_dev.p, offsets, (size_t)(n_events + 1) * sizeof(int64_t), cudaMemcpyHostToDevice,
+                       sim->stream));
+    if (n_points > 0) {
+        CU(cudaMemcpyAsync(sim->cloud_dev.p, cloud, (size_t)n_points * 3 * sizeof(double), cudaMemcpyHostToDevice,
+                           sim->stream));
+        CU(cudaMemcpyAsync(sim->labels_dev.p, labels, (size_t)n_points * sizeof(int64_t), cudaMemcpyHostToDevice,
+                           sim->stream));
+    }
+    result->n_events = n_events;
+    result->n_points = n_points;
+    rc = run_spyral(sim, n_events, n_points, result, true, (flags & ATTPC_ROWS_KEEP_ALL) != 0);
+    result->n_kernel_launches = sim->launches;
+    return rc;
+}
+
+int attpc_lookup_pads(AttpcSim* sim, const double* xy, int64_t n, int32_t* pads_out) {
+    if (!sim) return ATTPC_E_BADARG;
+    if (n < 0 || (n > 0 && (!xy || !pads_out))) return sim->fail(ATTPC_E_BADARG, "attpc_lookup_pads: bad arguments");
+    if (n == 0) return ATTPC_OK;
+    CU(cudaSetDevice(sim->device));
+    DevArray<double> d_xy;
+    DevArray<int32_t> d_out;
+    cudaError_t e = d_xy.reserve(n * 2);
+    if (e == cudaSuccess) e = d_out.reserve(n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_xy.p, xy, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, sim->stream);
+    if (e == cudaSuccess) {
+        lookup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sim->stream>>>(sim->P, d_xy.p, n, d_out.p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pads_out, d_out.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, sim->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(sim->stream);
+    d_xy.release();
+    d_out.release();
+    if (e != cudaSuccess) return sim->fail(ATTPC_E_CUDA, "attpc_lookup_pads: %s", cudaGetErrorString(e));
+    return ATTPC_OK;
+}
+
+}  // extern "C"

@@ -796,6 +796,7 @@ struct SpyralArgs {
     int64_t* row_labels;
     uint64_t* sort_keys;      // [n] scratch (order-preserving bits of z)
     uint32_t* sort_idx;       // [n] scratch
+    int32_t keep_all;         // 1: every row, input order (plain convert_to_spyral, detector/writer.py:61-112)
 };
 
 // detector/response.py:35-57: amplitude = max(min(r_i e, 4095)), integral = sum(min(r_i e, 4095)).
@@ -826,7 +827,7 @@ __global__ void __launch_bounds__(256) spyral_count_kernel(const __grid_constant
     unsigned mine = 0;
     for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
         const double amp = fmin(__dmul_rn(P.resp_max, sa.cloud[i * 3 + 2]), 4095.0);
-        if (amp > P.adc_threshold) mine += 1;
+        if (sa.keep_all || amp > P.adc_threshold) mine += 1;
     }
     atomicAdd(&s_n, mine);
     __syncthreads();
@@ -894,11 +895,11 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
     const int64_t out0 = sa.row_offsets[e];
     const int n = (int)sa.kept[e];
     if (n == 0) return;
-    const bool in_smem = n <= SPYRAL_SMEM_ITEMS;
+    const bool in_smem = n <= SPYRAL_SMEM_ITEMS && !sa.keep_all;
     uint64_t* keys = in_smem ? s_k : sa.sort_keys + a;
     uint32_t* idx = in_smem ? s_v : sa.sort_idx + a;
     const double span = (double)(P.win_edge - P.mm_edge);
-    for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
+    for (int64_t i = a + threadIdx.x; i < b && !sa.keep_all; i += blockDim.x) {
         const double amp = fmin(__dmul_rn(P.resp_max, sa.cloud[i * 3 + 2]), 4095.0);
         if (amp > P.adc_threshold) {
             const unsigned pos = atomicAdd(&s_n, 1u);
@@ -922,8 +923,8 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
     }
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         int rank = i;
-        const uint32_t id = idx[i];
-        if (!in_smem) {  // very dense events: rank by counting against the L2-resident scratch
+        const uint32_t id = sa.keep_all ? (uint32_t)i : idx[i];
+        if (!in_smem && !sa.keep_all) {  // very dense events: rank by counting against the L2-resident scratch
             const uint64_t k = keys[i];
             rank = 0;
             for (int j = 0; j < n; ++j) {

@@ -1,0 +1,20 @@
+"""Detector effects (mirror of `attpc_engine.detector`, reference `detector/__init__.py:3-21`)."""
+
+from .parameters import Config, DetectorParams, ElectronicsParams, PadParams
+from .simulator import SimEvent, run_simulation, simulate, simulate_batch
+from .writer import ArrayWriter, SimulationWriter, SpyralWriter, convert_to_spyral
+
+__all__ = [
+    "run_simulation",
+    "simulate",
+    "simulate_batch",
+    "SimEvent",
+    "DetectorParams",
+    "ElectronicsParams",
+    "PadParams",
+    "Config",
+    "SpyralWriter",
+    "ArrayWriter",
+    "SimulationWriter",
+    "convert_to_spyral",
+]

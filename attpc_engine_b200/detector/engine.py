@@ -1,0 +1,433 @@
+"""Host driver of the CUDA detector path: bakes ``Config`` into device constants and calls the C ABI.
+
+What is baked (once per ``Config`` x species set x device):
+
+* the pad lookup table -- the 1 mm sub-lattice of ``Config.pad_grid`` that
+  `detector/transporter.py:102-120` (``position_to_index``) can address, with holes and the
+  beam pads of `detector/beam_pads.py` folded to -1 (`transporter.py:165,237`);
+* pad centres / sizes (`parameters.py:207-261`), the GET response (`response.py:8-32`);
+* one stopping-power table per ion species (``target.DedxTable``), sampled from the user's
+  ``gas_target.get_dedx`` (`solver.py:64-66`).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .. import _lib
+from ..target import TableGasTarget, ensure_table_target
+from .beam_pads import BEAM_PADS_ARRAY
+from .constants import NUM_TB
+from .parameters import Config
+from .response import get_response
+
+
+def build_pad_lut(pad_grid: np.ndarray, edges: np.ndarray) -> tuple[np.ndarray, int]:
+    """Fold `position_to_index` + grid read + beam veto into one int16 table on whole millimetres.
+
+    Returns ``(lut, origin_mm)`` with ``lut[fx - origin, fy - origin]`` = pad id or -1 for every
+    integer ``fx = floor(x_mm)`` accepted by `transporter.py:109-115` (``low <= fx < high``).
+    The grid index uses the reference's own expression ``int((fx - low) / bin)``.
+    """
+    low, high, step = (float(v) for v in edges[:3])
+    first = math.ceil(low)
+    last_excl = math.ceil(high)  # integers f with f < high
+    fs = np.arange(first, last_excl, dtype=np.float64)
+    idx = ((fs - low) / step).astype(np.int64)
+    ok = (idx >= 0) & (idx < pad_grid.shape[0])
+    safe = np.where(ok, idx, 0)
+    lut = pad_grid[np.ix_(safe, safe)].astype(np.int16)
+    lut[~ok, :] = -1
+    lut[:, ~ok] = -1
+    lut[np.isin(lut, BEAM_PADS_ARRAY)] = -1
+    return np.ascontiguousarray(lut), int(first)
+
+
+def default_freeze_ke(fano_factor: float, w_value: float, z_abs_max: float = 8.66) -> float:
+    """KE [MeV] below which a track can no longer make an electron.
+
+    A grid step produces ``int(n + sqrt(F n) z)`` electrons with ``n = dKE / W``
+    (`solver.py:338-346`) and the device's Box-Muller normal is bounded by ``z_abs_max``.
+    Even if the whole remaining KE went into one step, ``n + sqrt(F n) z_max < 1`` holds for
+    ``n < n*``; the integrator stops once KE < n* W.  The reference instead integrates the
+    stalled ion to 1 us and discards those rows at `solver.py:387`.
+    """
+    a = math.sqrt(max(fano_factor, 0.0)) * z_abs_max
+    root = (-a + math.sqrt(a * a + 4.0)) / 2.0  # sqrt(n*) solves n + a sqrt(n) = 1
+    return 0.999 * root * root * w_value * 1.0e-6
+
+
+@dataclass
+class SimBatch:
+    """CSR point clouds of a batch: event ``e`` owns rows ``offsets[e]:offsets[e+1]``."""
+
+    first_event: int
+    offsets: np.ndarray
+    cloud: np.ndarray  # [N, 3] pad, time bucket, electrons
+    labels: np.ndarray  # [N]
+    row_offsets: np.ndarray | None = None
+    rows: np.ndarray | None = None  # [M, 8] Spyral rows
+    row_labels: np.ndarray | None = None
+    stats: dict = field(default_factory=dict)
+
+    def __len__(self) -> int:
+        return len(self.offsets) - 1
+
+    def event(self, e: int) -> tuple[np.ndarray, np.ndarray]:
+        a, b = self.offsets[e], self.offsets[e + 1]
+        return self.cloud[a:b], self.labels[a:b]
+
+    def event_rows(self, e: int) -> tuple[np.ndarray, np.ndarray]:
+        a, b = self.row_offsets[e], self.row_offsets[e + 1]
+        return self.rows[a:b], self.row_labels[a:b]
+
+
+def _ptr(arr: np.ndarray, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+_STAT_FIELDS = (
+    "n_tracks", "n_trajectory_points", "n_active_points", "n_primary_electrons", "n_deposits", "n_keys",
+    "ms_h2d", "ms_tracks", "ms_deposit", "ms_finalize", "ms_d2h", "ms_total", "n_kernel_launches", "n_retries",
+)  # fmt: skip
+
+
+class Engine:
+    """One CUDA simulator handle (one GPU, one species set)."""
+
+    def __init__(
+        self,
+        config: Config,
+        species: list,
+        device: int = 0,
+        ode_rtol: float = 1e-8,
+        ode_atol: float = 1e-12,
+        freeze_ke_mev: float | None = None,
+        max_events_per_launch: int = 0,
+        hash_capacity: int = 0,
+    ):
+        if config.pad_grid is None or config.pad_grid_edges is None:
+            raise ValueError("Pad grid is not loaded")  # solver.py:400-401
+        if config.pad_centers is None or config.pad_sizes is None:
+            raise ValueError("Pad centers are not assigned")  # writer.py:220-221
+        self.lib = _lib.load()
+        self.config = config
+        self.device = int(device)
+        self.species = list(species)
+        self.species_index = {(int(n.Z), int(n.A)): i for i, n in enumerate(self.species)}
+        det, elec = config.det_params, config.elec_params
+        target: TableGasTarget = ensure_table_target(det.gas_target)
+        self.target = target
+        tables = [target.table_for(n) for n in self.species]
+
+        lut, origin = build_pad_lut(config.pad_grid, config.pad_grid_edges)
+        self._lut = lut
+        self._pad_xy = np.ascontiguousarray(config.pad_centers, dtype=np.float64)
+        self._pad_scale = np.ascontiguousarray(config.pad_sizes, dtype=np.float64)
+        self._response = np.ascontiguousarray(get_response(config), dtype=np.float64)
+        self._tables = [np.ascontiguousarray(t.values, dtype=np.float64) for t in tables]
+
+        cfg = _lib.AttpcConfig()
+        cfg.length = float(det.length)
+        cfg.efield = float(det.efield)
+        cfg.bfield = float(det.bfield)
+        cfg.mpgd_gain = int(det.mpgd_gain)
+        cfg.diffusion = float(det.diffusion)
+        cfg.fano_factor = float(det.fano_factor)
+        cfg.w_value = float(det.w_value)
+        cfg.gas_density = float(target.density)
+        cfg.micromegas_edge = int(elec.micromegas_edge)
+        cfg.windows_edge = int(elec.windows_edge)
+        cfg.adc_threshold = float(elec.adc_threshold)
+        cfg.drift_velocity = float(config.drift_velocity)
+        cfg.grid_low_mm = float(config.pad_grid_edges[0])
+        cfg.grid_high_mm = float(config.pad_grid_edges[1])
+        cfg.lut_origin_mm = origin
+        cfg.lut_n = lut.shape[0]
+        cfg.ode_rtol = float(ode_rtol)
+        cfg.ode_atol = float(ode_atol)
+        if freeze_ke_mev is None:
+            freeze_ke_mev = default_freeze_ke(det.fano_factor, det.w_value)
+        self.freeze_ke_mev = float(freeze_ke_mev)
+        cfg.freeze_ke_mev = self.freeze_ke_mev
+        cfg.max_events_per_launch = int(max_events_per_launch)
+        cfg.hash_capacity = int(hash_capacity)
+
+        sp = (_lib.AttpcSpecies * len(self.species))()
+        for i, (nuc, tab) in enumerate(zip(self.species, tables)):
+            sp[i].z = int(nuc.Z)
+            sp[i].a = int(nuc.A)
+            sp[i].mass = float(nuc.mass)
+            sp[i].lm, sp[i].e_min, sp[i].n_oct = tab.lm, tab.e_min, tab.n_oct
+            sp[i].dedx = _ptr(self._tables[i], C.c_double)
+        handle = C.c_void_p()
+        code = self.lib.attpc_create(
+            C.byref(cfg), _ptr(lut, C.c_int16), _ptr(self._pad_xy, C.c_double), _ptr(self._pad_scale, C.c_double),
+            len(self._pad_scale), _ptr(self._response, C.c_double), len(self._response), sp, len(self.species),
+            self.device, C.byref(handle),
+        )  # fmt: skip
+        _lib.check(code, None)
+        self.handle = handle
+
+    @classmethod
+    def for_conversion(cls, window_edge, mm_edge, length, response, pad_centers, pad_sizes, threshold, device=0):
+        """Handle without species or pad map: only `convert_to_spyral` works on it (`writer.py:61-112`)."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.config = None
+        self.device = int(device)
+        self.species, self.species_index = [], {}
+        self._lut = np.full((1, 1), -1, dtype=np.int16)
+        self._pad_xy = np.ascontiguousarray(pad_centers, dtype=np.float64)
+        self._pad_scale = np.ascontiguousarray(pad_sizes, dtype=np.float64)
+        self._response = np.ascontiguousarray(response, dtype=np.float64)
+        cfg = _lib.AttpcConfig()
+        cfg.length = float(length)
+        cfg.efield, cfg.bfield, cfg.mpgd_gain = 1.0, 0.0, 1
+        cfg.diffusion, cfg.fano_factor, cfg.w_value, cfg.gas_density = 0.0, 0.0, 1.0, 0.0
+        cfg.micromegas_edge, cfg.windows_edge = int(mm_edge), int(window_edge)
+        cfg.adc_threshold = float(threshold)
+        cfg.drift_velocity = float(length) / float(int(window_edge) - int(mm_edge))
+        cfg.grid_low_mm, cfg.grid_high_mm, cfg.lut_origin_mm, cfg.lut_n = 0.0, 1.0, 0, 1
+        handle = C.c_void_p()
+        code = self.lib.attpc_create(
+            C.byref(cfg), _ptr(self._lut, C.c_int16), _ptr(self._pad_xy, C.c_double),
+            _ptr(self._pad_scale, C.c_double), len(self._pad_scale), _ptr(self._response, C.c_double),
+            len(self._response), None, 0, self.device, C.byref(handle),
+        )  # fmt: skip
+        _lib.check(code, None)
+        self.handle = handle
+        return self
+
+    # ------------------------------------------------------------------------------ lifecycle
+    def close(self) -> None:
+        if getattr(self, "handle", None):
+            self.lib.attpc_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -------------------------------------------------------------------------------- helpers
+    def _species_of(self, proton_numbers, mass_numbers, indices) -> tuple[np.ndarray, np.ndarray]:
+        nucleus = np.asarray(indices, dtype=np.int32)
+        spec = np.empty(len(nucleus), dtype=np.int32)
+        for t, idx in enumerate(nucleus):
+            z, a = int(proton_numbers[idx]), int(mass_numbers[idx])
+            if z == 0:
+                spec[t] = -1  # simulator.py:97
+            else:
+                spec[t] = self.species_index[(z, a)]
+        return np.ascontiguousarray(nucleus), spec
+
+    def _collect(self, res: _lib.AttpcResult, first_event: int, copy: bool, rows: bool) -> SimBatch:
+        n_ev, n_pts = int(res.n_events), int(res.n_points)
+        stats = {k: getattr(res, k) for k in _STAT_FIELDS}
+        if not res.offsets:  # SKIP_HOST_COPY
+            return SimBatch(first_event, np.zeros(n_ev + 1, np.int64), np.zeros((0, 3)), np.zeros(0, np.int64),
+                            stats=dict(stats, n_points=n_pts))  # fmt: skip
+        grab = (lambda a: a.copy()) if copy else (lambda a: a)
+        offsets = grab(np.ctypeslib.as_array(res.offsets, shape=(n_ev + 1,)))
+        if n_pts > 0:
+            cloud = grab(np.ctypeslib.as_array(res.cloud, shape=(n_pts, 3)))
+            labels = grab(np.ctypeslib.as_array(res.labels, shape=(n_pts,)))
+        else:
+            cloud, labels = np.zeros((0, 3)), np.zeros(0, np.int64)
+        out = SimBatch(first_event, offsets, cloud, labels, stats=dict(stats, n_points=n_pts))
+        if rows:
+            n_rows = int(res.n_rows)
+            out.row_offsets = grab(np.ctypeslib.as_array(res.row_offsets, shape=(n_ev + 1,)))
+            if n_rows > 0:
+                out.rows = grab(np.ctypeslib.as_array(res.rows, shape=(n_rows, 8)))
+                out.row_labels = grab(np.ctypeslib.as_array(res.row_labels, shape=(n_rows,)))
+            else:
+                out.rows, out.row_labels = np.zeros((0, 8)), np.zeros(0, np.int64)
+            out.stats["n_rows"] = n_rows
+        return out
+
+    # ------------------------------------------------------------------------------ hot path
+    def simulate_batch(
+        self,
+        momenta: np.ndarray,
+        vertices: np.ndarray,
+        proton_numbers,
+        mass_numbers,
+        indices,
+        seed: int = 0,
+        first_event: int = 0,
+        spyral_rows: bool = False,
+        keep_all_tb: bool = False,
+        copy: bool = True,
+        host_copy: bool = True,
+    ) -> SimBatch:
+        """`simulate` (`simulator.py:52-115`) for ``B`` events at once: ``momenta [B, K, 4]``, ``vertices [B, 3]``."""
+        momenta = np.ascontiguousarray(momenta, dtype=np.float64)
+        vertices = np.ascontiguousarray(vertices, dtype=np.float64)
+        if momenta.ndim != 3 or momenta.shape[2] != 4:
+            raise ValueError("momenta must have shape [n_events, n_nuclei, 4]")
+        if vertices.shape != (momenta.shape[0], 3):
+            raise ValueError("vertices must have shape [n_events, 3]")
+        nucleus, spec = self._species_of(proton_numbers, mass_numbers, indices)
+        flags = (_lib.SPYRAL_ROWS if spyral_rows else 0) | (_lib.KEEP_ALL_TB if keep_all_tb else 0)
+        if not host_copy:
+            flags |= _lib.SKIP_HOST_COPY
+        res = _lib.AttpcResult()
+        code = self.lib.attpc_simulate(
+            self.handle, _ptr(momenta, C.c_double), _ptr(vertices, C.c_double), momenta.shape[0], momenta.shape[1],
+            _ptr(nucleus, C.c_int32), _ptr(spec, C.c_int32), len(nucleus), int(seed) & (2**64 - 1), int(first_event),
+            flags, C.byref(res),
+        )  # fmt: skip
+        _lib.check(code, self.handle)
+        return self._collect(res, first_event, copy, spyral_rows)
+
+    def simulate_device(
+        self, momenta_ptr: int, vertices_ptr: int, n_events: int, n_nuclei: int, proton_numbers, mass_numbers,
+        indices, seed: int = 0, first_event: int = 0, host_copy: bool = False, spyral_rows: bool = False,
+    ) -> SimBatch:  # fmt: skip
+        """Same with inputs already resident in device memory (raw CUDA pointers, e.g. ``tensor.data_ptr()``)."""
+        nucleus, spec = self._species_of(proton_numbers, mass_numbers, indices)
+        flags = (0 if host_copy else _lib.SKIP_HOST_COPY) | (_lib.SPYRAL_ROWS if spyral_rows else 0)
+        res = _lib.AttpcResult()
+        code = self.lib.attpc_simulate_dev(
+            self.handle, C.c_void_p(momenta_ptr), C.c_void_p(vertices_ptr), int(n_events), int(n_nuclei),
+            _ptr(nucleus, C.c_int32), _ptr(spec, C.c_int32), len(nucleus), int(seed) & (2**64 - 1), int(first_event),
+            flags, C.byref(res),
+        )  # fmt: skip
+        _lib.check(code, self.handle)
+        return self._collect(res, first_event, False, spyral_rows and host_copy)
+
+    # ------------------------------------------------------------------ parity / staged entries
+    def simulate_replay(
+        self,
+        tracks: list[np.ndarray],
+        normals: list[np.ndarray],
+        track_event,
+        track_rank,
+        track_label,
+        track_za: list[tuple[int, int]],
+        n_events: int,
+        uniforms: list[tuple[np.ndarray, np.ndarray]] | None = None,
+        keep_all_tb: bool = False,
+        no_wiggle: bool = False,
+        spyral_rows: bool = False,
+    ) -> tuple[SimBatch, list[np.ndarray]]:
+        """Everything after the trajectory from given rows and random numbers (parity part (a)).
+
+        ``uniforms[e] = (keys, u)`` replays `simulator.py:108` keyed by Szudzik id.
+        Returns the batch and, per track, ``electrons`` as `solver.py:343-346` would.
+        """
+        n_tracks = len(tracks)
+        lens = np.array([len(t) for t in tracks], dtype=np.int64)
+        offsets = np.zeros(n_tracks + 1, dtype=np.int64)
+        np.cumsum(lens, out=offsets[1:])
+        rows = np.ascontiguousarray(np.concatenate(tracks) if n_tracks else np.zeros((0, 6)), dtype=np.float64)
+        zn = np.ascontiguousarray(np.concatenate(normals) if n_tracks else np.zeros(0), dtype=np.float64)
+        if len(zn) != len(rows):
+            raise ValueError("one standard normal per trajectory row is required")
+        ev = np.ascontiguousarray(track_event, dtype=np.int32)
+        rk = np.ascontiguousarray(track_rank, dtype=np.int32)
+        lb = np.ascontiguousarray(track_label, dtype=np.int32)
+        sp = np.array([-1 if z == 0 else self.species_index[(int(z), int(a))] for z, a in track_za], dtype=np.int32)
+        electrons = np.zeros(max(1, len(rows)), dtype=np.int64)
+        replay = None
+        keep = []
+        if uniforms is not None:
+            u_off = np.zeros(n_events + 1, dtype=np.int64)
+            ks, us = [], []
+            for e in range(n_events):
+                k, u = uniforms[e]
+                order = np.argsort(np.asarray(k, dtype=np.int64), kind="stable")
+                ks.append(np.asarray(k, dtype=np.int64)[order])
+                us.append(np.asarray(u, dtype=np.float64)[order])
+                u_off[e + 1] = u_off[e] + len(order)
+            u_keys = np.ascontiguousarray(np.concatenate(ks) if ks else np.zeros(0, np.int64))
+            u_vals = np.ascontiguousarray(np.concatenate(us) if us else np.zeros(0))
+            keep = [u_off, u_keys, u_vals]
+            replay = _lib.AttpcReplay(_ptr(u_off, C.c_int64), _ptr(u_keys, C.c_int64), _ptr(u_vals, C.c_double))
+        flags = (
+            (_lib.KEEP_ALL_TB if keep_all_tb else 0)
+            | (_lib.NO_WIGGLE if no_wiggle else 0)
+            | (_lib.SPYRAL_ROWS if spyral_rows else 0)
+        )
+        res = _lib.AttpcResult()
+        code = self.lib.attpc_simulate_replay(
+            self.handle, _ptr(offsets, C.c_int64), _ptr(rows, C.c_double), _ptr(zn, C.c_double), _ptr(ev, C.c_int32),
+            _ptr(rk, C.c_int32), _ptr(lb, C.c_int32), _ptr(sp, C.c_int32), n_tracks, int(n_events),
+            C.byref(replay) if replay is not None else None, flags, _ptr(electrons, C.c_int64), C.byref(res),
+        )  # fmt: skip
+        _lib.check(code, self.handle)
+        del keep
+        batch = self._collect(res, 0, True, spyral_rows)
+        per_track = [electrons[offsets[t] : offsets[t + 1]].copy() for t in range(n_tracks)]
+        return batch, per_track
+
+    def trajectories(self, momenta, vertices, nuclei, stride: int = 1, max_points: int = 10001):
+        """`generate_trajectory` (`solver.py:243-305`) for a list of tracks; returns (points, counts)."""
+        momenta = np.ascontiguousarray(momenta, dtype=np.float64).reshape(-1, 4)
+        vertices = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        n = len(momenta)
+        sp = np.array([self.species_index[(int(nu.Z), int(nu.A))] for nu in nuclei], dtype=np.int32)
+        out = np.zeros((n, max_points, 6), dtype=np.float64)
+        counts = np.zeros(n, dtype=np.int32)
+        code = self.lib.attpc_trajectories(
+            self.handle, _ptr(momenta, C.c_double), _ptr(vertices, C.c_double), _ptr(sp, C.c_int32), n, int(stride),
+            int(max_points), _ptr(out, C.c_double), _ptr(counts, C.c_int32),
+        )  # fmt: skip
+        _lib.check(code, self.handle)
+        return out, counts
+
+    def convert_to_spyral(self, offsets, cloud, labels, keep_all: bool = False) -> SimBatch:
+        """`convert_to_spyral` + threshold + z-sort (`writer.py:61-112, 232-238`) for CSR clouds.
+
+        ``keep_all=True`` is the bare `convert_to_spyral`: every row, input order.
+        """
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        cloud = np.ascontiguousarray(cloud, dtype=np.float64).reshape(-1, 3)
+        labels = np.ascontiguousarray(labels, dtype=np.int64)
+        res = _lib.AttpcResult()
+        code = self.lib.attpc_convert_to_spyral(
+            self.handle, _ptr(offsets, C.c_int64), _ptr(cloud, C.c_double), _ptr(labels, C.c_int64), len(offsets) - 1,
+            _lib.ROWS_KEEP_ALL if keep_all else 0, C.byref(res),
+        )  # fmt: skip
+        _lib.check(code, self.handle)
+        n_ev, n_rows = len(offsets) - 1, int(res.n_rows)
+        out = SimBatch(0, offsets, cloud, labels)
+        out.row_offsets = np.ctypeslib.as_array(res.row_offsets, shape=(n_ev + 1,)).copy()
+        if n_rows:
+            out.rows = np.ctypeslib.as_array(res.rows, shape=(n_rows, 8)).copy()
+            out.row_labels = np.ctypeslib.as_array(res.row_labels, shape=(n_rows,)).copy()
+        else:
+            out.rows, out.row_labels = np.zeros((0, 8)), np.zeros(0, np.int64)
+        return out
+
+    def lookup_pads(self, xy: np.ndarray) -> np.ndarray:
+        """`position_to_index` + grid read + beam veto (`transporter.py:78-120, 165`) for ``xy [n, 2]`` in m."""
+        xy = np.ascontiguousarray(xy, dtype=np.float64).reshape(-1, 2)
+        out = np.empty(len(xy), dtype=np.int32)
+        _lib.check(self.lib.attpc_lookup_pads(self.handle, _ptr(xy, C.c_double), len(xy), _ptr(out, C.c_int32)),
+                   self.handle)  # fmt: skip
+        return out
+
+
+def engine_for(config: Config, nuclei: list, device: int = 0, **tuning) -> Engine:
+    """Engine cached on the Config object, keyed by device, species set and tuning."""
+    cache = config.__dict__.setdefault("_b200_engines", {})
+    key = (int(device), tuple(sorted((int(n.Z), int(n.A)) for n in nuclei)), tuple(sorted(tuning.items())))
+    eng = cache.get(key)
+    if eng is None:
+        uniq = {}
+        for n in nuclei:
+            uniq.setdefault((int(n.Z), int(n.A)), n)
+        eng = Engine(config, [uniq[k] for k in sorted(uniq)], device=device, **tuning)
+        cache[key] = eng
+    return eng
+
+
+__all__ = ["Engine", "SimBatch", "engine_for", "build_pad_lut", "default_freeze_ke", "NUM_TB"]

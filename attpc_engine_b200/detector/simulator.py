@@ -1,0 +1,217 @@
+"""Event drivers of the detector simulation (reference: `detector/simulator.py`).
+
+``simulate`` and ``run_simulation`` keep the reference's signatures; ``simulate_batch`` is the
+array-level entry the CUDA path is built around.  All three run on the GPU through
+``engine.Engine``; there is no CPU implementation here.
+
+Randomness: the reference threads one unseeded PCG64 generator through all events
+(`simulator.py:169`).  Here every draw is a Philox4x32-10 value addressed by
+``(seed; event number, nucleus index, grid step)`` or ``(seed; event number, pad/time key)``, so a
+given ``seed`` reproduces a run bit-for-bit however it is batched or sharded over GPUs.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+from numpy.random import Generator, default_rng
+
+from .. import nuclear_map
+from .engine import SimBatch, engine_for
+from .parameters import Config
+from .writer import SimulationWriter
+
+
+@dataclass
+class SimEvent:
+    """One simulated event: the ``(cloud, labels)`` pair `simulate` returns, plus its number."""
+
+    event_number: int
+    cloud: np.ndarray  # [N, 3] pad id, time bucket, electrons
+    labels: np.ndarray  # [N] index of the nucleus that produced the point
+
+    def __iter__(self):
+        return iter((self.cloud, self.labels))
+
+
+def default_indices(n_nuclei: int) -> list[int]:
+    """All final products: ejectile, every decay's first product, and the last nucleus (`simulator.py:152-158`)."""
+    picks = list(range(2, n_nuclei, 2))
+    picks.append(n_nuclei - 1)
+    return picks
+
+
+def _nuclei_for(proton_numbers, mass_numbers, indices, nmap) -> list:
+    out = []
+    for idx in indices:
+        if proton_numbers[idx] == 0:  # neutrons leave no track (`simulator.py:97`)
+            continue
+        out.append(nmap.get_data(int(proton_numbers[idx]), int(mass_numbers[idx])))
+    return out
+
+
+def simulate_batch(
+    momenta: np.ndarray,
+    vertices: np.ndarray,
+    proton_numbers: np.ndarray,
+    mass_numbers: np.ndarray,
+    config: Config,
+    seed: int,
+    indices: list[int],
+    first_event: int = 0,
+    device: int = 0,
+    spyral_rows: bool = False,
+    copy: bool = True,
+    nuclear_data=None,
+    **tuning,
+) -> SimBatch:
+    """Detector simulation of ``B`` kinematics events in one call.
+
+    ``momenta [B, K, 4]`` (px, py, pz, E in MeV), ``vertices [B, 3]`` (m).  Event ``e`` of the batch
+    is global event ``first_event + e`` for the random streams.  Rows of each event come out in
+    ascending (time bucket, pad) pairing-key order (the reference's order is dict insertion order).
+    """
+    nmap = nuclear_data if nuclear_data is not None else nuclear_map
+    momenta = np.asarray(momenta, dtype=np.float64)
+    if momenta.ndim != 3:
+        raise ValueError("momenta must have shape [n_events, n_nuclei, 4]")
+    charged = _nuclei_for(proton_numbers, mass_numbers, indices, nmap)
+    if not charged or momenta.shape[0] == 0:
+        n = momenta.shape[0]
+        empty = SimBatch(first_event, np.zeros(n + 1, np.int64), np.zeros((0, 3)), np.zeros(0, np.int64))
+        if spyral_rows:
+            empty.row_offsets, empty.rows, empty.row_labels = empty.offsets.copy(), np.zeros((0, 8)), empty.labels
+        return empty
+    engine = engine_for(config, charged, device=device, **tuning)
+    return engine.simulate_batch(
+        momenta, vertices, proton_numbers, mass_numbers, indices, seed=seed, first_event=first_event,
+        spyral_rows=spyral_rows, copy=copy,
+    )  # fmt: skip
+
+
+def simulate(
+    momenta: np.ndarray,
+    vertex: np.ndarray,
+    proton_numbers: np.ndarray,
+    mass_numbers: np.ndarray,
+    config: Config,
+    rng: Generator,
+    indices: list[int],
+) -> tuple[np.ndarray, np.ndarray]:
+    """Apply the detector simulation to one kinematics event (`simulator.py:52-115`).
+
+    Same arguments and return value as the reference: ``(cloud [N, 3], labels [N])`` with rows
+    ``[pad id, time bucket, electrons]``.  ``rng`` only supplies the 63-bit seed of the event's
+    counter-based streams (one ``rng.integers`` draw per call).
+    """
+    seed = int(rng.integers(0, 2**63 - 1))
+    batch = simulate_batch(
+        np.asarray(momenta, dtype=np.float64)[None], np.asarray(vertex, dtype=np.float64)[None],
+        proton_numbers, mass_numbers, config, seed, indices,
+    )  # fmt: skip
+    return batch.event(0)
+
+
+class _ArrayKinematics:
+    """Kinematics events held as arrays: ``data [n, K, 4]``, ``vertices [n, 3]`` (+ Z, A)."""
+
+    def __init__(self, data, vertices, proton_numbers, mass_numbers):
+        self.data, self.vertices = data, vertices
+        self.proton_numbers, self.mass_numbers = np.asarray(proton_numbers), np.asarray(mass_numbers)
+        self.n_events = len(data)
+
+    def read(self, start: int, stop: int):
+        return self.data[start:stop], self.vertices[start:stop]
+
+
+class _Hdf5Kinematics:
+    """The reference's kinematics file (`kinematics/pipeline.py:449-493`), read in event ranges."""
+
+    def __init__(self, path: Path):
+        try:
+            import h5py
+        except ImportError as exc:  # pragma: no cover - depends on the environment
+            raise ImportError(
+                "reading HDF5 kinematics needs h5py; use a .npz kinematics file "
+                "(attpc_engine_b200.kinematics.save_kinematics_npz) where h5py is unavailable"
+            ) from exc
+        self.file = h5py.File(path, "r")
+        self.group = self.file["data"]
+        self.proton_numbers = np.asarray(self.group.attrs["proton_numbers"])
+        self.mass_numbers = np.asarray(self.group.attrs["mass_numbers"])
+        self.n_events = int(self.group.attrs["n_events"])
+        self.chunk_size = int(self.group.attrs["chunk_size"])
+
+    def read(self, start: int, stop: int):
+        k = len(self.proton_numbers)
+        data = np.empty((stop - start, k, 4))
+        vertices = np.empty((stop - start, 3))
+        for i, ev in enumerate(range(start, stop)):
+            dset = self.group[f"chunk_{ev // self.chunk_size}"][f"event_{ev}"]
+            data[i] = dset[:]
+            vertices[i] = (dset.attrs["vertex_x"], dset.attrs["vertex_y"], dset.attrs["vertex_z"])
+        return data, vertices
+
+
+def _open_kinematics(input_path):
+    if isinstance(input_path, _ArrayKinematics):
+        return input_path
+    path = Path(input_path)
+    if path.suffix == ".npz":
+        with np.load(path) as f:
+            return _ArrayKinematics(f["data"], f["vertices"], f["proton_numbers"], f["mass_numbers"])
+    return _Hdf5Kinematics(path)
+
+
+def run_simulation(
+    config: Config,
+    input_path: Path,
+    writer: SimulationWriter,
+    indices: list[int] | None = None,
+    seed: int | None = None,
+    batch_size: int = 16384,
+    device: int = 0,
+    verbose: bool = True,
+) -> None:
+    """Run the detector simulation over a kinematics file (`simulator.py:118-210`).
+
+    ``input_path``: the reference's HDF5 kinematics file (needs h5py) or an ``.npz`` with ``data``,
+    ``vertices``, ``proton_numbers``, ``mass_numbers``.  ``writer.write(cloud, labels, config,
+    event_number)`` is called once per non-empty event in ascending event order and
+    ``writer.close()`` at the end, exactly like the reference; a writer that also defines
+    ``write_batch(batch, config)`` receives whole :class:`SimBatch` objects instead (with the Spyral
+    rows already computed on the GPU when it sets ``wants_spyral_rows = True``).
+    ``seed=None`` draws one from the OS, like the reference's unseeded generator.
+    """
+    kin = _open_kinematics(input_path)
+    if verbose:
+        print("------- AT-TPC Simulation Engine (B200) -------")
+        print(f"Applying detector effects to kinematics from file: {input_path}")
+        print(f"Found {kin.n_events} kinematics events.")
+        print(f"Output will be written to {writer.get_directory_name()}.")
+    nuclei_to_sim = list(indices) if indices is not None else default_indices(len(kin.proton_numbers))
+    if seed is None:
+        seed = int(default_rng().integers(0, 2**63 - 1))
+    batched = hasattr(writer, "write_batch")
+    want_rows = bool(getattr(writer, "wants_spyral_rows", False)) and batched
+    for start in range(0, kin.n_events, batch_size):
+        stop = min(start + batch_size, kin.n_events)
+        momenta, vertices = kin.read(start, stop)
+        batch = simulate_batch(
+            momenta, vertices, kin.proton_numbers, kin.mass_numbers, config, seed, nuclei_to_sim,
+            first_event=start, device=device, spyral_rows=want_rows, copy=False,
+        )  # fmt: skip
+        if batched:
+            writer.write_batch(batch, config)
+            continue
+        for e in range(len(batch)):
+            cloud, labels = batch.event(e)
+            if len(cloud) == 0:  # `simulator.py:204`
+                continue
+            writer.write(cloud.copy(), labels.copy(), config, start + e)
+    writer.close()
+    if verbose:
+        print("Done.")
+        print("----------------------------------------")

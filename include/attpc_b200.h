@@ -35,7 +35,8 @@ enum {
     ATTPC_KEEP_ALL_TB = 1u << 0,   /* skip the 0 <= tb < 512 mask of detector/simulator.py:111-113 (tests) */
     ATTPC_SPYRAL_ROWS = 1u << 1,   /* also produce the 8-column Spyral rows (detector/writer.py:61-112,232-238) */
     ATTPC_NO_WIGGLE = 1u << 2,     /* add 0 instead of U[0,1) to the time bucket (tests) */
-    ATTPC_SKIP_HOST_COPY = 1u << 3 /* leave results in device memory only (device-resident benchmarking) */
+    ATTPC_SKIP_HOST_COPY = 1u << 3,/* leave results in device memory only (device-resident benchmarking) */
+    ATTPC_ROWS_KEEP_ALL = 1u << 4  /* attpc_convert_to_spyral: every row, input order (no threshold, no sort) */
 };
 
 /* Scalars of DetectorParams / ElectronicsParams / Config (detector/parameters.py:10-76,164-174). */
@@ -182,9 +183,11 @@ int attpc_trajectories(AttpcSim* sim, const double* momenta, const double* verti
                        int64_t n_tracks, int32_t stride, int32_t max_points, double* out_points, int32_t* out_counts);
 
 /* detector/writer.py:61-112 + :232-238 on a host cloud: rows, ADC threshold, per-event z-sort.
- *   offsets [n_events+1], cloud [n_points,3], labels [n_points]; results in result->rows etc. */
+ *   offsets [n_events+1], cloud [n_points,3], labels [n_points]; results in result->rows etc.
+ *   flags: ATTPC_ROWS_KEEP_ALL = plain convert_to_spyral (detector/writer.py:61-112 only).
+ * Needs no species: a handle created with n_species == 0 can only convert. */
 int attpc_convert_to_spyral(AttpcSim* sim, const int64_t* offsets, const double* cloud, const int64_t* labels,
-                            int64_t n_events, AttpcResult* result);
+                            int64_t n_events, uint32_t flags, AttpcResult* result);
 
 /* Pad lookup of detector/transporter.py:78-120 + the veto of :165,237 for n positions (metres). */
 int attpc_lookup_pads(AttpcSim* sim, const double* xy, int64_t n, int32_t* pads_out);

@@ -1,0 +1,78 @@
+"""Shared helpers of the test-suite: configurations of the golden cases, fixture loading."""
+
+import json
+from pathlib import Path
+
+import numpy as np
+
+from attpc_engine_b200 import nuclear_map
+from attpc_engine_b200.detector import Config, DetectorParams, ElectronicsParams, PadParams
+from attpc_engine_b200.detector.pairing import pair
+from attpc_engine_b200.target import AnalyticGasTarget, TableGasTarget
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+META = json.loads((GOLDEN / "golden_meta.json").read_text())
+GASES = {k: (v["compound"], v["pressure"]) for k, v in META["gases"].items()}
+_gas_cache: dict = {}
+
+
+def load_golden(name):
+    with np.load(GOLDEN / name) as f:
+        return {k: f[k] for k in f.files}
+
+
+def gas(name="D2_600"):
+    """Same dE/dx tables the fixtures were generated with (tests/golden/ref_shim.py: GasTarget)."""
+    if name not in _gas_cache:
+        compound, pressure = GASES[name]
+        _gas_cache[name] = TableGasTarget(AnalyticGasTarget([tuple(c) for c in compound], pressure))
+    return _gas_cache[name]
+
+
+def make_config(gas_name="D2_600", bfield=3.0, diffusion=0.277, threshold=40):
+    det = DetectorParams(
+        length=1.0, efield=45000.0, bfield=bfield, mpgd_gain=175000, gas_target=gas(gas_name),
+        diffusion=diffusion, fano_factor=0.2, w_value=34.0,
+    )  # fmt: skip
+    elec = ElectronicsParams(
+        clock_freq=6.25, amp_gain=900, shaping_time=1000, micromegas_edge=10, windows_edge=560,
+        adc_threshold=threshold,
+    )  # fmt: skip
+    return Config(det, elec, PadParams())
+
+
+def case_names():
+    return list(META["cases"].keys())
+
+
+def case_config(name):
+    return make_config(**META["cases"][name]["config"])
+
+
+def case_tracks(ev, name):
+    """Charged tracks of a golden case in `indices` order: list of (nucleus idx, rank, (Z, A), rows, normals, electrons)."""
+    zs, as_, indices = ev[f"{name}/Z"], ev[f"{name}/A"], ev[f"{name}/indices"]
+    out, slot = [], 0
+    for rank, idx in enumerate(indices):
+        if zs[idx] == 0:
+            continue
+        out.append(
+            dict(idx=int(idx), rank=rank, za=(int(zs[idx]), int(as_[idx])), rows=ev[f"{name}/track{slot}"],
+                 normals=ev[f"{name}/normals{slot}"], electrons=ev[f"{name}/electrons{slot}"])
+        )  # fmt: skip
+        slot += 1
+    return out
+
+
+def nuclei_of(tracks):
+    return [nuclear_map.get_data(z, a) for z, a in dict.fromkeys(t["za"] for t in tracks)]
+
+
+def cloud_keys(cloud):
+    """Szudzik key of every cloud row ([pad, tb(float), e])."""
+    return np.asarray(pair(np.floor(cloud[:, 1]).astype(np.int64), cloud[:, 0].astype(np.int64)), dtype=np.int64)
+
+
+def sort_cloud(cloud, labels):
+    order = np.argsort(cloud_keys(cloud), kind="stable")
+    return cloud[order], labels[order]
