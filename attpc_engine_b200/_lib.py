@@ -98,6 +98,8 @@ class AttpcResult(C.Structure):
         ("ms_total", C.c_float),
         ("n_kernel_launches", C.c_int32),
         ("n_retries", C.c_int32),
+        ("n_track_launches", C.c_int32),
+        ("n_group_launches", C.c_int32),
     ]
 
 

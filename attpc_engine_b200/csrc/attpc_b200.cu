@@ -87,7 +87,7 @@ struct AttpcSim {
     DevArray<double> pad_xy, pad_scale, response, resp_sorted, resp_prefix, tables;
 
     // sizing
-    int32_t launch_events = 16384;
+    int32_t launch_events = 32768;
     int32_t group_events = 512;
     int32_t hash_cap = 8192;
     int64_t group_point_cap = 0;
@@ -487,6 +487,8 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     cudaEventElapsedTime(&res->ms_total, t_begin, t_end);
     res->ms_total += ms_h2d;
     res->n_kernel_launches = sim->launches;
+    res->n_track_launches = (int32_t)trk_marks.size();
+    res->n_group_launches = (int32_t)dep_marks.size();
     return ATTPC_OK;
 }
 

@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Throughput benchmark of the detector-simulation hot path (see the task contract in DESIGN.md section "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--events B]
+
+A *step* is one pass of the whole hot path (`simulate` of detector/simulator.py:52-115 for every event) over one
+batch of B synthetic kinematics events per GPU.  Prints ONE JSON line (rank 0).
+
+* value      events/s with the inputs resident in HBM and the results left in HBM (device time, CUDA events
+             recorded by the library on its own stream, max over ranks).
+* e2e        the same metric through the public Python API `simulate_batch` with pinned HOST inputs and the
+             full point clouds copied back to HOST inside the timed region.
+* roofline   dominant kernel (by device time) against the measured HBM peak, algorithmic bytes of SURVEY.md 8(d).
+* cpu_baseline / --impl reference
+             the CPU oracle port of the reference (oracle/attpc_oracle.py: scipy Radau + numba, the reference's
+             own tool chain) on all host cores, on a bounded sample of the same events.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (description, gas, (target, projectile, ejectile), decays [(parent, residual_1)], excitations, beam MeV)
+    "c16dd": dict(
+        desc="16C(d,d')16C g.s., 184.131 MeV 16C (11.5 MeV/u) on D2 600 Torr, B=3 T, E=45 kV/m; tracks [2,3]",
+        gas=([(1, 2, 2)], 600.0), reaction=((1, 2), (6, 16), (1, 2)), decays=[], excitations=[("gauss", 0.0, 0.001)],
+        beam=184.131, config_id=1,
+    ),
+    "c14dp": dict(
+        desc="14C(d,p)15C* -> 14C + n, 161 MeV 14C on D2 600 Torr, B=3 T; tracks [2,4,5] (neutron skipped)",
+        gas=([(1, 2, 2)], 600.0), reaction=((1, 2), (6, 14), (1, 1)), decays=[((6, 15), (6, 14))],
+        excitations=[("gauss", 3.1, 0.04), ("gauss", 0.0, 0.0)], beam=161.0, config_id=2,
+    ),
+    "c12aa": dict(
+        desc="12C(a,a')12C*(7.654) -> a + 8Be -> 3a, 96 MeV 12C on 4He 600 Torr, B=3 T; tracks [2,4,6,7]",
+        gas=([(2, 4, 1)], 600.0), reaction=((2, 4), (6, 12), (2, 4)), decays=[((6, 12), (2, 4)), ((4, 8), (2, 4))],
+        excitations=[("gauss", 7.654, 0.0), ("gauss", 0.0, 0.0), ("gauss", 0.0, 0.0)], beam=96.0, config_id=3,
+    ),
+    "sn132dp": dict(
+        desc="132Sn(d,p)133Sn, 1320 MeV 132Sn (10 MeV/u) on D2 600 Torr, B=3 T; tracks [2,3]",
+        gas=([(1, 2, 2)], 600.0), reaction=((1, 2), (50, 132), (1, 1)), decays=[], excitations=[("gauss", 0.0, 0.001)],
+        beam=1320.0, config_id=4,
+    ),
+}  # fmt: skip
+
+
+def build_workload(name: str, n_events: int, seed_offset: int = 0):
+    """Synthetic kinematics of a named reaction + the detector Config."""
+    from attpc_engine_b200 import nuclear_map as nm
+    from attpc_engine_b200.detector import Config, DetectorParams, ElectronicsParams, PadParams
+    from attpc_engine_b200.detector.simulator import default_indices
+    from attpc_engine_b200.kinematics import (
+        Decay, ExcitationGaussian, KinematicsPipeline, KinematicsTargetMaterial, PolarUniform, Reaction,
+    )  # fmt: skip
+    from attpc_engine_b200.target import AnalyticGasTarget, TableGasTarget
+
+    w = WORKLOADS[name]
+    gas = TableGasTarget(AnalyticGasTarget(*w["gas"]))
+    t, p, e = (nm.get_data(*za) for za in w["reaction"])
+    steps = [Reaction(target=t, projectile=p, ejectile=e)]
+    steps += [Decay(parent=nm.get_data(*a), residual_1=nm.get_data(*b)) for a, b in w["decays"]]
+    pipeline = KinematicsPipeline(
+        steps, [ExcitationGaussian(c, fwhm) for _, c, fwhm in w["excitations"]], [PolarUniform(0.0, np.pi)] * len(steps),
+        beam_energy=w["beam"], target_material=KinematicsTargetMaterial(gas, (0.0, 1.0), 0.007),
+    ).seed(20260101 + w["config_id"] + 7919 * seed_offset)  # fmt: skip
+    vertices, momenta = pipeline.run_batch(n_events)
+    det = DetectorParams(length=1.0, efield=45000.0, bfield=3.0, mpgd_gain=175000, gas_target=gas, diffusion=0.277,
+                         fano_factor=0.2, w_value=34.0)  # fmt: skip
+    elec = ElectronicsParams(clock_freq=6.25, amp_gain=900, shaping_time=1000, micromegas_edge=10, windows_edge=560,
+                             adc_threshold=40)  # fmt: skip
+    config = Config(det, elec, PadParams())
+    zs, as_ = pipeline.get_proton_numbers(), pipeline.get_mass_numbers()
+    return config, momenta, vertices, zs, as_, default_indices(len(zs))
+
+
+# ----------------------------------------------------------------------------------------------- CPU (oracle) arm
+_CPU = {}
+
+
+def _cpu_init(name):
+    from attpc_engine_b200 import nuclear_map
+    from oracle import attpc_oracle as oracle
+
+    config, momenta, vertices, zs, as_, indices = build_workload(name, 4)
+    _CPU.update(config=config, zs=zs, as_=as_, indices=indices, oracle=oracle, nmap=nuclear_map)
+    oracle.simulate_event(momenta[0], vertices[0], zs, as_, config, np.random.default_rng(0), indices, nuclear_map)
+
+
+def _cpu_chunk(args):
+    momenta, vertices, first = args
+    c = _CPU
+    rec = {}
+    points = electrons = 0
+    t0 = time.perf_counter()
+    for i in range(len(momenta)):
+        cloud, _ = c["oracle"].simulate_event(
+            momenta[i], vertices[i], c["zs"], c["as_"], c["config"], np.random.default_rng(first + i), c["indices"],
+            c["nmap"], record=rec,
+        )  # fmt: skip
+        points += len(cloud)
+        electrons += rec["stats"]["primary_electrons"]
+    return len(momenta), points, electrons, time.perf_counter() - t0
+
+
+class CpuArm:
+    """The oracle port on all host cores (multiprocessing over disjoint event ranges)."""
+
+    def __init__(self, name, cores=None):
+        import multiprocessing as mp
+
+        self.cores = cores or len(os.sched_getaffinity(0))
+        self.pool = mp.get_context("spawn").Pool(self.cores, initializer=_cpu_init, initargs=(name,))
+
+    def run(self, momenta, vertices, first=0):
+        n = len(momenta)
+        per = max(1, -(-n // self.cores))
+        jobs = [(momenta[a : a + per], vertices[a : a + per], first + a) for a in range(0, n, per)]
+        t0 = time.perf_counter()
+        out = self.pool.map(_cpu_chunk, jobs)
+        wall = time.perf_counter() - t0
+        return dict(events=sum(o[0] for o in out), points=sum(o[1] for o in out), electrons=sum(o[2] for o in out),
+                    wall_s=wall, core_s=sum(o[3] for o in out))  # fmt: skip
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+# ------------------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")  # fmt: skip
+
+    def __init__(self, device):
+        self.device, self.proc = device, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )  # fmt: skip
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}  # fmt: skip
+
+
+def measured_peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dist_setup(n_gpus):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def reduce_max(dist, value, device):
+    if dist is None:
+        return value
+    import torch
+
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{device}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def reduce_sum(dist, value, device):
+    if dist is None:
+        return value
+    import torch
+
+    t = torch.tensor([value], dtype=torch.float64, device=f"cuda:{device}")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ------------------------------------------------------------------------------------------------------- arms
+def run_ours(args):
+    import torch
+
+    from attpc_engine_b200.detector.engine import engine_for
+    from attpc_engine_b200.detector.simulator import _nuclei_for
+    from attpc_engine_b200 import nuclear_map
+
+    rank, world, local, dist = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    B = args.events
+    config, momenta, vertices, zs, as_, indices = build_workload(args.workload, B, seed_offset=rank)
+    K = momenta.shape[1]
+    eng = engine_for(config, _nuclei_for(zs, as_, indices, nuclear_map), device=local,
+                     max_events_per_launch=args.launch_events)  # fmt: skip
+    # pinned host inputs (e2e) and device-resident inputs (value)
+    mom_pin = torch.from_numpy(momenta).pin_memory()
+    vtx_pin = torch.from_numpy(vertices).pin_memory()
+    mom_dev = mom_pin.to(f"cuda:{local}")
+    vtx_dev = vtx_pin.to(f"cuda:{local}")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+    seed = 20260101
+    first = rank * B  # this rank's event range: [rank*B, (rank+1)*B)
+
+    def flush_l2():
+        flush.zero_()
+        torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    def step_device(i):
+        return eng.simulate_device(mom_dev.data_ptr(), vtx_dev.data_ptr(), B, K, zs, as_, indices, seed=seed + i,
+                                   first_event=first).stats  # fmt: skip
+
+    def step_e2e(i):
+        return eng.simulate_batch(mom_pin.numpy(), vtx_pin.numpy(), zs, as_, indices, seed=seed + i, first_event=first,
+                                  copy=False).stats  # fmt: skip
+
+    for i in range(args.warmup):
+        step_device(i)
+        step_e2e(i)
+
+    sampler = ClockSampler(local)
+    # ---- value: device-resident
+    barrier()
+    sampler.start()
+    dev_ms, stats_sum, launches = 0.0, {}, 0
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush_l2()
+        st = step_device(100 + i)
+        dev_ms += st["ms_total"]
+        launches += st["n_kernel_launches"]
+        for k, v in st.items():
+            stats_sum[k] = stats_sum.get(k, 0) + v
+    barrier()
+    wall_dev = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    # ---- e2e: host buffers in, host buffers out
+    barrier()
+    e2e_s, e2e_points = 0.0, 0
+    for i in range(args.steps):
+        flush_l2()
+        barrier()
+        t0 = time.perf_counter()
+        st = step_e2e(100 + i)
+        torch.cuda.synchronize()
+        e2e_s += time.perf_counter() - t0
+        e2e_points += st["n_points"]
+    barrier()
+
+    dev_s = reduce_max(dist, dev_ms / 1e3, local)
+    e2e_s = reduce_max(dist, e2e_s, local)
+    total_events = B * world * args.steps
+    electrons = reduce_sum(dist, stats_sum["n_primary_electrons"], local)
+    points = reduce_sum(dist, stats_sum["n_points"], local)
+    deposits = reduce_sum(dist, stats_sum["n_deposits"], local)
+
+    if rank != 0:
+        return
+    peak, peak_src = measured_peak_hbm()
+    # dominant kernel by device time
+    stage_ms = {"track_kernel": stats_sum["ms_tracks"], "deposit_kernel": stats_sum["ms_deposit"],
+                "finalize (collect+scan+emit)": stats_sum["ms_finalize"]}  # fmt: skip
+    dominant = max(stage_ms, key=stage_ms.get)
+    n_ev_rank = B * args.steps
+    n_out = stats_sum["n_points"] / n_ev_rank
+    bytes_per_event = 8 * (4 * K + 3) + 32 * n_out
+    launches_dom = stats_sum["n_track_launches"] if dominant == "track_kernel" else stats_sum["n_group_launches"]
+    events_per_launch = n_ev_rank / launches_dom
+    avg_launch_ms = stage_ms[dominant] / launches_dom
+    achieved = bytes_per_event * events_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {
+        "kernel": dominant, "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
+        "frac": round(achieved / peak, 6), "traffic": None, "peak_source": peak_src,
+        "bytes_per_event": round(bytes_per_event, 1), "events_per_launch": round(events_per_launch, 1),
+        "avg_launch_ms": round(avg_launch_ms, 4),
+        "note": "path is issue/atomic bound, not HBM bound (SURVEY.md 8d); see profiles/ for ncu issue utilisation",
+        "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage_ms.items()},
+    }  # fmt: skip
+    out = {
+        "metric": "detector-simulated events/s", "value": round(total_events / dev_s, 1), "unit": "events/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_s / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: {WORKLOADS[args.workload]['desc']}", "events_per_gpu_per_step": B,
+            "nuclei_per_event": K, "tracks": indices, "l2": "flushed between steps (256 MiB device write)",
+            "dedx": "analytic Bethe+Lindhard table (not CATIMA)", "parallelism": f"event-range shards x{world}",
+        },
+        "electrons_per_s": round(electrons / dev_s, 1), "cloud_points_per_s": round(points / dev_s, 1),
+        "pixel_deposits_per_s": round(deposits / dev_s, 1),
+        "per_event": {"cloud_points": round(n_out, 1), "active_points": round(stats_sum["n_active_points"] / n_ev_rank, 1),
+                      "trajectory_points": round(stats_sum["n_trajectory_points"] / n_ev_rank, 1),
+                      "primary_electrons": round(stats_sum["n_primary_electrons"] / n_ev_rank, 1)},
+        "wall_s_device_loop": round(wall_dev, 3),
+        "e2e": {"value": round(total_events / e2e_s, 1), "unit": "events/s",
+                "h2d_bytes_per_step": int(momenta.nbytes + vertices.nbytes),
+                "d2h_bytes_per_step": int(e2e_points / args.steps * 32 + (B + 1) * 8)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+    }  # fmt: skip
+    if world == 1 and not args.no_cpu:
+        out["cpu_baseline"] = cpu_baseline(args, momenta, vertices)
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, momenta, vertices):
+    arm = CpuArm(args.workload, args.cpu_cores or None)
+    n = min(len(momenta), max(64, args.cpu_events_per_core * arm.cores))
+    res = arm.run(momenta[:n], vertices[:n])
+    arm.close()
+    return {"value": round(res["events"] / res["wall_s"], 2), "unit": "events/s", "cores": arm.cores, "kind": "port",
+            "sample": f"first {n} events of the same workload, {arm.cores} processes, numba warm-up excluded",
+            "events_per_s_per_core": round(res["events"] / res["core_s"], 2),
+            "electrons_per_s": round(res["electrons"] / res["wall_s"], 1)}  # fmt: skip
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arm = CpuArm(args.workload, args.cpu_cores or None)
+    n = max(64, args.cpu_events_per_core * arm.cores)
+    config, momenta, vertices, zs, as_, indices = build_workload(args.workload, n)
+    for _ in range(args.warmup):
+        arm.run(momenta[: arm.cores], vertices[: arm.cores])
+    wall = events = electrons = 0.0
+    core_s = 0.0
+    for i in range(args.steps):
+        res = arm.run(momenta, vertices, first=i * n)
+        wall += res["wall_s"]
+        events += res["events"]
+        electrons += res["electrons"]
+        core_s += res["core_s"]
+    arm.close()
+    value = round(events / wall, 2)
+    sample = f"{n} events per step of the same workload, {arm.cores} processes"
+    out = {
+        "impl": "reference", "metric": "detector-simulated events/s", "value": value, "unit": "events/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(wall / args.steps * 1e3, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {WORKLOADS[args.workload]['desc']}", "events_per_step": n,
+                   "dedx": "analytic Bethe+Lindhard table (not CATIMA)"},
+        "electrons_per_s": round(electrons / wall, 1),
+        "cpu_baseline": {"value": value, "unit": "events/s", "cores": arm.cores, "kind": "port", "sample": sample,
+                         "events_per_s_per_core": round(events / core_s, 2)},
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }  # fmt: skip
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c16dd", choices=sorted(WORKLOADS))
+    ap.add_argument("--events", type=int, default=32768, help="events per GPU per step")
+    ap.add_argument("--launch-events", type=int, default=0, help="events per track-kernel launch (0 = library default)")
+    ap.add_argument("--cpu-cores", type=int, default=0)
+    ap.add_argument("--cpu-events-per-core", type=int, default=24)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

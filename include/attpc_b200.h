@@ -114,6 +114,8 @@ typedef struct AttpcResult {
     float ms_h2d, ms_tracks, ms_deposit, ms_finalize, ms_d2h, ms_total;
     int32_t n_kernel_launches;
     int32_t n_retries;           /* capacity retries that happened inside the call */
+    int32_t n_track_launches;    /* launches of the track (or replay) kernel */
+    int32_t n_group_launches;    /* launches of the deposit kernel (= event groups processed) */
 } AttpcResult;
 
 typedef struct AttpcSim AttpcSim;
