@@ -166,7 +166,7 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events) {
     CU(sim->prank.reserve(pts));
     CU(sim->group_count.reserve(n_groups));
     CU(sim->hash.reserve((int64_t)sim->group_events * sim->hash_cap));
-    CU(sim->sort_items.reserve((int64_t)sim->group_events * sim->hash_cap));
+    CU(sim->sort_items.reserve((int64_t)sim->group_events * sim->hash_cap * 2));
     CU(sim->counters.reserve(1));
     CU(sim->counters_host.reserve(1));
     return ATTPC_OK;
@@ -262,8 +262,8 @@ int run_spyral(AttpcSim* sim, int64_t n_events, int64_t n_points, AttpcResult* r
     CU(sim->row_offsets_dev.reserve(n_events + 1));
     CU(sim->rows_dev.reserve(std::max<int64_t>(1, n_points) * 8));
     CU(sim->row_labels_dev.reserve(std::max<int64_t>(1, n_points)));
-    CU(sim->row_sort_keys.reserve(std::max<int64_t>(1, n_points)));
-    CU(sim->row_sort_idx.reserve(std::max<int64_t>(1, n_points)));
+    CU(sim->row_sort_keys.reserve(std::max<int64_t>(1, n_points) * 2));
+    CU(sim->row_sort_idx.reserve(std::max<int64_t>(1, n_points) * 2));
     SpyralArgs sa;
     sa.offsets = sim->offsets_dev.p;
     sa.cloud = sim->cloud_dev.p;

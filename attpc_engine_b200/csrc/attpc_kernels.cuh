@@ -9,7 +9,7 @@
 //   deposit_kernel    one warp per active point: sigma_t, 10x10 mesh, pad lookup, bivariate-normal share, Szudzik
 //                     key, accumulate into the event's open-addressing table kept L2-resident
 //                     (detector/transporter.py:11-41, 78-120, 123-249, 252-317; detector/pairing.py:6-28).
-//   collect/scan/emit TB wiggle, 0 <= tb < 512 mask, canonical (ascending-key) order, CSR compaction
+//   collect/scan/emit TB wiggle, 0 <= tb < 512 mask, canonical (ascending time bucket, pad) order, CSR compaction
 //                     (detector/simulator.py:19-49, 104-115); optional Spyral rows (detector/writer.py:61-112).
 //
 // Arithmetic that decides a pad id, a time bucket or an integer charge is written with the _rn intrinsics so that
@@ -625,7 +625,7 @@ struct FinalizeArgs {
     int32_t label_of_rank[MAX_TRACKS_PER_EVENT];
     const int32_t* label_of_event_rank;  // replay: [n_events, n_tracks_per_event] or null
     ReplayUniforms replay;
-    uint64_t* sort_items;     // [group_events][hash_cap] scratch: (order key << 32) | slot
+    uint64_t* sort_items;     // [group_events][2 * hash_cap] scratch: ordered items, then unordered survivors
     unsigned* kept;           // [launch events] rows kept per event
     int64_t* offsets;         // [launch events + 1] CSR offsets (global across groups of the launch)
     double* cloud;            // [out_cap, 3]
@@ -652,37 +652,31 @@ __device__ __forceinline__ double wiggle_of(const FinalizeArgs& fa, int slot_eve
 }
 
 constexpr int FINALIZE_THREADS = 256;
-constexpr int SORT_SMEM_ITEMS = 8192;  // 64 KB of shared memory
+constexpr int SORT_SMEM_ITEMS = 6144;  // 48 KB of shared memory for the in-CTA ordering
+constexpr int TB_BINS = 1024;          // counting-sort bins over the integer time bucket (last bin collects tb >= 1023)
 
-__device__ __forceinline__ void bitonic_sort(uint64_t* a, int n_pow2) {
-    for (int k = 2; k <= n_pow2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const uint64_t x = a[i], y = a[l];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) {
-                        a[i] = y;
-                        a[l] = x;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
+// Canonical row order of an event: ascending (time bucket, pad).  64-bit item = (tb << 47) | (pad << 32) | slot
+// (pad ids are int16 in the pad grid, so 15 bits hold them).
+__device__ __forceinline__ uint64_t make_item(unsigned tb, unsigned pad, unsigned slot) {
+    return ((uint64_t)tb << 47) | ((uint64_t)pad << 32) | (uint64_t)slot;
 }
 
-// One CTA per event: gather the occupied slots that survive the time-bucket mask and sort them by key.
+// One CTA per event: gather the occupied slots that survive the time-bucket mask (detector/simulator.py:104-113)
+// and put them in canonical order: counting sort on the time bucket (exact, O(n)), then an insertion sort of each
+// bucket's handful of pads.  No power-of-two padding and no dependence on which thread found which slot.
 __global__ void __launch_bounds__(FINALIZE_THREADS)
 collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView gv,
                Counters* ctr) {
     extern __shared__ uint64_t s_items[];
+    __shared__ unsigned s_hist[TB_BINS + 1];
+    __shared__ unsigned s_fill[TB_BINS];
     __shared__ unsigned s_n, s_keys;
     const int e = blockIdx.x;
     const int slot_event = gv.first_slot + e;
     const HashEntry* tab = gv.tables + (int64_t)e * gv.hash_cap;
-    uint64_t* items = fa.sort_items + (int64_t)e * gv.hash_cap;
+    uint64_t* sorted = fa.sort_items + (int64_t)e * 2 * gv.hash_cap;  // final order, read by emit_kernel
+    uint64_t* stash = sorted + gv.hash_cap;                           // unordered survivors
+    for (int i = threadIdx.x; i <= TB_BINS; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x == 0) {
         s_n = 0;
         s_keys = 0;
@@ -696,10 +690,10 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
         occupied += 1;
         unsigned tb, pad;
         szudzik_unpair(key, tb, pad);
-        const double tbf = (double)tb + wiggle_of(fa, slot_event, key, ctr);  // detector/simulator.py:108
-        if ((fa.flags & F_KEEP_ALL_TB) || (0.0 <= tbf && tbf < (double)NUM_TB)) {      // detector/simulator.py:111
-            const unsigned pos = atomicAdd(&s_n, 1u);
-            items[pos] = ((uint64_t)key << 32) | (uint64_t)i;
+        const double tbf = (double)tb + wiggle_of(fa, slot_event, key, ctr);      // detector/simulator.py:108
+        if ((fa.flags & F_KEEP_ALL_TB) || (0.0 <= tbf && tbf < (double)NUM_TB)) {  // detector/simulator.py:111
+            atomicAdd(&s_hist[min(tb, (unsigned)TB_BINS - 1u)], 1u);
+            stash[atomicAdd(&s_n, 1u)] = make_item(tb, pad, (unsigned)i);
         }
     }
     if (occupied) atomicAdd(&s_keys, occupied);
@@ -709,18 +703,59 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
         fa.kept[slot_event] = (unsigned)n;
         atomicAdd(&ctr->keys, (unsigned long long)s_keys);
     }
-    if (n <= 1) return;
-    int n2 = 1;
-    while (n2 < n) n2 <<= 1;
-    if (n2 <= SORT_SMEM_ITEMS) {
-        for (int i = threadIdx.x; i < n2; i += blockDim.x) s_items[i] = i < n ? items[i] : ~0ULL;
+    if (n == 0) return;
+    // exclusive scan of the histogram: 4 bins per thread, warp scan, carry across warps through shared memory
+    {
+        const int b0 = threadIdx.x * (TB_BINS / FINALIZE_THREADS);
+        unsigned local[TB_BINS / FINALIZE_THREADS], sum = 0;
+#pragma unroll
+        for (int k = 0; k < TB_BINS / FINALIZE_THREADS; ++k) {
+            local[k] = s_hist[b0 + k];
+            sum += local[k];
+        }
+        unsigned incl = sum;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __shared__ unsigned s_warp[FINALIZE_THREADS / 32];
+        if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        bitonic_sort(s_items, n2);
-        for (int i = threadIdx.x; i < n; i += blockDim.x) items[i] = s_items[i];
-    } else {  // rare, very dense events: sort in the (L2-resident) scratch itself; hash_cap is a power of two >= n2
-        for (int i = n + threadIdx.x; i < n2; i += blockDim.x) items[i] = ~0ULL;
+        unsigned base = incl - sum;
+        for (int w = 0; w < warp; ++w) base += s_warp[w];
+#pragma unroll
+        for (int k = 0; k < TB_BINS / FINALIZE_THREADS; ++k) {
+            s_hist[b0 + k] = base;
+            s_fill[b0 + k] = base;
+            base += local[k];
+        }
+        if (threadIdx.x == FINALIZE_THREADS - 1) s_hist[TB_BINS] = base;
         __syncthreads();
-        bitonic_sort(items, n2);
+    }
+    const bool in_smem = n <= SORT_SMEM_ITEMS;
+    uint64_t* buf = in_smem ? s_items : sorted;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t it = stash[i];
+        const unsigned bin = min((unsigned)(it >> 47), (unsigned)TB_BINS - 1u);
+        buf[atomicAdd(&s_fill[bin], 1u)] = it;
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < TB_BINS; b += blockDim.x) {
+        const int lo = (int)s_hist[b], hi = (int)s_hist[b + 1];
+        for (int i = lo + 1; i < hi; ++i) {
+            const uint64_t v = buf[i];
+            int j = i - 1;
+            while (j >= lo && buf[j] > v) {
+                buf[j + 1] = buf[j];
+                --j;
+            }
+            buf[j + 1] = v;
+        }
+    }
+    if (in_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sorted[i] = s_items[i];
     }
 }
 
@@ -755,7 +790,7 @@ scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr) {
     }
 }
 
-// One CTA per event: write [pad, tb + u, electrons] rows and labels in ascending-key order
+// One CTA per event: write [pad, tb + u, electrons] rows and labels in ascending (time bucket, pad) order
 // (detector/simulator.py:19-49, 104-115).
 __global__ void __launch_bounds__(FINALIZE_THREADS)
 emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView gv,
@@ -766,13 +801,12 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
     const int64_t off = fa.offsets[slot_event];
     if (off + n > fa.out_cap) return;
     const HashEntry* tab = gv.tables + (int64_t)e * gv.hash_cap;
-    const uint64_t* items = fa.sort_items + (int64_t)e * gv.hash_cap;
+    const uint64_t* items = fa.sort_items + (int64_t)e * 2 * gv.hash_cap;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint64_t it = items[i];
-        const unsigned key = (unsigned)(it >> 32);
+        const unsigned tb = (unsigned)(it >> 47), pad = (unsigned)(it >> 32) & 0x7FFFu;
+        const unsigned key = szudzik_pair(tb, pad);
         const HashEntry en = tab[(unsigned)it];
-        unsigned tb, pad;
-        szudzik_unpair(key, tb, pad);
         const double tbf = (double)tb + wiggle_of(fa, slot_event, key, ctr);
         double* row = fa.cloud + (off + i) * 3;
         row[0] = (double)pad;
@@ -859,85 +893,110 @@ __global__ void __launch_bounds__(1024) spyral_scan_kernel(SpyralArgs sa) {
     if (tid == 0) sa.row_offsets[sa.n_events] = (int64_t)s_base;
 }
 
-__device__ __forceinline__ void bitonic_sort_kv(uint64_t* k, uint32_t* v, int n_pow2) {
-    for (int size = 2; size <= n_pow2; size <<= 1) {
-        for (int j = size >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const uint64_t ki = k[i], kl = k[l];
-                    const uint32_t vi = v[i], vl = v[l];
-                    const bool gt = ki > kl || (ki == kl && vi > vl);
-                    if (gt == ((i & size) == 0)) {
-                        k[i] = kl; k[l] = ki;
-                        v[i] = vl; v[l] = vi;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-constexpr int SPYRAL_SMEM_ITEMS = 8192;  // 96 KB: 8 B z-bits + 4 B point index each
+constexpr int SPYRAL_SMEM_ITEMS = 4096;  // 48 KB: 8 B z-bits + 4 B point index each
 
 // pass 2: one CTA per event: keep rows above threshold, order by z (detector/writer.py:236; ties, which numpy's
 // unstable argsort leaves unspecified, are broken by input order), write the 8 columns of detector/writer.py:97-110.
+// z falls as the time bucket rises, so the order is a counting sort on the integer time bucket (descending) plus
+// an insertion sort inside each bucket.
 __global__ void __launch_bounds__(256)
 spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
     extern __shared__ uint64_t s_k[];
     uint32_t* s_v = (uint32_t*)(s_k + SPYRAL_SMEM_ITEMS);
-    const int e = blockIdx.x;
+    __shared__ unsigned s_hist[TB_BINS + 1];
+    __shared__ unsigned s_fill[TB_BINS];
     __shared__ unsigned s_n;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
+    __shared__ unsigned s_warp[8];
+    const int e = blockIdx.x;
     const int64_t a = sa.offsets[e], b = sa.offsets[e + 1];
     const int64_t out0 = sa.row_offsets[e];
     const int n = (int)sa.kept[e];
     if (n == 0) return;
-    const bool in_smem = n <= SPYRAL_SMEM_ITEMS && !sa.keep_all;
-    uint64_t* keys = in_smem ? s_k : sa.sort_keys + a;
-    uint32_t* idx = in_smem ? s_v : sa.sort_idx + a;
     const double span = (double)(P.win_edge - P.mm_edge);
-    for (int64_t i = a + threadIdx.x; i < b && !sa.keep_all; i += blockDim.x) {
-        const double amp = fmin(__dmul_rn(P.resp_max, sa.cloud[i * 3 + 2]), 4095.0);
-        if (amp > P.adc_threshold) {
-            const unsigned pos = atomicAdd(&s_n, 1u);
-            // detector/writer.py:101-103: (window_edge - tb) / (window_edge - mm_edge) * length * 1000.0
-            const double z = __dmul_rn(
-                __dmul_rn(__ddiv_rn(__dsub_rn(P.win_edge, sa.cloud[i * 3 + 1]), span), P.length), 1000.0);
-            keys[pos] = orderable(z);
-            idx[pos] = (uint32_t)(i - a);
-        }
-    }
-    __syncthreads();
-    if (in_smem) {
-        int n2 = 1;
-        while (n2 < n) n2 <<= 1;
-        for (int i = n + threadIdx.x; i < n2; i += blockDim.x) {
-            keys[i] = ~0ULL;
-            idx[i] = 0xFFFFFFFFu;
-        }
+    const int64_t total = sa.offsets[sa.n_events];
+    uint64_t* stash_k = sa.sort_keys + a;           // unordered survivors
+    uint32_t* stash_v = sa.sort_idx + a;
+    const bool in_smem = n <= SPYRAL_SMEM_ITEMS;
+    uint64_t* keys = in_smem ? s_k : sa.sort_keys + total + a;  // ordered
+    uint32_t* idx = in_smem ? s_v : sa.sort_idx + total + a;
+    if (!sa.keep_all) {
+        for (int i = threadIdx.x; i <= TB_BINS; i += blockDim.x) s_hist[i] = 0;
+        if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
-        bitonic_sort_kv(keys, idx, n2);
-    }
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int rank = i;
-        const uint32_t id = sa.keep_all ? (uint32_t)i : idx[i];
-        if (!in_smem && !sa.keep_all) {  // very dense events: rank by counting against the L2-resident scratch
-            const uint64_t k = keys[i];
-            rank = 0;
-            for (int j = 0; j < n; ++j) {
-                const uint64_t kj = keys[j];
-                rank += (kj < k) || (kj == k && idx[j] < id);
+        for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
+            const double amp = fmin(__dmul_rn(P.resp_max, sa.cloud[i * 3 + 2]), 4095.0);
+            if (amp > P.adc_threshold) {
+                const double tbf = sa.cloud[i * 3 + 1];
+                // detector/writer.py:101-103: (window_edge - tb) / (window_edge - mm_edge) * length * 1000.0
+                const double z = __dmul_rn(__dmul_rn(__ddiv_rn(__dsub_rn(P.win_edge, tbf), span), P.length), 1000.0);
+                const unsigned pos = atomicAdd(&s_n, 1u);
+                stash_k[pos] = orderable(z);
+                stash_v[pos] = (uint32_t)(i - a);
+                const int tbi = min(max((int)tbf, 0), TB_BINS - 1);
+                atomicAdd(&s_hist[TB_BINS - 1 - tbi], 1u);
             }
         }
+        __syncthreads();
+        {
+            const int b0 = threadIdx.x * (TB_BINS / 256);
+            unsigned local[TB_BINS / 256], sum = 0;
+#pragma unroll
+            for (int k = 0; k < TB_BINS / 256; ++k) {
+                local[k] = s_hist[b0 + k];
+                sum += local[k];
+            }
+            unsigned incl = sum;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();
+            unsigned base = incl - sum;
+            for (int w = 0; w < warp; ++w) base += s_warp[w];
+#pragma unroll
+            for (int k = 0; k < TB_BINS / 256; ++k) {
+                s_hist[b0 + k] = base;
+                s_fill[b0 + k] = base;
+                base += local[k];
+            }
+            if (threadIdx.x == 255) s_hist[TB_BINS] = base;
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t id = stash_v[i];
+            const int tbi = min(max((int)sa.cloud[(a + id) * 3 + 1], 0), TB_BINS - 1);
+            const unsigned pos = atomicAdd(&s_fill[TB_BINS - 1 - tbi], 1u);
+            keys[pos] = stash_k[i];
+            idx[pos] = id;
+        }
+        __syncthreads();
+        for (int bin = threadIdx.x; bin < TB_BINS; bin += blockDim.x) {
+            const int lo = (int)s_hist[bin], hi = (int)s_hist[bin + 1];
+            for (int i = lo + 1; i < hi; ++i) {
+                const uint64_t kv = keys[i];
+                const uint32_t vv = idx[i];
+                int j = i - 1;
+                while (j >= lo && (keys[j] > kv || (keys[j] == kv && idx[j] > vv))) {
+                    keys[j + 1] = keys[j];
+                    idx[j + 1] = idx[j];
+                    --j;
+                }
+                keys[j + 1] = kv;
+                idx[j + 1] = vv;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t id = sa.keep_all ? (uint32_t)i : idx[i];
         const int64_t src = a + id;
         const double padf = sa.cloud[src * 3 + 0], tbf = sa.cloud[src * 3 + 1], el = sa.cloud[src * 3 + 2];
         const int pad = (int)padf;
         double amp, integral;
         shaped(P, el, amp, integral);
-        double* row = sa.rows + (out0 + rank) * 8;
+        double* row = sa.rows + (out0 + i) * 8;
         row[0] = P.pad_xy[2 * pad];
         row[1] = P.pad_xy[2 * pad + 1];
         row[2] = __dmul_rn(__dmul_rn(__ddiv_rn(__dsub_rn(P.win_edge, tbf), span), P.length), 1000.0);
@@ -946,7 +1005,7 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
         row[5] = padf;
         row[6] = tbf;
         row[7] = P.pad_scale[pad];
-        sa.row_labels[out0 + rank] = sa.labels[src];
+        sa.row_labels[out0 + i] = sa.labels[src];
     }
 }
 

@@ -71,7 +71,7 @@ def simulate_batch(
 
     ``momenta [B, K, 4]`` (px, py, pz, E in MeV), ``vertices [B, 3]`` (m).  Event ``e`` of the batch
     is global event ``first_event + e`` for the random streams.  Rows of each event come out in
-    ascending (time bucket, pad) pairing-key order (the reference's order is dict insertion order).
+    ascending (time bucket, pad) order (the reference's order is dict insertion order).
     """
     nmap = nuclear_data if nuclear_data is not None else nuclear_map
     momenta = np.asarray(momenta, dtype=np.float64)

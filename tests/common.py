@@ -73,6 +73,11 @@ def cloud_keys(cloud):
     return np.asarray(pair(np.floor(cloud[:, 1]).astype(np.int64), cloud[:, 0].astype(np.int64)), dtype=np.int64)
 
 
+def canonical_order(cloud):
+    """Row order of the CUDA path: ascending (time bucket, pad)."""
+    return np.lexsort((cloud[:, 0].astype(np.int64), np.floor(cloud[:, 1]).astype(np.int64)))
+
+
 def sort_cloud(cloud, labels):
-    order = np.argsort(cloud_keys(cloud), kind="stable")
+    order = canonical_order(cloud)
     return cloud[order], labels[order]

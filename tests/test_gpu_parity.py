@@ -7,6 +7,7 @@ UNMODIFIED reference (tests/golden/make_golden.py)."""
 import numpy as np
 import pytest
 
+from attpc_engine_b200.detector.pairing import unpair
 from tests.common import case_config, case_names, case_tracks, cloud_keys, nuclei_of, sort_cloud
 
 pytestmark = pytest.mark.gpu
@@ -44,7 +45,8 @@ def test_dict_keys_charges_labels(golden_events, name):
     ev = golden_events
     _, _, batch, _ = _replay(ev, name, keep_all_tb=True)
     cloud, labels = batch.event(0)
-    order = np.argsort(ev[f"{name}/keys"], kind="stable")
+    tb, pad = unpair(ev[f"{name}/keys"])
+    order = np.lexsort((pad, tb))  # canonical order of the CUDA path: ascending (time bucket, pad)
     want_keys = ev[f"{name}/keys"][order]
     assert np.array_equal(cloud_keys(cloud), want_keys)
     want_charge = ev[f"{name}/charges"][order].astype(np.float64)
