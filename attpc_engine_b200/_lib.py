@@ -100,6 +100,9 @@ class AttpcResult(C.Structure):
         ("n_retries", C.c_int32),
         ("n_track_launches", C.c_int32),
         ("n_group_launches", C.c_int32),
+        ("n_hash_probes", C.c_int64),
+        ("hash_capacity", C.c_int32),
+        ("reserved1", C.c_int32),
     ]
 
 

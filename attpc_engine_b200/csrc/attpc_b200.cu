@@ -59,6 +59,7 @@ struct PinnedArray {
         if (p) cudaFreeHost(p);
         p = nullptr;
         n = 0;
+        want += want / 4;  // pinning is slow (~0.5 s/GB): grow with slack so that it is rare
         cudaError_t e = cudaHostAlloc((void**)&p, (size_t)want * sizeof(T), cudaHostAllocDefault);
         if (e == cudaSuccess) n = want;
         return e;
@@ -89,7 +90,7 @@ struct AttpcSim {
     // sizing
     int32_t launch_events = 32768;
     int32_t group_events = 512;
-    int32_t hash_cap = 8192;
+    int32_t hash_cap = 16384;
     int64_t group_point_cap = 0;
 
     // work buffers
@@ -457,9 +458,10 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     const bool copy_host = !(flags & ATTPC_SKIP_HOST_COPY);
     cudaEvent_t t_d2h0 = sim->mark();
     if (copy_host) {
-        CU(sim->offsets_host.reserve(n_events + 1));
-        CU(sim->cloud_host.reserve(std::max<int64_t>(1, n_points) * 3));
-        CU(sim->labels_host.reserve(std::max<int64_t>(1, n_points)));
+        // pinned mirrors are sized like the device buffers so that they are (re)allocated only when those grow
+        CU(sim->offsets_host.reserve(sim->offsets_dev.n));
+        CU(sim->cloud_host.reserve(sim->cloud_dev.n));
+        CU(sim->labels_host.reserve(sim->labels_dev.n));
         CU(cudaMemcpyAsync(sim->offsets_host.p, sim->offsets_dev.p, (size_t)(n_events + 1) * sizeof(int64_t),
                            cudaMemcpyDeviceToHost, sim->stream));
         if (n_points > 0) {
@@ -489,6 +491,8 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     res->n_kernel_launches = sim->launches;
     res->n_track_launches = (int32_t)trk_marks.size();
     res->n_group_launches = (int32_t)dep_marks.size();
+    res->n_hash_probes = (int64_t)snapshot.probes;
+    res->hash_capacity = sim->hash_cap;
     return ATTPC_OK;
 }
 
@@ -656,6 +660,31 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
             P.sp[s].qm_c = (double)species[s].z * E_CHARGE / mass_kg / C_LIGHT;
             P.sp[s].z = species[s].z;
             P.sp[s].table = s * P.n_nodes;
+            // terminal drift energy: first table node where the drag reaches the field acceleration |q E / (m c)|
+            {
+                const double field = std::fabs(P.sp[s].qm_c * P.E);
+                const double* t = &scaled[(size_t)s * P.n_nodes];
+                const int per_oct = 1 << P.lm;
+                double ke_eq = 0.0;
+                if (field > 0.0) {
+                    const double ke0 = std::ldexp(1.0, P.e_min);
+                    if (t[0] >= field) {  // below the table: drag = t[0] sqrt(ke / ke0)
+                        ke_eq = t[0] > 0.0 ? ke0 * (field / t[0]) * (field / t[0]) : 0.0;
+                    } else {
+                        for (int i = 1; i < P.n_nodes; ++i) {
+                            if (t[i] >= field) {
+                                auto node = [&](int j) {
+                                    return std::ldexp(1.0 + (double)(j % per_oct) / per_oct, P.e_min + j / per_oct);
+                                };
+                                const double f = (field - t[i - 1]) / (t[i] - t[i - 1]);
+                                ke_eq = node(i - 1) + f * (node(i) - node(i - 1));
+                                break;
+                            }
+                        }
+                    }
+                }
+                P.sp[s].ke_eq = ke_eq;
+            }
         }
         CUC(sim->tables.reserve(std::max<int64_t>(1, (int64_t)scaled.size())));
         if (!scaled.empty())

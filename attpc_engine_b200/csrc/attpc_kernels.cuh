@@ -38,6 +38,7 @@ struct SpeciesDev {
     double qm_c;     // Z e / (m_kg c)  [1/(T s)]
     int32_t z;
     int32_t table;   // offset (in doubles) of this species' deceleration table
+    double ke_eq;    // kinetic energy [MeV] of the terminal drift along the field: drag(ke_eq) == q E / m
 };
 
 // Scalars every kernel reads; passed by value as a __grid_constant__ parameter.
@@ -77,7 +78,7 @@ struct PointBuf {
 
 struct Counters {
     unsigned long long track_cursor;
-    unsigned long long traj_points, active_points, primary_electrons, deposits, keys;
+    unsigned long long traj_points, active_points, primary_electrons, deposits, keys, probes;
     unsigned long long out_points, out_rows;   // running CSR totals
     int overflow_points, overflow_hash, overflow_out, replay_miss;
 };
@@ -126,8 +127,24 @@ struct State {
 
 struct TrackConst {
     double mass, qmB, qmE;  // qm_c * B, qm_c * E
+    double ke_eq;
     TableView tab;
 };
+
+// Can this ion still make an electron?  (Production-only shortcut; the reference integrates a stalled ion to 1 us
+// and throws those rows away at detector/solver.py:387.)  A stopped ion relaxes to a drift along the field with
+// kinetic energy ke_eq: the transverse motion only decays and, once the ion already moves in the drift direction, the
+// parallel motion approaches the drift speed monotonically.  The total variation left in KE is then at most
+// KE_perp + |KE_par - ke_eq|; if twice that cannot give one grid step the `budget` = n* W needed for
+// int(n + sqrt(F n) z) >= 1 with |z| <= NORMAL_ABS_MAX, every later row has zero electrons.
+__device__ __forceinline__ bool inert_forever(const TrackConst& c, const State& s, double ke, double budget) {
+    if (!(budget > 0.0)) return false;
+    if (c.qmE == 0.0) return ke < budget;  // no field to re-accelerate the ion
+    if (!(s.uz * c.qmE > 0.0)) return false;
+    const double k_par = 0.5 * c.mass * s.uz * s.uz;
+    const double k_perp = 0.5 * c.mass * (s.ux * s.ux + s.uy * s.uy);
+    return 2.0 * (k_perp + fabs(k_par - c.ke_eq)) < budget;
+}
 
 __device__ __forceinline__ double kinetic_energy(const TrackConst& c, double ux, double uy, double uz) {
     const double g2 = ux * ux + uy * uy + uz * uz;
@@ -160,9 +177,15 @@ __device__ __forceinline__ State rhs(const TrackConst& c, const State& s) {
     dst.uy = base.uy + (h) * (expr(uy));    \
     dst.uz = base.uz + (h) * (expr(uz));
 
+// Coefficients of the 4th-order continuous extension of the step (Shampine's interpolant, the one scipy's RK45
+// uses): y(t0 + theta h) = y0 + h theta (q0 + theta (q1 + theta (q2 + theta q3))).
+struct Dense {
+    State q0, q1, q2, q3;
+};
+
 // One Dormand-Prince 5(4) step of size h from (y, k1 = f(y)).  Returns the scaled RMS error (<= 1 accepts).
 __device__ __forceinline__ double dopri5_step(const TrackConst& c, const State& y, const State& k1, double h,
-                                              double rtol, double atol, State& ynew, State& knew) {
+                                              double rtol, double atol, State& ynew, State& knew, Dense& dense) {
     State t, k2, k3, k4, k5, k6;
 #define E2(f) (0.2 * k1.f)
     ATTPC_COMBINE(t, y, h, E2)
@@ -196,6 +219,28 @@ __device__ __forceinline__ double dopri5_step(const TrackConst& c, const State& 
         acc += e * e;                                                           \
     }
     ERRTERM(x) ERRTERM(y) ERRTERM(z) ERRTERM(ux) ERRTERM(uy) ERRTERM(uz)
+    // dense-output polynomial: q_j = sum_i k_i P[i][j]  (P of scipy/integrate/_ivp/rk.py: RK45.P; row 2 is zero)
+#define Q0(f) (k1.f)
+#define Q1(f)                                                                                                       \
+    (-8048581381.0 / 2820520608.0 * k1.f + 131558114200.0 / 32700410799.0 * k3.f - 1754552775.0 / 470086768.0 * k4.f + \
+     127303824393.0 / 49829197408.0 * k5.f - 282668133.0 / 205662961.0 * k6.f + 40617522.0 / 29380423.0 * knew.f)
+#define Q2(f)                                                                                                        \
+    (8663915743.0 / 2820520608.0 * k1.f - 68118460800.0 / 10900136933.0 * k3.f + 14199869525.0 / 1410260304.0 * k4.f - \
+     318862633887.0 / 49829197408.0 * k5.f + 2019193451.0 / 616988883.0 * k6.f - 110615467.0 / 29380423.0 * knew.f)
+#define Q3(f)                                                                                                          \
+    (-12715105075.0 / 11282082432.0 * k1.f + 87487479700.0 / 32700410799.0 * k3.f - 10690763975.0 / 1880347072.0 * k4.f + \
+     701980252875.0 / 199316789632.0 * k5.f - 1453857185.0 / 822651844.0 * k6.f + 69997945.0 / 29380423.0 * knew.f)
+#define SETQ(f)           \
+    dense.q0.f = Q0(f);   \
+    dense.q1.f = Q1(f);   \
+    dense.q2.f = Q2(f);   \
+    dense.q3.f = Q3(f);
+    SETQ(x) SETQ(y) SETQ(z) SETQ(ux) SETQ(uy) SETQ(uz)
+#undef Q0
+#undef Q1
+#undef Q2
+#undef Q3
+#undef SETQ
 #undef E2
 #undef E3
 #undef E4
@@ -207,33 +252,21 @@ __device__ __forceinline__ double dopri5_step(const TrackConst& c, const State& 
     return sqrt(acc * (1.0 / 6.0));
 }
 
-// Advance one 0.1 ns grid cell with error-controlled sub-steps (nsub halves/doubles adaptively).
-__device__ __forceinline__ void advance_cell(const TrackConst& c, State& y, State& k, int& nsub, double rtol,
-                                             double atol) {
-    const State y0 = y, k0 = k;
-    while (true) {
-        const double h = GRID_DT / (double)nsub;
-        bool ok = true;
-        double worst = 0.0;
-        for (int s = 0; s < nsub; ++s) {
-            State yn, kn;
-            const double err = dopri5_step(c, y, k, h, rtol, atol, yn, kn);
-            if (!(err <= 1.0) && nsub < 4096) {
-                ok = false;
-                break;
-            }
-            worst = fmax(worst, err);
-            y = yn;
-            k = kn;
-        }
-        if (ok) {
-            if (nsub > 1 && worst < 0.01) nsub >>= 1;
-            return;
-        }
-        nsub <<= 1;
-        y = y0;
-        k = k0;
-    }
+__device__ __forceinline__ State dense_eval(const State& y0, const Dense& d, double h, double theta) {
+    State r;
+    const double ht = h * theta;
+#define DE(f) r.f = fma(ht, fma(theta, fma(theta, fma(theta, d.q3.f, d.q2.f), d.q1.f), d.q0.f), y0.f);
+    DE(x) DE(y) DE(z) DE(ux) DE(uy) DE(uz)
+#undef DE
+    return r;
+}
+
+constexpr double MAX_STEP_CELLS = 64.0;  // a step never spans more than 64 grid cells (6.4 ns)
+
+// Standard step-size controller of an order-5 pair: factor = 0.9 err^(-1/5), limited to [0.2, 5].
+__device__ __forceinline__ double step_factor(double err) {
+    if (!(err > 1e-10)) return 5.0;
+    return fmin(5.0, fmax(0.2, 0.9 * exp(-0.2 * log(err))));
 }
 
 // scipy's event rule (scipy/integrate/_ivp/ivp.py: find_active_events) applied per grid cell, with the
@@ -307,9 +340,10 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
 
     bool have = false, done = false;
     TrackConst c;
-    State y, k;
-    double ke = 0.0;
-    int step = 0, nsub = 1, ev = 0, rank = 0, nucleus = 0;
+    State y, k, y_grid;          // integrator state at time tc, its derivative, state at the last grid point
+    double ke = 0.0;             // kinetic energy at the last grid point
+    double tc = 0.0, hc = 1.0;   // time and step size in units of grid cells (0.1 ns)
+    int step = 0, ev = 0, rank = 0, nucleus = 0;
     int64_t track = 0;
     unsigned long long n_traj = 0, n_active = 0, n_prim = 0;
 
@@ -330,6 +364,7 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
                     c.mass = S.mass;
                     c.qmB = S.qm_c * P.B;
                     c.qmE = S.qm_c * P.E;
+                    c.ke_eq = S.ke_eq;
                     c.tab = make_table_view(P, tab_base + S.table);
                     y.x = vx[0];
                     y.y = vx[1];
@@ -338,9 +373,11 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
                     y.uy = m4[1] / S.mass;
                     y.uz = m4[2] / S.mass;
                     k = rhs(c, y);
+                    y_grid = y;
                     ke = kinetic_energy(c, y.ux, y.uy, y.uz);
                     step = 0;
-                    nsub = 1;
+                    tc = 0.0;
+                    hc = 1.0;
                     have = true;
                     n_traj += 1;  // grid point 0 (never active: detector/solver.py:338-339)
                     if (RECORD && tb.rec_max > 0) {
@@ -353,51 +390,64 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
             }
         }
         if (__all_sync(FULL, done)) break;
+        if (!have) continue;
 
-        bool emit = false;
-        double ex = 0.0, ey = 0.0, et = 0.0;
-        long long eq = 0;
-        if (have) {
-            const State y_prev = y;
-            const double ke_prev = ke;
-            advance_cell(c, y, k, nsub, P.rtol, P.atol);
-            ke = kinetic_energy(c, y.ux, y.uy, y.uz);
-            bool finished = terminal_event(c, y_prev, y, ke_prev, ke);
-            if (!finished) {
-                step += 1;
-                n_traj += 1;
-                if (RECORD) {
-                    if (step % tb.rec_stride == 0 && step / tb.rec_stride < tb.rec_max) {
-                        double* o = tb.rec_points + ((int64_t)track * tb.rec_max + step / tb.rec_stride) * 6;
-                        o[0] = y.x; o[1] = y.y; o[2] = y.z; o[3] = y.ux; o[4] = y.uy; o[5] = y.uz;
-                    }
-                } else {
-                    // detector/solver.py:338-346: mean = |dKE| / W, Gaussian with variance F * mean, truncation
-                    const double mean = fabs(ke - ke_prev) * P.ev_per_w;
-                    const double spread = sqrt(P.fano * mean);
-                    if (mean + spread * NORMAL_ABS_MAX >= 1.0) {
-                        const double zn = philox_normal(tb.seed, (uint64_t)(tb.first_event + ev), (uint32_t)nucleus,
-                                                        (uint32_t)step);
-                        const long long n_e = (long long)(mean + spread * zn);
-                        if (n_e >= 1) {  // detector/solver.py:387
-                            emit = true;
-                            ex = y.x;
-                            ey = y.y;
-                            et = (P.length - y.z) / P.dv + P.mm_edge;  // detector/solver.py:396-398
-                            eq = n_e * P.gain;                          // detector/solver.py:392
-                            n_active += 1;
-                            n_prim += (unsigned long long)n_e;
-                        }
+        // one Dormand-Prince attempt of hc grid cells from tc
+        State yn, kn;
+        Dense dense;
+        const double h = hc * GRID_DT;
+        const double err = dopri5_step(c, y, k, h, P.rtol, P.atol, yn, kn, dense);
+        if (!(err <= 1.0) && hc > 1.0 / 4096.0) {  // reject: retry with a smaller step
+            hc *= (err == err) ? fmin(0.9, step_factor(err)) : 0.2;
+            continue;
+        }
+        // accepted: emit every grid point inside (tc, tc + hc]
+        const double t_end = tc + hc;
+        bool finished = false;
+        while (!finished && (double)(step + 1) <= t_end + 1e-9) {
+            const double theta = fmin(1.0, ((double)(step + 1) - tc) / hc);
+            const State g = theta >= 1.0 ? yn : dense_eval(y, dense, h, theta);
+            const double ke_g = kinetic_energy(c, g.ux, g.uy, g.uz);
+            if (terminal_event(c, y_grid, g, ke, ke_g)) {
+                finished = true;
+                break;
+            }
+            step += 1;
+            n_traj += 1;
+            if (RECORD) {
+                if (step % tb.rec_stride == 0 && step / tb.rec_stride < tb.rec_max) {
+                    double* o = tb.rec_points + ((int64_t)track * tb.rec_max + step / tb.rec_stride) * 6;
+                    o[0] = g.x; o[1] = g.y; o[2] = g.z; o[3] = g.ux; o[4] = g.uy; o[5] = g.uz;
+                }
+            } else {
+                // detector/solver.py:338-346: mean = |dKE| / W, Gaussian with variance F * mean, truncation
+                const double mean = fabs(ke_g - ke) * P.ev_per_w;
+                const double spread = sqrt(P.fano * mean);
+                if (mean + spread * NORMAL_ABS_MAX >= 1.0) {
+                    const double zn =
+                        philox_normal(tb.seed, (uint64_t)(tb.first_event + ev), (uint32_t)nucleus, (uint32_t)step);
+                    const long long n_e = (long long)(mean + spread * zn);
+                    if (n_e >= 1) {  // detector/solver.py:387
+                        const double time = (P.length - g.z) / P.dv + P.mm_edge;  // detector/solver.py:396-398
+                        append_point(pb, ctr, true, ev, rank, g.x, g.y, time, n_e * P.gain);  // gain: solver.py:392
+                        n_active += 1;
+                        n_prim += (unsigned long long)n_e;
                     }
                 }
-                if (step >= GRID_POINTS - 1 || ke < P.freeze_ke) finished = true;
             }
-            if (finished) {
-                have = false;
-                if (RECORD) tb.rec_counts[track] = step + 1;
-            }
+            y_grid = g;
+            ke = ke_g;
+            if (step >= GRID_POINTS - 1 || inert_forever(c, g, ke, P.freeze_ke)) finished = true;
         }
-        if (!RECORD) append_point(pb, ctr, emit, ev, rank, ex, ey, et, eq);
+        if (finished) {
+            have = false;
+            if (RECORD) tb.rec_counts[track] = step + 1;
+        } else {
+            tc = t_end;
+            y = yn;
+            k = kn;
+            hc = fmin(MAX_STEP_CELLS, hc * step_factor(err));
+        }
     }
     // per-warp statistics
     for (int o = 16; o > 0; o >>= 1) {
@@ -510,15 +560,17 @@ __device__ __forceinline__ void szudzik_unpair(unsigned key, unsigned& tb, unsig
 }
 
 // ------------------------------------------------------------------------------------------------- accumulate
+constexpr unsigned MAX_PROBES = 512u;
 __device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) { return (key * 2654435761u >> 7) & mask; }
 
 // points[id] = (charge + q, label) of detector/transporter.py:166-169, 247-249: integer adds commute and the label
 // is "last track in indices order", i.e. the maximum rank, so the result does not depend on thread order.
-__device__ __forceinline__ void table_add(HashEntry* tab, unsigned mask, unsigned key, long long q, unsigned rank,
-                                          Counters* ctr) {
+__device__ __forceinline__ unsigned table_add(HashEntry* tab, unsigned mask, unsigned key, long long q, unsigned rank,
+                                              Counters* ctr) {
     const unsigned key1 = key + 1u;
     unsigned slot = hash_slot(key, mask);
-    for (unsigned probe = 0; probe <= mask; ++probe) {
+    const unsigned max_probe = min(mask, MAX_PROBES - 1u);  // a longer chain means the table is too full: grow it
+    for (unsigned probe = 0; probe <= max_probe; ++probe) {
         unsigned k = __ldcg(&tab[slot].key1);
         if (k == 0u) {
             k = atomicCAS(&tab[slot].key1, 0u, key1);
@@ -527,11 +579,12 @@ __device__ __forceinline__ void table_add(HashEntry* tab, unsigned mask, unsigne
         if (k == key1) {
             if (q != 0) atomicAdd(&tab[slot].charge, (unsigned long long)q);
             if (__ldcg(&tab[slot].rank) < rank) atomicMax(&tab[slot].rank, rank);
-            return;
+            return probe + 1u;
         }
         slot = (slot + 1u) & mask;
     }
     ctr->overflow_hash = 1;
+    return max_probe + 1u;
 }
 
 struct GroupView {
@@ -553,9 +606,10 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
     const int64_t n_points = min((int64_t)pb.count[gv.group], pb.group_cap);
     const int64_t base = (int64_t)gv.group * pb.group_cap;
     const unsigned mask = (unsigned)gv.hash_cap - 1u;
-    unsigned long long n_dep = 0;
+    unsigned long long n_dep = 0, n_probe = 0;
 
     for (int64_t p = warp; p < n_points; p += n_warps) {
+        if (*(volatile int*)&ctr->overflow_hash) break;  // the host will redo the launch with bigger tables
         const double cx = pb.x[base + p], cy = pb.y[base + p], time = pb.t[base + p];
         const long long q = pb.q[base + p];
         const int ev = pb.ev[base + p] - gv.first_slot;
@@ -570,7 +624,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
             if (lane == 0) {
                 const int pad = lookup_pad(P, cx, cy);
                 if (pad >= 0) {
-                    table_add(tab, mask, szudzik_pair((unsigned)tb, (unsigned)pad), q, rank, ctr);
+                    n_probe += table_add(tab, mask, szudzik_pair((unsigned)tb, (unsigned)pad), q, rank, ctr);
                     n_dep += 1;
                 }
             }
@@ -602,12 +656,18 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
             const double arg = __dmul_rn(c2, __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
             const double pdf = __dmul_rn(norm, exp(arg));
             const long long share = (long long)__dmul_rn(__dmul_rn(pdf, cell2), qd);
-            table_add(tab, mask, szudzik_pair((unsigned)tb, (unsigned)pad), share, rank, ctr);
+            n_probe += table_add(tab, mask, szudzik_pair((unsigned)tb, (unsigned)pad), share, rank, ctr);
             n_dep += 1;
         }
     }
-    for (int o = 16; o > 0; o >>= 1) n_dep += __shfl_xor_sync(FULL, n_dep, o);
-    if (lane == 0 && n_dep) atomicAdd(&ctr->deposits, n_dep);
+    for (int o = 16; o > 0; o >>= 1) {
+        n_dep += __shfl_xor_sync(FULL, n_dep, o);
+        n_probe += __shfl_xor_sync(FULL, n_probe, o);
+    }
+    if (lane == 0 && n_dep) {
+        atomicAdd(&ctr->deposits, n_dep);
+        atomicAdd(&ctr->probes, n_probe);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------- finalize

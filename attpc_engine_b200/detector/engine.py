@@ -48,13 +48,14 @@ def build_pad_lut(pad_grid: np.ndarray, edges: np.ndarray) -> tuple[np.ndarray, 
 
 
 def default_freeze_ke(fano_factor: float, w_value: float, z_abs_max: float = 8.66) -> float:
-    """KE [MeV] below which a track can no longer make an electron.
+    """Energy budget [MeV] below which a grid step can no longer make an electron.
 
-    A grid step produces ``int(n + sqrt(F n) z)`` electrons with ``n = dKE / W``
-    (`solver.py:338-346`) and the device's Box-Muller normal is bounded by ``z_abs_max``.
-    Even if the whole remaining KE went into one step, ``n + sqrt(F n) z_max < 1`` holds for
-    ``n < n*``; the integrator stops once KE < n* W.  The reference instead integrates the
-    stalled ion to 1 us and discards those rows at `solver.py:387`.
+    A grid step produces ``int(n + sqrt(F n) z)`` electrons with ``n = |dKE| / W``
+    (`solver.py:338-346`) and the device's Box-Muller normal is bounded by ``z_abs_max``, so
+    ``n + sqrt(F n) z_max < 1`` for ``n < n*``.  The integrator ends a track once the kinetic
+    energy it can still gain or lose while relaxing to its terminal drift is below ``n* W``
+    (`csrc/attpc_kernels.cuh: inert_forever`).  The reference instead integrates the stalled ion
+    to 1 us and discards those rows at `solver.py:387`.
     """
     a = math.sqrt(max(fano_factor, 0.0)) * z_abs_max
     root = (-a + math.sqrt(a * a + 4.0)) / 2.0  # sqrt(n*) solves n + a sqrt(n) = 1
@@ -93,7 +94,7 @@ def _ptr(arr: np.ndarray, ctype):
 _STAT_FIELDS = (
     "n_tracks", "n_trajectory_points", "n_active_points", "n_primary_electrons", "n_deposits", "n_keys",
     "ms_h2d", "ms_tracks", "ms_deposit", "ms_finalize", "ms_d2h", "ms_total", "n_kernel_launches", "n_retries",
-    "n_track_launches", "n_group_launches",
+    "n_track_launches", "n_group_launches", "n_hash_probes", "hash_capacity",
 )  # fmt: skip
 
 

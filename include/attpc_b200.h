@@ -60,7 +60,8 @@ typedef struct AttpcConfig {
     /* integrator controls (no counterpart in the reference, which uses scipy Radau defaults) */
     double ode_rtol;
     double ode_atol;
-    double freeze_ke_mev;   /* stop a track once KE < this (0 = integrate to 1 us like the reference) */
+    double freeze_ke_mev;   /* energy budget n* W [MeV] of the "can never make another electron" test that ends a
+                               stalled track early (0 = integrate to 1 us like the reference) */
     /* capacities (0 = library default); they grow automatically on overflow */
     int32_t max_events_per_launch;
     int32_t hash_capacity;          /* slots per event, power of two */
@@ -116,6 +117,9 @@ typedef struct AttpcResult {
     int32_t n_retries;           /* capacity retries that happened inside the call */
     int32_t n_track_launches;    /* launches of the track (or replay) kernel */
     int32_t n_group_launches;    /* launches of the deposit kernel (= event groups processed) */
+    int64_t n_hash_probes;       /* table slots inspected by the deposits (n_hash_probes / n_deposits ~ 1 is healthy) */
+    int32_t hash_capacity;       /* slots per event in use at the end of the call */
+    int32_t reserved1;
 } AttpcResult;
 
 typedef struct AttpcSim AttpcSim;
