@@ -1,0 +1,188 @@
+"""GPU tests of the public surface: simulate / simulate_batch / run_simulation / writers, sharding invariance,
+Spyral conversion against the oracle, and the statistical half of parity part (b) (KS tests against distribution
+samples of the unmodified reference, tests/golden/make_distributions.py)."""
+
+import sys
+import types
+
+import numpy as np
+import pytest
+from scipy.stats import ks_2samp
+
+from attpc_engine_b200 import nuclear_map
+from attpc_engine_b200.detector import ArrayWriter, SpyralWriter, convert_to_spyral, run_simulation, simulate, simulate_batch
+from attpc_engine_b200.detector.sharding import concat_batches, shard_range
+from oracle import attpc_oracle as oracle
+from tests.common import case_config, load_golden, make_config
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dist():
+    return load_golden("distributions.npz")
+
+
+def _workload(dist, name, n=None):
+    cfg = make_config("He4_600" if name == "c12aa" else "D2_600")
+    m, v = dist[f"{name}/momenta"], dist[f"{name}/vertices"]
+    n = len(m) if n is None else n
+    return cfg, m[:n], v[:n], dist[f"{name}/Z"], dist[f"{name}/A"], list(dist[f"{name}/indices"])
+
+
+def test_simulate_reference_signature(golden_events):
+    """`simulate(momenta, vertex, Z, A, config, rng, indices)` -> (cloud [N,3], labels [N]) like the reference."""
+    ev, name = golden_events, "dd_exit"
+    cfg = case_config(name)
+    event = simulate(ev[f"{name}/momenta"], ev[f"{name}/vertex"], ev[f"{name}/Z"], ev[f"{name}/A"], cfg,
+                     np.random.default_rng(3), list(ev[f"{name}/indices"]))  # fmt: skip
+    assert len(event) == 2
+    cloud, labels = event
+    assert cloud.ndim == 2 and cloud.shape[1] == 3 and labels.shape == (len(cloud),) and labels.dtype == np.int64
+    assert len(cloud) > 500 and set(np.unique(labels)) <= {2, 3}
+    assert np.all((cloud[:, 1] >= 0) & (cloud[:, 1] < 512)) and np.all(cloud[:, 0] == np.floor(cloud[:, 0]))
+    assert np.all(cloud[:, 2] % 1 == 0)
+
+
+def test_reference_smoke_case_outside_detector():
+    """The reference's own detector test (tests/test_detector.py:44-63): protons far outside -> empty 2-tuple."""
+    cfg = make_config(bfield=2.85)
+    fake = np.array([[0.0, 0.0, 10.0, 938.0]] * 4)
+    event = simulate(fake, np.array([1.0, 1.0, 1.0]), np.array([1, 1, 1, 1]), np.array([1, 1, 1, 1]), cfg,
+                     np.random.default_rng(), [0])  # fmt: skip
+    assert len(event) == 2 and len(event[0]) == 0 and len(event[1]) == 0
+
+
+def test_results_do_not_depend_on_batching(dist):
+    """Counter-based streams: splitting a batch (as the multi-GPU shards do) reproduces it bit for bit."""
+    cfg, m, v, zs, as_, idx = _workload(dist, "c16dd", 96)
+    whole = simulate_batch(m, v, zs, as_, cfg, 77, idx, first_event=1000)
+    parts = []
+    for rank in range(3):
+        a, b = shard_range(len(m), rank, 3)
+        parts.append(simulate_batch(m[a:b], v[a:b], zs, as_, cfg, 77, idx, first_event=1000 + a))
+    merged = concat_batches(parts)
+    assert np.array_equal(whole.offsets, merged.offsets)
+    assert np.array_equal(whole.cloud, merged.cloud) and np.array_equal(whole.labels, merged.labels)
+    other_seed = simulate_batch(m, v, zs, as_, cfg, 78, idx, first_event=1000)
+    assert not np.array_equal(whole.cloud[:, 1], other_seed.cloud[: len(whole.cloud), 1])
+
+
+def test_small_launches_and_small_tables_give_identical_results(dist):
+    """Capacity retries (hash tables, point buffers) and launch splitting are invisible in the output."""
+    cfg, m, v, zs, as_, idx = _workload(dist, "c16dd", 64)
+    base = simulate_batch(m, v, zs, as_, cfg, 5, idx)
+    tiny = simulate_batch(m, v, zs, as_, cfg, 5, idx, max_events_per_launch=24, hash_capacity=256)
+    assert tiny.stats["n_retries"] >= 1
+    assert np.array_equal(base.offsets, tiny.offsets) and np.array_equal(base.cloud, tiny.cloud)
+    assert np.array_equal(base.labels, tiny.labels)
+
+
+def test_convert_to_spyral_function_matches_oracle(golden_events):
+    ev, name = golden_events, "alpha_breakup"
+    cfg = case_config(name)
+    cloud = ev[f"{name}/cloud"]
+    resp = oracle.get_response(cfg)
+    got = convert_to_spyral(cloud, cfg.elec_params.windows_edge, cfg.elec_params.micromegas_edge, cfg.det_params.length,
+                            resp, cfg.pad_centers, cfg.pad_sizes)  # fmt: skip
+    want = oracle.spyral_rows(cloud, cfg.elec_params.windows_edge, cfg.elec_params.micromegas_edge,
+                              cfg.det_params.length, resp, cfg.pad_centers, cfg.pad_sizes)  # fmt: skip
+    assert got.shape == want.shape
+    for col in (0, 1, 2, 3, 5, 6, 7):
+        assert np.array_equal(got[:, col], want[:, col])
+    assert np.allclose(got[:, 4], want[:, 4], rtol=1e-12, atol=0)
+
+
+def test_run_simulation_with_array_writer(dist, tmp_path):
+    """run_simulation over an .npz kinematics file, batched writer hook, Spyral rows from the GPU."""
+    from attpc_engine_b200.kinematics import save_kinematics_npz
+
+    cfg, m, v, zs, as_, idx = _workload(dist, "c16dd", 40)
+    path = tmp_path / "kin.npz"
+    save_kinematics_npz(path, v, m, zs, as_)
+    writer = ArrayWriter(None, cfg, max_events_per_file=25)
+    run_simulation(cfg, path, writer, seed=9, batch_size=16, verbose=False)
+    direct = simulate_batch(m, v, zs, as_, cfg, 9, idx, spyral_rows=True)
+    non_empty = np.nonzero(np.diff(direct.offsets) > 0)[0]  # empty clouds are skipped (`simulator.py:204`)
+    assert len(non_empty) >= 30
+    assert [len(f["event_numbers"]) for f in writer.files] == [25, len(non_empty) - 25]
+    numbers = np.concatenate([f["event_numbers"] for f in writer.files])
+    assert np.array_equal(numbers, non_empty)
+    rows = np.concatenate([f["rows"] for f in writer.files])
+    assert np.array_equal(rows, direct.rows)
+    assert np.all(rows[:, 3] > cfg.elec_params.adc_threshold)
+
+    class PerEvent:  # a user writer that only knows the reference's protocol
+        def __init__(self):
+            self.seen, self.closed = [], False
+
+        def write(self, data, labels, config, event_number):
+            self.seen.append((event_number, data, labels))
+
+        def get_directory_name(self):
+            return tmp_path
+
+        def close(self):
+            self.closed = True
+
+    w = PerEvent()
+    run_simulation(cfg, path, w, seed=9, batch_size=16, verbose=False)
+    assert w.closed and [s[0] for s in w.seen] == list(non_empty)
+    assert np.array_equal(np.concatenate([s[1] for s in w.seen]), direct.cloud)
+
+
+def test_spyral_writer_layout_through_h5py_stand_in(dist, monkeypatch, tmp_path):
+    """File layout of the reference's SpyralWriter (writer.py:164-281), with h5py replaced by an in-memory fake."""
+    sys.path.insert(0, str((__import__("pathlib").Path(__file__).parent / "golden")))
+    import ref_shim
+
+    fake = types.ModuleType("h5py")
+    fake.File, fake.Group, fake.Dataset = ref_shim.MemFile, ref_shim.MemGroup, ref_shim.MemDataset
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    ref_shim.MemFile.opened.clear()
+    cfg, m, v, zs, as_, idx = _workload(dist, "c16dd", 12)
+    writer = SpyralWriter(tmp_path, cfg, max_events_per_file=5)
+    batch = simulate_batch(m, v, zs, as_, cfg, 4, idx, spyral_rows=True)
+    for e in range(len(batch)):  # reference protocol: one write per event
+        cloud, labels = batch.event(e)
+        writer.write(cloud, labels, cfg, e)
+    writer.close()
+    files = ref_shim.MemFile.opened
+    assert [str(f.path).rsplit("/", 1)[1] for f in files] == ["run_0000.h5", "run_0001.h5", "run_0002.h5"]
+    assert all(f.closed for f in files)
+    assert [(f["cloud"].attrs["min_event"], f["cloud"].attrs["max_event"]) for f in files] == [(0, 4), (5, 9), (10, 11)]
+    d = files[1]["cloud"]["cloud_7"]
+    rows, labels = batch.event_rows(7)
+    assert np.array_equal(d.data, rows) and np.array_equal(files[1]["cloud"]["labels_7"].data, labels)
+    assert d.attrs["orig_run"] == 1 and d.attrs["orig_event"] == 7 and d.attrs["ic_amplitude"] == -1.0
+
+
+@pytest.mark.parametrize("name", ["c16dd", "c12aa"])
+def test_distributions_match_reference(dist, name):
+    """KS tests at p > 0.01 against the unmodified reference run on the same kinematics (north_star part (b))."""
+    cfg, m, v, zs, as_, idx = _workload(dist, name)
+    batch = simulate_batch(m, v, zs, as_, cfg, 20261018, idx)
+    n = np.diff(batch.offsets).astype(np.float64)
+    sums = np.add.reduceat(batch.cloud[:, 2], batch.offsets[:-1][n > 0])
+    ext, pads, med, mx, one = [], [], [], [], []
+    picker = np.random.default_rng(2)
+    for e in range(len(batch)):
+        c, _ = batch.event(e)
+        ext.append(c[:, 1].max() - c[:, 1].min() if len(c) else 0.0)
+        pads.append(len(np.unique(c[:, 0])))
+        med.append(np.median(c[:, 2]) if len(c) else 0.0)
+        mx.append(c[:, 2].max() if len(c) else 0.0)
+        if len(c):  # one random point per event: points of one event are correlated, events are not
+            one.append(c[picker.integers(len(c)), 2])
+    checks = {
+        "points per event": (n, dist[f"{name}/n_points"]),
+        "charge per event": (sums, dist[f"{name}/sum_charge"][dist[f"{name}/n_points"] > 0]),
+        "time-bucket extent": (np.array(ext), dist[f"{name}/tb_extent"]),
+        "pads per event": (np.array(pads, dtype=np.float64), dist[f"{name}/n_pads"]),
+        "median point charge per event": (np.array(med), dist[f"{name}/median_charge"]),
+        "max point charge per event": (np.array(mx), dist[f"{name}/max_charge"]),
+        "charge per point (one point per event)": (np.array(one), dist[f"{name}/point_charge_sample"]),
+    }
+    for label, (ours, ref) in checks.items():
+        p = ks_2samp(ours, ref).pvalue
+        assert p > 0.01, f"{name}: {label}: KS p = {p:.4f}"

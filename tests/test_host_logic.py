@@ -1,0 +1,159 @@
+"""CPU tests of the host side: C-ABI surface, device-constant baking, mirrors of the reference's helpers."""
+
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from attpc_engine_b200 import _lib, nuclear_map
+from attpc_engine_b200.detector import pairing
+from attpc_engine_b200.detector.beam_pads import BEAM_PADS
+from attpc_engine_b200.detector.engine import SimBatch, build_pad_lut, default_freeze_ke
+from attpc_engine_b200.detector.response import get_response
+from attpc_engine_b200.detector.sharding import concat_batches, shard_range
+from attpc_engine_b200.detector.simulator import default_indices
+from attpc_engine_b200.target import AnalyticGasTarget, TableGasTarget, interpolation_error
+from tests.common import gas, make_config
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    """No compute call: the box running this has no GPU.  Every prototype of include/attpc_b200.h must resolve."""
+    header = (ROOT / "include" / "attpc_b200.h").read_text()
+    declared = set(re.findall(r"\b(attpc_[a-z_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.attpc_abi_version() == _lib.ABI_VERSION
+    assert re.search(r"#define ATTPC_ABI_VERSION (\d+)", header).group(1) == str(_lib.ABI_VERSION)
+
+
+def test_struct_layouts_match_header():
+    """ctypes mirrors have the field order of the C structs (sizes are checked against the C compiler's)."""
+    header = (ROOT / "include" / "attpc_b200.h").read_text()
+    for cls, cname in ((_lib.AttpcConfig, "AttpcConfig"), (_lib.AttpcSpecies, "AttpcSpecies"),
+                       (_lib.AttpcReplay, "AttpcReplay"), (_lib.AttpcResult, "AttpcResult")):  # fmt: skip
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                names.append(re.findall(r"[A-Za-z_][A-Za-z0-9_]*", part)[-1])
+        assert names == [f[0] for f in cls._fields_], cname
+
+
+def test_struct_sizes_match_c_compiler(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "attpc_b200.h"\nint main(void){printf("%zu %zu %zu %zu\\n", sizeof(AttpcConfig),'
+        " sizeof(AttpcSpecies), sizeof(AttpcReplay), sizeof(AttpcResult)); return 0;}\n"
+    )
+    import subprocess
+
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), "-o", str(exe), str(src)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(c) for c in (_lib.AttpcConfig, _lib.AttpcSpecies, _lib.AttpcReplay, _lib.AttpcResult)]
+
+
+def test_no_gpu_means_loud_failure():
+    """The product path has no CPU fallback: without a device, engine creation raises."""
+    lib = _lib.load()
+    if lib.attpc_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from attpc_engine_b200.detector.engine import Engine
+
+    with pytest.raises((RuntimeError, ValueError)):
+        Engine(make_config(), [nuclear_map.get_data(1, 2)])
+
+
+def test_pad_lut_reproduces_reference_lookup(golden_misc):
+    """The 1 mm LUT (host-built, uploaded to the GPU) answers exactly like position_to_index + grid + beam veto."""
+    cfg = make_config()
+    lut, origin = build_pad_lut(cfg.pad_grid, cfg.pad_grid_edges)
+    assert lut.shape == (559, 559) and origin == -280
+    assert not np.isin(lut, BEAM_PADS).any()
+    xy = golden_misc["pad_lookup/xy"]
+    f = np.floor(xy * 1000.0)
+    inside = np.all((f >= cfg.pad_grid_edges[0]) & (f < cfg.pad_grid_edges[1]), axis=1)
+    idx = (f - origin).astype(np.int64)
+    got = np.full(len(xy), -1, dtype=np.int16)
+    got[inside] = lut[idx[inside, 0], idx[inside, 1]]
+    assert np.array_equal(got, golden_misc["pad_lookup/pad"])
+
+
+def test_response_and_pairing_mirrors(golden_misc):
+    assert np.array_equal(get_response(make_config()), golden_misc["response/default"])
+    assert pairing.pair(56, 937) == 937**2 + 56 and pairing.pair(937, 56) == 937**2 + 937 + 56
+    assert pairing.unpair(937**2 + 56) == (56, 937) and pairing.unpair(937**2 + 937 + 56) == (937, 56)
+    tb, pad, key = golden_misc["pairing/tb"], golden_misc["pairing/pad"], golden_misc["pairing/key"]
+    assert np.array_equal(pairing.pair(tb, pad), key)
+    utb, upad = pairing.unpair(key)
+    assert np.array_equal(utb, tb) and np.array_equal(upad, pad)
+    assert pairing.pair(-1, 3) == -1
+
+
+def test_config_surface():
+    cfg = make_config()
+    assert cfg.pad_grid.shape == (5600, 5600) and cfg.pad_grid.dtype == np.int16
+    assert list(cfg.pad_grid_edges) == [-280.0, 279.0, 0.1]
+    assert cfg.pad_centers.shape == (10240, 2) and cfg.pad_sizes.shape == (10240,)
+    assert cfg.drift_velocity == 1.0 / 550.0
+    assert set(np.unique(cfg.pad_sizes)) == {0.5, 1.0}
+    assert default_indices(4) == [2, 3] and default_indices(6) == [2, 4, 5] and default_indices(8) == [2, 4, 6, 7]
+
+
+def test_dedx_table_scalar_and_vector_agree():
+    target = gas("D2_600")
+    deuteron = nuclear_map.get_data(1, 2)
+    table = target.table_for(deuteron)
+    ke = np.concatenate([np.logspace(-9, 3, 4001), table.nodes()[::37], [0.0, 1e-30, 5e3]])
+    vec = table.evaluate(ke)
+    assert np.array_equal(vec, np.array([table(float(k)) for k in ke]))
+    assert np.array_equal(table.evaluate(table.nodes()), table.values)
+    # the table reproduces its analytic source to the documented interpolation budget
+    assert interpolation_error(AnalyticGasTarget([(1, 2, 2)], 600.0), deuteron, table) < 5e-5
+    assert abs(target.density - 1.3128e-4) < 1e-7
+    # range / energy-loss helpers are consistent
+    loss = target.get_energy_loss(deuteron, 5.0, np.array([0.0, 0.1, 1e3]))
+    assert loss[0] == 0.0 and 0.0 < loss[1] < 5.0 and loss[2] == 5.0
+
+
+def test_freeze_budget_formula():
+    b = default_freeze_ke(0.2, 34.0)
+    n = b / 34.0e-6
+    assert n + np.sqrt(0.2 * n) * 8.66 < 1.0 < (n * 1.01) + np.sqrt(0.2 * n * 1.01) * 8.66 + 0.01
+
+
+def test_shard_ranges_partition_the_events():
+    for n, world in ((10, 1), (10, 3), (7, 8), (1_000_000, 8), (0, 4)):
+        ranges = [shard_range(n, r, world) for r in range(world)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = [b - a for a, b in ranges]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _fake_batch(first, counts, seed):
+    rng = np.random.default_rng(seed)
+    offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    n = int(offsets[-1])
+    return SimBatch(first, offsets, rng.random((n, 3)), rng.integers(0, 4, n), stats={"n_points": n, "ms_total": 1.0})
+
+
+def test_concat_batches_rebases_offsets():
+    a, b, c = _fake_batch(0, [3, 0, 2], 1), _fake_batch(3, [0, 4], 2), _fake_batch(5, [1], 3)
+    whole = concat_batches([c, a, b])
+    assert whole.first_event == 0 and len(whole) == 6
+    assert list(whole.offsets) == [0, 3, 3, 5, 5, 9, 10]
+    assert np.array_equal(whole.event(4)[0], b.event(1)[0]) and np.array_equal(whole.event(5)[1], c.event(0)[1])
+    assert whole.stats["n_points"] == 10 and "ms_total" not in whole.stats
+    with pytest.raises(ValueError):
+        concat_batches([a, c])
