@@ -89,7 +89,7 @@ struct AttpcSim {
 
     // sizing
     int32_t launch_events = 32768;
-    int32_t group_events = 512;
+    int32_t group_events = 2048;
     int32_t hash_cap = 16384;
     int64_t group_point_cap = 0;
 
@@ -97,7 +97,13 @@ struct AttpcSim {
     DevArray<double> px, py, pt;
     DevArray<long long> pq;
     DevArray<int32_t> pev, prank;
-    DevArray<unsigned> group_count;
+    DevArray<uint32_t> pj;
+    DevArray<double> geom;
+    DevArray<long long> sq;
+    DevArray<int32_t> meta, unit_event, unit_first, unit_count, unit_order, n_units;
+    DevArray<unsigned> group_count, pcnt, pstart, n_entries, mode;
+    int32_t ranks = 1;
+    int32_t max_units = 0;
     DevArray<HashEntry> hash;
     DevArray<uint64_t> sort_items;
     DevArray<Counters> counters;
@@ -155,17 +161,32 @@ int next_pow2(int64_t v) {
     return (int)p;
 }
 
-int ensure_work_buffers(AttpcSim* sim, int64_t launch_events) {
+int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
     if (sim->group_point_cap == 0) sim->group_point_cap = (int64_t)sim->group_events * 1024;
     const int64_t pts = n_groups * sim->group_point_cap;
+    sim->ranks = ranks;
     CU(sim->px.reserve(pts));
     CU(sim->py.reserve(pts));
     CU(sim->pt.reserve(pts));
     CU(sim->pq.reserve(pts));
     CU(sim->pev.reserve(pts));
     CU(sim->prank.reserve(pts));
+    CU(sim->pj.reserve(pts));
+    CU(sim->geom.reserve(pts * GEOM_DOUBLES));
+    CU(sim->sq.reserve(pts));
+    CU(sim->meta.reserve(pts));
+    sim->max_units = (int32_t)(sim->group_events + sim->group_point_cap / UNIT_POINTS + 1);
+    CU(sim->unit_event.reserve(n_groups * sim->max_units));
+    CU(sim->unit_first.reserve(n_groups * sim->max_units));
+    CU(sim->unit_count.reserve(n_groups * sim->max_units));
+    CU(sim->unit_order.reserve(n_groups * sim->max_units));
+    CU(sim->n_units.reserve(n_groups));
     CU(sim->group_count.reserve(n_groups));
+    CU(sim->pcnt.reserve(launch_events * ranks));
+    CU(sim->pstart.reserve(launch_events * ranks));
+    CU(sim->n_entries.reserve(launch_events));
+    CU(sim->mode.reserve(launch_events));
     CU(sim->hash.reserve((int64_t)sim->group_events * sim->hash_cap));
     CU(sim->sort_items.reserve((int64_t)sim->group_events * sim->hash_cap * 2));
     CU(sim->counters.reserve(1));
@@ -189,9 +210,22 @@ PointBuf point_buf(AttpcSim* sim) {
     pb.q = sim->pq.p;
     pb.ev = sim->pev.p;
     pb.rank = sim->prank.p;
+    pb.j = sim->pj.p;
     pb.count = sim->group_count.p;
+    pb.cnt = sim->pcnt.p;
+    pb.start = sim->pstart.p;
+    pb.geom = sim->geom.p;
+    pb.sq = sim->sq.p;
+    pb.meta = sim->meta.p;
+    pb.unit_event = sim->unit_event.p;
+    pb.unit_first = sim->unit_first.p;
+    pb.unit_count = sim->unit_count.p;
+    pb.unit_order = sim->unit_order.p;
+    pb.n_units = sim->n_units.p;
+    pb.max_units = sim->max_units;
     pb.group_cap = sim->group_point_cap;
     pb.group_events = sim->group_events;
+    pb.ranks = sim->ranks;
     return pb;
 }
 
@@ -225,6 +259,7 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, float* ms_
     fa.sort_items = sim->sort_items.p;
     const size_t sort_smem = (size_t)SORT_SMEM_ITEMS * sizeof(uint64_t);
     CU(cudaFuncSetAttribute(collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    CU(cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEPOSIT_SMEM_BYTES));
     for (int64_t g = 0; g < n_groups; ++g) {
         GroupView gv;
         gv.first_slot = (int32_t)(g * sim->group_events);
@@ -232,15 +267,20 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, float* ms_
         gv.group = (int32_t)g;
         gv.hash_cap = sim->hash_cap;
         gv.tables = sim->hash.p;
+        gv.n_entries = sim->n_entries.p;
+        gv.mode = sim->mode.p;
         cudaEvent_t d0 = sim->mark();
-        CU(cudaMemsetAsync(sim->hash.p, 0, (size_t)gv.n_events * sim->hash_cap * sizeof(HashEntry), sim->stream));
-        deposit_kernel<<<sim->sm_count * 8, DEPOSIT_THREADS, 0, sim->stream>>>(sim->P, pb, gv, sim->counters.p);
+        point_scan_kernel<<<1, 1024, 0, sim->stream>>>(pb, gv);
+        point_order_kernel<<<sim->sm_count * 4, 256, 0, sim->stream>>>(sim->P, pb, gv);
+        zero_shared_tables_kernel<<<gv.n_events, 256, 0, sim->stream>>>(gv);
+        deposit_kernel<<<sim->max_units, DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES, sim->stream>>>(sim->P, pb, gv,
+                                                                                             sim->counters.p);
         cudaEvent_t d1 = sim->mark();
         collect_kernel<<<gv.n_events, FINALIZE_THREADS, sort_smem, sim->stream>>>(sim->P, fa, gv, sim->counters.p);
         scan_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, sim->counters.p);
         emit_kernel<<<gv.n_events, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, sim->counters.p);
         cudaEvent_t f1 = sim->mark();
-        sim->launches += 4;
+        sim->launches += 7;
         dep_marks.push_back({d0, d1});
         fin_marks.push_back({d1, f1});
     }
@@ -339,7 +379,8 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     int rc = ensure_out_buffers(sim, n_events, out_cap, false);
     if (rc) return rc;
     const int64_t launch_cap = plan.replay ? n_events : sim->launch_events;
-    rc = ensure_work_buffers(sim, std::min<int64_t>(std::max<int64_t>(n_events, 1), launch_cap));
+    const int32_t ranks = std::max<int32_t>(1, plan.n_tracks_per_event);
+    rc = ensure_work_buffers(sim, std::min<int64_t>(std::max<int64_t>(n_events, 1), launch_cap), ranks);
     if (rc) return rc;
     CU(cudaMemsetAsync(sim->counters.p, 0, sizeof(Counters), sim->stream));
     CU(cudaMemsetAsync(sim->offsets_dev.p, 0, sizeof(int64_t), sim->stream));
@@ -351,7 +392,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     int retries = 0;
     for (int64_t b0 = 0; b0 < n_events;) {
         const int64_t nb = std::min<int64_t>(launch_cap, n_events - b0);
-        rc = ensure_work_buffers(sim, nb);
+        rc = ensure_work_buffers(sim, nb, ranks);
         if (rc) return rc;
         const int64_t n_groups = (nb + sim->group_events - 1) / sim->group_events;
         // restore the counters to the state before this launch (first attempt: no-op apart from the cursor)
@@ -361,6 +402,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         CU(cudaMemcpyAsync(sim->counters.p, sim->counters_host.p, sizeof(Counters), cudaMemcpyHostToDevice,
                            sim->stream));
         CU(cudaMemsetAsync(sim->group_count.p, 0, (size_t)n_groups * sizeof(unsigned), sim->stream));
+        CU(cudaMemsetAsync(sim->pcnt.p, 0, (size_t)nb * ranks * sizeof(unsigned), sim->stream));
 
         FinalizeArgs fa;
         memset(&fa, 0, sizeof fa);
@@ -421,7 +463,10 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             if (now.overflow_points) {
                 sim->group_point_cap *= 2;
                 sim->px.release(); sim->py.release(); sim->pt.release();
-                sim->pq.release(); sim->pev.release(); sim->prank.release();
+                sim->pq.release(); sim->pev.release(); sim->prank.release(); sim->pj.release();
+                sim->geom.release(); sim->sq.release(); sim->meta.release();
+                sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release();
+                sim->unit_order.release();
             }
             if (now.overflow_hash) {
                 if (sim->hash_cap >= (1 << 20)) return sim->fail(ATTPC_E_CAPACITY, "event needs > 2^20 hash slots");
@@ -535,6 +580,10 @@ void attpc_destroy(AttpcSim* sim) {
     sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release();
     sim->px.release(); sim->py.release(); sim->pt.release(); sim->pq.release(); sim->pev.release();
     sim->prank.release(); sim->group_count.release(); sim->hash.release(); sim->sort_items.release();
+    sim->pj.release(); sim->geom.release(); sim->sq.release(); sim->meta.release();
+    sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release(); sim->unit_order.release();
+    sim->n_units.release();
+    sim->pcnt.release(); sim->pstart.release(); sim->n_entries.release(); sim->mode.release();
     sim->counters.release(); sim->kept.release(); sim->in_momenta.release(); sim->in_vertices.release();
     sim->offsets_dev.release(); sim->labels_dev.release(); sim->row_offsets_dev.release();
     sim->row_labels_dev.release(); sim->cloud_dev.release(); sim->rows_dev.release(); sim->row_kept.release();
@@ -858,7 +907,7 @@ int attpc_trajectories(AttpcSim* sim, const double* momenta, const double* verti
     for (int64_t t = 0; t < n_tracks; ++t)
         if (species[t] >= sim->P.n_species) return sim->fail(ATTPC_E_BADARG, "species[%lld] out of range", (long long)t);
     CU(cudaSetDevice(sim->device));
-    int rc = ensure_work_buffers(sim, 1);
+    int rc = ensure_work_buffers(sim, 1, 1);
     if (rc) return rc;
     DevArray<double> d_m, d_v, d_out;
     DevArray<int32_t> d_sp, d_cnt;

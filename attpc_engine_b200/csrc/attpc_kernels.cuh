@@ -63,7 +63,9 @@ struct SimParams {
     double resp_max;
 };
 
-// Active track points (>= 1 electron), appended per event group by the track kernels.
+// Active track points (>= 1 electron).  The track kernels append them per event group in arrival order and number
+// them inside their (event, rank) list; order_points_kernel then scatters them into (event, rank, arrival) order so
+// that the deposit kernel of an event reads one contiguous run per track.
 struct PointBuf {
     double* x;
     double* y;
@@ -71,9 +73,23 @@ struct PointBuf {
     long long* q;       // electrons after mpgd_gain
     int32_t* ev;        // event slot inside the launch batch
     int32_t* rank;      // position of the track in `indices`
-    unsigned* count;    // [n_groups]
+    uint32_t* j;        // arrival index inside the (event, rank) list
+    unsigned* count;    // [n_groups] points appended per group
+    unsigned* cnt;      // [launch events * ranks] points per (event, rank)
+    unsigned* start;    // [launch events * ranks] first position of the list inside the group's ordered run
+    double* geom;       // ordered: GEOM_DOUBLES per point, the per-point constants of the drift mesh
+    long long* sq;      // ordered: electrons after gain
+    int32_t* meta;      // ordered: time bucket | kind << 30
+    // work units of the deposit kernel (one CTA each): a slice of <= UNIT_POINTS points of one event
+    int32_t* unit_event;   // [max_units] event index inside the group
+    int32_t* unit_first;   // [max_units] first point of the slice inside the event's ordered run
+    int32_t* unit_count;   // [max_units]
+    int32_t* unit_order;   // [max_units] units by decreasing size (longest first)
+    int32_t* n_units;      // [n_groups]
     int64_t group_cap;  // points per group
     int32_t group_events;
+    int32_t ranks;      // tracks per event
+    int32_t max_units;  // capacity of the unit arrays per group
 };
 
 struct Counters {
@@ -304,6 +320,7 @@ __device__ __forceinline__ void append_point(const PointBuf& pb, Counters* ctr, 
     pb.q[i] = q;
     pb.ev[i] = ev;
     pb.rank[i] = rank;
+    pb.j[i] = atomicAdd(&pb.cnt[(int64_t)ev * pb.ranks + rank], 1u);
 }
 
 struct TrackBatch {
@@ -591,83 +608,393 @@ struct GroupView {
     int32_t first_slot;   // first event slot of the group inside the launch batch
     int32_t n_events;     // events in this group
     int32_t group;        // group index (selects the PointBuf region)
-    int32_t hash_cap;     // slots per event (power of two)
-    HashEntry* tables;    // [group_events][hash_cap]
+    int32_t hash_cap;     // entries per event region (power of two)
+    HashEntry* tables;    // [group_events][hash_cap]: dense entry list (mode 0) or open-addressing table (mode 1)
+    unsigned* n_entries;  // [launch events] entries of the dense list
+    unsigned* mode;       // [launch events] 0 = dense list, 1 = the event spilled to a global table
 };
 
-constexpr int DEPOSIT_THREADS = 256;
+// ------------------------------------------------------------------------------------------- ordering of points
+constexpr int UNIT_POINTS = 1024;   // longest slice of one event handled by one CTA of the deposit kernel
+constexpr int MAX_UNITS_SORT = 8192;
+constexpr int GEOM_DOUBLES = 12;
 
-// One warp per active point; lanes cover the 10x10 mesh (pixel = lane + 32 r).
-__global__ void __launch_bounds__(DEPOSIT_THREADS)
-deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, Counters* ctr) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int64_t n_points = min((int64_t)pb.count[gv.group], pb.group_cap);
-    const int64_t base = (int64_t)gv.group * pb.group_cap;
-    const unsigned mask = (unsigned)gv.hash_cap - 1u;
-    unsigned long long n_dep = 0, n_probe = 0;
-
-    for (int64_t p = warp; p < n_points; p += n_warps) {
-        if (*(volatile int*)&ctr->overflow_hash) break;  // the host will redo the launch with bigger tables
-        const double cx = pb.x[base + p], cy = pb.y[base + p], time = pb.t[base + p];
-        const long long q = pb.q[base + p];
-        const int ev = pb.ev[base + p] - gv.first_slot;
-        const unsigned rank = (unsigned)pb.rank[base + p];
-        HashEntry* tab = gv.tables + (int64_t)ev * gv.hash_cap;
-        // detector/transporter.py:301, evaluated left to right
-        const double sigma =
-            __dsqrt_rn(__ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, P.diffusion), P.dv), time), P.efield));
-        const int tb = (int)time;  // detector/transporter.py:165, 238
-        if (tb < 0 || !(sigma == sigma)) continue;  // never reached for z <= length + mm_edge * dv
-        if (sigma == 0.0) {  // detector/transporter.py:123-169
-            if (lane == 0) {
-                const int pad = lookup_pad(P, cx, cy);
-                if (pad >= 0) {
-                    n_probe += table_add(tab, mask, szudzik_pair((unsigned)tb, (unsigned)pad), q, rank, ctr);
-                    n_dep += 1;
+// Per group, single CTA: (1) exclusive scan of the (event, rank) list lengths -> start of every list in the group's
+// ordered run; (2) split every event into work units of <= UNIT_POINTS points; (3) order the units by decreasing
+// size so that the longest start first (the per-event cost varies by 100x between a short recoil and a stopped ion).
+__global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView gv) {
+    __shared__ unsigned s_part[1024];
+    __shared__ unsigned s_base, s_ubase;
+    __shared__ uint32_t s_sort[MAX_UNITS_SORT];
+    const int tid = threadIdx.x;
+    const int n = gv.n_events * pb.ranks;
+    const int64_t first = (int64_t)gv.first_slot * pb.ranks;
+    int32_t* u_event = pb.unit_event + (int64_t)gv.group * pb.max_units;
+    int32_t* u_first = pb.unit_first + (int64_t)gv.group * pb.max_units;
+    int32_t* u_count = pb.unit_count + (int64_t)gv.group * pb.max_units;
+    int32_t* u_order = pb.unit_order + (int64_t)gv.group * pb.max_units;
+    if (tid == 0) {
+        s_base = 0;
+        s_ubase = 0;
+    }
+    __syncthreads();
+    for (int start = 0; start < n; start += 1024) {
+        const int i = start + tid;
+        const unsigned v = i < n ? pb.cnt[first + i] : 0u;
+        s_part[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned add = tid >= o ? s_part[tid - o] : 0u;
+            __syncthreads();
+            s_part[tid] += add;
+            __syncthreads();
+        }
+        if (i < n) pb.start[first + i] = s_base + s_part[tid] - v;
+        __syncthreads();
+        if (tid == 0) s_base += s_part[1023];
+        __syncthreads();
+    }
+    // units: event e has ceil(points / UNIT_POINTS) of them (at least one, so that empty events still get their
+    // zero-length entry list written)
+    for (int start = 0; start < gv.n_events; start += 1024) {
+        const int e = start + tid;
+        unsigned pts = 0;
+        if (e < gv.n_events)
+            for (int r = 0; r < pb.ranks; ++r) pts += pb.cnt[first + (int64_t)e * pb.ranks + r];
+        const unsigned nu = e < gv.n_events ? max(1u, (pts + UNIT_POINTS - 1) / UNIT_POINTS) : 0u;
+        s_part[tid] = nu;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned add = tid >= o ? s_part[tid - o] : 0u;
+            __syncthreads();
+            s_part[tid] += add;
+            __syncthreads();
+        }
+        if (e < gv.n_events) {
+            unsigned u0 = s_ubase + s_part[tid] - nu;
+            gv.mode[gv.first_slot + e] = nu > 1 ? 1u : 0u;  // several units merge through the event's global table
+            for (unsigned k = 0; k < nu; ++k) {
+                const unsigned u = u0 + k;
+                if (u < (unsigned)pb.max_units) {
+                    u_event[u] = e;
+                    u_first[u] = (int32_t)(k * UNIT_POINTS);
+                    u_count[u] = (int32_t)min((unsigned)UNIT_POINTS, pts - min(pts, k * UNIT_POINTS));
                 }
             }
-            continue;
         }
-        // detector/transporter.py:217-226 with numba's linspace (numba/np/arrayobj.py: linspace)
-        const double three_sigma = __dmul_rn(3.0, sigma);
-        const double lo_x = __dsub_rn(cx, three_sigma), hi_x = __dadd_rn(cx, three_sigma);
-        const double lo_y = __dsub_rn(cy, three_sigma), hi_y = __dadd_rn(cy, three_sigma);
-        const double dx = __ddiv_rn(__dsub_rn(hi_x, lo_x), (double)(MESH_N - 1));
-        const double dy = __ddiv_rn(__dsub_rn(hi_y, lo_y), (double)(MESH_N - 1));
-        const double cell = __ddiv_rn(__dmul_rn(6.0, sigma), (double)(MESH_N - 1));
-        const double cell2 = __dmul_rn(cell, cell);
-        const double s2 = __dmul_rn(sigma, sigma);
-        const double norm = __ddiv_rn(__ddiv_rn(0.5, 3.141592653589793), s2);  // 1 / 2 / pi / sigma**2
-        const double c2 = __ddiv_rn(-0.5, s2);                                 // -1 / 2 / sigma**2
-        const double qd = (double)q;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int pix = lane + 32 * r;
-            if (pix >= MESH_N * MESH_N) break;
-            const int i = pix / MESH_N, j = pix - i * MESH_N;
-            const double px = (i == MESH_N - 1) ? hi_x : __dadd_rn(lo_x, __dmul_rn((double)i, dx));
-            const double py = (j == MESH_N - 1) ? hi_y : __dadd_rn(lo_y, __dmul_rn((double)j, dy));
-            const int pad = lookup_pad(P, px, py);
-            if (pad < 0) continue;
-            // detector/transporter.py:36-41, 240-246
-            const double ddx = __dsub_rn(px, cx), ddy = __dsub_rn(py, cy);
-            const double arg = __dmul_rn(c2, __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy)));
-            const double pdf = __dmul_rn(norm, exp(arg));
-            const long long share = (long long)__dmul_rn(__dmul_rn(pdf, cell2), qd);
-            n_probe += table_add(tab, mask, szudzik_pair((unsigned)tb, (unsigned)pad), share, rank, ctr);
-            n_dep += 1;
-        }
+        __syncthreads();
+        if (tid == 0) s_ubase += s_part[1023];
+        __syncthreads();
     }
+    const int total = min((int)s_ubase, pb.max_units);
+    if (tid == 0) pb.n_units[gv.group] = total;
+    // longest first: bitonic sort of (UNIT_POINTS - count) << 16 | unit ... only when it fits the sort buffer
+    if (total <= MAX_UNITS_SORT) {
+        int n2 = 1;
+        while (n2 < total) n2 <<= 1;
+        for (int i = tid; i < n2; i += 1024)
+            s_sort[i] = i < total ? ((uint32_t)(UNIT_POINTS - u_count[i]) << 16) | (uint32_t)i : 0xFFFFFFFFu;
+        __syncthreads();
+        for (int k = 2; k <= n2; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = tid; i < n2; i += 1024) {
+                    const int l = i ^ j;
+                    if (l > i) {
+                        const uint32_t a = s_sort[i], b = s_sort[l];
+                        if ((a > b) == ((i & k) == 0)) {
+                            s_sort[i] = b;
+                            s_sort[l] = a;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int i = tid; i < total; i += 1024) u_order[i] = (int32_t)(s_sort[i] & 0xFFFFu);
+    } else {
+        for (int i = tid; i < total; i += 1024) u_order[i] = i;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- drift geometry
+// Per-point constants of detector/transporter.py:172-249, in the reference's operation order.
+// geom[] = cx, cy, lo_x, hi_x, dx, lo_y, hi_y, dy, cell2, norm, c2, qd
+__device__ __forceinline__ int make_geom(const SimParams& P, double cx, double cy, double time, long long q,
+                                         double* g) {
+    g[0] = cx;
+    g[1] = cy;
+    g[11] = (double)q;
+    // detector/transporter.py:301, evaluated left to right
+    const double sigma = __dsqrt_rn(__ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, P.diffusion), P.dv), time), P.efield));
+    const int tb = (int)time;  // detector/transporter.py:165, 238
+    if (tb < 0 || tb >= (1 << 29) || !(sigma == sigma)) return 0;  // kind 0: never reached for z <= length + mm_edge*dv
+    if (sigma == 0.0) return tb | (1 << 30);                      // kind 1: single deposit, transporter.py:123-169
+    // detector/transporter.py:217-226 with numba's linspace (numba/np/arrayobj.py: linspace)
+    const double three_sigma = __dmul_rn(3.0, sigma);
+    g[2] = __dsub_rn(cx, three_sigma);
+    g[3] = __dadd_rn(cx, three_sigma);
+    g[4] = __ddiv_rn(__dsub_rn(g[3], g[2]), (double)(MESH_N - 1));
+    g[5] = __dsub_rn(cy, three_sigma);
+    g[6] = __dadd_rn(cy, three_sigma);
+    g[7] = __ddiv_rn(__dsub_rn(g[6], g[5]), (double)(MESH_N - 1));
+    const double cell = __ddiv_rn(__dmul_rn(6.0, sigma), (double)(MESH_N - 1));
+    g[8] = __dmul_rn(cell, cell);
+    const double s2 = __dmul_rn(sigma, sigma);
+    g[9] = __ddiv_rn(__ddiv_rn(0.5, 3.141592653589793), s2);  // 1 / 2 / pi / sigma**2
+    g[10] = __ddiv_rn(-0.5, s2);                              // -1 / 2 / sigma**2
+    return tb | (2 << 30);                                    // kind 2: 10x10 mesh
+}
+
+// Scatter the group's points into (event, rank, arrival) order and compute their mesh constants (one thread each).
+__global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant__ SimParams P, PointBuf pb,
+                                                          GroupView gv) {
+    const int64_t n = min((int64_t)pb.count[gv.group], pb.group_cap);
+    const int64_t base = (int64_t)gv.group * pb.group_cap;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = base + p;
+        const int64_t d = base + pb.start[(int64_t)pb.ev[i] * pb.ranks + pb.rank[i]] + pb.j[i];
+        double g[GEOM_DOUBLES];
+#pragma unroll
+        for (int k = 0; k < GEOM_DOUBLES; ++k) g[k] = 0.0;
+        const long long q = pb.q[i];
+        pb.meta[d] = make_geom(P, pb.x[i], pb.y[i], pb.t[i], q, g);
+        pb.sq[d] = q;
+        double2* out = reinterpret_cast<double2*>(pb.geom + d * GEOM_DOUBLES);
+#pragma unroll
+        for (int k = 0; k < GEOM_DOUBLES / 2; ++k) out[k] = make_double2(g[2 * k], g[2 * k + 1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------- shared-memory accumulate
+constexpr int DEPOSIT_THREADS = 256;
+constexpr int DEPOSIT_WARPS = DEPOSIT_THREADS / 32;
+constexpr int SMEM_SLOTS = 8192;   // per-CTA table in shared memory
+constexpr int SPILL_CHECK_EVERY = 2;  // iterations (of DEPOSIT_WARPS points) between two fill checks
+constexpr int SMEM_SPILL_AT = SMEM_SLOTS - 100 * DEPOSIT_WARPS * SPILL_CHECK_EVERY - 512;
+constexpr size_t DEPOSIT_SMEM_BYTES = (size_t)SMEM_SLOTS * (3 * sizeof(unsigned) + 1);
+
+struct SmemTable {
+    unsigned* key1;   // Szudzik key + 1, 0 = empty
+    unsigned* lo;     // charge bits 0..31
+    unsigned* hi;     // charge bits 32..63
+    uint8_t* rank;    // last track rank that touched the slot (tracks are processed in rank order)
+};
+
+// Find the slot of `key`, claiming an empty one if it is new.  The table is flushed long before it can fill.
+__device__ __forceinline__ unsigned smem_find(const SmemTable& t, unsigned key, unsigned* n_keys, unsigned& probes) {
+    const unsigned key1 = key + 1u, mask = SMEM_SLOTS - 1;
+    unsigned slot = hash_slot(key, mask);
+#pragma unroll 1
+    for (unsigned probe = 0; probe <= mask; ++probe) {
+        unsigned k = *(volatile unsigned*)&t.key1[slot];
+        if (k == 0u) {
+            k = atomicCAS(&t.key1[slot], 0u, key1);
+            if (k == 0u) {
+                k = key1;
+                atomicAdd(n_keys, 1u);
+            }
+        }
+        if (k == key1) {
+            probes += probe + 1u;
+            return slot;
+        }
+        slot = (slot + 1u) & mask;
+    }
+    return slot;
+}
+
+// Exact 64-bit accumulate from two native 32-bit shared-memory atomics.
+__device__ __forceinline__ void smem_charge(const SmemTable& t, unsigned slot, unsigned long long q) {
+    const unsigned vlo = (unsigned)q, vhi = (unsigned)(q >> 32);
+    unsigned carry = 0u;
+    if (vlo) carry = atomicAdd(&t.lo[slot], vlo) > ~vlo ? 1u : 0u;
+    if (vhi + carry) atomicAdd(&t.hi[slot], vhi + carry);
+}
+
+// One CTA per work unit (a slice of one event's points).  Tracks are processed in rank order (label = last track
+// to touch a key, detector/transporter.py:166-169, 247-249), one warp per active point, lanes over the 10x10 mesh,
+// accumulating into a shared-memory open-addressing table.  At the end the table is compacted into the event's
+// dense entry list (events of one unit) or merged into the event's global table (events split over several units,
+// and units dense enough to overflow the shared table).
+__global__ void __launch_bounds__(DEPOSIT_THREADS, 2)
+deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, Counters* ctr) {
+    extern __shared__ unsigned s_raw[];
+    __shared__ unsigned s_nkeys, s_out, s_spilled;
+    if ((int)blockIdx.x >= pb.n_units[gv.group]) return;
+    const int64_t ubase = (int64_t)gv.group * pb.max_units;
+    const int unit = pb.unit_order[ubase + blockIdx.x];
+    const int e = pb.unit_event[ubase + unit];
+    const int u_first = pb.unit_first[ubase + unit], u_count = pb.unit_count[ubase + unit];
+    SmemTable t;
+    t.key1 = s_raw;
+    t.lo = s_raw + SMEM_SLOTS;
+    t.hi = s_raw + 2 * SMEM_SLOTS;
+    t.rank = (uint8_t*)(s_raw + 3 * SMEM_SLOTS);
+    const int slot_event = gv.first_slot + e;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool shared_event = gv.mode[slot_event] != 0u;  // several units: merge through the (pre-zeroed) global table
+    HashEntry* region = gv.tables + (int64_t)e * gv.hash_cap;
+    const unsigned gmask = (unsigned)gv.hash_cap - 1u;
+    const int64_t base = (int64_t)gv.group * pb.group_cap;
+    for (int i = threadIdx.x; i < 3 * SMEM_SLOTS; i += blockDim.x) s_raw[i] = 0u;
+    if (threadIdx.x == 0) {
+        s_nkeys = 0;
+        s_out = 0;
+        s_spilled = 0;
+    }
+    __syncthreads();
+    unsigned long long n_dep = 0;
+    unsigned n_probe = 0;
+    // pixel (i, j) of this lane in each of the four rounds (x-major like the reference's meshgrid)
+    int pi[4], pj[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int pix = lane + 32 * k;
+        pi[k] = pix / MESH_N;
+        pj[k] = pix - pi[k] * MESH_N;
+    }
+
+    auto flush_to_global = [&]() {  // all threads
+        if (!shared_event && !s_spilled) {
+            for (int i = threadIdx.x; i < gv.hash_cap; i += blockDim.x) region[i] = HashEntry{0u, 0u, 0ULL};
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < SMEM_SLOTS; i += blockDim.x) {
+            const unsigned k = t.key1[i];
+            if (k) {
+                const long long q = (long long)(((unsigned long long)t.hi[i] << 32) | t.lo[i]);
+                table_add(region, gmask, k - 1u, q, t.rank[i], ctr);
+                t.key1[i] = 0u;
+                t.lo[i] = 0u;
+                t.hi[i] = 0u;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_nkeys = 0;
+            s_spilled = 1;
+        }
+        __syncthreads();
+    };
+
+    // the unit's slice [u_first, u_first + u_count) of the event's run, walked rank by rank
+    const int64_t li0 = (int64_t)slot_event * pb.ranks;
+    const int64_t run0 = pb.start[li0];
+    int rank_begin = 0;  // position of the current rank's list inside the event's run
+    int iter = 0;
+    for (int r = 0; r < pb.ranks; ++r) {
+        const int rank_len = (int)pb.cnt[li0 + r];
+        const int lo = max(rank_begin, u_first), hi = min(rank_begin + rank_len, u_first + u_count);
+        rank_begin += rank_len;
+        if (lo >= hi) continue;
+        for (int p0 = lo; p0 < hi; p0 += DEPOSIT_WARPS) {
+            const int pp = p0 + warp;
+            if (pp < hi) {
+                const int64_t p = base + run0 + pp;
+                const int meta = pb.meta[p];
+                const int kind = (meta >> 30) & 3, tb = meta & ((1 << 30) - 1);
+                if (kind == 1) {  // detector/transporter.py:123-169
+                    if (lane == 0) {
+                        const double* g = pb.geom + p * GEOM_DOUBLES;
+                        const int pad = lookup_pad(P, g[0], g[1]);
+                        if (pad >= 0) {
+                            const unsigned slot = smem_find(t, szudzik_pair((unsigned)tb, (unsigned)pad), &s_nkeys, n_probe);
+                            smem_charge(t, slot, (unsigned long long)pb.sq[p]);
+                            t.rank[slot] = (uint8_t)r;
+                            n_dep += 1;
+                        }
+                    }
+                } else if (kind == 2) {
+                    const double2* gp = reinterpret_cast<const double2*>(pb.geom + p * GEOM_DOUBLES);
+                    const double2 g01 = gp[0], g23 = gp[1], g45 = gp[2], g67 = gp[3], g89 = gp[4], gab = gp[5];
+                    // per-axis values, once per point: lanes 0-9 own x_i, lanes 10-19 own y_j
+                    const bool is_y = lane >= MESH_N;
+                    const int a = is_y ? lane - MESH_N : lane;
+                    const double c = is_y ? g01.y : g01.x;
+                    const double lo_a = is_y ? g45.y : g23.x, hi_a = is_y ? g67.x : g23.y, d_a = is_y ? g67.y : g45.x;
+                    const double pa = (a == MESH_N - 1) ? hi_a : __dadd_rn(lo_a, __dmul_rn((double)a, d_a));
+                    // detector/transporter.py:102-120 on one coordinate: floor(mm), range test, LUT row / column
+                    const double f = floor(__dmul_rn(pa, 1000.0));
+                    int idx = -1;
+                    if (f < P.grid_high && f >= P.grid_low) {
+                        idx = (int)f - P.lut_origin;
+                        if ((unsigned)idx >= (unsigned)P.lut_n) idx = -1;
+                    }
+                    const double dd = __dsub_rn(pa, c);
+                    const double dd2 = __dmul_rn(dd, dd);  // (pixel - center)**2 of transporter.py:38
+                    int pad[4];
+                    double r2[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // all pad lookups first: independent loads in flight
+                        const int ix = __shfl_sync(FULL, idx, pi[k]), iy = __shfl_sync(FULL, idx, MESH_N + pj[k]);
+                        r2[k] = __dadd_rn(__shfl_sync(FULL, dd2, pi[k]), __shfl_sync(FULL, dd2, MESH_N + pj[k]));
+                        const bool ok = (lane + 32 * k < MESH_N * MESH_N) && ix >= 0 && iy >= 0;
+                        pad[k] = ok ? (int)__ldg(P.lut + (int64_t)ix * P.lut_n + iy) : -1;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const bool ok = pad[k] >= 0;
+                        unsigned slot = 0;
+                        long long share = 0;
+                        if (ok) {
+                            // detector/transporter.py:36-41, 240-246
+                            const double pdf = __dmul_rn(g89.y, exp(__dmul_rn(gab.x, r2[k])));
+                            share = (long long)__dmul_rn(__dmul_rn(pdf, g89.x), gab.y);
+                            slot = smem_find(t, szudzik_pair((unsigned)tb, (unsigned)pad[k]), &s_nkeys, n_probe);
+                        }
+                        if (ok) {  // reconverged: one pass of atomics for all valid lanes
+                            smem_charge(t, slot, (unsigned long long)share);
+                            t.rank[slot] = (uint8_t)r;  // same value from every writer of this phase
+                            n_dep += 1;
+                        }
+                    }
+                }
+            }
+            if (++iter % SPILL_CHECK_EVERY == 0) {
+                if (__syncthreads_or(s_nkeys > (unsigned)SMEM_SPILL_AT)) flush_to_global();
+            }
+        }
+        __syncthreads();  // rank phases do not overlap: plain stores of the label are race-free
+        if (s_nkeys > (unsigned)SMEM_SPILL_AT) flush_to_global();
+    }
+    if (shared_event || s_spilled) {
+        flush_to_global();
+        if (threadIdx.x == 0) {
+            gv.mode[slot_event] = 1u;
+            gv.n_entries[slot_event] = 0u;
+        }
+    } else if (s_nkeys > (unsigned)gv.hash_cap) {  // the dense list does not fit the event's region: host grows it
+        if (threadIdx.x == 0) {
+            ctr->overflow_hash = 1;
+            gv.n_entries[slot_event] = 0u;
+        }
+    } else {
+        for (int i = threadIdx.x; i < SMEM_SLOTS; i += blockDim.x) {
+            const unsigned k = t.key1[i];
+            if (k) {
+                const unsigned pos = atomicAdd(&s_out, 1u);
+                region[pos] = HashEntry{k, (unsigned)t.rank[i], ((unsigned long long)t.hi[i] << 32) | t.lo[i]};
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) gv.n_entries[slot_event] = s_out;
+    }
+    unsigned long long n_probe64 = n_probe;
     for (int o = 16; o > 0; o >>= 1) {
         n_dep += __shfl_xor_sync(FULL, n_dep, o);
-        n_probe += __shfl_xor_sync(FULL, n_probe, o);
+        n_probe64 += __shfl_xor_sync(FULL, n_probe64, o);
     }
     if (lane == 0 && n_dep) {
         atomicAdd(&ctr->deposits, n_dep);
-        atomicAdd(&ctr->probes, n_probe);
+        atomicAdd(&ctr->probes, n_probe64);
     }
+}
+
+// Zero the global tables of the events that are split over several units (before the deposit kernel merges into them).
+__global__ void __launch_bounds__(256) zero_shared_tables_kernel(GroupView gv) {
+    const int e = blockIdx.x;
+    if (gv.mode[gv.first_slot + e] == 0u) return;
+    HashEntry* region = gv.tables + (int64_t)e * gv.hash_cap;
+    for (int i = threadIdx.x; i < gv.hash_cap; i += blockDim.x) region[i] = HashEntry{0u, 0u, 0ULL};
 }
 
 // ---------------------------------------------------------------------------------------------------- finalize
@@ -743,7 +1070,8 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     }
     __syncthreads();
     unsigned occupied = 0;
-    for (int i = threadIdx.x; i < gv.hash_cap; i += blockDim.x) {
+    const int limit = gv.mode[slot_event] ? gv.hash_cap : (int)gv.n_entries[slot_event];
+    for (int i = threadIdx.x; i < limit; i += blockDim.x) {
         const unsigned key1 = tab[i].key1;
         if (key1 == 0u) continue;
         const unsigned key = key1 - 1u;
@@ -794,28 +1122,29 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
         __syncthreads();
     }
     const bool in_smem = n <= SORT_SMEM_ITEMS;
-    uint64_t* buf = in_smem ? s_items : sorted;
+    uint64_t* buf = in_smem ? s_items : sorted;  // bucketed, unordered inside a bucket
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint64_t it = stash[i];
         const unsigned bin = min((unsigned)(it >> 47), (unsigned)TB_BINS - 1u);
         buf[atomicAdd(&s_fill[bin], 1u)] = it;
     }
     __syncthreads();
-    for (int b = threadIdx.x; b < TB_BINS; b += blockDim.x) {
+    // order every bucket: one warp per bucket, each lane ranks its items by counting the smaller ones (items are
+    // distinct, a bucket holds the few pads hit in one time bucket)
+    uint64_t* dst = in_smem ? sorted : stash;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int b = warp; b < TB_BINS; b += FINALIZE_THREADS / 32) {
         const int lo = (int)s_hist[b], hi = (int)s_hist[b + 1];
-        for (int i = lo + 1; i < hi; ++i) {
+        for (int i = lo + lane; i < hi; i += 32) {
             const uint64_t v = buf[i];
-            int j = i - 1;
-            while (j >= lo && buf[j] > v) {
-                buf[j + 1] = buf[j];
-                --j;
-            }
-            buf[j + 1] = v;
+            int rank = 0;
+            for (int j = lo; j < hi; ++j) rank += buf[j] < v;
+            dst[lo + rank] = v;
         }
     }
-    if (in_smem) {
+    if (!in_smem) {
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) sorted[i] = s_items[i];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sorted[i] = stash[i];
     }
 }
 
