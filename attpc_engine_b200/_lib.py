@@ -45,7 +45,7 @@ class AttpcConfig(C.Structure):
         ("freeze_ke_mev", C.c_double),
         ("max_events_per_launch", C.c_int32),
         ("hash_capacity", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("copy_events_per_launch", C.c_int32),
     ]
 
 

@@ -54,14 +54,16 @@ template <typename T>
 struct PinnedArray {
     T* p = nullptr;
     int64_t n = 0;
-    cudaError_t reserve(int64_t want) {
+    cudaError_t reserve(int64_t want, bool keep = false) {
         if (want <= n) return cudaSuccess;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        n = 0;
         want += want / 4;  // pinning is slow (~0.5 s/GB): grow with slack so that it is rare
-        cudaError_t e = cudaHostAlloc((void**)&p, (size_t)want * sizeof(T), cudaHostAllocDefault);
-        if (e == cudaSuccess) n = want;
+        T* q = nullptr;
+        cudaError_t e = cudaHostAlloc((void**)&q, (size_t)want * sizeof(T), cudaHostAllocMapped);
+        if (e != cudaSuccess) return e;
+        if (keep && p && n > 0) memcpy(q, p, (size_t)n * sizeof(T));
+        if (p) cudaFreeHost(p);
+        p = q;
+        n = want;
         return e;
     }
     void release() {
@@ -89,24 +91,42 @@ struct AttpcSim {
 
     // sizing
     int32_t launch_events = 32768;
+    int32_t copy_launch_events = 4096;
     int32_t group_events = 2048;
     int32_t hash_cap = 16384;
     int64_t group_point_cap = 0;
 
-    // work buffers
-    DevArray<double> px, py, pt;
-    DevArray<long long> pq;
-    DevArray<int32_t> pev, prank;
-    DevArray<uint32_t> pj;
+    // work buffers; the arrays the track kernel fills exist twice so that the track kernel of launch i+1 can run
+    // (on its own stream) while the deposit / finalize kernels of launch i consume the other set
+    struct LaunchSlot {
+        DevArray<double> px, py, pt;
+        DevArray<long long> pq;
+        DevArray<int32_t> pev, prank;
+        DevArray<uint32_t> pj;
+        DevArray<unsigned> group_count, pcnt;
+        DevArray<Counters> counters;
+        PinnedArray<Counters> counters_host;
+        void release_points() {
+            px.release(); py.release(); pt.release(); pq.release(); pev.release(); prank.release(); pj.release();
+        }
+        void release_all() {
+            release_points();
+            group_count.release(); pcnt.release(); counters.release(); counters_host.release();
+        }
+    } slot[2];
+    cudaStream_t stream_t = nullptr, stream_c = nullptr;  // track kernels, device-to-host copies
+    std::vector<cudaEvent_t> sync_events;                 // untimed events for cross-stream ordering
+    size_t sync_used = 0;
+    DevArray<unsigned long long> csr_total;
+    PinnedArray<unsigned long long> csr_host;
     DevArray<double> geom;
     DevArray<long long> sq;
     DevArray<int32_t> meta, unit_event, unit_first, unit_count, unit_order, n_units;
-    DevArray<unsigned> group_count, pcnt, pstart, n_entries, mode;
+    DevArray<unsigned> pstart, n_entries, mode;
     int32_t ranks = 1;
     int32_t max_units = 0;
     DevArray<HashEntry> hash;
     DevArray<uint64_t> sort_items;
-    DevArray<Counters> counters;
     DevArray<unsigned> kept;
     DevArray<double> in_momenta, in_vertices;
 
@@ -118,7 +138,6 @@ struct AttpcSim {
     DevArray<uint32_t> row_sort_idx;
     PinnedArray<int64_t> offsets_host, labels_host, row_offsets_host, row_labels_host;
     PinnedArray<double> cloud_host, rows_host;
-    PinnedArray<Counters> counters_host;
 
     std::vector<cudaEvent_t> events;
     size_t events_used = 0;
@@ -133,14 +152,24 @@ struct AttpcSim {
         error = buf;
         return code;
     }
-    cudaEvent_t mark() {
+    cudaEvent_t mark(cudaStream_t s = nullptr) {
         if (events_used == events.size()) {
             cudaEvent_t e;
             cudaEventCreate(&e);
             events.push_back(e);
         }
         cudaEvent_t e = events[events_used++];
-        cudaEventRecord(e, stream);
+        cudaEventRecord(e, s ? s : stream);
+        return e;
+    }
+    cudaEvent_t fence(cudaStream_t s) {  // untimed event recorded on s
+        if (sync_used == sync_events.size()) {
+            cudaEvent_t e;
+            cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            sync_events.push_back(e);
+        }
+        cudaEvent_t e = sync_events[sync_used++];
+        cudaEventRecord(e, s);
         return e;
     }
 };
@@ -166,13 +195,19 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     if (sim->group_point_cap == 0) sim->group_point_cap = (int64_t)sim->group_events * 1024;
     const int64_t pts = n_groups * sim->group_point_cap;
     sim->ranks = ranks;
-    CU(sim->px.reserve(pts));
-    CU(sim->py.reserve(pts));
-    CU(sim->pt.reserve(pts));
-    CU(sim->pq.reserve(pts));
-    CU(sim->pev.reserve(pts));
-    CU(sim->prank.reserve(pts));
-    CU(sim->pj.reserve(pts));
+    for (auto& ls : sim->slot) {
+        CU(ls.px.reserve(pts));
+        CU(ls.py.reserve(pts));
+        CU(ls.pt.reserve(pts));
+        CU(ls.pq.reserve(pts));
+        CU(ls.pev.reserve(pts));
+        CU(ls.prank.reserve(pts));
+        CU(ls.pj.reserve(pts));
+        CU(ls.group_count.reserve(n_groups));
+        CU(ls.pcnt.reserve(launch_events * ranks));
+        CU(ls.counters.reserve(1));
+        CU(ls.counters_host.reserve(1));
+    }
     CU(sim->geom.reserve(pts * GEOM_DOUBLES));
     CU(sim->sq.reserve(pts));
     CU(sim->meta.reserve(pts));
@@ -182,15 +217,13 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     CU(sim->unit_count.reserve(n_groups * sim->max_units));
     CU(sim->unit_order.reserve(n_groups * sim->max_units));
     CU(sim->n_units.reserve(n_groups));
-    CU(sim->group_count.reserve(n_groups));
-    CU(sim->pcnt.reserve(launch_events * ranks));
     CU(sim->pstart.reserve(launch_events * ranks));
     CU(sim->n_entries.reserve(launch_events));
     CU(sim->mode.reserve(launch_events));
     CU(sim->hash.reserve((int64_t)sim->group_events * sim->hash_cap));
     CU(sim->sort_items.reserve((int64_t)sim->group_events * sim->hash_cap * 2));
-    CU(sim->counters.reserve(1));
-    CU(sim->counters_host.reserve(1));
+    CU(sim->csr_total.reserve(2));
+    CU(sim->csr_host.reserve(2));
     return ATTPC_OK;
 }
 
@@ -202,17 +235,18 @@ int ensure_out_buffers(AttpcSim* sim, int64_t n_events, int64_t n_points, bool k
     return ATTPC_OK;
 }
 
-PointBuf point_buf(AttpcSim* sim) {
+PointBuf point_buf(AttpcSim* sim, int which) {
+    AttpcSim::LaunchSlot& ls = sim->slot[which];
     PointBuf pb;
-    pb.x = sim->px.p;
-    pb.y = sim->py.p;
-    pb.t = sim->pt.p;
-    pb.q = sim->pq.p;
-    pb.ev = sim->pev.p;
-    pb.rank = sim->prank.p;
-    pb.j = sim->pj.p;
-    pb.count = sim->group_count.p;
-    pb.cnt = sim->pcnt.p;
+    pb.x = ls.px.p;
+    pb.y = ls.py.p;
+    pb.t = ls.pt.p;
+    pb.q = ls.pq.p;
+    pb.ev = ls.pev.p;
+    pb.rank = ls.prank.p;
+    pb.j = ls.pj.p;
+    pb.count = ls.group_count.p;
+    pb.cnt = ls.pcnt.p;
     pb.start = sim->pstart.p;
     pb.geom = sim->geom.p;
     pb.sq = sim->sq.p;
@@ -230,18 +264,19 @@ PointBuf point_buf(AttpcSim* sim) {
 }
 
 template <bool RECORD>
-int launch_tracks(AttpcSim* sim, const TrackBatch& tb, int64_t n_tracks) {
+int launch_tracks(AttpcSim* sim, const TrackBatch& tb, int64_t n_tracks, int which, cudaStream_t stream) {
     const int threads = TRACK_THREADS;
     int64_t blocks64 = (n_tracks + threads - 1) / threads;
     const int max_blocks = sim->sm_count * 4;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(blocks64, max_blocks));
-    PointBuf pb = point_buf(sim);
+    PointBuf pb = point_buf(sim, which);
+    Counters* ctr = sim->slot[which].counters.p;
     if (sim->tables_in_smem) {
         auto kern = track_kernel<true, RECORD>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim->table_smem_bytes));
-        kern<<<blocks, threads, sim->table_smem_bytes, sim->stream>>>(sim->P, tb, pb, sim->counters.p);
+        kern<<<blocks, threads, sim->table_smem_bytes, stream>>>(sim->P, tb, pb, ctr);
     } else {
-        track_kernel<false, RECORD><<<blocks, threads, 0, sim->stream>>>(sim->P, tb, pb, sim->counters.p);
+        track_kernel<false, RECORD><<<blocks, threads, 0, stream>>>(sim->P, tb, pb, ctr);
     }
     sim->launches += 1;
     CU(cudaGetLastError());
@@ -249,12 +284,11 @@ int launch_tracks(AttpcSim* sim, const TrackBatch& tb, int64_t n_tracks) {
 }
 
 // deposit + finalize of every group of one launch; the track/replay kernel has already filled the point buffers.
-int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, float* ms_deposit, float* ms_finalize,
+int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
                std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& dep_marks,
                std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& fin_marks) {
-    (void)ms_deposit;
-    (void)ms_finalize;
-    PointBuf pb = point_buf(sim);
+    PointBuf pb = point_buf(sim, which);
+    Counters* ctr = sim->slot[which].counters.p;
     const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
     fa.sort_items = sim->sort_items.p;
     const size_t sort_smem = (size_t)SORT_SMEM_ITEMS * sizeof(uint64_t);
@@ -273,12 +307,11 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, float* ms_
         point_scan_kernel<<<1, 1024, 0, sim->stream>>>(pb, gv);
         point_order_kernel<<<sim->sm_count * 4, 256, 0, sim->stream>>>(sim->P, pb, gv);
         zero_shared_tables_kernel<<<gv.n_events, 256, 0, sim->stream>>>(gv);
-        deposit_kernel<<<sim->max_units, DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES, sim->stream>>>(sim->P, pb, gv,
-                                                                                             sim->counters.p);
+        deposit_kernel<<<sim->max_units, DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES, sim->stream>>>(sim->P, pb, gv, ctr);
         cudaEvent_t d1 = sim->mark();
-        collect_kernel<<<gv.n_events, FINALIZE_THREADS, sort_smem, sim->stream>>>(sim->P, fa, gv, sim->counters.p);
-        scan_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, sim->counters.p);
-        emit_kernel<<<gv.n_events, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, sim->counters.p);
+        collect_kernel<<<gv.n_events, FINALIZE_THREADS, sort_smem, sim->stream>>>(sim->P, fa, gv, ctr);
+        scan_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, ctr, sim->csr_total.p);
+        emit_kernel<<<gv.n_events, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
         cudaEvent_t f1 = sim->mark();
         sim->launches += 7;
         dep_marks.push_back({d0, d1});
@@ -368,42 +401,99 @@ struct LaunchPlan {
 };
 
 // Shared driver of attpc_simulate / attpc_simulate_dev / attpc_simulate_replay.
+//
+// Three streams: T runs the (latency-bound, few-warp) track kernel of launch i+1 while G runs the deposit and
+// finalize kernels of launch i, and C copies the finished rows of launch i-1 to the host.  After every launch the
+// host reads that launch's counters; a capacity overflow grows the buffer in question and redoes the launch.
 int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t flags, AttpcResult* res,
               float ms_h2d) {
     memset(res, 0, sizeof *res);
     sim->events_used = 0;
+    sim->sync_used = 0;
     sim->launches = 0;
     res->n_events = n_events;
     res->ms_h2d = ms_h2d;
+    const bool copy_host = !(flags & ATTPC_SKIP_HOST_COPY);
     int64_t out_cap = std::max<int64_t>(sim->labels_dev.n, std::max<int64_t>(n_events * 2048, 1 << 20));
     int rc = ensure_out_buffers(sim, n_events, out_cap, false);
     if (rc) return rc;
-    const int64_t launch_cap = plan.replay ? n_events : sim->launch_events;
+    // device-resident results: big launches (the latency-bound track kernel wants many tracks in flight);
+    // results copied to the host: smaller launches, so that the copy of one overlaps the compute of the next
+    const int64_t launch_cap = plan.replay ? std::max<int64_t>(n_events, 1)
+                               : copy_host ? std::min(sim->launch_events, sim->copy_launch_events)
+                                           : sim->launch_events;
     const int32_t ranks = std::max<int32_t>(1, plan.n_tracks_per_event);
     rc = ensure_work_buffers(sim, std::min<int64_t>(std::max<int64_t>(n_events, 1), launch_cap), ranks);
     if (rc) return rc;
-    CU(cudaMemsetAsync(sim->counters.p, 0, sizeof(Counters), sim->stream));
-    CU(cudaMemsetAsync(sim->offsets_dev.p, 0, sizeof(int64_t), sim->stream));
-    Counters snapshot;
-    memset(&snapshot, 0, sizeof snapshot);
+    if (copy_host) {  // pinned mirrors are sized like the device buffers: (re)allocated only when those grow
+        CU(sim->offsets_host.reserve(sim->offsets_dev.n));
+        CU(sim->cloud_host.reserve(sim->cloud_dev.n));
+        CU(sim->labels_host.reserve(sim->labels_dev.n));
+    }
+    cudaStream_t G = sim->stream, T = sim->stream_t, C = sim->stream_c;
+    CU(cudaMemsetAsync(sim->csr_total.p, 0, 2 * sizeof(unsigned long long), G));
+    CU(cudaMemsetAsync(sim->offsets_dev.p, 0, sizeof(int64_t), G));
+    cudaEvent_t t_begin = sim->mark(G);
+    CU(cudaStreamWaitEvent(T, t_begin, 0));
+    CU(cudaStreamWaitEvent(C, t_begin, 0));
 
-    cudaEvent_t t_begin = sim->mark();
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trk_marks, dep_marks, fin_marks;
+    const int64_t n_launch = n_events > 0 ? (n_events + launch_cap - 1) / launch_cap : 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trk_marks(n_launch), dep_marks, fin_marks, copy_marks;
+    std::vector<cudaEvent_t> track_done(n_launch);
+    Counters totals;
+    memset(&totals, 0, sizeof totals);
+    unsigned long long csr_before = 0;  // rows emitted by the launches completed so far
     int retries = 0;
-    for (int64_t b0 = 0; b0 < n_events;) {
-        const int64_t nb = std::min<int64_t>(launch_cap, n_events - b0);
-        rc = ensure_work_buffers(sim, nb, ranks);
-        if (rc) return rc;
-        const int64_t n_groups = (nb + sim->group_events - 1) / sim->group_events;
-        // restore the counters to the state before this launch (first attempt: no-op apart from the cursor)
-        snapshot.track_cursor = 0;
-        snapshot.overflow_points = snapshot.overflow_hash = snapshot.overflow_out = 0;
-        *sim->counters_host.p = snapshot;
-        CU(cudaMemcpyAsync(sim->counters.p, sim->counters_host.p, sizeof(Counters), cudaMemcpyHostToDevice,
-                           sim->stream));
-        CU(cudaMemsetAsync(sim->group_count.p, 0, (size_t)n_groups * sizeof(unsigned), sim->stream));
-        CU(cudaMemsetAsync(sim->pcnt.p, 0, (size_t)nb * ranks * sizeof(unsigned), sim->stream));
+    int64_t next_track = 0;  // launches whose track kernel is enqueued
 
+    auto enqueue_track = [&](int64_t i) -> int {
+        const int which = (int)(i & 1);
+        AttpcSim::LaunchSlot& ls = sim->slot[which];
+        const int64_t b0 = i * launch_cap, nb = std::min<int64_t>(launch_cap, n_events - b0);
+        const int64_t n_groups = (nb + sim->group_events - 1) / sim->group_events;
+        CU(cudaMemsetAsync(ls.counters.p, 0, sizeof(Counters), T));
+        CU(cudaMemsetAsync(ls.group_count.p, 0, (size_t)n_groups * sizeof(unsigned), T));
+        CU(cudaMemsetAsync(ls.pcnt.p, 0, (size_t)nb * ranks * sizeof(unsigned), T));
+        cudaEvent_t k0 = sim->mark(T);
+        if (plan.replay) {
+            const ReplayBatch& rb = *plan.replay;
+            if (rb.n_rows > 0) {
+                const int blocks = (int)((rb.n_rows + 255) / 256);
+                replay_kernel<<<blocks, 256, 0, T>>>(sim->P, rb, point_buf(sim, which), ls.counters.p);
+                sim->launches += 1;
+                CU(cudaGetLastError());
+            }
+        } else {
+            TrackBatch tb;
+            memset(&tb, 0, sizeof tb);
+            tb.momenta = plan.momenta_dev + b0 * plan.n_nuclei * 4;
+            tb.vertices = plan.vertices_dev + b0 * 3;
+            tb.n_events = nb;
+            tb.n_nuclei = plan.n_nuclei;
+            tb.n_tracks_per_event = plan.n_tracks_per_event;
+            for (int t = 0; t < plan.n_tracks_per_event; ++t) {
+                tb.nucleus[t] = plan.track_nucleus[t];
+                tb.species[t] = plan.track_species[t];
+            }
+            tb.seed = plan.seed;
+            tb.first_event = plan.first_event + b0;
+            int r = launch_tracks<false>(sim, tb, nb * plan.n_tracks_per_event, which, T);
+            if (r) return r;
+        }
+        cudaEvent_t k1 = sim->mark(T);
+        trk_marks[i] = {k0, k1};
+        track_done[i] = k1;
+        return ATTPC_OK;
+    };
+
+    for (int64_t i = 0; i < n_launch;) {
+        const int which = (int)(i & 1);
+        AttpcSim::LaunchSlot& ls = sim->slot[which];
+        const int64_t b0 = i * launch_cap, nb = std::min<int64_t>(launch_cap, n_events - b0);
+        while (next_track <= i) {
+            rc = enqueue_track(next_track++);
+            if (rc) return rc;
+        }
         FinalizeArgs fa;
         memset(&fa, 0, sizeof fa);
         fa.seed = plan.seed;
@@ -416,54 +506,35 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         fa.out_cap = sim->labels_dev.n;
         fa.replay = plan.uniforms;
         if (fa.replay.offsets) fa.replay.offsets += b0;
-
-        cudaEvent_t k0 = sim->mark();
+        fa.n_tracks_per_event = plan.n_tracks_per_event;
         if (plan.replay) {
-            const ReplayBatch& rb = *plan.replay;
-            fa.n_tracks_per_event = plan.n_tracks_per_event;
             fa.label_of_event_rank = plan.label_of_event_rank_dev;
-            if (rb.n_rows > 0) {
-                const int blocks = (int)((rb.n_rows + 255) / 256);
-                replay_kernel<<<blocks, 256, 0, sim->stream>>>(sim->P, rb, point_buf(sim), sim->counters.p);
-                sim->launches += 1;
-                CU(cudaGetLastError());
-            }
         } else {
-            TrackBatch tb;
-            memset(&tb, 0, sizeof tb);
-            tb.momenta = plan.momenta_dev + b0 * plan.n_nuclei * 4;
-            tb.vertices = plan.vertices_dev + b0 * 3;
-            tb.n_events = nb;
-            tb.n_nuclei = plan.n_nuclei;
-            tb.n_tracks_per_event = plan.n_tracks_per_event;
-            fa.n_tracks_per_event = plan.n_tracks_per_event;
-            for (int t = 0; t < plan.n_tracks_per_event; ++t) {
-                tb.nucleus[t] = plan.track_nucleus[t];
-                tb.species[t] = plan.track_species[t];
-                fa.label_of_rank[t] = plan.track_nucleus[t];
-            }
-            tb.seed = plan.seed;
-            tb.first_event = plan.first_event + b0;
-            rc = launch_tracks<false>(sim, tb, nb * plan.n_tracks_per_event);
+            for (int t = 0; t < plan.n_tracks_per_event; ++t) fa.label_of_rank[t] = plan.track_nucleus[t];
+        }
+        CU(cudaStreamWaitEvent(G, track_done[i], 0));
+        const size_t dep_before = dep_marks.size(), fin_before = fin_marks.size();
+        rc = run_groups(sim, nb, fa, which, dep_marks, fin_marks);
+        if (rc) return rc;
+        publish_kernel<<<1, 1, 0, G>>>(ls.counters.p, sim->csr_total.p, ls.counters_host.p, sim->csr_host.p);
+        sim->launches += 1;
+        cudaEvent_t groups_done = sim->fence(G);
+        if (next_track <= i + 1 && i + 1 < n_launch) {  // overlaps with the groups just enqueued
+            rc = enqueue_track(next_track++);
             if (rc) return rc;
         }
-        cudaEvent_t k1 = sim->mark();
-        const size_t dep_before = dep_marks.size(), fin_before = fin_marks.size();
-        rc = run_groups(sim, nb, fa, nullptr, nullptr, dep_marks, fin_marks);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(sim->counters_host.p, sim->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost,
-                           sim->stream));
-        CU(cudaStreamSynchronize(sim->stream));
-        const Counters now = *sim->counters_host.p;
+        CU(cudaEventSynchronize(groups_done));
+        const Counters now = *ls.counters_host.p;
         if (now.replay_miss) return sim->fail(ATTPC_E_BADARG, "replay uniforms do not cover every (event, key)");
         if (now.overflow_points || now.overflow_hash || now.overflow_out) {
             dep_marks.resize(dep_before);
             fin_marks.resize(fin_before);
             if (++retries > 24) return sim->fail(ATTPC_E_CAPACITY, "buffers still too small after 24 retries");
+            CU(cudaStreamSynchronize(T));  // the next launch's track kernel may be using buffers we are about to free
+            CU(cudaStreamSynchronize(C));
             if (now.overflow_points) {
                 sim->group_point_cap *= 2;
-                sim->px.release(); sim->py.release(); sim->pt.release();
-                sim->pq.release(); sim->pev.release(); sim->prank.release(); sim->pj.release();
+                for (auto& s2 : sim->slot) s2.release_points();
                 sim->geom.release(); sim->sq.release(); sim->meta.release();
                 sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release();
                 sim->unit_order.release();
@@ -475,45 +546,64 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 sim->sort_items.release();
             }
             if (now.overflow_out) {
-                out_cap = std::max<int64_t>(sim->labels_dev.n * 2, (int64_t)now.out_points + (1 << 20));
+                out_cap = std::max<int64_t>(sim->labels_dev.n * 2, (int64_t)sim->csr_host.p[0] + (1 << 20));
                 rc = ensure_out_buffers(sim, n_events, out_cap, true);
                 if (rc) return rc;
+                if (copy_host) {
+                    CU(sim->cloud_host.reserve(sim->cloud_dev.n, true));
+                    CU(sim->labels_host.reserve(sim->labels_dev.n, true));
+                }
             }
-            continue;  // redo this launch
+            rc = ensure_work_buffers(sim, std::min<int64_t>(n_events, launch_cap), ranks);
+            if (rc) return rc;
+            sim->csr_host.p[0] = csr_before;  // forget the rows of the failed attempt
+            sim->csr_host.p[1] = 0;
+            CU(cudaMemcpyAsync(sim->csr_total.p, sim->csr_host.p, 2 * sizeof(unsigned long long),
+                               cudaMemcpyHostToDevice, G));
+            CU(cudaStreamSynchronize(G));
+            next_track = i;  // redo this launch (and the one that was running ahead)
+            continue;
         }
-        trk_marks.push_back({k0, k1});
-        snapshot = now;
-        b0 += nb;
+        totals.traj_points += now.traj_points;
+        totals.active_points += now.active_points;
+        totals.primary_electrons += now.primary_electrons;
+        totals.deposits += now.deposits;
+        totals.keys += now.keys;
+        totals.probes += now.probes;
+        const unsigned long long csr_after = sim->csr_host.p[0];
+        if (copy_host) {  // rows of this launch go home while the next launch computes
+            CU(cudaStreamWaitEvent(C, groups_done, 0));
+            cudaEvent_t c0 = sim->mark(C);
+            const int64_t first_off = b0 == 0 ? 0 : b0 + 1;  // offsets[b0] was already copied with the previous launch
+            CU(cudaMemcpyAsync(sim->offsets_host.p + first_off, sim->offsets_dev.p + first_off,
+                               (size_t)(b0 + nb + 1 - first_off) * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+            const int64_t n_new = (int64_t)(csr_after - csr_before);
+            if (n_new > 0) {
+                CU(cudaMemcpyAsync(sim->cloud_host.p + csr_before * 3, sim->cloud_dev.p + csr_before * 3,
+                                   (size_t)n_new * 3 * sizeof(double), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->labels_host.p + csr_before, sim->labels_dev.p + csr_before,
+                                   (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+            }
+            copy_marks.push_back({c0, sim->mark(C)});
+        }
+        csr_before = csr_after;
+        ++i;
     }
-    cudaEvent_t t_compute_end = sim->mark();
-
-    const int64_t n_points = (int64_t)snapshot.out_points;
+    const int64_t n_points = (int64_t)csr_before;
     res->n_points = n_points;
     res->offsets_dev = sim->offsets_dev.p;
     res->cloud_dev = sim->cloud_dev.p;
     res->labels_dev = sim->labels_dev.p;
-    res->n_tracks = 0;
-    res->n_trajectory_points = (int64_t)snapshot.traj_points;
-    res->n_active_points = (int64_t)snapshot.active_points;
-    res->n_primary_electrons = (int64_t)snapshot.primary_electrons;
-    res->n_deposits = (int64_t)snapshot.deposits;
-    res->n_keys = (int64_t)snapshot.keys;
+    res->n_trajectory_points = (int64_t)totals.traj_points;
+    res->n_active_points = (int64_t)totals.active_points;
+    res->n_primary_electrons = (int64_t)totals.primary_electrons;
+    res->n_deposits = (int64_t)totals.deposits;
+    res->n_keys = (int64_t)totals.keys;
+    res->n_hash_probes = (int64_t)totals.probes;
     res->n_retries = retries;
-
-    const bool copy_host = !(flags & ATTPC_SKIP_HOST_COPY);
-    cudaEvent_t t_d2h0 = sim->mark();
     if (copy_host) {
-        // pinned mirrors are sized like the device buffers so that they are (re)allocated only when those grow
-        CU(sim->offsets_host.reserve(sim->offsets_dev.n));
-        CU(sim->cloud_host.reserve(sim->cloud_dev.n));
-        CU(sim->labels_host.reserve(sim->labels_dev.n));
-        CU(cudaMemcpyAsync(sim->offsets_host.p, sim->offsets_dev.p, (size_t)(n_events + 1) * sizeof(int64_t),
-                           cudaMemcpyDeviceToHost, sim->stream));
-        if (n_points > 0) {
-            CU(cudaMemcpyAsync(sim->cloud_host.p, sim->cloud_dev.p, (size_t)n_points * 3 * sizeof(double),
-                               cudaMemcpyDeviceToHost, sim->stream));
-            CU(cudaMemcpyAsync(sim->labels_host.p, sim->labels_dev.p, (size_t)n_points * sizeof(int64_t),
-                               cudaMemcpyDeviceToHost, sim->stream));
+        if (n_events == 0) {
+            CU(cudaMemcpyAsync(sim->offsets_host.p, sim->offsets_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, C));
         }
         res->offsets = sim->offsets_host.p;
         res->cloud = sim->cloud_host.p;
@@ -523,20 +613,20 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         rc = run_spyral(sim, n_events, n_points, res, copy_host);
         if (rc) return rc;
     }
-    cudaEvent_t t_end = sim->mark();
-    CU(cudaStreamSynchronize(sim->stream));
+    // close the timeline on G after the other two streams have drained
+    CU(cudaStreamWaitEvent(G, sim->fence(T), 0));
+    CU(cudaStreamWaitEvent(G, sim->fence(C), 0));
+    cudaEvent_t t_end = sim->mark(G);
+    CU(cudaStreamSynchronize(G));
     res->ms_tracks = sum_ms(trk_marks);
     res->ms_deposit = sum_ms(dep_marks);
     res->ms_finalize = sum_ms(fin_marks);
-    cudaEventElapsedTime(&res->ms_d2h, t_d2h0, t_end);
-    float ms_compute = 0.f;
-    cudaEventElapsedTime(&ms_compute, t_begin, t_compute_end);
+    res->ms_d2h = sum_ms(copy_marks);
     cudaEventElapsedTime(&res->ms_total, t_begin, t_end);
     res->ms_total += ms_h2d;
     res->n_kernel_launches = sim->launches;
     res->n_track_launches = (int32_t)trk_marks.size();
     res->n_group_launches = (int32_t)dep_marks.size();
-    res->n_hash_probes = (int64_t)snapshot.probes;
     res->hash_capacity = sim->hash_cap;
     return ATTPC_OK;
 }
@@ -575,22 +665,27 @@ void attpc_destroy(AttpcSim* sim) {
     if (!sim) return;
     cudaSetDevice(sim->device);
     if (sim->stream) cudaStreamSynchronize(sim->stream);
+    if (sim->stream_t) cudaStreamSynchronize(sim->stream_t);
+    if (sim->stream_c) cudaStreamSynchronize(sim->stream_c);
     for (auto e : sim->events) cudaEventDestroy(e);
+    for (auto e : sim->sync_events) cudaEventDestroy(e);
+    for (auto& ls : sim->slot) ls.release_all();
+    sim->csr_total.release(); sim->csr_host.release();
+    if (sim->stream_t) cudaStreamDestroy(sim->stream_t);
+    if (sim->stream_c) cudaStreamDestroy(sim->stream_c);
     sim->lut.release(); sim->pad_xy.release(); sim->pad_scale.release(); sim->response.release();
     sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release();
-    sim->px.release(); sim->py.release(); sim->pt.release(); sim->pq.release(); sim->pev.release();
-    sim->prank.release(); sim->group_count.release(); sim->hash.release(); sim->sort_items.release();
-    sim->pj.release(); sim->geom.release(); sim->sq.release(); sim->meta.release();
+    sim->hash.release(); sim->sort_items.release();
+    sim->geom.release(); sim->sq.release(); sim->meta.release();
     sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release(); sim->unit_order.release();
     sim->n_units.release();
-    sim->pcnt.release(); sim->pstart.release(); sim->n_entries.release(); sim->mode.release();
-    sim->counters.release(); sim->kept.release(); sim->in_momenta.release(); sim->in_vertices.release();
+    sim->pstart.release(); sim->n_entries.release(); sim->mode.release();
+    sim->kept.release(); sim->in_momenta.release(); sim->in_vertices.release();
     sim->offsets_dev.release(); sim->labels_dev.release(); sim->row_offsets_dev.release();
     sim->row_labels_dev.release(); sim->cloud_dev.release(); sim->rows_dev.release(); sim->row_kept.release();
     sim->row_sort_keys.release(); sim->row_sort_idx.release();
     sim->offsets_host.release(); sim->labels_host.release(); sim->row_offsets_host.release();
     sim->row_labels_host.release(); sim->cloud_host.release(); sim->rows_host.release();
-    sim->counters_host.release();
     if (sim->stream) cudaStreamDestroy(sim->stream);
     delete sim;
 }
@@ -638,6 +733,8 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
         }                                                                                           \
     } while (0)
     CUC(cudaStreamCreateWithFlags(&sim->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&sim->stream_t, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&sim->stream_c, cudaStreamNonBlocking));
     int sm = 0;
     CUC(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
     sim->sm_count = sm > 0 ? sm : 148;
@@ -670,6 +767,7 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
     P.n_pads = n_pads;
     P.n_response = n_response;
     if (cfg->max_events_per_launch > 0) sim->launch_events = cfg->max_events_per_launch;
+    if (cfg->copy_events_per_launch > 0) sim->copy_launch_events = cfg->copy_events_per_launch;  // events per launch when rows go to the host
     if (cfg->hash_capacity > 0) sim->hash_cap = next_pow2(cfg->hash_capacity);
     sim->group_events = std::min(sim->group_events, sim->launch_events);
 
@@ -921,7 +1019,7 @@ int attpc_trajectories(AttpcSim* sim, const double* momenta, const double* verti
         ok(cudaMemcpyAsync(d_sp.p, species, (size_t)n_tracks * sizeof(int32_t), cudaMemcpyHostToDevice, sim->stream)) &&
         ok(cudaMemsetAsync(d_out.p, 0, (size_t)n_tracks * max_points * 6 * sizeof(double), sim->stream)) &&
         ok(cudaMemsetAsync(d_cnt.p, 0, (size_t)n_tracks * sizeof(int32_t), sim->stream)) &&
-        ok(cudaMemsetAsync(sim->counters.p, 0, sizeof(Counters), sim->stream));
+        ok(cudaMemsetAsync(sim->slot[0].counters.p, 0, sizeof(Counters), sim->stream));
     if (e != cudaSuccess) {
         cleanup();
         return sim->fail(ATTPC_E_CUDA, "attpc_trajectories setup: %s", cudaGetErrorString(e));
@@ -938,7 +1036,7 @@ int attpc_trajectories(AttpcSim* sim, const double* momenta, const double* verti
     tb.rec_counts = d_cnt.p;
     tb.rec_stride = stride;
     tb.rec_max = max_points;
-    rc = launch_tracks<true>(sim, tb, n_tracks);
+    rc = launch_tracks<true>(sim, tb, n_tracks, 0, sim->stream);
     if (rc == ATTPC_OK) {
         ok(cudaMemcpyAsync(out_points, d_out.p, (size_t)n_tracks * max_points * 6 * sizeof(double),
                            cudaMemcpyDeviceToHost, sim->stream)) &&

@@ -92,12 +92,22 @@ struct PointBuf {
     int32_t max_units;  // capacity of the unit arrays per group
 };
 
+// Per-launch counters (one set per in-flight launch; zeroed when the launch starts).
 struct Counters {
     unsigned long long track_cursor;
     unsigned long long traj_points, active_points, primary_electrons, deposits, keys, probes;
-    unsigned long long out_points, out_rows;   // running CSR totals
     int overflow_points, overflow_hash, overflow_out, replay_miss;
 };
+
+// Publish a launch's counters and the running CSR totals into mapped host memory.  A copy-engine transfer would
+// queue behind the (large) device-to-host copy of the previous launch's rows and stall the compute stream.
+__global__ void publish_kernel(const Counters* ctr, const unsigned long long* csr, Counters* host_ctr,
+                               unsigned long long* host_csr) {
+    *host_ctr = *ctr;
+    host_csr[0] = csr[0];
+    host_csr[1] = csr[1];
+    __threadfence_system();
+}
 
 struct HashEntry {
     unsigned key1;   // Szudzik key + 1, 0 = empty
@@ -1150,11 +1160,11 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
 
 // Exclusive scan of the kept counts of one group onto the running CSR total (single CTA).
 __global__ void __launch_bounds__(1024)
-scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr) {
+scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr, unsigned long long* csr_total) {
     __shared__ unsigned long long s_part[1024];
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x;
-    if (tid == 0) s_base = ctr->out_points;
+    if (tid == 0) s_base = *csr_total;
     __syncthreads();
     for (int start = 0; start < gv.n_events; start += 1024) {
         const int i = start + tid;
@@ -1174,7 +1184,7 @@ scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr) {
     }
     if (tid == 0) {
         fa.offsets[gv.first_slot + gv.n_events] = (int64_t)s_base;
-        ctr->out_points = s_base;
+        *csr_total = s_base;
         if ((int64_t)s_base > fa.out_cap) ctr->overflow_out = 1;
     }
 }

@@ -111,6 +111,7 @@ class Engine:
         freeze_ke_mev: float | None = None,
         max_events_per_launch: int = 0,
         hash_capacity: int = 0,
+        copy_events_per_launch: int = 0,
     ):
         if config.pad_grid is None or config.pad_grid_edges is None:
             raise ValueError("Pad grid is not loaded")  # solver.py:400-401
@@ -158,6 +159,7 @@ class Engine:
         cfg.freeze_ke_mev = self.freeze_ke_mev
         cfg.max_events_per_launch = int(max_events_per_launch)
         cfg.hash_capacity = int(hash_capacity)
+        cfg.copy_events_per_launch = int(copy_events_per_launch)
 
         sp = (_lib.AttpcSpecies * len(self.species))()
         for i, (nuc, tab) in enumerate(zip(self.species, tables)):
