@@ -288,11 +288,12 @@ __device__ __forceinline__ State dense_eval(const State& y0, const Dense& d, dou
 }
 
 constexpr double MAX_STEP_CELLS = 64.0;  // a step never spans more than 64 grid cells (6.4 ns)
+constexpr int EMIT_CHUNK = 8;            // grid points a lane emits between two integrator steps of the warp
 
 // Standard step-size controller of an order-5 pair: factor = 0.9 err^(-1/5), limited to [0.2, 5].
 __device__ __forceinline__ double step_factor(double err) {
     if (!(err > 1e-10)) return 5.0;
-    return fmin(5.0, fmax(0.2, 0.9 * exp(-0.2 * log(err))));
+    return (double)fminf(5.0f, fmaxf(0.2f, 0.9f * exp2f(-0.2f * log2f((float)err))));  // step control needs no FP64
 }
 
 // scipy's event rule (scipy/integrate/_ivp/ivp.py: find_active_events) applied per grid cell, with the
@@ -300,11 +301,13 @@ __device__ __forceinline__ double step_factor(double err) {
 __device__ __forceinline__ bool crossed_up(double g0, double g1) { return g0 <= 0.0 && g1 >= 0.0; }
 __device__ __forceinline__ bool crossed_down(double g0, double g1) { return g0 >= 0.0 && g1 <= 0.0; }
 
+// The radial bound is tested on rho^2 - R^2, which has the sign of rho - R; all four tests are evaluated (bitwise or)
+// so that the warp does not diverge on them.
 __device__ __forceinline__ bool terminal_event(const TrackConst& c, const State& a, const State& b, double ke_a,
                                                double ke_b) {
-    return crossed_down(ke_a - KE_LIMIT, ke_b - KE_LIMIT) || crossed_up(a.z - Z_HI, b.z - Z_HI) ||
-           crossed_down(a.z - Z_LO, b.z - Z_LO) ||
-           crossed_up(hypot(a.x, a.y) - RHO_MAX, hypot(b.x, b.y) - RHO_MAX);
+    const double ra = a.x * a.x + a.y * a.y - RHO_MAX * RHO_MAX, rb = b.x * b.x + b.y * b.y - RHO_MAX * RHO_MAX;
+    return crossed_down(ke_a - KE_LIMIT, ke_b - KE_LIMIT) | crossed_up(a.z - Z_HI, b.z - Z_HI) |
+           crossed_down(a.z - Z_LO, b.z - Z_LO) | crossed_up(ra, rb);
 }
 
 __device__ __forceinline__ unsigned lanemask_lt() {
@@ -333,6 +336,59 @@ __device__ __forceinline__ void append_point(const PointBuf& pb, Counters* ctr, 
     pb.j[i] = atomicAdd(&pb.cnt[(int64_t)ev * pb.ranks + rank], 1u);
 }
 
+// Points staged by one lane of the track kernel between two flushes (shared memory, EMIT_CHUNK per lane).
+struct StagedPoint {
+    double x, y, t;
+    long long q;
+};
+
+// Flush the staged points of a warp: one atomic on the group counter per warp (all lanes of a warp almost always
+// work on tracks of the same event group), then every lane stores its own run.  `j0` is the arrival index of the
+// lane's first staged point inside its track; the track kernel owns a track from start to end, so no atomic is
+// needed for it.
+__device__ __forceinline__ void flush_staged(const PointBuf& pb, Counters* ctr, const StagedPoint* mine, int n,
+                                             int ev, int rank, unsigned j0) {
+    const unsigned lane = threadIdx.x & 31;
+    const int g = n > 0 ? ev / pb.group_events : -1;
+    const unsigned active = __ballot_sync(FULL, n > 0);
+    if (active == 0u) return;
+    const int leader = __ffs(active) - 1;
+    const int g0 = __shfl_sync(FULL, g, leader);
+    const bool uniform = __all_sync(FULL, n == 0 || g == g0);
+    unsigned pos = 0;
+    if (uniform) {
+        unsigned incl = (unsigned)n;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= (unsigned)o) incl += v;
+        }
+        const unsigned total = __shfl_sync(FULL, incl, 31);
+        unsigned base = 0;
+        if (lane == (unsigned)leader) base = atomicAdd(&pb.count[g0], total);
+        base = __shfl_sync(FULL, base, leader);
+        pos = base + incl - (unsigned)n;
+    } else if (n > 0) {
+        pos = atomicAdd(&pb.count[g], (unsigned)n);
+    }
+    if (n > 0) {
+        if ((int64_t)pos + n > pb.group_cap) {
+            ctr->overflow_points = 1;
+            return;
+        }
+        const int64_t i0 = (int64_t)g * pb.group_cap + pos;
+        for (int k = 0; k < n; ++k) {
+            const StagedPoint sp = mine[k];
+            pb.x[i0 + k] = sp.x;
+            pb.y[i0 + k] = sp.y;
+            pb.t[i0 + k] = sp.t;
+            pb.q[i0 + k] = sp.q;
+            pb.ev[i0 + k] = ev;
+            pb.rank[i0 + k] = rank;
+            pb.j[i0 + k] = j0 + (unsigned)k;
+        }
+    }
+}
+
 struct TrackBatch {
     const double* momenta;   // [n_events, n_nuclei, 4]
     const double* vertices;  // [n_events, 3]
@@ -354,9 +410,11 @@ constexpr int TRACK_THREADS = 128;
 // One lane integrates one track at a time and pulls the next from a global cursor when it finishes, so short
 // (exiting) tracks do not wait for the long (stopping) tracks of the same warp.
 template <bool TAB_SMEM, bool RECORD>
-__global__ void __launch_bounds__(TRACK_THREADS)
+__global__ void __launch_bounds__(TRACK_THREADS, 3)
 track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackBatch tb, PointBuf pb, Counters* ctr) {
     extern __shared__ double s_tab[];
+    __shared__ StagedPoint s_stage[RECORD ? 1 : TRACK_THREADS * EMIT_CHUNK];
+    StagedPoint* mine = s_stage + (RECORD ? 0 : threadIdx.x * EMIT_CHUNK);
     if (TAB_SMEM) {
         const int n = P.n_species * P.n_nodes;
         for (int i = threadIdx.x; i < n; i += blockDim.x) s_tab[i] = P.tables[i];
@@ -368,6 +426,11 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
     bool have = false, done = false;
     TrackConst c;
     State y, k, y_grid;          // integrator state at time tc, its derivative, state at the last grid point
+    State yn, kn;                // end state of the accepted step whose grid points are being emitted
+    Dense dense;                 // ... and its continuous extension
+    double h = 0.0, err = 0.0, t_end = 0.0;
+    int pending = 0;             // grid points of the accepted step still to emit
+    unsigned n_out = 0;          // active points this track has produced so far
     double ke = 0.0;             // kinetic energy at the last grid point
     double tc = 0.0, hc = 1.0;   // time and step size in units of grid cells (0.1 ns)
     int step = 0, ev = 0, rank = 0, nucleus = 0;
@@ -405,6 +468,8 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
                     step = 0;
                     tc = 0.0;
                     hc = 1.0;
+                    pending = 0;
+                    n_out = 0;
                     have = true;
                     n_traj += 1;  // grid point 0 (never active: detector/solver.py:338-339)
                     if (RECORD && tb.rec_max > 0) {
@@ -417,63 +482,82 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
             }
         }
         if (__all_sync(FULL, done)) break;
-        if (!have) continue;
 
-        // one Dormand-Prince attempt of hc grid cells from tc
-        State yn, kn;
-        Dense dense;
-        const double h = hc * GRID_DT;
-        const double err = dopri5_step(c, y, k, h, P.rtol, P.atol, yn, kn, dense);
-        if (!(err <= 1.0) && hc > 1.0 / 4096.0) {  // reject: retry with a smaller step
-            hc *= (err == err) ? fmin(0.9, step_factor(err)) : 0.2;
-            continue;
-        }
-        // accepted: emit every grid point inside (tc, tc + hc]
-        const double t_end = tc + hc;
-        bool finished = false;
-        while (!finished && (double)(step + 1) <= t_end + 1e-9) {
-            const double theta = fmin(1.0, ((double)(step + 1) - tc) / hc);
-            const State g = theta >= 1.0 ? yn : dense_eval(y, dense, h, theta);
-            const double ke_g = kinetic_energy(c, g.ux, g.uy, g.uz);
-            if (terminal_event(c, y_grid, g, ke, ke_g)) {
-                finished = true;
-                break;
-            }
-            step += 1;
-            n_traj += 1;
-            if (RECORD) {
-                if (step % tb.rec_stride == 0 && step / tb.rec_stride < tb.rec_max) {
-                    double* o = tb.rec_points + ((int64_t)track * tb.rec_max + step / tb.rec_stride) * 6;
-                    o[0] = g.x; o[1] = g.y; o[2] = g.z; o[3] = g.ux; o[4] = g.uy; o[5] = g.uz;
-                }
+        // ---- phase A: lanes with no grid point left to emit try one Dormand-Prince step of hc grid cells from tc
+        if (have && pending == 0) {
+            h = hc * GRID_DT;
+            err = dopri5_step(c, y, k, h, P.rtol, P.atol, yn, kn, dense);
+            if (!(err <= 1.0) && hc > 1.0 / 4096.0) {  // reject: retry with a smaller step
+                hc *= (err == err) ? fmin(0.9, step_factor(err)) : 0.2;
             } else {
-                // detector/solver.py:338-346: mean = |dKE| / W, Gaussian with variance F * mean, truncation
-                const double mean = fabs(ke_g - ke) * P.ev_per_w;
-                const double spread = sqrt(P.fano * mean);
-                if (mean + spread * NORMAL_ABS_MAX >= 1.0) {
-                    const double zn =
-                        philox_normal(tb.seed, (uint64_t)(tb.first_event + ev), (uint32_t)nucleus, (uint32_t)step);
-                    const long long n_e = (long long)(mean + spread * zn);
-                    if (n_e >= 1) {  // detector/solver.py:387
-                        const double time = (P.length - g.z) / P.dv + P.mm_edge;  // detector/solver.py:396-398
-                        append_point(pb, ctr, true, ev, rank, g.x, g.y, time, n_e * P.gain);  // gain: solver.py:392
-                        n_active += 1;
-                        n_prim += (unsigned long long)n_e;
+                t_end = tc + hc;
+                pending = max(0, (int)floor(t_end + 1e-9) - step);  // grid points inside (tc, tc + hc]
+                if (pending == 0) {  // step ends before the next grid point: just advance
+                    tc = t_end;
+                    y = yn;
+                    k = kn;
+                    hc = fmin(MAX_STEP_CELLS, hc * step_factor(err));
+                }
+            }
+        }
+        // ---- phase B: every lane emits up to EMIT_CHUNK of its pending grid points.  Lanes stay in lock step, so the
+        //      per-point code runs converged even though steps of different lanes span 1..64 grid cells.
+        bool finished = false;
+        int n_staged = 0;
+#pragma unroll 1
+        for (int it = 0; it < EMIT_CHUNK; ++it) {
+            if (pending > 0 && !finished) {
+                const double theta = fmin(1.0, ((double)(step + 1) - tc) / hc);
+                const State g = theta >= 1.0 ? yn : dense_eval(y, dense, h, theta);
+                const double ke_g = kinetic_energy(c, g.ux, g.uy, g.uz);
+                pending -= 1;
+                if (terminal_event(c, y_grid, g, ke, ke_g)) {
+                    finished = true;
+                } else {
+                    step += 1;
+                    n_traj += 1;
+                    if (RECORD) {
+                        if (step % tb.rec_stride == 0 && step / tb.rec_stride < tb.rec_max) {
+                            double* o = tb.rec_points + ((int64_t)track * tb.rec_max + step / tb.rec_stride) * 6;
+                            o[0] = g.x; o[1] = g.y; o[2] = g.z; o[3] = g.ux; o[4] = g.uy; o[5] = g.uz;
+                        }
+                    } else {
+                        // detector/solver.py:338-346: mean = |dKE| / W, Gaussian with variance F * mean, truncation
+                        const double mean = fabs(ke_g - ke) * P.ev_per_w;
+                        const double spread = sqrt(P.fano * mean);
+                        if (mean + spread * NORMAL_ABS_MAX >= 1.0) {
+                            const double zn = philox_normal(tb.seed, (uint64_t)(tb.first_event + ev),
+                                                            (uint32_t)nucleus, (uint32_t)step);
+                            const long long n_e = (long long)(mean + spread * zn);
+                            if (n_e >= 1) {  // detector/solver.py:387
+                                const double time = (P.length - g.z) / P.dv + P.mm_edge;  // solver.py:396-398
+                                mine[n_staged++] = StagedPoint{g.x, g.y, time, n_e * P.gain};      // solver.py:392
+                                n_active += 1;
+                                n_prim += (unsigned long long)n_e;
+                            }
+                        }
+                    }
+                    y_grid = g;
+                    ke = ke_g;
+                    if (step >= GRID_POINTS - 1 || inert_forever(c, g, ke, P.freeze_ke)) finished = true;
+                    if (pending == 0 && !finished) {  // all grid points of the step are out: advance the integrator
+                        tc = t_end;
+                        y = yn;
+                        k = kn;
+                        hc = fmin(MAX_STEP_CELLS, hc * step_factor(err));
                     }
                 }
             }
-            y_grid = g;
-            ke = ke_g;
-            if (step >= GRID_POINTS - 1 || inert_forever(c, g, ke, P.freeze_ke)) finished = true;
+        }
+        if (!RECORD) {
+            flush_staged(pb, ctr, mine, n_staged, ev, rank, n_out);
+            n_out += (unsigned)n_staged;
         }
         if (finished) {
             have = false;
+            pending = 0;
             if (RECORD) tb.rec_counts[track] = step + 1;
-        } else {
-            tc = t_end;
-            y = yn;
-            k = kn;
-            hc = fmin(MAX_STEP_CELLS, hc * step_factor(err));
+            else pb.cnt[(int64_t)ev * pb.ranks + rank] = n_out;  // length of this track's list (no other writer)
         }
     }
     // per-warp statistics

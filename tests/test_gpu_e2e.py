@@ -186,3 +186,48 @@ def test_distributions_match_reference(dist, name):
     for label, (ours, ref) in checks.items():
         p = ks_2samp(ours, ref).pvalue
         assert p > 0.01, f"{name}: {label}: KS p = {p:.4f}"
+
+
+def _full_size_batch(name, n_events, seed):
+    import bench
+
+    config, momenta, vertices, zs, as_, indices = bench.build_workload(name, n_events)
+    return config, zs, indices, simulate_batch(momenta, vertices, zs, as_, config, seed, indices), (momenta, vertices, as_)
+
+
+@pytest.mark.parametrize("name, n_events", [("c16dd", 10000), ("c14dp", 4000), ("c12aa", 2000), ("sn132dp", 2000)])
+def test_full_size_properties(name, n_events):
+    """Size-independent properties at BASELINE.json config sizes (10k events is the reference's documented run)."""
+    from attpc_engine_b200.detector.beam_pads import BEAM_PADS_ARRAY
+
+    config, zs, indices, batch, (momenta, vertices, as_) = _full_size_batch(name, n_events, 99)
+    off, cloud, labels = batch.offsets, batch.cloud, batch.labels
+    assert len(off) == n_events + 1 and off[0] == 0 and off[-1] == len(cloud) == len(labels)
+    assert np.all(np.diff(off) >= 0)
+    pad, tbf, charge = cloud[:, 0], cloud[:, 1], cloud[:, 2]
+    tb = np.floor(tbf)
+    assert np.all((tbf >= 0) & (tbf < 512)) and np.all(tb >= config.elec_params.micromegas_edge)
+    assert np.all((pad >= 0) & (pad < 10240) & (pad == np.floor(pad)))
+    assert not np.isin(pad.astype(np.int64), BEAM_PADS_ARRAY).any()  # beam pads never fire
+    assert np.all(charge >= 0) and np.all(charge == np.floor(charge))
+    charged = [i for i in indices if zs[i] != 0]
+    assert set(np.unique(labels)) <= set(charged)
+    # canonical order inside every event: strictly ascending (time bucket, pad), hence unique keys
+    key = tb * 16384 + pad
+    inner = np.ones(len(key), dtype=bool)
+    inner[off[1:-1][off[1:-1] < len(key)]] = False  # first row of an event may restart the order
+    assert np.all(np.diff(key)[inner[1:]] > 0)
+    # electrons are conserved up to the mesh truncation: the 10x10 mesh integrates 99.8627 % of the Gaussian and
+    # every pixel truncates to an integer, so the cloud can never hold more than gain * primaries
+    gain = config.det_params.mpgd_gain
+    assert charge.sum() <= batch.stats["n_primary_electrons"] * gain
+    assert batch.stats["n_deposits"] <= 100 * batch.stats["n_active_points"]
+    assert batch.stats["n_hash_probes"] < 3 * batch.stats["n_deposits"]
+    # determinism: the same seed reproduces the batch bit for bit; sharding it reproduces it too
+    again = simulate_batch(momenta, vertices, zs, as_, config, 99, indices)
+    assert np.array_equal(again.offsets, off) and np.array_equal(again.cloud, cloud) and np.array_equal(again.labels, labels)
+    half = n_events // 2
+    a = simulate_batch(momenta[:half], vertices[:half], zs, as_, config, 99, indices, first_event=0)
+    b = simulate_batch(momenta[half:], vertices[half:], zs, as_, config, 99, indices, first_event=half)
+    merged = concat_batches([a, b])
+    assert np.array_equal(merged.offsets, off) and np.array_equal(merged.cloud, cloud)
