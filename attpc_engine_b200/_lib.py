@@ -103,6 +103,7 @@ class AttpcResult(C.Structure):
         ("n_hash_probes", C.c_int64),
         ("hash_capacity", C.c_int32),
         ("reserved1", C.c_int32),
+        ("n_table_flushes", C.c_int64),
     ]
 
 

@@ -570,6 +570,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         totals.deposits += now.deposits;
         totals.keys += now.keys;
         totals.probes += now.probes;
+        totals.flushes += now.flushes;
         const unsigned long long csr_after = sim->csr_host.p[0];
         if (copy_host) {  // rows of this launch go home while the next launch computes
             CU(cudaStreamWaitEvent(C, groups_done, 0));
@@ -600,6 +601,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     res->n_deposits = (int64_t)totals.deposits;
     res->n_keys = (int64_t)totals.keys;
     res->n_hash_probes = (int64_t)totals.probes;
+    res->n_table_flushes = (int64_t)totals.flushes;
     res->n_retries = retries;
     if (copy_host) {
         if (n_events == 0) {

@@ -95,7 +95,7 @@ struct PointBuf {
 // Per-launch counters (one set per in-flight launch; zeroed when the launch starts).
 struct Counters {
     unsigned long long track_cursor;
-    unsigned long long traj_points, active_points, primary_electrons, deposits, keys, probes;
+    unsigned long long traj_points, active_points, primary_electrons, deposits, keys, probes, flushes;
     int overflow_points, overflow_hash, overflow_out, replay_miss;
 };
 
@@ -966,6 +966,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
         if (threadIdx.x == 0) {
             s_nkeys = 0;
             s_spilled = 1;
+            atomicAdd(&ctr->flushes, 1ULL);
         }
         __syncthreads();
     };

@@ -94,7 +94,7 @@ def _ptr(arr: np.ndarray, ctype):
 _STAT_FIELDS = (
     "n_tracks", "n_trajectory_points", "n_active_points", "n_primary_electrons", "n_deposits", "n_keys",
     "ms_h2d", "ms_tracks", "ms_deposit", "ms_finalize", "ms_d2h", "ms_total", "n_kernel_launches", "n_retries",
-    "n_track_launches", "n_group_launches", "n_hash_probes", "hash_capacity",
+    "n_track_launches", "n_group_launches", "n_hash_probes", "hash_capacity", "n_table_flushes",
 )  # fmt: skip
 
 

@@ -120,6 +120,7 @@ typedef struct AttpcResult {
     int64_t n_hash_probes;       /* table slots inspected by the deposits (n_hash_probes / n_deposits ~ 1 is healthy) */
     int32_t hash_capacity;       /* slots per event in use at the end of the call */
     int32_t reserved1;
+    int64_t n_table_flushes;     /* shared-memory tables merged into a global table (dense or split events) */
 } AttpcResult;
 
 typedef struct AttpcSim AttpcSim;
