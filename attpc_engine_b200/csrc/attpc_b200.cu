@@ -526,6 +526,8 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         CU(cudaEventSynchronize(groups_done));
         const Counters now = *ls.counters_host.p;
         if (now.replay_miss) return sim->fail(ATTPC_E_BADARG, "replay uniforms do not cover every (event, key)");
+        if (now.overflow_charge)
+            return sim->fail(ATTPC_E_CAPACITY, "a (pad, time bucket) charge exceeded 2^48 electrons");
         if (now.overflow_points || now.overflow_hash || now.overflow_out) {
             dep_marks.resize(dep_before);
             fin_marks.resize(fin_before);

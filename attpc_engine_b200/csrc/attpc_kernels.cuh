@@ -96,7 +96,7 @@ struct PointBuf {
 struct Counters {
     unsigned long long track_cursor;
     unsigned long long traj_points, active_points, primary_electrons, deposits, keys, probes, flushes;
-    int overflow_points, overflow_hash, overflow_out, replay_miss;
+    int overflow_points, overflow_hash, overflow_out, replay_miss, overflow_charge, pad_;
 };
 
 // Publish a launch's counters and the running CSR totals into mapped host memory.  A copy-engine transfer would
@@ -820,7 +820,7 @@ __device__ __forceinline__ int make_geom(const SimParams& P, double cx, double c
     // detector/transporter.py:301, evaluated left to right
     const double sigma = __dsqrt_rn(__ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, P.diffusion), P.dv), time), P.efield));
     const int tb = (int)time;  // detector/transporter.py:165, 238
-    if (tb < 0 || tb >= (1 << 29) || !(sigma == sigma)) return 0;  // kind 0: never reached for z <= length + mm_edge*dv
+    if (tb < 0 || tb >= 8192 || !(sigma == sigma)) return 0;  // kind 0: never reached for 0 <= z <= length + mm_edge*dv (tb <= windows_edge)
     if (sigma == 0.0) return tb | (1 << 30);                      // kind 1: single deposit, transporter.py:123-169
     // detector/transporter.py:217-226 with numba's linspace (numba/np/arrayobj.py: linspace)
     const double three_sigma = __dmul_rn(3.0, sigma);
@@ -861,47 +861,68 @@ __global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------------- shared-memory accumulate
 constexpr int DEPOSIT_THREADS = 256;
 constexpr int DEPOSIT_WARPS = DEPOSIT_THREADS / 32;
-constexpr int SMEM_SLOTS = 8192;   // per-CTA table in shared memory
+constexpr int SMEM_SLOTS = 11264;  // per-CTA table in shared memory: 10 B per slot = 110 KB, two CTAs per SM
 constexpr int SPILL_CHECK_EVERY = 2;  // iterations (of DEPOSIT_WARPS points) between two fill checks
 constexpr int SMEM_SPILL_AT = SMEM_SLOTS - 100 * DEPOSIT_WARPS * SPILL_CHECK_EVERY - 512;
-constexpr size_t DEPOSIT_SMEM_BYTES = (size_t)SMEM_SLOTS * (3 * sizeof(unsigned) + 1);
+constexpr size_t DEPOSIT_SMEM_BYTES = (size_t)SMEM_SLOTS * (2 * sizeof(unsigned) + sizeof(uint16_t));
+constexpr unsigned SMEM_KEY_MASK = 0x0FFFFFFFu;  // low 28 bits: ((tb << 15) | pad) + 1; top 4 bits: track rank
 
+// Slot word = compact key (time bucket < 8192, pad id < 32768) + 1 in the low 28 bits, 0 = empty, and in the top four
+// bits the rank of the last track that touched the slot.  Tracks are processed in rank order, so the rank is kept
+// current with a plain store of the whole word (every writer of a phase stores the same value; a concurrent CAS on
+// a non-empty word simply fails and re-reads it).  The charge is a 48-bit sum: 32 low bits + 16 high bits packed two
+// per word (max 2.8e14 electrons per pad and time bucket, far above anything physical; overflow is flagged).
 struct SmemTable {
-    unsigned* key1;   // Szudzik key + 1, 0 = empty
+    unsigned* word;   // key + rank
     unsigned* lo;     // charge bits 0..31
-    unsigned* hi;     // charge bits 32..63
-    uint8_t* rank;    // last track rank that touched the slot (tracks are processed in rank order)
+    unsigned* hi2;    // charge bits 32..47, two slots per 32-bit word
 };
 
-// Find the slot of `key`, claiming an empty one if it is new.  The table is flushed long before it can fill.
-__device__ __forceinline__ unsigned smem_find(const SmemTable& t, unsigned key, unsigned* n_keys, unsigned& probes) {
-    const unsigned key1 = key + 1u, mask = SMEM_SLOTS - 1;
-    unsigned slot = hash_slot(key, mask);
+__device__ __forceinline__ unsigned smem_key(unsigned tb, unsigned pad) { return ((tb << 15) | pad) + 1u; }
+
+__device__ __forceinline__ unsigned smem_home(unsigned key1) {
+    return __umulhi(key1 * 2654435761u, (unsigned)SMEM_SLOTS);  // multiply-shift range reduction, no division
+}
+
+// Find the slot of `key1`, claiming an empty one if it is new.  The table is flushed long before it can fill.
+__device__ __forceinline__ unsigned smem_find(const SmemTable& t, unsigned key1, unsigned rank, unsigned* n_keys,
+                                              unsigned& probes) {
+    unsigned slot = smem_home(key1);
 #pragma unroll 1
-    for (unsigned probe = 0; probe <= mask; ++probe) {
-        unsigned k = *(volatile unsigned*)&t.key1[slot];
-        if (k == 0u) {
-            k = atomicCAS(&t.key1[slot], 0u, key1);
-            if (k == 0u) {
-                k = key1;
+    for (unsigned probe = 0; probe < (unsigned)SMEM_SLOTS; ++probe) {
+        unsigned w = *(volatile unsigned*)&t.word[slot];
+        if (w == 0u) {
+            w = atomicCAS(&t.word[slot], 0u, key1 | (rank << 28));
+            if (w == 0u) {
+                w = key1;
                 atomicAdd(n_keys, 1u);
             }
         }
-        if (k == key1) {
+        if ((w & SMEM_KEY_MASK) == key1) {
             probes += probe + 1u;
             return slot;
         }
-        slot = (slot + 1u) & mask;
+        slot = slot + 1u == (unsigned)SMEM_SLOTS ? 0u : slot + 1u;
     }
     return slot;
 }
 
-// Exact 64-bit accumulate from two native 32-bit shared-memory atomics.
-__device__ __forceinline__ void smem_charge(const SmemTable& t, unsigned slot, unsigned long long q) {
+// Exact accumulate from native 32-bit shared-memory atomics (carry into the 16-bit high part).
+__device__ __forceinline__ void smem_charge(const SmemTable& t, unsigned slot, unsigned long long q, int* overflow) {
     const unsigned vlo = (unsigned)q, vhi = (unsigned)(q >> 32);
     unsigned carry = 0u;
     if (vlo) carry = atomicAdd(&t.lo[slot], vlo) > ~vlo ? 1u : 0u;
-    if (vhi + carry) atomicAdd(&t.hi[slot], vhi + carry);
+    const unsigned add = vhi + carry;
+    if (add) {
+        const unsigned shift = (slot & 1u) * 16u;
+        const unsigned old = (atomicAdd(&t.hi2[slot >> 1], add << shift) >> shift) & 0xFFFFu;
+        if (add > 0xFFFFu || old + add > 0xFFFFu) *overflow = 1;
+    }
+}
+
+__device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t, unsigned slot) {
+    const unsigned hi = (t.hi2[slot >> 1] >> ((slot & 1u) * 16u)) & 0xFFFFu;
+    return ((unsigned long long)hi << 32) | t.lo[slot];
 }
 
 // One CTA per work unit (a slice of one event's points).  Tracks are processed in rank order (label = last track
@@ -919,17 +940,16 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
     const int e = pb.unit_event[ubase + unit];
     const int u_first = pb.unit_first[ubase + unit], u_count = pb.unit_count[ubase + unit];
     SmemTable t;
-    t.key1 = s_raw;
+    t.word = s_raw;
     t.lo = s_raw + SMEM_SLOTS;
-    t.hi = s_raw + 2 * SMEM_SLOTS;
-    t.rank = (uint8_t*)(s_raw + 3 * SMEM_SLOTS);
+    t.hi2 = s_raw + 2 * SMEM_SLOTS;
     const int slot_event = gv.first_slot + e;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool shared_event = gv.mode[slot_event] != 0u;  // several units: merge through the (pre-zeroed) global table
     HashEntry* region = gv.tables + (int64_t)e * gv.hash_cap;
     const unsigned gmask = (unsigned)gv.hash_cap - 1u;
     const int64_t base = (int64_t)gv.group * pb.group_cap;
-    for (int i = threadIdx.x; i < 3 * SMEM_SLOTS; i += blockDim.x) s_raw[i] = 0u;
+    for (int i = threadIdx.x; i < 2 * SMEM_SLOTS + SMEM_SLOTS / 2; i += blockDim.x) s_raw[i] = 0u;
     if (threadIdx.x == 0) {
         s_nkeys = 0;
         s_out = 0;
@@ -953,16 +973,15 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
         }
         __syncthreads();
         for (int i = threadIdx.x; i < SMEM_SLOTS; i += blockDim.x) {
-            const unsigned k = t.key1[i];
-            if (k) {
-                const long long q = (long long)(((unsigned long long)t.hi[i] << 32) | t.lo[i]);
-                table_add(region, gmask, k - 1u, q, t.rank[i], ctr);
-                t.key1[i] = 0u;
-                t.lo[i] = 0u;
-                t.hi[i] = 0u;
+            const unsigned w = t.word[i];
+            if (w) {
+                const unsigned kc = (w & SMEM_KEY_MASK) - 1u;
+                table_add(region, gmask, szudzik_pair(kc >> 15, kc & 0x7FFFu), (long long)smem_charge_of(t, i), w >> 28,
+                          ctr);
             }
         }
         __syncthreads();
+        for (int i = threadIdx.x; i < 2 * SMEM_SLOTS + SMEM_SLOTS / 2; i += blockDim.x) s_raw[i] = 0u;
         if (threadIdx.x == 0) {
             s_nkeys = 0;
             s_spilled = 1;
@@ -992,9 +1011,10 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
                         const double* g = pb.geom + p * GEOM_DOUBLES;
                         const int pad = lookup_pad(P, g[0], g[1]);
                         if (pad >= 0) {
-                            const unsigned slot = smem_find(t, szudzik_pair((unsigned)tb, (unsigned)pad), &s_nkeys, n_probe);
-                            smem_charge(t, slot, (unsigned long long)pb.sq[p]);
-                            t.rank[slot] = (uint8_t)r;
+                            const unsigned key1 = smem_key((unsigned)tb, (unsigned)pad);
+                            const unsigned slot = smem_find(t, key1, (unsigned)r, &s_nkeys, n_probe);
+                            smem_charge(t, slot, (unsigned long long)pb.sq[p], &ctr->overflow_charge);
+                            t.word[slot] = key1 | ((unsigned)r << 28);
                             n_dep += 1;
                         }
                     }
@@ -1028,17 +1048,18 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const bool ok = pad[k] >= 0;
+                        const unsigned key1 = smem_key((unsigned)tb, (unsigned)max(pad[k], 0));
                         unsigned slot = 0;
                         long long share = 0;
                         if (ok) {
                             // detector/transporter.py:36-41, 240-246
                             const double pdf = __dmul_rn(g89.y, exp(__dmul_rn(gab.x, r2[k])));
                             share = (long long)__dmul_rn(__dmul_rn(pdf, g89.x), gab.y);
-                            slot = smem_find(t, szudzik_pair((unsigned)tb, (unsigned)pad[k]), &s_nkeys, n_probe);
+                            slot = smem_find(t, key1, (unsigned)r, &s_nkeys, n_probe);
                         }
                         if (ok) {  // reconverged: one pass of atomics for all valid lanes
-                            smem_charge(t, slot, (unsigned long long)share);
-                            t.rank[slot] = (uint8_t)r;  // same value from every writer of this phase
+                            smem_charge(t, slot, (unsigned long long)share, &ctr->overflow_charge);
+                            t.word[slot] = key1 | ((unsigned)r << 28);  // same value from every writer of this phase
                             n_dep += 1;
                         }
                     }
@@ -1064,10 +1085,11 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
         }
     } else {
         for (int i = threadIdx.x; i < SMEM_SLOTS; i += blockDim.x) {
-            const unsigned k = t.key1[i];
-            if (k) {
+            const unsigned w = t.word[i];
+            if (w) {
+                const unsigned kc = (w & SMEM_KEY_MASK) - 1u;
                 const unsigned pos = atomicAdd(&s_out, 1u);
-                region[pos] = HashEntry{k, (unsigned)t.rank[i], ((unsigned long long)t.hi[i] << 32) | t.lo[i]};
+                region[pos] = HashEntry{szudzik_pair(kc >> 15, kc & 0x7FFFu) + 1u, w >> 28, smem_charge_of(t, i)};
             }
         }
         __syncthreads();
