@@ -1045,20 +1045,22 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
                         const bool ok = (lane + 32 * k < MESH_N * MESH_N) && ix >= 0 && iy >= 0;
                         pad[k] = ok ? (int)__ldg(P.lut + (int64_t)ix * P.lut_n + iy) : -1;
                     }
+                    // the four shares first: their FP64 work overlaps the latency of the pad-LUT loads
+                    long long share[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        // detector/transporter.py:36-41, 240-246
+                        const double pdf = __dmul_rn(g89.y, exp(__dmul_rn(gab.x, r2[k])));
+                        share[k] = (long long)__dmul_rn(__dmul_rn(pdf, g89.x), gab.y);
+                    }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const bool ok = pad[k] >= 0;
                         const unsigned key1 = smem_key((unsigned)tb, (unsigned)max(pad[k], 0));
                         unsigned slot = 0;
-                        long long share = 0;
-                        if (ok) {
-                            // detector/transporter.py:36-41, 240-246
-                            const double pdf = __dmul_rn(g89.y, exp(__dmul_rn(gab.x, r2[k])));
-                            share = (long long)__dmul_rn(__dmul_rn(pdf, g89.x), gab.y);
-                            slot = smem_find(t, key1, (unsigned)r, &s_nkeys, n_probe);
-                        }
+                        if (ok) slot = smem_find(t, key1, (unsigned)r, &s_nkeys, n_probe);
                         if (ok) {  // reconverged: one pass of atomics for all valid lanes
-                            smem_charge(t, slot, (unsigned long long)share, &ctr->overflow_charge);
+                            smem_charge(t, slot, (unsigned long long)share[k], &ctr->overflow_charge);
                             t.word[slot] = key1 | ((unsigned)r << 28);  // same value from every writer of this phase
                             n_dep += 1;
                         }
