@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant_
 constexpr int DEPOSIT_THREADS = 256;
 constexpr int DEPOSIT_WARPS = DEPOSIT_THREADS / 32;
 constexpr int SMEM_SLOTS = 11264;  // per-CTA table in shared memory: 10 B per slot = 110 KB, two CTAs per SM
-constexpr int SPILL_CHECK_EVERY = 2;  // iterations (of DEPOSIT_WARPS points) between two fill checks
+constexpr int SPILL_CHECK_EVERY = 4;  // iterations (of DEPOSIT_WARPS points) between two fill checks
 constexpr int SMEM_SPILL_AT = SMEM_SLOTS - 100 * DEPOSIT_WARPS * SPILL_CHECK_EVERY - 512;
 constexpr size_t DEPOSIT_SMEM_BYTES = (size_t)SMEM_SLOTS * (2 * sizeof(unsigned) + sizeof(uint16_t));
 constexpr unsigned SMEM_KEY_MASK = 0x0FFFFFFFu;  // low 28 bits: ((tb << 15) | pad) + 1; top 4 bits: track rank
