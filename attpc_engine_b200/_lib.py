@@ -20,6 +20,7 @@ SPYRAL_ROWS = 1 << 1
 NO_WIGGLE = 1 << 2
 SKIP_HOST_COPY = 1 << 3
 ROWS_KEEP_ALL = 1 << 4
+SKIP_CLOUD_COPY = 1 << 5
 
 
 class AttpcConfig(C.Structure):

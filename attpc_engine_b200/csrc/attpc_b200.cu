@@ -414,6 +414,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     res->n_events = n_events;
     res->ms_h2d = ms_h2d;
     const bool copy_host = !(flags & ATTPC_SKIP_HOST_COPY);
+    const bool copy_cloud = copy_host && !((flags & ATTPC_SKIP_CLOUD_COPY) && (flags & ATTPC_SPYRAL_ROWS));
     int64_t out_cap = std::max<int64_t>(sim->labels_dev.n, std::max<int64_t>(n_events * 2048, 1 << 20));
     int rc = ensure_out_buffers(sim, n_events, out_cap, false);
     if (rc) return rc;
@@ -425,8 +426,8 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     const int32_t ranks = std::max<int32_t>(1, plan.n_tracks_per_event);
     rc = ensure_work_buffers(sim, std::min<int64_t>(std::max<int64_t>(n_events, 1), launch_cap), ranks);
     if (rc) return rc;
-    if (copy_host) {  // pinned mirrors are sized like the device buffers: (re)allocated only when those grow
-        CU(sim->offsets_host.reserve(sim->offsets_dev.n));
+    if (copy_host) CU(sim->offsets_host.reserve(sim->offsets_dev.n));
+    if (copy_cloud) {  // pinned mirrors are sized like the device buffers: (re)allocated only when those grow
         CU(sim->cloud_host.reserve(sim->cloud_dev.n));
         CU(sim->labels_host.reserve(sim->labels_dev.n));
     }
@@ -551,7 +552,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 out_cap = std::max<int64_t>(sim->labels_dev.n * 2, (int64_t)sim->csr_host.p[0] + (1 << 20));
                 rc = ensure_out_buffers(sim, n_events, out_cap, true);
                 if (rc) return rc;
-                if (copy_host) {
+                if (copy_cloud) {
                     CU(sim->cloud_host.reserve(sim->cloud_dev.n, true));
                     CU(sim->labels_host.reserve(sim->labels_dev.n, true));
                 }
@@ -581,7 +582,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             CU(cudaMemcpyAsync(sim->offsets_host.p + first_off, sim->offsets_dev.p + first_off,
                                (size_t)(b0 + nb + 1 - first_off) * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
             const int64_t n_new = (int64_t)(csr_after - csr_before);
-            if (n_new > 0) {
+            if (n_new > 0 && copy_cloud) {
                 CU(cudaMemcpyAsync(sim->cloud_host.p + csr_before * 3, sim->cloud_dev.p + csr_before * 3,
                                    (size_t)n_new * 3 * sizeof(double), cudaMemcpyDeviceToHost, C));
                 CU(cudaMemcpyAsync(sim->labels_host.p + csr_before, sim->labels_dev.p + csr_before,
@@ -610,8 +611,10 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             CU(cudaMemcpyAsync(sim->offsets_host.p, sim->offsets_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, C));
         }
         res->offsets = sim->offsets_host.p;
-        res->cloud = sim->cloud_host.p;
-        res->labels = sim->labels_host.p;
+        if (copy_cloud) {
+            res->cloud = sim->cloud_host.p;
+            res->labels = sim->labels_host.p;
+        }
     }
     if (flags & ATTPC_SPYRAL_ROWS) {
         rc = run_spyral(sim, n_events, n_points, res, copy_host);

@@ -239,7 +239,7 @@ class Engine:
                             stats=dict(stats, n_points=n_pts))  # fmt: skip
         grab = (lambda a: a.copy()) if copy else (lambda a: a)
         offsets = grab(np.ctypeslib.as_array(res.offsets, shape=(n_ev + 1,)))
-        if n_pts > 0:
+        if n_pts > 0 and res.cloud:
             cloud = grab(np.ctypeslib.as_array(res.cloud, shape=(n_pts, 3)))
             labels = grab(np.ctypeslib.as_array(res.labels, shape=(n_pts,)))
         else:
@@ -270,8 +270,12 @@ class Engine:
         keep_all_tb: bool = False,
         copy: bool = True,
         host_copy: bool = True,
+        rows_only: bool = False,
     ) -> SimBatch:
-        """`simulate` (`simulator.py:52-115`) for ``B`` events at once: ``momenta [B, K, 4]``, ``vertices [B, 3]``."""
+        """`simulate` (`simulator.py:52-115`) for ``B`` events at once: ``momenta [B, K, 4]``, ``vertices [B, 3]``.
+
+        ``rows_only`` (with ``spyral_rows``): bring back offsets and Spyral rows but leave the raw cloud on the GPU.
+        """
         momenta = np.ascontiguousarray(momenta, dtype=np.float64)
         vertices = np.ascontiguousarray(vertices, dtype=np.float64)
         if momenta.ndim != 3 or momenta.shape[2] != 4:
@@ -282,6 +286,8 @@ class Engine:
         flags = (_lib.SPYRAL_ROWS if spyral_rows else 0) | (_lib.KEEP_ALL_TB if keep_all_tb else 0)
         if not host_copy:
             flags |= _lib.SKIP_HOST_COPY
+        if rows_only and spyral_rows:
+            flags |= _lib.SKIP_CLOUD_COPY
         res = _lib.AttpcResult()
         code = self.lib.attpc_simulate(
             self.handle, _ptr(momenta, C.c_double), _ptr(vertices, C.c_double), momenta.shape[0], momenta.shape[1],

@@ -65,6 +65,7 @@ def simulate_batch(
     spyral_rows: bool = False,
     copy: bool = True,
     nuclear_data=None,
+    rows_only: bool = False,
     **tuning,
 ) -> SimBatch:
     """Detector simulation of ``B`` kinematics events in one call.
@@ -87,7 +88,7 @@ def simulate_batch(
     engine = engine_for(config, charged, device=device, **tuning)
     return engine.simulate_batch(
         momenta, vertices, proton_numbers, mass_numbers, indices, seed=seed, first_event=first_event,
-        spyral_rows=spyral_rows, copy=copy,
+        spyral_rows=spyral_rows, copy=copy, rows_only=rows_only,
     )  # fmt: skip
 
 
@@ -202,6 +203,7 @@ def run_simulation(
         batch = simulate_batch(
             momenta, vertices, kin.proton_numbers, kin.mass_numbers, config, seed, nuclei_to_sim,
             first_event=start, device=device, spyral_rows=want_rows, copy=False,
+            rows_only=want_rows and bool(getattr(writer, "rows_only", False)),
         )  # fmt: skip
         if batched:
             writer.write_batch(batch, config)

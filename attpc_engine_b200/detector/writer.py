@@ -87,6 +87,7 @@ class SpyralWriter:
     """
 
     wants_spyral_rows = True
+    rows_only = True  # `write_batch` never looks at the raw cloud: it can stay on the GPU
 
     def __init__(
         self,
@@ -184,6 +185,7 @@ class ArrayWriter:
         self.max_events_per_file = max_events_per_file
         self.run_number = first_run_number
         self.wants_spyral_rows = spyral
+        self.rows_only = spyral  # `write_batch` then needs the offsets and the rows, not the raw cloud
         self.response = get_response(config).copy()
         self.files: list[dict] = []
         self._reset()

@@ -263,11 +263,11 @@ def run_ours(args):
 
     def step_device(i):
         return eng.simulate_device(mom_dev.data_ptr(), vtx_dev.data_ptr(), B, K, zs, as_, indices, seed=seed + i,
-                                   first_event=first).stats  # fmt: skip
+                                   first_event=first, spyral_rows=args.spyral).stats  # fmt: skip
 
     def step_e2e(i):
         return eng.simulate_batch(mom_pin.numpy(), vtx_pin.numpy(), zs, as_, indices, seed=seed + i, first_event=first,
-                                  copy=False).stats  # fmt: skip
+                                  copy=False, spyral_rows=args.spyral, rows_only=args.spyral).stats  # fmt: skip
 
     for i in range(args.warmup):
         step_device(i)
@@ -292,7 +292,7 @@ def run_ours(args):
     clocks = sampler.stop()
     # ---- e2e: host buffers in, host buffers out
     barrier()
-    e2e_s, e2e_points = 0.0, 0
+    e2e_s, e2e_points, e2e_rows = 0.0, 0, 0
     for i in range(0 if args.no_e2e else args.steps):
         flush_l2()
         barrier()
@@ -301,6 +301,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_s += time.perf_counter() - t0
         e2e_points += st["n_points"]
+        e2e_rows += st.get("n_rows", 0)
     barrier()
 
     dev_s = reduce_max(dist, dev_ms / 1e3, local)
@@ -340,6 +341,7 @@ def run_ours(args):
             "workload": f"{args.workload}: {WORKLOADS[args.workload]['desc']}", "events_per_gpu_per_step": B,
             "nuclei_per_event": K, "tracks": indices, "l2": "flushed between steps (256 MiB device write)",
             "dedx": "analytic Bethe+Lindhard table (not CATIMA)", "parallelism": f"event-range shards x{world}",
+            "output": "raw cloud [pad, tb, e] + Spyral rows (response, threshold, z-sort)" if args.spyral else "raw cloud [pad, tb, e]",
         },
         "electrons_per_s": round(electrons / dev_s, 1), "cloud_points_per_s": round(points / dev_s, 1),
         "pixel_deposits_per_s": round(deposits / dev_s, 1),
@@ -349,7 +351,8 @@ def run_ours(args):
         "wall_s_device_loop": round(wall_dev, 3),
         "e2e": {"value": None if args.no_e2e else round(total_events / e2e_s, 1), "unit": "events/s",
                 "h2d_bytes_per_step": int(momenta.nbytes + vertices.nbytes),
-                "d2h_bytes_per_step": int(e2e_points / args.steps * 32 + (B + 1) * 8)},
+                "d2h_bytes_per_step": int((e2e_rows * 72 if args.spyral else e2e_points * 32) / args.steps
+                                          + (B + 1) * 8 * (2 if args.spyral else 1))},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }  # fmt: skip
     if world == 1 and not args.no_cpu:
@@ -419,6 +422,7 @@ def main():
     ap.add_argument("--cpu-events-per-core", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: only the device-resident steps")
+    ap.add_argument("--spyral", action="store_true", help="also produce the Spyral 8-column rows (full pad-plane response)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

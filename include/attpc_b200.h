@@ -36,7 +36,8 @@ enum {
     ATTPC_SPYRAL_ROWS = 1u << 1,   /* also produce the 8-column Spyral rows (detector/writer.py:61-112,232-238) */
     ATTPC_NO_WIGGLE = 1u << 2,     /* add 0 instead of U[0,1) to the time bucket (tests) */
     ATTPC_SKIP_HOST_COPY = 1u << 3,/* leave results in device memory only (device-resident benchmarking) */
-    ATTPC_ROWS_KEEP_ALL = 1u << 4  /* attpc_convert_to_spyral: every row, input order (no threshold, no sort) */
+    ATTPC_ROWS_KEEP_ALL = 1u << 4, /* attpc_convert_to_spyral: every row, input order (no threshold, no sort) */
+    ATTPC_SKIP_CLOUD_COPY = 1u << 5 /* with ATTPC_SPYRAL_ROWS: copy offsets and rows to the host, not the raw cloud */
 };
 
 /* Scalars of DetectorParams / ElectronicsParams / Config (detector/parameters.py:10-76,164-174). */
