@@ -304,9 +304,9 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         gv.n_entries = sim->n_entries.p;
         gv.mode = sim->mode.p;
         cudaEvent_t d0 = sim->mark();
-        point_scan_kernel<<<1, 1024, 0, sim->stream>>>(pb, gv);
-        point_order_kernel<<<sim->sm_count * 4, 256, 0, sim->stream>>>(sim->P, pb, gv);
-        zero_shared_tables_kernel<<<gv.n_events, 256, 0, sim->stream>>>(gv);
+        point_scan_kernel<<<1, 1024, 0, sim->stream>>>(pb, gv, ctr);
+        point_order_kernel<<<sim->sm_count * 4, 256, 0, sim->stream>>>(sim->P, pb, gv, ctr);
+        zero_shared_tables_kernel<<<gv.n_events, 256, 0, sim->stream>>>(gv, ctr);
         deposit_kernel<<<sim->max_units, DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES, sim->stream>>>(sim->P, pb, gv, ctr);
         cudaEvent_t d1 = sim->mark();
         collect_kernel<<<gv.n_events, FINALIZE_THREADS, sort_smem, sim->stream>>>(sim->P, fa, gv, ctr);

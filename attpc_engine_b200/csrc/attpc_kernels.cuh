@@ -716,11 +716,15 @@ constexpr int GEOM_DOUBLES = 12;
 // Per group, single CTA: (1) exclusive scan of the (event, rank) list lengths -> start of every list in the group's
 // ordered run; (2) split every event into work units of <= UNIT_POINTS points; (3) order the units by decreasing
 // size so that the longest start first (the per-event cost varies by 100x between a short recoil and a stopped ion).
-__global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView gv) {
+__global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView gv, const Counters* ctr) {
     __shared__ unsigned s_part[1024];
     __shared__ unsigned s_base, s_ubase;
     __shared__ uint32_t s_sort[MAX_UNITS_SORT];
     const int tid = threadIdx.x;
+    if (ctr->overflow_points) {  // the point lists are incomplete: the host will redo the launch with bigger buffers
+        if (tid == 0) pb.n_units[gv.group] = 0;
+        return;
+    }
     const int n = gv.n_events * pb.ranks;
     const int64_t first = (int64_t)gv.first_slot * pb.ranks;
     int32_t* u_event = pb.unit_event + (int64_t)gv.group * pb.max_units;
@@ -840,7 +844,8 @@ __device__ __forceinline__ int make_geom(const SimParams& P, double cx, double c
 
 // Scatter the group's points into (event, rank, arrival) order and compute their mesh constants (one thread each).
 __global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant__ SimParams P, PointBuf pb,
-                                                          GroupView gv) {
+                                                          GroupView gv, const Counters* ctr) {
+    if (ctr->overflow_points) return;
     const int64_t n = min((int64_t)pb.count[gv.group], pb.group_cap);
     const int64_t base = (int64_t)gv.group * pb.group_cap;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
@@ -1109,7 +1114,8 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
 }
 
 // Zero the global tables of the events that are split over several units (before the deposit kernel merges into them).
-__global__ void __launch_bounds__(256) zero_shared_tables_kernel(GroupView gv) {
+__global__ void __launch_bounds__(256) zero_shared_tables_kernel(GroupView gv, const Counters* ctr) {
+    if (ctr->overflow_points) return;
     const int e = blockIdx.x;
     if (gv.mode[gv.first_slot + e] == 0u) return;
     HashEntry* region = gv.tables + (int64_t)e * gv.hash_cap;
@@ -1179,6 +1185,10 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     __shared__ unsigned s_n, s_keys;
     const int e = blockIdx.x;
     const int slot_event = gv.first_slot + e;
+    if (ctr->overflow_points | ctr->overflow_hash) {  // this attempt is void: nothing below may be trusted
+        if (threadIdx.x == 0) fa.kept[slot_event] = 0u;
+        return;
+    }
     const HashEntry* tab = gv.tables + (int64_t)e * gv.hash_cap;
     uint64_t* sorted = fa.sort_items + (int64_t)e * 2 * gv.hash_cap;  // final order, read by emit_kernel
     uint64_t* stash = sorted + gv.hash_cap;                           // unordered survivors
