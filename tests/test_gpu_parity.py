@@ -98,3 +98,29 @@ def test_pad_lookup(golden_misc):
     eng = engine_for(make_config(), [nuclear_map.get_data(1, 2)])
     got = eng.lookup_pads(golden_misc["pad_lookup/xy"])
     assert np.array_equal(got, golden_misc["pad_lookup/pad"].astype(np.int32))
+
+
+def test_three_events_in_one_replay_call(golden_events):
+    """Several events per call: per-event tables, labels and replayed uniforms stay separate."""
+    from attpc_engine_b200.detector.engine import engine_for
+
+    ev = golden_events
+    names = ["dd_exit", "dd_stop", "dd_back"]  # same Config
+    cfg = case_config(names[0])
+    rows, normals, events, ranks, labels, zas, uniforms = [], [], [], [], [], [], []
+    for e, name in enumerate(names):
+        for t in case_tracks(ev, name):
+            rows.append(t["rows"])
+            normals.append(t["normals"])
+            events.append(e)
+            ranks.append(t["rank"])
+            labels.append(t["idx"])
+            zas.append(t["za"])
+        uniforms.append((ev[f"{name}/keys"], ev[f"{name}/uniforms"]))
+    eng = engine_for(cfg, nuclei_of([{"za": za} for za in zas]))
+    batch, _ = eng.simulate_replay(rows, normals, events, ranks, labels, zas, len(names), uniforms=uniforms)
+    for e, name in enumerate(names):
+        cloud, lab = batch.event(e)
+        want_cloud, want_labels = sort_cloud(ev[f"{name}/cloud"], ev[f"{name}/labels"])
+        assert np.array_equal(cloud, want_cloud), name
+        assert np.array_equal(lab, want_labels), name
