@@ -269,15 +269,15 @@ def run_ours(args):
         return eng.simulate_batch(mom_pin.numpy(), vtx_pin.numpy(), zs, as_, indices, seed=seed + i, first_event=first,
                                   copy=False, spyral_rows=args.spyral, rows_only=args.spyral).stats  # fmt: skip
 
+    sampler = ClockSampler(local)
+    sampler.start()  # nvidia-smi needs a moment to come up: started before the warm-up, read after the timed loops
     for i in range(args.warmup):
         step_device(i)
         if not args.no_e2e:
             step_e2e(i)
 
-    sampler = ClockSampler(local)
     # ---- value: device-resident
     barrier()
-    sampler.start()
     dev_ms, stats_sum, launches = 0.0, {}, 0
     wall0 = time.perf_counter()
     for i in range(args.steps):
@@ -289,7 +289,6 @@ def run_ours(args):
             stats_sum[k] = stats_sum.get(k, 0) + v
     barrier()
     wall_dev = time.perf_counter() - wall0
-    clocks = sampler.stop()
     # ---- e2e: host buffers in, host buffers out
     barrier()
     e2e_s, e2e_points, e2e_rows = 0.0, 0, 0
@@ -303,6 +302,7 @@ def run_ours(args):
         e2e_points += st["n_points"]
         e2e_rows += st.get("n_rows", 0)
     barrier()
+    clocks = sampler.stop()
 
     dev_s = reduce_max(dist, dev_ms / 1e3, local)
     e2e_s = reduce_max(dist, e2e_s, local) if not args.no_e2e else float("nan")
