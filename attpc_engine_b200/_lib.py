@@ -21,6 +21,7 @@ NO_WIGGLE = 1 << 2
 SKIP_HOST_COPY = 1 << 3
 ROWS_KEEP_ALL = 1 << 4
 SKIP_CLOUD_COPY = 1 << 5
+COLUMNS = 1 << 6
 
 
 class AttpcConfig(C.Structure):
@@ -105,6 +106,10 @@ class AttpcResult(C.Structure):
         ("hash_capacity", C.c_int32),
         ("reserved1", C.c_int32),
         ("n_table_flushes", C.c_int64),
+        ("col_pad", C.POINTER(C.c_int16)),
+        ("col_tb", C.POINTER(C.c_double)),
+        ("col_electrons", C.POINTER(C.c_int64)),
+        ("col_label", C.POINTER(C.c_int8)),
     ]
 
 

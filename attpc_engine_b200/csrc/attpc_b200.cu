@@ -131,6 +131,15 @@ struct AttpcSim {
     DevArray<double> in_momenta, in_vertices;
 
     // outputs
+    DevArray<int16_t> col_pad_dev;
+    DevArray<double> col_tb_dev;
+    DevArray<int64_t> col_q_dev;
+    DevArray<int8_t> col_label_dev;
+    PinnedArray<int16_t> col_pad_host;
+    PinnedArray<double> col_tb_host;
+    PinnedArray<int64_t> col_q_host;
+    PinnedArray<int8_t> col_label_host;
+    bool columns = false;  // sticky: once a call asked for columns the buffers are kept in step with the others
     DevArray<int64_t> offsets_dev, labels_dev, row_offsets_dev, row_labels_dev;
     DevArray<double> cloud_dev, rows_dev;
     DevArray<unsigned> row_kept;
@@ -232,6 +241,12 @@ int ensure_out_buffers(AttpcSim* sim, int64_t n_events, int64_t n_points, bool k
     CU(sim->kept.reserve(n_events + 1, keep, sim->stream));
     CU(sim->cloud_dev.reserve(n_points * 3, keep, sim->stream));
     CU(sim->labels_dev.reserve(n_points, keep, sim->stream));
+    if (sim->columns) {
+        CU(sim->col_pad_dev.reserve(sim->labels_dev.n, keep, sim->stream));
+        CU(sim->col_tb_dev.reserve(sim->labels_dev.n, keep, sim->stream));
+        CU(sim->col_q_dev.reserve(sim->labels_dev.n, keep, sim->stream));
+        CU(sim->col_label_dev.reserve(sim->labels_dev.n, keep, sim->stream));
+    }
     return ATTPC_OK;
 }
 
@@ -414,7 +429,10 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     res->n_events = n_events;
     res->ms_h2d = ms_h2d;
     const bool copy_host = !(flags & ATTPC_SKIP_HOST_COPY);
-    const bool copy_cloud = copy_host && !((flags & ATTPC_SKIP_CLOUD_COPY) && (flags & ATTPC_SPYRAL_ROWS));
+    const bool use_columns = copy_host && (flags & ATTPC_COLUMNS);
+    const bool copy_cloud =
+        copy_host && !use_columns && !((flags & ATTPC_SKIP_CLOUD_COPY) && (flags & ATTPC_SPYRAL_ROWS));
+    if (use_columns) sim->columns = true;
     int64_t out_cap = std::max<int64_t>(sim->labels_dev.n, std::max<int64_t>(n_events * 2048, 1 << 20));
     int rc = ensure_out_buffers(sim, n_events, out_cap, false);
     if (rc) return rc;
@@ -430,6 +448,12 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     if (copy_cloud) {  // pinned mirrors are sized like the device buffers: (re)allocated only when those grow
         CU(sim->cloud_host.reserve(sim->cloud_dev.n));
         CU(sim->labels_host.reserve(sim->labels_dev.n));
+    }
+    if (use_columns) {
+        CU(sim->col_pad_host.reserve(sim->labels_dev.n));
+        CU(sim->col_tb_host.reserve(sim->labels_dev.n));
+        CU(sim->col_q_host.reserve(sim->labels_dev.n));
+        CU(sim->col_label_host.reserve(sim->labels_dev.n));
     }
     cudaStream_t G = sim->stream, T = sim->stream_t, C = sim->stream_c;
     CU(cudaMemsetAsync(sim->csr_total.p, 0, 2 * sizeof(unsigned long long), G));
@@ -505,6 +529,12 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         fa.cloud = sim->cloud_dev.p;
         fa.labels = sim->labels_dev.p;
         fa.out_cap = sim->labels_dev.n;
+        if (use_columns) {
+            fa.col_pad = sim->col_pad_dev.p;
+            fa.col_tb = sim->col_tb_dev.p;
+            fa.col_electrons = sim->col_q_dev.p;
+            fa.col_label = sim->col_label_dev.p;
+        }
         fa.replay = plan.uniforms;
         if (fa.replay.offsets) fa.replay.offsets += b0;
         fa.n_tracks_per_event = plan.n_tracks_per_event;
@@ -556,6 +586,12 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                     CU(sim->cloud_host.reserve(sim->cloud_dev.n, true));
                     CU(sim->labels_host.reserve(sim->labels_dev.n, true));
                 }
+                if (use_columns) {
+                    CU(sim->col_pad_host.reserve(sim->labels_dev.n, true));
+                    CU(sim->col_tb_host.reserve(sim->labels_dev.n, true));
+                    CU(sim->col_q_host.reserve(sim->labels_dev.n, true));
+                    CU(sim->col_label_host.reserve(sim->labels_dev.n, true));
+                }
             }
             rc = ensure_work_buffers(sim, std::min<int64_t>(n_events, launch_cap), ranks);
             if (rc) return rc;
@@ -588,6 +624,16 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 CU(cudaMemcpyAsync(sim->labels_host.p + csr_before, sim->labels_dev.p + csr_before,
                                    (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
             }
+            if (n_new > 0 && use_columns) {
+                CU(cudaMemcpyAsync(sim->col_pad_host.p + csr_before, sim->col_pad_dev.p + csr_before,
+                                   (size_t)n_new * sizeof(int16_t), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->col_tb_host.p + csr_before, sim->col_tb_dev.p + csr_before,
+                                   (size_t)n_new * sizeof(double), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->col_q_host.p + csr_before, sim->col_q_dev.p + csr_before,
+                                   (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->col_label_host.p + csr_before, sim->col_label_dev.p + csr_before,
+                                   (size_t)n_new * sizeof(int8_t), cudaMemcpyDeviceToHost, C));
+            }
             copy_marks.push_back({c0, sim->mark(C)});
         }
         csr_before = csr_after;
@@ -614,6 +660,12 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         if (copy_cloud) {
             res->cloud = sim->cloud_host.p;
             res->labels = sim->labels_host.p;
+        }
+        if (use_columns) {
+            res->col_pad = sim->col_pad_host.p;
+            res->col_tb = sim->col_tb_host.p;
+            res->col_electrons = sim->col_q_host.p;
+            res->col_label = sim->col_label_host.p;
         }
     }
     if (flags & ATTPC_SPYRAL_ROWS) {
@@ -691,6 +743,8 @@ void attpc_destroy(AttpcSim* sim) {
     sim->offsets_dev.release(); sim->labels_dev.release(); sim->row_offsets_dev.release();
     sim->row_labels_dev.release(); sim->cloud_dev.release(); sim->rows_dev.release(); sim->row_kept.release();
     sim->row_sort_keys.release(); sim->row_sort_idx.release();
+    sim->col_pad_dev.release(); sim->col_tb_dev.release(); sim->col_q_dev.release(); sim->col_label_dev.release();
+    sim->col_pad_host.release(); sim->col_tb_host.release(); sim->col_q_host.release(); sim->col_label_host.release();
     sim->offsets_host.release(); sim->labels_host.release(); sim->row_offsets_host.release();
     sim->row_labels_host.release(); sim->cloud_host.release(); sim->rows_host.release();
     if (sim->stream) cudaStreamDestroy(sim->stream);

@@ -1143,6 +1143,11 @@ struct FinalizeArgs {
     double* cloud;            // [out_cap, 3]
     int64_t* labels;          // [out_cap]
     int64_t out_cap;
+    // optional columnar copy of the same rows in their natural types (19 B instead of 32 B per row on the wire)
+    int16_t* col_pad;
+    double* col_tb;
+    int64_t* col_electrons;
+    int8_t* col_label;
 };
 
 constexpr uint32_t F_KEEP_ALL_TB = 1u, F_SPYRAL = 2u, F_NO_WIGGLE = 4u;
@@ -1330,9 +1335,16 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
         row[0] = (double)pad;
         row[1] = tbf;
         row[2] = (double)(long long)en.charge;
-        fa.labels[off + i] = fa.label_of_event_rank
-                                 ? (int64_t)fa.label_of_event_rank[(int64_t)slot_event * fa.n_tracks_per_event + en.rank]
-                                 : (int64_t)fa.label_of_rank[en.rank];
+        const int64_t label = fa.label_of_event_rank
+                                  ? (int64_t)fa.label_of_event_rank[(int64_t)slot_event * fa.n_tracks_per_event + en.rank]
+                                  : (int64_t)fa.label_of_rank[en.rank];
+        fa.labels[off + i] = label;
+        if (fa.col_pad) {
+            fa.col_pad[off + i] = (int16_t)pad;
+            fa.col_tb[off + i] = tbf;
+            fa.col_electrons[off + i] = (long long)en.charge;
+            fa.col_label[off + i] = (int8_t)label;
+        }
     }
 }
 

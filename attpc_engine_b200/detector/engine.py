@@ -14,7 +14,6 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from dataclasses import dataclass, field
 
 import numpy as np
 
@@ -62,25 +61,58 @@ def default_freeze_ke(fano_factor: float, w_value: float, z_abs_max: float = 8.6
     return 0.999 * root * root * w_value * 1.0e-6
 
 
-@dataclass
 class SimBatch:
-    """CSR point clouds of a batch: event ``e`` owns rows ``offsets[e]:offsets[e+1]``."""
+    """CSR point clouds of a batch: event ``e`` owns rows ``offsets[e]:offsets[e+1]``.
 
-    first_event: int
-    offsets: np.ndarray
-    cloud: np.ndarray  # [N, 3] pad, time bucket, electrons
-    labels: np.ndarray  # [N]
-    row_offsets: np.ndarray | None = None
-    rows: np.ndarray | None = None  # [M, 8] Spyral rows
-    row_labels: np.ndarray | None = None
-    stats: dict = field(default_factory=dict)
+    Rows are either held as the reference's arrays (``cloud`` float64 ``[N, 3]`` = pad, time bucket, electrons;
+    ``labels`` int64 ``[N]``) or, for batches simulated with ``columns=True``, as typed columns (``pad`` int16,
+    ``tb`` float64, ``electrons`` int64, ``label8`` int8: 19 instead of 32 bytes per row over PCIe).  ``cloud`` /
+    ``labels`` / ``event(e)`` work in both cases; with columns they are materialised on demand.
+    """
+
+    def __init__(self, first_event, offsets, cloud=None, labels=None, row_offsets=None, rows=None, row_labels=None,
+                 stats=None, columns=None):  # fmt: skip
+        self.first_event = first_event
+        self.offsets = offsets
+        self._cloud = cloud
+        self._labels = labels
+        self.row_offsets = row_offsets
+        self.rows = rows  # [M, 8] Spyral rows
+        self.row_labels = row_labels
+        self.stats = {} if stats is None else stats
+        self.columns = columns  # dict(pad, tb, electrons, label8) or None
 
     def __len__(self) -> int:
         return len(self.offsets) - 1
 
+    @property
+    def cloud(self) -> np.ndarray:
+        if self._cloud is None and self.columns is not None:
+            c = self.columns
+            out = np.empty((len(c["pad"]), 3), dtype=np.float64)
+            out[:, 0] = c["pad"]
+            out[:, 1] = c["tb"]
+            out[:, 2] = c["electrons"]
+            self._cloud = out
+        return self._cloud
+
+    @property
+    def labels(self) -> np.ndarray:
+        if self._labels is None and self.columns is not None:
+            self._labels = self.columns["label8"].astype(np.int64)
+        return self._labels
+
     def event(self, e: int) -> tuple[np.ndarray, np.ndarray]:
+        """``(cloud [n, 3] float64, labels [n] int64)`` of event ``e``, like `simulate` returns them."""
         a, b = self.offsets[e], self.offsets[e + 1]
-        return self.cloud[a:b], self.labels[a:b]
+        if self._cloud is None and self.columns is not None:
+            c = self.columns
+            cloud = np.empty((b - a, 3), dtype=np.float64)
+            cloud[:, 0] = c["pad"][a:b]
+            cloud[:, 1] = c["tb"][a:b]
+            cloud[:, 2] = c["electrons"][a:b]
+            return cloud, c["label8"][a:b].astype(np.int64)
+        return self._cloud[a:b], self._labels[a:b]
 
     def event_rows(self, e: int) -> tuple[np.ndarray, np.ndarray]:
         a, b = self.row_offsets[e], self.row_offsets[e + 1]
@@ -239,12 +271,22 @@ class Engine:
                             stats=dict(stats, n_points=n_pts))  # fmt: skip
         grab = (lambda a: a.copy()) if copy else (lambda a: a)
         offsets = grab(np.ctypeslib.as_array(res.offsets, shape=(n_ev + 1,)))
-        if n_pts > 0 and res.cloud:
+        columns = None
+        if res.col_pad:
+            take = (lambda p: grab(np.ctypeslib.as_array(p, shape=(n_pts,)))) if n_pts > 0 else None
+            columns = dict(
+                pad=take(res.col_pad) if take else np.zeros(0, np.int16),
+                tb=take(res.col_tb) if take else np.zeros(0, np.float64),
+                electrons=take(res.col_electrons) if take else np.zeros(0, np.int64),
+                label8=take(res.col_label) if take else np.zeros(0, np.int8),
+            )
+            cloud = labels = None
+        elif n_pts > 0 and res.cloud:
             cloud = grab(np.ctypeslib.as_array(res.cloud, shape=(n_pts, 3)))
             labels = grab(np.ctypeslib.as_array(res.labels, shape=(n_pts,)))
         else:
             cloud, labels = np.zeros((0, 3)), np.zeros(0, np.int64)
-        out = SimBatch(first_event, offsets, cloud, labels, stats=dict(stats, n_points=n_pts))
+        out = SimBatch(first_event, offsets, cloud, labels, stats=dict(stats, n_points=n_pts), columns=columns)
         if rows:
             n_rows = int(res.n_rows)
             out.row_offsets = grab(np.ctypeslib.as_array(res.row_offsets, shape=(n_ev + 1,)))
@@ -271,10 +313,12 @@ class Engine:
         copy: bool = True,
         host_copy: bool = True,
         rows_only: bool = False,
+        columns: bool = False,
     ) -> SimBatch:
         """`simulate` (`simulator.py:52-115`) for ``B`` events at once: ``momenta [B, K, 4]``, ``vertices [B, 3]``.
 
         ``rows_only`` (with ``spyral_rows``): bring back offsets and Spyral rows but leave the raw cloud on the GPU.
+        ``columns``: bring the rows back as typed columns (19 B/row instead of 32 B/row over PCIe), see `SimBatch`.
         """
         momenta = np.ascontiguousarray(momenta, dtype=np.float64)
         vertices = np.ascontiguousarray(vertices, dtype=np.float64)
@@ -288,6 +332,8 @@ class Engine:
             flags |= _lib.SKIP_HOST_COPY
         if rows_only and spyral_rows:
             flags |= _lib.SKIP_CLOUD_COPY
+        elif columns:
+            flags |= _lib.COLUMNS
         res = _lib.AttpcResult()
         code = self.lib.attpc_simulate(
             self.handle, _ptr(momenta, C.c_double), _ptr(vertices, C.c_double), momenta.shape[0], momenta.shape[1],

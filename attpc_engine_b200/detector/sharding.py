@@ -53,8 +53,9 @@ def concat_batches(batches: list[SimBatch]) -> SimBatch:
 def gather_to_rank0(batch: SimBatch, dist) -> SimBatch | None:
     """Gather every rank's shard on rank 0 through ``torch.distributed`` (host objects; any backend)."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    payload = dict(first_event=batch.first_event, offsets=batch.offsets, cloud=batch.cloud, labels=batch.labels,
-                   row_offsets=batch.row_offsets, rows=batch.rows, row_labels=batch.row_labels, stats=batch.stats)  # fmt: skip
+    payload = dict(first_event=batch.first_event, offsets=batch.offsets, cloud=batch._cloud, labels=batch._labels,
+                   row_offsets=batch.row_offsets, rows=batch.rows, row_labels=batch.row_labels, stats=batch.stats,
+                   columns=batch.columns)  # fmt: skip
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(payload, gathered, dst=0)
     if rank != 0:

@@ -66,6 +66,7 @@ def simulate_batch(
     copy: bool = True,
     nuclear_data=None,
     rows_only: bool = False,
+    columns: bool = False,
     **tuning,
 ) -> SimBatch:
     """Detector simulation of ``B`` kinematics events in one call.
@@ -88,7 +89,7 @@ def simulate_batch(
     engine = engine_for(config, charged, device=device, **tuning)
     return engine.simulate_batch(
         momenta, vertices, proton_numbers, mass_numbers, indices, seed=seed, first_event=first_event,
-        spyral_rows=spyral_rows, copy=copy, rows_only=rows_only,
+        spyral_rows=spyral_rows, copy=copy, rows_only=rows_only, columns=columns,
     )  # fmt: skip
 
 
@@ -204,6 +205,7 @@ def run_simulation(
             momenta, vertices, kin.proton_numbers, kin.mass_numbers, config, seed, nuclei_to_sim,
             first_event=start, device=device, spyral_rows=want_rows, copy=False,
             rows_only=want_rows and bool(getattr(writer, "rows_only", False)),
+            columns=not batched,  # per-event writers get their arrays built event by event anyway
         )  # fmt: skip
         if batched:
             writer.write_batch(batch, config)
@@ -212,7 +214,7 @@ def run_simulation(
             cloud, labels = batch.event(e)
             if len(cloud) == 0:  # `simulator.py:204`
                 continue
-            writer.write(cloud.copy(), labels.copy(), config, start + e)
+            writer.write(np.array(cloud), np.array(labels), config, start + e)
     writer.close()
     if verbose:
         print("Done.")

@@ -267,7 +267,8 @@ def run_ours(args):
 
     def step_e2e(i):
         return eng.simulate_batch(mom_pin.numpy(), vtx_pin.numpy(), zs, as_, indices, seed=seed + i, first_event=first,
-                                  copy=False, spyral_rows=args.spyral, rows_only=args.spyral).stats  # fmt: skip
+                                  copy=False, spyral_rows=args.spyral, rows_only=args.spyral,
+                                  columns=not args.float64_rows).stats  # fmt: skip
 
     sampler = ClockSampler(local)
     sampler.start()  # nvidia-smi needs a moment to come up: started before the warm-up, read after the timed loops
@@ -351,7 +352,10 @@ def run_ours(args):
         "wall_s_device_loop": round(wall_dev, 3),
         "e2e": {"value": None if args.no_e2e else round(total_events / e2e_s, 1), "unit": "events/s",
                 "h2d_bytes_per_step": int(momenta.nbytes + vertices.nbytes),
-                "d2h_bytes_per_step": int((e2e_rows * 72 if args.spyral else e2e_points * 32) / args.steps
+                "result": ("Spyral rows float64[M,8] + labels" if args.spyral else
+                           "cloud float64[N,3] + int64 labels" if args.float64_rows else
+                           "typed columns: pad int16, tb float64, electrons int64, label int8"),
+                "d2h_bytes_per_step": int((e2e_rows * 72 if args.spyral else e2e_points * (32 if args.float64_rows else 19)) / args.steps
                                           + (B + 1) * 8 * (2 if args.spyral else 1))},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }  # fmt: skip
@@ -423,6 +427,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: only the device-resident steps")
     ap.add_argument("--spyral", action="store_true", help="also produce the Spyral 8-column rows (full pad-plane response)")
+    ap.add_argument("--float64-rows", action="store_true",
+                    help="e2e: bring the cloud back as float64[N,3] + int64 labels (32 B/row) instead of typed columns")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

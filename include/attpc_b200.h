@@ -37,7 +37,9 @@ enum {
     ATTPC_NO_WIGGLE = 1u << 2,     /* add 0 instead of U[0,1) to the time bucket (tests) */
     ATTPC_SKIP_HOST_COPY = 1u << 3,/* leave results in device memory only (device-resident benchmarking) */
     ATTPC_ROWS_KEEP_ALL = 1u << 4, /* attpc_convert_to_spyral: every row, input order (no threshold, no sort) */
-    ATTPC_SKIP_CLOUD_COPY = 1u << 5 /* with ATTPC_SPYRAL_ROWS: copy offsets and rows to the host, not the raw cloud */
+    ATTPC_SKIP_CLOUD_COPY = 1u << 5,/* with ATTPC_SPYRAL_ROWS: copy offsets and rows to the host, not the raw cloud */
+    ATTPC_COLUMNS = 1u << 6        /* host result as typed columns (col_* of AttpcResult, 19 B/row) instead of the
+                                      float64 cloud + int64 labels (32 B/row); same rows, same order */
 };
 
 /* Scalars of DetectorParams / ElectronicsParams / Config (detector/parameters.py:10-76,164-174). */
@@ -122,6 +124,11 @@ typedef struct AttpcResult {
     int32_t hash_capacity;       /* slots per event in use at the end of the call */
     int32_t reserved1;
     int64_t n_table_flushes;     /* shared-memory tables merged into a global table (dense or split events) */
+    /* ATTPC_COLUMNS: the rows of `cloud` / `labels` as typed columns (pinned host memory) */
+    const int16_t* col_pad;      /* [n_points] pad id */
+    const double* col_tb;        /* [n_points] time bucket + wiggle */
+    const int64_t* col_electrons;/* [n_points] electrons (after gain) */
+    const int8_t* col_label;     /* [n_points] index of the nucleus that last touched the point */
 } AttpcResult;
 
 typedef struct AttpcSim AttpcSim;

@@ -231,3 +231,16 @@ def test_full_size_properties(name, n_events):
     b = simulate_batch(momenta[half:], vertices[half:], zs, as_, config, 99, indices, first_event=half)
     merged = concat_batches([a, b])
     assert np.array_equal(merged.offsets, off) and np.array_equal(merged.cloud, cloud)
+
+
+def test_typed_columns_hold_the_same_rows(dist):
+    """`columns=True` changes the wire format (19 B/row instead of 32 B/row), not the content."""
+    cfg, m, v, zs, as_, idx = _workload(dist, "c16dd", 200)
+    plain = simulate_batch(m, v, zs, as_, cfg, 31, idx)
+    cols = simulate_batch(m, v, zs, as_, cfg, 31, idx, columns=True, max_events_per_launch=64, copy_events_per_launch=64)
+    assert cols.columns is not None and cols.columns["pad"].dtype == np.int16 and cols.columns["label8"].dtype == np.int8
+    assert np.array_equal(cols.offsets, plain.offsets)
+    ev_cloud, ev_labels = cols.event(17)
+    assert ev_cloud.dtype == np.float64 and ev_labels.dtype == np.int64
+    assert np.array_equal(ev_cloud, plain.event(17)[0]) and np.array_equal(ev_labels, plain.event(17)[1])
+    assert np.array_equal(cols.cloud, plain.cloud) and np.array_equal(cols.labels, plain.labels)
