@@ -91,7 +91,7 @@ struct AttpcSim {
 
     // sizing
     int32_t launch_events = 32768;
-    int32_t copy_launch_events = 4096;
+    int32_t copy_launch_events = 2048;
     int32_t group_events = 2048;
     int32_t hash_cap = 16384;
     int64_t group_point_cap = 0;
@@ -119,6 +119,7 @@ struct AttpcSim {
     size_t sync_used = 0;
     DevArray<unsigned long long> csr_total;
     PinnedArray<unsigned long long> csr_host;
+    PinnedArray<unsigned long long> chunk_totals;  // running CSR total after each chunk of groups (mapped)
     DevArray<double> geom;
     DevArray<long long> sq;
     DevArray<int32_t> meta, unit_event, unit_first, unit_count, unit_order, n_units;
@@ -233,6 +234,7 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     CU(sim->sort_items.reserve((int64_t)sim->group_events * sim->hash_cap * 2));
     CU(sim->csr_total.reserve(2));
     CU(sim->csr_host.reserve(2));
+    CU(sim->chunk_totals.reserve(n_groups + 1));
     return ATTPC_OK;
 }
 
@@ -299,9 +301,17 @@ int launch_tracks(AttpcSim* sim, const TrackBatch& tb, int64_t n_tracks, int whi
 }
 
 // deposit + finalize of every group of one launch; the track/replay kernel has already filled the point buffers.
+// One entry per chunk of groups whose rows can be copied to the host as soon as `done` has fired.
+struct ChunkFence {
+    cudaEvent_t done;
+    int64_t last_event;  // events [.., last_event) of the launch are final after this chunk
+    int slot;            // index into sim->chunk_totals (running CSR total after the chunk)
+};
+
 int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
                std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& dep_marks,
-               std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& fin_marks) {
+               std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& fin_marks, int groups_per_chunk,
+               std::vector<ChunkFence>* fences) {
     PointBuf pb = point_buf(sim, which);
     Counters* ctr = sim->slot[which].counters.p;
     const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
@@ -331,6 +341,14 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         sim->launches += 7;
         dep_marks.push_back({d0, d1});
         fin_marks.push_back({d1, f1});
+        if (fences && groups_per_chunk > 0 && ((g + 1) % groups_per_chunk == 0 || g + 1 == n_groups)) {
+            const int slot = (int)fences->size();
+            if (slot < (int)sim->chunk_totals.n) {
+                publish_total_kernel<<<1, 1, 0, sim->stream>>>(sim->csr_total.p, sim->chunk_totals.p + slot);
+                sim->launches += 1;
+                fences->push_back({sim->fence(sim->stream), gv.first_slot + (int64_t)gv.n_events, slot});
+            }
+        }
     }
     CU(cudaGetLastError());
     return ATTPC_OK;
@@ -436,11 +454,11 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     int64_t out_cap = std::max<int64_t>(sim->labels_dev.n, std::max<int64_t>(n_events * 2048, 1 << 20));
     int rc = ensure_out_buffers(sim, n_events, out_cap, false);
     if (rc) return rc;
-    // device-resident results: big launches (the latency-bound track kernel wants many tracks in flight);
-    // results copied to the host: smaller launches, so that the copy of one overlaps the compute of the next
-    const int64_t launch_cap = plan.replay ? std::max<int64_t>(n_events, 1)
-                               : copy_host ? std::min(sim->launch_events, sim->copy_launch_events)
-                                           : sim->launch_events;
+    // big launches: the latency-bound track kernel wants many tracks in flight.  When rows go to the host they are
+    // copied in chunks of a few groups while the following groups are still being computed.
+    const int64_t launch_cap = plan.replay ? std::max<int64_t>(n_events, 1) : sim->launch_events;
+    const int groups_per_chunk =
+        std::max<int>(1, (int)((sim->copy_launch_events + sim->group_events - 1) / sim->group_events));
     const int32_t ranks = std::max<int32_t>(1, plan.n_tracks_per_event);
     rc = ensure_work_buffers(sim, std::min<int64_t>(std::max<int64_t>(n_events, 1), launch_cap), ranks);
     if (rc) return rc;
@@ -544,14 +562,55 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             for (int t = 0; t < plan.n_tracks_per_event; ++t) fa.label_of_rank[t] = plan.track_nucleus[t];
         }
         CU(cudaStreamWaitEvent(G, track_done[i], 0));
-        const size_t dep_before = dep_marks.size(), fin_before = fin_marks.size();
-        rc = run_groups(sim, nb, fa, which, dep_marks, fin_marks);
+        const size_t dep_before = dep_marks.size(), fin_before = fin_marks.size(), copy_before = copy_marks.size();
+        std::vector<ChunkFence> fences;
+        rc = run_groups(sim, nb, fa, which, dep_marks, fin_marks, groups_per_chunk, copy_host ? &fences : nullptr);
         if (rc) return rc;
         publish_kernel<<<1, 1, 0, G>>>(ls.counters.p, sim->csr_total.p, ls.counters_host.p, sim->csr_host.p);
         sim->launches += 1;
         cudaEvent_t groups_done = sim->fence(G);
         if (next_track <= i + 1 && i + 1 < n_launch) {  // overlaps with the groups just enqueued
             rc = enqueue_track(next_track++);
+            if (rc) return rc;
+        }
+        // rows of finished chunks go home while the later groups (and the next launch's tracks) compute
+        unsigned long long copied = csr_before;
+        int64_t copied_events = 0;  // events of this launch whose offsets are on the host
+        auto copy_rows = [&](unsigned long long upto, int64_t upto_event) -> int {
+            cudaEvent_t c0 = sim->mark(C);
+            const int64_t first_off = (b0 + copied_events == 0) ? 0 : b0 + copied_events + 1;
+            const int64_t end_off = b0 + upto_event + 1;
+            if (end_off > first_off)
+                CU(cudaMemcpyAsync(sim->offsets_host.p + first_off, sim->offsets_dev.p + first_off,
+                                   (size_t)(end_off - first_off) * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+            const int64_t n_new = (int64_t)(upto - copied);
+            if (n_new > 0 && copy_cloud) {
+                CU(cudaMemcpyAsync(sim->cloud_host.p + copied * 3, sim->cloud_dev.p + copied * 3,
+                                   (size_t)n_new * 3 * sizeof(double), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->labels_host.p + copied, sim->labels_dev.p + copied,
+                                   (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+            }
+            if (n_new > 0 && use_columns) {
+                CU(cudaMemcpyAsync(sim->col_pad_host.p + copied, sim->col_pad_dev.p + copied,
+                                   (size_t)n_new * sizeof(int16_t), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->col_tb_host.p + copied, sim->col_tb_dev.p + copied,
+                                   (size_t)n_new * sizeof(double), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->col_q_host.p + copied, sim->col_q_dev.p + copied,
+                                   (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->col_label_host.p + copied, sim->col_label_dev.p + copied,
+                                   (size_t)n_new * sizeof(int8_t), cudaMemcpyDeviceToHost, C));
+            }
+            copy_marks.push_back({c0, sim->mark(C)});
+            copied = upto;
+            copied_events = upto_event;
+            return ATTPC_OK;
+        };
+        for (const ChunkFence& cf : fences) {
+            CU(cudaEventSynchronize(cf.done));
+            const unsigned long long upto = sim->chunk_totals.p[cf.slot];
+            if ((int64_t)upto > sim->labels_dev.n) break;  // output overflow: the launch will be redone below
+            CU(cudaStreamWaitEvent(C, cf.done, 0));
+            rc = copy_rows(upto, cf.last_event);
             if (rc) return rc;
         }
         CU(cudaEventSynchronize(groups_done));
@@ -562,6 +621,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         if (now.overflow_points || now.overflow_hash || now.overflow_out) {
             dep_marks.resize(dep_before);
             fin_marks.resize(fin_before);
+            copy_marks.resize(copy_before);
             if (++retries > 24) return sim->fail(ATTPC_E_CAPACITY, "buffers still too small after 24 retries");
             CU(cudaStreamSynchronize(T));  // the next launch's track kernel may be using buffers we are about to free
             CU(cudaStreamSynchronize(C));
@@ -611,30 +671,10 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         totals.probes += now.probes;
         totals.flushes += now.flushes;
         const unsigned long long csr_after = sim->csr_host.p[0];
-        if (copy_host) {  // rows of this launch go home while the next launch computes
+        if (copy_host && (copied < csr_after || copied_events < nb)) {  // whatever the chunk copies did not cover
             CU(cudaStreamWaitEvent(C, groups_done, 0));
-            cudaEvent_t c0 = sim->mark(C);
-            const int64_t first_off = b0 == 0 ? 0 : b0 + 1;  // offsets[b0] was already copied with the previous launch
-            CU(cudaMemcpyAsync(sim->offsets_host.p + first_off, sim->offsets_dev.p + first_off,
-                               (size_t)(b0 + nb + 1 - first_off) * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
-            const int64_t n_new = (int64_t)(csr_after - csr_before);
-            if (n_new > 0 && copy_cloud) {
-                CU(cudaMemcpyAsync(sim->cloud_host.p + csr_before * 3, sim->cloud_dev.p + csr_before * 3,
-                                   (size_t)n_new * 3 * sizeof(double), cudaMemcpyDeviceToHost, C));
-                CU(cudaMemcpyAsync(sim->labels_host.p + csr_before, sim->labels_dev.p + csr_before,
-                                   (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
-            }
-            if (n_new > 0 && use_columns) {
-                CU(cudaMemcpyAsync(sim->col_pad_host.p + csr_before, sim->col_pad_dev.p + csr_before,
-                                   (size_t)n_new * sizeof(int16_t), cudaMemcpyDeviceToHost, C));
-                CU(cudaMemcpyAsync(sim->col_tb_host.p + csr_before, sim->col_tb_dev.p + csr_before,
-                                   (size_t)n_new * sizeof(double), cudaMemcpyDeviceToHost, C));
-                CU(cudaMemcpyAsync(sim->col_q_host.p + csr_before, sim->col_q_dev.p + csr_before,
-                                   (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
-                CU(cudaMemcpyAsync(sim->col_label_host.p + csr_before, sim->col_label_dev.p + csr_before,
-                                   (size_t)n_new * sizeof(int8_t), cudaMemcpyDeviceToHost, C));
-            }
-            copy_marks.push_back({c0, sim->mark(C)});
+            rc = copy_rows(csr_after, nb);
+            if (rc) return rc;
         }
         csr_before = csr_after;
         ++i;
@@ -729,7 +769,7 @@ void attpc_destroy(AttpcSim* sim) {
     for (auto e : sim->events) cudaEventDestroy(e);
     for (auto e : sim->sync_events) cudaEventDestroy(e);
     for (auto& ls : sim->slot) ls.release_all();
-    sim->csr_total.release(); sim->csr_host.release();
+    sim->csr_total.release(); sim->csr_host.release(); sim->chunk_totals.release();
     if (sim->stream_t) cudaStreamDestroy(sim->stream_t);
     if (sim->stream_c) cudaStreamDestroy(sim->stream_c);
     sim->lut.release(); sim->pad_xy.release(); sim->pad_scale.release(); sim->response.release();

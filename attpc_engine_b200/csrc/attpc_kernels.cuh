@@ -109,6 +109,12 @@ __global__ void publish_kernel(const Counters* ctr, const unsigned long long* cs
     __threadfence_system();
 }
 
+// Running CSR total after a chunk of groups, published for the host so that it can start copying the finished rows.
+__global__ void publish_total_kernel(const unsigned long long* csr, unsigned long long* host_slot) {
+    *host_slot = csr[0];
+    __threadfence_system();
+}
+
 struct HashEntry {
     unsigned key1;   // Szudzik key + 1, 0 = empty
     unsigned rank;   // highest track rank that touched the key (label precedence, transporter.py:247-249)

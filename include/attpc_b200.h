@@ -68,7 +68,7 @@ typedef struct AttpcConfig {
     /* capacities (0 = library default); they grow automatically on overflow */
     int32_t max_events_per_launch;
     int32_t hash_capacity;          /* slots per event, power of two */
-    int32_t copy_events_per_launch; /* launch size when results are copied to the host (copy/compute overlap) */
+    int32_t copy_events_per_launch; /* events per host-copy chunk: rows are copied while later groups compute */
 } AttpcConfig;
 
 /* One ion species: the dE/dx table of attpc_engine_b200/target.py:DedxTable (pseudo-log grid). */

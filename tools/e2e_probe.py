@@ -13,7 +13,7 @@ mp = torch.from_numpy(momenta).pin_memory(); vp = torch.from_numpy(vertices).pin
 md = mp.cuda(); vd = vp.cuda()
 keys = ('ms_h2d','ms_tracks','ms_deposit','ms_finalize','ms_d2h','ms_total','n_retries','n_points','n_kernel_launches')
 for i in range(4):
-    t0 = time.perf_counter(); st = eng.simulate_batch(mp.numpy(), vp.numpy(), zs, as_, indices, seed=i, copy=False).stats; w = time.perf_counter() - t0
+    t0 = time.perf_counter(); st = eng.simulate_batch(mp.numpy(), vp.numpy(), zs, as_, indices, seed=i, copy=False, columns=True).stats; w = time.perf_counter() - t0
     print('e2e ', round(w * 1e3, 1), 'ms wall', {k: round(st[k], 2) if isinstance(st[k], float) else st[k] for k in keys})
 for i in range(3):
     t0 = time.perf_counter(); st = eng.simulate_device(md.data_ptr(), vd.data_ptr(), B, 4, zs, as_, indices, seed=i).stats; w = time.perf_counter() - t0
