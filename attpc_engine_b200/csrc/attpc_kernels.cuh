@@ -116,7 +116,7 @@ __global__ void publish_total_kernel(const unsigned long long* csr, unsigned lon
 }
 
 struct HashEntry {
-    unsigned key1;   // Szudzik key + 1, 0 = empty
+    unsigned key1;   // compact key ((time bucket << 15) | pad) + 1, 0 = empty (the Szudzik id is formed on output)
     unsigned rank;   // highest track rank that touched the key (label precedence, transporter.py:247-249)
     unsigned long long charge;
 };
@@ -987,8 +987,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
             const unsigned w = t.word[i];
             if (w) {
                 const unsigned kc = (w & SMEM_KEY_MASK) - 1u;
-                table_add(region, gmask, szudzik_pair(kc >> 15, kc & 0x7FFFu), (long long)smem_charge_of(t, i), w >> 28,
-                          ctr);
+                table_add(region, gmask, kc, (long long)smem_charge_of(t, i), w >> 28, ctr);
             }
         }
         __syncthreads();
@@ -1102,7 +1101,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
             if (w) {
                 const unsigned kc = (w & SMEM_KEY_MASK) - 1u;
                 const unsigned pos = atomicAdd(&s_out, 1u);
-                region[pos] = HashEntry{szudzik_pair(kc >> 15, kc & 0x7FFFu) + 1u, w >> 28, smem_charge_of(t, i)};
+                region[pos] = HashEntry{kc + 1u, w >> 28, smem_charge_of(t, i)};
             }
         }
         __syncthreads();
@@ -1214,10 +1213,9 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     for (int i = threadIdx.x; i < limit; i += blockDim.x) {
         const unsigned key1 = tab[i].key1;
         if (key1 == 0u) continue;
-        const unsigned key = key1 - 1u;
         occupied += 1;
-        unsigned tb, pad;
-        szudzik_unpair(key, tb, pad);
+        const unsigned tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
+        const unsigned key = szudzik_pair(tb, pad);  // detector/pairing.py: id of the (tb, pad) cell
         const double tbf = (double)tb + wiggle_of(fa, slot_event, key, ctr);      // detector/simulator.py:108
         if ((fa.flags & F_KEEP_ALL_TB) || (0.0 <= tbf && tbf < (double)NUM_TB)) {  // detector/simulator.py:111
             atomicAdd(&s_hist[min(tb, (unsigned)TB_BINS - 1u)], 1u);
@@ -1275,10 +1273,16 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int b = warp; b < TB_BINS; b += FINALIZE_THREADS / 32) {
         const int lo = (int)s_hist[b], hi = (int)s_hist[b + 1];
+        const bool one_tb = b < TB_BINS - 1;  // all items of the bucket share the time bucket: compare pads only
         for (int i = lo + lane; i < hi; i += 32) {
             const uint64_t v = buf[i];
             int rank = 0;
-            for (int j = lo; j < hi; ++j) rank += buf[j] < v;
+            if (one_tb) {
+                const uint32_t vp = (uint32_t)(v >> 32);
+                for (int j = lo; j < hi; ++j) rank += (uint32_t)(buf[j] >> 32) < vp;
+            } else {
+                for (int j = lo; j < hi; ++j) rank += buf[j] < v;
+            }
             dst[lo + rank] = v;
         }
     }
