@@ -22,6 +22,7 @@ SKIP_HOST_COPY = 1 << 3
 ROWS_KEEP_ALL = 1 << 4
 SKIP_CLOUD_COPY = 1 << 5
 COLUMNS = 1 << 6
+EXACT_MESH = 1 << 7
 
 
 class AttpcConfig(C.Structure):

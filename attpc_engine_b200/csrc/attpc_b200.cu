@@ -328,6 +328,7 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         gv.tables = sim->hash.p;
         gv.n_entries = sim->n_entries.p;
         gv.mode = sim->mode.p;
+        gv.exact_mesh = (fa.flags & ATTPC_EXACT_MESH) ? 1 : 0;
         cudaEvent_t d0 = sim->mark();
         point_scan_kernel<<<1, 1024, 0, sim->stream>>>(pb, gv, ctr);
         point_order_kernel<<<sim->sm_count * 4, 256, 0, sim->stream>>>(sim->P, pb, gv, ctr);
@@ -939,6 +940,16 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
             CUC(cudaMemcpy(sim->tables.p, scaled.data(), scaled.size() * sizeof(double), cudaMemcpyHostToDevice));
         sim->table_smem_bytes = scaled.size() * sizeof(double);
         sim->tables_in_smem = sim->table_smem_bytes <= 160 * 1024;
+    }
+    {
+        // constant mesh weights pdf * step^2 of detector/transporter.py:217-246 in exact arithmetic (sigma cancels):
+        // (36 / 81) / (2 pi) * exp(-(a_i^2 + a_j^2) / 2), a_i = -3 + 6 i / 9, rounded once from extended precision
+        const long double pi_l = 3.14159265358979323846264338327950288L;
+        for (int i = 0; i < MESH_N; ++i)
+            for (int j = 0; j < MESH_N; ++j) {
+                const long double ai = -3.0L + 6.0L * i / 9.0L, aj = -3.0L + 6.0L * j / 9.0L;
+                P.mesh_w[i * MESH_N + j] = (double)((2.0L / (9.0L * pi_l)) * expl(-(ai * ai + aj * aj) / 2.0L));
+            }
     }
     P.lut = sim->lut.p;
     P.tables = sim->tables.p;

@@ -61,6 +61,7 @@ struct SimParams {
     const double* resp_sorted;   // response sorted descending
     const double* resp_prefix;   // prefix sums of resp_sorted, [n_response + 1]
     double resp_max;
+    double mesh_w[MESH_N * MESH_N];  // (2 / (9 pi)) exp(-(a_i^2 + a_j^2) / 2), a_i = -3 + 6 i / 9: pdf * step^2 of the mesh
 };
 
 // Active track points (>= 1 electron).  The track kernels append them per event group in arrival order and number
@@ -712,6 +713,7 @@ struct GroupView {
     HashEntry* tables;    // [group_events][hash_cap]: dense entry list (mode 0) or open-addressing table (mode 1)
     unsigned* n_entries;  // [launch events] entries of the dense list
     unsigned* mode;       // [launch events] 0 = dense list, 1 = the event spilled to a global table
+    int32_t exact_mesh;   // ATTPC_EXACT_MESH: every pixel through the reference's own expression (validation)
 };
 
 // ------------------------------------------------------------------------------------------- ordering of points
@@ -821,12 +823,26 @@ __global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView
 
 // ------------------------------------------------------------------------------------------------- drift geometry
 // Per-point constants of detector/transporter.py:172-249, in the reference's operation order.
-// geom[] = cx, cy, lo_x, hi_x, dx, lo_y, hi_y, dy, cell2, norm, c2, qd
+// geom[] = cx, cy, lo_x, hi_x, dx, lo_y, hi_y, dy, sigma, guard, qd, (unused)
+//
+// `guard` bounds the relative distance between the reference's floating-point value of
+//     pdf * (step_x * step_y) * electrons                      (detector/transporter.py:240-246)
+// and the exact-arithmetic value  (2 / (9 pi)) exp(-(a_i^2 + a_j^2) / 2) * electrons,  a_i = -3 + 6 i / 9,  which does
+// not depend on sigma or on the mesh centre.  Error budget in units of u = 2^-53, with M = max(|cx|, |cy|) + 3 sigma
+// the largest magnitude that is rounded while the pixel coordinates are formed:
+//   * pixel - centre: numba's linspace rounds lo, hi, (hi - lo) / 9, i * d and lo + i * d: |err| <= (4 M + 21 sigma) u
+//   * exponent (-1 / 2 / sigma^2) * (dx^2 + dy^2): |err| <= 6 (4 M + 21 sigma) u / sigma + 54 u   (|exponent| <= 9)
+//   * c1, exp (<= 1 ulp), the two products, the constant table: < 40 u
+// => relative error <= (24 M / sigma + 220) u.  The deposit kernel uses the table whenever the product is further
+// than twice that bound from an integer (so the truncation of transporter.py:240 cannot differ) and evaluates the
+// reference's own expression otherwise.
+constexpr double MESH_GUARD_U = 1.1102230246251565e-16;  // 2^-53
+
 __device__ __forceinline__ int make_geom(const SimParams& P, double cx, double cy, double time, long long q,
                                          double* g) {
     g[0] = cx;
     g[1] = cy;
-    g[11] = (double)q;
+    g[10] = (double)q;
     // detector/transporter.py:301, evaluated left to right
     const double sigma = __dsqrt_rn(__ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, P.diffusion), P.dv), time), P.efield));
     const int tb = (int)time;  // detector/transporter.py:165, 238
@@ -840,12 +856,26 @@ __device__ __forceinline__ int make_geom(const SimParams& P, double cx, double c
     g[5] = __dsub_rn(cy, three_sigma);
     g[6] = __dadd_rn(cy, three_sigma);
     g[7] = __ddiv_rn(__dsub_rn(g[6], g[5]), (double)(MESH_N - 1));
-    const double cell = __ddiv_rn(__dmul_rn(6.0, sigma), (double)(MESH_N - 1));
-    g[8] = __dmul_rn(cell, cell);
-    const double s2 = __dmul_rn(sigma, sigma);
-    g[9] = __ddiv_rn(__ddiv_rn(0.5, 3.141592653589793), s2);  // 1 / 2 / pi / sigma**2
-    g[10] = __ddiv_rn(-0.5, s2);                              // -1 / 2 / sigma**2
+    g[8] = sigma;
+    const double big = fmax(fabs(cx), fabs(cy)) + three_sigma;
+    g[9] = 2.0 * (24.0 * big / sigma + 220.0) * MESH_GUARD_U;
     return tb | (2 << 30);                                    // kind 2: 10x10 mesh
+}
+
+// The reference's own arithmetic for one mesh pixel (i, j): detector/transporter.py:36-41, 217-226, 240-246.
+__device__ __noinline__ long long exact_share(const double* g, int i, int j) {
+    const double px = (i == MESH_N - 1) ? g[3] : __dadd_rn(g[2], __dmul_rn((double)i, g[4]));
+    const double py = (j == MESH_N - 1) ? g[6] : __dadd_rn(g[5], __dmul_rn((double)j, g[7]));
+    const double ddx = __dsub_rn(px, g[0]), ddy = __dsub_rn(py, g[1]);
+    const double r2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+    const double sigma = g[8];
+    const double cell = __ddiv_rn(__dmul_rn(6.0, sigma), (double)(MESH_N - 1));
+    const double cell2 = __dmul_rn(cell, cell);
+    const double s2 = __dmul_rn(sigma, sigma);
+    const double norm = __ddiv_rn(__ddiv_rn(0.5, 3.141592653589793), s2);  // 1 / 2 / pi / sigma**2
+    const double c2 = __ddiv_rn(-0.5, s2);                                 // -1 / 2 / sigma**2
+    const double pdf = __dmul_rn(norm, exp(__dmul_rn(c2, r2)));
+    return (long long)__dmul_rn(__dmul_rn(pdf, cell2), g[10]);
 }
 
 // Scatter the group's points into (event, rank, arrival) order and compute their mesh constants (one thread each).
@@ -977,6 +1007,10 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
         pi[k] = pix / MESH_N;
         pj[k] = pix - pi[k] * MESH_N;
     }
+    double wk[4];  // constant mesh weight of this lane's pixel in each round
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wk[k] = P.mesh_w[min(lane + 32 * k, MESH_N * MESH_N - 1)];
+    const bool exact_mesh = gv.exact_mesh != 0;
 
     auto flush_to_global = [&]() {  // all threads
         if (!shared_event && !s_spilled) {
@@ -1029,12 +1063,13 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
                         }
                     }
                 } else if (kind == 2) {
-                    const double2* gp = reinterpret_cast<const double2*>(pb.geom + p * GEOM_DOUBLES);
-                    const double2 g01 = gp[0], g23 = gp[1], g45 = gp[2], g67 = gp[3], g89 = gp[4], gab = gp[5];
+                    const double* g = pb.geom + p * GEOM_DOUBLES;
+                    const double2* gp = reinterpret_cast<const double2*>(g);
+                    const double2 g23 = gp[1], g45 = gp[2], g67 = gp[3], g89 = gp[4];
+                    const double qd = g[10];
                     // per-axis values, once per point: lanes 0-9 own x_i, lanes 10-19 own y_j
                     const bool is_y = lane >= MESH_N;
                     const int a = is_y ? lane - MESH_N : lane;
-                    const double c = is_y ? g01.y : g01.x;
                     const double lo_a = is_y ? g45.y : g23.x, hi_a = is_y ? g67.x : g23.y, d_a = is_y ? g67.y : g45.x;
                     const double pa = (a == MESH_N - 1) ? hi_a : __dadd_rn(lo_a, __dmul_rn((double)a, d_a));
                     // detector/transporter.py:102-120 on one coordinate: floor(mm), range test, LUT row / column
@@ -1044,24 +1079,24 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
                         idx = (int)f - P.lut_origin;
                         if ((unsigned)idx >= (unsigned)P.lut_n) idx = -1;
                     }
-                    const double dd = __dsub_rn(pa, c);
-                    const double dd2 = __dmul_rn(dd, dd);  // (pixel - center)**2 of transporter.py:38
                     int pad[4];
-                    double r2[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {  // all pad lookups first: independent loads in flight
                         const int ix = __shfl_sync(FULL, idx, pi[k]), iy = __shfl_sync(FULL, idx, MESH_N + pj[k]);
-                        r2[k] = __dadd_rn(__shfl_sync(FULL, dd2, pi[k]), __shfl_sync(FULL, dd2, MESH_N + pj[k]));
                         const bool ok = (lane + 32 * k < MESH_N * MESH_N) && ix >= 0 && iy >= 0;
                         pad[k] = ok ? (int)__ldg(P.lut + (int64_t)ix * P.lut_n + iy) : -1;
                     }
-                    // the four shares first: their FP64 work overlaps the latency of the pad-LUT loads
+                    // detector/transporter.py:240-246: int(pdf * step^2 * electrons).  pdf * step^2 is the constant
+                    // mesh weight up to rounding (see make_geom); the reference's own expression is evaluated only for
+                    // a product so close to an integer that the rounding could change the truncation.
                     long long share[4];
+                    const double guard = exact_mesh ? 2.0 : g89.y;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        // detector/transporter.py:36-41, 240-246
-                        const double pdf = __dmul_rn(g89.y, exp(__dmul_rn(gab.x, r2[k])));
-                        share[k] = (long long)__dmul_rn(__dmul_rn(pdf, g89.x), gab.y);
+                        const double v = __dmul_rn(wk[k], qd);
+                        share[k] = (long long)v;
+                        const bool risky = !(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v));
+                        if (risky && pad[k] >= 0) share[k] = exact_share(g, pi[k], pj[k]);
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {

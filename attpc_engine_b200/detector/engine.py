@@ -298,6 +298,13 @@ class Engine:
             out.stats["n_rows"] = n_rows
         return out
 
+    #: validation switch: evaluate every mesh pixel with the reference's own expression (`transporter.py:36-41`)
+    #: instead of the constant weight table + exactness guard.  Both give identical results.
+    exact_mesh = False
+
+    def _mesh_flag(self) -> int:
+        return _lib.EXACT_MESH if self.exact_mesh else 0
+
     # ------------------------------------------------------------------------------ hot path
     def simulate_batch(
         self,
@@ -334,6 +341,7 @@ class Engine:
             flags |= _lib.SKIP_CLOUD_COPY
         elif columns:
             flags |= _lib.COLUMNS
+        flags |= self._mesh_flag()
         res = _lib.AttpcResult()
         code = self.lib.attpc_simulate(
             self.handle, _ptr(momenta, C.c_double), _ptr(vertices, C.c_double), momenta.shape[0], momenta.shape[1],
@@ -350,6 +358,7 @@ class Engine:
         """Same with inputs already resident in device memory (raw CUDA pointers, e.g. ``tensor.data_ptr()``)."""
         nucleus, spec = self._species_of(proton_numbers, mass_numbers, indices)
         flags = (0 if host_copy else _lib.SKIP_HOST_COPY) | (_lib.SPYRAL_ROWS if spyral_rows else 0)
+        flags |= self._mesh_flag()
         res = _lib.AttpcResult()
         code = self.lib.attpc_simulate_dev(
             self.handle, C.c_void_p(momenta_ptr), C.c_void_p(vertices_ptr), int(n_events), int(n_nuclei),
@@ -411,6 +420,7 @@ class Engine:
             (_lib.KEEP_ALL_TB if keep_all_tb else 0)
             | (_lib.NO_WIGGLE if no_wiggle else 0)
             | (_lib.SPYRAL_ROWS if spyral_rows else 0)
+            | self._mesh_flag()
         )
         res = _lib.AttpcResult()
         code = self.lib.attpc_simulate_replay(

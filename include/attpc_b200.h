@@ -38,8 +38,12 @@ enum {
     ATTPC_SKIP_HOST_COPY = 1u << 3,/* leave results in device memory only (device-resident benchmarking) */
     ATTPC_ROWS_KEEP_ALL = 1u << 4, /* attpc_convert_to_spyral: every row, input order (no threshold, no sort) */
     ATTPC_SKIP_CLOUD_COPY = 1u << 5,/* with ATTPC_SPYRAL_ROWS: copy offsets and rows to the host, not the raw cloud */
-    ATTPC_COLUMNS = 1u << 6        /* host result as typed columns (col_* of AttpcResult, 19 B/row) instead of the
+    ATTPC_COLUMNS = 1u << 6,       /* host result as typed columns (col_* of AttpcResult, 19 B/row) instead of the
                                       float64 cloud + int64 labels (32 B/row); same rows, same order */
+    ATTPC_EXACT_MESH = 1u << 7     /* validation: evaluate every mesh pixel with the reference's own expression
+                                      (detector/transporter.py:36-41, 240-246).  The default reads pdf * step^2 from
+                                      the constant 10x10 weight table and falls back to that expression only where
+                                      rounding could change the integer share; both give identical results */
 };
 
 /* Scalars of DetectorParams / ElectronicsParams / Config (detector/parameters.py:10-76,164-174). */

@@ -244,3 +244,24 @@ def test_typed_columns_hold_the_same_rows(dist):
     assert ev_cloud.dtype == np.float64 and ev_labels.dtype == np.int64
     assert np.array_equal(ev_cloud, plain.event(17)[0]) and np.array_equal(ev_labels, plain.event(17)[1])
     assert np.array_equal(cols.cloud, plain.cloud) and np.array_equal(cols.labels, plain.labels)
+
+
+@pytest.mark.parametrize("name, n_events", [("c16dd", 10000), ("c14dp", 3000), ("c12aa", 2000), ("sn132dp", 2000)])
+def test_mesh_weight_table_equals_reference_expression(name, n_events):
+    """The constant mesh-weight table + exactness guard (default) gives the same integer shares as evaluating
+    `pdf * step_x * step_y * electrons` (`transporter.py:36-41, 240-246`) for every pixel (ATTPC_EXACT_MESH)."""
+    import bench
+    from attpc_engine_b200.detector.engine import engine_for
+    from attpc_engine_b200.detector.simulator import _nuclei_for
+
+    config, momenta, vertices, zs, as_, indices = bench.build_workload(name, n_events)
+    eng = engine_for(config, _nuclei_for(zs, as_, indices, nuclear_map))
+    fast = eng.simulate_batch(momenta, vertices, zs, as_, indices, seed=5)
+    eng.exact_mesh = True
+    try:
+        exact = eng.simulate_batch(momenta, vertices, zs, as_, indices, seed=5)
+    finally:
+        eng.exact_mesh = False
+    assert fast.stats["n_deposits"] == exact.stats["n_deposits"] > 0
+    assert np.array_equal(fast.offsets, exact.offsets) and np.array_equal(fast.labels, exact.labels)
+    assert np.array_equal(fast.cloud, exact.cloud)
