@@ -902,9 +902,12 @@ __global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant_
 // ---------------------------------------------------------------------------------------- shared-memory accumulate
 constexpr int DEPOSIT_THREADS = 256;
 constexpr int DEPOSIT_WARPS = DEPOSIT_THREADS / 32;
-constexpr int SMEM_SLOTS = 11264;  // per-CTA table in shared memory: 10 B per slot = 110 KB, two CTAs per SM
-constexpr int SPILL_CHECK_EVERY = 4;  // iterations (of DEPOSIT_WARPS points) between two fill checks
-constexpr int SMEM_SPILL_AT = SMEM_SLOTS - 100 * DEPOSIT_WARPS * SPILL_CHECK_EVERY - 512;
+constexpr int POINTS_PER_WARP = 3;   // three active points per warp pass: 3 x 10 mesh rows on 30 lanes
+constexpr int POINTS_PER_ITER = DEPOSIT_WARPS * POINTS_PER_WARP;
+constexpr int QUEUE_SLOTS = 64;      // per-warp ring of finished (key, charge) runs waiting for a full 32-lane insert
+constexpr int SMEM_SLOTS = 10752;    // per-CTA table in shared memory: 10 B per slot = 105 KB, two CTAs per SM
+// fill check once per pass of the CTA: a pass adds at most 100 keys per point plus what the rings still hold
+constexpr int SMEM_SPILL_AT = SMEM_SLOTS - 100 * POINTS_PER_ITER - DEPOSIT_WARPS * QUEUE_SLOTS - 512;
 constexpr size_t DEPOSIT_SMEM_BYTES = (size_t)SMEM_SLOTS * (2 * sizeof(unsigned) + sizeof(uint16_t));
 constexpr unsigned SMEM_KEY_MASK = 0x0FFFFFFFu;  // low 28 bits: ((tb << 15) | pad) + 1; top 4 bits: track rank
 
@@ -967,14 +970,22 @@ __device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t,
 }
 
 // One CTA per work unit (a slice of one event's points).  Tracks are processed in rank order (label = last track
-// to touch a key, detector/transporter.py:166-169, 247-249), one warp per active point, lanes over the 10x10 mesh,
-// accumulating into a shared-memory open-addressing table.  At the end the table is compacted into the event's
-// dense entry list (events of one unit) or merged into the event's global table (events split over several units,
-// and units dense enough to overflow the shared table).
+// to touch a key, detector/transporter.py:166-169, 247-249).
+//
+// A warp takes three active points per pass; lane (s, i) owns row i (one x of the 10x10 mesh) of point s and walks
+// the ten y of that row in the reference's pixel order.  Neighbouring pixels of a row usually fall on the same pad, so
+// the lane sums the integer shares of such a run in registers (integer adds commute and every share is truncated
+// on its own first, exactly as transporter.py:240-248 does) and only a finished run (key, charge) is pushed into the
+// warp's ring in shared memory.  Whenever the ring holds 32 runs, all 32 lanes insert one each into the CTA's
+// open-addressing table: the insert code (probe loop, two atomics) runs once per 32 runs instead of once per 32
+// pixels.  At the end the table is compacted into the event's dense entry list (events of one unit) or merged into
+// the event's global table (events split over several units, and units dense enough to overflow the shared table).
 __global__ void __launch_bounds__(DEPOSIT_THREADS, 2)
 deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, Counters* ctr) {
     extern __shared__ unsigned s_raw[];
     __shared__ unsigned s_nkeys, s_out, s_spilled;
+    __shared__ unsigned s_qkey[DEPOSIT_WARPS][QUEUE_SLOTS], s_qlo[DEPOSIT_WARPS][QUEUE_SLOTS],
+        s_qhi[DEPOSIT_WARPS][QUEUE_SLOTS];
     if ((int)blockIdx.x >= pb.n_units[gv.group]) return;
     const int64_t ubase = (int64_t)gv.group * pb.max_units;
     const int unit = pb.unit_order[ubase + blockIdx.x];
@@ -997,20 +1008,33 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
         s_spilled = 0;
     }
     __syncthreads();
-    unsigned long long n_dep = 0;
-    unsigned n_probe = 0;
-    // pixel (i, j) of this lane in each of the four rounds (x-major like the reference's meshgrid)
-    int pi[4], pj[4];
+    unsigned n_dep = 0, n_probe = 0;
+    const int sub = lane / MESH_N;                                  // point of the warp's triple; 3 = idle lanes 30, 31
+    const int row = lane - sub * MESH_N;                            // mesh row (x index) of this lane
+    const int sub_lane0 = min(sub, POINTS_PER_WARP - 1) * MESH_N;   // first lane of this lane's point
+    double wrow[MESH_N];  // constant mesh weights of this lane's row
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int pix = lane + 32 * k;
-        pi[k] = pix / MESH_N;
-        pj[k] = pix - pi[k] * MESH_N;
-    }
-    double wk[4];  // constant mesh weight of this lane's pixel in each round
-#pragma unroll
-    for (int k = 0; k < 4; ++k) wk[k] = P.mesh_w[min(lane + 32 * k, MESH_N * MESH_N - 1)];
+    for (int j = 0; j < MESH_N; ++j) wrow[j] = P.mesh_w[row * MESH_N + j];
     const bool exact_mesh = gv.exact_mesh != 0;
+    unsigned* qkey = s_qkey[warp];
+    unsigned* qlo = s_qlo[warp];
+    unsigned* qhi = s_qhi[warp];
+    unsigned q_head = 0, q_tail = 0;  // warp-uniform ring positions
+    const unsigned lanes_below = lanemask_lt();
+
+    auto drain = [&](unsigned n) {  // whole warp: insert ring entries [q_head, q_head + n), n <= 32
+        __syncwarp();
+        if ((unsigned)lane < n) {
+            const unsigned at = (q_head + (unsigned)lane) & (QUEUE_SLOTS - 1);
+            const unsigned kw = qkey[at];
+            const unsigned long long q = ((unsigned long long)qhi[at] << 32) | qlo[at];
+            const unsigned slot = smem_find(t, kw & SMEM_KEY_MASK, kw >> 28, &s_nkeys, n_probe);
+            smem_charge(t, slot, q, &ctr->overflow_charge);
+            t.word[slot] = kw;  // key + rank: the same value from every writer of this rank phase
+        }
+        __syncwarp();
+        q_head += n;
+    };
 
     auto flush_to_global = [&]() {  // all threads
         if (!shared_event && !s_spilled) {
@@ -1038,85 +1062,99 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
     const int64_t li0 = (int64_t)slot_event * pb.ranks;
     const int64_t run0 = pb.start[li0];
     int rank_begin = 0;  // position of the current rank's list inside the event's run
-    int iter = 0;
     for (int r = 0; r < pb.ranks; ++r) {
         const int rank_len = (int)pb.cnt[li0 + r];
         const int lo = max(rank_begin, u_first), hi = min(rank_begin + rank_len, u_first + u_count);
         rank_begin += rank_len;
         if (lo >= hi) continue;
-        for (int p0 = lo; p0 < hi; p0 += DEPOSIT_WARPS) {
-            const int pp = p0 + warp;
-            if (pp < hi) {
-                const int64_t p = base + run0 + pp;
-                const int meta = pb.meta[p];
+        for (int p0 = lo; p0 < hi; p0 += POINTS_PER_ITER) {
+            const int w0 = p0 + warp * POINTS_PER_WARP;
+            if (w0 < hi) {  // warp-uniform
+                const int pp = w0 + sub;
+                const bool have = sub < POINTS_PER_WARP && pp < hi;
+                const int64_t p = base + run0 + (have ? pp : w0);
+                const int meta = have ? pb.meta[p] : 0;
                 const int kind = (meta >> 30) & 3, tb = meta & ((1 << 30) - 1);
-                if (kind == 1) {  // detector/transporter.py:123-169
-                    if (lane == 0) {
-                        const double* g = pb.geom + p * GEOM_DOUBLES;
-                        const int pad = lookup_pad(P, g[0], g[1]);
-                        if (pad >= 0) {
-                            const unsigned key1 = smem_key((unsigned)tb, (unsigned)pad);
-                            const unsigned slot = smem_find(t, key1, (unsigned)r, &s_nkeys, n_probe);
-                            smem_charge(t, slot, (unsigned long long)pb.sq[p], &ctr->overflow_charge);
-                            t.word[slot] = key1 | ((unsigned)r << 28);
-                            n_dep += 1;
+                const double* g = pb.geom + p * GEOM_DOUBLES;
+                const unsigned keybase = (((unsigned)tb << 15) + 1u) | ((unsigned)r << 28);  // + pad = slot word
+                int cur = -1;         // pad of the run being summed
+                long long acc = 0;    // its charge so far
+                int pad[MESH_N];
+#pragma unroll
+                for (int j = 0; j < MESH_N; ++j) pad[j] = -1;
+                double qd = 0.0, guard = 2.0;
+                if (__any_sync(FULL, kind == 2)) {
+                    // detector/transporter.py:217-226 (numba linspace) and :102-120 per coordinate: the lane forms
+                    // x_row for itself and y_row for the other lanes of its point
+                    int ix = -1, iy_mine = -1;
+                    if (kind == 2) {
+                        const double2* gp = reinterpret_cast<const double2*>(g);
+                        const double2 g23 = gp[1], g45 = gp[2], g67 = gp[3], g89 = gp[4];
+                        qd = g[10];
+                        if (!exact_mesh) guard = g89.y;
+                        const double px = (row == MESH_N - 1) ? g23.y : __dadd_rn(g23.x, __dmul_rn((double)row, g45.x));
+                        const double py = (row == MESH_N - 1) ? g67.x : __dadd_rn(g45.y, __dmul_rn((double)row, g67.y));
+                        const double fx = floor(__dmul_rn(px, 1000.0)), fy = floor(__dmul_rn(py, 1000.0));
+                        if (fx < P.grid_high && fx >= P.grid_low) {
+                            ix = (int)fx - P.lut_origin;
+                            if ((unsigned)ix >= (unsigned)P.lut_n) ix = -1;
+                        }
+                        if (fy < P.grid_high && fy >= P.grid_low) {
+                            iy_mine = (int)fy - P.lut_origin;
+                            if ((unsigned)iy_mine >= (unsigned)P.lut_n) iy_mine = -1;
                         }
                     }
-                } else if (kind == 2) {
-                    const double* g = pb.geom + p * GEOM_DOUBLES;
-                    const double2* gp = reinterpret_cast<const double2*>(g);
-                    const double2 g23 = gp[1], g45 = gp[2], g67 = gp[3], g89 = gp[4];
-                    const double qd = g[10];
-                    // per-axis values, once per point: lanes 0-9 own x_i, lanes 10-19 own y_j
-                    const bool is_y = lane >= MESH_N;
-                    const int a = is_y ? lane - MESH_N : lane;
-                    const double lo_a = is_y ? g45.y : g23.x, hi_a = is_y ? g67.x : g23.y, d_a = is_y ? g67.y : g45.x;
-                    const double pa = (a == MESH_N - 1) ? hi_a : __dadd_rn(lo_a, __dmul_rn((double)a, d_a));
-                    // detector/transporter.py:102-120 on one coordinate: floor(mm), range test, LUT row / column
-                    const double f = floor(__dmul_rn(pa, 1000.0));
-                    int idx = -1;
-                    if (f < P.grid_high && f >= P.grid_low) {
-                        idx = (int)f - P.lut_origin;
-                        if ((unsigned)idx >= (unsigned)P.lut_n) idx = -1;
-                    }
-                    int pad[4];
+                    const int16_t* lut_row = P.lut + (int64_t)max(ix, 0) * P.lut_n;
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // all pad lookups first: independent loads in flight
-                        const int ix = __shfl_sync(FULL, idx, pi[k]), iy = __shfl_sync(FULL, idx, MESH_N + pj[k]);
-                        const bool ok = (lane + 32 * k < MESH_N * MESH_N) && ix >= 0 && iy >= 0;
-                        pad[k] = ok ? (int)__ldg(P.lut + (int64_t)ix * P.lut_n + iy) : -1;
+                    for (int j = 0; j < MESH_N; ++j) {  // all pad lookups first: independent loads in flight
+                        const int iy = __shfl_sync(FULL, iy_mine, sub_lane0 + j);
+                        if (ix >= 0 && iy >= 0) pad[j] = (int)__ldg(lut_row + iy);
                     }
-                    // detector/transporter.py:240-246: int(pdf * step^2 * electrons).  pdf * step^2 is the constant
-                    // mesh weight up to rounding (see make_geom); the reference's own expression is evaluated only for
-                    // a product so close to an integer that the rounding could change the truncation.
-                    long long share[4];
-                    const double guard = exact_mesh ? 2.0 : g89.y;
+                } else if (kind == 1 && row == 0) {  // detector/transporter.py:123-169: all electrons on one pad
+                    cur = lookup_pad(P, g[0], g[1]);
+                    acc = pb.sq[p];
+                    n_dep += cur >= 0;
+                }
+                // j == MESH_N is the sentinel that pushes the last run of the row
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const double v = __dmul_rn(wk[k], qd);
-                        share[k] = (long long)v;
+                for (int j = 0; j <= MESH_N; ++j) {
+                    const int pj = j < MESH_N ? pad[j] : -1;
+                    long long share = 0;
+                    if (j < MESH_N) {
+                        // detector/transporter.py:240-246: int(pdf * step^2 * electrons).  pdf * step^2 is the
+                        // constant mesh weight up to rounding (see make_geom); the reference's own expression is
+                        // evaluated only where the rounding could change the truncation.
+                        const double v = __dmul_rn(wrow[j], qd);
+                        share = (long long)v;
                         const bool risky = !(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v));
-                        if (risky && pad[k] >= 0) share[k] = exact_share(g, pi[k], pj[k]);
+                        if (risky && pj >= 0) share = exact_share(g, row, j);
+                        n_dep += pj >= 0;
                     }
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const bool ok = pad[k] >= 0;
-                        const unsigned key1 = smem_key((unsigned)tb, (unsigned)max(pad[k], 0));
-                        unsigned slot = 0;
-                        if (ok) slot = smem_find(t, key1, (unsigned)r, &s_nkeys, n_probe);
-                        if (ok) {  // reconverged: one pass of atomics for all valid lanes
-                            smem_charge(t, slot, (unsigned long long)share[k], &ctr->overflow_charge);
-                            t.word[slot] = key1 | ((unsigned)r << 28);  // same value from every writer of this phase
-                            n_dep += 1;
+                    const bool change = pj != cur;
+                    const bool push = change && cur >= 0;
+                    const unsigned m = __ballot_sync(FULL, push);
+                    if (m) {  // warp-uniform
+                        if (push) {
+                            const unsigned at = (q_tail + __popc(m & lanes_below)) & (QUEUE_SLOTS - 1);
+                            qkey[at] = keybase + (unsigned)cur;
+                            qlo[at] = (unsigned)acc;
+                            qhi[at] = (unsigned)((unsigned long long)acc >> 32);
                         }
+                        q_tail += __popc(m);
+                        if (q_tail - q_head >= 32u) drain(32u);
                     }
+                    if (change) {
+                        cur = pj;
+                        acc = 0;
+                    }
+                    acc += share;
                 }
             }
-            if (++iter % SPILL_CHECK_EVERY == 0) {
-                if (__syncthreads_or(s_nkeys > (unsigned)SMEM_SPILL_AT)) flush_to_global();
-            }
+            if (__syncthreads_or(s_nkeys > (unsigned)SMEM_SPILL_AT)) flush_to_global();
         }
-        __syncthreads();  // rank phases do not overlap: plain stores of the label are race-free
+        // rank phases do not overlap: the rings are emptied, then plain stores of the label are race-free
+        while (q_tail != q_head) drain(min(32u, q_tail - q_head));
+        __syncthreads();
         if (s_nkeys > (unsigned)SMEM_SPILL_AT) flush_to_global();
     }
     if (shared_event || s_spilled) {
@@ -1142,13 +1180,13 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
         __syncthreads();
         if (threadIdx.x == 0) gv.n_entries[slot_event] = s_out;
     }
-    unsigned long long n_probe64 = n_probe;
+    unsigned long long n_dep64 = n_dep, n_probe64 = n_probe;
     for (int o = 16; o > 0; o >>= 1) {
-        n_dep += __shfl_xor_sync(FULL, n_dep, o);
+        n_dep64 += __shfl_xor_sync(FULL, n_dep64, o);
         n_probe64 += __shfl_xor_sync(FULL, n_probe64, o);
     }
-    if (lane == 0 && n_dep) {
-        atomicAdd(&ctr->deposits, n_dep);
+    if (lane == 0 && n_dep64) {
+        atomicAdd(&ctr->deposits, n_dep64);
         atomicAdd(&ctr->probes, n_probe64);
     }
 }
