@@ -121,8 +121,8 @@ struct AttpcSim {
     PinnedArray<unsigned long long> csr_host;
     PinnedArray<unsigned long long> chunk_totals;  // running CSR total after each chunk of groups (mapped)
     DevArray<double> geom;
-    DevArray<long long> sq;
-    DevArray<int32_t> meta, unit_event, unit_first, unit_count, unit_order, n_units;
+    DevArray<uint32_t> rec;
+    DevArray<int32_t> unit_event, unit_first, unit_count, unit_order, n_units;
     DevArray<unsigned> pstart, n_entries, mode;
     int32_t ranks = 1;
     int32_t max_units = 0;
@@ -219,8 +219,7 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
         CU(ls.counters_host.reserve(1));
     }
     CU(sim->geom.reserve(pts * GEOM_DOUBLES));
-    CU(sim->sq.reserve(pts));
-    CU(sim->meta.reserve(pts));
+    CU(sim->rec.reserve(pts * REC_WORDS));
     sim->max_units = (int32_t)(sim->group_events + sim->group_point_cap / UNIT_POINTS + 1);
     CU(sim->unit_event.reserve(n_groups * sim->max_units));
     CU(sim->unit_first.reserve(n_groups * sim->max_units));
@@ -266,8 +265,7 @@ PointBuf point_buf(AttpcSim* sim, int which) {
     pb.cnt = ls.pcnt.p;
     pb.start = sim->pstart.p;
     pb.geom = sim->geom.p;
-    pb.sq = sim->sq.p;
-    pb.meta = sim->meta.p;
+    pb.rec = sim->rec.p;
     pb.unit_event = sim->unit_event.p;
     pb.unit_first = sim->unit_first.p;
     pb.unit_count = sim->unit_count.p;
@@ -629,7 +627,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             if (now.overflow_points) {
                 sim->group_point_cap *= 2;
                 for (auto& s2 : sim->slot) s2.release_points();
-                sim->geom.release(); sim->sq.release(); sim->meta.release();
+                sim->geom.release(); sim->rec.release();
                 sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release();
                 sim->unit_order.release();
             }
@@ -776,7 +774,7 @@ void attpc_destroy(AttpcSim* sim) {
     sim->lut.release(); sim->pad_xy.release(); sim->pad_scale.release(); sim->response.release();
     sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release();
     sim->hash.release(); sim->sort_items.release();
-    sim->geom.release(); sim->sq.release(); sim->meta.release();
+    sim->geom.release(); sim->rec.release();
     sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release(); sim->unit_order.release();
     sim->n_units.release();
     sim->pstart.release(); sim->n_entries.release(); sim->mode.release();

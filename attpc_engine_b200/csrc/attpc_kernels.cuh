@@ -17,6 +17,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <type_traits>
 
 #include "philox.cuh"
 
@@ -78,9 +79,8 @@ struct PointBuf {
     unsigned* count;    // [n_groups] points appended per group
     unsigned* cnt;      // [launch events * ranks] points per (event, rank)
     unsigned* start;    // [launch events * ranks] first position of the list inside the group's ordered run
-    double* geom;       // ordered: GEOM_DOUBLES per point, the per-point constants of the drift mesh
-    long long* sq;      // ordered: electrons after gain
-    int32_t* meta;      // ordered: time bucket | kind << 30
+    double* geom;       // ordered: GEOM_DOUBLES per point, the per-point constants of the drift mesh (exact path)
+    uint32_t* rec;      // ordered: REC_WORDS per point, what the deposit kernel reads (see make_point)
     // work units of the deposit kernel (one CTA each): a slice of <= UNIT_POINTS points of one event
     int32_t* unit_event;   // [max_units] event index inside the group
     int32_t* unit_first;   // [max_units] first point of the slice inside the event's ordered run
@@ -838,16 +838,41 @@ __global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView
 // reference's own expression otherwise.
 constexpr double MESH_GUARD_U = 1.1102230246251565e-16;  // 2^-53
 
-__device__ __forceinline__ int make_geom(const SimParams& P, double cx, double cy, double time, long long q,
-                                         double* g) {
+// detector/transporter.py:102-120 on one coordinate: floor(mm), range test, row / column of the 1 mm pad table
+__device__ __forceinline__ int lut_index(const SimParams& P, double coord_m) {
+    const double f = floor(__dmul_rn(coord_m, 1000.0));
+    if (!(f < P.grid_high) || !(f >= P.grid_low)) return -1;  // also NaN
+    const int idx = (int)f - P.lut_origin;
+    return (unsigned)idx < (unsigned)P.lut_n ? idx : -1;
+}
+
+// Record of one ordered point as the deposit kernel reads it (64 B):
+//   word 0      time bucket | kind << 30   (kind 0: nothing, 1: single deposit, 2: 10x10 mesh)
+//   word 1      guard as float, rounded up
+//   words 2-3   electrons after gain as double
+//   words 4-8   int16 iy[10]: pad-table column of mesh column j (-1 = outside), kind 1: iy[0] of the point itself
+//   words 9-13  int16 ix[10]: pad-table row of mesh row i
+constexpr int REC_WORDS = 16;
+
+__device__ __forceinline__ void make_point(const SimParams& P, double cx, double cy, double time, long long q,
+                                           double* g, uint32_t* rec) {
     g[0] = cx;
     g[1] = cy;
     g[10] = (double)q;
+#pragma unroll
+    for (int k = 0; k < REC_WORDS; ++k) rec[k] = 0u;
+    rec[2] = (uint32_t)__double2loint(g[10]);
+    rec[3] = (uint32_t)__double2hiint(g[10]);
     // detector/transporter.py:301, evaluated left to right
     const double sigma = __dsqrt_rn(__ddiv_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, P.diffusion), P.dv), time), P.efield));
     const int tb = (int)time;  // detector/transporter.py:165, 238
-    if (tb < 0 || tb >= 8192 || !(sigma == sigma)) return 0;  // kind 0: never reached for 0 <= z <= length + mm_edge*dv (tb <= windows_edge)
-    if (sigma == 0.0) return tb | (1 << 30);                      // kind 1: single deposit, transporter.py:123-169
+    if (tb < 0 || tb >= 8192 || !(sigma == sigma)) return;  // kind 0: never reached for 0 <= z <= length + mm_edge*dv (tb <= windows_edge)
+    if (sigma == 0.0) {  // kind 1: single deposit, transporter.py:123-169
+        rec[0] = (uint32_t)tb | (1u << 30);
+        rec[4] = (uint32_t)(uint16_t)(int16_t)lut_index(P, cy);
+        rec[9] = (uint32_t)(uint16_t)(int16_t)lut_index(P, cx);
+        return;
+    }
     // detector/transporter.py:217-226 with numba's linspace (numba/np/arrayobj.py: linspace)
     const double three_sigma = __dmul_rn(3.0, sigma);
     g[2] = __dsub_rn(cx, three_sigma);
@@ -859,7 +884,16 @@ __device__ __forceinline__ int make_geom(const SimParams& P, double cx, double c
     g[8] = sigma;
     const double big = fmax(fabs(cx), fabs(cy)) + three_sigma;
     g[9] = 2.0 * (24.0 * big / sigma + 220.0) * MESH_GUARD_U;
-    return tb | (2 << 30);                                    // kind 2: 10x10 mesh
+    rec[0] = (uint32_t)tb | (2u << 30);
+    rec[1] = __float_as_uint(__double2float_ru(g[9]));
+#pragma unroll
+    for (int a = 0; a < MESH_N; ++a) {
+        const double px = (a == MESH_N - 1) ? g[3] : __dadd_rn(g[2], __dmul_rn((double)a, g[4]));
+        const double py = (a == MESH_N - 1) ? g[6] : __dadd_rn(g[5], __dmul_rn((double)a, g[7]));
+        const uint32_t ix = (uint32_t)(uint16_t)(int16_t)lut_index(P, px), iy = (uint32_t)(uint16_t)(int16_t)lut_index(P, py);
+        rec[4 + a / 2] |= iy << (16 * (a & 1));
+        rec[9 + a / 2] |= ix << (16 * (a & 1));
+    }
 }
 
 // The reference's own arithmetic for one mesh pixel (i, j): detector/transporter.py:36-41, 217-226, 240-246.
@@ -888,14 +922,16 @@ __global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant_
         const int64_t i = base + p;
         const int64_t d = base + pb.start[(int64_t)pb.ev[i] * pb.ranks + pb.rank[i]] + pb.j[i];
         double g[GEOM_DOUBLES];
+        uint32_t rec[REC_WORDS];
 #pragma unroll
         for (int k = 0; k < GEOM_DOUBLES; ++k) g[k] = 0.0;
-        const long long q = pb.q[i];
-        pb.meta[d] = make_geom(P, pb.x[i], pb.y[i], pb.t[i], q, g);
-        pb.sq[d] = q;
+        make_point(P, pb.x[i], pb.y[i], pb.t[i], pb.q[i], g, rec);
         double2* out = reinterpret_cast<double2*>(pb.geom + d * GEOM_DOUBLES);
 #pragma unroll
         for (int k = 0; k < GEOM_DOUBLES / 2; ++k) out[k] = make_double2(g[2 * k], g[2 * k + 1]);
+        uint4* out_rec = reinterpret_cast<uint4*>(pb.rec + d * REC_WORDS);
+#pragma unroll
+        for (int k = 0; k < REC_WORDS / 4; ++k) out_rec[k] = make_uint4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
     }
 }
 
@@ -928,26 +964,27 @@ __device__ __forceinline__ unsigned smem_home(unsigned key1) {
     return __umulhi(key1 * 2654435761u, (unsigned)SMEM_SLOTS);  // multiply-shift range reduction, no division
 }
 
-// Find the slot of `key1`, claiming an empty one if it is new.  The table is flushed long before it can fill.
-__device__ __forceinline__ unsigned smem_find(const SmemTable& t, unsigned key1, unsigned rank, unsigned* n_keys,
+// Find the slot of `key1`, claiming an empty one if it is new (counted in the lane's `n_new`; the warp publishes the
+// sum before every fill check).  The table is flushed long before it can fill.
+__device__ __forceinline__ unsigned smem_find(const SmemTable& t, unsigned key1, unsigned rank, unsigned& n_new,
                                               unsigned& probes) {
     unsigned slot = smem_home(key1);
 #pragma unroll 1
     for (unsigned probe = 0; probe < (unsigned)SMEM_SLOTS; ++probe) {
         unsigned w = *(volatile unsigned*)&t.word[slot];
+        if ((w & SMEM_KEY_MASK) == key1) break;  // the common case: the key is there, at its home slot
         if (w == 0u) {
             w = atomicCAS(&t.word[slot], 0u, key1 | (rank << 28));
             if (w == 0u) {
-                w = key1;
-                atomicAdd(n_keys, 1u);
+                n_new += 1u;
+                break;
             }
+            if ((w & SMEM_KEY_MASK) == key1) break;
         }
-        if ((w & SMEM_KEY_MASK) == key1) {
-            probes += probe + 1u;
-            return slot;
-        }
+        probes += 1u;
         slot = slot + 1u == (unsigned)SMEM_SLOTS ? 0u : slot + 1u;
     }
+    probes += 1u;
     return slot;
 }
 
@@ -982,7 +1019,7 @@ __device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t,
 // the event's global table (events split over several units, and units dense enough to overflow the shared table).
 __global__ void __launch_bounds__(DEPOSIT_THREADS, 2)
 deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, Counters* ctr) {
-    extern __shared__ unsigned s_raw[];
+    extern __shared__ __align__(16) unsigned s_raw[];
     __shared__ unsigned s_nkeys, s_out, s_spilled;
     __shared__ unsigned s_qkey[DEPOSIT_WARPS][QUEUE_SLOTS], s_qlo[DEPOSIT_WARPS][QUEUE_SLOTS],
         s_qhi[DEPOSIT_WARPS][QUEUE_SLOTS];
@@ -1001,17 +1038,21 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
     HashEntry* region = gv.tables + (int64_t)e * gv.hash_cap;
     const unsigned gmask = (unsigned)gv.hash_cap - 1u;
     const int64_t base = (int64_t)gv.group * pb.group_cap;
-    for (int i = threadIdx.x; i < 2 * SMEM_SLOTS + SMEM_SLOTS / 2; i += blockDim.x) s_raw[i] = 0u;
+    constexpr int TABLE_VEC4 = (2 * SMEM_SLOTS + SMEM_SLOTS / 2) / 4;
+    auto clear_table = [&]() {
+        uint4* v = reinterpret_cast<uint4*>(s_raw);
+        for (int i = threadIdx.x; i < TABLE_VEC4; i += blockDim.x) v[i] = make_uint4(0u, 0u, 0u, 0u);
+    };
+    clear_table();
     if (threadIdx.x == 0) {
         s_nkeys = 0;
         s_out = 0;
         s_spilled = 0;
     }
     __syncthreads();
-    unsigned n_dep = 0, n_probe = 0;
+    unsigned n_dep = 0, n_probe = 0, n_new = 0;
     const int sub = lane / MESH_N;                                  // point of the warp's triple; 3 = idle lanes 30, 31
     const int row = lane - sub * MESH_N;                            // mesh row (x index) of this lane
-    const int sub_lane0 = min(sub, POINTS_PER_WARP - 1) * MESH_N;   // first lane of this lane's point
     double wrow[MESH_N];  // constant mesh weights of this lane's row
 #pragma unroll
     for (int j = 0; j < MESH_N; ++j) wrow[j] = P.mesh_w[row * MESH_N + j];
@@ -1028,12 +1069,17 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
             const unsigned at = (q_head + (unsigned)lane) & (QUEUE_SLOTS - 1);
             const unsigned kw = qkey[at];
             const unsigned long long q = ((unsigned long long)qhi[at] << 32) | qlo[at];
-            const unsigned slot = smem_find(t, kw & SMEM_KEY_MASK, kw >> 28, &s_nkeys, n_probe);
+            const unsigned slot = smem_find(t, kw & SMEM_KEY_MASK, kw >> 28, n_new, n_probe);
             smem_charge(t, slot, q, &ctr->overflow_charge);
             t.word[slot] = kw;  // key + rank: the same value from every writer of this rank phase
         }
         __syncwarp();
         q_head += n;
+    };
+    auto publish_new_keys = [&]() {  // whole warp, before a barrier that precedes a read of s_nkeys
+        const unsigned total = __reduce_add_sync(FULL, n_new);
+        if (lane == 0 && total) atomicAdd(&s_nkeys, total);
+        n_new = 0;
     };
 
     auto flush_to_global = [&]() {  // all threads
@@ -1049,7 +1095,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < 2 * SMEM_SLOTS + SMEM_SLOTS / 2; i += blockDim.x) s_raw[i] = 0u;
+        clear_table();
         if (threadIdx.x == 0) {
             s_nkeys = 0;
             s_spilled = 1;
@@ -1073,87 +1119,90 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
                 const int pp = w0 + sub;
                 const bool have = sub < POINTS_PER_WARP && pp < hi;
                 const int64_t p = base + run0 + (have ? pp : w0);
-                const int meta = have ? pb.meta[p] : 0;
-                const int kind = (meta >> 30) & 3, tb = meta & ((1 << 30) - 1);
-                const double* g = pb.geom + p * GEOM_DOUBLES;
+                const uint4* rp = reinterpret_cast<const uint4*>(pb.rec + p * REC_WORDS);
+                uint4 head = __ldg(rp);
+                if (!have) head.x = 0u;
+                const int kind = (int)(head.x >> 30), tb = (int)(head.x & 0x3FFFFFFFu);
                 const unsigned keybase = (((unsigned)tb << 15) + 1u) | ((unsigned)r << 28);  // + pad = slot word
+                const double qd = kind == 2 ? __hiloint2double((int)head.w, (int)head.z) : 0.0;
+                const double guard = exact_mesh ? 2.0 : (double)__uint_as_float(head.y);
                 int cur = -1;         // pad of the run being summed
                 long long acc = 0;    // its charge so far
                 int pad[MESH_N];
 #pragma unroll
                 for (int j = 0; j < MESH_N; ++j) pad[j] = -1;
-                double qd = 0.0, guard = 2.0;
-                if (__any_sync(FULL, kind == 2)) {
-                    // detector/transporter.py:217-226 (numba linspace) and :102-120 per coordinate: the lane forms
-                    // x_row for itself and y_row for the other lanes of its point
-                    int ix = -1, iy_mine = -1;
-                    if (kind == 2) {
-                        const double2* gp = reinterpret_cast<const double2*>(g);
-                        const double2 g23 = gp[1], g45 = gp[2], g67 = gp[3], g89 = gp[4];
-                        qd = g[10];
-                        if (!exact_mesh) guard = g89.y;
-                        const double px = (row == MESH_N - 1) ? g23.y : __dadd_rn(g23.x, __dmul_rn((double)row, g45.x));
-                        const double py = (row == MESH_N - 1) ? g67.x : __dadd_rn(g45.y, __dmul_rn((double)row, g67.y));
-                        const double fx = floor(__dmul_rn(px, 1000.0)), fy = floor(__dmul_rn(py, 1000.0));
-                        if (fx < P.grid_high && fx >= P.grid_low) {
-                            ix = (int)fx - P.lut_origin;
-                            if ((unsigned)ix >= (unsigned)P.lut_n) ix = -1;
-                        }
-                        if (fy < P.grid_high && fy >= P.grid_low) {
-                            iy_mine = (int)fy - P.lut_origin;
-                            if ((unsigned)iy_mine >= (unsigned)P.lut_n) iy_mine = -1;
-                        }
-                    }
+                if (kind != 0) {
+                    // pad-table row of this lane's mesh row, columns of the ten mesh columns (make_point)
+                    const uint4 cols = __ldg(rp + 1);
+                    const uint2 tail = __ldg(reinterpret_cast<const uint2*>(rp + 2));  // iy[8], iy[9] | ix[0], ix[1]
+                    const int ix = (int)__ldg(reinterpret_cast<const int16_t*>(rp) + 18 + row);
+                    const unsigned cw[5] = {cols.x, cols.y, cols.z, cols.w, tail.x};
                     const int16_t* lut_row = P.lut + (int64_t)max(ix, 0) * P.lut_n;
+                    if (kind == 2) {
 #pragma unroll
-                    for (int j = 0; j < MESH_N; ++j) {  // all pad lookups first: independent loads in flight
-                        const int iy = __shfl_sync(FULL, iy_mine, sub_lane0 + j);
-                        if (ix >= 0 && iy >= 0) pad[j] = (int)__ldg(lut_row + iy);
-                    }
-                } else if (kind == 1 && row == 0) {  // detector/transporter.py:123-169: all electrons on one pad
-                    cur = lookup_pad(P, g[0], g[1]);
-                    acc = pb.sq[p];
-                    n_dep += cur >= 0;
-                }
-                // j == MESH_N is the sentinel that pushes the last run of the row
-#pragma unroll
-                for (int j = 0; j <= MESH_N; ++j) {
-                    const int pj = j < MESH_N ? pad[j] : -1;
-                    long long share = 0;
-                    if (j < MESH_N) {
-                        // detector/transporter.py:240-246: int(pdf * step^2 * electrons).  pdf * step^2 is the
-                        // constant mesh weight up to rounding (see make_geom); the reference's own expression is
-                        // evaluated only where the rounding could change the truncation.
-                        const double v = __dmul_rn(wrow[j], qd);
-                        share = (long long)v;
-                        const bool risky = !(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v));
-                        if (risky && pj >= 0) share = exact_share(g, row, j);
-                        n_dep += pj >= 0;
-                    }
-                    const bool change = pj != cur;
-                    const bool push = change && cur >= 0;
-                    const unsigned m = __ballot_sync(FULL, push);
-                    if (m) {  // warp-uniform
-                        if (push) {
-                            const unsigned at = (q_tail + __popc(m & lanes_below)) & (QUEUE_SLOTS - 1);
-                            qkey[at] = keybase + (unsigned)cur;
-                            qlo[at] = (unsigned)acc;
-                            qhi[at] = (unsigned)((unsigned long long)acc >> 32);
+                        for (int j = 0; j < MESH_N; ++j) {  // all pad lookups first: independent loads in flight
+                            const int iy = (j & 1) ? (int)cw[j / 2] >> 16 : (int)(int16_t)(cw[j / 2] & 0xFFFFu);
+                            if (ix >= 0 && iy >= 0) pad[j] = (int)__ldg(lut_row + iy);
                         }
-                        q_tail += __popc(m);
-                        if (q_tail - q_head >= 32u) drain(32u);
+                    } else if (row == 0) {  // detector/transporter.py:123-169: all electrons on one pad
+                        const int iy = (int)(int16_t)(cw[0] & 0xFFFFu);
+                        if (ix >= 0 && iy >= 0) cur = (int)__ldg(lut_row + iy);
+                        acc = (long long)__hiloint2double((int)head.w, (int)head.z);
+                        n_dep += cur >= 0;
                     }
-                    if (change) {
-                        cur = pj;
-                        acc = 0;
-                    }
-                    acc += share;
                 }
+                // detector/transporter.py:240-246: int(pdf * step^2 * electrons).  pdf * step^2 is the constant mesh
+                // weight up to rounding (see make_point); the reference's own expression is evaluated only where the
+                // rounding could change the truncation -- rare, so the warp then takes a second copy of the loop.
+                unsigned risky = 0u;
+#pragma unroll
+                for (int j = 0; j < MESH_N; ++j) {
+                    const double v = __dmul_rn(wrow[j], qd);
+                    if (!(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v)) && pad[j] >= 0) risky |= 1u << j;
+                }
+                const double* g = pb.geom + p * GEOM_DOUBLES;
+                auto walk_row = [&](auto careful) {
+                    // j == MESH_N is the sentinel that pushes the last run of the row
+#pragma unroll
+                    for (int j = 0; j <= MESH_N; ++j) {
+                        const int pj = j < MESH_N ? pad[j] : -1;
+                        long long share = 0;  // (of a pixel without pad: added to a run that is never pushed)
+                        if (j < MESH_N) {
+                            share = (long long)__dmul_rn(wrow[j], qd);
+                            if (decltype(careful)::value) {
+                                if ((risky >> j) & 1u) share = exact_share(g, row, j);
+                            }
+                            n_dep += pj >= 0;
+                        }
+                        const bool change = pj != cur;
+                        const bool push = change && cur >= 0;
+                        const unsigned m = __ballot_sync(FULL, push);
+                        if (m) {  // warp-uniform
+                            if (push) {
+                                const unsigned at = (q_tail + __popc(m & lanes_below)) & (QUEUE_SLOTS - 1);
+                                qkey[at] = keybase + (unsigned)cur;
+                                qlo[at] = (unsigned)acc;
+                                qhi[at] = (unsigned)((unsigned long long)acc >> 32);
+                            }
+                            q_tail += __popc(m);
+                            if (q_tail - q_head >= 32u) drain(32u);
+                        }
+                        if (change) {
+                            cur = pj;
+                            acc = 0;
+                        }
+                        acc += share;
+                    }
+                };
+                if (__any_sync(FULL, risky != 0u)) walk_row(std::true_type{});
+                else walk_row(std::false_type{});
             }
+            publish_new_keys();
             if (__syncthreads_or(s_nkeys > (unsigned)SMEM_SPILL_AT)) flush_to_global();
         }
         // rank phases do not overlap: the rings are emptied, then plain stores of the label are race-free
         while (q_tail != q_head) drain(min(32u, q_tail - q_head));
+        publish_new_keys();
         __syncthreads();
         if (s_nkeys > (unsigned)SMEM_SPILL_AT) flush_to_global();
     }
@@ -1169,12 +1218,16 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
             gv.n_entries[slot_event] = 0u;
         }
     } else {
-        for (int i = threadIdx.x; i < SMEM_SLOTS; i += blockDim.x) {
-            const unsigned w = t.word[i];
-            if (w) {
-                const unsigned kc = (w & SMEM_KEY_MASK) - 1u;
-                const unsigned pos = atomicAdd(&s_out, 1u);
-                region[pos] = HashEntry{kc + 1u, w >> 28, smem_charge_of(t, i)};
+        const uint4* words = reinterpret_cast<const uint4*>(t.word);
+        for (int i = threadIdx.x; i < SMEM_SLOTS / 4; i += blockDim.x) {
+            const uint4 w4 = words[i];
+            const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
+            const unsigned cnt = (w4.x != 0u) + (w4.y != 0u) + (w4.z != 0u) + (w4.w != 0u);
+            if (cnt) {
+                unsigned pos = atomicAdd(&s_out, cnt);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (w[k]) region[pos++] = HashEntry{w[k] & SMEM_KEY_MASK, w[k] >> 28, smem_charge_of(t, 4 * i + k)};
             }
         }
         __syncthreads();
