@@ -12,7 +12,7 @@ from pathlib import Path
 
 LIB_NAME = "libattpc_b200.so"
 LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # flags (include/attpc_b200.h)
 KEEP_ALL_TB = 1 << 0
@@ -111,6 +111,9 @@ class AttpcResult(C.Structure):
         ("col_tb", C.POINTER(C.c_double)),
         ("col_electrons", C.POINTER(C.c_int64)),
         ("col_label", C.POINTER(C.c_int8)),
+        ("n_rk_steps", C.c_int64),
+        ("n_rk_rejects", C.c_int64),
+        ("max_track_passes", C.c_int64),
     ]
 
 

@@ -280,18 +280,25 @@ PointBuf point_buf(AttpcSim* sim, int which) {
 
 template <bool RECORD>
 int launch_tracks(AttpcSim* sim, const TrackBatch& tb, int64_t n_tracks, int which, cudaStream_t stream) {
-    const int threads = TRACK_THREADS;
-    int64_t blocks64 = (n_tracks + threads - 1) / threads;
-    const int max_blocks = sim->sm_count * 4;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(blocks64, max_blocks));
+    // The kernel is latency bound (FP64 dependency chains): spread the tracks over all SMs first, then add warps per
+    // SM up to the one-CTA-per-SM limit the register file allows.  Lanes pull further tracks from a global cursor.
+    const int64_t lanes_per_sm = (n_tracks + sim->sm_count - 1) / sim->sm_count;
+    const int warps = (int)std::max<int64_t>(1, std::min<int64_t>(TRACK_THREADS / 32, (lanes_per_sm + 31) / 32));
+    const int threads = warps * 32;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_tracks + threads - 1) / threads, sim->sm_count));
     PointBuf pb = point_buf(sim, which);
     Counters* ctr = sim->slot[which].counters.p;
+    const size_t slot_bytes = (size_t)warps * TRACK_SLOT_BYTES_PER_WARP;
     if (sim->tables_in_smem) {
         auto kern = track_kernel<true, RECORD>;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim->table_smem_bytes));
-        kern<<<blocks, threads, sim->table_smem_bytes, stream>>>(sim->P, tb, pb, ctr);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((TRACK_THREADS / 32) * TRACK_SLOT_BYTES_PER_WARP + sim->table_smem_bytes)));
+        kern<<<blocks, threads, slot_bytes + sim->table_smem_bytes, stream>>>(sim->P, tb, pb, ctr);
     } else {
-        track_kernel<false, RECORD><<<blocks, threads, 0, stream>>>(sim->P, tb, pb, ctr);
+        auto kern = track_kernel<false, RECORD>;
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((TRACK_THREADS / 32) * TRACK_SLOT_BYTES_PER_WARP)));
+        kern<<<blocks, threads, slot_bytes, stream>>>(sim->P, tb, pb, ctr);
     }
     sim->launches += 1;
     CU(cudaGetLastError());
@@ -669,6 +676,9 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         totals.keys += now.keys;
         totals.probes += now.probes;
         totals.flushes += now.flushes;
+        totals.rk_steps += now.rk_steps;
+        totals.rk_rejects += now.rk_rejects;
+        totals.max_track_passes = std::max(totals.max_track_passes, now.max_track_passes);
         const unsigned long long csr_after = sim->csr_host.p[0];
         if (copy_host && (copied < csr_after || copied_events < nb)) {  // whatever the chunk copies did not cover
             CU(cudaStreamWaitEvent(C, groups_done, 0));
@@ -690,6 +700,9 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     res->n_keys = (int64_t)totals.keys;
     res->n_hash_probes = (int64_t)totals.probes;
     res->n_table_flushes = (int64_t)totals.flushes;
+    res->n_rk_steps = (int64_t)totals.rk_steps;
+    res->n_rk_rejects = (int64_t)totals.rk_rejects;
+    res->max_track_passes = (int64_t)totals.max_track_passes;
     res->n_retries = retries;
     if (copy_host) {
         if (n_events == 0) {
@@ -856,8 +869,8 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
     P.lut_origin = cfg->lut_origin_mm;
     P.lut_n = cfg->lut_n;
     P.adc_threshold = cfg->adc_threshold;
-    P.rtol = cfg->ode_rtol > 0 ? cfg->ode_rtol : 1e-8;
-    P.atol = cfg->ode_atol > 0 ? cfg->ode_atol : 1e-12;
+    P.rtol = cfg->ode_rtol > 0 ? cfg->ode_rtol : 1e-6;
+    P.atol = cfg->ode_atol > 0 ? cfg->ode_atol : 1e-10;
     P.freeze_ke = cfg->freeze_ke_mev;
     P.lm = n_species ? species[0].lm : 0;
     P.e_min = n_species ? species[0].e_min : 0;
@@ -937,7 +950,7 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
         if (!scaled.empty())
             CUC(cudaMemcpy(sim->tables.p, scaled.data(), scaled.size() * sizeof(double), cudaMemcpyHostToDevice));
         sim->table_smem_bytes = scaled.size() * sizeof(double);
-        sim->tables_in_smem = sim->table_smem_bytes <= 160 * 1024;
+        sim->tables_in_smem = sim->table_smem_bytes + (TRACK_THREADS / 32) * TRACK_SLOT_BYTES_PER_WARP <= 227 * 1024;
     }
     {
         // constant mesh weights pdf * step^2 of detector/transporter.py:217-246 in exact arithmetic (sigma cancels):

@@ -98,6 +98,9 @@ struct Counters {
     unsigned long long track_cursor;
     unsigned long long traj_points, active_points, primary_electrons, deposits, keys, probes, flushes;
     int overflow_points, overflow_hash, overflow_out, replay_miss, overflow_charge, pad_;
+    // integrator probes: Dormand-Prince steps tried / rejected, and the most loop passes any one track needed (the
+    // serial critical path of a launch)
+    unsigned long long rk_steps, rk_rejects, max_track_passes;
 };
 
 // Publish a launch's counters and the running CSR totals into mapped host memory.  A copy-engine transfer would
@@ -170,18 +173,19 @@ struct TrackConst {
 // parallel motion approaches the drift speed monotonically.  The total variation left in KE is then at most
 // KE_perp + |KE_par - ke_eq|; if twice that cannot give one grid step the `budget` = n* W needed for
 // int(n + sqrt(F n) z) >= 1 with |z| <= NORMAL_ABS_MAX, every later row has zero electrons.
-__device__ __forceinline__ bool inert_forever(const TrackConst& c, const State& s, double ke, double budget) {
+__device__ __forceinline__ bool inert_forever(double mass, double qmE, double ke_eq, const State& s, double ke,
+                                              double budget) {
     if (!(budget > 0.0)) return false;
-    if (c.qmE == 0.0) return ke < budget;  // no field to re-accelerate the ion
-    if (!(s.uz * c.qmE > 0.0)) return false;
-    const double k_par = 0.5 * c.mass * s.uz * s.uz;
-    const double k_perp = 0.5 * c.mass * (s.ux * s.ux + s.uy * s.uy);
-    return 2.0 * (k_perp + fabs(k_par - c.ke_eq)) < budget;
+    if (qmE == 0.0) return ke < budget;  // no field to re-accelerate the ion
+    if (!(s.uz * qmE > 0.0)) return false;
+    const double k_par = 0.5 * mass * s.uz * s.uz;
+    const double k_perp = 0.5 * mass * (s.ux * s.ux + s.uy * s.uy);
+    return 2.0 * (k_perp + fabs(k_par - ke_eq)) < budget;
 }
 
-__device__ __forceinline__ double kinetic_energy(const TrackConst& c, double ux, double uy, double uz) {
+__device__ __forceinline__ double kinetic_energy(double mass, double ux, double uy, double uz) {
     const double g2 = ux * ux + uy * uy + uz * uz;
-    return c.mass * g2 / (sqrt(1.0 + g2) + 1.0);  // m (gamma - 1) without the cancellation
+    return mass * g2 / (sqrt(1.0 + g2) + 1.0);  // m (gamma - 1) without the cancellation
 }
 
 // detector/solver.py:52-76 with u = gamma*beta:  v = u c / gamma,  du/dt = (q/m (v x B + E) - a u_hat) / c
@@ -295,7 +299,6 @@ __device__ __forceinline__ State dense_eval(const State& y0, const Dense& d, dou
 }
 
 constexpr double MAX_STEP_CELLS = 64.0;  // a step never spans more than 64 grid cells (6.4 ns)
-constexpr int EMIT_CHUNK = 8;            // grid points a lane emits between two integrator steps of the warp
 
 // Standard step-size controller of an order-5 pair: factor = 0.9 err^(-1/5), limited to [0.2, 5].
 __device__ __forceinline__ double step_factor(double err) {
@@ -308,13 +311,13 @@ __device__ __forceinline__ double step_factor(double err) {
 __device__ __forceinline__ bool crossed_up(double g0, double g1) { return g0 <= 0.0 && g1 >= 0.0; }
 __device__ __forceinline__ bool crossed_down(double g0, double g1) { return g0 >= 0.0 && g1 <= 0.0; }
 
-// The radial bound is tested on rho^2 - R^2, which has the sign of rho - R; all four tests are evaluated (bitwise or)
-// so that the warp does not diverge on them.
-__device__ __forceinline__ bool terminal_event(const TrackConst& c, const State& a, const State& b, double ke_a,
-                                               double ke_b) {
-    const double ra = a.x * a.x + a.y * a.y - RHO_MAX * RHO_MAX, rb = b.x * b.x + b.y * b.y - RHO_MAX * RHO_MAX;
-    return crossed_down(ke_a - KE_LIMIT, ke_b - KE_LIMIT) | crossed_up(a.z - Z_HI, b.z - Z_HI) |
-           crossed_down(a.z - Z_LO, b.z - Z_LO) | crossed_up(ra, rb);
+// Terminal events between two consecutive grid points a -> b.  The radial bound is tested on rho^2 - R^2, which has
+// the sign of rho - R; all four tests are evaluated (bitwise or) so that the warp does not diverge on them.
+__device__ __forceinline__ bool terminal_event(double ax, double ay, double az, double ke_a, double bx, double by,
+                                               double bz, double ke_b) {
+    const double ra = ax * ax + ay * ay - RHO_MAX * RHO_MAX, rb = bx * bx + by * by - RHO_MAX * RHO_MAX;
+    return crossed_down(ke_a - KE_LIMIT, ke_b - KE_LIMIT) | crossed_up(az - Z_HI, bz - Z_HI) |
+           crossed_down(az - Z_LO, bz - Z_LO) | crossed_up(ra, rb);
 }
 
 __device__ __forceinline__ unsigned lanemask_lt() {
@@ -323,7 +326,7 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
-// Warp-aggregated append of one active point per emitting lane into the lane's event-group region.
+// Append of one active point (replay kernel: one thread per trajectory row).
 __device__ __forceinline__ void append_point(const PointBuf& pb, Counters* ctr, bool emit, int ev, int rank,
                                              double x, double y, double t, long long q) {
     if (!emit) return;
@@ -343,59 +346,6 @@ __device__ __forceinline__ void append_point(const PointBuf& pb, Counters* ctr, 
     pb.j[i] = atomicAdd(&pb.cnt[(int64_t)ev * pb.ranks + rank], 1u);
 }
 
-// Points staged by one lane of the track kernel between two flushes (shared memory, EMIT_CHUNK per lane).
-struct StagedPoint {
-    double x, y, t;
-    long long q;
-};
-
-// Flush the staged points of a warp: one atomic on the group counter per warp (all lanes of a warp almost always
-// work on tracks of the same event group), then every lane stores its own run.  `j0` is the arrival index of the
-// lane's first staged point inside its track; the track kernel owns a track from start to end, so no atomic is
-// needed for it.
-__device__ __forceinline__ void flush_staged(const PointBuf& pb, Counters* ctr, const StagedPoint* mine, int n,
-                                             int ev, int rank, unsigned j0) {
-    const unsigned lane = threadIdx.x & 31;
-    const int g = n > 0 ? ev / pb.group_events : -1;
-    const unsigned active = __ballot_sync(FULL, n > 0);
-    if (active == 0u) return;
-    const int leader = __ffs(active) - 1;
-    const int g0 = __shfl_sync(FULL, g, leader);
-    const bool uniform = __all_sync(FULL, n == 0 || g == g0);
-    unsigned pos = 0;
-    if (uniform) {
-        unsigned incl = (unsigned)n;
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= (unsigned)o) incl += v;
-        }
-        const unsigned total = __shfl_sync(FULL, incl, 31);
-        unsigned base = 0;
-        if (lane == (unsigned)leader) base = atomicAdd(&pb.count[g0], total);
-        base = __shfl_sync(FULL, base, leader);
-        pos = base + incl - (unsigned)n;
-    } else if (n > 0) {
-        pos = atomicAdd(&pb.count[g], (unsigned)n);
-    }
-    if (n > 0) {
-        if ((int64_t)pos + n > pb.group_cap) {
-            ctr->overflow_points = 1;
-            return;
-        }
-        const int64_t i0 = (int64_t)g * pb.group_cap + pos;
-        for (int k = 0; k < n; ++k) {
-            const StagedPoint sp = mine[k];
-            pb.x[i0 + k] = sp.x;
-            pb.y[i0 + k] = sp.y;
-            pb.t[i0 + k] = sp.t;
-            pb.q[i0 + k] = sp.q;
-            pb.ev[i0 + k] = ev;
-            pb.rank[i0 + k] = rank;
-            pb.j[i0 + k] = j0 + (unsigned)k;
-        }
-    }
-}
-
 struct TrackBatch {
     const double* momenta;   // [n_events, n_nuclei, 4]
     const double* vertices;  // [n_events, 3]
@@ -412,16 +362,48 @@ struct TrackBatch {
     int32_t rec_stride, rec_max;
 };
 
-constexpr int TRACK_THREADS = 128;
+// Step slot: what the lanes of a warp need to turn one accepted step of ONE track into its 0.1 ns grid points.
+// Every warp has 32 slots (one per lane = per track in flight), stored field-major in shared memory
+// (field k of slot o at [k * 32 + o]) so that owners write and evaluators read without bank conflicts.
+enum {
+    SF_Y = 0,     // state at the start of the step (6)
+    SF_Q = 6,     // continuous extension q0..q3 (4 x 6)
+    SF_YN = 30,   // state at the end of the step (6)
+    SF_H = 36, SF_TC = 37, SF_HC = 38,
+    SF_PX = 39, SF_PY = 40, SF_PZ = 41, SF_PKE = 42,  // last grid point of the track so far: position and KE
+    SF_MASS = 43, SF_QME = 44, SF_KEEQ = 45,
+    SF_DOUBLES = 46
+};
+enum { SI_STEP = 0, SI_EV, SI_RANK, SI_NUC, SI_NOUT, SI_CUT, SI_TRACK, SI_INTS = 8 };
+constexpr int TRACK_THREADS = 384;  // at most: 12 warps, one CTA per SM (65536 registers / 384 = 170 per thread)
+// + per lane one staged active point (x, y, time, electrons, event, rank, arrival index) waiting for its position
+constexpr int STAGE_DOUBLES = 4, STAGE_INTS = 4;
+constexpr size_t TRACK_SLOT_BYTES_PER_WARP =
+    32 * ((SF_DOUBLES + STAGE_DOUBLES) * sizeof(double) + (SI_INTS + STAGE_INTS) * sizeof(int));
 
-// One lane integrates one track at a time and pulls the next from a global cursor when it finishes, so short
-// (exiting) tracks do not wait for the long (stopping) tracks of the same warp.
+// One lane OWNS one track at a time (and pulls the next from a global cursor when it finishes, so exiting tracks
+// do not wait for the stopping tracks of the same warp); the warp SHARES the per-grid-point work.  A pass of the
+// warp is
+//   A  every owner takes one Dormand-Prince step (error controlled, <= 64 grid cells);
+//   B  the grid points inside all accepted steps of the warp are laid out as one flat list and evaluated 32 at a
+//      time, whoever owns them: continuous extension, kinetic energy, the four terminal events against the
+//      previous grid point, |dKE| / W, the Fano normal, the >= 1 mask, gain, z -> time bucket, and a coalesced
+//      append.  Everything a point needs from its neighbour comes from the lane below (or the previous round).
+//      The append position comes from one global atomic per round whose result is only consumed a round later
+//      (the points wait in shared memory), so its latency is off the critical path.
+// The serial critical path of a track is then its number of steps (tens), not its number of grid points (thousands),
+// and the per-point code always runs with full warps.
 template <bool TAB_SMEM, bool RECORD>
-__global__ void __launch_bounds__(TRACK_THREADS, 3)
+__global__ void __launch_bounds__(TRACK_THREADS, 1)
 track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackBatch tb, PointBuf pb, Counters* ctr) {
-    extern __shared__ double s_tab[];
-    __shared__ StagedPoint s_stage[RECORD ? 1 : TRACK_THREADS * EMIT_CHUNK];
-    StagedPoint* mine = s_stage + (RECORD ? 0 : threadIdx.x * EMIT_CHUNK);
+    extern __shared__ __align__(16) double s_dyn[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    double* sf = s_dyn + (size_t)warp * (SF_DOUBLES + STAGE_DOUBLES) * 32;
+    double* stage_d = sf + SF_DOUBLES * 32;  // [STAGE_DOUBLES][32]
+    int* si = reinterpret_cast<int*>(s_dyn + (size_t)n_warps * (SF_DOUBLES + STAGE_DOUBLES) * 32) +
+              warp * (SI_INTS + STAGE_INTS) * 32;
+    int* stage_i = si + SI_INTS * 32;        // [STAGE_INTS][32]
+    double* s_tab = s_dyn + (size_t)n_warps * ((SF_DOUBLES + STAGE_DOUBLES) * 32 + (SI_INTS + STAGE_INTS) * 32 / 2);
     if (TAB_SMEM) {
         const int n = P.n_species * P.n_nodes;
         for (int i = threadIdx.x; i < n; i += blockDim.x) s_tab[i] = P.tables[i];
@@ -429,20 +411,47 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
     }
     const double* tab_base = TAB_SMEM ? s_tab : P.tables;
     const int64_t n_tracks = tb.n_events * tb.n_tracks_per_event;
+    const unsigned lanes_below = lanemask_lt();
 
     bool have = false, done = false;
     TrackConst c;
-    State y, k, y_grid;          // integrator state at time tc, its derivative, state at the last grid point
+    State y, k;                  // integrator state at time tc and its derivative
     State yn, kn;                // end state of the accepted step whose grid points are being emitted
-    Dense dense;                 // ... and its continuous extension
+    double gx = 0.0, gy = 0.0, gz = 0.0, ke = 0.0;  // position and kinetic energy at the last grid point
     double h = 0.0, err = 0.0, t_end = 0.0;
-    int pending = 0;             // grid points of the accepted step still to emit
-    unsigned n_out = 0;          // active points this track has produced so far
-    double ke = 0.0;             // kinetic energy at the last grid point
+    int pending = 0;             // grid points inside the accepted step
+    int n_out = 0;               // active points this track has produced so far
     double tc = 0.0, hc = 1.0;   // time and step size in units of grid cells (0.1 ns)
     int step = 0, ev = 0, rank = 0, nucleus = 0;
     int64_t track = 0;
     unsigned long long n_traj = 0, n_active = 0, n_prim = 0;
+    unsigned n_steps = 0, n_rejects = 0, passes = 0, max_passes = 0;
+    // Points staged by the previous round (warp-uniform mask of the lanes that hold one) and the still pending result
+    // of the atomic that reserved their positions: in the leader's register (one atomic for the warp, leader >= 0)
+    // or in every lane's own (tracks of several event groups in one round, leader < 0).
+    unsigned staged_mask = 0, staged_first = 0, staged_prefix = 0;
+    int staged_leader = 0;
+    auto store_staged = [&]() {  // whole warp; the first read of staged_first waits for the atomic issued a round ago
+        if (staged_mask == 0u) return;
+        const unsigned pos =
+            staged_leader >= 0 ? __shfl_sync(FULL, staged_first, staged_leader) + staged_prefix : staged_first;
+        if ((staged_mask >> lane) & 1u) {
+            const int gi = stage_i[0 * 32 + lane] / pb.group_events;
+            if ((int64_t)pos >= pb.group_cap) {
+                ctr->overflow_points = 1;
+            } else {
+                const int64_t i = (int64_t)gi * pb.group_cap + pos;
+                pb.x[i] = stage_d[0 * 32 + lane];
+                pb.y[i] = stage_d[1 * 32 + lane];
+                pb.t[i] = stage_d[2 * 32 + lane];
+                pb.q[i] = __double_as_longlong(stage_d[3 * 32 + lane]);
+                pb.ev[i] = stage_i[0 * 32 + lane];
+                pb.rank[i] = stage_i[1 * 32 + lane];
+                pb.j[i] = (unsigned)stage_i[2 * 32 + lane];
+            }
+        }
+        staged_mask = 0u;
+    };
 
     while (true) {
         if (!have && !done) {
@@ -470,13 +479,16 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
                     y.uy = m4[1] / S.mass;
                     y.uz = m4[2] / S.mass;
                     k = rhs(c, y);
-                    y_grid = y;
-                    ke = kinetic_energy(c, y.ux, y.uy, y.uz);
+                    gx = y.x;
+                    gy = y.y;
+                    gz = y.z;
+                    ke = kinetic_energy(c.mass, y.ux, y.uy, y.uz);
                     step = 0;
                     tc = 0.0;
                     hc = 1.0;
                     pending = 0;
                     n_out = 0;
+                    passes = 0;
                     have = true;
                     n_traj += 1;  // grid point 0 (never active: detector/solver.py:338-339)
                     if (RECORD && tb.rec_max > 0) {
@@ -490,11 +502,15 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
         }
         if (__all_sync(FULL, done)) break;
 
-        // ---- phase A: lanes with no grid point left to emit try one Dormand-Prince step of hc grid cells from tc
-        if (have && pending == 0) {
+        // ---- phase A: every owner tries one Dormand-Prince step of hc grid cells from tc
+        passes += have;
+        if (have) {
+            Dense dense;
             h = hc * GRID_DT;
             err = dopri5_step(c, y, k, h, P.rtol, P.atol, yn, kn, dense);
+            n_steps += 1;
             if (!(err <= 1.0) && hc > 1.0 / 4096.0) {  // reject: retry with a smaller step
+                n_rejects += 1;
                 hc *= (err == err) ? fmin(0.9, step_factor(err)) : 0.2;
             } else {
                 t_end = tc + hc;
@@ -504,79 +520,202 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
                     y = yn;
                     k = kn;
                     hc = fmin(MAX_STEP_CELLS, hc * step_factor(err));
+                } else {  // hand the step to the warp
+#define PUT(field, value) sf[(field) * 32 + lane] = (value)
+                    PUT(SF_Y + 0, y.x); PUT(SF_Y + 1, y.y); PUT(SF_Y + 2, y.z);
+                    PUT(SF_Y + 3, y.ux); PUT(SF_Y + 4, y.uy); PUT(SF_Y + 5, y.uz);
+#define PUTQ(n, q) \
+    PUT(SF_Q + 6 * n + 0, q.x); PUT(SF_Q + 6 * n + 1, q.y); PUT(SF_Q + 6 * n + 2, q.z); \
+    PUT(SF_Q + 6 * n + 3, q.ux); PUT(SF_Q + 6 * n + 4, q.uy); PUT(SF_Q + 6 * n + 5, q.uz);
+                    PUTQ(0, dense.q0) PUTQ(1, dense.q1) PUTQ(2, dense.q2) PUTQ(3, dense.q3)
+#undef PUTQ
+                    PUT(SF_YN + 0, yn.x); PUT(SF_YN + 1, yn.y); PUT(SF_YN + 2, yn.z);
+                    PUT(SF_YN + 3, yn.ux); PUT(SF_YN + 4, yn.uy); PUT(SF_YN + 5, yn.uz);
+                    PUT(SF_H, h); PUT(SF_TC, tc); PUT(SF_HC, hc);
+                    PUT(SF_PX, gx); PUT(SF_PY, gy); PUT(SF_PZ, gz); PUT(SF_PKE, ke);
+                    PUT(SF_MASS, c.mass); PUT(SF_QME, c.qmE); PUT(SF_KEEQ, c.ke_eq);
+#undef PUT
+                    si[SI_STEP * 32 + lane] = step;
+                    si[SI_EV * 32 + lane] = ev;
+                    si[SI_RANK * 32 + lane] = rank;
+                    si[SI_NUC * 32 + lane] = nucleus;
+                    si[SI_NOUT * 32 + lane] = n_out;
+                    si[SI_CUT * 32 + lane] = INT_MAX;
+                    si[SI_TRACK * 32 + lane] = (int)track;
                 }
             }
         }
-        // ---- phase B: every lane emits up to EMIT_CHUNK of its pending grid points.  Lanes stay in lock step, so the
-        //      per-point code runs converged even though steps of different lanes span 1..64 grid cells.
-        bool finished = false;
-        int n_staged = 0;
-#pragma unroll 1
-        for (int it = 0; it < EMIT_CHUNK; ++it) {
-            if (pending > 0 && !finished) {
-                const double theta = fmin(1.0, ((double)(step + 1) - tc) / hc);
-                const State g = theta >= 1.0 ? yn : dense_eval(y, dense, h, theta);
-                const double ke_g = kinetic_energy(c, g.ux, g.uy, g.uz);
-                pending -= 1;
-                if (terminal_event(c, y_grid, g, ke, ke_g)) {
-                    finished = true;
-                } else {
-                    step += 1;
-                    n_traj += 1;
-                    if (RECORD) {
-                        if (step % tb.rec_stride == 0 && step / tb.rec_stride < tb.rec_max) {
-                            double* o = tb.rec_points + ((int64_t)track * tb.rec_max + step / tb.rec_stride) * 6;
-                            o[0] = g.x; o[1] = g.y; o[2] = g.z; o[3] = g.ux; o[4] = g.uy; o[5] = g.uz;
-                        }
-                    } else {
-                        // detector/solver.py:338-346: mean = |dKE| / W, Gaussian with variance F * mean, truncation
-                        const double mean = fabs(ke_g - ke) * P.ev_per_w;
-                        const double spread = sqrt(P.fano * mean);
-                        if (mean + spread * NORMAL_ABS_MAX >= 1.0) {
-                            const double zn = philox_normal(tb.seed, (uint64_t)(tb.first_event + ev),
-                                                            (uint32_t)nucleus, (uint32_t)step);
-                            const long long n_e = (long long)(mean + spread * zn);
-                            if (n_e >= 1) {  // detector/solver.py:387
-                                const double time = (P.length - g.z) / P.dv + P.mm_edge;  // solver.py:396-398
-                                mine[n_staged++] = StagedPoint{g.x, g.y, time, n_e * P.gain};      // solver.py:392
-                                n_active += 1;
-                                n_prim += (unsigned long long)n_e;
-                            }
-                        }
-                    }
-                    y_grid = g;
-                    ke = ke_g;
-                    if (step >= GRID_POINTS - 1 || inert_forever(c, g, ke, P.freeze_ke)) finished = true;
-                    if (pending == 0 && !finished) {  // all grid points of the step are out: advance the integrator
-                        tc = t_end;
-                        y = yn;
-                        k = kn;
-                        hc = fmin(MAX_STEP_CELLS, hc * step_factor(err));
-                    }
+        // ---- phase B: the grid points of all accepted steps of the warp, 32 at a time
+        const bool emitting = have && pending > 0;
+        const int mine = emitting ? pending : 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int excl = incl - mine;
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (total == 0) continue;  // warp-uniform
+        __syncwarp();
+        double carry_x = 0.0, carry_y = 0.0, carry_z = 0.0, carry_ke = 0.0;  // lane 31 of the previous round
+        for (int base = 0; base < total; base += 32) {
+            const int f = base + lane;
+            const bool valid = f < total;
+            int o = 0;  // owner of flat point f: the number of lanes whose inclusive count is <= f
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const int v = __shfl_sync(FULL, incl, o + s - 1);
+                if (v <= f) o += s;
+            }
+            const int j = f - __shfl_sync(FULL, excl, o);  // position inside the owner's step
+#define GET(field) sf[(field) * 32 + o]
+            const int s_idx = si[SI_STEP * 32 + o] + 1 + j;  // grid step of this point
+            const double hc_o = GET(SF_HC);
+            const double theta = fmin(1.0, ((double)s_idx - GET(SF_TC)) / hc_o);
+            State g;
+            if (theta >= 1.0) {
+                g.x = GET(SF_YN + 0); g.y = GET(SF_YN + 1); g.z = GET(SF_YN + 2);
+                g.ux = GET(SF_YN + 3); g.uy = GET(SF_YN + 4); g.uz = GET(SF_YN + 5);
+            } else {
+                const double ht = GET(SF_H) * theta;
+#define DE(f, i) \
+    g.f = fma(ht, fma(theta, fma(theta, fma(theta, GET(SF_Q + 18 + i), GET(SF_Q + 12 + i)), GET(SF_Q + 6 + i)), GET(SF_Q + i)), GET(SF_Y + i));
+                DE(x, 0) DE(y, 1) DE(z, 2) DE(ux, 3) DE(uy, 4) DE(uz, 5)
+#undef DE
+            }
+            const double mass = GET(SF_MASS);
+            const double ke_g = kinetic_energy(mass, g.ux, g.uy, g.uz);
+            // the previous grid point of the same track: the lane below, the last lane of the previous round, or
+            // (first point of the step) what the owner left in the slot
+            double px = __shfl_up_sync(FULL, g.x, 1), py = __shfl_up_sync(FULL, g.y, 1);
+            double pz = __shfl_up_sync(FULL, g.z, 1), pke = __shfl_up_sync(FULL, ke_g, 1);
+            if (lane == 0) {
+                px = carry_x; py = carry_y; pz = carry_z; pke = carry_ke;
+            }
+            if (j == 0) {
+                px = GET(SF_PX); py = GET(SF_PY); pz = GET(SF_PZ); pke = GET(SF_PKE);
+            }
+            // the track ends BEFORE this point (terminal event in the cell) or AFTER it (time limit, inert ion)
+            const bool term = valid && terminal_event(px, py, pz, pke, g.x, g.y, g.z, ke_g);
+            const bool after = valid && !term &&
+                               (s_idx >= GRID_POINTS - 1 ||
+                                inert_forever(mass, GET(SF_QME), GET(SF_KEEQ), g, ke_g, P.freeze_ke));
+            if (term | after) atomicMin(&si[SI_CUT * 32 + o], term ? j : j + 1);
+            __syncwarp();
+            const bool live = valid && j < si[SI_CUT * 32 + o];  // a row of the trajectory
+            const int ev_o = si[SI_EV * 32 + o];
+            bool emit = false;
+            long long n_e = 0;
+            if (RECORD) {
+                if (live && s_idx % tb.rec_stride == 0 && s_idx / tb.rec_stride < tb.rec_max) {
+                    double* r = tb.rec_points + ((int64_t)si[SI_TRACK * 32 + o] * tb.rec_max + s_idx / tb.rec_stride) * 6;
+                    r[0] = g.x; r[1] = g.y; r[2] = g.z; r[3] = g.ux; r[4] = g.uy; r[5] = g.uz;
+                }
+            } else if (live) {
+                // detector/solver.py:338-346: mean = |dKE| / W, Gaussian with variance F * mean, truncation
+                const double mean = fabs(ke_g - pke) * P.ev_per_w;
+                const double spread = sqrt(P.fano * mean);
+                if (mean + spread * NORMAL_ABS_MAX >= 1.0) {
+                    const double zn = philox_normal(tb.seed, (uint64_t)(tb.first_event + ev_o),
+                                                    (uint32_t)si[SI_NUC * 32 + o], (uint32_t)s_idx);
+                    n_e = (long long)(mean + spread * zn);
+                    emit = n_e >= 1;  // detector/solver.py:387
                 }
             }
+            n_traj += live;
+            const unsigned emit_mask = __ballot_sync(FULL, emit);
+            // arrival index inside the track: emitted points of the same owner below this lane
+            const int seg_start = max(0, lane - j);
+            const int before = __popc(emit_mask & lanes_below & ~((1u << seg_start) - 1u));
+            const int n_out_o = si[SI_NOUT * 32 + o];
+            const int o_next = __shfl_down_sync(FULL, o, 1);
+            const int live_next = __shfl_down_sync(FULL, (int)live, 1);
+            const bool same_next = lane < 31 && f + 1 < total && o_next == o;
+            __syncwarp();  // every read of this round's slot fields is done
+            if (valid && !same_next) si[SI_NOUT * 32 + o] = n_out_o + before + (int)emit;
+            if (live && !(same_next && live_next)) {  // the last row so far of this track
+                sf[SF_PX * 32 + o] = g.x;
+                sf[SF_PY * 32 + o] = g.y;
+                sf[SF_PZ * 32 + o] = g.z;
+                sf[SF_PKE * 32 + o] = ke_g;
+            }
+#undef GET
+            store_staged();  // the points of the previous round: their positions have arrived by now
+            if (emit_mask) {  // warp-uniform: one atomic on the group counter per round (tracks of a warp almost
+                              // always belong to the same event group); the lanes keep their points in shared
+                              // memory until the next round
+                const int gi = emit ? ev_o / pb.group_events : -1;
+                const int leader = __ffs(emit_mask) - 1;
+                const int g0 = __shfl_sync(FULL, gi, leader);
+                const bool uniform = __all_sync(FULL, !emit || gi == g0);
+                staged_mask = emit_mask;
+                staged_leader = uniform ? leader : -1;
+                staged_prefix = (unsigned)__popc(emit_mask & lanes_below);
+                if (uniform) {
+                    if (lane == leader) staged_first = atomicAdd(&pb.count[g0], (unsigned)__popc(emit_mask));
+                } else if (emit) {
+                    staged_first = atomicAdd(&pb.count[gi], 1u);
+                }
+                if (emit) {
+                    stage_d[0 * 32 + lane] = g.x;
+                    stage_d[1 * 32 + lane] = g.y;
+                    stage_d[2 * 32 + lane] = (P.length - g.z) / P.dv + P.mm_edge;  // detector/solver.py:396-398
+                    stage_d[3 * 32 + lane] = __longlong_as_double(n_e * P.gain);     // detector/solver.py:392
+                    stage_i[0 * 32 + lane] = ev_o;
+                    stage_i[1 * 32 + lane] = si[SI_RANK * 32 + o];
+                    stage_i[2 * 32 + lane] = n_out_o + before;
+                    n_active += 1;
+                    n_prim += (unsigned long long)n_e;
+                }
+            }
+            carry_x = __shfl_sync(FULL, g.x, 31);
+            carry_y = __shfl_sync(FULL, g.y, 31);
+            carry_z = __shfl_sync(FULL, g.z, 31);
+            carry_ke = __shfl_sync(FULL, ke_g, 31);
         }
-        if (!RECORD) {
-            flush_staged(pb, ctr, mine, n_staged, ev, rank, n_out);
-            n_out += (unsigned)n_staged;
-        }
-        if (finished) {
-            have = false;
+        __syncwarp();
+        if (emitting) {  // owners take their tracks back
+            const int cut = si[SI_CUT * 32 + lane];
+            const bool finished = cut <= pending;
+            step += min(pending, cut);
+            n_out = si[SI_NOUT * 32 + lane];
+            gx = sf[SF_PX * 32 + lane];
+            gy = sf[SF_PY * 32 + lane];
+            gz = sf[SF_PZ * 32 + lane];
+            ke = sf[SF_PKE * 32 + lane];
             pending = 0;
-            if (RECORD) tb.rec_counts[track] = step + 1;
-            else pb.cnt[(int64_t)ev * pb.ranks + rank] = n_out;  // length of this track's list (no other writer)
+            if (!finished) {  // all grid points of the step are out: advance the integrator
+                tc = t_end;
+                y = yn;
+                k = kn;
+                hc = fmin(MAX_STEP_CELLS, hc * step_factor(err));
+            } else {
+                have = false;
+                max_passes = max(max_passes, passes);
+                if (RECORD) tb.rec_counts[track] = step + 1;
+                else pb.cnt[(int64_t)ev * pb.ranks + rank] = (unsigned)n_out;  // length of this track's list
+            }
         }
+        __syncwarp();
     }
+    store_staged();
     // per-warp statistics
     for (int o = 16; o > 0; o >>= 1) {
         n_traj += __shfl_xor_sync(FULL, n_traj, o);
         n_active += __shfl_xor_sync(FULL, n_active, o);
         n_prim += __shfl_xor_sync(FULL, n_prim, o);
     }
+    n_steps = __reduce_add_sync(FULL, n_steps);
+    n_rejects = __reduce_add_sync(FULL, n_rejects);
+    max_passes = __reduce_max_sync(FULL, max_passes);
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&ctr->traj_points, n_traj);
         atomicAdd(&ctr->active_points, n_active);
         atomicAdd(&ctr->primary_electrons, n_prim);
+        atomicAdd(&ctr->rk_steps, (unsigned long long)n_steps);
+        atomicAdd(&ctr->rk_rejects, (unsigned long long)n_rejects);
+        atomicMax(&ctr->max_track_passes, (unsigned long long)max_passes);
     }
 }
 

@@ -127,6 +127,7 @@ _STAT_FIELDS = (
     "n_tracks", "n_trajectory_points", "n_active_points", "n_primary_electrons", "n_deposits", "n_keys",
     "ms_h2d", "ms_tracks", "ms_deposit", "ms_finalize", "ms_d2h", "ms_total", "n_kernel_launches", "n_retries",
     "n_track_launches", "n_group_launches", "n_hash_probes", "hash_capacity", "n_table_flushes",
+    "n_rk_steps", "n_rk_rejects", "max_track_passes",
 )  # fmt: skip
 
 
@@ -138,8 +139,8 @@ class Engine:
         config: Config,
         species: list,
         device: int = 0,
-        ode_rtol: float = 1e-8,
-        ode_atol: float = 1e-12,
+        ode_rtol: float = 1e-6,
+        ode_atol: float = 1e-10,
         freeze_ke_mev: float | None = None,
         max_events_per_launch: int = 0,
         hash_capacity: int = 0,

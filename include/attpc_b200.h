@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ATTPC_ABI_VERSION 1
+#define ATTPC_ABI_VERSION 2
 
 enum {
     ATTPC_OK = 0,
@@ -133,6 +133,10 @@ typedef struct AttpcResult {
     const double* col_tb;        /* [n_points] time bucket + wiggle */
     const int64_t* col_electrons;/* [n_points] electrons (after gain) */
     const int8_t* col_label;     /* [n_points] index of the nucleus that last touched the point */
+    /* integrator statistics (right-hand-side evaluations = 6 * n_rk_steps + n_tracks) */
+    int64_t n_rk_steps;          /* Dormand-Prince steps tried (accepted + rejected) */
+    int64_t n_rk_rejects;        /* of which rejected by the error control */
+    int64_t max_track_passes;    /* most step/emit passes any single track needed: the serial critical path */
 } AttpcResult;
 
 typedef struct AttpcSim AttpcSim;
