@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -93,6 +94,7 @@ struct AttpcSim {
     int32_t launch_events = 32768;
     int32_t copy_launch_events = 2048;
     int32_t group_events = 2048;
+    int32_t chunk_groups = 16;  // groups per kernel launch when the rows stay on the device
     int32_t hash_cap = 16384;
     int64_t group_point_cap = 0;
 
@@ -229,8 +231,11 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     CU(sim->pstart.reserve(launch_events * ranks));
     CU(sim->n_entries.reserve(launch_events));
     CU(sim->mode.reserve(launch_events));
-    CU(sim->hash.reserve((int64_t)sim->group_events * sim->hash_cap));
-    CU(sim->sort_items.reserve((int64_t)sim->group_events * sim->hash_cap * 2));
+    // tables and sort scratch for one chunk of groups (run_groups)
+    const int64_t copy_groups = (sim->copy_launch_events + sim->group_events - 1) / sim->group_events;
+    const int64_t table_groups = std::min<int64_t>(n_groups, std::max<int64_t>(sim->chunk_groups, copy_groups));
+    CU(sim->hash.reserve(table_groups * sim->group_events * sim->hash_cap));
+    CU(sim->sort_items.reserve(table_groups * sim->group_events * sim->hash_cap * 2));
     CU(sim->csr_total.reserve(2));
     CU(sim->csr_host.reserve(2));
     CU(sim->chunk_totals.reserve(n_groups + 1));
@@ -324,30 +329,40 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
     const size_t sort_smem = (size_t)SORT_SMEM_ITEMS * sizeof(uint64_t);
     CU(cudaFuncSetAttribute(collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
     CU(cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEPOSIT_SMEM_BYTES));
-    for (int64_t g = 0; g < n_groups; ++g) {
+    // Groups are processed in chunks: every kernel is launched once per chunk with one grid row per group, so the
+    // ramp-up and tail of a launch are paid once per chunk.  When rows go to the host a chunk is what is copied while
+    // the next chunk computes; otherwise it is as many groups as the tables are sized for.
+    const int64_t gpc = std::max<int64_t>(1, fences ? groups_per_chunk : sim->chunk_groups);
+    for (int64_t g0 = 0; g0 < n_groups; g0 += gpc) {
+        const int64_t ng = std::min<int64_t>(gpc, n_groups - g0);
         GroupView gv;
-        gv.first_slot = (int32_t)(g * sim->group_events);
-        gv.n_events = (int32_t)std::min<int64_t>(sim->group_events, launch_events - gv.first_slot);
-        gv.group = (int32_t)g;
+        gv.first_slot = (int32_t)(g0 * sim->group_events);
+        gv.n_events = (int32_t)std::min<int64_t>(ng * sim->group_events, launch_events - gv.first_slot);
+        gv.group = (int32_t)g0;
         gv.hash_cap = sim->hash_cap;
         gv.tables = sim->hash.p;
         gv.n_entries = sim->n_entries.p;
         gv.mode = sim->mode.p;
         gv.exact_mesh = (fa.flags & ATTPC_EXACT_MESH) ? 1 : 0;
+        gv.group_events = sim->group_events;
+        gv.chunk_e0 = 0;
+        const dim3 per_event((unsigned)std::min<int64_t>(sim->group_events, gv.n_events), (unsigned)ng);
         cudaEvent_t d0 = sim->mark();
-        point_scan_kernel<<<1, 1024, 0, sim->stream>>>(pb, gv, ctr);
-        point_order_kernel<<<sim->sm_count * 4, 256, 0, sim->stream>>>(sim->P, pb, gv, ctr);
-        zero_shared_tables_kernel<<<gv.n_events, 256, 0, sim->stream>>>(gv, ctr);
-        deposit_kernel<<<sim->max_units, DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES, sim->stream>>>(sim->P, pb, gv, ctr);
+        point_scan_kernel<<<(unsigned)ng, 1024, 0, sim->stream>>>(pb, gv, ctr);
+        point_order_kernel<<<dim3((unsigned)std::max<int64_t>(1, sim->sm_count * 4 / ng), (unsigned)ng), 256, 0,
+                             sim->stream>>>(sim->P, pb, gv, ctr);
+        zero_shared_tables_kernel<<<per_event, 256, 0, sim->stream>>>(gv, ctr);
+        deposit_kernel<<<dim3((unsigned)sim->max_units, (unsigned)ng), DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES,
+                         sim->stream>>>(sim->P, pb, gv, ctr);
         cudaEvent_t d1 = sim->mark();
-        collect_kernel<<<gv.n_events, FINALIZE_THREADS, sort_smem, sim->stream>>>(sim->P, fa, gv, ctr);
+        collect_kernel<<<per_event, FINALIZE_THREADS, sort_smem, sim->stream>>>(sim->P, fa, gv, ctr);
         scan_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, ctr, sim->csr_total.p);
-        emit_kernel<<<gv.n_events, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
+        emit_kernel<<<per_event, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
         cudaEvent_t f1 = sim->mark();
         sim->launches += 7;
         dep_marks.push_back({d0, d1});
         fin_marks.push_back({d1, f1});
-        if (fences && groups_per_chunk > 0 && ((g + 1) % groups_per_chunk == 0 || g + 1 == n_groups)) {
+        if (fences) {
             const int slot = (int)fences->size();
             if (slot < (int)sim->chunk_totals.n) {
                 publish_total_kernel<<<1, 1, 0, sim->stream>>>(sim->csr_total.p, sim->chunk_totals.p + slot);
@@ -883,6 +898,7 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
     if (cfg->copy_events_per_launch > 0) sim->copy_launch_events = cfg->copy_events_per_launch;  // events per launch when rows go to the host
     if (cfg->hash_capacity > 0) sim->hash_cap = next_pow2(cfg->hash_capacity);
     sim->group_events = std::min(sim->group_events, sim->launch_events);
+    if (const char* env = getenv("ATTPC_CHUNK_GROUPS")) sim->chunk_groups = std::max(1, atoi(env));  // tuning aid
 
     const int64_t lut_cells = (int64_t)cfg->lut_n * cfg->lut_n;
     CUC(sim->lut.reserve(lut_cells));

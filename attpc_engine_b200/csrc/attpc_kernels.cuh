@@ -853,7 +853,20 @@ struct GroupView {
     unsigned* n_entries;  // [launch events] entries of the dense list
     unsigned* mode;       // [launch events] 0 = dense list, 1 = the event spilled to a global table
     int32_t exact_mesh;   // ATTPC_EXACT_MESH: every pixel through the reference's own expression (validation)
+    int32_t group_events; // events per full group
+    int32_t chunk_e0;     // first event of the group inside the chunk (row of `tables` and of the sort scratch)
 };
+
+// The host describes a CHUNK of consecutive groups (first_slot / group / n_events of the whole chunk) and launches
+// every group kernel once per chunk with one grid row (or, for point_scan_kernel, one CTA) per group.
+__device__ __forceinline__ GroupView sub_group(GroupView gv, int dy) {
+    const int skip = dy * gv.group_events;
+    gv.group += dy;
+    gv.first_slot += skip;
+    gv.n_events = max(0, min(gv.group_events, gv.n_events - skip));
+    gv.chunk_e0 = skip;
+    return gv;
+}
 
 // ------------------------------------------------------------------------------------------- ordering of points
 constexpr int UNIT_POINTS = 1024;   // longest slice of one event handled by one CTA of the deposit kernel
@@ -863,7 +876,8 @@ constexpr int GEOM_DOUBLES = 12;
 // Per group, single CTA: (1) exclusive scan of the (event, rank) list lengths -> start of every list in the group's
 // ordered run; (2) split every event into work units of <= UNIT_POINTS points; (3) order the units by decreasing
 // size so that the longest start first (the per-event cost varies by 100x between a short recoil and a stopped ion).
-__global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView gv, const Counters* ctr) {
+__global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView chunk, const Counters* ctr) {
+    const GroupView gv = sub_group(chunk, blockIdx.x);
     __shared__ unsigned s_part[1024];
     __shared__ unsigned s_base, s_ubase;
     __shared__ uint32_t s_sort[MAX_UNITS_SORT];
@@ -1053,8 +1067,9 @@ __device__ __noinline__ long long exact_share(const double* g, int i, int j) {
 
 // Scatter the group's points into (event, rank, arrival) order and compute their mesh constants (one thread each).
 __global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant__ SimParams P, PointBuf pb,
-                                                          GroupView gv, const Counters* ctr) {
+                                                          GroupView chunk, const Counters* ctr) {
     if (ctr->overflow_points) return;
+    const GroupView gv = sub_group(chunk, blockIdx.y);
     const int64_t n = min((int64_t)pb.count[gv.group], pb.group_cap);
     const int64_t base = (int64_t)gv.group * pb.group_cap;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
@@ -1157,7 +1172,8 @@ __device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t,
 // pixels.  At the end the table is compacted into the event's dense entry list (events of one unit) or merged into
 // the event's global table (events split over several units, and units dense enough to overflow the shared table).
 __global__ void __launch_bounds__(DEPOSIT_THREADS, 2)
-deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, Counters* ctr) {
+deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk, Counters* ctr) {
+    const GroupView gv = sub_group(chunk, blockIdx.y);
     extern __shared__ __align__(16) unsigned s_raw[];
     __shared__ unsigned s_nkeys, s_out, s_spilled;
     __shared__ unsigned s_qkey[DEPOSIT_WARPS][QUEUE_SLOTS], s_qlo[DEPOSIT_WARPS][QUEUE_SLOTS],
@@ -1174,7 +1190,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
     const int slot_event = gv.first_slot + e;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool shared_event = gv.mode[slot_event] != 0u;  // several units: merge through the (pre-zeroed) global table
-    HashEntry* region = gv.tables + (int64_t)e * gv.hash_cap;
+    HashEntry* region = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
     const unsigned gmask = (unsigned)gv.hash_cap - 1u;
     const int64_t base = (int64_t)gv.group * pb.group_cap;
     constexpr int TABLE_VEC4 = (2 * SMEM_SLOTS + SMEM_SLOTS / 2) / 4;
@@ -1384,11 +1400,12 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView gv, C
 }
 
 // Zero the global tables of the events that are split over several units (before the deposit kernel merges into them).
-__global__ void __launch_bounds__(256) zero_shared_tables_kernel(GroupView gv, const Counters* ctr) {
+__global__ void __launch_bounds__(256) zero_shared_tables_kernel(GroupView chunk, const Counters* ctr) {
     if (ctr->overflow_points) return;
+    const GroupView gv = sub_group(chunk, blockIdx.y);
     const int e = blockIdx.x;
-    if (gv.mode[gv.first_slot + e] == 0u) return;
-    HashEntry* region = gv.tables + (int64_t)e * gv.hash_cap;
+    if (e >= gv.n_events || gv.mode[gv.first_slot + e] == 0u) return;
+    HashEntry* region = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
     for (int i = threadIdx.x; i < gv.hash_cap; i += blockDim.x) region[i] = HashEntry{0u, 0u, 0ULL};
 }
 
@@ -1452,8 +1469,10 @@ __device__ __forceinline__ uint64_t make_item(unsigned tb, unsigned pad, unsigne
 // and put them in canonical order: counting sort on the time bucket (exact, O(n)), then an insertion sort of each
 // bucket's handful of pads.  No power-of-two padding and no dependence on which thread found which slot.
 __global__ void __launch_bounds__(FINALIZE_THREADS)
-collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView gv,
+collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView chunk,
                Counters* ctr) {
+    const GroupView gv = sub_group(chunk, blockIdx.y);
+    if ((int)blockIdx.x >= gv.n_events) return;
     extern __shared__ uint64_t s_items[];
     __shared__ unsigned s_hist[TB_BINS + 1];
     __shared__ unsigned s_fill[TB_BINS];
@@ -1464,8 +1483,8 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
         if (threadIdx.x == 0) fa.kept[slot_event] = 0u;
         return;
     }
-    const HashEntry* tab = gv.tables + (int64_t)e * gv.hash_cap;
-    uint64_t* sorted = fa.sort_items + (int64_t)e * 2 * gv.hash_cap;  // final order, read by emit_kernel
+    const HashEntry* tab = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
+    uint64_t* sorted = fa.sort_items + (int64_t)(gv.chunk_e0 + e) * 2 * gv.hash_cap;  // final order, read by emit_kernel
     uint64_t* stash = sorted + gv.hash_cap;                           // unordered survivors
     for (int i = threadIdx.x; i <= TB_BINS; i += blockDim.x) s_hist[i] = 0;
     if (threadIdx.x == 0) {
@@ -1591,15 +1610,17 @@ scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr, unsigned long long* cs
 // One CTA per event: write [pad, tb + u, electrons] rows and labels in ascending (time bucket, pad) order
 // (detector/simulator.py:19-49, 104-115).
 __global__ void __launch_bounds__(FINALIZE_THREADS)
-emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView gv,
+emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView chunk,
             Counters* ctr) {
+    const GroupView gv = sub_group(chunk, blockIdx.y);
+    if ((int)blockIdx.x >= gv.n_events) return;
     const int e = blockIdx.x;
     const int slot_event = gv.first_slot + e;
     const int n = (int)fa.kept[slot_event];
     const int64_t off = fa.offsets[slot_event];
     if (off + n > fa.out_cap) return;
-    const HashEntry* tab = gv.tables + (int64_t)e * gv.hash_cap;
-    const uint64_t* items = fa.sort_items + (int64_t)e * 2 * gv.hash_cap;
+    const HashEntry* tab = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
+    const uint64_t* items = fa.sort_items + (int64_t)(gv.chunk_e0 + e) * 2 * gv.hash_cap;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint64_t it = items[i];
         const unsigned tb = (unsigned)(it >> 47), pad = (unsigned)(it >> 32) & 0x7FFFu;
