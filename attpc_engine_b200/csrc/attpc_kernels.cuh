@@ -1005,6 +1005,7 @@ __device__ __forceinline__ int lut_index(const SimParams& P, double coord_m) {
 //   words 2-3   electrons after gain as double
 //   words 4-8   int16 iy[10]: pad-table column of mesh column j (-1 = outside), kind 1: iy[0] of the point itself
 //   words 9-13  int16 ix[10]: pad-table row of mesh row i
+//   word 14     rank of the track (position in `indices`)
 constexpr int REC_WORDS = 16;
 
 __device__ __forceinline__ void make_point(const SimParams& P, double cx, double cy, double time, long long q,
@@ -1080,6 +1081,7 @@ __global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant_
 #pragma unroll
         for (int k = 0; k < GEOM_DOUBLES; ++k) g[k] = 0.0;
         make_point(P, pb.x[i], pb.y[i], pb.t[i], pb.q[i], g, rec);
+        rec[14] = (uint32_t)pb.rank[i];
         double2* out = reinterpret_cast<double2*>(pb.geom + d * GEOM_DOUBLES);
 #pragma unroll
         for (int k = 0; k < GEOM_DOUBLES / 2; ++k) out[k] = make_double2(g[2 * k], g[2 * k + 1]);
@@ -1175,7 +1177,7 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, 2)
 deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk, Counters* ctr) {
     const GroupView gv = sub_group(chunk, blockIdx.y);
     extern __shared__ __align__(16) unsigned s_raw[];
-    __shared__ unsigned s_nkeys, s_out, s_spilled;
+    __shared__ unsigned s_nkeys, s_out, s_spilled, s_flush;
     __shared__ unsigned s_qkey[DEPOSIT_WARPS][QUEUE_SLOTS], s_qlo[DEPOSIT_WARPS][QUEUE_SLOTS],
         s_qhi[DEPOSIT_WARPS][QUEUE_SLOTS];
     if ((int)blockIdx.x >= pb.n_units[gv.group]) return;
@@ -1203,6 +1205,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
         s_nkeys = 0;
         s_out = 0;
         s_spilled = 0;
+        s_flush = 0;
     }
     __syncthreads();
     unsigned n_dep = 0, n_probe = 0, n_new = 0;
@@ -1226,7 +1229,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
             const unsigned long long q = ((unsigned long long)qhi[at] << 32) | qlo[at];
             const unsigned slot = smem_find(t, kw & SMEM_KEY_MASK, kw >> 28, n_new, n_probe);
             smem_charge(t, slot, q, &ctr->overflow_charge);
-            t.word[slot] = kw;  // key + rank: the same value from every writer of this rank phase
+            atomicMax(&t.word[slot], kw);  // same key bits: the highest rank wins (transporter.py:247-249)
         }
         __syncwarp();
         q_head += n;
@@ -1254,112 +1257,118 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
         if (threadIdx.x == 0) {
             s_nkeys = 0;
             s_spilled = 1;
+            s_flush = 0;
             atomicAdd(&ctr->flushes, 1ULL);
         }
         __syncthreads();
     };
 
-    // the unit's slice [u_first, u_first + u_count) of the event's run, walked rank by rank
-    const int64_t li0 = (int64_t)slot_event * pb.ranks;
-    const int64_t run0 = pb.start[li0];
-    int rank_begin = 0;  // position of the current rank's list inside the event's run
-    for (int r = 0; r < pb.ranks; ++r) {
-        const int rank_len = (int)pb.cnt[li0 + r];
-        const int lo = max(rank_begin, u_first), hi = min(rank_begin + rank_len, u_first + u_count);
-        rank_begin += rank_len;
-        if (lo >= hi) continue;
-        for (int p0 = lo; p0 < hi; p0 += POINTS_PER_ITER) {
-            const int w0 = p0 + warp * POINTS_PER_WARP;
-            if (w0 < hi) {  // warp-uniform
-                const int pp = w0 + sub;
-                const bool have = sub < POINTS_PER_WARP && pp < hi;
-                const int64_t p = base + run0 + (have ? pp : w0);
-                const uint4* rp = reinterpret_cast<const uint4*>(pb.rec + p * REC_WORDS);
-                uint4 head = __ldg(rp);
-                if (!have) head.x = 0u;
-                const int kind = (int)(head.x >> 30), tb = (int)(head.x & 0x3FFFFFFFu);
-                const unsigned keybase = (((unsigned)tb << 15) + 1u) | ((unsigned)r << 28);  // + pad = slot word
-                const double qd = kind == 2 ? __hiloint2double((int)head.w, (int)head.z) : 0.0;
-                const double guard = exact_mesh ? 2.0 : (double)__uint_as_float(head.y);
-                int cur = -1;         // pad of the run being summed
-                long long acc = 0;    // its charge so far
-                int pad[MESH_N];
+    // The unit's slice [u_first, u_first + u_count) of the event's run, all tracks together: the label of a key is
+    // the highest rank that touched it (atomicMax on the slot word), so points need no ordering.  Warps run freely:
+    // a warp that sees the table filling up raises s_flush, every warp notices at its next pass boundary and only
+    // then do they meet at a barrier (every barrier of this kernel is followed by the same uniform decision on
+    // s_flush, whichever call site a warp arrives from).
+    const int64_t run0 = pb.start[(int64_t)slot_event * pb.ranks];
+    const int end = u_first + u_count;
+    for (int p0 = u_first; p0 < end; p0 += POINTS_PER_ITER) {
+        const int w0 = p0 + warp * POINTS_PER_WARP;
+        if (w0 < end) {  // warp-uniform
+            const int pp = w0 + sub;
+            const bool have = sub < POINTS_PER_WARP && pp < end;
+            const int64_t p = base + run0 + (have ? pp : w0);
+            const uint4* rp = reinterpret_cast<const uint4*>(pb.rec + p * REC_WORDS);
+            uint4 head = __ldg(rp);
+            if (!have) head.x = 0u;
+            const unsigned r = __ldg(pb.rec + p * REC_WORDS + 14);  // rank of the point's track
+            const int kind = (int)(head.x >> 30), tb = (int)(head.x & 0x3FFFFFFFu);
+            const unsigned keybase = (((unsigned)tb << 15) + 1u) | (r << 28);  // + pad = slot word
+            const double qd = kind == 2 ? __hiloint2double((int)head.w, (int)head.z) : 0.0;
+            const double guard = exact_mesh ? 2.0 : (double)__uint_as_float(head.y);
+            int cur = -1;         // pad of the run being summed
+            long long acc = 0;    // its charge so far
+            int pad[MESH_N];
 #pragma unroll
-                for (int j = 0; j < MESH_N; ++j) pad[j] = -1;
-                if (kind != 0) {
-                    // pad-table row of this lane's mesh row, columns of the ten mesh columns (make_point)
-                    const uint4 cols = __ldg(rp + 1);
-                    const uint2 tail = __ldg(reinterpret_cast<const uint2*>(rp + 2));  // iy[8], iy[9] | ix[0], ix[1]
-                    const int ix = (int)__ldg(reinterpret_cast<const int16_t*>(rp) + 18 + row);
-                    const unsigned cw[5] = {cols.x, cols.y, cols.z, cols.w, tail.x};
-                    const int16_t* lut_row = P.lut + (int64_t)max(ix, 0) * P.lut_n;
-                    if (kind == 2) {
+            for (int j = 0; j < MESH_N; ++j) pad[j] = -1;
+            if (kind != 0) {
+                // pad-table row of this lane's mesh row, columns of the ten mesh columns (make_point)
+                const uint4 cols = __ldg(rp + 1);
+                const uint2 tail = __ldg(reinterpret_cast<const uint2*>(rp + 2));  // iy[8], iy[9] | ix[0], ix[1]
+                const int ix = (int)__ldg(reinterpret_cast<const int16_t*>(rp) + 18 + row);
+                const unsigned cw[5] = {cols.x, cols.y, cols.z, cols.w, tail.x};
+                const int16_t* lut_row = P.lut + (int64_t)max(ix, 0) * P.lut_n;
+                if (kind == 2) {
 #pragma unroll
-                        for (int j = 0; j < MESH_N; ++j) {  // all pad lookups first: independent loads in flight
-                            const int iy = (j & 1) ? (int)cw[j / 2] >> 16 : (int)(int16_t)(cw[j / 2] & 0xFFFFu);
-                            if (ix >= 0 && iy >= 0) pad[j] = (int)__ldg(lut_row + iy);
-                        }
-                    } else if (row == 0) {  // detector/transporter.py:123-169: all electrons on one pad
-                        const int iy = (int)(int16_t)(cw[0] & 0xFFFFu);
-                        if (ix >= 0 && iy >= 0) cur = (int)__ldg(lut_row + iy);
-                        acc = (long long)__hiloint2double((int)head.w, (int)head.z);
-                        n_dep += cur >= 0;
+                    for (int j = 0; j < MESH_N; ++j) {  // all pad lookups first: independent loads in flight
+                        const int iy = (j & 1) ? (int)cw[j / 2] >> 16 : (int)(int16_t)(cw[j / 2] & 0xFFFFu);
+                        if (ix >= 0 && iy >= 0) pad[j] = (int)__ldg(lut_row + iy);
                     }
+                } else if (row == 0) {  // detector/transporter.py:123-169: all electrons on one pad
+                    const int iy = (int)(int16_t)(cw[0] & 0xFFFFu);
+                    if (ix >= 0 && iy >= 0) cur = (int)__ldg(lut_row + iy);
+                    acc = (long long)__hiloint2double((int)head.w, (int)head.z);
+                    n_dep += cur >= 0;
                 }
-                // detector/transporter.py:240-246: int(pdf * step^2 * electrons).  pdf * step^2 is the constant mesh
-                // weight up to rounding (see make_point); the reference's own expression is evaluated only where the
-                // rounding could change the truncation -- rare, so the warp then takes a second copy of the loop.
-                unsigned risky = 0u;
-#pragma unroll
-                for (int j = 0; j < MESH_N; ++j) {
-                    const double v = __dmul_rn(wrow[j], qd);
-                    if (!(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v)) && pad[j] >= 0) risky |= 1u << j;
-                }
-                const double* g = pb.geom + p * GEOM_DOUBLES;
-                auto walk_row = [&](auto careful) {
-                    // j == MESH_N is the sentinel that pushes the last run of the row
-#pragma unroll
-                    for (int j = 0; j <= MESH_N; ++j) {
-                        const int pj = j < MESH_N ? pad[j] : -1;
-                        long long share = 0;  // (of a pixel without pad: added to a run that is never pushed)
-                        if (j < MESH_N) {
-                            share = (long long)__dmul_rn(wrow[j], qd);
-                            if (decltype(careful)::value) {
-                                if ((risky >> j) & 1u) share = exact_share(g, row, j);
-                            }
-                            n_dep += pj >= 0;
-                        }
-                        const bool change = pj != cur;
-                        const bool push = change && cur >= 0;
-                        const unsigned m = __ballot_sync(FULL, push);
-                        if (m) {  // warp-uniform
-                            if (push) {
-                                const unsigned at = (q_tail + __popc(m & lanes_below)) & (QUEUE_SLOTS - 1);
-                                qkey[at] = keybase + (unsigned)cur;
-                                qlo[at] = (unsigned)acc;
-                                qhi[at] = (unsigned)((unsigned long long)acc >> 32);
-                            }
-                            q_tail += __popc(m);
-                            if (q_tail - q_head >= 32u) drain(32u);
-                        }
-                        if (change) {
-                            cur = pj;
-                            acc = 0;
-                        }
-                        acc += share;
-                    }
-                };
-                if (__any_sync(FULL, risky != 0u)) walk_row(std::true_type{});
-                else walk_row(std::false_type{});
             }
-            publish_new_keys();
-            if (__syncthreads_or(s_nkeys > (unsigned)SMEM_SPILL_AT)) flush_to_global();
+            // detector/transporter.py:240-246: int(pdf * step^2 * electrons).  pdf * step^2 is the constant mesh
+            // weight up to rounding (see make_point); the reference's own expression is evaluated only where the
+            // rounding could change the truncation -- rare, so the warp then takes a second copy of the loop.
+            unsigned risky = 0u;
+#pragma unroll
+            for (int j = 0; j < MESH_N; ++j) {
+                const double v = __dmul_rn(wrow[j], qd);
+                if (!(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v)) && pad[j] >= 0) risky |= 1u << j;
+            }
+            const double* g = pb.geom + p * GEOM_DOUBLES;
+            auto walk_row = [&](auto careful) {
+                // j == MESH_N is the sentinel that pushes the last run of the row
+#pragma unroll
+                for (int j = 0; j <= MESH_N; ++j) {
+                    const int pj = j < MESH_N ? pad[j] : -1;
+                    long long share = 0;  // (of a pixel without pad: added to a run that is never pushed)
+                    if (j < MESH_N) {
+                        share = (long long)__dmul_rn(wrow[j], qd);
+                        if (decltype(careful)::value) {
+                            if ((risky >> j) & 1u) share = exact_share(g, row, j);
+                        }
+                        n_dep += pj >= 0;
+                    }
+                    const bool change = pj != cur;
+                    const bool push = change && cur >= 0;
+                    const unsigned m = __ballot_sync(FULL, push);
+                    if (m) {  // warp-uniform
+                        if (push) {
+                            const unsigned at = (q_tail + __popc(m & lanes_below)) & (QUEUE_SLOTS - 1);
+                            qkey[at] = keybase + (unsigned)cur;
+                            qlo[at] = (unsigned)acc;
+                            qhi[at] = (unsigned)((unsigned long long)acc >> 32);
+                        }
+                        q_tail += __popc(m);
+                        if (q_tail - q_head >= 32u) drain(32u);
+                    }
+                    if (change) {
+                        cur = pj;
+                        acc = 0;
+                    }
+                    acc += share;
+                }
+            };
+            if (__any_sync(FULL, risky != 0u)) walk_row(std::true_type{});
+            else walk_row(std::false_type{});
         }
-        // rank phases do not overlap: the rings are emptied, then plain stores of the label are race-free
-        while (q_tail != q_head) drain(min(32u, q_tail - q_head));
         publish_new_keys();
+        if (*(volatile unsigned*)&s_nkeys > (unsigned)SMEM_SPILL_AT) *(volatile unsigned*)&s_flush = 1u;
+        if (__any_sync(FULL, *(volatile unsigned*)&s_flush != 0u)) {
+            __syncthreads();
+            flush_to_global();
+        }
+    }
+    while (q_tail != q_head) drain(min(32u, q_tail - q_head));
+    publish_new_keys();
+    if (*(volatile unsigned*)&s_nkeys > (unsigned)SMEM_SPILL_AT) *(volatile unsigned*)&s_flush = 1u;
+    while (true) {
         __syncthreads();
-        if (s_nkeys > (unsigned)SMEM_SPILL_AT) flush_to_global();
+        if (*(volatile unsigned*)&s_flush == 0u) break;
+        flush_to_global();
     }
     if (shared_event || s_spilled) {
         flush_to_global();
