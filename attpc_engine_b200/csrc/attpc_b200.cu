@@ -351,7 +351,7 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         point_scan_kernel<<<(unsigned)ng, 1024, 0, sim->stream>>>(pb, gv, ctr);
         point_order_kernel<<<dim3((unsigned)std::max<int64_t>(1, sim->sm_count * 4 / ng), (unsigned)ng), 256, 0,
                              sim->stream>>>(sim->P, pb, gv, ctr);
-        zero_shared_tables_kernel<<<per_event, 256, 0, sim->stream>>>(gv, ctr);
+        CU(cudaMemsetAsync(sim->n_entries.p + gv.first_slot, 0, (size_t)gv.n_events * sizeof(unsigned), sim->stream));
         deposit_kernel<<<dim3((unsigned)sim->max_units, (unsigned)ng), DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES,
                          sim->stream>>>(sim->P, pb, gv, ctr);
         cudaEvent_t d1 = sim->mark();
@@ -359,7 +359,7 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         scan_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, ctr, sim->csr_total.p);
         emit_kernel<<<per_event, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
         cudaEvent_t f1 = sim->mark();
-        sim->launches += 7;
+        sim->launches += 6;
         dep_marks.push_back({d0, d1});
         fin_marks.push_back({d1, f1});
         if (fences) {

@@ -817,41 +817,17 @@ __device__ __forceinline__ void szudzik_unpair(unsigned key, unsigned& tb, unsig
 }
 
 // ------------------------------------------------------------------------------------------------- accumulate
-constexpr unsigned MAX_PROBES = 512u;
-__device__ __forceinline__ unsigned hash_slot(unsigned key, unsigned mask) { return (key * 2654435761u >> 7) & mask; }
-
 // points[id] = (charge + q, label) of detector/transporter.py:166-169, 247-249: integer adds commute and the label
 // is "last track in indices order", i.e. the maximum rank, so the result does not depend on thread order.
-__device__ __forceinline__ unsigned table_add(HashEntry* tab, unsigned mask, unsigned key, long long q, unsigned rank,
-                                              Counters* ctr) {
-    const unsigned key1 = key + 1u;
-    unsigned slot = hash_slot(key, mask);
-    const unsigned max_probe = min(mask, MAX_PROBES - 1u);  // a longer chain means the table is too full: grow it
-    for (unsigned probe = 0; probe <= max_probe; ++probe) {
-        unsigned k = __ldcg(&tab[slot].key1);
-        if (k == 0u) {
-            k = atomicCAS(&tab[slot].key1, 0u, key1);
-            if (k == 0u) k = key1;
-        }
-        if (k == key1) {
-            if (q != 0) atomicAdd(&tab[slot].charge, (unsigned long long)q);
-            if (__ldcg(&tab[slot].rank) < rank) atomicMax(&tab[slot].rank, rank);
-            return probe + 1u;
-        }
-        slot = (slot + 1u) & mask;
-    }
-    ctr->overflow_hash = 1;
-    return max_probe + 1u;
-}
-
 struct GroupView {
     int32_t first_slot;   // first event slot of the group inside the launch batch
     int32_t n_events;     // events in this group
     int32_t group;        // group index (selects the PointBuf region)
     int32_t hash_cap;     // entries per event region (power of two)
-    HashEntry* tables;    // [group_events][hash_cap]: dense entry list (mode 0) or open-addressing table (mode 1)
-    unsigned* n_entries;  // [launch events] entries of the dense list
-    unsigned* mode;       // [launch events] 0 = dense list, 1 = the event spilled to a global table
+    HashEntry* tables;    // [chunk events][hash_cap]: entry list of every event
+    unsigned* n_entries;  // [launch events] entries of the list (zeroed before the deposit kernel)
+    unsigned* mode;       // [launch events] 0 = every key once, 1 = a key may appear several times (the event was
+                          // deposited in several segments: dense event, or split over several units)
     int32_t exact_mesh;   // ATTPC_EXACT_MESH: every pixel through the reference's own expression (validation)
     int32_t group_events; // events per full group
     int32_t chunk_e0;     // first event of the group inside the chunk (row of `tables` and of the sort scratch)
@@ -1177,7 +1153,7 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, 2)
 deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk, Counters* ctr) {
     const GroupView gv = sub_group(chunk, blockIdx.y);
     extern __shared__ __align__(16) unsigned s_raw[];
-    __shared__ unsigned s_nkeys, s_out, s_spilled, s_flush;
+    __shared__ unsigned s_nkeys, s_out, s_flush, s_base;
     __shared__ unsigned s_qkey[DEPOSIT_WARPS][QUEUE_SLOTS], s_qlo[DEPOSIT_WARPS][QUEUE_SLOTS],
         s_qhi[DEPOSIT_WARPS][QUEUE_SLOTS];
     if ((int)blockIdx.x >= pb.n_units[gv.group]) return;
@@ -1191,9 +1167,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
     t.hi2 = s_raw + 2 * SMEM_SLOTS;
     const int slot_event = gv.first_slot + e;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool shared_event = gv.mode[slot_event] != 0u;  // several units: merge through the (pre-zeroed) global table
     HashEntry* region = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
-    const unsigned gmask = (unsigned)gv.hash_cap - 1u;
     const int64_t base = (int64_t)gv.group * pb.group_cap;
     constexpr int TABLE_VEC4 = (2 * SMEM_SLOTS + SMEM_SLOTS / 2) / 4;
     auto clear_table = [&]() {
@@ -1204,7 +1178,6 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
     if (threadIdx.x == 0) {
         s_nkeys = 0;
         s_out = 0;
-        s_spilled = 0;
         s_flush = 0;
     }
     __syncthreads();
@@ -1240,25 +1213,44 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
         n_new = 0;
     };
 
-    auto flush_to_global = [&]() {  // all threads
-        if (!shared_event && !s_spilled) {
-            for (int i = threadIdx.x; i < gv.hash_cap; i += blockDim.x) region[i] = HashEntry{0u, 0u, 0ULL};
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < SMEM_SLOTS; i += blockDim.x) {
-            const unsigned w = t.word[i];
-            if (w) {
-                const unsigned kc = (w & SMEM_KEY_MASK) - 1u;
-                table_add(region, gmask, kc, (long long)smem_charge_of(t, i), w >> 28, ctr);
+    // Append the table as one dense SEGMENT to the event's entry list and clear it (all threads, after a barrier that
+    // follows every warp's publish_new_keys).  The position comes from the event's entry counter, which the units
+    // of a split event share.  A key can then sit in several segments of the list: gv.mode marks such events and
+    // collect_kernel merges the copies after sorting (integer adds commute, the label is a maximum).
+    auto append_segment = [&](bool last) {
+        if (threadIdx.x == 0) {
+            s_base = atomicAdd(&gv.n_entries[slot_event], s_nkeys);
+            if (!last) {
+                gv.mode[slot_event] = 1u;
+                atomicAdd(&ctr->flushes, 1ULL);
             }
         }
+        __syncthreads();
+        const unsigned seg0 = s_base;
+        if (seg0 + s_nkeys > (unsigned)gv.hash_cap) {  // the list does not fit the event's region: the host grows it
+            if (threadIdx.x == 0) ctr->overflow_hash = 1;
+        } else {
+            const uint4* words = reinterpret_cast<const uint4*>(t.word);
+            for (int i = threadIdx.x; i < SMEM_SLOTS / 4; i += blockDim.x) {
+                const uint4 w4 = words[i];
+                const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
+                const unsigned cnt = (w4.x != 0u) + (w4.y != 0u) + (w4.z != 0u) + (w4.w != 0u);
+                if (cnt) {
+                    unsigned pos = seg0 + atomicAdd(&s_out, cnt);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (w[k])
+                            region[pos++] = HashEntry{w[k] & SMEM_KEY_MASK, w[k] >> 28, smem_charge_of(t, 4 * i + k)};
+                }
+            }
+        }
+        if (last) return;
         __syncthreads();
         clear_table();
         if (threadIdx.x == 0) {
             s_nkeys = 0;
-            s_spilled = 1;
+            s_out = 0;
             s_flush = 0;
-            atomicAdd(&ctr->flushes, 1ULL);
         }
         __syncthreads();
     };
@@ -1359,7 +1351,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
         if (*(volatile unsigned*)&s_nkeys > (unsigned)SMEM_SPILL_AT) *(volatile unsigned*)&s_flush = 1u;
         if (__any_sync(FULL, *(volatile unsigned*)&s_flush != 0u)) {
             __syncthreads();
-            flush_to_global();
+            append_segment(false);
         }
     }
     while (q_tail != q_head) drain(min(32u, q_tail - q_head));
@@ -1368,35 +1360,9 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
     while (true) {
         __syncthreads();
         if (*(volatile unsigned*)&s_flush == 0u) break;
-        flush_to_global();
+        append_segment(false);
     }
-    if (shared_event || s_spilled) {
-        flush_to_global();
-        if (threadIdx.x == 0) {
-            gv.mode[slot_event] = 1u;
-            gv.n_entries[slot_event] = 0u;
-        }
-    } else if (s_nkeys > (unsigned)gv.hash_cap) {  // the dense list does not fit the event's region: host grows it
-        if (threadIdx.x == 0) {
-            ctr->overflow_hash = 1;
-            gv.n_entries[slot_event] = 0u;
-        }
-    } else {
-        const uint4* words = reinterpret_cast<const uint4*>(t.word);
-        for (int i = threadIdx.x; i < SMEM_SLOTS / 4; i += blockDim.x) {
-            const uint4 w4 = words[i];
-            const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
-            const unsigned cnt = (w4.x != 0u) + (w4.y != 0u) + (w4.z != 0u) + (w4.w != 0u);
-            if (cnt) {
-                unsigned pos = atomicAdd(&s_out, cnt);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (w[k]) region[pos++] = HashEntry{w[k] & SMEM_KEY_MASK, w[k] >> 28, smem_charge_of(t, 4 * i + k)};
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) gv.n_entries[slot_event] = s_out;
-    }
+    append_segment(true);
     unsigned long long n_dep64 = n_dep, n_probe64 = n_probe;
     for (int o = 16; o > 0; o >>= 1) {
         n_dep64 += __shfl_xor_sync(FULL, n_dep64, o);
@@ -1406,16 +1372,6 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
         atomicAdd(&ctr->deposits, n_dep64);
         atomicAdd(&ctr->probes, n_probe64);
     }
-}
-
-// Zero the global tables of the events that are split over several units (before the deposit kernel merges into them).
-__global__ void __launch_bounds__(256) zero_shared_tables_kernel(GroupView chunk, const Counters* ctr) {
-    if (ctr->overflow_points) return;
-    const GroupView gv = sub_group(chunk, blockIdx.y);
-    const int e = blockIdx.x;
-    if (e >= gv.n_events || gv.mode[gv.first_slot + e] == 0u) return;
-    HashEntry* region = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
-    for (int i = threadIdx.x; i < gv.hash_cap; i += blockDim.x) region[i] = HashEntry{0u, 0u, 0ULL};
 }
 
 // ---------------------------------------------------------------------------------------------------- finalize
@@ -1475,7 +1431,7 @@ __device__ __forceinline__ uint64_t make_item(unsigned tb, unsigned pad, unsigne
 }
 
 // One CTA per event: gather the occupied slots that survive the time-bucket mask (detector/simulator.py:104-113)
-// and put them in canonical order: counting sort on the time bucket (exact, O(n)), then an insertion sort of each
+// and put them in canonical order: counting sort on the time bucket (exact, O(n)), then rank-by-counting inside each
 // bucket's handful of pads.  No power-of-two padding and no dependence on which thread found which slot.
 __global__ void __launch_bounds__(FINALIZE_THREADS)
 collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView chunk,
@@ -1502,7 +1458,8 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     }
     __syncthreads();
     unsigned occupied = 0;
-    const int limit = gv.mode[slot_event] ? gv.hash_cap : (int)gv.n_entries[slot_event];
+    const bool dup = gv.mode[slot_event] != 0u;  // the list may hold a key several times
+    const int limit = (int)min(gv.n_entries[slot_event], (unsigned)gv.hash_cap);
     for (int i = threadIdx.x; i < limit; i += blockDim.x) {
         const unsigned key1 = tab[i].key1;
         if (key1 == 0u) continue;
@@ -1519,7 +1476,7 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     __syncthreads();
     const int n = (int)s_n;
     if (threadIdx.x == 0) {
-        fa.kept[slot_event] = (unsigned)n;
+        fa.kept[slot_event] = (unsigned)n;  // (events with copies: corrected after the merge below)
         atomicAdd(&ctr->keys, (unsigned long long)s_keys);
     }
     if (n == 0) return;
@@ -1560,28 +1517,84 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
         buf[atomicAdd(&s_fill[bin], 1u)] = it;
     }
     __syncthreads();
-    // order every bucket: one warp per bucket, each lane ranks its items by counting the smaller ones (items are
-    // distinct, a bucket holds the few pads hit in one time bucket)
+    // order every bucket: one thread per item counts the smaller pads of its bucket (items are distinct; a bucket
+    // holds the pads hit in one time bucket, a handful for most tracks, so neighbouring threads walk the same few
+    // items and the reads are broadcasts)
     uint64_t* dst = in_smem ? sorted : stash;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int b = warp; b < TB_BINS; b += FINALIZE_THREADS / 32) {
-        const int lo = (int)s_hist[b], hi = (int)s_hist[b + 1];
-        const bool one_tb = b < TB_BINS - 1;  // all items of the bucket share the time bucket: compare pads only
-        for (int i = lo + lane; i < hi; i += 32) {
-            const uint64_t v = buf[i];
-            int rank = 0;
-            if (one_tb) {
-                const uint32_t vp = (uint32_t)(v >> 32);
-                for (int j = lo; j < hi; ++j) rank += (uint32_t)(buf[j] >> 32) < vp;
-            } else {
-                for (int j = lo; j < hi; ++j) rank += buf[j] < v;
-            }
-            dst[lo + rank] = v;
+    const uint32_t* key_words = reinterpret_cast<const uint32_t*>(buf) + 1;  // (tb << 15) | pad of item j at [2 j]
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t v = buf[i];
+        const unsigned bin = min((unsigned)(v >> 47), (unsigned)TB_BINS - 1u);
+        const int lo = (int)s_hist[bin], hi = (int)s_hist[bin + 1];
+        int rank = 0;
+        if (!dup && bin < (unsigned)TB_BINS - 1u) {  // all items of the bucket share the time bucket: compare pads only
+            const uint32_t vp = (uint32_t)(v >> 32);
+#pragma unroll 4
+            for (int j = lo; j < hi; ++j) rank += key_words[2 * j] < vp;
+        } else {  // whole items: copies of a key are ordered by their position in the list
+            for (int j = lo; j < hi; ++j) rank += buf[j] < v;
         }
+        dst[lo + rank] = v;
+    }
+    int n_final = n;
+    if (dup) {
+        // Copies of a key are now neighbours.  The first one becomes the row: it takes the summed charge and the
+        // highest rank (written into its own list entry, which emit_kernel reads), the others are dropped and the
+        // sequence is compacted in place, 256 items at a time.
+        HashEntry* wtab = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
+        __shared__ unsigned s_wsum[FINALIZE_THREADS / 32];
+        __shared__ unsigned s_done, s_prev_key;
+        if (threadIdx.x == 0) {
+            s_done = 0;
+            s_prev_key = 0xFFFFFFFFu;  // no item has this key word (time bucket < 1024)
+        }
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int start = 0; start < n; start += FINALIZE_THREADS) {
+            const int i = start + threadIdx.x;
+            uint64_t v = 0;
+            bool head = false;
+            if (i < n) {
+                v = dst[i];
+                const uint32_t kw = (uint32_t)(v >> 32);
+                const uint32_t before = threadIdx.x == 0 ? s_prev_key : (uint32_t)(dst[i - 1] >> 32);
+                head = kw != before;
+                if (head) {
+                    unsigned long long extra = 0;
+                    unsigned rank = wtab[(unsigned)v].rank;
+                    bool any = false;
+                    for (int j = i + 1; j < n && (uint32_t)(dst[j] >> 32) == kw; ++j) {
+                        const HashEntry other = wtab[(unsigned)dst[j]];
+                        extra += other.charge;
+                        rank = max(rank, other.rank);
+                        any = true;
+                    }
+                    if (any) {
+                        wtab[(unsigned)v].charge += extra;
+                        wtab[(unsigned)v].rank = rank;
+                    }
+                }
+            }
+            const unsigned heads = __ballot_sync(FULL, head);
+            if (lane == 0) s_wsum[warp] = __popc(heads);
+            __syncthreads();  // every read of this tile (and of its right neighbours) is done
+            unsigned pos = s_done + __popc(heads & ((1u << lane) - 1u));
+            for (int w = 0; w < warp; ++w) pos += s_wsum[w];
+            if (head) dst[pos] = v;
+            __syncthreads();
+            if (threadIdx.x == FINALIZE_THREADS - 1) {
+                unsigned total = pos + (head ? 1u : 0u);  // last thread: its prefix covers the whole tile
+                s_done = total;
+                if (i < n) s_prev_key = (uint32_t)(v >> 32);
+            }
+            __syncthreads();
+        }
+        n_final = (int)s_done;
+        if (threadIdx.x == 0) fa.kept[slot_event] = (unsigned)n_final;
     }
     if (!in_smem) {
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += blockDim.x) sorted[i] = stash[i];
+        for (int i = threadIdx.x; i < n_final; i += blockDim.x) sorted[i] = stash[i];
     }
 }
 
