@@ -977,6 +977,13 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
                 const long double ai = -3.0L + 6.0L * i / 9.0L, aj = -3.0L + 6.0L * j / 9.0L;
                 P.mesh_w[i * MESH_N + j] = (double)((2.0L / (9.0L * pi_l)) * expl(-(ai * ai + aj * aj) / 2.0L));
             }
+        // the distinct values of the table (the mesh is symmetric): what the per-point exactness test multiplies
+        P.n_mesh_w_unique = 0;
+        for (int k = 0; k < MESH_N * MESH_N; ++k) {
+            bool seen = false;
+            for (int u = 0; u < P.n_mesh_w_unique; ++u) seen = seen || P.mesh_w_unique[u] == P.mesh_w[k];
+            if (!seen) P.mesh_w_unique[P.n_mesh_w_unique++] = P.mesh_w[k];
+        }
     }
     P.lut = sim->lut.p;
     P.tables = sim->tables.p;

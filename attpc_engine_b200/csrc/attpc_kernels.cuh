@@ -63,6 +63,8 @@ struct SimParams {
     const double* resp_prefix;   // prefix sums of resp_sorted, [n_response + 1]
     double resp_max;
     double mesh_w[MESH_N * MESH_N];  // (2 / (9 pi)) exp(-(a_i^2 + a_j^2) / 2), a_i = -3 + 6 i / 9: pdf * step^2 of the mesh
+    double mesh_w_unique[MESH_N * MESH_N];  // its distinct values (15 for the symmetric 10 x 10 mesh)
+    int32_t n_mesh_w_unique, pad1;
 };
 
 // Active track points (>= 1 electron).  The track kernels append them per event group in arrival order and number
@@ -976,7 +978,9 @@ __device__ __forceinline__ int lut_index(const SimParams& P, double coord_m) {
 }
 
 // Record of one ordered point as the deposit kernel reads it (64 B):
-//   word 0      time bucket | kind << 30   (kind 0: nothing, 1: single deposit, 2: 10x10 mesh)
+//   word 0      time bucket | careful << 29 | kind << 30   (kind 0: nothing, 1: single deposit, 2: 10x10 mesh;
+//               careful: some pixel's share is so close to an integer that the table weight might round it differently
+//               from the reference's expression -- the deposit kernel then tests every pixel of the point)
 //   word 1      guard as float, rounded up
 //   words 2-3   electrons after gain as double
 //   words 4-8   int16 iy[10]: pad-table column of mesh column j (-1 = outside), kind 1: iy[0] of the point itself
@@ -985,7 +989,7 @@ __device__ __forceinline__ int lut_index(const SimParams& P, double coord_m) {
 constexpr int REC_WORDS = 16;
 
 __device__ __forceinline__ void make_point(const SimParams& P, double cx, double cy, double time, long long q,
-                                           double* g, uint32_t* rec) {
+                                           bool exact_mesh, double* g, uint32_t* rec) {
     g[0] = cx;
     g[1] = cy;
     g[10] = (double)q;
@@ -1015,7 +1019,17 @@ __device__ __forceinline__ void make_point(const SimParams& P, double cx, double
     const double big = fmax(fabs(cx), fabs(cy)) + three_sigma;
     g[9] = 2.0 * (24.0 * big / sigma + 220.0) * MESH_GUARD_U;
     rec[0] = (uint32_t)tb | (2u << 30);
-    rec[1] = __float_as_uint(__double2float_ru(g[9]));
+    const float guard_f = __double2float_ru(g[9]);
+    rec[1] = __float_as_uint(guard_f);
+    // can the constant-weight shortcut change any of the 100 truncations of this point?  (same test, same operands
+    // as the deposit kernel's per-pixel one, on the distinct weights)
+    bool careful = exact_mesh;
+    const double guard = (double)guard_f;
+    for (int k = 0; k < P.n_mesh_w_unique; ++k) {
+        const double v = __dmul_rn(P.mesh_w_unique[k], g[10]);
+        careful = careful || !(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v));
+    }
+    if (careful) rec[0] |= 1u << 29;
 #pragma unroll
     for (int a = 0; a < MESH_N; ++a) {
         const double px = (a == MESH_N - 1) ? g[3] : __dadd_rn(g[2], __dmul_rn((double)a, g[4]));
@@ -1056,7 +1070,7 @@ __global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant_
         uint32_t rec[REC_WORDS];
 #pragma unroll
         for (int k = 0; k < GEOM_DOUBLES; ++k) g[k] = 0.0;
-        make_point(P, pb.x[i], pb.y[i], pb.t[i], pb.q[i], g, rec);
+        make_point(P, pb.x[i], pb.y[i], pb.t[i], pb.q[i], gv.exact_mesh != 0, g, rec);
         rec[14] = (uint32_t)pb.rank[i];
         double2* out = reinterpret_cast<double2*>(pb.geom + d * GEOM_DOUBLES);
 #pragma unroll
@@ -1272,7 +1286,8 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
             uint4 head = __ldg(rp);
             if (!have) head.x = 0u;
             const unsigned r = __ldg(pb.rec + p * REC_WORDS + 14);  // rank of the point's track
-            const int kind = (int)(head.x >> 30), tb = (int)(head.x & 0x3FFFFFFFu);
+            const int kind = (int)(head.x >> 30), tb = (int)(head.x & 0x1FFFFFFFu);
+            const bool careful_point = (head.x >> 29) & 1u;
             const unsigned keybase = (((unsigned)tb << 15) + 1u) | (r << 28);  // + pad = slot word
             const double qd = kind == 2 ? __hiloint2double((int)head.w, (int)head.z) : 0.0;
             const double guard = exact_mesh ? 2.0 : (double)__uint_as_float(head.y);
@@ -1305,10 +1320,13 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
             // weight up to rounding (see make_point); the reference's own expression is evaluated only where the
             // rounding could change the truncation -- rare, so the warp then takes a second copy of the loop.
             unsigned risky = 0u;
+            const bool careful_warp = __any_sync(FULL, careful_point);
+            if (careful_warp && careful_point) {
 #pragma unroll
-            for (int j = 0; j < MESH_N; ++j) {
-                const double v = __dmul_rn(wrow[j], qd);
-                if (!(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v)) && pad[j] >= 0) risky |= 1u << j;
+                for (int j = 0; j < MESH_N; ++j) {
+                    const double v = __dmul_rn(wrow[j], qd);
+                    if (!(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v)) && pad[j] >= 0) risky |= 1u << j;
+                }
             }
             const double* g = pb.geom + p * GEOM_DOUBLES;
             auto walk_row = [&](auto careful) {
@@ -1344,7 +1362,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
                     acc += share;
                 }
             };
-            if (__any_sync(FULL, risky != 0u)) walk_row(std::true_type{});
+            if (careful_warp && __any_sync(FULL, risky != 0u)) walk_row(std::true_type{});
             else walk_row(std::false_type{});
         }
         publish_new_keys();
@@ -1513,8 +1531,7 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     uint64_t* buf = in_smem ? s_items : sorted;  // bucketed, unordered inside a bucket
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint64_t it = stash[i];
-        const unsigned bin = min((unsigned)(it >> 47), (unsigned)TB_BINS - 1u);
-        buf[atomicAdd(&s_fill[bin], 1u)] = it;
+        buf[atomicAdd(&s_fill[min((unsigned)(it >> 47), (unsigned)TB_BINS - 1u)], 1u)] = it;
     }
     __syncthreads();
     // order every bucket: one thread per item counts the smaller pads of its bucket (items are distinct; a bucket
@@ -1527,7 +1544,7 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
         const unsigned bin = min((unsigned)(v >> 47), (unsigned)TB_BINS - 1u);
         const int lo = (int)s_hist[bin], hi = (int)s_hist[bin + 1];
         int rank = 0;
-        if (!dup && bin < (unsigned)TB_BINS - 1u) {  // all items of the bucket share the time bucket: compare pads only
+        if (!dup) {  // distinct keys: compare the (time bucket, pad) words only
             const uint32_t vp = (uint32_t)(v >> 32);
 #pragma unroll 4
             for (int j = lo; j < hi; ++j) rank += key_words[2 * j] < vp;
