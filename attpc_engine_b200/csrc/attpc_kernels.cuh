@@ -1413,9 +1413,12 @@ struct FinalizeArgs {
     double* cloud;            // [out_cap, 3]
     int64_t* labels;          // [out_cap]
     int64_t out_cap;
-    // optional columnar copy of the same rows in their natural types (19 B instead of 32 B per row on the wire)
+    // optional columnar copy of the same rows in their natural types (17 B instead of 32 B per row on the wire).
+    // time bucket + wiggle = col_tb_bucket + col_tb_offset exactly for the library's own 24-bit wiggle; a replayed
+    // 53-bit uniform is rounded to float32 in the offset column (replay tests read the float64 cloud).
     int16_t* col_pad;
-    double* col_tb;
+    int16_t* col_tb_bucket;
+    float* col_tb_offset;
     int64_t* col_electrons;
     int8_t* col_label;
 };
@@ -1435,7 +1438,7 @@ __device__ __forceinline__ double wiggle_of(const FinalizeArgs& fa, int slot_eve
         ctr->replay_miss = 1;
         return 0.0;
     }
-    return philox_uniform(fa.seed, (uint64_t)(fa.first_event + slot_event), STREAM_WIGGLE, key);
+    return philox_uniform24(fa.seed, (uint64_t)(fa.first_event + slot_event), STREAM_WIGGLE, key);
 }
 
 constexpr int FINALIZE_THREADS = 256;
@@ -1665,7 +1668,8 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
         const unsigned tb = (unsigned)(it >> 47), pad = (unsigned)(it >> 32) & 0x7FFFu;
         const unsigned key = szudzik_pair(tb, pad);
         const HashEntry en = tab[(unsigned)it];
-        const double tbf = (double)tb + wiggle_of(fa, slot_event, key, ctr);
+        const double u = wiggle_of(fa, slot_event, key, ctr);
+        const double tbf = (double)tb + u;
         double* row = fa.cloud + (off + i) * 3;
         row[0] = (double)pad;
         row[1] = tbf;
@@ -1676,7 +1680,8 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
         fa.labels[off + i] = label;
         if (fa.col_pad) {
             fa.col_pad[off + i] = (int16_t)pad;
-            fa.col_tb[off + i] = tbf;
+            fa.col_tb_bucket[off + i] = (int16_t)tb;
+            fa.col_tb_offset[off + i] = (float)u;
             fa.col_electrons[off + i] = (long long)en.charge;
             fa.col_label[off + i] = (int8_t)label;
         }
