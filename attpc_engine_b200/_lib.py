@@ -49,6 +49,8 @@ class AttpcConfig(C.Structure):
         ("max_events_per_launch", C.c_int32),
         ("hash_capacity", C.c_int32),
         ("copy_events_per_launch", C.c_int32),
+        ("unit_points", C.c_int32),
+        ("table_spill_keys", C.c_int32),
     ]
 
 
@@ -115,6 +117,8 @@ class AttpcResult(C.Structure):
         ("n_rk_steps", C.c_int64),
         ("n_rk_rejects", C.c_int64),
         ("max_track_passes", C.c_int64),
+        ("ms_order", C.c_float),
+        ("reserved2", C.c_float),
     ]
 
 

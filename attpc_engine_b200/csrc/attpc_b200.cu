@@ -95,6 +95,8 @@ struct AttpcSim {
     int32_t copy_launch_events = 2048;
     int32_t group_events = 2048;
     int32_t chunk_groups = 16;  // groups per kernel launch when the rows stay on the device
+    int32_t unit_points = UNIT_POINTS;     // test knobs (AttpcConfig.unit_points / table_spill_keys)
+    int32_t spill_keys = SMEM_SPILL_AT;
     int32_t hash_cap = 16384;
     int64_t group_point_cap = 0;
 
@@ -224,7 +226,7 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     }
     CU(sim->geom.reserve(pts * GEOM_DOUBLES));
     CU(sim->rec.reserve(pts * REC_WORDS));
-    sim->max_units = (int32_t)(sim->group_events + sim->group_point_cap / UNIT_POINTS + 1);
+    sim->max_units = (int32_t)(sim->group_events + sim->group_point_cap / sim->unit_points + 1);
     CU(sim->unit_event.reserve(n_groups * sim->max_units));
     CU(sim->unit_first.reserve(n_groups * sim->max_units));
     CU(sim->unit_count.reserve(n_groups * sim->max_units));
@@ -280,6 +282,7 @@ PointBuf point_buf(AttpcSim* sim, int which) {
     pb.unit_order = sim->unit_order.p;
     pb.n_units = sim->n_units.p;
     pb.max_units = sim->max_units;
+    pb.unit_points = sim->unit_points;
     pb.group_cap = sim->group_point_cap;
     pb.group_events = sim->group_events;
     pb.ranks = sim->ranks;
@@ -322,6 +325,7 @@ struct ChunkFence {
 };
 
 int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
+               std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& ord_marks,
                std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& dep_marks,
                std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& fin_marks, int groups_per_chunk,
                std::vector<ChunkFence>* fences) {
@@ -349,12 +353,14 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         gv.exact_mesh = (fa.flags & ATTPC_EXACT_MESH) ? 1 : 0;
         gv.group_events = sim->group_events;
         gv.chunk_e0 = 0;
+        gv.spill_keys = sim->spill_keys;
         const dim3 per_event((unsigned)std::min<int64_t>(sim->group_events, gv.n_events), (unsigned)ng);
         cudaEvent_t d0 = sim->mark();
         point_scan_kernel<<<(unsigned)ng, 1024, 0, sim->stream>>>(pb, gv, ctr);
         point_order_kernel<<<dim3((unsigned)std::max<int64_t>(1, sim->sm_count * 4 / ng), (unsigned)ng), 256, 0,
                              sim->stream>>>(sim->P, pb, gv, ctr);
         CU(cudaMemsetAsync(sim->n_entries.p + gv.first_slot, 0, (size_t)gv.n_events * sizeof(unsigned), sim->stream));
+        cudaEvent_t k0 = sim->mark();
         deposit_kernel<<<dim3((unsigned)sim->max_units, (unsigned)ng), DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES,
                          sim->stream>>>(sim->P, pb, gv, ctr);
         cudaEvent_t d1 = sim->mark();
@@ -363,7 +369,8 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         emit_kernel<<<per_event, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
         cudaEvent_t f1 = sim->mark();
         sim->launches += 6;
-        dep_marks.push_back({d0, d1});
+        ord_marks.push_back({d0, k0});
+        dep_marks.push_back({k0, d1});
         fin_marks.push_back({d1, f1});
         if (fences) {
             const int slot = (int)fences->size();
@@ -506,7 +513,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     CU(cudaStreamWaitEvent(C, t_begin, 0));
 
     const int64_t n_launch = n_events > 0 ? (n_events + launch_cap - 1) / launch_cap : 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trk_marks(n_launch), dep_marks, fin_marks, copy_marks;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> trk_marks(n_launch), ord_marks, dep_marks, fin_marks, copy_marks;
     std::vector<cudaEvent_t> track_done(n_launch);
     Counters totals;
     memset(&totals, 0, sizeof totals);
@@ -589,8 +596,10 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         }
         CU(cudaStreamWaitEvent(G, track_done[i], 0));
         const size_t dep_before = dep_marks.size(), fin_before = fin_marks.size(), copy_before = copy_marks.size();
+        const size_t ord_before = ord_marks.size();
         std::vector<ChunkFence> fences;
-        rc = run_groups(sim, nb, fa, which, dep_marks, fin_marks, groups_per_chunk, copy_host ? &fences : nullptr);
+        rc = run_groups(sim, nb, fa, which, ord_marks, dep_marks, fin_marks, groups_per_chunk,
+                        copy_host ? &fences : nullptr);
         if (rc) return rc;
         publish_kernel<<<1, 1, 0, G>>>(ls.counters.p, sim->csr_total.p, ls.counters_host.p, sim->csr_host.p);
         sim->launches += 1;
@@ -647,6 +656,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         if (now.overflow_charge)
             return sim->fail(ATTPC_E_CAPACITY, "a (pad, time bucket) charge exceeded 2^48 electrons");
         if (now.overflow_points || now.overflow_hash || now.overflow_out) {
+            ord_marks.resize(ord_before);
             dep_marks.resize(dep_before);
             fin_marks.resize(fin_before);
             copy_marks.resize(copy_before);
@@ -754,6 +764,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     cudaEvent_t t_end = sim->mark(G);
     CU(cudaStreamSynchronize(G));
     res->ms_tracks = sum_ms(trk_marks);
+    res->ms_order = sum_ms(ord_marks);
     res->ms_deposit = sum_ms(dep_marks);
     res->ms_finalize = sum_ms(fin_marks);
     res->ms_d2h = sum_ms(copy_marks);
@@ -906,6 +917,8 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
     if (cfg->max_events_per_launch > 0) sim->launch_events = cfg->max_events_per_launch;
     if (cfg->copy_events_per_launch > 0) sim->copy_launch_events = cfg->copy_events_per_launch;  // events per launch when rows go to the host
     if (cfg->hash_capacity > 0) sim->hash_cap = next_pow2(cfg->hash_capacity);
+    if (cfg->unit_points > 0) sim->unit_points = std::min<int32_t>(cfg->unit_points, UNIT_POINTS);
+    if (cfg->table_spill_keys > 0) sim->spill_keys = std::min<int32_t>(cfg->table_spill_keys, SMEM_SPILL_AT);
     sim->group_events = std::min(sim->group_events, sim->launch_events);
     if (const char* env = getenv("ATTPC_CHUNK_GROUPS")) sim->chunk_groups = std::max(1, atoi(env));  // tuning aid
 

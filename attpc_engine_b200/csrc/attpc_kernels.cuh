@@ -93,6 +93,7 @@ struct PointBuf {
     int32_t group_events;
     int32_t ranks;      // tracks per event
     int32_t max_units;  // capacity of the unit arrays per group
+    int32_t unit_points;  // longest slice of one event handled by one CTA of the deposit kernel (<= UNIT_POINTS)
 };
 
 // Per-launch counters (one set per in-flight launch; zeroed when the launch starts).
@@ -833,6 +834,7 @@ struct GroupView {
     int32_t exact_mesh;   // ATTPC_EXACT_MESH: every pixel through the reference's own expression (validation)
     int32_t group_events; // events per full group
     int32_t chunk_e0;     // first event of the group inside the chunk (row of `tables` and of the sort scratch)
+    int32_t spill_keys;   // keys in a CTA's shared-memory table that trigger a segment append (<= SMEM_SPILL_AT)
 };
 
 // The host describes a CHUNK of consecutive groups (first_slot / group / n_events of the whole chunk) and launches
@@ -898,7 +900,8 @@ __global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView
         unsigned pts = 0;
         if (e < gv.n_events)
             for (int r = 0; r < pb.ranks; ++r) pts += pb.cnt[first + (int64_t)e * pb.ranks + r];
-        const unsigned nu = e < gv.n_events ? max(1u, (pts + UNIT_POINTS - 1) / UNIT_POINTS) : 0u;
+        const unsigned up = (unsigned)pb.unit_points;
+        const unsigned nu = e < gv.n_events ? max(1u, (pts + up - 1u) / up) : 0u;
         s_part[tid] = nu;
         __syncthreads();
         for (int o = 1; o < 1024; o <<= 1) {
@@ -914,8 +917,8 @@ __global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView
                 const unsigned u = u0 + k;
                 if (u < (unsigned)pb.max_units) {
                     u_event[u] = e;
-                    u_first[u] = (int32_t)(k * UNIT_POINTS);
-                    u_count[u] = (int32_t)min((unsigned)UNIT_POINTS, pts - min(pts, k * UNIT_POINTS));
+                    u_first[u] = (int32_t)(k * up);
+                    u_count[u] = (int32_t)min(up, pts - min(pts, k * up));
                 }
             }
         }
@@ -1366,7 +1369,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
             else walk_row(std::false_type{});
         }
         publish_new_keys();
-        if (*(volatile unsigned*)&s_nkeys > (unsigned)SMEM_SPILL_AT) *(volatile unsigned*)&s_flush = 1u;
+        if (*(volatile unsigned*)&s_nkeys > (unsigned)gv.spill_keys) *(volatile unsigned*)&s_flush = 1u;
         if (__any_sync(FULL, *(volatile unsigned*)&s_flush != 0u)) {
             __syncthreads();
             append_segment(false);
@@ -1374,7 +1377,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
     }
     while (q_tail != q_head) drain(min(32u, q_tail - q_head));
     publish_new_keys();
-    if (*(volatile unsigned*)&s_nkeys > (unsigned)SMEM_SPILL_AT) *(volatile unsigned*)&s_flush = 1u;
+    if (*(volatile unsigned*)&s_nkeys > (unsigned)gv.spill_keys) *(volatile unsigned*)&s_flush = 1u;
     while (true) {
         __syncthreads();
         if (*(volatile unsigned*)&s_flush == 0u) break;

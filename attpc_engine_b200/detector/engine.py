@@ -130,7 +130,7 @@ _STAT_FIELDS = (
     "n_tracks", "n_trajectory_points", "n_active_points", "n_primary_electrons", "n_deposits", "n_keys",
     "ms_h2d", "ms_tracks", "ms_deposit", "ms_finalize", "ms_d2h", "ms_total", "n_kernel_launches", "n_retries",
     "n_track_launches", "n_group_launches", "n_hash_probes", "hash_capacity", "n_table_flushes",
-    "n_rk_steps", "n_rk_rejects", "max_track_passes",
+    "n_rk_steps", "n_rk_rejects", "max_track_passes", "ms_order",
 )  # fmt: skip
 
 
@@ -148,6 +148,8 @@ class Engine:
         max_events_per_launch: int = 0,
         hash_capacity: int = 0,
         copy_events_per_launch: int = 0,
+        unit_points: int = 0,
+        table_spill_keys: int = 0,
     ):
         if config.pad_grid is None or config.pad_grid_edges is None:
             raise ValueError("Pad grid is not loaded")  # solver.py:400-401
@@ -196,6 +198,8 @@ class Engine:
         cfg.max_events_per_launch = int(max_events_per_launch)
         cfg.hash_capacity = int(hash_capacity)
         cfg.copy_events_per_launch = int(copy_events_per_launch)
+        cfg.unit_points = int(unit_points)
+        cfg.table_spill_keys = int(table_spill_keys)
 
         sp = (_lib.AttpcSpecies * len(self.species))()
         for i, (nuc, tab) in enumerate(zip(self.species, tables)):

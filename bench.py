@@ -242,7 +242,7 @@ def run_ours(args):
     config, momenta, vertices, zs, as_, indices = build_workload(args.workload, B, seed_offset=rank)
     K = momenta.shape[1]
     eng = engine_for(config, _nuclei_for(zs, as_, indices, nuclear_map), device=local,
-                     max_events_per_launch=args.launch_events)  # fmt: skip
+                     max_events_per_launch=args.launch_events, copy_events_per_launch=args.copy_events)  # fmt: skip
     # pinned host inputs (e2e) and device-resident inputs (value)
     mom_pin = torch.from_numpy(momenta).pin_memory()
     vtx_pin = torch.from_numpy(vertices).pin_memory()
@@ -315,9 +315,9 @@ def run_ours(args):
     if rank != 0:
         return
     peak, peak_src = measured_peak_hbm()
-    # dominant kernel by device time
-    stage_ms = {"track_kernel": stats_sum["ms_tracks"], "deposit_kernel": stats_sum["ms_deposit"],
-                "finalize (collect+scan+emit)": stats_sum["ms_finalize"]}  # fmt: skip
+    # dominant kernel by device time (CUDA events recorded by the library around each stage, on its own stream)
+    stage_ms = {"track_kernel": stats_sum["ms_tracks"], "point_scan+point_order": stats_sum["ms_order"],
+                "deposit_kernel": stats_sum["ms_deposit"], "finalize (collect+scan+emit)": stats_sum["ms_finalize"]}  # fmt: skip
     dominant = max(stage_ms, key=stage_ms.get)
     n_ev_rank = B * args.steps
     n_out = stats_sum["n_points"] / n_ev_rank
@@ -326,12 +326,26 @@ def run_ours(args):
     events_per_launch = n_ev_rank / launches_dom
     avg_launch_ms = stage_ms[dominant] / launches_dom
     achieved = bytes_per_event * events_per_launch / (avg_launch_ms * 1e-3) / 1e9
+    # DRAM traffic of the same kernel from the committed `ncu --set full` capture (profiles/traffic.json, written by
+    # tools/ncu_summary.py): dram__bytes_read.sum + dram__bytes_write.sum per launch, scaled to this launch size
+    traffic, traffic_note = None, "no ncu capture committed for this kernel"
+    tj = ROOT / "profiles" / "traffic.json"
+    if tj.exists():
+        try:
+            rec = json.loads(tj.read_text()).get(dominant)
+            if rec and rec.get("workload") == args.workload:
+                traffic = round(rec["dram_bytes_per_launch"] * events_per_launch / rec["events_per_launch"] / 1e9, 4)
+                traffic_note = (f"GB per launch; {rec['source']}: {rec['dram_bytes_per_launch'] / 1e9:.3f} GB for "
+                                f"{rec['events_per_launch']} events; issue slots busy {rec.get('issue_active_pct')} %")
+        except Exception as exc:  # a malformed file must not break the benchmark
+            traffic_note = f"profiles/traffic.json unreadable: {exc}"
     roofline = {
         "kernel": dominant, "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 6), "traffic": None, "peak_source": peak_src,
+        "frac": round(achieved / peak, 6), "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
         "bytes_per_event": round(bytes_per_event, 1), "events_per_launch": round(events_per_launch, 1),
         "avg_launch_ms": round(avg_launch_ms, 4),
-        "note": "path is issue/atomic bound, not HBM bound (SURVEY.md 8d); see profiles/ for ncu issue utilisation",
+        "note": "path is instruction-issue / shared-memory-atomic bound, not HBM bound (SURVEY.md 8d); profiles/ holds "
+                "the ncu issue-slot utilisation of every kernel",
         "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage_ms.items()},
     }  # fmt: skip
     out = {
@@ -424,6 +438,7 @@ def main():
     ap.add_argument("--workload", default="c16dd", choices=sorted(WORKLOADS))
     ap.add_argument("--events", type=int, default=32768, help="events per GPU per step")
     ap.add_argument("--launch-events", type=int, default=0, help="events per track-kernel launch (0 = library default)")
+    ap.add_argument("--copy-events", type=int, default=0, help="events per host-copy chunk (0 = library default)")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--cpu-events-per-core", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

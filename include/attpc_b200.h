@@ -73,6 +73,9 @@ typedef struct AttpcConfig {
     int32_t max_events_per_launch;
     int32_t hash_capacity;          /* slots per event, power of two */
     int32_t copy_events_per_launch; /* events per host-copy chunk: rows are copied while later groups compute */
+    /* stress knobs for tests (0 = library default; values above the default are clamped): results never depend on them */
+    int32_t unit_points;            /* points of one event handled by one CTA of the deposit kernel (default 1024) */
+    int32_t table_spill_keys;       /* keys in a CTA's shared-memory table that trigger an append to the event's list */
 } AttpcConfig;
 
 /* One ion species: the dE/dx table of attpc_engine_b200/target.py:DedxTable (pseudo-log grid). */
@@ -139,6 +142,9 @@ typedef struct AttpcResult {
     int64_t n_rk_steps;          /* Dormand-Prince steps tried (accepted + rejected) */
     int64_t n_rk_rejects;        /* of which rejected by the error control */
     int64_t max_track_passes;    /* most step/emit passes any single track needed: the serial critical path */
+    float ms_order;              /* device time of the point ordering kernels (scan + scatter) before the deposit kernel;
+                                    ms_deposit is the deposit kernel alone */
+    float reserved2;
 } AttpcResult;
 
 typedef struct AttpcSim AttpcSim;

@@ -78,6 +78,24 @@ def test_small_launches_and_small_tables_give_identical_results(dist):
     assert np.array_equal(base.labels, tiny.labels)
 
 
+@pytest.mark.parametrize("name, n", [("c16dd", 96), ("c12aa", 48), ("sn132dp", 48)])
+def test_work_splitting_is_invisible(dist, name, n):
+    """Events split over many deposit CTAs (tiny work units) and tables appended to the entry list in many segments
+    (tiny spill threshold) give the same rows, charges and labels: copies of a key are merged after sorting."""
+    if name in ("c16dd", "c12aa"):
+        cfg, m, v, zs, as_, idx = _workload(dist, name, n)
+    else:
+        import bench
+
+        cfg, m, v, zs, as_, idx = bench.build_workload(name, n)
+    base = simulate_batch(m, v, zs, as_, cfg, 9, idx)
+    for tuning in (dict(unit_points=48), dict(table_spill_keys=150), dict(unit_points=96, table_spill_keys=400)):
+        split = simulate_batch(m, v, zs, as_, cfg, 9, idx, **tuning)
+        assert np.array_equal(base.offsets, split.offsets), tuning
+        assert np.array_equal(base.cloud, split.cloud) and np.array_equal(base.labels, split.labels), tuning
+    assert split.stats["n_table_flushes"] > n  # the stress really went through the segment path
+
+
 def test_convert_to_spyral_function_matches_oracle(golden_events):
     ev, name = golden_events, "alpha_breakup"
     cfg = case_config(name)

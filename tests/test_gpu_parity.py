@@ -15,14 +15,14 @@ pytestmark = pytest.mark.gpu
 CHARGE_RTOL = 1e-6  # north_star tolerance for charges; pad / tb / key must be exact
 
 
-def _replay(ev, name, **kw):
+def _replay(ev, name, tuning=None, **kw):
     from attpc_engine_b200.detector.engine import engine_for
 
     cfg = case_config(name)
     tracks = case_tracks(ev, name)
     if not tracks:
         pytest.skip("no charged track")
-    eng = engine_for(cfg, nuclei_of(tracks))
+    eng = engine_for(cfg, nuclei_of(tracks), **(tuning or {}))
     batch, electrons = eng.simulate_replay(
         [t["rows"] for t in tracks], [t["normals"] for t in tracks], [0] * len(tracks),
         [t["rank"] for t in tracks], [t["idx"] for t in tracks], [t["za"] for t in tracks], 1,
@@ -39,11 +39,12 @@ def test_electrons_bit_exact(golden_events, name):
         assert np.array_equal(got, t["electrons"])
 
 
+@pytest.mark.parametrize("tuning", [None, dict(unit_points=40, table_spill_keys=120)], ids=["default", "stress-split"])
 @pytest.mark.parametrize("name", case_names())
-def test_dict_keys_charges_labels(golden_events, name):
+def test_dict_keys_charges_labels(golden_events, name, tuning):
     """The (pad, tb) -> (charge, label) map after all tracks (`transporter.py:252-317`)."""
     ev = golden_events
-    _, _, batch, _ = _replay(ev, name, keep_all_tb=True)
+    _, _, batch, _ = _replay(ev, name, tuning=tuning, keep_all_tb=True)
     cloud, labels = batch.event(0)
     tb, pad = unpair(ev[f"{name}/keys"])
     order = np.lexsort((pad, tb))  # canonical order of the CUDA path: ascending (time bucket, pad)
@@ -56,11 +57,16 @@ def test_dict_keys_charges_labels(golden_events, name):
     assert np.array_equal(cloud[:, 1], np.floor(cloud[:, 1]) + ev[f"{name}/uniforms"][order])
 
 
+# default work split, and a stress split: each event over many deposit CTAs, each CTA's table appended in many segments
+SPLITS = [None, dict(unit_points=40, table_spill_keys=120)]
+
+
+@pytest.mark.parametrize("tuning", SPLITS, ids=["default", "stress-split"])
 @pytest.mark.parametrize("name", case_names())
-def test_simulate_cloud(golden_events, name):
+def test_simulate_cloud(golden_events, name, tuning):
     """Final `simulate` output (`simulator.py:104-115`), compared in canonical key order."""
     ev = golden_events
-    _, _, batch, _ = _replay(ev, name)
+    _, _, batch, _ = _replay(ev, name, tuning=tuning)
     cloud, labels = batch.event(0)
     want_cloud, want_labels = sort_cloud(ev[f"{name}/cloud"], ev[f"{name}/labels"])
     assert cloud.shape == want_cloud.shape

@@ -47,6 +47,9 @@ def launches():
         print(f"{k[:70]:70s} n={v[0]:4d} total={v[1]:10.1f} us avg={v[1] / v[0]:9.1f} us share={v[1] / tot * 100:5.1f}%")
 
 
+TRAFFIC = {}
+
+
 def reports():
     for rep in sorted(OUT.glob("prof_*.ncu-rep")):
         txt = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -55,6 +58,19 @@ def reports():
             continue
         h, units = rows[0], rows[1]
         print(f"== {rep.name}: {rows[2][h.index('Kernel Name')][:90]}")
+        try:
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            rd, wr = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+            total = float(rows[2][rd].replace(",", "")) * scale[units[rd]] + float(rows[2][wr].replace(",", "")) * scale[units[wr]]
+            name = rep.name[len("prof_"):-len(".ncu-rep")]
+            TRAFFIC[name] = {
+                "dram_bytes_per_launch": total,
+                "duration_us": rows[2][h.index("gpu__time_duration.sum")] + " " + units[h.index("gpu__time_duration.sum")],
+                "issue_active_pct": round(float(rows[2][h.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]), 1),
+                "grid": rows[2][h.index("launch__grid_size")],
+            }
+        except (ValueError, KeyError) as exc:
+            print("  (no traffic record:", exc, ")")
         for w in WANT:
             if w in h:
                 i = h.index(w)
@@ -63,3 +79,13 @@ def reports():
 
 launches()
 reports()
+
+if len(sys.argv) > 2:  # python tools/ncu_summary.py gpurun_out profiles/traffic.json [workload events_per_launch source]
+    import json
+
+    workload = sys.argv[3] if len(sys.argv) > 3 else "c16dd"
+    events = int(sys.argv[4]) if len(sys.argv) > 4 else 32768
+    source = sys.argv[5] if len(sys.argv) > 5 else "ncu --set full"
+    for rec in TRAFFIC.values():
+        rec.update(workload=workload, events_per_launch=events, source=source)
+    Path(sys.argv[2]).write_text(json.dumps(TRAFFIC, indent=1) + "\n")
