@@ -1075,9 +1075,11 @@ __global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant_
         for (int k = 0; k < GEOM_DOUBLES; ++k) g[k] = 0.0;
         make_point(P, pb.x[i], pb.y[i], pb.t[i], pb.q[i], gv.exact_mesh != 0, g, rec);
         rec[14] = (uint32_t)pb.rank[i];
-        double2* out = reinterpret_cast<double2*>(pb.geom + d * GEOM_DOUBLES);
+        if ((rec[0] >> 29) & 1u) {  // only the exact path of the deposit kernel reads the mesh constants
+            double2* out = reinterpret_cast<double2*>(pb.geom + d * GEOM_DOUBLES);
 #pragma unroll
-        for (int k = 0; k < GEOM_DOUBLES / 2; ++k) out[k] = make_double2(g[2 * k], g[2 * k + 1]);
+            for (int k = 0; k < GEOM_DOUBLES / 2; ++k) out[k] = make_double2(g[2 * k], g[2 * k + 1]);
+        }
         uint4* out_rec = reinterpret_cast<uint4*>(pb.rec + d * REC_WORDS);
 #pragma unroll
         for (int k = 0; k < REC_WORDS / 4; ++k) out_rec[k] = make_uint4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
