@@ -242,7 +242,8 @@ def run_ours(args):
     config, momenta, vertices, zs, as_, indices = build_workload(args.workload, B, seed_offset=rank)
     K = momenta.shape[1]
     eng = engine_for(config, _nuclei_for(zs, as_, indices, nuclear_map), device=local,
-                     max_events_per_launch=args.launch_events, copy_events_per_launch=args.copy_events)  # fmt: skip
+                     max_events_per_launch=args.launch_events, copy_events_per_launch=args.copy_events,
+                     **{k: int(v) for k, v in (kv.split("=") for kv in args.tune)})  # fmt: skip
     # pinned host inputs (e2e) and device-resident inputs (value)
     mom_pin = torch.from_numpy(momenta).pin_memory()
     vtx_pin = torch.from_numpy(vertices).pin_memory()
@@ -439,6 +440,8 @@ def main():
     ap.add_argument("--events", type=int, default=32768, help="events per GPU per step")
     ap.add_argument("--launch-events", type=int, default=0, help="events per track-kernel launch (0 = library default)")
     ap.add_argument("--copy-events", type=int, default=0, help="events per host-copy chunk (0 = library default)")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=INT",
+                    help="engine tuning knob, e.g. table_spill_keys=3000 or unit_points=512 (results do not depend on them)")
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--cpu-events-per-core", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
