@@ -88,7 +88,10 @@ struct AttpcSim {
 
     // constants
     DevArray<int16_t> lut;
-    DevArray<double> pad_xy, pad_scale, response, resp_sorted, resp_prefix, tables;
+    DevArray<double> pad_xy, pad_scale, response, resp_sorted, resp_prefix, tables, stop_ns;
+    DevArray<uint8_t> plan_cls;
+    DevArray<unsigned> plan_counts;
+    DevArray<int32_t> plan_order;
 
     // sizing
     int32_t launch_events = 32768;
@@ -565,7 +568,20 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             }
             tb.seed = plan.seed;
             tb.first_event = plan.first_event + b0;
-            int r = launch_tracks<false>(sim, tb, nb * plan.n_tracks_per_event, which, T);
+            const int64_t n_trk = nb * plan.n_tracks_per_event;
+            if (n_trk >= 4 * (int64_t)sim->sm_count * 32) {  // enough tracks for the order to matter
+                const int ctas = (int)((n_trk + PLAN_THREADS - 1) / PLAN_THREADS);
+                CU(sim->plan_cls.reserve(n_trk));
+                CU(sim->plan_counts.reserve((int64_t)ctas * PLAN_CLASSES));
+                CU(sim->plan_order.reserve(n_trk));
+                track_plan_count_kernel<<<ctas, PLAN_THREADS, 0, T>>>(sim->P, tb, sim->plan_cls.p, sim->plan_counts.p);
+                track_plan_scan_kernel<<<1, 1024, 0, T>>>(sim->plan_counts.p, ctas * PLAN_CLASSES);
+                track_plan_scatter_kernel<<<ctas, PLAN_THREADS, 0, T>>>(sim->plan_cls.p, sim->plan_counts.p, n_trk,
+                                                                        sim->plan_order.p);
+                sim->launches += 3;
+                tb.order = sim->plan_order.p;
+            }
+            int r = launch_tracks<false>(sim, tb, n_trk, which, T);
             if (r) return r;
         }
         cudaEvent_t k1 = sim->mark(T);
@@ -833,7 +849,7 @@ void attpc_destroy(AttpcSim* sim) {
     if (sim->stream_t) cudaStreamDestroy(sim->stream_t);
     if (sim->stream_c) cudaStreamDestroy(sim->stream_c);
     sim->lut.release(); sim->pad_xy.release(); sim->pad_scale.release(); sim->response.release();
-    sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release();
+    sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release(); sim->stop_ns.release(); sim->plan_cls.release(); sim->plan_counts.release(); sim->plan_order.release();
     sim->hash.release(); sim->sort_items.release();
     sim->geom.release(); sim->rec.release();
     sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release(); sim->unit_order.release();
@@ -1000,6 +1016,23 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
         CUC(sim->tables.reserve(std::max<int64_t>(1, (int64_t)scaled.size())));
         if (!scaled.empty())
             CUC(cudaMemcpy(sim->tables.p, scaled.data(), scaled.size() * sizeof(double), cudaMemcpyHostToDevice));
+        // time [ns] to slow down from node i to node 0: integral of d(gamma beta) / deceleration (trapezoids); only the
+        // launch order of the tracks depends on it
+        std::vector<double> stop((size_t)n_species * P.n_nodes, 0.0);
+        for (int s = 0; s < n_species; ++s) {
+            const int per_oct = 1 << P.lm;
+            auto node = [&](int j) { return std::ldexp(1.0 + (double)(j % per_oct) / per_oct, P.e_min + j / per_oct); };
+            auto gb = [&](double ke) { const double g = ke / species[s].mass + 1.0; return std::sqrt(g * g - 1.0); };
+            const double* a = &scaled[(size_t)s * P.n_nodes];
+            double* out = &stop[(size_t)s * P.n_nodes];
+            for (int i = 1; i < P.n_nodes; ++i) {
+                const double mean = 0.5 * (a[i] + a[i - 1]);
+                out[i] = out[i - 1] + (mean > 0.0 ? (gb(node(i)) - gb(node(i - 1))) / mean * 1e9 : 0.0);
+            }
+        }
+        CUC(sim->stop_ns.reserve(std::max<int64_t>(1, (int64_t)stop.size())));
+        if (!stop.empty())
+            CUC(cudaMemcpy(sim->stop_ns.p, stop.data(), stop.size() * sizeof(double), cudaMemcpyHostToDevice));
         sim->table_smem_bytes = scaled.size() * sizeof(double);
         sim->tables_in_smem = sim->table_smem_bytes + (TRACK_THREADS / 32) * TRACK_SLOT_BYTES_PER_WARP <= 227 * 1024;
     }
@@ -1022,6 +1055,7 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
     }
     P.lut = sim->lut.p;
     P.tables = sim->tables.p;
+    P.stop_ns = sim->stop_ns.p;
     P.pad_xy = sim->pad_xy.p;
     P.pad_scale = sim->pad_scale.p;
     P.response = sim->response.p;

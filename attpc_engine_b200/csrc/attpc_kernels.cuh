@@ -56,6 +56,7 @@ struct SimParams {
     SpeciesDev sp[MAX_SPECIES];
     const int16_t* lut;
     const double* tables;  // [n_species][n_nodes]: dE/dx * MEV_2_JOULE * density * 100 / (m_kg c)  -> d(gamma beta)/dt
+    const double* stop_ns; // [n_species][n_nodes]: time [ns] an ion of that energy needs to slow down to the first node
     const double* pad_xy;
     const double* pad_scale;
     const double* response;
@@ -358,12 +359,119 @@ struct TrackBatch {
     int32_t species[MAX_TRACKS_PER_EVENT];
     uint64_t seed;
     int64_t first_event;  // global id of event slot 0
+    const int32_t* order; // longest-first order of the tracks (track_plan kernels), or null = as they come
     // trajectory recording (attpc_trajectories): one track per "event", rows to rec_points
     const int32_t* rec_species;  // [n_events]
     double* rec_points;          // [n_events, rec_max, 6]
     int32_t* rec_counts;         // [n_events]
     int32_t rec_stride, rec_max;
 };
+
+// ---- longest first.  The track kernel is bound by its longest tracks (a stopping light ion takes ten times the
+// steps of an exiting one), so the tracks that are expected to live long must start at once, not when a lane happens
+// to reach them.  Expected lifetime = min(time to slow down, time to reach the end wall at the initial speed); four
+// classes, stable partition (tracks keep their event order inside a class, which keeps the appends of a warp in one
+// event group for all but the long classes).
+constexpr int PLAN_CLASSES = 4;
+constexpr int PLAN_THREADS = 256;
+
+__device__ __forceinline__ int track_class(const SimParams& P, const TrackBatch& tb, int64_t track) {
+    const int ev = (int)(track / tb.n_tracks_per_event), rank = (int)(track % tb.n_tracks_per_event);
+    const int sp = tb.species[rank];
+    if (sp < 0) return PLAN_CLASSES - 1;
+    const SpeciesDev& S = P.sp[sp];
+    const double* m4 = tb.momenta + ((int64_t)ev * tb.n_nuclei + tb.nucleus[rank]) * 4;
+    const double ux = m4[0] / S.mass, uy = m4[1] / S.mass, uz = m4[2] / S.mass;
+    const double g2 = ux * ux + uy * uy + uz * uz;
+    const double gamma = sqrt(1.0 + g2);
+    const double ke = S.mass * g2 / (gamma + 1.0);
+    const TableView v = make_table_view(P, P.stop_ns + S.table);
+    double life = table_eval(v, ke);                                // ns to slow down
+    const double z = tb.vertices[(int64_t)ev * 3 + 2];
+    const double vz = uz * C_LIGHT / gamma * 1e-9;                  // m / ns
+    if (vz > 0.0) life = fmin(life, (Z_HI - z) / vz);
+    if (vz < 0.0) life = fmin(life, (Z_LO - z) / vz);
+    return life > 120.0 ? 0 : life > 40.0 ? 1 : life > 12.0 ? 2 : 3;
+}
+
+// (1) class of every track, per-CTA class counts
+__global__ void __launch_bounds__(PLAN_THREADS)
+track_plan_count_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackBatch tb, uint8_t* cls,
+                        unsigned* cta_counts) {
+    __shared__ unsigned s_cnt[PLAN_CLASSES];
+    if (threadIdx.x < PLAN_CLASSES) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t n_tracks = tb.n_events * tb.n_tracks_per_event;
+    const int64_t t = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
+    if (t < n_tracks) {
+        const int c = track_class(P, tb, t);
+        cls[t] = (uint8_t)c;
+        atomicAdd(&s_cnt[c], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < PLAN_CLASSES) cta_counts[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+// (2) exclusive scan of the counts, class-major (one CTA)
+__global__ void __launch_bounds__(1024) track_plan_scan_kernel(unsigned* cta_counts, int n) {
+    __shared__ unsigned s_part[1024];
+    __shared__ unsigned s_base;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int start = 0; start < n; start += 1024) {
+        const int i = start + tid;
+        const unsigned v = i < n ? cta_counts[i] : 0u;
+        s_part[tid] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned add = tid >= o ? s_part[tid - o] : 0u;
+            __syncthreads();
+            s_part[tid] += add;
+            __syncthreads();
+        }
+        if (i < n) cta_counts[i] = s_base + s_part[tid] - v;
+        __syncthreads();
+        if (tid == 0) s_base += s_part[1023];
+        __syncthreads();
+    }
+}
+
+// (3) stable scatter: position = start of (class, CTA) + tracks of the same class before this one in the CTA
+__global__ void __launch_bounds__(PLAN_THREADS)
+track_plan_scatter_kernel(const uint8_t* cls, const unsigned* cta_starts, int64_t n_tracks, int32_t* order) {
+    __shared__ unsigned s_warp[PLAN_CLASSES][PLAN_THREADS / 32];
+    const int64_t t = (int64_t)blockIdx.x * PLAN_THREADS + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c = t < n_tracks ? (int)cls[t] : -1;
+    unsigned below = 0;
+#pragma unroll
+    for (int k = 0; k < PLAN_CLASSES; ++k) {
+        const unsigned m = __ballot_sync(FULL, c == k);
+        if (c == k) below = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) s_warp[k][warp] = __popc(m);
+    }
+    __syncthreads();
+    if (c >= 0) {
+        unsigned idx = cta_starts[(int64_t)c * gridDim.x + blockIdx.x] + below;  // class-major, stable
+        for (int w = 0; w < warp; ++w) idx += s_warp[c][w];
+        // Spread the long classes (0, 1) over the warps instead of packing them: every S-th position of the order is
+        // a long track, the positions between are filled with the others in their order.  A warp full of long tracks
+        // would make every one of them pay for the grid points of 31 others at every step.
+        const unsigned n_long = cta_starts[(int64_t)2 * gridDim.x];
+        const unsigned S = n_long > 0 ? min(32u, (unsigned)(n_tracks / n_long)) : 0u;
+        unsigned pos = idx;
+        if (S >= 2u) {
+            if (idx < n_long) {
+                pos = idx * S;
+            } else {
+                const unsigned k = idx - n_long, block = k / (S - 1u);
+                pos = block < n_long ? block * S + k % (S - 1u) + 1u : n_long * S + (k - n_long * (S - 1u));
+            }
+        }
+        order[pos] = (int32_t)t;
+    }
+}
 
 // Step slot: what the lanes of a warp need to turn one accepted step of ONE track into its 0.1 ns grid points.
 // Every warp has 32 slots (one per lane = per track in flight), stored field-major in shared memory
@@ -432,12 +540,16 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
     // Points staged by the previous round (warp-uniform mask of the lanes that hold one) and the still pending result
     // of the atomic that reserved their positions: in the leader's register (one atomic for the warp, leader >= 0)
     // or in every lane's own (tracks of several event groups in one round, leader < 0).
-    unsigned staged_mask = 0, staged_first = 0, staged_prefix = 0;
+    unsigned staged_mask = 0, staged_first = 0, staged_prefix = 0, staged_peers = 0;
     int staged_leader = 0;
     auto store_staged = [&]() {  // whole warp; the first read of staged_first waits for the atomic issued a round ago
         if (staged_mask == 0u) return;
-        const unsigned pos =
-            staged_leader >= 0 ? __shfl_sync(FULL, staged_first, staged_leader) + staged_prefix : staged_first;
+        unsigned pos = 0;
+        if (staged_leader >= 0) {
+            pos = __shfl_sync(FULL, staged_first, staged_leader) + staged_prefix;
+        } else if ((staged_mask >> lane) & 1u) {  // one atomic per event group: its result sits in the group's first lane
+            pos = __shfl_sync(staged_peers, staged_first, __ffs(staged_peers) - 1) + staged_prefix;
+        }
         if ((staged_mask >> lane) & 1u) {
             const int gi = stage_i[0 * 32 + lane] / pb.group_events;
             if ((int64_t)pos >= pb.group_cap) {
@@ -462,6 +574,7 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
             if (track >= n_tracks) {
                 done = true;
             } else {
+                if (!RECORD && tb.order) track = tb.order[track];
                 ev = (int)(track / tb.n_tracks_per_event);
                 rank = (int)(track % tb.n_tracks_per_event);
                 const int sp = RECORD ? tb.rec_species[track] : tb.species[rank];
@@ -657,8 +770,14 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
                 staged_prefix = (unsigned)__popc(emit_mask & lanes_below);
                 if (uniform) {
                     if (lane == leader) staged_first = atomicAdd(&pb.count[g0], (unsigned)__popc(emit_mask));
-                } else if (emit) {
-                    staged_first = atomicAdd(&pb.count[gi], 1u);
+                } else {  // tracks of several event groups (the long tracks run first, whatever their event):
+                          // one atomic per group present in the round
+                    staged_peers = __match_any_sync(FULL, gi) & emit_mask;
+                    if (emit) {
+                        staged_prefix = (unsigned)__popc(staged_peers & lanes_below);
+                        if (lane == __ffs(staged_peers) - 1)
+                            staged_first = atomicAdd(&pb.count[gi], (unsigned)__popc(staged_peers));
+                    }
                 }
                 if (emit) {
                     stage_d[0 * 32 + lane] = g.x;
