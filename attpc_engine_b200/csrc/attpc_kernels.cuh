@@ -1607,9 +1607,8 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     unsigned occupied = 0;
     const bool dup = gv.mode[slot_event] != 0u;  // the list may hold a key several times
     const int limit = (int)min(gv.n_entries[slot_event], (unsigned)gv.hash_cap);
-    for (int i = threadIdx.x; i < limit; i += blockDim.x) {
-        const unsigned key1 = tab[i].key1;
-        if (key1 == 0u) continue;
+    auto take = [&](int i, unsigned key1) {
+        if (key1 == 0u) return;
         occupied += 1;
         const unsigned tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
         const unsigned key = szudzik_pair(tb, pad);  // detector/pairing.py: id of the (tb, pad) cell
@@ -1618,6 +1617,16 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
             atomicAdd(&s_hist[min(tb, (unsigned)TB_BINS - 1u)], 1u);
             stash[atomicAdd(&s_n, 1u)] = make_item(tb, pad, (unsigned)i);
         }
+    };
+    for (int i0 = threadIdx.x; i0 < limit; i0 += 4 * blockDim.x) {  // four loads in flight per thread
+        unsigned k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            k[u] = i < limit ? tab[i].key1 : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) take(i0 + u * (int)blockDim.x, k[u]);
     }
     if (occupied) atomicAdd(&s_keys, occupied);
     __syncthreads();
@@ -1658,9 +1667,17 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     }
     const bool in_smem = n <= SORT_SMEM_ITEMS;
     uint64_t* buf = in_smem ? s_items : sorted;  // bucketed, unordered inside a bucket
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint64_t it = stash[i];
-        buf[atomicAdd(&s_fill[min((unsigned)(it >> 47), (unsigned)TB_BINS - 1u)], 1u)] = it;
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {  // four loads in flight per thread
+        uint64_t it[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            it[u] = i < n ? stash[i] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * (int)blockDim.x < n)
+                buf[atomicAdd(&s_fill[min((unsigned)(it[u] >> 47), (unsigned)TB_BINS - 1u)], 1u)] = it[u];
     }
     __syncthreads();
     // order every bucket: one thread per item counts the smaller pads of its bucket (items are distinct; a bucket
