@@ -1715,28 +1715,23 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         for (int start = 0; start < n; start += FINALIZE_THREADS) {
             const int i = start + threadIdx.x;
-            uint64_t v = 0;
-            bool head = false;
-            if (i < n) {
-                v = dst[i];
-                const uint32_t kw = (uint32_t)(v >> 32);
-                const uint32_t before = threadIdx.x == 0 ? s_prev_key : (uint32_t)(dst[i - 1] >> 32);
-                head = kw != before;
-                if (head) {
-                    unsigned long long extra = 0;
-                    unsigned rank = wtab[(unsigned)v].rank;
-                    bool any = false;
-                    for (int j = i + 1; j < n && (uint32_t)(dst[j] >> 32) == kw; ++j) {
-                        const HashEntry other = wtab[(unsigned)dst[j]];
-                        extra += other.charge;
-                        rank = max(rank, other.rank);
-                        any = true;
-                    }
-                    if (any) {
-                        wtab[(unsigned)v].charge += extra;
-                        wtab[(unsigned)v].rank = rank;
-                    }
+            const uint64_t v = i < n ? dst[i] : 0ull;
+            const uint32_t kw = i < n ? (uint32_t)(v >> 32) : 0xFFFFFFFEu;
+            // neighbours' keys from the lanes beside; only the edge lanes of a warp read them from memory
+            uint32_t before = __shfl_up_sync(FULL, kw, 1), after = __shfl_down_sync(FULL, kw, 1);
+            if (lane == 0 && i < n) before = threadIdx.x == 0 ? s_prev_key : (uint32_t)(dst[i - 1] >> 32);
+            if (lane == 31) after = i + 1 < n ? (uint32_t)(dst[i + 1] >> 32) : 0xFFFFFFFEu;
+            const bool head = i < n && kw != before;
+            if (head && after == kw) {  // copies follow (rare): fold them into this entry
+                unsigned long long extra = 0;
+                unsigned rank = wtab[(unsigned)v].rank;
+                for (int j = i + 1; j < n && (uint32_t)(dst[j] >> 32) == kw; ++j) {
+                    const HashEntry other = wtab[(unsigned)dst[j]];
+                    extra += other.charge;
+                    rank = max(rank, other.rank);
                 }
+                wtab[(unsigned)v].charge += extra;
+                wtab[(unsigned)v].rank = rank;
             }
             const unsigned heads = __ballot_sync(FULL, head);
             if (lane == 0) s_wsum[warp] = __popc(heads);
