@@ -99,7 +99,7 @@ struct AttpcSim {
     int32_t group_events = 2048;
     int32_t chunk_groups = 16;  // groups per kernel launch when the rows stay on the device
     int32_t unit_points = UNIT_POINTS;     // test knobs (AttpcConfig.unit_points / table_spill_keys)
-    int32_t spill_keys = SMEM_SPILL_AT;
+    int32_t spill_keys = SMEM_SPILL_DEFAULT;
     int32_t hash_cap = 16384;
     int64_t group_point_cap = 0;
 

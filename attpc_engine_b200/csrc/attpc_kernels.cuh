@@ -1214,8 +1214,9 @@ constexpr int QUEUE_SLOTS = 64;      // per-warp ring of finished (key, charge) 
 constexpr int SMEM_SLOTS = 6912;     // per-CTA table in shared memory: 10 B per slot = 67.5 KB, three CTAs per SM
 // fill check once per pass of the CTA: a pass adds at most 100 keys per point plus what the rings still hold
 constexpr int SMEM_SPILL_AT = SMEM_SLOTS - 100 * POINTS_PER_ITER - DEPOSIT_WARPS * QUEUE_SLOTS - 512;
-// (The bound is generous -- real points touch a few dozen pads -- but a fuller table is no faster: at 75 % load the
-// probe sequences of the linear probing cost more than the appends they save; AttpcConfig.table_spill_keys lowers it.)
+// That is the highest safe threshold.  The default is lower: a table at 30 % load answers most inserts with one probe,
+// and the appends it costs are cheap (measured optimum over the four workloads; AttpcConfig.table_spill_keys).
+constexpr int SMEM_SPILL_DEFAULT = 2000 < SMEM_SPILL_AT ? 2000 : SMEM_SPILL_AT;
 constexpr size_t DEPOSIT_SMEM_BYTES = (size_t)SMEM_SLOTS * (2 * sizeof(unsigned) + sizeof(uint16_t));
 constexpr unsigned SMEM_KEY_MASK = 0x0FFFFFFFu;  // low 28 bits: ((tb << 15) | pad) + 1; top 4 bits: track rank
 
