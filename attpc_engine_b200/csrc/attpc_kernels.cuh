@@ -1211,7 +1211,7 @@ constexpr int DEPOSIT_WARPS = DEPOSIT_THREADS / 32;
 constexpr int POINTS_PER_WARP = 3;   // three active points per warp pass: 3 x 10 mesh rows on 30 lanes
 constexpr int POINTS_PER_ITER = DEPOSIT_WARPS * POINTS_PER_WARP;
 constexpr int QUEUE_SLOTS = 64;      // per-warp ring of finished (key, charge) runs waiting for a full 32-lane insert
-constexpr int SMEM_SLOTS = 6912;     // per-CTA table in shared memory: 10 B per slot = 67.5 KB, three CTAs per SM
+constexpr int SMEM_SLOTS = 4864;     // per-CTA table in shared memory: 10 B per slot = 47.5 KB, four CTAs per SM
 // fill check once per pass of the CTA: a pass adds at most 100 keys per point plus what the rings still hold
 constexpr int SMEM_SPILL_AT = SMEM_SLOTS - 100 * POINTS_PER_ITER - DEPOSIT_WARPS * QUEUE_SLOTS - 512;
 // That is the highest safe threshold.  The default is lower: a table at 30 % load answers most inserts with one probe,
@@ -1290,7 +1290,7 @@ __device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t,
 // open-addressing table: the insert code (probe loop, two atomics) runs once per 32 runs instead of once per 32
 // pixels.  At the end the table is compacted into the event's dense entry list (events of one unit) or merged into
 // the event's global table (events split over several units, and units dense enough to overflow the shared table).
-__global__ void __launch_bounds__(DEPOSIT_THREADS, 3)
+__global__ void __launch_bounds__(DEPOSIT_THREADS, 4)
 deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk, Counters* ctr) {
     const GroupView gv = sub_group(chunk, blockIdx.y);
     extern __shared__ __align__(16) unsigned s_raw[];
