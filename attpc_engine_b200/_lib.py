@@ -12,7 +12,7 @@ from pathlib import Path
 
 LIB_NAME = "libattpc_b200.so"
 LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # flags (include/attpc_b200.h)
 KEEP_ALL_TB = 1 << 0
@@ -110,8 +110,7 @@ class AttpcResult(C.Structure):
         ("reserved1", C.c_int32),
         ("n_table_flushes", C.c_int64),
         ("col_pad", C.POINTER(C.c_int16)),
-        ("col_tb_bucket", C.POINTER(C.c_int16)),
-        ("col_tb_offset", C.POINTER(C.c_float)),
+        ("col_tb_q16", C.POINTER(C.c_uint32)),
         ("col_electrons", C.POINTER(C.c_int64)),
         ("col_label", C.POINTER(C.c_int8)),
         ("n_rk_steps", C.c_int64),

@@ -140,13 +140,11 @@ struct AttpcSim {
 
     // outputs
     DevArray<int16_t> col_pad_dev;
-    DevArray<int16_t> col_tbb_dev;
-    DevArray<float> col_tbo_dev;
+    DevArray<uint32_t> col_tbq_dev;
     DevArray<int64_t> col_q_dev;
     DevArray<int8_t> col_label_dev;
     PinnedArray<int16_t> col_pad_host;
-    PinnedArray<int16_t> col_tbb_host;
-    PinnedArray<float> col_tbo_host;
+    PinnedArray<uint32_t> col_tbq_host;
     PinnedArray<int64_t> col_q_host;
     PinnedArray<int8_t> col_label_host;
     bool columns = false;  // sticky: once a call asked for columns the buffers are kept in step with the others
@@ -256,8 +254,7 @@ int ensure_out_buffers(AttpcSim* sim, int64_t n_events, int64_t n_points, bool k
     CU(sim->labels_dev.reserve(n_points, keep, sim->stream));
     if (sim->columns) {
         CU(sim->col_pad_dev.reserve(sim->labels_dev.n, keep, sim->stream));
-        CU(sim->col_tbb_dev.reserve(sim->labels_dev.n, keep, sim->stream));
-        CU(sim->col_tbo_dev.reserve(sim->labels_dev.n, keep, sim->stream));
+        CU(sim->col_tbq_dev.reserve(sim->labels_dev.n, keep, sim->stream));
         CU(sim->col_q_dev.reserve(sim->labels_dev.n, keep, sim->stream));
         CU(sim->col_label_dev.reserve(sim->labels_dev.n, keep, sim->stream));
     }
@@ -503,8 +500,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     }
     if (use_columns) {
         CU(sim->col_pad_host.reserve(sim->labels_dev.n));
-        CU(sim->col_tbb_host.reserve(sim->labels_dev.n));
-        CU(sim->col_tbo_host.reserve(sim->labels_dev.n));
+        CU(sim->col_tbq_host.reserve(sim->labels_dev.n));
         CU(sim->col_q_host.reserve(sim->labels_dev.n));
         CU(sim->col_label_host.reserve(sim->labels_dev.n));
     }
@@ -610,8 +606,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         fa.out_cap = sim->labels_dev.n;
         if (use_columns) {
             fa.col_pad = sim->col_pad_dev.p;
-            fa.col_tb_bucket = sim->col_tbb_dev.p;
-            fa.col_tb_offset = sim->col_tbo_dev.p;
+            fa.col_tb_q16 = sim->col_tbq_dev.p;
             fa.col_electrons = sim->col_q_dev.p;
             fa.col_label = sim->col_label_dev.p;
         }
@@ -657,10 +652,8 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             if (n_new > 0 && use_columns) {
                 CU(cudaMemcpyAsync(sim->col_pad_host.p + copied, sim->col_pad_dev.p + copied,
                                    (size_t)n_new * sizeof(int16_t), cudaMemcpyDeviceToHost, C));
-                CU(cudaMemcpyAsync(sim->col_tbb_host.p + copied, sim->col_tbb_dev.p + copied,
-                                   (size_t)n_new * sizeof(int16_t), cudaMemcpyDeviceToHost, C));
-                CU(cudaMemcpyAsync(sim->col_tbo_host.p + copied, sim->col_tbo_dev.p + copied,
-                                   (size_t)n_new * sizeof(float), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->col_tbq_host.p + copied, sim->col_tbq_dev.p + copied,
+                                   (size_t)n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, C));
                 CU(cudaMemcpyAsync(sim->col_q_host.p + copied, sim->col_q_dev.p + copied,
                                    (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
                 CU(cudaMemcpyAsync(sim->col_label_host.p + copied, sim->col_label_dev.p + copied,
@@ -715,8 +708,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 }
                 if (use_columns) {
                     CU(sim->col_pad_host.reserve(sim->labels_dev.n, true));
-                    CU(sim->col_tbb_host.reserve(sim->labels_dev.n, true));
-                    CU(sim->col_tbo_host.reserve(sim->labels_dev.n, true));
+                    CU(sim->col_tbq_host.reserve(sim->labels_dev.n, true));
                     CU(sim->col_q_host.reserve(sim->labels_dev.n, true));
                     CU(sim->col_label_host.reserve(sim->labels_dev.n, true));
                 }
@@ -777,8 +769,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         }
         if (use_columns) {
             res->col_pad = sim->col_pad_host.p;
-            res->col_tb_bucket = sim->col_tbb_host.p;
-            res->col_tb_offset = sim->col_tbo_host.p;
+            res->col_tb_q16 = sim->col_tbq_host.p;
             res->col_electrons = sim->col_q_host.p;
             res->col_label = sim->col_label_host.p;
         }
@@ -859,8 +850,8 @@ void attpc_destroy(AttpcSim* sim) {
     sim->offsets_dev.release(); sim->labels_dev.release(); sim->row_offsets_dev.release();
     sim->row_labels_dev.release(); sim->cloud_dev.release(); sim->rows_dev.release(); sim->row_kept.release();
     sim->row_sort_keys.release(); sim->row_sort_idx.release();
-    sim->col_pad_dev.release(); sim->col_tbb_dev.release(); sim->col_tbo_dev.release(); sim->col_q_dev.release(); sim->col_label_dev.release();
-    sim->col_pad_host.release(); sim->col_tbb_host.release(); sim->col_tbo_host.release(); sim->col_q_host.release(); sim->col_label_host.release();
+    sim->col_pad_dev.release(); sim->col_tbq_dev.release(); sim->col_q_dev.release(); sim->col_label_dev.release();
+    sim->col_pad_host.release(); sim->col_tbq_host.release(); sim->col_q_host.release(); sim->col_label_host.release();
     sim->offsets_host.release(); sim->labels_host.release(); sim->row_offsets_host.release();
     sim->row_labels_host.release(); sim->cloud_host.release(); sim->rows_host.release();
     if (sim->stream) cudaStreamDestroy(sim->stream);

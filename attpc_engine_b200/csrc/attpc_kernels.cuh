@@ -1540,12 +1540,12 @@ struct FinalizeArgs {
     double* cloud;            // [out_cap, 3]
     int64_t* labels;          // [out_cap]
     int64_t out_cap;
-    // optional columnar copy of the same rows in their natural types (17 B instead of 32 B per row on the wire).
-    // time bucket + wiggle = col_tb_bucket + col_tb_offset exactly for the library's own 24-bit wiggle; a replayed
-    // 53-bit uniform is rounded to float32 in the offset column (replay tests read the float64 cloud).
+    // optional columnar copy of the same rows in their natural types (15 B instead of 32 B per row on the wire).
+    // col_tb_q16 = (time bucket << 16) | (wiggle * 2^16): time bucket + wiggle == col_tb_q16 / 65536 exactly for the
+    // library's own 16-bit wiggle; a replayed 53-bit uniform is truncated to 16 bits there (replay tests read the
+    // float64 cloud).
     int16_t* col_pad;
-    int16_t* col_tb_bucket;
-    float* col_tb_offset;
+    uint32_t* col_tb_q16;
     int64_t* col_electrons;
     int8_t* col_label;
 };
@@ -1565,7 +1565,7 @@ __device__ __forceinline__ double wiggle_of(const FinalizeArgs& fa, int slot_eve
         ctr->replay_miss = 1;
         return 0.0;
     }
-    return philox_uniform24(fa.seed, (uint64_t)(fa.first_event + slot_event), STREAM_WIGGLE, key);
+    return philox_uniform16(fa.seed, (uint64_t)(fa.first_event + slot_event), STREAM_WIGGLE, key);
 }
 
 constexpr int FINALIZE_THREADS = 256;
@@ -1819,8 +1819,7 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
         fa.labels[off + i] = label;
         if (fa.col_pad) {
             fa.col_pad[off + i] = (int16_t)pad;
-            fa.col_tb_bucket[off + i] = (int16_t)tb;
-            fa.col_tb_offset[off + i] = (float)u;
+            fa.col_tb_q16[off + i] = (tb << 16) | (uint32_t)(u * 65536.0);
             fa.col_electrons[off + i] = (long long)en.charge;
             fa.col_label[off + i] = (int8_t)label;
         }

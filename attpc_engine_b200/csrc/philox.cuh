@@ -3,7 +3,7 @@
 // The reference threads ONE numpy PCG64 generator through all events (detector/simulator.py:169), so its
 // stream depends on event order.  Here every draw is addressed by what it is FOR:
 //   Fano normal  of (event, nucleus index, grid step k) -> counter (event_lo, event_hi, nucleus, k)
-//   TB wiggle    of (event, Szudzik key)                -> counter (event_lo, event_hi, 0xFFFFFFFF, key), 24 bits
+//   TB wiggle    of (event, Szudzik key)                -> counter (event_lo, event_hi, 0xFFFFFFFF, key), 16 bits
 // keyed by the 64-bit seed, which makes results independent of batching and of the GPU that ran the event.
 #pragma once
 #include <cstdint>
@@ -65,13 +65,13 @@ __host__ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_
     return uniform53(r.x, r.y);
 }
 
-// 24-bit uniform in [0, 1): k / 2^24.  Exact in float32, and time bucket + k / 2^24 is exact in float64, so the
-// time-bucket wiggle travels as (int16 bucket, float32 offset) without losing a bit.
-__host__ __device__ __forceinline__ double philox_uniform24(uint64_t seed, uint64_t event, uint32_t stream,
+// 16-bit uniform in [0, 1): k / 2^16.  time bucket + k / 2^16 is exact in float64 and travels as one Q16.16
+// fixed-point uint32 ((bucket << 16) | k) without losing a bit.
+__host__ __device__ __forceinline__ double philox_uniform16(uint64_t seed, uint64_t event, uint32_t stream,
                                                             uint32_t index) {
     const Philox4 r = philox4x32_10((uint32_t)event, (uint32_t)(event >> 32), stream, index, (uint32_t)seed,
                                     (uint32_t)(seed >> 32));
-    return (double)(r.x >> 8) * (1.0 / 16777216.0);
+    return (double)(r.x >> 16) * (1.0 / 65536.0);
 }
 
 }  // namespace attpc

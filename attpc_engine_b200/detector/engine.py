@@ -66,8 +66,8 @@ class SimBatch:
 
     Rows are either held as the reference's arrays (``cloud`` float64 ``[N, 3]`` = pad, time bucket, electrons;
     ``labels`` int64 ``[N]``) or, for batches simulated with ``columns=True``, as typed columns (``pad`` int16,
-    ``tb_bucket`` int16 + ``tb_offset`` float32 whose sum is the float64 time bucket exactly, ``electrons`` int64,
-    ``label8`` int8: 17 instead of 32 bytes per row over PCIe).  ``cloud`` / ``labels`` / ``event(e)`` work in both
+    ``tb_q16`` uint32 = the float64 time bucket times 65536, exactly (Q16.16 fixed point), ``electrons`` int64,
+    ``label8`` int8: 15 instead of 32 bytes per row over PCIe).  ``cloud`` / ``labels`` / ``event(e)`` work in both
     cases; with columns they are materialised on demand.
     """
 
@@ -81,7 +81,7 @@ class SimBatch:
         self.rows = rows  # [M, 8] Spyral rows
         self.row_labels = row_labels
         self.stats = {} if stats is None else stats
-        self.columns = columns  # dict(pad, tb_bucket, tb_offset, electrons, label8) or None
+        self.columns = columns  # dict(pad, tb_q16, electrons, label8) or None
 
     def __len__(self) -> int:
         return len(self.offsets) - 1
@@ -92,8 +92,8 @@ class SimBatch:
             c = self.columns
             out = np.empty((len(c["pad"]), 3), dtype=np.float64)
             out[:, 0] = c["pad"]
-            out[:, 1] = c["tb_bucket"]
-            out[:, 1] += c["tb_offset"]  # exact: the wiggle has 24 bits
+            out[:, 1] = c["tb_q16"]
+            out[:, 1] *= 1.0 / 65536.0  # exact: Q16.16 fixed point
             out[:, 2] = c["electrons"]
             self._cloud = out
         return self._cloud
@@ -111,8 +111,8 @@ class SimBatch:
             c = self.columns
             cloud = np.empty((b - a, 3), dtype=np.float64)
             cloud[:, 0] = c["pad"][a:b]
-            cloud[:, 1] = c["tb_bucket"][a:b]
-            cloud[:, 1] += c["tb_offset"][a:b]
+            cloud[:, 1] = c["tb_q16"][a:b]
+            cloud[:, 1] *= 1.0 / 65536.0
             cloud[:, 2] = c["electrons"][a:b]
             return cloud, c["label8"][a:b].astype(np.int64)
         return self._cloud[a:b], self._labels[a:b]
@@ -284,8 +284,7 @@ class Engine:
             take = (lambda p: grab(np.ctypeslib.as_array(p, shape=(n_pts,)))) if n_pts > 0 else None
             columns = dict(
                 pad=take(res.col_pad) if take else np.zeros(0, np.int16),
-                tb_bucket=take(res.col_tb_bucket) if take else np.zeros(0, np.int16),
-                tb_offset=take(res.col_tb_offset) if take else np.zeros(0, np.float32),
+                tb_q16=take(res.col_tb_q16) if take else np.zeros(0, np.uint32),
                 electrons=take(res.col_electrons) if take else np.zeros(0, np.int64),
                 label8=take(res.col_label) if take else np.zeros(0, np.int8),
             )
@@ -334,7 +333,7 @@ class Engine:
         """`simulate` (`simulator.py:52-115`) for ``B`` events at once: ``momenta [B, K, 4]``, ``vertices [B, 3]``.
 
         ``rows_only`` (with ``spyral_rows``): bring back offsets and Spyral rows but leave the raw cloud on the GPU.
-        ``columns``: bring the rows back as typed columns (17 B/row instead of 32 B/row over PCIe), see `SimBatch`.
+        ``columns``: bring the rows back as typed columns (15 B/row instead of 32 B/row over PCIe), see `SimBatch`.
         """
         momenta = np.ascontiguousarray(momenta, dtype=np.float64)
         vertices = np.ascontiguousarray(vertices, dtype=np.float64)

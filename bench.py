@@ -371,8 +371,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(momenta.nbytes + vertices.nbytes),
                 "result": ("Spyral rows float64[M,8] + labels" if args.spyral else
                            "cloud float64[N,3] + int64 labels" if args.float64_rows else
-                           "typed columns: pad int16, tb bucket int16 + offset float32, electrons int64, label int8"),
-                "d2h_bytes_per_step": int((e2e_rows * 72 if args.spyral else e2e_points * (32 if args.float64_rows else 17)) / args.steps
+                           "typed columns: pad int16, time bucket uint32 Q16.16, electrons int64, label int8"),
+                "d2h_bytes_per_step": int((e2e_rows * 72 if args.spyral else e2e_points * (32 if args.float64_rows else 15)) / args.steps
                                           + (B + 1) * 8 * (2 if args.spyral else 1))},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }  # fmt: skip

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ATTPC_ABI_VERSION 3
+#define ATTPC_ABI_VERSION 4
 
 enum {
     ATTPC_OK = 0,
@@ -38,7 +38,7 @@ enum {
     ATTPC_SKIP_HOST_COPY = 1u << 3,/* leave results in device memory only (device-resident benchmarking) */
     ATTPC_ROWS_KEEP_ALL = 1u << 4, /* attpc_convert_to_spyral: every row, input order (no threshold, no sort) */
     ATTPC_SKIP_CLOUD_COPY = 1u << 5,/* with ATTPC_SPYRAL_ROWS: copy offsets and rows to the host, not the raw cloud */
-    ATTPC_COLUMNS = 1u << 6,       /* host result as typed columns (col_* of AttpcResult, 17 B/row) instead of the
+    ATTPC_COLUMNS = 1u << 6,       /* host result as typed columns (col_* of AttpcResult, 15 B/row) instead of the
                                       float64 cloud + int64 labels (32 B/row); same rows, same order */
     ATTPC_EXACT_MESH = 1u << 7     /* validation: evaluate every mesh pixel with the reference's own expression
                                       (detector/transporter.py:36-41, 240-246).  The default reads pdf * step^2 from
@@ -133,9 +133,8 @@ typedef struct AttpcResult {
     int64_t n_table_flushes;     /* shared-memory tables merged into a global table (dense or split events) */
     /* ATTPC_COLUMNS: the rows of `cloud` / `labels` as typed columns (pinned host memory) */
     const int16_t* col_pad;      /* [n_points] pad id */
-    const int16_t* col_tb_bucket;/* [n_points] integer time bucket */
-    const float* col_tb_offset;  /* [n_points] wiggle in [0, 1): cloud[:, 1] == col_tb_bucket + col_tb_offset exactly (the
-                                    library's wiggle has 24 bits; a replayed 53-bit uniform is rounded to float32 here) */
+    const uint32_t* col_tb_q16;  /* [n_points] time bucket + wiggle as Q16.16 fixed point: cloud[:, 1] == col_tb_q16 / 65536
+                                    exactly (the library's wiggle has 16 bits; a replayed 53-bit uniform is truncated here) */
     const int64_t* col_electrons;/* [n_points] electrons (after gain) */
     const int8_t* col_label;     /* [n_points] index of the nucleus that last touched the point */
     /* integrator statistics (right-hand-side evaluations = 6 * n_rk_steps + n_tracks) */

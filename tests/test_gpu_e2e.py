@@ -252,12 +252,12 @@ def test_full_size_properties(name, n_events):
 
 
 def test_typed_columns_hold_the_same_rows(dist):
-    """`columns=True` changes the wire format (17 B/row instead of 32 B/row), not the content."""
+    """`columns=True` changes the wire format (15 B/row instead of 32 B/row), not the content."""
     cfg, m, v, zs, as_, idx = _workload(dist, "c16dd", 200)
     plain = simulate_batch(m, v, zs, as_, cfg, 31, idx)
     cols = simulate_batch(m, v, zs, as_, cfg, 31, idx, columns=True, max_events_per_launch=64, copy_events_per_launch=64)
     assert cols.columns is not None and cols.columns["pad"].dtype == np.int16 and cols.columns["label8"].dtype == np.int8
-    assert cols.columns["tb_bucket"].dtype == np.int16 and cols.columns["tb_offset"].dtype == np.float32
+    assert cols.columns["tb_q16"].dtype == np.uint32
     assert np.array_equal(cols.offsets, plain.offsets)
     ev_cloud, ev_labels = cols.event(17)
     assert ev_cloud.dtype == np.float64 and ev_labels.dtype == np.int64
