@@ -12,7 +12,7 @@ from pathlib import Path
 
 LIB_NAME = "libattpc_b200.so"
 LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # flags (include/attpc_b200.h)
 KEEP_ALL_TB = 1 << 0
@@ -23,6 +23,7 @@ ROWS_KEEP_ALL = 1 << 4
 SKIP_CLOUD_COPY = 1 << 5
 COLUMNS = 1 << 6
 EXACT_MESH = 1 << 7
+COLUMNS32 = 1 << 8
 
 
 class AttpcConfig(C.Structure):
@@ -116,6 +117,10 @@ class AttpcResult(C.Structure):
         ("n_rk_steps", C.c_int64),
         ("n_rk_rejects", C.c_int64),
         ("max_track_passes", C.c_int64),
+        ("col_electrons32", C.POINTER(C.c_uint32)),
+        ("n_big", C.c_int64),
+        ("big_rows", C.POINTER(C.c_int64)),
+        ("big_electrons", C.POINTER(C.c_int64)),
         ("ms_order", C.c_float),
         ("reserved2", C.c_float),
     ]

@@ -76,6 +76,8 @@ struct PinnedArray {
 
 }  // namespace
 
+constexpr int64_t ATTPC_BIG_CAP = 1 << 20;  // (row, count) exceptions of the compact electrons column per call
+
 struct AttpcSim {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -100,6 +102,7 @@ struct AttpcSim {
     int32_t chunk_groups = 16;  // groups per kernel launch when the rows stay on the device
     int32_t unit_points = UNIT_POINTS;     // test knobs (AttpcConfig.unit_points / table_spill_keys)
     int32_t spill_keys = SMEM_SPILL_DEFAULT;
+    int64_t big_cap = ATTPC_BIG_CAP;             // exceptions accepted before a call returns the int64 column (<= ATTPC_BIG_CAP)
     int32_t hash_cap = 16384;
     int64_t group_point_cap = 0;
 
@@ -141,11 +144,14 @@ struct AttpcSim {
     // outputs
     DevArray<int16_t> col_pad_dev;
     DevArray<uint32_t> col_tbq_dev;
-    DevArray<int64_t> col_q_dev;
+    DevArray<int64_t> col_q_dev, big_rows_dev, big_q_dev;
+    DevArray<uint32_t> col_q32_dev;
     DevArray<int8_t> col_label_dev;
     PinnedArray<int16_t> col_pad_host;
     PinnedArray<uint32_t> col_tbq_host;
-    PinnedArray<int64_t> col_q_host;
+    PinnedArray<int64_t> col_q_host, big_rows_host, big_q_host;
+    PinnedArray<uint32_t> col_q32_host;
+    bool q32_off = false;  // sticky: a call overflowed the exception list (heavy ions): later calls copy int64 directly
     PinnedArray<int8_t> col_label_host;
     bool columns = false;  // sticky: once a call asked for columns the buffers are kept in step with the others
     DevArray<int64_t> offsets_dev, labels_dev, row_offsets_dev, row_labels_dev;
@@ -256,6 +262,9 @@ int ensure_out_buffers(AttpcSim* sim, int64_t n_events, int64_t n_points, bool k
         CU(sim->col_pad_dev.reserve(sim->labels_dev.n, keep, sim->stream));
         CU(sim->col_tbq_dev.reserve(sim->labels_dev.n, keep, sim->stream));
         CU(sim->col_q_dev.reserve(sim->labels_dev.n, keep, sim->stream));
+        CU(sim->col_q32_dev.reserve(sim->labels_dev.n, keep, sim->stream));
+        CU(sim->big_rows_dev.reserve(ATTPC_BIG_CAP));
+        CU(sim->big_q_dev.reserve(ATTPC_BIG_CAP));
         CU(sim->col_label_dev.reserve(sim->labels_dev.n, keep, sim->stream));
     }
     return ATTPC_OK;
@@ -479,6 +488,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     res->ms_h2d = ms_h2d;
     const bool copy_host = !(flags & ATTPC_SKIP_HOST_COPY);
     const bool use_columns = copy_host && (flags & ATTPC_COLUMNS);
+    const bool use_q32 = use_columns && (flags & ATTPC_COLUMNS32) && !sim->q32_off;
     const bool copy_cloud =
         copy_host && !use_columns && !((flags & ATTPC_SKIP_CLOUD_COPY) && (flags & ATTPC_SPYRAL_ROWS));
     if (use_columns) sim->columns = true;
@@ -501,7 +511,8 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     if (use_columns) {
         CU(sim->col_pad_host.reserve(sim->labels_dev.n));
         CU(sim->col_tbq_host.reserve(sim->labels_dev.n));
-        CU(sim->col_q_host.reserve(sim->labels_dev.n));
+        if (use_q32) CU(sim->col_q32_host.reserve(sim->labels_dev.n));
+        else CU(sim->col_q_host.reserve(sim->labels_dev.n));
         CU(sim->col_label_host.reserve(sim->labels_dev.n));
     }
     cudaStream_t G = sim->stream, T = sim->stream_t, C = sim->stream_c;
@@ -530,6 +541,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     Counters totals;
     memset(&totals, 0, sizeof totals);
     unsigned long long csr_before = 0;  // rows emitted by the launches completed so far
+    unsigned long long big_before = 0;  // ... and electron counts >= 2^32 among them
     int retries = 0;
     int64_t next_track = 0;  // launches whose track kernel is enqueued
 
@@ -608,6 +620,11 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             fa.col_pad = sim->col_pad_dev.p;
             fa.col_tb_q16 = sim->col_tbq_dev.p;
             fa.col_electrons = sim->col_q_dev.p;
+            fa.col_electrons32 = sim->col_q32_dev.p;
+            fa.big_rows = sim->big_rows_dev.p;
+            fa.big_electrons = sim->big_q_dev.p;
+            fa.big_count = sim->csr_total.p + 1;
+            fa.big_cap = sim->big_cap;
             fa.col_label = sim->col_label_dev.p;
         }
         fa.replay = plan.uniforms;
@@ -654,8 +671,12 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                                    (size_t)n_new * sizeof(int16_t), cudaMemcpyDeviceToHost, C));
                 CU(cudaMemcpyAsync(sim->col_tbq_host.p + copied, sim->col_tbq_dev.p + copied,
                                    (size_t)n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, C));
-                CU(cudaMemcpyAsync(sim->col_q_host.p + copied, sim->col_q_dev.p + copied,
-                                   (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+                if (use_q32)
+                    CU(cudaMemcpyAsync(sim->col_q32_host.p + copied, sim->col_q32_dev.p + copied,
+                                       (size_t)n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, C));
+                else
+                    CU(cudaMemcpyAsync(sim->col_q_host.p + copied, sim->col_q_dev.p + copied,
+                                       (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
                 CU(cudaMemcpyAsync(sim->col_label_host.p + copied, sim->col_label_dev.p + copied,
                                    (size_t)n_new * sizeof(int8_t), cudaMemcpyDeviceToHost, C));
             }
@@ -709,14 +730,15 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 if (use_columns) {
                     CU(sim->col_pad_host.reserve(sim->labels_dev.n, true));
                     CU(sim->col_tbq_host.reserve(sim->labels_dev.n, true));
-                    CU(sim->col_q_host.reserve(sim->labels_dev.n, true));
+                    if (use_q32) CU(sim->col_q32_host.reserve(sim->labels_dev.n, true));
+                    else CU(sim->col_q_host.reserve(sim->labels_dev.n, true));
                     CU(sim->col_label_host.reserve(sim->labels_dev.n, true));
                 }
             }
             rc = ensure_work_buffers(sim, std::min<int64_t>(n_events, launch_cap), ranks);
             if (rc) return rc;
-            sim->csr_host.p[0] = csr_before;  // forget the rows of the failed attempt
-            sim->csr_host.p[1] = 0;
+            sim->csr_host.p[0] = csr_before;  // forget the rows (and the big-count exceptions) of the failed attempt
+            sim->csr_host.p[1] = big_before;
             CU(cudaMemcpyAsync(sim->csr_total.p, sim->csr_host.p, 2 * sizeof(unsigned long long),
                                cudaMemcpyHostToDevice, G));
             CU(cudaStreamSynchronize(G));
@@ -734,6 +756,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         totals.rk_rejects += now.rk_rejects;
         totals.max_track_passes = std::max(totals.max_track_passes, now.max_track_passes);
         const unsigned long long csr_after = sim->csr_host.p[0];
+        big_before = sim->csr_host.p[1];
         if (copy_host && (copied < csr_after || copied_events < nb)) {  // whatever the chunk copies did not cover
             CU(cudaStreamWaitEvent(C, groups_done, 0));
             rc = copy_rows(csr_after, nb);
@@ -770,7 +793,29 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         if (use_columns) {
             res->col_pad = sim->col_pad_host.p;
             res->col_tb_q16 = sim->col_tbq_host.p;
-            res->col_electrons = sim->col_q_host.p;
+            if (!use_q32) {
+                res->col_electrons = sim->col_q_host.p;
+            } else if ((int64_t)big_before <= sim->big_cap) {
+                res->col_electrons32 = sim->col_q32_host.p;
+                res->n_big = (int64_t)big_before;
+                if (big_before > 0) {
+                    CU(sim->big_rows_host.reserve((int64_t)big_before));
+                    CU(sim->big_q_host.reserve((int64_t)big_before));
+                    CU(cudaMemcpyAsync(sim->big_rows_host.p, sim->big_rows_dev.p, (size_t)big_before * sizeof(int64_t),
+                                       cudaMemcpyDeviceToHost, C));
+                    CU(cudaMemcpyAsync(sim->big_q_host.p, sim->big_q_dev.p, (size_t)big_before * sizeof(int64_t),
+                                       cudaMemcpyDeviceToHost, C));
+                    res->big_rows = sim->big_rows_host.p;
+                    res->big_electrons = sim->big_q_host.p;
+                }
+            } else {  // too many exceptions for the list (heavy ions): the full-width column after all, and from now on
+                sim->q32_off = true;
+                CU(sim->col_q_host.reserve(sim->labels_dev.n));
+                if (n_points > 0)
+                    CU(cudaMemcpyAsync(sim->col_q_host.p, sim->col_q_dev.p, (size_t)n_points * sizeof(int64_t),
+                                       cudaMemcpyDeviceToHost, C));
+                res->col_electrons = sim->col_q_host.p;
+            }
             res->col_label = sim->col_label_host.p;
         }
     }
@@ -850,8 +895,8 @@ void attpc_destroy(AttpcSim* sim) {
     sim->offsets_dev.release(); sim->labels_dev.release(); sim->row_offsets_dev.release();
     sim->row_labels_dev.release(); sim->cloud_dev.release(); sim->rows_dev.release(); sim->row_kept.release();
     sim->row_sort_keys.release(); sim->row_sort_idx.release();
-    sim->col_pad_dev.release(); sim->col_tbq_dev.release(); sim->col_q_dev.release(); sim->col_label_dev.release();
-    sim->col_pad_host.release(); sim->col_tbq_host.release(); sim->col_q_host.release(); sim->col_label_host.release();
+    sim->col_pad_dev.release(); sim->col_tbq_dev.release(); sim->col_q_dev.release(); sim->col_q32_dev.release(); sim->big_rows_dev.release(); sim->big_q_dev.release(); sim->col_label_dev.release();
+    sim->col_pad_host.release(); sim->col_tbq_host.release(); sim->col_q_host.release(); sim->col_q32_host.release(); sim->big_rows_host.release(); sim->big_q_host.release(); sim->col_label_host.release();
     sim->offsets_host.release(); sim->labels_host.release(); sim->row_offsets_host.release();
     sim->row_labels_host.release(); sim->cloud_host.release(); sim->rows_host.release();
     if (sim->stream) cudaStreamDestroy(sim->stream);
@@ -941,6 +986,7 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
     if (cfg->table_spill_keys > 0) sim->spill_keys = std::min<int32_t>(cfg->table_spill_keys, SMEM_SPILL_AT);
     sim->group_events = std::min(sim->group_events, sim->launch_events);
     if (const char* env = getenv("ATTPC_CHUNK_GROUPS")) sim->chunk_groups = std::max(1, atoi(env));  // tuning aid
+    if (const char* env = getenv("ATTPC_BIG_CAP")) sim->big_cap = std::min<int64_t>(ATTPC_BIG_CAP, std::max(0, atoi(env)));  // tests
 
     const int64_t lut_cells = (int64_t)cfg->lut_n * cfg->lut_n;
     CUC(sim->lut.reserve(lut_cells));

@@ -1548,6 +1548,13 @@ struct FinalizeArgs {
     uint32_t* col_tb_q16;
     int64_t* col_electrons;
     int8_t* col_label;
+    // compact electrons column: the low 32 bits of every count, plus a list of (row, count) for the counts that
+    // need more (rare for light ions; the host falls back to col_electrons when the list overflows)
+    uint32_t* col_electrons32;
+    int64_t* big_rows;
+    int64_t* big_electrons;
+    unsigned long long* big_count;  // running number of exceptions of the call (also counts what did not fit)
+    int64_t big_cap;
 };
 
 constexpr uint32_t F_KEEP_ALL_TB = 1u, F_SPYRAL = 2u, F_NO_WIGGLE = 4u;
@@ -1821,6 +1828,14 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
             fa.col_pad[off + i] = (int16_t)pad;
             fa.col_tb_q16[off + i] = (tb << 16) | (uint32_t)(u * 65536.0);
             fa.col_electrons[off + i] = (long long)en.charge;
+            fa.col_electrons32[off + i] = (uint32_t)en.charge;
+            if (en.charge >> 32) {
+                const unsigned long long k = atomicAdd(fa.big_count, 1ULL);
+                if ((int64_t)k < fa.big_cap) {
+                    fa.big_rows[k] = off + i;
+                    fa.big_electrons[k] = (long long)en.charge;
+                }
+            }
             fa.col_label[off + i] = (int8_t)label;
         }
     }

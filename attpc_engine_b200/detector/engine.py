@@ -66,8 +66,10 @@ class SimBatch:
 
     Rows are either held as the reference's arrays (``cloud`` float64 ``[N, 3]`` = pad, time bucket, electrons;
     ``labels`` int64 ``[N]``) or, for batches simulated with ``columns=True``, as typed columns (``pad`` int16,
-    ``tb_q16`` uint32 = the float64 time bucket times 65536, exactly (Q16.16 fixed point), ``electrons`` int64,
-    ``label8`` int8: 15 instead of 32 bytes per row over PCIe).  ``cloud`` / ``labels`` / ``event(e)`` work in both
+    ``tb_q16`` uint32 = the float64 time bucket times 65536, exactly (Q16.16 fixed point), ``label8`` int8 and the
+    electron counts either as ``electrons`` int64 or -- the default for light ions -- as ``electrons_u32`` (count modulo
+    2^32) plus the sorted ``big_rows`` / ``big_electrons`` of the rows that need more: 11 instead of 32 bytes per row
+    over PCIe).  ``cloud`` / ``labels`` / ``event(e)`` work in both
     cases; with columns they are materialised on demand.
     """
 
@@ -81,10 +83,23 @@ class SimBatch:
         self.rows = rows  # [M, 8] Spyral rows
         self.row_labels = row_labels
         self.stats = {} if stats is None else stats
-        self.columns = columns  # dict(pad, tb_q16, electrons, label8) or None
+        self.columns = columns  # dict(pad, tb_q16, label8, and electrons or electrons_u32 + big_rows + big_electrons) or None
 
     def __len__(self) -> int:
         return len(self.offsets) - 1
+
+    def _electrons(self, a: int = 0, b: int | None = None) -> np.ndarray:
+        """Electron counts of rows ``a:b`` from the typed columns, as float64 (exact: counts are < 2^53)."""
+        c = self.columns
+        if "electrons" in c:
+            return c["electrons"][a:b].astype(np.float64)
+        out = c["electrons_u32"][a:b].astype(np.float64)  # low 32 bits; the few larger counts are listed apart
+        rows = c["big_rows"]
+        if len(rows):
+            b = len(c["electrons_u32"]) if b is None else b
+            lo, hi = np.searchsorted(rows, [a, b])
+            out[rows[lo:hi] - a] = c["big_electrons"][lo:hi]
+        return out
 
     @property
     def cloud(self) -> np.ndarray:
@@ -94,7 +109,7 @@ class SimBatch:
             out[:, 0] = c["pad"]
             out[:, 1] = c["tb_q16"]
             out[:, 1] *= 1.0 / 65536.0  # exact: Q16.16 fixed point
-            out[:, 2] = c["electrons"]
+            out[:, 2] = self._electrons()
             self._cloud = out
         return self._cloud
 
@@ -113,7 +128,7 @@ class SimBatch:
             cloud[:, 0] = c["pad"][a:b]
             cloud[:, 1] = c["tb_q16"][a:b]
             cloud[:, 1] *= 1.0 / 65536.0
-            cloud[:, 2] = c["electrons"][a:b]
+            cloud[:, 2] = self._electrons(int(a), int(b))
             return cloud, c["label8"][a:b].astype(np.int64)
         return self._cloud[a:b], self._labels[a:b]
 
@@ -130,7 +145,7 @@ _STAT_FIELDS = (
     "n_tracks", "n_trajectory_points", "n_active_points", "n_primary_electrons", "n_deposits", "n_keys",
     "ms_h2d", "ms_tracks", "ms_deposit", "ms_finalize", "ms_d2h", "ms_total", "n_kernel_launches", "n_retries",
     "n_track_launches", "n_group_launches", "n_hash_probes", "hash_capacity", "n_table_flushes",
-    "n_rk_steps", "n_rk_rejects", "max_track_passes", "ms_order",
+    "n_rk_steps", "n_rk_rejects", "max_track_passes", "ms_order", "n_big",
 )  # fmt: skip
 
 
@@ -285,9 +300,17 @@ class Engine:
             columns = dict(
                 pad=take(res.col_pad) if take else np.zeros(0, np.int16),
                 tb_q16=take(res.col_tb_q16) if take else np.zeros(0, np.uint32),
-                electrons=take(res.col_electrons) if take else np.zeros(0, np.int64),
                 label8=take(res.col_label) if take else np.zeros(0, np.int8),
             )
+            if res.col_electrons32:  # compact: low 32 bits + the (row, count) pairs of the counts that need more
+                n_big = int(res.n_big)
+                rows_big = np.ctypeslib.as_array(res.big_rows, shape=(n_big,)).copy() if n_big else np.zeros(0, np.int64)
+                vals_big = np.ctypeslib.as_array(res.big_electrons, shape=(n_big,)).copy() if n_big else np.zeros(0, np.int64)
+                order = np.argsort(rows_big, kind="stable")
+                columns.update(electrons_u32=take(res.col_electrons32) if take else np.zeros(0, np.uint32),
+                               big_rows=rows_big[order], big_electrons=vals_big[order])
+            else:
+                columns["electrons"] = take(res.col_electrons) if take else np.zeros(0, np.int64)
             cloud = labels = None
         elif n_pts > 0 and res.cloud:
             cloud = grab(np.ctypeslib.as_array(res.cloud, shape=(n_pts, 3)))
@@ -333,7 +356,7 @@ class Engine:
         """`simulate` (`simulator.py:52-115`) for ``B`` events at once: ``momenta [B, K, 4]``, ``vertices [B, 3]``.
 
         ``rows_only`` (with ``spyral_rows``): bring back offsets and Spyral rows but leave the raw cloud on the GPU.
-        ``columns``: bring the rows back as typed columns (15 B/row instead of 32 B/row over PCIe), see `SimBatch`.
+        ``columns``: bring the rows back as typed columns (11 B/row instead of 32 B/row over PCIe), see `SimBatch`.
         """
         momenta = np.ascontiguousarray(momenta, dtype=np.float64)
         vertices = np.ascontiguousarray(vertices, dtype=np.float64)
@@ -348,7 +371,7 @@ class Engine:
         if rows_only and spyral_rows:
             flags |= _lib.SKIP_CLOUD_COPY
         elif columns:
-            flags |= _lib.COLUMNS
+            flags |= _lib.COLUMNS | _lib.COLUMNS32
         flags |= self._mesh_flag()
         res = _lib.AttpcResult()
         code = self.lib.attpc_simulate(

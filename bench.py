@@ -293,7 +293,7 @@ def run_ours(args):
     wall_dev = time.perf_counter() - wall0
     # ---- e2e: host buffers in, host buffers out
     barrier()
-    e2e_s, e2e_points, e2e_rows = 0.0, 0, 0
+    e2e_s, e2e_points, e2e_rows, e2e_big = 0.0, 0, 0, 0
     for i in range(0 if args.no_e2e else args.steps):
         flush_l2()
         barrier()
@@ -302,6 +302,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_s += time.perf_counter() - t0
         e2e_points += st["n_points"]
+        e2e_big += st.get("n_big", 0)
         e2e_rows += st.get("n_rows", 0)
     barrier()
     clocks = sampler.stop()
@@ -371,8 +372,8 @@ def run_ours(args):
                 "h2d_bytes_per_step": int(momenta.nbytes + vertices.nbytes),
                 "result": ("Spyral rows float64[M,8] + labels" if args.spyral else
                            "cloud float64[N,3] + int64 labels" if args.float64_rows else
-                           "typed columns: pad int16, time bucket uint32 Q16.16, electrons int64, label int8"),
-                "d2h_bytes_per_step": int((e2e_rows * 72 if args.spyral else e2e_points * (32 if args.float64_rows else 15)) / args.steps
+                           "typed columns: pad int16, time bucket uint32 Q16.16, electrons uint32 + list of the counts >= 2^32, label int8"),
+                "d2h_bytes_per_step": int((e2e_rows * 72 if args.spyral else e2e_points * (32 if args.float64_rows else 11) + 16 * e2e_big) / args.steps
                                           + (B + 1) * 8 * (2 if args.spyral else 1))},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }  # fmt: skip

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ATTPC_ABI_VERSION 4
+#define ATTPC_ABI_VERSION 5
 
 enum {
     ATTPC_OK = 0,
@@ -40,6 +40,9 @@ enum {
     ATTPC_SKIP_CLOUD_COPY = 1u << 5,/* with ATTPC_SPYRAL_ROWS: copy offsets and rows to the host, not the raw cloud */
     ATTPC_COLUMNS = 1u << 6,       /* host result as typed columns (col_* of AttpcResult, 15 B/row) instead of the
                                       float64 cloud + int64 labels (32 B/row); same rows, same order */
+    ATTPC_COLUMNS32 = 1u << 8,     /* with ATTPC_COLUMNS: electrons as uint32 (low 32 bits) + a list of the (row, count)
+                                      pairs that need more: 11 B/row.  A call with more than 2^20 such rows returns
+                                      the int64 column instead (and so do the later calls on the handle) */
     ATTPC_EXACT_MESH = 1u << 7     /* validation: evaluate every mesh pixel with the reference's own expression
                                       (detector/transporter.py:36-41, 240-246).  The default reads pdf * step^2 from
                                       the constant 10x10 weight table and falls back to that expression only where
@@ -141,6 +144,11 @@ typedef struct AttpcResult {
     int64_t n_rk_steps;          /* Dormand-Prince steps tried (accepted + rejected) */
     int64_t n_rk_rejects;        /* of which rejected by the error control */
     int64_t max_track_passes;    /* most step/emit passes any single track needed: the serial critical path */
+    /* ATTPC_COLUMNS32: either col_electrons32 (+ the exceptions) or col_electrons is set, never both */
+    const uint32_t* col_electrons32; /* [n_points] electrons modulo 2^32 */
+    int64_t n_big;                   /* rows whose count is >= 2^32 */
+    const int64_t* big_rows;         /* [n_big] row index (unordered) */
+    const int64_t* big_electrons;    /* [n_big] full count of that row */
     float ms_order;              /* device time of the point ordering kernels (scan + scatter) before the deposit kernel;
                                     ms_deposit is the deposit kernel alone */
     float reserved2;

@@ -252,7 +252,7 @@ def test_full_size_properties(name, n_events):
 
 
 def test_typed_columns_hold_the_same_rows(dist):
-    """`columns=True` changes the wire format (15 B/row instead of 32 B/row), not the content."""
+    """`columns=True` changes the wire format (11 B/row instead of 32 B/row), not the content."""
     cfg, m, v, zs, as_, idx = _workload(dist, "c16dd", 200)
     plain = simulate_batch(m, v, zs, as_, cfg, 31, idx)
     cols = simulate_batch(m, v, zs, as_, cfg, 31, idx, columns=True, max_events_per_launch=64, copy_events_per_launch=64)
@@ -262,6 +262,29 @@ def test_typed_columns_hold_the_same_rows(dist):
     ev_cloud, ev_labels = cols.event(17)
     assert ev_cloud.dtype == np.float64 and ev_labels.dtype == np.int64
     assert np.array_equal(ev_cloud, plain.event(17)[0]) and np.array_equal(ev_labels, plain.event(17)[1])
+    assert np.array_equal(cols.cloud, plain.cloud) and np.array_equal(cols.labels, plain.labels)
+
+
+@pytest.mark.parametrize("compact", [True, False])
+def test_typed_columns_with_large_electron_counts(compact, monkeypatch):
+    """Heavy ions put more than 2^32 electrons on a pad: those rows are listed beside the uint32 column; a call with
+    more of them than the list takes (forced here through ATTPC_BIG_CAP) comes back with the int64 column.  Both hold
+    the same rows as the float64 path."""
+    import bench
+
+    cfg, m, v, zs, as_, idx = bench.build_workload("sn132dp", 150)
+    plain = simulate_batch(m, v, zs, as_, cfg, 3, idx)
+    if not compact:
+        monkeypatch.setenv("ATTPC_BIG_CAP", "2")
+    # (a tuning value of its own gives the call its own engine, created under the environment above)
+    cols = simulate_batch(m, v, zs, as_, cfg, 3, idx, columns=True, hash_capacity=16384 if compact else 32768)
+    assert ("electrons_u32" in cols.columns) == compact
+    if compact:
+        assert len(cols.columns["big_rows"]) > 2 and cols.columns["electrons_u32"].dtype == np.uint32
+    else:
+        assert cols.columns["electrons"].dtype == np.int64
+    assert np.array_equal(cols.offsets, plain.offsets)
+    assert np.array_equal(cols.event(7)[0], plain.event(7)[0])
     assert np.array_equal(cols.cloud, plain.cloud) and np.array_equal(cols.labels, plain.labels)
 
 
