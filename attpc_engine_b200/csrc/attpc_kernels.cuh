@@ -1,14 +1,17 @@
 // Device code of the AT-TPC detector-simulation hot path for B200 (sm_100a).
 //
 // Stages (one kernel each, all launched on the handle's stream; see DESIGN.md for the data layout):
-//   track_kernel      Lorentz force + energy loss, Dormand-Prince 5(4) on the reference's 0.1 ns grid, one lane
-//                     per track with a dynamic work cursor; fused Fano electrons, >=1 mask, gain, z -> time bucket
-//                     (detector/solver.py:19-76, 243-305, 308-347, 386-398).
+//   track_plan_*      longest-first launch order of the tracks (expected lifetime), stable four-class partition.
+//   track_kernel      Lorentz force + energy loss, Dormand-Prince 5(4) on the reference's 0.1 ns grid: a lane owns a
+//                     track (dynamic work cursor), the warp shares the grid points of all accepted steps; fused Fano
+//                     electrons, >=1 mask, gain, z -> time bucket (detector/solver.py:19-76, 243-305, 308-347, 386-398).
 //   replay_kernel     the same electron/mask/gain/time arithmetic from GIVEN trajectory rows and normals, in the
 //                     reference's exact operation order (parity part (a)).
-//   deposit_kernel    one warp per active point: sigma_t, 10x10 mesh, pad lookup, bivariate-normal share, Szudzik
-//                     key, accumulate into the event's open-addressing table kept L2-resident
-//                     (detector/transporter.py:11-41, 78-120, 123-249, 252-317; detector/pairing.py:6-28).
+//   point_scan/order  per-event work units, points into (event, rank, arrival) order, sigma_t and the pad-table rows and
+//                     columns of the 10x10 mesh of every point (detector/transporter.py:78-120, 217-226, 301).
+//   deposit_kernel    one CTA per work unit, one lane per mesh row: pad lookup, bivariate-normal share, accumulation
+//                     per (pad, time bucket) in a shared-memory open-addressing table that is appended to the event's
+//                     entry list in dense segments (detector/transporter.py:11-41, 123-249, 252-317; pairing.py:6-28).
 //   collect/scan/emit TB wiggle, 0 <= tb < 512 mask, canonical (ascending time bucket, pad) order, CSR compaction
 //                     (detector/simulator.py:19-49, 104-115); optional Spyral rows (detector/writer.py:61-112).
 //
@@ -1031,7 +1034,7 @@ __global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView
         }
         if (e < gv.n_events) {
             unsigned u0 = s_ubase + s_part[tid] - nu;
-            gv.mode[gv.first_slot + e] = nu > 1 ? 1u : 0u;  // several units merge through the event's global table
+            gv.mode[gv.first_slot + e] = nu > 1 ? 1u : 0u;  // several units: a key may be listed once per unit
             for (unsigned k = 0; k < nu; ++k) {
                 const unsigned u = u0 + k;
                 if (u < (unsigned)pb.max_units) {
@@ -1279,8 +1282,8 @@ __device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t,
     return ((unsigned long long)hi << 32) | t.lo[slot];
 }
 
-// One CTA per work unit (a slice of one event's points).  Tracks are processed in rank order (label = last track
-// to touch a key, detector/transporter.py:166-169, 247-249).
+// One CTA per work unit (a slice of one event's points, all tracks together; label = last track in `indices` order
+// to touch a key, detector/transporter.py:166-169, 247-249 = the highest rank, kept with an atomicMax).
 //
 // A warp takes three active points per pass; lane (s, i) owns row i (one x of the 10x10 mesh) of point s and walks
 // the ten y of that row in the reference's pixel order.  Neighbouring pixels of a row usually fall on the same pad, so
@@ -1288,8 +1291,9 @@ __device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t,
 // on its own first, exactly as transporter.py:240-248 does) and only a finished run (key, charge) is pushed into the
 // warp's ring in shared memory.  Whenever the ring holds 32 runs, all 32 lanes insert one each into the CTA's
 // open-addressing table: the insert code (probe loop, two atomics) runs once per 32 runs instead of once per 32
-// pixels.  At the end the table is compacted into the event's dense entry list (events of one unit) or merged into
-// the event's global table (events split over several units, and units dense enough to overflow the shared table).
+// pixels.  The table is appended to the event's entry list as a dense segment whenever it reaches the spill threshold
+// and at the end; events deposited in several segments (dense events, events split over several units) may then list
+// a key several times, which collect_kernel merges after sorting.
 __global__ void __launch_bounds__(DEPOSIT_THREADS, 4)
 deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk, Counters* ctr) {
     const GroupView gv = sub_group(chunk, blockIdx.y);

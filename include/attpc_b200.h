@@ -133,7 +133,7 @@ typedef struct AttpcResult {
     int64_t n_hash_probes;       /* table slots inspected by the deposits (n_hash_probes / n_deposits ~ 1 is healthy) */
     int32_t hash_capacity;       /* slots per event in use at the end of the call */
     int32_t reserved1;
-    int64_t n_table_flushes;     /* shared-memory tables merged into a global table (dense or split events) */
+    int64_t n_table_flushes;     /* shared-memory tables appended to an event's entry list before the end of their work unit */
     /* ATTPC_COLUMNS: the rows of `cloud` / `labels` as typed columns (pinned host memory) */
     const int16_t* col_pad;      /* [n_points] pad id */
     const uint32_t* col_tb_q16;  /* [n_points] time bucket + wiggle as Q16.16 fixed point: cloud[:, 1] == col_tb_q16 / 65536
