@@ -1257,10 +1257,9 @@ __device__ __forceinline__ unsigned smem_find(const SmemTable& t, unsigned key1,
             }
             if ((w & SMEM_KEY_MASK) == key1) break;
         }
-        probes += 1u;
+        probes += 1u;  // (extra probes; the first probe of every insert is counted from the number of pushes)
         slot = slot + 1u == (unsigned)SMEM_SLOTS ? 0u : slot + 1u;
     }
-    probes += 1u;
     return slot;
 }
 
@@ -1329,9 +1328,12 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
     unsigned n_dep = 0, n_probe = 0, n_new = 0;
     const int sub = lane / MESH_N;                                  // point of the warp's triple; 3 = idle lanes 30, 31
     const int row = lane - sub * MESH_N;                            // mesh row (x index) of this lane
-    double wrow[MESH_N];  // constant mesh weights of this lane's row
-#pragma unroll
-    for (int j = 0; j < MESH_N; ++j) wrow[j] = P.mesh_w[row * MESH_N + j];
+    // constant mesh weights: the rows differ from lane to lane, so they are read from shared memory (row stride 11
+    // doubles: the ten rows start in ten different bank pairs), not through the constant cache
+    __shared__ double s_w[MESH_N][MESH_N + 1];
+    for (int k = threadIdx.x; k < MESH_N * MESH_N; k += blockDim.x) s_w[k / MESH_N][k % MESH_N] = P.mesh_w[k];
+    __syncthreads();
+    const double* wrow = s_w[row];
     const bool exact_mesh = gv.exact_mesh != 0;
     unsigned* qkey = s_qkey[warp];
     unsigned* qlo = s_qlo[warp];
@@ -1512,7 +1514,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
         append_segment(false);
     }
     append_segment(true);
-    unsigned long long n_dep64 = n_dep, n_probe64 = n_probe;
+    unsigned long long n_dep64 = n_dep, n_probe64 = n_probe + (lane == 0 ? q_tail : 0u);  // q_tail: runs pushed = inserts
     for (int o = 16; o > 0; o >>= 1) {
         n_dep64 += __shfl_xor_sync(FULL, n_dep64, o);
         n_probe64 += __shfl_xor_sync(FULL, n_probe64, o);
