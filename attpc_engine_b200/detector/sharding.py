@@ -8,9 +8,48 @@ gather of the finished CSR clouds to the writer, done here on the host.
 
 from __future__ import annotations
 
+import os
+import subprocess
+
 import numpy as np
 
 from .engine import SimBatch
+
+
+def parse_cpu_list(text: str) -> set[int]:
+    """``"0-3,8,10-11"`` (the format of ``/sys/.../local_cpulist``) -> ``{0, 1, 2, 3, 8, 10, 11}``."""
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device: int) -> set[int] | None:
+    """Pin the calling process to the CPUs next to GPU ``device`` (Linux; best effort, returns the CPU set or None).
+
+    A call that brings its rows to the host is PCIe-bound, and with one process per GPU the pinned result buffers
+    should live on the NUMA node the GPU's PCIe link ends in: otherwise half the ranks of a two-socket box push their
+    rows across the socket interconnect.  Call it before the first simulation of the process (the library allocates
+    its pinned buffers in the calling thread, so first touch puts them on that node).
+    """
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(int(device))],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()  # fmt: skip
+        if not bus:
+            return None
+        if len(bus.split(":")[0]) == 8:  # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        cpus = parse_cpu_list(open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read())
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except (OSError, ValueError, subprocess.SubprocessError):
+        return None
 
 
 def shard_range(n_events: int, rank: int, world: int) -> tuple[int, int]:

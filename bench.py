@@ -236,6 +236,12 @@ def run_ours(args):
     from attpc_engine_b200.detector.simulator import _nuclei_for
     from attpc_engine_b200 import nuclear_map
 
+    local_env = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_cpus = None
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.no_numa:
+        from attpc_engine_b200.detector.sharding import bind_to_gpu_numa_node
+
+        numa_cpus = bind_to_gpu_numa_node(local_env)  # before CUDA starts: pinned buffers land next to the GPU
     rank, world, local, dist = dist_setup(args.gpus)
     torch.cuda.set_device(local)
     B = args.events
@@ -313,6 +319,10 @@ def run_ours(args):
     electrons = reduce_sum(dist, stats_sum["n_primary_electrons"], local)
     points = reduce_sum(dist, stats_sum["n_points"], local)
     deposits = reduce_sum(dist, stats_sum["n_deposits"], local)
+    # bytes this rank brought to the host per step of the e2e loop (rows + CSR offsets), summed over the ranks
+    row_bytes = e2e_rows * 72 if args.spyral else e2e_points * (32 if args.float64_rows else 11) + 16 * e2e_big
+    d2h_local = 0.0 if args.no_e2e else row_bytes / max(1, args.steps) + (B + 1) * 8 * (2 if args.spyral else 1)
+    d2h_total = reduce_sum(dist, d2h_local, local)
 
     if rank != 0:
         return
@@ -358,6 +368,7 @@ def run_ours(args):
             "workload": f"{args.workload}: {WORKLOADS[args.workload]['desc']}", "events_per_gpu_per_step": B,
             "nuclei_per_event": K, "tracks": indices, "l2": "flushed between steps (256 MiB device write)",
             "dedx": "analytic Bethe+Lindhard table (not CATIMA)", "parallelism": f"event-range shards x{world}",
+            "numa": f"rank 0 bound to {len(numa_cpus)} CPUs next to its GPU" if numa_cpus else "no binding",
             "output": "raw cloud [pad, tb, e] + Spyral rows (response, threshold, z-sort)" if args.spyral else "raw cloud [pad, tb, e]",
         },
         "electrons_per_s": round(electrons / dev_s, 1), "cloud_points_per_s": round(points / dev_s, 1),
@@ -369,12 +380,11 @@ def run_ours(args):
                       "rhs_evals_per_track": round((6 * stats_sum["n_rk_steps"] + stats_sum["n_tracks"]) / max(1, stats_sum["n_tracks"]), 1)},
         "wall_s_device_loop": round(wall_dev, 3),
         "e2e": {"value": None if args.no_e2e else round(total_events / e2e_s, 1), "unit": "events/s",
-                "h2d_bytes_per_step": int(momenta.nbytes + vertices.nbytes),
+                "h2d_bytes_per_step": int(momenta.nbytes + vertices.nbytes) * world,
                 "result": ("Spyral rows float64[M,8] + labels" if args.spyral else
                            "cloud float64[N,3] + int64 labels" if args.float64_rows else
                            "typed columns: pad int16, time bucket uint32 Q16.16, electrons uint32 + list of the counts >= 2^32, label int8"),
-                "d2h_bytes_per_step": int((e2e_rows * 72 if args.spyral else e2e_points * (32 if args.float64_rows else 11) + 16 * e2e_big) / args.steps
-                                          + (B + 1) * 8 * (2 if args.spyral else 1))},
+                "d2h_bytes_per_step": int(d2h_total)},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }  # fmt: skip
     if world == 1 and not args.no_cpu:
@@ -446,6 +456,7 @@ def main():
     ap.add_argument("--cpu-cores", type=int, default=0)
     ap.add_argument("--cpu-events-per-core", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa", action="store_true", help="multi-GPU: do not bind each rank to the CPUs next to its GPU")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: only the device-resident steps")
     ap.add_argument("--spyral", action="store_true", help="also produce the Spyral 8-column rows (full pad-plane response)")
     ap.add_argument("--float64-rows", action="store_true",

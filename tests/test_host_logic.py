@@ -157,3 +157,20 @@ def test_concat_batches_rebases_offsets():
     assert whole.stats["n_points"] == 10 and "ms_total" not in whole.stats
     with pytest.raises(ValueError):
         concat_batches([a, c])
+
+
+def test_cpu_list_parser_and_numa_binding_is_best_effort():
+    """`bind_to_gpu_numa_node` reads sysfs CPU lists; without a GPU (here) it must return None and change nothing."""
+    import os
+
+    from attpc_engine_b200.detector.sharding import bind_to_gpu_numa_node, parse_cpu_list
+
+    assert parse_cpu_list("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert parse_cpu_list("") == set()
+    before = os.sched_getaffinity(0)
+    got = bind_to_gpu_numa_node(0)
+    assert got is None or got <= before
+    if got is None:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
