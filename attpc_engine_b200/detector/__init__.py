@@ -2,7 +2,14 @@
 
 from .parameters import Config, DetectorParams, ElectronicsParams, PadParams
 from .simulator import SimEvent, run_simulation, simulate, simulate_batch
-from .writer import ArrayWriter, SimulationWriter, SpyralWriter, convert_to_spyral
+from .writer import (
+    ArrayWriter,
+    ParquetCloudWriter,
+    SimulationWriter,
+    SpyralWriter,
+    convert_to_spyral,
+    read_parquet_clouds,
+)
 
 __all__ = [
     "run_simulation",
@@ -15,6 +22,8 @@ __all__ = [
     "Config",
     "SpyralWriter",
     "ArrayWriter",
+    "ParquetCloudWriter",
+    "read_parquet_clouds",
     "SimulationWriter",
     "convert_to_spyral",
 ]

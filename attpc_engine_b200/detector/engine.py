@@ -130,7 +130,7 @@ class SimBatch:
             cloud[:, 1] *= 1.0 / 65536.0
             cloud[:, 2] = self._electrons(int(a), int(b))
             return cloud, c["label8"][a:b].astype(np.int64)
-        return self._cloud[a:b], self._labels[a:b]
+        return self.cloud[a:b], self.labels[a:b]
 
     def event_rows(self, e: int) -> tuple[np.ndarray, np.ndarray]:
         a, b = self.row_offsets[e], self.row_offsets[e + 1]

@@ -205,7 +205,8 @@ def run_simulation(
             momenta, vertices, kin.proton_numbers, kin.mass_numbers, config, seed, nuclei_to_sim,
             first_event=start, device=device, spyral_rows=want_rows, copy=False,
             rows_only=want_rows and bool(getattr(writer, "rows_only", False)),
-            columns=not batched,  # per-event writers get their arrays built event by event anyway
+            # per-event writers get their arrays built event by event anyway; batch writers say if they want columns
+            columns=not batched or bool(getattr(writer, "wants_columns", False)),
         )  # fmt: skip
         if batched:
             writer.write_batch(batch, config)

@@ -248,3 +248,100 @@ class ArrayWriter:
 
     def close(self) -> None:
         self._flush()
+
+
+class ParquetCloudWriter:
+    """Bulk columnar writer of the raw point clouds: ``run_{n:04d}.parquet`` via pyarrow.
+
+    One table row per cloud point, in event order and, inside an event, in the engine's canonical (time bucket, pad)
+    order: ``event`` int64, ``pad`` int16, ``tb`` float64 (time bucket + wiggle), ``electrons`` int64, ``label`` int8.
+    It takes whole batches (``write_batch``) as typed columns, so no Python loop over events or points stands between
+    the GPU and the file; the per-event ``write`` of the `SimulationWriter` protocol works too.  Files roll over at
+    ``max_events_per_file`` events like the reference's writer (`writer.py:214-218`).  `read_parquet_clouds` turns a
+    file back into CSR arrays.
+    """
+
+    wants_columns = True  # `run_simulation`: bring the rows to the host as typed columns (11 B/row over PCIe)
+
+    def __init__(self, directory_path: Path, config: Config | None = None, max_events_per_file: int = 1_000_000,
+                 first_run_number: int = 0, compression: str = "zstd"):  # fmt: skip
+        import pyarrow  # noqa: F401  (fail at construction, not at the first write)
+
+        self.directory_path = Path(directory_path)
+        self.max_events_per_file = int(max_events_per_file)
+        self.run_number = int(first_run_number)
+        self.compression = compression
+        self._writer = None
+        self._events_in_file = 0
+        self.directory_path.mkdir(parents=True, exist_ok=True)
+
+    def _table(self, event, pad, tb, electrons, label):
+        import pyarrow as pa
+
+        return pa.table({
+            "event": pa.array(event, type=pa.int64()), "pad": pa.array(pad, type=pa.int16()),
+            "tb": pa.array(tb, type=pa.float64()), "electrons": pa.array(electrons, type=pa.int64()),
+            "label": pa.array(label, type=pa.int8()),
+        })  # fmt: skip
+
+    def _emit(self, table, n_events: int) -> None:
+        import pyarrow.parquet as pq
+
+        if self._writer is not None and self._events_in_file + n_events > self.max_events_per_file:
+            self._close_file()
+            self.run_number += 1
+        if self._writer is None:
+            path = self.directory_path / f"run_{self.run_number:04d}.parquet"
+            self._writer = pq.ParquetWriter(path, table.schema, compression=self.compression)
+            self._events_in_file = 0
+        self._writer.write_table(table)
+        self._events_in_file += n_events
+
+    def write(self, data: np.ndarray, labels: np.ndarray, config: Config, event_number: int) -> None:
+        data = np.asarray(data, dtype=np.float64).reshape(-1, 3)
+        n = len(data)
+        self._emit(self._table(np.full(n, int(event_number), np.int64), data[:, 0].astype(np.int16), data[:, 1],
+                               data[:, 2].astype(np.int64), np.asarray(labels).astype(np.int8)), 1)  # fmt: skip
+
+    def write_batch(self, batch: SimBatch, config: Config | None = None) -> None:
+        counts = np.diff(batch.offsets)
+        event = np.repeat(batch.first_event + np.arange(len(batch), dtype=np.int64), counts)
+        c = batch.columns
+        if c is not None:
+            tb = c["tb_q16"].astype(np.float64)
+            tb *= 1.0 / 65536.0
+            electrons = c["electrons"] if "electrons" in c else batch._electrons().astype(np.int64)
+            table = self._table(event, c["pad"], tb, electrons, c["label8"])
+        else:
+            cloud = batch.cloud
+            table = self._table(event, cloud[:, 0].astype(np.int16), cloud[:, 1], cloud[:, 2].astype(np.int64),
+                                batch.labels.astype(np.int8))  # fmt: skip
+        self._emit(table, len(batch))
+
+    def _close_file(self) -> None:
+        if self._writer is not None:
+            self._writer.close()
+            self._writer = None
+
+    def get_directory_name(self) -> Path:
+        return self.directory_path
+
+    def close(self) -> None:
+        self._close_file()
+
+
+def read_parquet_clouds(path: Path) -> tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+    """``(event_numbers [E], offsets [E + 1], cloud [N, 3] float64, labels [N] int64)`` of a `ParquetCloudWriter` file
+    (events without points do not appear, like in the reference's files)."""
+    import pyarrow.parquet as pq
+
+    t = pq.read_table(path)
+    event = t["event"].to_numpy()
+    cloud = np.empty((len(event), 3), dtype=np.float64)
+    cloud[:, 0] = t["pad"].to_numpy()
+    cloud[:, 1] = t["tb"].to_numpy()
+    cloud[:, 2] = t["electrons"].to_numpy()
+    labels = t["label"].to_numpy().astype(np.int64)
+    starts = np.flatnonzero(np.r_[True, event[1:] != event[:-1]]) if len(event) else np.zeros(0, np.int64)
+    offsets = np.r_[starts, len(event)].astype(np.int64)
+    return event[starts].astype(np.int64), offsets, cloud, labels

@@ -149,6 +149,24 @@ def test_run_simulation_with_array_writer(dist, tmp_path):
     assert np.array_equal(np.concatenate([s[1] for s in w.seen]), direct.cloud)
 
 
+def test_run_simulation_with_parquet_writer(dist, tmp_path):
+    """run_simulation -> typed columns over PCIe -> ParquetCloudWriter: the file holds what simulate_batch returns."""
+    pytest.importorskip("pyarrow")
+    from attpc_engine_b200.detector import ParquetCloudWriter, read_parquet_clouds
+    from attpc_engine_b200.kinematics import save_kinematics_npz
+
+    cfg, m, v, zs, as_, idx = _workload(dist, "c16dd", 50)
+    kin = tmp_path / "kin.npz"
+    save_kinematics_npz(kin, v, m, zs, as_)
+    writer = ParquetCloudWriter(tmp_path / "out")
+    run_simulation(cfg, kin, writer, indices=idx, seed=12, batch_size=32, verbose=False)
+    want = simulate_batch(m, v, zs, as_, cfg, 12, idx)
+    ev, off, cloud, labels = read_parquet_clouds(tmp_path / "out" / "run_0000.parquet")
+    nonempty = np.flatnonzero(np.diff(want.offsets))
+    assert np.array_equal(ev, nonempty) and np.array_equal(np.diff(off), np.diff(want.offsets)[nonempty])
+    assert np.array_equal(cloud, want.cloud) and np.array_equal(labels, want.labels)
+
+
 def test_spyral_writer_layout_through_h5py_stand_in(dist, monkeypatch, tmp_path):
     """File layout of the reference's SpyralWriter (writer.py:164-281), with h5py replaced by an in-memory fake."""
     sys.path.insert(0, str((__import__("pathlib").Path(__file__).parent / "golden")))

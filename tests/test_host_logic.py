@@ -174,3 +174,36 @@ def test_cpu_list_parser_and_numa_binding_is_best_effort():
         assert os.sched_getaffinity(0) == before
     else:
         os.sched_setaffinity(0, before)
+
+
+def test_parquet_cloud_writer_round_trip(tmp_path):
+    """Bulk columnar output: typed columns -> parquet -> the same CSR clouds, file roll-over included."""
+    pytest.importorskip("pyarrow")
+    from attpc_engine_b200.detector import ParquetCloudWriter, read_parquet_clouds
+    from attpc_engine_b200.detector.engine import SimBatch
+
+    rng = np.random.default_rng(1)
+
+    def batch(first, counts):
+        off = np.r_[0, np.cumsum(counts)].astype(np.int64)
+        n = int(off[-1])
+        cols = dict(pad=rng.integers(0, 10240, n).astype(np.int16),
+                    tb_q16=rng.integers(10 << 16, 500 << 16, n).astype(np.uint32),
+                    label8=rng.integers(2, 4, n).astype(np.int8),
+                    electrons_u32=rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32),
+                    big_rows=np.array([1], np.int64), big_electrons=np.array([2**33 + 5], np.int64))  # fmt: skip
+        return SimBatch(first, off, columns=cols)
+
+    a, b = batch(100, [3, 0, 5, 2]), batch(104, [4, 4])
+    w = ParquetCloudWriter(tmp_path, max_events_per_file=4)
+    w.write_batch(a)
+    w.write_batch(b)  # does not fit the first file any more
+    w.write(b.event(1)[0], b.event(1)[1], None, 200)  # the per-event protocol works too
+    w.close()
+    ev, off, cloud, labels = read_parquet_clouds(tmp_path / "run_0000.parquet")
+    assert list(ev) == [100, 102, 103] and list(off) == [0, 3, 8, 10]  # the empty event leaves no trace
+    assert np.array_equal(cloud, a.cloud) and np.array_equal(labels, a.labels)
+    assert cloud[1, 2] == 2**33 + 5
+    ev, off, cloud, labels = read_parquet_clouds(tmp_path / "run_0001.parquet")
+    assert list(ev) == [104, 105, 200] and list(off) == [0, 4, 8, 12]
+    assert np.array_equal(cloud[:8], b.cloud) and np.array_equal(cloud[8:], b.event(1)[0])
