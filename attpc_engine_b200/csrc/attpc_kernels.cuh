@@ -1625,9 +1625,14 @@ collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
         if (key1 == 0u) return;
         occupied += 1;
         const unsigned tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
-        const unsigned key = szudzik_pair(tb, pad);  // detector/pairing.py: id of the (tb, pad) cell
-        const double tbf = (double)tb + wiggle_of(fa, slot_event, key, ctr);      // detector/simulator.py:108
-        if ((fa.flags & F_KEEP_ALL_TB) || (0.0 <= tbf && tbf < (double)NUM_TB)) {  // detector/simulator.py:111
+        // detector/simulator.py:108-113: keep 0 <= tb + u < 512 with u in [0, 1).  Only the last bucket needs u (a
+        // replayed 53-bit uniform can round 511 + u up to 512.0); emit_kernel draws the wiggle of the rows it writes.
+        bool keep = (fa.flags & F_KEEP_ALL_TB) || tb < (unsigned)NUM_TB - 1u;
+        if (!keep && tb == (unsigned)NUM_TB - 1u) {
+            const unsigned key = szudzik_pair(tb, pad);  // detector/pairing.py: id of the (tb, pad) cell
+            keep = (double)tb + wiggle_of(fa, slot_event, key, ctr) < (double)NUM_TB;
+        }
+        if (keep) {
             atomicAdd(&s_hist[min(tb, (unsigned)TB_BINS - 1u)], 1u);
             stash[atomicAdd(&s_n, 1u)] = make_item(tb, pad, (unsigned)i);
         }
