@@ -53,9 +53,12 @@ constexpr double NORMAL_ABS_MAX = 8.66;
 __device__ __forceinline__ double philox_normal(uint64_t seed, uint64_t event, uint32_t stream, uint32_t index) {
     const Philox4 r = philox4x32_10((uint32_t)event, (uint32_t)(event >> 32), stream, index, (uint32_t)seed,
                                     (uint32_t)(seed >> 32));
-    const double u1 = uniform53(r.x, r.y) + (0.5 / 9007199254740992.0);  // (0, 1)
-    const double u2 = uniform53(r.z, r.w);
-    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+    // Box-Muller evaluated in single precision: the normal only enters int(mean + spread * z), whose own width
+    // dwarfs a 2^-24 relative error of z.  u1 keeps its 53 random bits before the conversion, so the tail reaches
+    // |z| = sqrt(-2 ln 2^-54) = 8.66 = NORMAL_ABS_MAX like the double-precision form.
+    const float u1 = (float)(uniform53(r.x, r.y) + (0.5 / 9007199254740992.0));  // (0, 1]
+    const float u2 = (float)(r.z >> 8) * (1.0f / 16777216.0f);
+    return (double)(sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2));
 }
 
 __host__ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint64_t event, uint32_t stream,
