@@ -86,6 +86,7 @@ struct AttpcSim {
     std::string error;
     int sm_count = 148;
     bool tables_in_smem = true;
+    int track_warps_max = TRACK_THREADS / 32;  // warps per track CTA that fit beside the tables in shared memory
     size_t table_smem_bytes = 0;
 
     // constants
@@ -303,7 +304,7 @@ int launch_tracks(AttpcSim* sim, const TrackBatch& tb, int64_t n_tracks, int whi
     // The kernel is latency bound (FP64 dependency chains): spread the tracks over all SMs first, then add warps per
     // SM up to the one-CTA-per-SM limit the register file allows.  Lanes pull further tracks from a global cursor.
     const int64_t lanes_per_sm = (n_tracks + sim->sm_count - 1) / sim->sm_count;
-    const int warps = (int)std::max<int64_t>(1, std::min<int64_t>(TRACK_THREADS / 32, (lanes_per_sm + 31) / 32));
+    const int warps = (int)std::max<int64_t>(1, std::min<int64_t>(sim->track_warps_max, (lanes_per_sm + 31) / 32));
     const int threads = warps * 32;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_tracks + threads - 1) / threads, sim->sm_count));
     PointBuf pb = point_buf(sim, which);
@@ -312,7 +313,7 @@ int launch_tracks(AttpcSim* sim, const TrackBatch& tb, int64_t n_tracks, int whi
     if (sim->tables_in_smem) {
         auto kern = track_kernel<true, RECORD>;
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)((TRACK_THREADS / 32) * TRACK_SLOT_BYTES_PER_WARP + sim->table_smem_bytes)));
+                                (int)(sim->track_warps_max * TRACK_SLOT_BYTES_PER_WARP + sim->table_smem_bytes)));
         kern<<<blocks, threads, slot_bytes + sim->table_smem_bytes, stream>>>(sim->P, tb, pb, ctr);
     } else {
         auto kern = track_kernel<false, RECORD>;
@@ -1071,7 +1072,12 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
         if (!stop.empty())
             CUC(cudaMemcpy(sim->stop_ns.p, stop.data(), stop.size() * sizeof(double), cudaMemcpyHostToDevice));
         sim->table_smem_bytes = scaled.size() * sizeof(double);
-        sim->tables_in_smem = sim->table_smem_bytes + (TRACK_THREADS / 32) * TRACK_SLOT_BYTES_PER_WARP <= 227 * 1024;
+        // the tables share the SM's 227 KB with the step slots of the warps: many species -> fewer warps per CTA;
+        // below four warps the tables stay in global memory (L1/L2) instead
+        const int64_t room = 227 * 1024 - (int64_t)sim->table_smem_bytes;
+        const int fit = (int)std::min<int64_t>(TRACK_THREADS / 32, room / (int64_t)TRACK_SLOT_BYTES_PER_WARP);
+        sim->tables_in_smem = fit >= 4;
+        sim->track_warps_max = sim->tables_in_smem ? fit : TRACK_THREADS / 32;
     }
     {
         // constant mesh weights pdf * step^2 of detector/transporter.py:217-246 in exact arithmetic (sigma cancels):

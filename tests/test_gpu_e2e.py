@@ -96,6 +96,19 @@ def test_work_splitting_is_invisible(dist, name, n):
     assert split.stats["n_table_flushes"] > n  # the stress really went through the segment path
 
 
+def test_many_species_share_the_track_kernels_shared_memory(dist):
+    """An engine built for eight species keeps their stopping-power tables in shared memory with fewer warps per track
+    CTA; the tracks of a two-species workload come out exactly as from the two-species engine."""
+    from attpc_engine_b200.detector.engine import engine_for
+
+    cfg, m, v, zs, as_, idx = _workload(dist, "c16dd", 300)
+    base = simulate_batch(m, v, zs, as_, cfg, 21, idx)
+    many = [nuclear_map.get_data(z, a) for z, a in ((1, 1), (1, 2), (1, 3), (2, 3), (2, 4), (6, 12), (6, 14), (6, 16))]
+    wide = engine_for(cfg, many).simulate_batch(m, v, zs, as_, idx, seed=21)
+    assert np.array_equal(base.offsets, wide.offsets)
+    assert np.array_equal(base.cloud, wide.cloud) and np.array_equal(base.labels, wide.labels)
+
+
 def test_convert_to_spyral_function_matches_oracle(golden_events):
     ev, name = golden_events, "alpha_breakup"
     cfg = case_config(name)
