@@ -1871,8 +1871,9 @@ struct SpyralArgs {
 // max commutes with the monotone map r -> min(fl(r e), 4095), so amplitude = min(fl(r_max e), 4095) exactly.  The
 // integral uses the descending-sorted response and its prefix sums: entries with r_i e > 4095 form a prefix.
 __device__ __forceinline__ void shaped(const SimParams& P, double electrons, double& amp, double& integral) {
-    amp = fmin(__dmul_rn(P.resp_max, electrons), 4095.0);
-    int lo = 0, hi = P.n_response;  // first index whose scaled response is <= 4095
+    const double top = __dmul_rn(P.resp_max, electrons);
+    amp = fmin(top, 4095.0);
+    int lo = 0, hi = top > 4095.0 ? P.n_response : 0;  // first index whose scaled response is <= 4095 (0: none clipped)
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (__dmul_rn(P.resp_sorted[mid], electrons) > 4095.0) lo = mid + 1; else hi = mid;
@@ -2006,31 +2007,27 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
             idx[pos] = id;
         }
         __syncthreads();
-        for (int bin = threadIdx.x; bin < TB_BINS; bin += blockDim.x) {
-            const int lo = (int)s_hist[bin], hi = (int)s_hist[bin + 1];
-            for (int i = lo + 1; i < hi; ++i) {
-                const uint64_t kv = keys[i];
-                const uint32_t vv = idx[i];
-                int j = i - 1;
-                while (j >= lo && (keys[j] > kv || (keys[j] == kv && idx[j] > vv))) {
-                    keys[j + 1] = keys[j];
-                    idx[j + 1] = idx[j];
-                    --j;
-                }
-                keys[j + 1] = kv;
-                idx[j + 1] = vv;
-            }
-        }
-        __syncthreads();
     }
+    // One thread per kept row.  Its place inside its time bucket is the number of rows of the bucket that sort before
+    // it ((z, index) order: detector/writer.py:236 sorts by z, equal z keep their cloud order), so the z-sort costs a
+    // handful of shared-memory reads per row.
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t id = sa.keep_all ? (uint32_t)i : idx[i];
         const int64_t src = a + id;
         const double padf = sa.cloud[src * 3 + 0], tbf = sa.cloud[src * 3 + 1], el = sa.cloud[src * 3 + 2];
+        int place = i;
+        if (!sa.keep_all) {
+            const int bin = TB_BINS - 1 - min(max((int)tbf, 0), TB_BINS - 1);
+            const int lo = (int)s_hist[bin], hi = (int)s_hist[bin + 1];
+            const uint64_t kv = keys[i];
+            int before = 0;
+            for (int j = lo; j < hi; ++j) before += keys[j] < kv || (keys[j] == kv && idx[j] < id);
+            place = lo + before;
+        }
         const int pad = (int)padf;
         double amp, integral;
         shaped(P, el, amp, integral);
-        double* row = sa.rows + (out0 + i) * 8;
+        double* row = sa.rows + (out0 + place) * 8;
         row[0] = P.pad_xy[2 * pad];
         row[1] = P.pad_xy[2 * pad + 1];
         row[2] = __dmul_rn(__dmul_rn(__ddiv_rn(__dsub_rn(P.win_edge, tbf), span), P.length), 1000.0);
@@ -2039,7 +2036,7 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
         row[5] = padf;
         row[6] = tbf;
         row[7] = P.pad_scale[pad];
-        sa.row_labels[out0 + i] = sa.labels[src];
+        sa.row_labels[out0 + place] = sa.labels[src];
     }
 }
 
