@@ -305,6 +305,50 @@ class AnalyticGasTarget:
 GasTarget = AnalyticGasTarget
 
 
+# --------------------------------------------------------------------------------------
+# Table files: tabulate once where pycatima is installed, run anywhere
+# --------------------------------------------------------------------------------------
+def save_table_target(path, target: TableGasTarget) -> None:
+    """Write the tables of ``target`` (every species tabulated so far) and its density to one ``.npz`` file."""
+    payload = {"density": np.float64(target.density), "grid": np.array([target.lm, target.e_min, target.n_oct])}
+    for (z, a), tab in sorted(target.tables.items()):
+        if (tab.lm, tab.e_min, tab.n_oct) != (target.lm, target.e_min, target.n_oct):
+            raise ValueError("all tables of a file share one grid")
+        payload[f"dedx_{z}_{a}"] = tab.values
+        payload[f"mass_{z}_{a}"] = np.float64(tab.mass)
+    np.savez(path, **payload)
+
+
+def load_table_target(path) -> TableGasTarget:
+    """A `TableGasTarget` without a source: exactly the species stored in the file (`save_table_target`)."""
+    with np.load(path) as f:
+        lm, e_min, n_oct = (int(v) for v in f["grid"])
+        tables = {}
+        for name in f.files:
+            if name.startswith("dedx_"):
+                z, a = (int(v) for v in name.split("_")[1:])
+                tables[(z, a)] = DedxTable(z=z, a=a, mass=float(f[f"mass_{z}_{a}"]), lm=lm, e_min=e_min, n_oct=n_oct,
+                                           values=np.array(f[name], dtype=np.float64))  # fmt: skip
+        return TableGasTarget(density=float(f["density"]), tables=tables, lm=lm, e_min=e_min, n_oct=n_oct)
+
+
+def tabulate_gas_target(gas_target, nuclei, path=None, max_error: float | None = None) -> TableGasTarget:
+    """Tabulate ``gas_target.get_dedx`` (e.g. a real ``spyral_utils`` `GasTarget` backed by pycatima) for ``nuclei``,
+    check the interpolation error against ``max_error`` (relative; None = report only, see ``.errors``) and
+    optionally write the file.  The returned target is what `DetectorParams.gas_target` takes."""
+    target = TableGasTarget(gas_target)
+    target.errors = {}
+    for nucleus in nuclei:
+        table = target.table_for(nucleus)
+        err = interpolation_error(gas_target, nucleus, table)
+        target.errors[(int(nucleus.Z), int(nucleus.A))] = err
+        if max_error is not None and err > max_error:
+            raise ValueError(f"dE/dx table of Z={nucleus.Z} A={nucleus.A}: interpolation error {err:.2e} > {max_error:.2e}")
+    if path is not None:
+        save_table_target(path, target)
+    return target
+
+
 def ensure_table_target(gas_target) -> TableGasTarget:
     """Wrap any duck-typed gas target (``get_dedx``, ``density``) into a table target."""
     if isinstance(gas_target, TableGasTarget):
@@ -328,5 +372,8 @@ __all__ = [
     "build_dedx_table",
     "interpolation_error",
     "ensure_table_target",
+    "save_table_target",
+    "load_table_target",
+    "tabulate_gas_target",
     "table_nodes",
 ]

@@ -207,3 +207,22 @@ def test_parquet_cloud_writer_round_trip(tmp_path):
     ev, off, cloud, labels = read_parquet_clouds(tmp_path / "run_0001.parquet")
     assert list(ev) == [104, 105, 200] and list(off) == [0, 4, 8, 12]
     assert np.array_equal(cloud[:8], b.cloud) and np.array_equal(cloud[8:], b.event(1)[0])
+
+
+def test_dedx_table_file_round_trip(tmp_path):
+    """tabulate a gas target once (pycatima where it is installed), validate, serialise, reload."""
+    from attpc_engine_b200.target import load_table_target, tabulate_gas_target
+
+    d, c16 = nuclear_map.get_data(1, 2), nuclear_map.get_data(6, 16)
+    source = AnalyticGasTarget([(1, 2, 2)], 600.0)
+    made = tabulate_gas_target(source, [d, c16], tmp_path / "d2_600.npz", max_error=1e-4)
+    assert set(made.errors) == {(1, 2), (6, 16)} and max(made.errors.values()) < 1e-4
+    with pytest.raises(ValueError):
+        tabulate_gas_target(source, [d], max_error=1e-9)
+    back = load_table_target(tmp_path / "d2_600.npz")
+    assert back.density == made.density and set(back.tables) == {(1, 2), (6, 16)}
+    for key in back.tables:
+        assert np.array_equal(back.tables[key].values, made.tables[key].values)
+    assert back.get_dedx(d, 3.7) == made.get_dedx(d, 3.7)
+    with pytest.raises(KeyError):
+        back.get_dedx(nuclear_map.get_data(2, 4), 1.0)  # not in the file, and no source to tabulate from
