@@ -798,6 +798,7 @@ track_kernel(const __grid_constant__ SimParams P, const __grid_constant__ TrackB
             carry_y = __shfl_sync(FULL, g.y, 31);
             carry_z = __shfl_sync(FULL, g.z, 31);
             carry_ke = __shfl_sync(FULL, ke_g, 31);
+            __syncwarp();  // the slot updates of this round are visible to the first reads of the next
         }
         __syncwarp();
         if (emitting) {  // owners take their tracks back
