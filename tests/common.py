@@ -81,3 +81,65 @@ def canonical_order(cloud):
 def sort_cloud(cloud, labels):
     order = canonical_order(cloud)
     return cloud[order], labels[order]
+
+
+# ------------------------------------------------------------------ fixtures drawn from the bench workloads
+WORKLOAD_NAMES = ("c16dd", "c14dp", "c12aa", "sn132dp")
+WORKLOAD_GAS = {"c16dd": "D2_600", "c14dp": "D2_600", "c12aa": "He4_600", "sn132dp": "D2_600"}
+
+
+def digest(*arrays):
+    """SHA-256 over dtype, shape and bytes (tests/golden/make_workload_golden.py: digest)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def workload_config(name):
+    """The Config of bench.build_workload(name) (same numbers for all four; only the gas differs)."""
+    return make_config(WORKLOAD_GAS[name])
+
+
+def load_workload(name):
+    """Fixture of tests/golden/make_workload_golden.py as a dict + per-event digests of the reference's outputs."""
+    fx = load_golden(f"workload_{name}.npz")
+    fx["digests"] = json.loads((GOLDEN / "workload_digests.json").read_text())[name]
+    return fx
+
+
+def workload_tracks(fx):
+    """Per charged track: dict(event, rank, idx, za, rows, normals, electrons), in the order the reference ran them."""
+    off = fx["track_offsets"]
+    out = []
+    for t in range(len(off) - 1):
+        idx = int(fx["track_idx"][t])
+        a, b = off[t], off[t + 1]
+        out.append(dict(event=int(fx["track_event"][t]), rank=int(fx["track_rank"][t]), idx=idx,
+                        za=(int(fx["Z"][idx]), int(fx["A"][idx])), rows=fx["track_rows"][a:b],
+                        normals=fx["track_normals"][a:b], electrons=fx["track_electrons"][a:b]))  # fmt: skip
+    return out
+
+
+def workload_event_dict(fx, e):
+    """(keys, charges, labels, uniforms) of event e in the reference's dict insertion order."""
+    a, b = fx["key_offsets"][e], fx["key_offsets"][e + 1]
+    return fx["keys"][a:b], fx["charges"][a:b], fx["key_labels"][a:b], fx["uniforms"][a:b]
+
+
+def reference_cloud_from_dict(keys, charges, labels, uniforms, num_tb=512):
+    """`dict_to_points` + wiggle + time-bucket mask (detector/simulator.py:19-49, 104-113) on a recorded dict."""
+    from attpc_engine_b200.detector.pairing import unpair
+
+    tb, pad = unpair(keys)
+    cloud = np.empty((len(keys), 3), dtype=np.float64)
+    cloud[:, 0] = pad
+    cloud[:, 1] = tb
+    cloud[:, 2] = charges
+    cloud[:, 1] += uniforms
+    keep = np.logical_and(0 <= cloud[:, 1], cloud[:, 1] < num_tb)
+    return cloud[keep], np.asarray(labels, dtype=np.int64)[keep]

@@ -8,7 +8,10 @@ import numpy as np
 import pytest
 
 from attpc_engine_b200.detector.pairing import unpair
-from tests.common import case_config, case_names, case_tracks, cloud_keys, nuclei_of, sort_cloud
+from tests.common import (
+    WORKLOAD_NAMES, case_config, case_names, case_tracks, cloud_keys, load_workload, nuclei_of, reference_cloud_from_dict,
+    sort_cloud, workload_config, workload_event_dict, workload_tracks,
+)  # fmt: skip
 
 pytestmark = pytest.mark.gpu
 
@@ -130,3 +133,68 @@ def test_three_events_in_one_replay_call(golden_events):
         want_cloud, want_labels = sort_cloud(ev[f"{name}/cloud"], ev[f"{name}/labels"])
         assert np.array_equal(cloud, want_cloud), name
         assert np.array_equal(lab, want_labels), name
+
+
+# ------------------------------------------------------------- 32 reference events per bench workload, one call
+def _workload_replay(name, tuning=None, **kw):
+    from attpc_engine_b200.detector.engine import engine_for
+
+    fx = load_workload(name)
+    cfg = workload_config(name)
+    tracks = workload_tracks(fx)
+    n_events = len(fx["digests"])
+    eng = engine_for(cfg, nuclei_of(tracks), **(tuning or {}))
+    batch, electrons = eng.simulate_replay(
+        [t["rows"] for t in tracks], [t["normals"] for t in tracks], [t["event"] for t in tracks],
+        [t["rank"] for t in tracks], [t["idx"] for t in tracks], [t["za"] for t in tracks], n_events,
+        uniforms=[workload_event_dict(fx, e)[::3] for e in range(n_events)], **kw,
+    )  # fmt: skip
+    return fx, cfg, tracks, batch, electrons
+
+
+@pytest.mark.parametrize("tuning", SPLITS, ids=["default", "stress-split"])
+@pytest.mark.parametrize("name", WORKLOAD_NAMES)
+def test_workload_replay_dict(name, tuning):
+    """Events drawn from bench.build_workload: electrons per row and the whole (pad, tb) -> (charge, label) map equal
+    the reference's, for all 32 events of a workload in ONE replay call (`solver.py:308-347`, `transporter.py:252-317`)."""
+    fx, _, tracks, batch, electrons = _workload_replay(name, tuning, keep_all_tb=True)
+    for t, got in zip(tracks, electrons):
+        assert np.array_equal(got, t["electrons"])
+    for e in range(len(fx["digests"])):
+        keys, charges, labels, uniforms = workload_event_dict(fx, e)
+        tb, pad = unpair(keys)
+        order = np.lexsort((pad, tb))
+        cloud, lab = batch.event(e)
+        assert np.array_equal(cloud_keys(cloud), keys[order]), (name, e)
+        assert np.array_equal(cloud[:, 0], pad[order]) and np.array_equal(np.floor(cloud[:, 1]), tb[order])
+        assert np.allclose(cloud[:, 2], charges[order].astype(np.float64), rtol=CHARGE_RTOL, atol=0.0)
+        assert np.array_equal(cloud[:, 2], charges[order].astype(np.float64)), (name, e)
+        assert np.array_equal(lab, labels[order]), (name, e)
+        assert np.array_equal(cloud[:, 1], np.floor(cloud[:, 1]) + uniforms[order])
+
+
+@pytest.mark.parametrize("name", WORKLOAD_NAMES)
+def test_workload_replay_cloud_and_spyral(name):
+    """Final `simulate` cloud (`simulator.py:104-115`) and `SpyralWriter.write` rows (`writer.py:61-112, 232-238`) of
+    the same 32 events.  The expected arrays are rebuilt from the reference's recorded dict; the CPU test
+    `test_workload_fixture_digests` pins that reconstruction to the digests of the reference's actual output."""
+    from oracle import attpc_oracle as oracle
+
+    fx, cfg, _, batch, _ = _workload_replay(name, spyral_rows=True)
+    resp = oracle.get_response(cfg)
+    for e, want in enumerate(fx["digests"]):
+        want_cloud, want_labels = reference_cloud_from_dict(*workload_event_dict(fx, e))
+        assert len(want_cloud) == want["n_cloud"]
+        cloud, lab = batch.event(e)
+        sorted_cloud, sorted_labels = sort_cloud(want_cloud, want_labels)
+        assert np.array_equal(cloud, sorted_cloud) and np.array_equal(lab, sorted_labels), (name, e)
+        rows, row_labels = batch.event_rows(e)
+        assert len(rows) == want["n_spyral"], (name, e)
+        if len(rows) == 0:
+            continue
+        want_rows, want_row_labels = oracle.spyral_event(want_cloud, want_labels, cfg, resp)
+        assert np.all(np.diff(rows[:, 2]) >= 0)
+        for col in (0, 1, 2, 3, 5, 6, 7):
+            assert np.array_equal(rows[:, col], want_rows[:, col]), (name, e, col)
+        assert np.allclose(rows[:, 4], want_rows[:, 4], rtol=1e-12, atol=0.0)
+        assert np.array_equal(row_labels, want_row_labels)

@@ -6,7 +6,10 @@ import pytest
 
 from attpc_engine_b200 import nuclear_map
 from oracle import attpc_oracle as oracle
-from tests.common import case_config, case_names, case_tracks, make_config
+from tests.common import (
+    WORKLOAD_NAMES, case_config, case_names, case_tracks, digest, load_workload, make_config, reference_cloud_from_dict,
+    workload_config, workload_event_dict, workload_tracks,
+)  # fmt: skip
 
 
 def test_pairing_known_answers():
@@ -94,3 +97,35 @@ def test_pad_lookup_matches_reference(golden_misc):
         pad = -1 if ix == -1 or iy == -1 else int(cfg.pad_grid[ix, iy])
         got[i] = -1 if (pad == -1 or pad in oracle.BEAM_PAD_IDS) else pad
     assert np.array_equal(got, golden_misc["pad_lookup/pad"])
+
+
+@pytest.mark.parametrize("name", WORKLOAD_NAMES)
+def test_workload_fixture_digests(name):
+    """32 events per bench workload (tests/golden/make_workload_golden.py): the oracle, replaying the recorded
+    trajectories / normals / uniforms, reproduces the reference's dict in insertion order, and the cloud and Spyral
+    rows rebuilt from that dict hash to the digests of the reference's own `simulate` / `SpyralWriter.write` output."""
+    fx = load_workload(name)
+    cfg = workload_config(name)
+    resp = oracle.get_response(cfg)
+    tracks = workload_tracks(fx)
+    indices = list(fx["indices"])
+    for e, want in enumerate(fx["digests"]):
+        mine = [t for t in tracks if t["event"] == e]
+        keys, charges, labels, uniforms = workload_event_dict(fx, e)
+        rec = {}
+        cloud, lab = oracle.simulate_event(
+            fx["momenta"][e], fx["vertices"][e], fx["Z"], fx["A"], cfg, None, indices, nuclear_map, record=rec,
+            tracks=[t["rows"] for t in mine], normals=[t["normals"] for t in mine], uniforms=uniforms,
+        )  # fmt: skip
+        for t, got in zip(mine, rec["electrons"]):
+            assert np.array_equal(got, t["electrons"])
+        assert np.array_equal(rec["keys"], keys) and np.array_equal(rec["charges"], charges)
+        assert np.array_equal(rec["key_labels"], labels)
+        rebuilt, rebuilt_lab = reference_cloud_from_dict(keys, charges, labels, uniforms)
+        assert np.array_equal(cloud, rebuilt) and np.array_equal(lab, rebuilt_lab)
+        assert len(cloud) == want["n_cloud"] and digest(cloud, lab) == want["cloud"], (name, e)
+        if len(cloud):
+            rows, row_labels = oracle.spyral_event(cloud, lab, cfg, resp)
+        else:
+            rows, row_labels = np.zeros((0, 8)), np.zeros(0, np.int64)
+        assert len(rows) == want["n_spyral"] and digest(rows, row_labels) == want["spyral"], (name, e)
