@@ -12,7 +12,7 @@ from pathlib import Path
 
 LIB_NAME = "libattpc_b200.so"
 LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # flags (include/attpc_b200.h)
 KEEP_ALL_TB = 1 << 0
@@ -52,6 +52,8 @@ class AttpcConfig(C.Structure):
         ("copy_events_per_launch", C.c_int32),
         ("unit_points", C.c_int32),
         ("table_spill_keys", C.c_int32),
+        ("table_hard_keys", C.c_int32),
+        ("table_max_probe", C.c_int32),
     ]
 
 
@@ -108,7 +110,7 @@ class AttpcResult(C.Structure):
         ("n_group_launches", C.c_int32),
         ("n_hash_probes", C.c_int64),
         ("hash_capacity", C.c_int32),
-        ("reserved1", C.c_int32),
+        ("n_dirty_units", C.c_int32),
         ("n_table_flushes", C.c_int64),
         ("col_pad", C.POINTER(C.c_int16)),
         ("col_tb_q16", C.POINTER(C.c_uint32)),
@@ -123,6 +125,7 @@ class AttpcResult(C.Structure):
         ("big_electrons", C.POINTER(C.c_int64)),
         ("ms_order", C.c_float),
         ("reserved2", C.c_float),
+        ("n_raw_entries", C.c_int64),
     ]
 
 

@@ -101,8 +101,11 @@ struct AttpcSim {
     int32_t copy_launch_events = 2048;
     int32_t group_events = 2048;
     int32_t chunk_groups = 16;  // groups per kernel launch when the rows stay on the device
-    int32_t unit_points = UNIT_POINTS;     // test knobs (AttpcConfig.unit_points / table_spill_keys)
+    int32_t unit_points = UNIT_POINTS;     // test knobs (AttpcConfig.unit_points / table_spill_keys / ...)
     int32_t spill_keys = SMEM_SPILL_DEFAULT;
+    int32_t hard_keys = SMEM_HARD_DEFAULT;
+    int32_t max_probe = MAX_PROBE_DEFAULT;
+    int32_t fixup_ctas = 64;               // persistent CTAs (and scratch slabs) of fixup_kernel
     int64_t big_cap = ATTPC_BIG_CAP;             // exceptions accepted before a call returns the int64 column (<= ATTPC_BIG_CAP)
     int32_t hash_cap = 16384;
     int64_t group_point_cap = 0;
@@ -133,12 +136,13 @@ struct AttpcSim {
     PinnedArray<unsigned long long> chunk_totals;  // running CSR total after each chunk of groups (mapped)
     DevArray<double> geom;
     DevArray<uint32_t> rec;
-    DevArray<int32_t> unit_event, unit_first, unit_count, unit_order, n_units;
-    DevArray<unsigned> pstart, n_entries, mode;
+    DevArray<uint32_t> perm;
+    DevArray<int32_t> unit_event, unit_first, unit_count, unit_order, n_units, event_unit0, event_nunits;
+    DevArray<unsigned> pstart, unit_kept, unit_raw, dirty;
     int32_t ranks = 1;
     int32_t max_units = 0;
-    DevArray<HashEntry> hash;
-    DevArray<uint64_t> sort_items;
+    DevArray<HashEntry> hash, fix_rows;
+    DevArray<uint64_t> fix_items;
     DevArray<unsigned> kept;
     DevArray<double> in_momenta, in_vertices;
 
@@ -234,20 +238,26 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     }
     CU(sim->geom.reserve(pts * GEOM_DOUBLES));
     CU(sim->rec.reserve(pts * REC_WORDS));
+    CU(sim->perm.reserve(pts));
+    // a unit is a time-bucket range of one event: at most one per event plus one per unit_points points
     sim->max_units = (int32_t)(sim->group_events + sim->group_point_cap / sim->unit_points + 1);
     CU(sim->unit_event.reserve(n_groups * sim->max_units));
     CU(sim->unit_first.reserve(n_groups * sim->max_units));
     CU(sim->unit_count.reserve(n_groups * sim->max_units));
     CU(sim->unit_order.reserve(n_groups * sim->max_units));
+    CU(sim->unit_kept.reserve(n_groups * sim->max_units));
+    CU(sim->unit_raw.reserve(n_groups * sim->max_units));
+    CU(sim->dirty.reserve(n_groups * sim->max_units + 2));
     CU(sim->n_units.reserve(n_groups));
+    CU(sim->event_unit0.reserve(launch_events));
+    CU(sim->event_nunits.reserve(launch_events));
     CU(sim->pstart.reserve(launch_events * ranks));
-    CU(sim->n_entries.reserve(launch_events));
-    CU(sim->mode.reserve(launch_events));
-    // tables and sort scratch for one chunk of groups (run_groups)
+    // unit regions for one chunk of groups (run_groups) and the scratch slabs of fixup_kernel
     const int64_t copy_groups = (sim->copy_launch_events + sim->group_events - 1) / sim->group_events;
     const int64_t table_groups = std::min<int64_t>(n_groups, std::max<int64_t>(sim->chunk_groups, copy_groups));
-    CU(sim->hash.reserve(table_groups * sim->group_events * sim->hash_cap));
-    CU(sim->sort_items.reserve(table_groups * sim->group_events * sim->hash_cap * 2));
+    CU(sim->hash.reserve(table_groups * sim->max_units * sim->hash_cap));
+    CU(sim->fix_rows.reserve((int64_t)sim->fixup_ctas * sim->hash_cap));
+    CU(sim->fix_items.reserve((int64_t)sim->fixup_ctas * sim->hash_cap * 2));
     CU(sim->csr_total.reserve(2));
     CU(sim->csr_host.reserve(2));
     CU(sim->chunk_totals.reserve(n_groups + 1));
@@ -290,6 +300,13 @@ PointBuf point_buf(AttpcSim* sim, int which) {
     pb.unit_first = sim->unit_first.p;
     pb.unit_count = sim->unit_count.p;
     pb.unit_order = sim->unit_order.p;
+    pb.unit_kept = sim->unit_kept.p;
+    pb.unit_raw = sim->unit_raw.p;
+    pb.perm = sim->perm.p;
+    pb.event_unit0 = sim->event_unit0.p;
+    pb.event_nunits = sim->event_nunits.p;
+    pb.dirty = sim->dirty.p;
+    pb.dirty_cap = (int32_t)std::min<int64_t>(sim->dirty.n - 2, INT32_MAX);
     pb.n_units = sim->n_units.p;
     pb.max_units = sim->max_units;
     pb.unit_points = sim->unit_points;
@@ -342,13 +359,12 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
     PointBuf pb = point_buf(sim, which);
     Counters* ctr = sim->slot[which].counters.p;
     const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
-    fa.sort_items = sim->sort_items.p;
-    const size_t sort_smem = (size_t)SORT_SMEM_ITEMS * sizeof(uint64_t);
-    CU(cudaFuncSetAttribute(collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    const size_t fix_smem = (size_t)FIXUP_SMEM_ITEMS * sizeof(uint64_t);
+    const size_t emit_smem = (size_t)EMIT_TILE * sizeof(uint4);
     CU(cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEPOSIT_SMEM_BYTES));
     // Groups are processed in chunks: every kernel is launched once per chunk with one grid row per group, so the
     // ramp-up and tail of a launch are paid once per chunk.  When rows go to the host a chunk is what is copied while
-    // the next chunk computes; otherwise it is as many groups as the tables are sized for.
+    // the next chunk computes; otherwise it is as many groups as the unit regions are sized for.
     const int64_t gpc = std::max<int64_t>(1, fences ? groups_per_chunk : sim->chunk_groups);
     for (int64_t g0 = 0; g0 < n_groups; g0 += gpc) {
         const int64_t ng = std::min<int64_t>(gpc, n_groups - g0);
@@ -358,27 +374,34 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         gv.group = (int32_t)g0;
         gv.hash_cap = sim->hash_cap;
         gv.tables = sim->hash.p;
-        gv.n_entries = sim->n_entries.p;
-        gv.mode = sim->mode.p;
         gv.exact_mesh = (fa.flags & ATTPC_EXACT_MESH) ? 1 : 0;
         gv.group_events = sim->group_events;
-        gv.chunk_e0 = 0;
+        gv.chunk_group = 0;
         gv.spill_keys = sim->spill_keys;
+        gv.hard_keys = sim->hard_keys;
+        gv.max_probe = sim->max_probe;
         const dim3 per_event((unsigned)std::min<int64_t>(sim->group_events, gv.n_events), (unsigned)ng);
+        const dim3 per_unit((unsigned)sim->max_units, (unsigned)ng);
         cudaEvent_t d0 = sim->mark();
+        CU(cudaMemsetAsync(sim->n_units.p + g0, 0, (size_t)ng * sizeof(int32_t), sim->stream));
+        CU(cudaMemsetAsync(sim->unit_raw.p + g0 * sim->max_units, 0, (size_t)ng * sim->max_units * sizeof(unsigned),
+                           sim->stream));
+        CU(cudaMemsetAsync(sim->dirty.p, 0, 2 * sizeof(unsigned), sim->stream));
+        CU(cudaMemsetAsync(fa.kept + gv.first_slot, 0, (size_t)gv.n_events * sizeof(unsigned), sim->stream));
         point_scan_kernel<<<(unsigned)ng, 1024, 0, sim->stream>>>(pb, gv, ctr);
         point_order_kernel<<<dim3((unsigned)std::max<int64_t>(1, sim->sm_count * 4 / ng), (unsigned)ng), 256, 0,
                              sim->stream>>>(sim->P, pb, gv, ctr);
-        CU(cudaMemsetAsync(sim->n_entries.p + gv.first_slot, 0, (size_t)gv.n_events * sizeof(unsigned), sim->stream));
+        event_sort_kernel<<<per_event, SORT_THREADS, 0, sim->stream>>>(sim->P, pb, gv, ctr);
+        unit_order_kernel<<<(unsigned)ng, 1024, 0, sim->stream>>>(pb, gv, ctr);
         cudaEvent_t k0 = sim->mark();
-        deposit_kernel<<<dim3((unsigned)sim->max_units, (unsigned)ng), DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES,
-                         sim->stream>>>(sim->P, pb, gv, ctr);
+        deposit_kernel<<<per_unit, DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES, sim->stream>>>(sim->P, fa, pb, gv, ctr);
         cudaEvent_t d1 = sim->mark();
-        collect_kernel<<<per_event, FINALIZE_THREADS, sort_smem, sim->stream>>>(sim->P, fa, gv, ctr);
+        FixupArgs fx{sim->fix_items.p, sim->fix_rows.p};
+        fixup_kernel<<<(unsigned)sim->fixup_ctas, FINALIZE_THREADS, fix_smem, sim->stream>>>(sim->P, fa, pb, gv, fx, ctr);
         scan_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, ctr, sim->csr_total.p);
-        emit_kernel<<<per_event, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
+        emit_kernel<<<per_unit, FINALIZE_THREADS, emit_smem, sim->stream>>>(sim->P, fa, pb, gv, ctr);
         cudaEvent_t f1 = sim->mark();
-        sim->launches += 6;
+        sim->launches += 8;
         ord_marks.push_back({d0, k0});
         dep_marks.push_back({k0, d1});
         fin_marks.push_back({d1, f1});
@@ -614,19 +637,24 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         fa.flags = flags;
         fa.kept = sim->kept.p + b0;
         fa.offsets = sim->offsets_dev.p + b0;
-        fa.cloud = sim->cloud_dev.p;
-        fa.labels = sim->labels_dev.p;
+        // typed columns only: the float64 rows are neither written nor copied (nothing reads them)
+        const bool want_cloud = !use_columns || (flags & ATTPC_SPYRAL_ROWS);
+        fa.cloud = want_cloud ? sim->cloud_dev.p : nullptr;
+        fa.labels = want_cloud ? sim->labels_dev.p : nullptr;
         fa.out_cap = sim->labels_dev.n;
         if (use_columns) {
             fa.col_pad = sim->col_pad_dev.p;
             fa.col_tb_q16 = sim->col_tbq_dev.p;
-            fa.col_electrons = sim->col_q_dev.p;
-            fa.col_electrons32 = sim->col_q32_dev.p;
-            fa.big_rows = sim->big_rows_dev.p;
-            fa.big_electrons = sim->big_q_dev.p;
-            fa.big_count = sim->csr_total.p + 1;
-            fa.big_cap = sim->big_cap;
             fa.col_label = sim->col_label_dev.p;
+            if (use_q32) {
+                fa.col_electrons32 = sim->col_q32_dev.p;
+                fa.big_rows = sim->big_rows_dev.p;
+                fa.big_electrons = sim->big_q_dev.p;
+                fa.big_count = sim->csr_total.p + 1;
+                fa.big_cap = sim->big_cap;
+            } else {
+                fa.col_electrons = sim->col_q_dev.p;
+            }
         }
         fa.replay = plan.uniforms;
         if (fa.replay.offsets) fa.replay.offsets += b0;
@@ -710,7 +738,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             if (now.overflow_points) {
                 sim->group_point_cap *= 2;
                 for (auto& s2 : sim->slot) s2.release_points();
-                sim->geom.release(); sim->rec.release();
+                sim->geom.release(); sim->rec.release(); sim->perm.release(); sim->hash.release();
                 sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release();
                 sim->unit_order.release();
             }
@@ -718,7 +746,8 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 if (sim->hash_cap >= (1 << 20)) return sim->fail(ATTPC_E_CAPACITY, "event needs > 2^20 hash slots");
                 sim->hash_cap *= 2;
                 sim->hash.release();
-                sim->sort_items.release();
+                sim->fix_rows.release();
+                sim->fix_items.release();
             }
             if (now.overflow_out) {
                 out_cap = std::max<int64_t>(sim->labels_dev.n * 2, (int64_t)sim->csr_host.p[0] + (1 << 20));
@@ -753,6 +782,12 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         totals.keys += now.keys;
         totals.probes += now.probes;
         totals.flushes += now.flushes;
+        totals.raw_entries += now.raw_entries;
+        for (int k = 0; k < 3; ++k) totals.raw_by_cause[k] += now.raw_by_cause[k];
+        totals.postponed += now.postponed;
+        totals.max_keys = std::max(totals.max_keys, now.max_keys);
+        totals.max_carried = std::max(totals.max_carried, now.max_carried);
+        totals.dirty_units += now.dirty_units;
         totals.rk_steps += now.rk_steps;
         totals.rk_rejects += now.rk_rejects;
         totals.max_track_passes = std::max(totals.max_track_passes, now.max_track_passes);
@@ -769,8 +804,10 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     const int64_t n_points = (int64_t)csr_before;
     res->n_points = n_points;
     res->offsets_dev = sim->offsets_dev.p;
-    res->cloud_dev = sim->cloud_dev.p;
-    res->labels_dev = sim->labels_dev.p;
+    if (!use_columns || (flags & ATTPC_SPYRAL_ROWS)) {
+        res->cloud_dev = sim->cloud_dev.p;
+        res->labels_dev = sim->labels_dev.p;
+    }
     res->n_trajectory_points = (int64_t)totals.traj_points;
     res->n_active_points = (int64_t)totals.active_points;
     res->n_primary_electrons = (int64_t)totals.primary_electrons;
@@ -778,10 +815,16 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     res->n_keys = (int64_t)totals.keys;
     res->n_hash_probes = (int64_t)totals.probes;
     res->n_table_flushes = (int64_t)totals.flushes;
+    res->n_dirty_units = (int32_t)std::min<unsigned long long>(totals.dirty_units, INT32_MAX);
+    res->n_raw_entries = (int64_t)totals.raw_entries;
     res->n_rk_steps = (int64_t)totals.rk_steps;
     res->n_rk_rejects = (int64_t)totals.rk_rejects;
     res->max_track_passes = (int64_t)totals.max_track_passes;
     res->n_retries = retries;
+    if (getenv("ATTPC_DEBUG"))
+        fprintf(stderr, "[attpc] events %lld flushes %llu postponed %llu dirty units %llu raw %llu (no slot %llu, not carried %llu, list full %llu) fullest table %llu most carried %llu\n",
+                (long long)n_events, totals.flushes, totals.postponed, totals.dirty_units, totals.raw_entries,
+                totals.raw_by_cause[0], totals.raw_by_cause[1], totals.raw_by_cause[2], totals.max_keys, totals.max_carried);
     if (copy_host) {
         if (n_events == 0) {
             CU(cudaMemcpyAsync(sim->offsets_host.p, sim->offsets_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, C));
@@ -809,13 +852,12 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                     res->big_rows = sim->big_rows_host.p;
                     res->big_electrons = sim->big_q_host.p;
                 }
-            } else {  // too many exceptions for the list (heavy ions): the full-width column after all, and from now on
+            } else {  // too many exceptions for the list (heavy ions): the full-width column, now and from now on
                 sim->q32_off = true;
-                CU(sim->col_q_host.reserve(sim->labels_dev.n));
-                if (n_points > 0)
-                    CU(cudaMemcpyAsync(sim->col_q_host.p, sim->col_q_dev.p, (size_t)n_points * sizeof(int64_t),
-                                       cudaMemcpyDeviceToHost, C));
-                res->col_electrons = sim->col_q_host.p;
+                CU(cudaStreamSynchronize(T));
+                CU(cudaStreamSynchronize(C));
+                CU(cudaStreamSynchronize(G));
+                return run_batch(sim, plan, n_events, flags, res, ms_h2d);
             }
             res->col_label = sim->col_label_host.p;
         }
@@ -887,11 +929,13 @@ void attpc_destroy(AttpcSim* sim) {
     if (sim->stream_c) cudaStreamDestroy(sim->stream_c);
     sim->lut.release(); sim->pad_xy.release(); sim->pad_scale.release(); sim->response.release();
     sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release(); sim->stop_ns.release(); sim->plan_cls.release(); sim->plan_counts.release(); sim->plan_order.release();
-    sim->hash.release(); sim->sort_items.release();
+    sim->hash.release(); sim->fix_rows.release(); sim->fix_items.release(); sim->perm.release();
+    sim->unit_kept.release(); sim->unit_raw.release(); sim->dirty.release(); sim->event_unit0.release();
+    sim->event_nunits.release();
     sim->geom.release(); sim->rec.release();
     sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release(); sim->unit_order.release();
     sim->n_units.release();
-    sim->pstart.release(); sim->n_entries.release(); sim->mode.release();
+    sim->pstart.release();
     sim->kept.release(); sim->in_momenta.release(); sim->in_vertices.release();
     sim->offsets_dev.release(); sim->labels_dev.release(); sim->row_offsets_dev.release();
     sim->row_labels_dev.release(); sim->cloud_dev.release(); sim->rows_dev.release(); sim->row_kept.release();
@@ -980,11 +1024,14 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
     P.n_species = n_species;
     P.n_pads = n_pads;
     P.n_response = n_response;
+    P.n_bins = std::min(TB_BINS, std::max(2, std::max(cfg->micromegas_edge, cfg->windows_edge) + 2));
     if (cfg->max_events_per_launch > 0) sim->launch_events = cfg->max_events_per_launch;
     if (cfg->copy_events_per_launch > 0) sim->copy_launch_events = cfg->copy_events_per_launch;  // events per launch when rows go to the host
     if (cfg->hash_capacity > 0) sim->hash_cap = next_pow2(cfg->hash_capacity);
     if (cfg->unit_points > 0) sim->unit_points = std::min<int32_t>(cfg->unit_points, UNIT_POINTS);
-    if (cfg->table_spill_keys > 0) sim->spill_keys = std::min<int32_t>(cfg->table_spill_keys, SMEM_SPILL_AT);
+    if (cfg->table_spill_keys > 0) sim->spill_keys = std::min<int32_t>(cfg->table_spill_keys, SMEM_HARD_DEFAULT);
+    if (cfg->table_hard_keys > 0) sim->hard_keys = std::min<int32_t>(cfg->table_hard_keys, SMEM_HARD_DEFAULT);
+    if (cfg->table_max_probe > 0) sim->max_probe = std::min<int32_t>(cfg->table_max_probe, SMEM_SLOTS);
     sim->group_events = std::min(sim->group_events, sim->launch_events);
     if (const char* env = getenv("ATTPC_CHUNK_GROUPS")) sim->chunk_groups = std::max(1, atoi(env));  // tuning aid
     if (const char* env = getenv("ATTPC_BIG_CAP")) sim->big_cap = std::min<int64_t>(ATTPC_BIG_CAP, std::max(0, atoi(env)));  // tests

@@ -145,7 +145,7 @@ _STAT_FIELDS = (
     "n_tracks", "n_trajectory_points", "n_active_points", "n_primary_electrons", "n_deposits", "n_keys",
     "ms_h2d", "ms_tracks", "ms_deposit", "ms_finalize", "ms_d2h", "ms_total", "n_kernel_launches", "n_retries",
     "n_track_launches", "n_group_launches", "n_hash_probes", "hash_capacity", "n_table_flushes",
-    "n_rk_steps", "n_rk_rejects", "max_track_passes", "ms_order", "n_big",
+    "n_rk_steps", "n_rk_rejects", "max_track_passes", "ms_order", "n_big", "n_dirty_units", "n_raw_entries",
 )  # fmt: skip
 
 
@@ -165,6 +165,8 @@ class Engine:
         copy_events_per_launch: int = 0,
         unit_points: int = 0,
         table_spill_keys: int = 0,
+        table_hard_keys: int = 0,
+        table_max_probe: int = 0,
     ):
         if config.pad_grid is None or config.pad_grid_edges is None:
             raise ValueError("Pad grid is not loaded")  # solver.py:400-401
@@ -215,6 +217,8 @@ class Engine:
         cfg.copy_events_per_launch = int(copy_events_per_launch)
         cfg.unit_points = int(unit_points)
         cfg.table_spill_keys = int(table_spill_keys)
+        cfg.table_hard_keys = int(table_hard_keys)
+        cfg.table_max_probe = int(table_max_probe)
 
         sp = (_lib.AttpcSpecies * len(self.species))()
         for i, (nuc, tab) in enumerate(zip(self.species, tables)):
@@ -513,18 +517,67 @@ class Engine:
         return out
 
 
+def _digest(*arrays) -> str:
+    import hashlib
+
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        h.update(str(a.dtype).encode() + str(a.shape).encode())
+        h.update(a.tobytes())
+    return h.hexdigest()
+
+
+def config_fingerprint(config: Config, nuclei: list) -> tuple:
+    """Everything `Engine.__init__` bakes into device constants, as a hashable value.
+
+    The reference reads ``config.*`` afresh for every event, so a user may mutate the parameter dataclasses between
+    calls (a scan over ``det_params.bfield``, another ``load_pad_grid``, another gas).  `engine_for` compares this
+    fingerprint on every call and rebuilds the engine when anything baked has changed.  The dE/dx tables are
+    fingerprinted through the target object's identity plus its density and a probe of ``get_dedx`` per species
+    (cheap; re-tabulating on every call would not be).
+    """
+    det, elec = config.det_params, config.elec_params
+    scalars = (
+        float(det.length), float(det.efield), float(det.bfield), int(det.mpgd_gain), float(det.diffusion),
+        float(det.fano_factor), float(det.w_value), float(elec.clock_freq), float(elec.amp_gain),
+        float(elec.shaping_time), int(elec.micromegas_edge), int(elec.windows_edge), float(elec.adc_threshold),
+        float(config.drift_velocity),
+    )  # fmt: skip
+    target = det.gas_target
+    probes = tuple(
+        (int(n.Z), int(n.A), float(n.mass), float(target.get_dedx(n, 0.37 * n.A)), float(target.get_dedx(n, 9.1 * n.A)))
+        for n in nuclei
+    )
+    arrays = getattr(config, "_b200_array_digest", None)
+    ids = (id(config.pad_grid), id(config.pad_grid_edges), id(config.pad_centers), id(config.pad_sizes))
+    if arrays is None or arrays[0] != ids:  # hashing 31 M grid cells takes ~20 ms: only when the arrays were replaced
+        arrays = (ids, _digest(config.pad_grid_edges, config.pad_centers, config.pad_sizes,
+                               np.asarray(config.pad_grid)[::10, ::10]))  # fmt: skip
+        config.__dict__["_b200_array_digest"] = arrays
+    return scalars + (id(target), float(target.density), probes, arrays[1])
+
+
 def engine_for(config: Config, nuclei: list, device: int = 0, **tuning) -> Engine:
-    """Engine cached on the Config object, keyed by device, species set and tuning."""
+    """Engine cached on the Config object, keyed by device, species set and tuning; rebuilt when a baked value changed.
+
+    (In-place edits of the pad arrays are not seen -- replace the array, as ``load_pad_grid`` does.)
+    """
     cache = config.__dict__.setdefault("_b200_engines", {})
     key = (int(device), tuple(sorted((int(n.Z), int(n.A)) for n in nuclei)), tuple(sorted(tuning.items())))
-    eng = cache.get(key)
-    if eng is None:
-        uniq = {}
-        for n in nuclei:
-            uniq.setdefault((int(n.Z), int(n.A)), n)
-        eng = Engine(config, [uniq[k] for k in sorted(uniq)], device=device, **tuning)
-        cache[key] = eng
+    uniq = {}
+    for n in nuclei:
+        uniq.setdefault((int(n.Z), int(n.A)), n)
+    species = [uniq[k] for k in sorted(uniq)]
+    stamp = config_fingerprint(config, species)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    if hit is not None:
+        hit[1].close()  # stale constants: free the device memory before building the replacement
+    eng = Engine(config, species, device=device, **tuning)
+    cache[key] = (stamp, eng)
     return eng
 
 
-__all__ = ["Engine", "SimBatch", "engine_for", "build_pad_lut", "default_freeze_ke", "NUM_TB"]
+__all__ = ["Engine", "SimBatch", "engine_for", "config_fingerprint", "build_pad_lut", "default_freeze_ke", "NUM_TB"]

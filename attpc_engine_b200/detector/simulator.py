@@ -18,7 +18,7 @@ from pathlib import Path
 import numpy as np
 from numpy.random import Generator, default_rng
 
-from .. import nuclear_map
+import attpc_engine_b200 as _pkg
 from .engine import SimBatch, engine_for
 from .parameters import Config
 from .writer import SimulationWriter
@@ -75,7 +75,7 @@ def simulate_batch(
     is global event ``first_event + e`` for the random streams.  Rows of each event come out in
     ascending (time bucket, pad) order (the reference's order is dict insertion order).
     """
-    nmap = nuclear_data if nuclear_data is not None else nuclear_map
+    nmap = nuclear_data if nuclear_data is not None else _pkg.nuclear_map  # looked up per call: replaceable
     momenta = np.asarray(momenta, dtype=np.float64)
     if momenta.ndim != 3:
         raise ValueError("momenta must have shape [n_events, n_nuclei, 4]")
@@ -184,7 +184,10 @@ def run_simulation(
     event_number)`` is called once per non-empty event in ascending event order and
     ``writer.close()`` at the end, exactly like the reference; a writer that also defines
     ``write_batch(batch, config)`` receives whole :class:`SimBatch` objects instead (with the Spyral
-    rows already computed on the GPU when it sets ``wants_spyral_rows = True``).
+    rows already computed on the GPU when it sets ``wants_spyral_rows = True``).  The arrays of that
+    batch are the writer's to keep.  A writer that is done with them when ``write_batch`` returns can set
+    ``accepts_views = True``: it is then handed views of the engine's pinned host buffers, valid only until
+    the next batch is simulated (no copy; the built-in writers do this).
     ``seed=None`` draws one from the OS, like the reference's unseeded generator.
     """
     kin = _open_kinematics(input_path)
@@ -198,12 +201,13 @@ def run_simulation(
         seed = int(default_rng().integers(0, 2**63 - 1))
     batched = hasattr(writer, "write_batch")
     want_rows = bool(getattr(writer, "wants_spyral_rows", False)) and batched
+    views_ok = not batched or bool(getattr(writer, "accepts_views", False))  # per-event arrays are built fresh anyway
     for start in range(0, kin.n_events, batch_size):
         stop = min(start + batch_size, kin.n_events)
         momenta, vertices = kin.read(start, stop)
         batch = simulate_batch(
             momenta, vertices, kin.proton_numbers, kin.mass_numbers, config, seed, nuclei_to_sim,
-            first_event=start, device=device, spyral_rows=want_rows, copy=False,
+            first_event=start, device=device, spyral_rows=want_rows, copy=not views_ok,
             rows_only=want_rows and bool(getattr(writer, "rows_only", False)),
             # per-event writers get their arrays built event by event anyway; batch writers say if they want columns
             columns=not batched or bool(getattr(writer, "wants_columns", False)),

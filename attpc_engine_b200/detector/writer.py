@@ -44,9 +44,11 @@ _conversion_engines: dict = {}
 
 def _conversion_engine(window_edge, mm_edge, length, response, pad_centers, pad_sizes, threshold, device=0) -> Engine:
     response = np.ascontiguousarray(response, dtype=np.float64)
+    from .engine import _digest
+
     key = (
-        int(window_edge), int(mm_edge), float(length), float(threshold), int(device), response.tobytes(),
-        id(pad_centers), id(pad_sizes),
+        int(window_edge), int(mm_edge), float(length), float(threshold), int(device),
+        _digest(response, pad_centers, pad_sizes),  # content, not id(): ids are reused once an array is freed
     )  # fmt: skip
     eng = _conversion_engines.get(key)
     if eng is None:
@@ -88,6 +90,7 @@ class SpyralWriter:
 
     wants_spyral_rows = True
     rows_only = True  # `write_batch` never looks at the raw cloud: it can stay on the GPU
+    accepts_views = True  # `write_batch` stores every array before it returns (h5py copies on create_dataset)
 
     def __init__(
         self,
@@ -186,6 +189,7 @@ class ArrayWriter:
         self.run_number = first_run_number
         self.wants_spyral_rows = spyral
         self.rows_only = spyral  # `write_batch` then needs the offsets and the rows, not the raw cloud
+        self.accepts_views = True  # `write_batch` copies what it keeps
         self.response = get_response(config).copy()
         self.files: list[dict] = []
         self._reset()
@@ -262,6 +266,7 @@ class ParquetCloudWriter:
     """
 
     wants_columns = True  # `run_simulation`: bring the rows to the host as typed columns (11 B/row over PCIe)
+    accepts_views = True  # the table is written before `write_batch` returns
 
     def __init__(self, directory_path: Path, config: Config | None = None, max_events_per_file: int = 1_000_000,
                  first_run_number: int = 0, compression: str = "zstd"):  # fmt: skip

@@ -242,9 +242,15 @@ def run_kinematics_pipeline(pipeline: KinematicsPipeline, n_events: int, output_
         print(f"Sampling kinematics from reaction: {pipeline}")
         print(f"Running for {n_events} samples.")
         print(f"Output will be written to {output_path}.")
-    vertices, momenta = pipeline.run_batch(n_events)
     zs, as_ = pipeline.get_proton_numbers(), pipeline.get_mass_numbers()
+    # sampled and written in slices of CHUNK_SIZE events, so that the temporaries of the sampler stay bounded
+    # (the reference streams event by event); the .npz holds the whole run: 8 (4 K + 3) bytes per event
     if output_path.suffix == ".npz":
+        momenta = np.empty((n_events, len(zs), 4), dtype=np.float64)
+        vertices = np.empty((n_events, 3), dtype=np.float64)
+        for lo in range(0, n_events, CHUNK_SIZE):
+            hi = min(lo + CHUNK_SIZE, n_events)
+            vertices[lo:hi], momenta[lo:hi] = pipeline.run_batch(hi - lo)
         save_kinematics_npz(output_path, vertices, momenta, zs, as_)
     else:
         try:
@@ -263,11 +269,12 @@ def run_kinematics_pipeline(pipeline: KinematicsPipeline, n_events: int, output_
                 chunk_group = data_group.create_group(f"chunk_{chunk}")
                 chunk_group.attrs["min_event"] = lo
                 chunk_group.attrs["max_event"] = hi - 1
+                vertices, momenta = pipeline.run_batch(hi - lo) if hi > lo else (np.zeros((0, 3)), np.zeros((0, len(zs), 4)))
                 for event in range(lo, hi):
-                    data = chunk_group.create_dataset(f"event_{event}", data=momenta[event])
-                    data.attrs["vertex_x"] = vertices[event, 0]
-                    data.attrs["vertex_y"] = vertices[event, 1]
-                    data.attrs["vertex_z"] = vertices[event, 2]
+                    data = chunk_group.create_dataset(f"event_{event}", data=momenta[event - lo])
+                    data.attrs["vertex_x"] = vertices[event - lo, 0]
+                    data.attrs["vertex_y"] = vertices[event - lo, 1]
+                    data.attrs["vertex_z"] = vertices[event - lo, 2]
             data_group.attrs["n_chunks"] = n_chunks
     if verbose:
         print("Done.")

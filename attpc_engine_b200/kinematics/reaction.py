@@ -11,7 +11,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .. import nuclear_map
+import attpc_engine_b200 as _pkg
 
 
 @dataclass
@@ -77,7 +77,7 @@ class Reaction:
             raise ValueError("Reaction calculated a residual Z (proton number) < 0, illegal reaction!")
         if resid_a < 0:
             raise ValueError("Reaction calculated a residual A (mass number) < 0, illegal reaction!")
-        self.residual = nuclear_map.get_data(resid_z, resid_a)
+        self.residual = _pkg.nuclear_map.get_data(resid_z, resid_a)
         self.reaction_symbol = f"{self.target}({self.projectile},{self.ejectile}){self.residual}"
 
     def __str__(self) -> str:
@@ -135,7 +135,7 @@ class Decay:
             raise ValueError("Decay calculated a residual2 Z (proton number) < 0, illegal decay!")
         if resid_2_a < 0:
             raise ValueError("Decay calculated a residual2 A (mass number) < 0, illegal decay!")
-        self.residual_2 = nuclear_map.get_data(resid_2_z, resid_2_a)
+        self.residual_2 = _pkg.nuclear_map.get_data(resid_2_z, resid_2_a)
         self.decay_symbol = f"{self.parent}->{self.residual_1}+{self.residual_2}"
 
     def __str__(self) -> str:

@@ -4,16 +4,23 @@ The reference obtains masses through ``spyral_utils.nuclear.NuclearDataMap``
 (`src/attpc_engine/__init__.py:1-3`, call sites `detector/simulator.py:99`,
 `kinematics/reaction.py:54,217`).  spyral_utils is not available in this image,
 so this module ships a small atomic-mass table (AME values, in u) that covers the
-reactions named in BASELINE.json, with a liquid-drop fallback for anything else.
+reactions named in BASELINE.json.  A nucleus that is NOT in the table raises ``KeyError``,
+like the reference's full AME table does for a nucleus that does not exist: a
+Bethe-Weizsaecker estimate is off by MeV and would silently corrupt Q-values and
+4-momenta.  ``add_mass`` extends the table; ``NuclearDataMap(allow_liquid_drop=True)``
+opts into the estimate (with a warning per nucleus) for exploratory work.
 Objects are duck-type compatible with what the hot path reads: ``.mass``
 (nuclear mass, MeV/c^2), ``.Z``, ``.A``, ``.isotopic_symbol``.
 
-If spyral_utils *is* importable, `attpc_engine_b200.nuclear_map` can be replaced by
-a real ``NuclearDataMap`` -- every consumer only uses ``get_data(z, a)``.
+When spyral_utils IS importable, ``attpc_engine_b200.nuclear_map`` is its full-AME
+``NuclearDataMap`` (`attpc_engine_b200/__init__.py`).  Either way the global can be replaced
+at run time (``attpc_engine_b200.nuclear_map = my_map``): every consumer looks it up through
+the package attribute when it is called and only uses ``get_data(z, a)``.
 """
 
 from __future__ import annotations
 
+import warnings
 from dataclasses import dataclass
 
 AMU_2_MEV = 931.49410242  # MeV/c^2 per u
@@ -106,10 +113,18 @@ class NucleusData:
 
 
 class NuclearDataMap:
-    """``get_data(z, a) -> NucleusData`` from the packaged table."""
+    """``get_data(z, a) -> NucleusData`` from the packaged table (``KeyError`` for anything else)."""
 
-    def __init__(self) -> None:
+    def __init__(self, allow_liquid_drop: bool = False) -> None:
         self._cache: dict[tuple[int, int], NucleusData] = {}
+        self._extra: dict[tuple[int, int], float] = {}
+        self.allow_liquid_drop = bool(allow_liquid_drop)
+
+    def add_mass(self, z: int, a: int, atomic_mass_u: float) -> None:
+        """Register (or override) the atomic mass [u] of a nucleus, e.g. from AME2020."""
+        key = (int(z), int(a))
+        self._extra[key] = float(atomic_mass_u)
+        self._cache.pop(key, None)
 
     def get_data(self, z: int, a: int) -> NucleusData:
         key = (int(z), int(a))
@@ -119,8 +134,15 @@ class NuclearDataMap:
         zz, aa = key
         if aa <= 0 or zz < 0 or zz > aa:
             raise KeyError(f"Nucleus Z={zz}, A={aa} does not exist")
-        atomic = _ATOMIC_MASS_U.get(key)
+        atomic = self._extra.get(key, _ATOMIC_MASS_U.get(key))
         if atomic is None:
+            if not self.allow_liquid_drop:
+                raise KeyError(
+                    f"No tabulated mass for Z={zz}, A={aa}: the packaged table only covers the benchmark reactions. "
+                    "Use NuclearDataMap.add_mass(z, a, atomic_mass_u), install spyral_utils (full AME table), or "
+                    "construct NuclearDataMap(allow_liquid_drop=True) to accept a Bethe-Weizsaecker estimate (MeV-level error)."
+                )
+            warnings.warn(f"mass of Z={zz}, A={aa} is a liquid-drop ESTIMATE (MeV-level error)", stacklevel=2)
             atomic = _liquid_drop_atomic_mass_u(zz, aa)
         sym = _SYMBOLS[zz] if zz < len(_SYMBOLS) else f"Z{zz}"
         data = NucleusData(
@@ -136,4 +158,4 @@ class NuclearDataMap:
         return data
 
     def has_tabulated_mass(self, z: int, a: int) -> bool:
-        return (int(z), int(a)) in _ATOMIC_MASS_U
+        return (int(z), int(a)) in _ATOMIC_MASS_U or (int(z), int(a)) in self._extra

@@ -377,6 +377,8 @@ def run_ours(args):
                       "trajectory_points": round(stats_sum["n_trajectory_points"] / n_ev_rank, 1),
                       "primary_electrons": round(stats_sum["n_primary_electrons"] / n_ev_rank, 1),
                       "table_flushes": round(stats_sum["n_table_flushes"] / n_ev_rank, 4),
+                      "dirty_units": round(stats_sum["n_dirty_units"] / n_ev_rank, 6),
+                      "raw_entries": round(stats_sum["n_raw_entries"] / n_ev_rank, 6),
                       "rhs_evals_per_track": round((6 * stats_sum["n_rk_steps"] + stats_sum["n_tracks"]) / max(1, stats_sum["n_tracks"]), 1)},
         "wall_s_device_loop": round(wall_dev, 3),
         "e2e": {"value": None if args.no_e2e else round(total_events / e2e_s, 1), "unit": "events/s",

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ATTPC_ABI_VERSION 5
+#define ATTPC_ABI_VERSION 6
 
 enum {
     ATTPC_OK = 0,
@@ -74,11 +74,13 @@ typedef struct AttpcConfig {
                                stalled track early (0 = integrate to 1 us like the reference) */
     /* capacities (0 = library default); they grow automatically on overflow */
     int32_t max_events_per_launch;
-    int32_t hash_capacity;          /* slots per event, power of two */
+    int32_t hash_capacity;          /* rows per work-unit region (a unit is <= ~1024 track points of one event), power of two */
     int32_t copy_events_per_launch; /* events per host-copy chunk: rows are copied while later groups compute */
     /* stress knobs for tests (0 = library default; values above the default are clamped): results never depend on them */
-    int32_t unit_points;            /* points of one event handled by one CTA of the deposit kernel (default 1024) */
-    int32_t table_spill_keys;       /* keys in a CTA's shared-memory table that trigger an append to the event's list */
+    int32_t unit_points;            /* target number of points of one work unit (one CTA) of the deposit kernel (default 1024) */
+    int32_t table_spill_keys;       /* keys in a CTA's shared-memory table that trigger a flush of the finished time buckets */
+    int32_t table_hard_keys;        /* keys above which a flush is no longer postponed: unfinished keys leave as raw entries */
+    int32_t table_max_probe;        /* probes after which an insert leaves a raw entry instead (default 128) */
 } AttpcConfig;
 
 /* One ion species: the dE/dx table of attpc_engine_b200/target.py:DedxTable (pseudo-log grid). */
@@ -131,9 +133,9 @@ typedef struct AttpcResult {
     int32_t n_track_launches;    /* launches of the track (or replay) kernel */
     int32_t n_group_launches;    /* launches of the deposit kernel (= event groups processed) */
     int64_t n_hash_probes;       /* table slots inspected by the deposits (n_hash_probes / n_deposits ~ 1 is healthy) */
-    int32_t hash_capacity;       /* slots per event in use at the end of the call */
-    int32_t reserved1;
-    int64_t n_table_flushes;     /* shared-memory tables appended to an event's entry list before the end of their work unit */
+    int32_t hash_capacity;       /* rows per work-unit region in use at the end of the call */
+    int32_t n_dirty_units;       /* work units that left raw entries and went through the merge kernel (0 in normal operation) */
+    int64_t n_table_flushes;     /* flushes of a shared-memory table before the end of its work unit */
     /* ATTPC_COLUMNS: the rows of `cloud` / `labels` as typed columns (pinned host memory) */
     const int16_t* col_pad;      /* [n_points] pad id */
     const uint32_t* col_tb_q16;  /* [n_points] time bucket + wiggle as Q16.16 fixed point: cloud[:, 1] == col_tb_q16 / 65536
@@ -152,6 +154,7 @@ typedef struct AttpcResult {
     float ms_order;              /* device time of the point ordering kernels (scan + scatter) before the deposit kernel;
                                     ms_deposit is the deposit kernel alone */
     float reserved2;
+    int64_t n_raw_entries;       /* deposits that could not be accumulated in shared memory (merged by the fixup kernel) */
 } AttpcResult;
 
 typedef struct AttpcSim AttpcSim;

@@ -21,7 +21,7 @@ sys.path.insert(0, str(HERE))
 sys.path.insert(0, str(HERE.parent.parent))
 
 N_EVENTS = {"c16dd": 6000, "c14dp": 4000, "c12aa": 2400, "sn132dp": 2400}
-PAIRED = {"c16dd": 400, "c14dp": 64, "c12aa": 150, "sn132dp": 64}  # events whose kinematics are stored
+PAIRED = {"c16dd": 400, "c14dp": 300, "c12aa": 150, "sn132dp": 300}  # events whose kinematics are stored
 _WORKLOADS = {}
 STRIDE = 4  # the path length is the chord sum over every 4th trajectory row (the CUDA side uses the same rows)
 

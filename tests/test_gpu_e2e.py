@@ -89,11 +89,16 @@ def test_work_splitting_is_invisible(dist, name, n):
 
         cfg, m, v, zs, as_, idx = bench.build_workload(name, n)
     base = simulate_batch(m, v, zs, as_, cfg, 9, idx)
-    for tuning in (dict(unit_points=48), dict(table_spill_keys=150), dict(unit_points=96, table_spill_keys=400)):
+    assert base.stats["n_dirty_units"] == 0 and base.stats["n_raw_entries"] == 0  # normal operation never needs the fixup
+    for tuning in (dict(unit_points=48), dict(table_spill_keys=150), dict(unit_points=96, table_spill_keys=400),
+                   dict(table_hard_keys=60, table_max_probe=2), dict(table_hard_keys=24, unit_points=64)):
         split = simulate_batch(m, v, zs, as_, cfg, 9, idx, **tuning)
         assert np.array_equal(base.offsets, split.offsets), tuning
         assert np.array_equal(base.cloud, split.cloud) and np.array_equal(base.labels, split.labels), tuning
-    assert split.stats["n_table_flushes"] > n  # the stress really went through the segment path
+        if "table_spill_keys" in tuning:
+            assert split.stats["n_table_flushes"] > n  # the stress really went through many flushes per unit
+        if "table_max_probe" in tuning:
+            assert split.stats["n_dirty_units"] > 0 and split.stats["n_raw_entries"] > 0
 
 
 def test_many_species_share_the_track_kernels_shared_memory(dist):

@@ -7,6 +7,19 @@ event, time-bucket extent, pads per event, median / maximum charge per point, ch
 one random pad ("charge per pad"), cloud points per track (label), trajectory rows per track and path length per
 track ("track-length and point-count distributions").
 
+Multiple comparisons: the four workloads carry about sixty KS tests; at a per-test level of 0.01 a sound
+implementation trips one of them in 45 % of the runs.  An observable that falls below 0.01 is therefore re-tested
+ONCE on a fresh, independent CUDA sample (other kinematics seed, other simulation seed) and must pass there: a real
+difference fails both with near certainty, chance fails both with probability 1e-4.  (Measured while writing this:
+with the SAME kinematics the CUDA path and the reference's algorithm agree per event to 2e-4 in total charge and
+8e-4 in the maximum charge, tools/tolerance_study.py + tools/paired_probe.py; KS p-values of 0.01-0.05 in the
+unpaired comparison come from the kinematics draw of the fixed reference sample.)
+
+`test_paired_events_show_no_bias` closes the gap a KS test on kinematics-dominated observables leaves open: on the
+events whose kinematics the fixture stores, the per-event ratio CUDA / reference of the number of cloud points and of
+the total charge must average to 1 within a few 1e-3 (the two sides draw different random numbers, so single events
+differ by the Fano noise; a few-percent bias in the electron count would show as a ratio of 1.0x).
+
 Also here: the production-only early stop of stalled ions (`inert_forever`) must not change a single row.
 """
 
@@ -57,29 +70,30 @@ def _event_observables(batch, indices, seed):
     return {k: np.asarray(v, dtype=np.float64) for k, v in obs.items()}, per_label
 
 
-@pytest.mark.parametrize("name", WORKLOAD_NAMES)
-def test_distributions_match_reference_unpaired(dist, name):
+def _ks_table(dist, name, kin_seed, sim_seed, only=None):
+    """KS p-value of every observable (or of those in `only`) for one independent CUDA sample."""
     import bench
     from attpc_engine_b200.detector import simulate_batch
     from attpc_engine_b200.detector.engine import engine_for
     from attpc_engine_b200.detector.simulator import _nuclei_for
 
     n = N_GPU[name]
-    cfg, momenta, vertices, zs, as_, indices = bench.build_workload(name, n, seed_offset=1)  # not the reference's events
-    batch = simulate_batch(momenta, vertices, zs, as_, cfg, 20261018, indices, columns=True)
-    obs, per_label = _event_observables(batch, indices, 5)
-    failures = []
+    cfg, momenta, vertices, zs, as_, indices = bench.build_workload(name, n, seed_offset=kin_seed)  # not the reference's events
+    p_values = {}
 
     def check(what, ours, theirs):
-        p = ks_2samp(ours, theirs).pvalue
-        if not p > P_MIN:
-            failures.append(f"{what}: p = {p:.3g} (n = {len(ours)} vs {len(theirs)})")
+        if only is None or what in only:
+            p_values[what] = ks_2samp(ours, theirs).pvalue
 
-    for key, ours in obs.items():
-        check(key, ours, dist[f"{name}/{key}"])
     charged = [k for k, idx in enumerate(indices) if zs[idx] != 0]
-    for k in charged:
-        check(f"points_per_track[{indices[k]}]", per_label[:, k], dist[f"{name}/points_per_track"][:, k])
+    cloud_obs = [w for w in (only or ["n_points"]) if not w.startswith(("traj_rows", "path_length"))]
+    if cloud_obs:
+        batch = simulate_batch(momenta, vertices, zs, as_, cfg, sim_seed, indices, columns=True)
+        obs, per_label = _event_observables(batch, indices, 5 + kin_seed)
+        for key, ours in obs.items():
+            check(key, ours, dist[f"{name}/{key}"])
+        for k in charged:
+            check(f"points_per_track[{indices[k]}]", per_label[:, k], dist[f"{name}/points_per_track"][:, k])
     # trajectories: rows on the 0.1 ns grid and path length per track; freeze_ke_mev = 0 integrates a stalled ion to
     # 1 us like the reference, so that the row counts mean the same thing on both sides
     nuclei = _nuclei_for(zs, as_, indices, nuclear_map)
@@ -87,6 +101,8 @@ def test_distributions_match_reference_unpaired(dist, name):
     n_traj = min(n, 1500)
     max_rows = 10001 // STRIDE + 1
     for t, k in enumerate(charged):
+        if only is not None and not {f"traj_rows[{indices[k]}]", f"path_length[{indices[k]}]"} & set(only):
+            continue
         nucleus = nuclear_map.get_data(int(zs[indices[k]]), int(as_[indices[k]]))
         rows, length = [], []
         for a in range(0, n_traj, 250):
@@ -100,7 +116,38 @@ def test_distributions_match_reference_unpaired(dist, name):
                 length.append(np.sqrt((seg**2).sum(axis=1)).sum() if m > 1 else 0.0)
         check(f"traj_rows[{indices[k]}]", np.concatenate(rows).astype(np.float64), dist[f"{name}/traj_rows"][:, t])
         check(f"path_length[{indices[k]}]", np.asarray(length), dist[f"{name}/path_length"][:, t])
-    assert not failures, f"{name}: " + "; ".join(failures)
+    return p_values
+
+
+@pytest.mark.parametrize("name", WORKLOAD_NAMES)
+def test_distributions_match_reference_unpaired(dist, name):
+    first = _ks_table(dist, name, kin_seed=1, sim_seed=20261018)
+    assert len(first) >= 12
+    suspects = [k for k, p in first.items() if not p > P_MIN]
+    if suspects:  # one re-test on an independent sample (see the module docstring)
+        second = _ks_table(dist, name, kin_seed=2, sim_seed=77, only=suspects)
+        failed = {k: (first[k], second[k]) for k in suspects if not second[k] > P_MIN}
+        assert not failed, f"{name}: KS p-values (first sample, independent re-test) {failed}"
+
+
+@pytest.mark.parametrize("name", WORKLOAD_NAMES)
+def test_paired_events_show_no_bias(dist, name):
+    from attpc_engine_b200.detector import simulate_batch
+    from tests.common import workload_config
+
+    m, v = dist[f"{name}/momenta"], dist[f"{name}/vertices"]
+    zs, as_, indices = dist[f"{name}/Z"], dist[f"{name}/A"], list(dist[f"{name}/indices"])
+    batch = simulate_batch(m, v, zs, as_, workload_config(name), 4242, indices, columns=True)
+    n_ref, q_ref = dist[f"{name}/n_points"][: len(m)], dist[f"{name}/sum_charge"][: len(m)]
+    n_gpu = np.diff(batch.offsets).astype(np.float64)
+    q_gpu = np.array([batch.event(e)[0][:, 2].sum() for e in range(len(m))])
+    ok = (n_ref > 50) & (n_gpu > 50)
+    assert ok.sum() > 0.8 * len(m)
+    assert np.array_equal(n_ref == 0, n_gpu == 0) or abs(int((n_ref == 0).sum()) - int((n_gpu == 0).sum())) <= 2
+    for what, ratio in (("cloud points", n_gpu[ok] / n_ref[ok]), ("total charge", q_gpu[ok] / q_ref[ok])):
+        err = ratio.std() / np.sqrt(len(ratio))
+        assert abs(ratio.mean() - 1.0) < max(5.0 * err, 2e-3), f"{name}: {what}: CUDA / reference = {ratio.mean():.5f} +- {err:.5f}"
+        assert abs(np.median(ratio) - 1.0) < 5e-3, f"{name}: {what}: median ratio {np.median(ratio):.5f}"
 
 
 @pytest.mark.parametrize("name", WORKLOAD_NAMES)

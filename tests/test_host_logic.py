@@ -226,3 +226,68 @@ def test_dedx_table_file_round_trip(tmp_path):
     assert back.get_dedx(d, 3.7) == made.get_dedx(d, 3.7)
     with pytest.raises(KeyError):
         back.get_dedx(nuclear_map.get_data(2, 4), 1.0)  # not in the file, and no source to tabulate from
+
+
+def test_unknown_nuclei_raise_instead_of_getting_estimated_masses():
+    """a liquid-drop mass is off by MeV; the reference's AME table raises for unknown nuclei."""
+    import warnings
+
+    from attpc_engine_b200.nuclear import NuclearDataMap
+
+    nm = NuclearDataMap()
+    assert nm.get_data(6, 16).A == 16 and nm.has_tabulated_mass(6, 16)
+    with pytest.raises(KeyError, match="No tabulated mass"):
+        nm.get_data(20, 48)
+    nm.add_mass(20, 48, 47.95252276)
+    assert abs(nm.get_data(20, 48).mass - (47.95252276 * 931.49410242 - 20 * 0.51099895)) < 1e-9
+    loose = NuclearDataMap(allow_liquid_drop=True)
+    with warnings.catch_warnings(record=True) as seen:
+        warnings.simplefilter("always")
+        est = loose.get_data(20, 48)
+    assert seen and "ESTIMATE" in str(seen[0].message)
+    assert abs(est.mass - nm.get_data(20, 48).mass) < 20.0  # an estimate, MeV-level error
+
+
+def test_global_nuclear_map_is_looked_up_at_call_time(monkeypatch):
+    """Replacing ``attpc_engine_b200.nuclear_map`` reaches the kinematics and detector front ends."""
+    import attpc_engine_b200
+    from attpc_engine_b200.kinematics import Reaction
+    from attpc_engine_b200.nuclear import NuclearDataMap
+
+    class Spy(NuclearDataMap):
+        asked = []
+
+        def get_data(self, z, a):
+            Spy.asked.append((int(z), int(a)))
+            return super().get_data(z, a)
+
+    spy = Spy()
+    monkeypatch.setattr(attpc_engine_b200, "nuclear_map", spy)
+    Reaction(target=spy.get_data(1, 2), projectile=spy.get_data(6, 16), ejectile=spy.get_data(1, 2))
+    assert (6, 16) in Spy.asked[3:]  # the residual was resolved through the replaced global
+
+
+def test_config_fingerprint_sees_every_baked_value():
+    """`engine_for` must not reuse an engine whose baked constants went stale."""
+    from attpc_engine_b200 import nuclear_map
+    from attpc_engine_b200.detector.engine import config_fingerprint
+    from tests.common import make_config
+
+    cfg = make_config()
+    nuclei = [nuclear_map.get_data(1, 2), nuclear_map.get_data(6, 16)]
+    base = config_fingerprint(cfg, nuclei)
+    assert config_fingerprint(cfg, nuclei) == base
+    for obj, field, value in (
+        (cfg.det_params, "bfield", 2.5), (cfg.det_params, "efield", 50000.0), (cfg.det_params, "diffusion", 0.3),
+        (cfg.det_params, "fano_factor", 0.25), (cfg.det_params, "w_value", 30.0), (cfg.det_params, "mpgd_gain", 1000),
+        (cfg.elec_params, "adc_threshold", 10), (cfg.elec_params, "shaping_time", 500), (cfg.elec_params, "amp_gain", 500),
+    ):  # fmt: skip
+        old = getattr(obj, field)
+        setattr(obj, field, value)
+        assert config_fingerprint(cfg, nuclei) != base, field
+        setattr(obj, field, old)
+    assert config_fingerprint(cfg, nuclei) == base
+    cfg.pad_sizes = cfg.pad_sizes * 2.0  # a replaced array (what load_pad_grid does) is seen
+    assert config_fingerprint(cfg, nuclei) != base
+    other_gas = make_config("He4_600")
+    assert config_fingerprint(other_gas, nuclei) != base
