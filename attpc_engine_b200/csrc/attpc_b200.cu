@@ -138,7 +138,8 @@ struct AttpcSim {
     DevArray<uint32_t> rec;
     DevArray<uint32_t> perm;
     DevArray<int32_t> unit_event, unit_first, unit_count, unit_order, n_units, event_unit0, event_nunits;
-    DevArray<unsigned> pstart, unit_kept, unit_raw, dirty;
+    DevArray<unsigned> pstart, unit_kept, unit_raw, unit_nseg, unit_segend, dirty;
+    DevArray<uint32_t> tbend;
     int32_t ranks = 1;
     int32_t max_units = 0;
     DevArray<HashEntry> hash, fix_rows;
@@ -239,6 +240,7 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     CU(sim->geom.reserve(pts * GEOM_DOUBLES));
     CU(sim->rec.reserve(pts * REC_WORDS));
     CU(sim->perm.reserve(pts));
+    CU(sim->tbend.reserve(pts));
     // a unit is a time-bucket range of one event: at most one per event plus one per unit_points points
     sim->max_units = (int32_t)(sim->group_events + sim->group_point_cap / sim->unit_points + 1);
     CU(sim->unit_event.reserve(n_groups * sim->max_units));
@@ -247,6 +249,8 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     CU(sim->unit_order.reserve(n_groups * sim->max_units));
     CU(sim->unit_kept.reserve(n_groups * sim->max_units));
     CU(sim->unit_raw.reserve(n_groups * sim->max_units));
+    CU(sim->unit_nseg.reserve(n_groups * sim->max_units));
+    CU(sim->unit_segend.reserve(n_groups * sim->max_units * MAX_SEGMENTS));
     CU(sim->dirty.reserve(n_groups * sim->max_units + 2));
     CU(sim->n_units.reserve(n_groups));
     CU(sim->event_unit0.reserve(launch_events));
@@ -303,6 +307,9 @@ PointBuf point_buf(AttpcSim* sim, int which) {
     pb.unit_kept = sim->unit_kept.p;
     pb.unit_raw = sim->unit_raw.p;
     pb.perm = sim->perm.p;
+    pb.tbend = sim->tbend.p;
+    pb.unit_nseg = sim->unit_nseg.p;
+    pb.unit_segend = sim->unit_segend.p;
     pb.event_unit0 = sim->event_unit0.p;
     pb.event_nunits = sim->event_nunits.p;
     pb.dirty = sim->dirty.p;
@@ -360,7 +367,8 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
     Counters* ctr = sim->slot[which].counters.p;
     const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
     const size_t fix_smem = (size_t)FIXUP_SMEM_ITEMS * sizeof(uint64_t);
-    const size_t emit_smem = (size_t)EMIT_TILE * sizeof(uint4);
+    const size_t emit_smem = sizeof(EmitShared);
+    CU(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
     CU(cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEPOSIT_SMEM_BYTES));
     // Groups are processed in chunks: every kernel is launched once per chunk with one grid row per group, so the
     // ramp-up and tail of a launch are paid once per chunk.  When rows go to the host a chunk is what is copied while
@@ -738,7 +746,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             if (now.overflow_points) {
                 sim->group_point_cap *= 2;
                 for (auto& s2 : sim->slot) s2.release_points();
-                sim->geom.release(); sim->rec.release(); sim->perm.release(); sim->hash.release();
+                sim->geom.release(); sim->rec.release(); sim->perm.release(); sim->tbend.release(); sim->hash.release();
                 sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release();
                 sim->unit_order.release();
             }
@@ -931,6 +939,7 @@ void attpc_destroy(AttpcSim* sim) {
     sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release(); sim->stop_ns.release(); sim->plan_cls.release(); sim->plan_counts.release(); sim->plan_order.release();
     sim->hash.release(); sim->fix_rows.release(); sim->fix_items.release(); sim->perm.release();
     sim->unit_kept.release(); sim->unit_raw.release(); sim->dirty.release(); sim->event_unit0.release();
+    sim->unit_nseg.release(); sim->unit_segend.release(); sim->tbend.release();
     sim->event_nunits.release();
     sim->geom.release(); sim->rec.release();
     sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release(); sim->unit_order.release();

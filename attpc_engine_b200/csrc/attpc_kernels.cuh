@@ -95,6 +95,7 @@ struct PointBuf {
     double* geom;       // ordered: GEOM_DOUBLES per point, the per-point constants of the drift mesh (exact path)
     uint32_t* rec;      // ordered: REC_WORDS per point, what the deposit kernel reads (see make_point)
     uint32_t* perm;     // ordered: per event, the indices of its depositing points in ascending time-bucket order
+    uint32_t* tbend;    // ordered: per position of that list, the position where the next time bucket starts
     // work units of the deposit kernel (one CTA each): a time-bucket range of one event (event_sort_kernel)
     int32_t* unit_event;   // [n_groups][max_units] event index inside the group
     int32_t* unit_first;   // first position of the range inside the event's time-bucket-ordered list (perm)
@@ -102,6 +103,8 @@ struct PointBuf {
     int32_t* unit_order;   // units by decreasing size (longest first)
     unsigned* unit_kept;   // rows the unit left in its region (after the time-bucket mask), in final order
     unsigned* unit_raw;    // entries the unit had to leave unmerged at the top of its region (fixup_kernel)
+    unsigned* unit_nseg;   // segments (flushes) the unit's rows were written in; 0 = the rows are already in final order
+    unsigned* unit_segend; // [max_units][MAX_SEGMENTS] end of every segment inside the region
     int32_t* n_units;      // [n_groups]
     int32_t* event_unit0;  // [launch events] first unit of the event (its units are consecutive, ascending time bucket)
     int32_t* event_nunits; // [launch events]
@@ -994,6 +997,7 @@ constexpr int MAX_UNITS_SORT = 8192;
 constexpr int GEOM_DOUBLES = 12;
 constexpr int REC_WORDS = 16;       // words of an ordered point record (make_point)
 constexpr int TB_BINS = 1024;       // bins of the per-event counting sort on the time bucket (SimParams.n_bins <= TB_BINS)
+constexpr int MAX_SEGMENTS = 64;    // flushes of one work unit emit_kernel can order one by one (more: fixup_kernel)
 
 // Per group, single CTA: exclusive scan of the (event, rank) list lengths -> start of every list in the group's
 // ordered run (the lists of one event are consecutive: the event's points form one contiguous run).
@@ -1152,9 +1156,15 @@ event_sort_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView ch
     }
     // scatter the point indices into time-bucket order
     uint32_t* perm = pb.perm + base;
+    uint32_t* tbend = pb.tbend + base;
     for (unsigned p = tid; p < n; p += SORT_THREADS) {
         const unsigned w = __ldg(pb.rec + (base + p) * REC_WORDS);
-        if (w >> 30) perm[atomicAdd(&s_fill[tb_bin(P, w & 0x1FFFFFFFu)], 1u)] = p;
+        if (w >> 30) {
+            const int bin = tb_bin(P, w & 0x1FFFFFFFu);
+            const unsigned at = atomicAdd(&s_fill[bin], 1u);
+            perm[at] = p;
+            tbend[at] = s_start[bin + 1];  // first position of the next bin (bins are time buckets but for the last one)
+        }
     }
     __syncthreads();  // (also orders the unit_first stores of this CTA before the reads below)
     const unsigned live = s_start[TB_BINS];
@@ -1400,16 +1410,14 @@ constexpr int DEPOSIT_WARPS = DEPOSIT_THREADS / 32;
 constexpr int POINTS_PER_WARP = 3;   // three active points per warp pass: 3 x 10 mesh rows on 30 lanes
 constexpr int POINTS_PER_ITER = DEPOSIT_WARPS * POINTS_PER_WARP;
 constexpr int QUEUE_SLOTS = 64;      // per-warp ring of finished (key, charge) runs waiting for a full 32-lane insert
-constexpr int SMEM_SLOTS = 4096;     // per-CTA table in shared memory: 10 B per slot = 40 KB, four CTAs per SM
-constexpr int SMEM_SPILL_DEFAULT = 1700;  // keys that trigger a flush of the finished time buckets
-constexpr int SMEM_HARD_DEFAULT = 2400;   // keys above which a flush is no longer postponed (59 % load)
-constexpr int MAX_PROBE_DEFAULT = 128;
-constexpr int FLUSH_BINS = 640;      // time buckets (relative to the first unfinished one) the flush sorts exactly;
-                                     // whatever lies beyond shares the last bin (ordered by full key, just slower)
+constexpr int SMEM_SLOTS = 4864;     // per-CTA table in shared memory: 10 B per slot = 47.5 KB, four CTAs per SM
+constexpr int SMEM_SPILL_DEFAULT = 1600;  // keys that trigger a flush of the finished time buckets
+constexpr int SMEM_HARD_DEFAULT = 2800;   // keys above which a flush is no longer postponed (58 % load)
+constexpr int MAX_PROBE_DEFAULT = SMEM_SLOTS;  // an insert only gives up on a table that is completely full
 constexpr int CARRY_SLOTS = 512;     // unfinished keys whose slots a flush remembers (more: found again by a rescan)
-constexpr size_t DEPOSIT_SMEM_BYTES = (size_t)SMEM_SLOTS * (2 * sizeof(unsigned) + sizeof(uint16_t));
+constexpr int DEPOSIT_TABLE_WORDS = 2 * SMEM_SLOTS + SMEM_SLOTS / 2;  // key words, charge low words, charge high halves
 constexpr unsigned SMEM_KEY_MASK = 0x0FFFFFFFu;  // low 28 bits: ((tb << 15) | pad) + 1; top 4 bits: track rank
-static_assert(SMEM_SLOTS % (4 * DEPOSIT_THREADS) == 0 && (SMEM_SLOTS & (SMEM_SLOTS - 1)) == 0, "table size");
+static_assert(SMEM_SLOTS % 8 == 0, "table size: uint4 loads of the key words, 16-byte sub-arrays");
 
 // Slot word = compact key (time bucket < 8192, pad id < 32768) + 1 in the low 28 bits, 0 = empty, and in the top four
 // bits the rank of the last track that touched the slot (atomicMax: same key bits, the highest rank wins).  The charge
@@ -1430,9 +1438,8 @@ __device__ __forceinline__ unsigned smem_home(unsigned key1) {
     unsigned h = key1 * 0x9E3779B1u;
     h ^= h >> 15;
     h *= 0x85EBCA6Bu;
-    return h >> (32 - 12);  // 4096 slots
+    return __umulhi(h, (unsigned)SMEM_SLOTS);  // multiply-shift range reduction, no division
 }
-static_assert(SMEM_SLOTS == 4096, "smem_home shifts for 4096 slots");
 
 // Find the slot of `key1`, claiming an empty one if it is new (counted in the lane's `n_new`; the warp publishes the
 // sum before every fill check).  Gives up after max_probe probes (returns SMEM_SLOTS): the caller then leaves the
@@ -1462,7 +1469,7 @@ __device__ __forceinline__ unsigned smem_find(const SmemTable& t, unsigned key1,
             }
         }
         probes += 1u;  // (extra probes; the first probe of every insert is counted from the number of pushes)
-        slot = (slot + 1u) & (unsigned)(SMEM_SLOTS - 1);
+        slot = slot + 1u == (unsigned)SMEM_SLOTS ? 0u : slot + 1u;
     }
     return found ? slot : (unsigned)SMEM_SLOTS;
 }
@@ -1488,28 +1495,46 @@ __device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t,
 // Everything a CTA of the deposit kernel keeps in (static) shared memory besides its table.
 struct DepositShared {
     unsigned ring[3][DEPOSIT_WARPS][QUEUE_SLOTS];  // key word, charge low, charge high of the queued runs
-    unsigned hist[FLUSH_BINS];                     // flush: finished keys per relative time bucket -> write positions
     double w[MESH_N][MESH_N + 1];                  // constant mesh weights, row stride 11 doubles
     uint16_t carry[CARRY_SLOTS];                   // flush: slots of the unfinished keys
     unsigned next[DEPOSIT_WARPS];                  // list position every warp stands at when a flush is called
-    unsigned wsum[DEPOSIT_WARPS];
-    unsigned nkeys, flush, rows, trigger, lo_bin, frontier, nsurv, nfinal, nsv, mode, nkept;
+    unsigned nkeys, flush, rows, trigger, frontier, nsurv, nfinal, nsv, mode, nkept, nseg, last_pos;
 };
 
 // What the out-of-line helpers of the deposit kernel need to know about the CTA's work unit (kept in shared memory:
 // the same for every thread, and a reference to a local copy would turn every field access into a local-memory load).
 struct DepositCtx {
-    SmemTable t;
-    DepositShared* sh;
     HashEntry* region;       // the unit's rows (from the bottom) and raw entries (from the top)
     unsigned* raw_counter;
     Counters* ctr;
+    unsigned* segend;        // ends of the unit's segments inside the region
     const uint32_t* perm;    // the event's points in time-bucket order
     const uint32_t* rec0;    // record of the event's first point
     unsigned cap, max_probe;
     int end, slot_event, spill_keys, hard_keys;
 };
-static_assert(sizeof(DepositShared) + sizeof(DepositCtx) + DEPOSIT_SMEM_BYTES + 1024 <= 233472 / 4, "four deposit CTAs per SM");
+// Dynamic shared memory of a deposit CTA: the table, then DepositShared, then DepositCtx.  The out-of-line helpers
+// reach all three through the one extern array, i.e. at addresses known at compile time.
+constexpr size_t DEPOSIT_SHARED_AT = (size_t)DEPOSIT_TABLE_WORDS * sizeof(unsigned);
+constexpr size_t DEPOSIT_CTX_AT = (DEPOSIT_SHARED_AT + sizeof(DepositShared) + 15) / 16 * 16;
+constexpr size_t DEPOSIT_SMEM_BYTES = DEPOSIT_CTX_AT + sizeof(DepositCtx);
+static_assert(DEPOSIT_SMEM_BYTES + 1024 <= 233472 / 4, "four deposit CTAs per SM");
+static_assert(DEPOSIT_SHARED_AT % 16 == 0, "alignment of DepositShared");
+
+__device__ __forceinline__ unsigned* dep_smem() {
+    extern __shared__ __align__(16) unsigned s_dep[];
+    return s_dep;
+}
+__device__ __forceinline__ SmemTable dep_table() {
+    unsigned* base = dep_smem();
+    return SmemTable{base, base + SMEM_SLOTS, base + 2 * SMEM_SLOTS};
+}
+__device__ __forceinline__ DepositShared& dep_shared() {
+    return *reinterpret_cast<DepositShared*>(reinterpret_cast<unsigned char*>(dep_smem()) + DEPOSIT_SHARED_AT);
+}
+__device__ __forceinline__ DepositCtx& dep_ctx() {
+    return *reinterpret_cast<DepositCtx*>(reinterpret_cast<unsigned char*>(dep_smem()) + DEPOSIT_CTX_AT);
+}
 
 struct WarpStats {
     unsigned n_new, n_probe, n_raw;
@@ -1517,8 +1542,8 @@ struct WarpStats {
 
 // A deposit the table could not take (or a key a flush could not finish): left as a raw entry at the top of the
 // unit's region, merged by fixup_kernel.
-__device__ __forceinline__ void raw_entry(const DepositCtx& c, unsigned word, unsigned long long q, unsigned& n_raw,
-                                          int cause) {
+__device__ __forceinline__ void raw_entry(unsigned word, unsigned long long q, unsigned& n_raw, int cause) {
+    const DepositCtx& c = dep_ctx();
     const unsigned r = atomicAdd(c.raw_counter, 1u);
     n_raw += 1u;
     atomicAdd(&c.ctr->raw_by_cause[cause], 1ULL);  // (rare path)
@@ -1531,94 +1556,97 @@ __device__ __forceinline__ void raw_entry(const DepositCtx& c, unsigned word, un
 
 // Whole warp: insert ring entries [q_head, q_head + n), n <= 32, one per lane.  Out of line on purpose: the call sits
 // in the unrolled pixel loop and the kernel must stay inside the instruction cache.
-__device__ __noinline__ void drain_ring(const DepositCtx& c, int warp, unsigned q_head, unsigned n, WarpStats& st) {
+__device__ __noinline__ void drain_ring(int warp, unsigned q_head, unsigned n, WarpStats& st) {
     const int lane = threadIdx.x & 31;
+    const SmemTable t = dep_table();
+    DepositShared& sh = dep_shared();
     __syncwarp();
     const bool mine = (unsigned)lane < n;
     unsigned kw = 0u, slot = (unsigned)SMEM_SLOTS;
     unsigned long long q = 0ULL;
     if (mine) {
         const unsigned at = (q_head + (unsigned)lane) & (QUEUE_SLOTS - 1);
-        kw = c.sh->ring[0][warp][at];
-        q = ((unsigned long long)c.sh->ring[2][warp][at] << 32) | c.sh->ring[1][warp][at];
-        slot = smem_find(c.t, kw & SMEM_KEY_MASK, kw >> 28, c.max_probe, st.n_new, st.n_probe);
+        kw = sh.ring[0][warp][at];
+        q = ((unsigned long long)sh.ring[2][warp][at] << 32) | sh.ring[1][warp][at];
+        slot = smem_find(t, kw & SMEM_KEY_MASK, kw >> 28, dep_ctx().max_probe, st.n_new, st.n_probe);
     }
     __syncwarp();  // the probe loops end at different times: all lanes together again before the atomics
     if (mine) {
         if (slot < (unsigned)SMEM_SLOTS) {
-            smem_charge(c.t, slot, q, &c.ctr->overflow_charge);
-            atomicMax(&c.t.word[slot], kw);  // same key bits: the highest rank wins (transporter.py:247-249)
+            smem_charge(t, slot, q, &dep_ctx().ctr->overflow_charge);
+            atomicMax(&t.word[slot], kw);  // same key bits: the highest rank wins (transporter.py:247-249)
         } else {
-            raw_entry(c, kw, q, st.n_raw, 0);
+            raw_entry(kw, q, st.n_raw, 0);
         }
     }
     __syncwarp();
 }
 
-__device__ __forceinline__ unsigned rel_bin(const SimParams& P, unsigned key1, unsigned lo_bin) {
-    const int b = tb_bin(P, (key1 - 1u) >> 15) - (int)lo_bin;  // bin of a key relative to the first unfinished bucket
-    return (unsigned)min(max(b, 0), FLUSH_BINS - 1);
-}
-
 // FLUSH (all threads of the CTA, after a barrier that follows every warp's drain; every point of the unit's list
 // before position `next` has been deposited, none at or after it).  Keys in time buckets below the bucket of point
 // `next` can receive nothing more (points are ordered, units never share a bucket): they are masked (0 <= tb < 512,
-// detector/simulator.py:111-113) and written to the unit's region, grouped by time bucket (counting sort: histogram,
-// scan, scatter); emit_kernel orders the pads inside a bucket when it reads them.  The keys at or above the frontier
-// are parked in global memory while the table is cleared and re-inserted.  Segments of successive flushes are disjoint
-// and ascending in time bucket, so the region ends up as the unit's rows bucket by bucket.  Escapes that keep every
-// input correct: a flush that would finish less than a quarter of the keys is postponed while the table has room;
-// past `hard_keys` the unfinished keys are left as RAW entries at the top of the region (fixup_kernel).
-__device__ __noinline__ void flush_table(const SimParams& P, const FinalizeArgs& fa, const DepositCtx& c, bool at_end,
-                                         unsigned next, WarpStats& st) {
-    DepositShared& sh = *c.sh;
-    const SmemTable& t = c.t;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// detector/simulator.py:111-113) and appended to the unit's region as one SEGMENT, in table order; emit_kernel puts
+// every segment into (time bucket, pad) order when it reads it.  Segments of successive flushes hold disjoint,
+// ascending ranges of time buckets, so their concatenation is the unit's rows.  The caller flushes at the start of
+// a time bucket whenever it can, so that normally NO key is unfinished and the table starts over empty; otherwise the
+// keys at or above the frontier are parked in global memory while the table is cleared and re-inserted.  Escapes
+// that keep every input correct: a flush that would finish less than a quarter of the keys is postponed while the
+// table has room; past `hard_keys` the unfinished keys are left as RAW entries at the top of the region, and so is
+// everything once a unit has used up its MAX_SEGMENTS segments (fixup_kernel merges and sorts such a unit).
+__device__ __noinline__ void flush_table(const SimParams& P, const FinalizeArgs& fa, bool all_final, unsigned next,
+                                         WarpStats& st) {
+    DepositShared& sh = dep_shared();
+    const DepositCtx& c = dep_ctx();
+    const SmemTable t = dep_table();
+    const int lane = threadIdx.x & 31;
+    const uint4* words4 = reinterpret_cast<const uint4*>(t.word);
     if (threadIdx.x == 0) {
         unsigned fb = 0xFFFFFFFFu;  // everything is final
-        if (!at_end && next < (unsigned)c.end)
+        if (!all_final && next < (unsigned)c.end)
             fb = (unsigned)tb_bin(P, __ldg(c.rec0 + (int64_t)c.perm[next] * REC_WORDS) & 0x1FFFFFFFu);
         sh.frontier = fb;
         sh.nsurv = 0;
         sh.nfinal = 0;
         sh.nsv = 0;
+        sh.nkept = 0;
+        sh.mode = sh.nseg >= (unsigned)MAX_SEGMENTS ? 3u : 0u;
     }
-    for (int i = threadIdx.x; i < FLUSH_BINS; i += DEPOSIT_THREADS) sh.hist[i] = 0;
     __syncthreads();
-    const unsigned fb = sh.frontier, lo_bin = sh.lo_bin;
-    // (1) classify: finished keys per relative time bucket (after the mask), unfinished keys
-    unsigned my_surv = 0, my_final = 0;
-#pragma unroll 4
-    for (int slot = threadIdx.x; slot < SMEM_SLOTS; slot += DEPOSIT_THREADS) {
-        const unsigned w = t.word[slot];
-        if (!w) continue;
-        const unsigned key1 = w & SMEM_KEY_MASK, tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
-        if ((unsigned)tb_bin(P, tb) >= fb) {
-            my_surv += 1;
-            continue;
+    const unsigned fb = sh.frontier;
+    if (fb != 0xFFFFFFFFu) {
+        // (1) a flush inside a time bucket: how many keys are finished, how many are not?
+        unsigned my_surv = 0, my_final = 0;
+        for (int v = threadIdx.x; v < SMEM_SLOTS / 4; v += DEPOSIT_THREADS) {
+            const uint4 w4 = words4[v];
+            const unsigned ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (ws[k]) {
+                    if ((unsigned)tb_bin(P, ((ws[k] & SMEM_KEY_MASK) - 1u) >> 15) >= fb) my_surv += 1;
+                    else my_final += 1;
+                }
         }
-        my_final += 1;
-        if (keeps_row(fa, c.slot_event, tb, pad, c.ctr)) atomicAdd(&sh.hist[rel_bin(P, key1, lo_bin)], 1u);
+        my_surv = __reduce_add_sync(FULL, my_surv);
+        my_final = __reduce_add_sync(FULL, my_final);
+        if (lane == 0) {
+            if (my_surv) atomicAdd(&sh.nsurv, my_surv);
+            if (my_final) atomicAdd(&sh.nfinal, my_final);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            // 0: append the finished keys as a segment, carry the others over; 1: postpone (little is finished yet
+            // and the table has room); 2: append the finished keys, leave the others as raw entries (only a table
+            // that fills up with the keys of ONE time bucket gets here); 3: the unit has no segment left: all raw
+            unsigned mode = 0;
+            const unsigned total = sh.nsurv + sh.nfinal;
+            atomicMax(&c.ctr->max_carried, (unsigned long long)sh.nsurv);
+            if (4u * sh.nfinal < total) mode = total <= (unsigned)c.hard_keys ? 1u : 2u;
+            if (mode != 1u && sh.nseg >= (unsigned)MAX_SEGMENTS) mode = 3u;
+            sh.mode = mode;
+            sh.nfinal = 0;  // (counted again below, for the statistics)
+        }
+        __syncthreads();
     }
-    my_surv = __reduce_add_sync(FULL, my_surv);
-    my_final = __reduce_add_sync(FULL, my_final);
-    if (lane == 0) {
-        if (my_surv) atomicAdd(&sh.nsurv, my_surv);
-        if (my_final) atomicAdd(&sh.nfinal, my_final);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        // 0: write the finished keys, carry the others over; 1: postpone (little is finished yet and the table has
-        // room); 2: write the finished keys, leave the others as raw entries (only a table that fills up with the
-        // keys of ONE time bucket gets here)
-        unsigned mode = 0;
-        const unsigned total = sh.nsurv + sh.nfinal;
-        atomicMax(&c.ctr->max_keys, (unsigned long long)total);
-        atomicMax(&c.ctr->max_carried, (unsigned long long)sh.nsurv);
-        if (!at_end && 4u * sh.nfinal < total) mode = total <= (unsigned)c.hard_keys ? 1u : 2u;
-        sh.mode = mode;
-    }
-    __syncthreads();
     const unsigned mode = sh.mode;
     if (mode == 1u) {
         if (threadIdx.x == 0) {
@@ -1629,60 +1657,63 @@ __device__ __noinline__ void flush_table(const SimParams& P, const FinalizeArgs&
         __syncthreads();
         return;
     }
-    // (2) exclusive scan of the bucket counts (three bins per thread): hist[b] = first position of bucket b
-    {
-        constexpr int PER = (FLUSH_BINS + DEPOSIT_THREADS - 1) / DEPOSIT_THREADS;
-        unsigned local[PER], sum = 0;
+    // (2) the finished keys that survive the mask go to the region in table order (four slots per thread and round,
+    // one shared-memory atomic per warp and round); the slots of the unfinished keys are remembered (or the keys left
+    // as raw entries)
+    const unsigned seg0 = sh.rows;
+    const unsigned room = c.cap - min(c.cap, __ldcg(c.raw_counter) + (mode >= 2u ? sh.nsurv : 0u));  // rows may not reach the raw entries
+    unsigned my_final = 0;
+    for (int v = threadIdx.x; v < SMEM_SLOTS / 4; v += DEPOSIT_THREADS) {
+        const uint4 w4 = words4[v];
+        const unsigned ws[4] = {w4.x, w4.y, w4.z, w4.w};
+        unsigned outmask = 0;
 #pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int b = threadIdx.x * PER + k;
-            local[k] = b < FLUSH_BINS ? sh.hist[b] : 0u;
-            sum += local[k];
+        for (int k = 0; k < 4; ++k) {
+            const unsigned w = ws[k];
+            if (!w) continue;
+            const unsigned key1 = w & SMEM_KEY_MASK, tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
+            const unsigned slot = 4u * (unsigned)v + (unsigned)k;
+            const bool unfinished = (unsigned)tb_bin(P, tb) >= fb;
+            my_final += !unfinished;
+            if (mode == 3u) {
+                if (unfinished || keeps_row(fa, c.slot_event, tb, pad, c.ctr)) raw_entry(w, smem_charge_of(t, slot), st.n_raw, 2);
+            } else if (unfinished) {
+                if (mode == 2u) raw_entry(w, smem_charge_of(t, slot), st.n_raw, 1);
+                else sh.carry[atomicAdd(&sh.nsv, 1u) & (CARRY_SLOTS - 1)] = (uint16_t)slot;  // (more than CARRY_SLOTS: rescan below)
+            } else if (keeps_row(fa, c.slot_event, tb, pad, c.ctr)) {
+                outmask |= 1u << k;
+            }
         }
-        unsigned incl = sum;
+        const unsigned cnt = __popc(outmask);
+        unsigned incl = cnt;
         for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
+            const unsigned x = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += x;
         }
-        if (lane == 31) sh.wsum[warp] = incl;
-        __syncthreads();
-        unsigned run = incl - sum;
-        for (int w = 0; w < warp; ++w) run += sh.wsum[w];
+        const unsigned total = __shfl_sync(FULL, incl, 31);
+        if (total) {  // warp-uniform
+            unsigned at = 0;
+            if (lane == 31) at = atomicAdd(&sh.nkept, total);
+            at = seg0 + __shfl_sync(FULL, at, 31) + incl - cnt;
 #pragma unroll
-        for (int k = 0; k < PER; ++k) {
-            const int b = threadIdx.x * PER + k;
-            if (b < FLUSH_BINS) sh.hist[b] = run;
-            run += local[k];
+            for (int k = 0; k < 4; ++k)
+                if ((outmask >> k) & 1u) {
+                    const unsigned slot = 4u * (unsigned)v + (unsigned)k;
+                    if (at < room) c.region[at] = HashEntry{ws[k] & SMEM_KEY_MASK, ws[k] >> 28, smem_charge_of(t, slot)};
+                    else c.ctr->overflow_hash = 1;  // the host grows the regions and redoes the launch
+                    at += 1;
+                }
         }
-        if (threadIdx.x == DEPOSIT_THREADS - 1) sh.nkept = run;  // rows this flush writes
-        __syncthreads();
     }
-    // (3) the finished keys go to the region, bucket by bucket (inside a bucket in the order the threads arrive:
-    // emit_kernel sorts the pads of a bucket); the slots of the unfinished keys are remembered (or the keys left as
-    // raw entries)
-    const unsigned seg0 = sh.rows, n = sh.nkept;
-    const unsigned n_sv_all = mode == 2u ? 0u : sh.nsurv;
-    const bool fits = seg0 + n + n_sv_all + __ldcg(c.raw_counter) + (mode == 2u ? sh.nsurv : 0u) <= c.cap;
-    if (!fits && threadIdx.x == 0) c.ctr->overflow_hash = 1;  // the host grows the regions and redoes the launch
-#pragma unroll 4
-    for (int slot = threadIdx.x; slot < SMEM_SLOTS && fits; slot += DEPOSIT_THREADS) {
-        const unsigned w = t.word[slot];
-        if (!w) continue;
-        const unsigned key1 = w & SMEM_KEY_MASK, tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
-        if ((unsigned)tb_bin(P, tb) >= fb) {
-            if (mode == 2u) raw_entry(c, w, smem_charge_of(t, slot), st.n_raw, 1);
-            else sh.carry[atomicAdd(&sh.nsv, 1u) & (CARRY_SLOTS - 1)] = (uint16_t)slot;  // (more than CARRY_SLOTS: rescan below)
-            continue;
-        }
-        if (!keeps_row(fa, c.slot_event, tb, pad, c.ctr)) continue;
-        const unsigned pos = atomicAdd(&sh.hist[rel_bin(P, key1, lo_bin)], 1u);
-        c.region[seg0 + pos] = HashEntry{key1, w >> 28, smem_charge_of(t, slot)};
-    }
-    // (4) the unfinished keys wait in global memory (in the region, above the rows just written) while the table is
-    // cleared; the first CARRY_SLOTS of them are found through the slot list, more than that by a rescan
-    HashEntry* parked = c.region + seg0 + n;
-    const unsigned n_sv = fits ? n_sv_all : 0u;
+    my_final = __reduce_add_sync(FULL, my_final);
+    if (lane == 0 && my_final) atomicAdd(&sh.nfinal, my_final);
     __syncthreads();
+    // (3) the unfinished keys wait in global memory (in the region, above the rows just written) while the table is
+    // cleared; the first CARRY_SLOTS of them are found through the slot list, more than that by a rescan
+    const unsigned n = sh.nkept;
+    const unsigned n_sv = (mode == 0u && seg0 + n + sh.nsurv <= room) ? sh.nsurv : 0u;
+    if (mode == 0u && n_sv != sh.nsurv && threadIdx.x == 0) c.ctr->overflow_hash = 1;
+    HashEntry* parked = c.region + seg0 + n;
     if (n_sv > (unsigned)CARRY_SLOTS) {
         if (threadIdx.x == 0) sh.nsv = 0;
         __syncthreads();
@@ -1702,25 +1733,29 @@ __device__ __noinline__ void flush_table(const SimParams& P, const FinalizeArgs&
     }
     __syncthreads();
     {
-        constexpr int TABLE_VEC4 = (2 * SMEM_SLOTS + SMEM_SLOTS / 2) / 4;
         uint4* v = reinterpret_cast<uint4*>(t.word);
-        for (int i = threadIdx.x; i < TABLE_VEC4; i += DEPOSIT_THREADS) v[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < DEPOSIT_TABLE_WORDS / 4; i += DEPOSIT_THREADS) v[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (threadIdx.x == 0) {
-        sh.rows = seg0 + (fits ? n : 0u);
+        if (n > 0u && seg0 + n <= room) {  // one more segment
+            c.segend[sh.nseg] = seg0 + n;
+            sh.nseg += 1;
+            sh.rows = seg0 + n;
+        }
         sh.nkeys = n_sv;
         sh.trigger = min((unsigned)c.hard_keys, n_sv + (unsigned)c.spill_keys);
-        if (fb != 0xFFFFFFFFu) sh.lo_bin = fb;
+        sh.last_pos = min(next, (unsigned)c.end);
         sh.flush = 0;
         atomicAdd(&c.ctr->keys, (unsigned long long)sh.nfinal);
-        if (!at_end) atomicAdd(&c.ctr->flushes, 1ULL);
+        atomicMax(&c.ctr->max_keys, (unsigned long long)(sh.nfinal + sh.nsurv));
+        if (next < (unsigned)c.end) atomicAdd(&c.ctr->flushes, 1ULL);
     }
     __syncthreads();
     for (unsigned i = threadIdx.x; i < n_sv; i += DEPOSIT_THREADS) {
         const HashEntry en = parked[i];
         const unsigned w = en.key1 | (en.rank << 28);
         unsigned slot = smem_home(en.key1);
-        while (atomicCAS(&t.word[slot], 0u, w) != 0u) slot = (slot + 1u) & (unsigned)(SMEM_SLOTS - 1);  // distinct keys
+        while (atomicCAS(&t.word[slot], 0u, w) != 0u) slot = slot + 1u == (unsigned)SMEM_SLOTS ? 0u : slot + 1u;  // distinct keys
         t.lo[slot] = (unsigned)en.charge;
         const unsigned hi = (unsigned)(en.charge >> 32);
         if (hi) atomicAdd(&t.hi2[slot >> 1], hi << ((slot & 1u) * 16u));
@@ -1747,10 +1782,10 @@ __global__ void __launch_bounds__(DEPOSIT_THREADS, 4)
 deposit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, PointBuf pb,
                GroupView chunk, Counters* ctr) {
     const GroupView gv = sub_group(chunk, blockIdx.y);
-    extern __shared__ __align__(16) unsigned s_raw[];
-    __shared__ DepositShared sh;
-    __shared__ DepositCtx c;
     if ((int)blockIdx.x >= pb.n_units[gv.group] || ctr->overflow_points) return;
+    unsigned* s_raw = dep_smem();
+    DepositShared& sh = dep_shared();
+    DepositCtx& c = dep_ctx();
     const int64_t ubase = (int64_t)gv.group * pb.max_units;
     const int unit = pb.unit_order[ubase + blockIdx.x];
     const int e = pb.unit_event[ubase + unit];
@@ -1762,12 +1797,9 @@ deposit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     const uint32_t* perm = pb.perm + base;
     const uint32_t* rec0 = pb.rec + base * REC_WORDS;
     if (threadIdx.x == 0) {
-        c.t.word = s_raw;
-        c.t.lo = s_raw + SMEM_SLOTS;
-        c.t.hi2 = s_raw + 2 * SMEM_SLOTS;
-        c.sh = &sh;
         c.region = gv.tables + ((int64_t)gv.chunk_group * pb.max_units + unit) * gv.hash_cap;
         c.raw_counter = pb.unit_raw + ubase + unit;
+        c.segend = pb.unit_segend + (ubase + unit) * MAX_SEGMENTS;
         c.ctr = ctr;
         c.perm = perm;
         c.rec0 = rec0;
@@ -1779,16 +1811,16 @@ deposit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
         c.hard_keys = gv.hard_keys;
     }
     {
-        constexpr int TABLE_VEC4 = (2 * SMEM_SLOTS + SMEM_SLOTS / 2) / 4;
         uint4* v = reinterpret_cast<uint4*>(s_raw);
-        for (int i = threadIdx.x; i < TABLE_VEC4; i += DEPOSIT_THREADS) v[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = threadIdx.x; i < DEPOSIT_TABLE_WORDS / 4; i += DEPOSIT_THREADS) v[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (threadIdx.x == 0) {
         sh.nkeys = 0;
         sh.flush = 0;
         sh.rows = 0;
         sh.trigger = (unsigned)min(gv.spill_keys, gv.hard_keys);
-        sh.lo_bin = u_count > 0 ? (unsigned)tb_bin(P, __ldg(rec0 + (int64_t)perm[u_first] * REC_WORDS) & 0x1FFFFFFFu) : 0u;
+        sh.nseg = 0;
+        sh.last_pos = (unsigned)u_first;
     }
     // constant mesh weights: the rows differ from lane to lane, so they are read from shared memory (row stride 11
     // doubles: the ten rows start in ten different bank pairs), not through the constant cache
@@ -1808,7 +1840,7 @@ deposit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
     auto drain_all = [&]() {
         while (q_tail != q_head) {
             const unsigned n = min(32u, q_tail - q_head);
-            drain_ring(c, warp, q_head, n, st);
+            drain_ring(warp, q_head, n, st);
             q_head += n;
         }
     };
@@ -1817,19 +1849,19 @@ deposit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
         if (lane == 0 && total) atomicAdd(&sh.nkeys, total);
         st.n_new = 0;
     };
-    // Last position of the pass lattice: a warp whose points are done stands there.
-    const unsigned end_aligned = (unsigned)(u_first + (u_count + POINTS_PER_ITER - 1) / POINTS_PER_ITER * POINTS_PER_ITER);
-
     int p0 = u_first;
     unsigned target = 0;      // > 0: a flush has been called for list position `target`; this warp is catching up
+    bool clean = false;       // ... and `target` is the start of a time bucket: no key will be unfinished there
     bool closing = false;     // the points are done: the last flush is being arranged
     while (true) {
         if (p0 < end) {
-            // ---- this warp's three points of the CTA pass that starts at list position p0
+            // ---- this warp's three points of the CTA pass that starts at list position p0 (a pass before a flush
+            // stops at the flush position; the next one starts there)
+            const int limit = target ? min(end, (int)target) : end;
             const int w0 = p0 + warp * POINTS_PER_WARP;
-            if (w0 < end) {  // warp-uniform
+            if (w0 < limit) {  // warp-uniform
                 const int pp = w0 + sub;
-                const bool have = sub < POINTS_PER_WARP && pp < end;
+                const bool have = sub < POINTS_PER_WARP && pp < limit;
                 const int64_t p = (int64_t)__ldg(perm + (have ? pp : w0));
                 const uint4* rp = reinterpret_cast<const uint4*>(rec0 + p * REC_WORDS);
                 uint4 head = __ldg(rp);
@@ -1900,7 +1932,7 @@ deposit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
                         }
                         q_tail += __popc(m);
                         if (q_tail - q_head >= 32u) {
-                            drain_ring(c, warp, q_head, 32u, st);
+                            drain_ring(warp, q_head, 32u, st);
                             q_head += 32u;
                         }
                     }
@@ -1929,30 +1961,45 @@ deposit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Fina
             __syncthreads();
             unsigned lead = 0, all_done = 1;
             for (int w = 0; w < DEPOSIT_WARPS; ++w) {
-                lead = max(lead, min(sh.next[w], end_aligned));
+                lead = max(lead, min(sh.next[w], (unsigned)end));
                 all_done &= sh.next[w] == 0xFFFFFFFFu;
             }
             const bool wanted = *(volatile unsigned*)&sh.flush != 0u;
             __syncthreads();  // (sh.next may be rewritten only after everybody has read it)
             if (!wanted && !all_done) continue;  // a finished warp waiting for the others: back to the barrier
             if (all_done) {  // every point of the unit is in the table: the last flush(es)
-                flush_table(P, fa, c, true, 0xFFFFFFFFu, st);
+                flush_table(P, fa, true, 0xFFFFFFFFu, st);
                 break;
             }
-            target = lead;  // the warps behind catch up with the leading one first
+            // The warps behind catch up with the leading one first -- and all go on to the start of the next time
+            // bucket if that is near: a flush there leaves no key unfinished and the table starts over empty.
+            target = lead;
+            clean = lead >= (unsigned)end;
+            if (!clean) {
+                const unsigned boundary = __ldg(pb.tbend + base + lead);  // (<= end: a unit ends at a bucket boundary)
+                const unsigned keys_now = *(volatile unsigned*)&sh.nkeys;  // (nobody inserts between the two barriers)
+                const unsigned per_point = keys_now / max(lead - sh.last_pos, 1u) + 1u;  // keys a point has brought so far
+                if (keys_now + (boundary - lead) * per_point <= (unsigned)gv.hard_keys) {
+                    target = boundary;
+                    clean = true;
+                }
+            }
         }
         if ((unsigned)p0 >= target || p0 >= end) {
             drain_all();
             publish_new_keys();
             __syncthreads();
-            flush_table(P, fa, c, false, target, st);
+            flush_table(P, fa, clean, target, st);
+            p0 = (int)target;  // every warp goes on from the flush position
             target = 0u;
+            closing = false;
         }
     }
     if (threadIdx.x == 0) {
         const unsigned rows = sh.rows;
         const unsigned raw = atomicAdd(pb.unit_raw + ubase + unit, 0u);
         pb.unit_kept[ubase + unit] = rows;
+        pb.unit_nseg[ubase + unit] = sh.nseg;
         if (rows) atomicAdd(&fa.kept[slot_event], rows);
         if (rows + raw > (unsigned)gv.hash_cap) ctr->overflow_hash = 1;
         if (raw) {  // fixup_kernel merges the raw entries into the rows
@@ -2076,6 +2123,7 @@ fixup_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finali
         for (unsigned i = threadIdx.x; i < n_final; i += blockDim.x) region[i] = out[i];
         if (threadIdx.x == 0) {
             pb.unit_kept[ubase + unit] = n_final;
+            pb.unit_nseg[ubase + unit] = 0u;  // emit_kernel: these rows are in final order
             if (n_final >= n_rows) atomicAdd(&fa.kept[slot_event], n_final - n_rows);
             else atomicSub(&fa.kept[slot_event], n_rows - n_final);
         }
@@ -2114,81 +2162,226 @@ scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr, unsigned long long* cs
     }
 }
 
-// One CTA per work unit.  Its region holds the unit's rows grouped by ascending time bucket (deposit_kernel); the units
-// of an event are consecutive and ascending in time bucket, so the event's rows are their concatenation.  The pads of
-// one time bucket are put in ascending order here: a row's place is the start of its bucket plus the number of smaller
-// pads in the bucket, counted from a shared-memory copy of the entries (a bucket holds a few dozen pads; the kernel
-// is bound by the rows it writes, the counting is free).  Writes [pad, tb + u, electrons] rows and labels
-// (detector/simulator.py:19-49, 104-115) and / or the typed columns.
-constexpr int EMIT_TILE = 2048;  // entries per shared-memory tile (32 KB)
+// One CTA per work unit.  Its region holds the unit's rows as SEGMENTS (one per flush of the deposit kernel) that cover
+// disjoint, ascending ranges of time buckets; the units of an event are consecutive and ascending in time bucket, so
+// the event's rows are the concatenation of all those segments once every segment is in (time bucket, pad) order.
+// Per segment: counting sort on the time bucket in shared memory (histogram, scan, scatter of the entry indices),
+// then one warp per bucket orders its pads through a bitmap over the pad ids: all keys of a bucket share the time
+// bucket, so the place of a pad is the bucket's start plus the number of smaller pads present (prefix population
+// count).  Linear in the number of rows, whatever the shape of the event.  Then [pad, tb + u, electrons] rows and labels
+// (detector/simulator.py:19-49, 104-115) and / or the typed columns are written at their final places.
+constexpr int EMIT_SEG_CAP = SMEM_SLOTS;   // a segment is one table: at most SMEM_SLOTS entries
+constexpr int EMIT_BINS = 1024;            // time buckets of a segment relative to its first one; the last bin collects
+                                           // everything above (ordered by full key there)
+constexpr int EMIT_WARPS = FINALIZE_THREADS / 32;
+constexpr int BITMAP_PADS = 10240;         // pad ids the bitmap covers (the AT-TPC pad plane); larger pad maps: by counting
+constexpr int BITMAP_WORDS = BITMAP_PADS / 32;
+static_assert(BITMAP_WORDS % 32 == 0 && BITMAP_WORDS / 32 == 10, "lane l owns bitmap words 10 l .. 10 l + 9");
+
+struct EmitShared {
+    unsigned key[EMIT_SEG_CAP];            // key word of every entry of the segment; later its place in the segment
+    uint16_t list[EMIT_SEG_CAP];           // entry indices bucket by bucket
+    unsigned hist[EMIT_BINS];              // entries per bucket -> bucket ends
+    unsigned bitmap[EMIT_WARPS][BITMAP_WORDS];
+    uint16_t prefix[EMIT_WARPS][BITMAP_WORDS];  // pads present below each bitmap word
+    unsigned wsum[EMIT_WARPS];
+    unsigned lo_tb;
+};
 
 __global__ void __launch_bounds__(FINALIZE_THREADS)
 emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, PointBuf pb, GroupView chunk,
             Counters* ctr) {
-    extern __shared__ uint4 s_ent[];
+    extern __shared__ __align__(16) unsigned char s_emit_raw[];
+    EmitShared& sh = *reinterpret_cast<EmitShared*>(s_emit_raw);
     const GroupView gv = sub_group(chunk, blockIdx.y);
     if ((int)blockIdx.x >= pb.n_units[gv.group] || (ctr->overflow_points | ctr->overflow_hash)) return;
     const int64_t ubase = (int64_t)gv.group * pb.max_units;
     const int unit = blockIdx.x;
     const int slot_event = gv.first_slot + pb.unit_event[ubase + unit];
     const int n = (int)pb.unit_kept[ubase + unit];
+    if (n == 0) return;
     int64_t off = fa.offsets[slot_event];
     for (int u = pb.event_unit0[slot_event]; u < unit; ++u) off += pb.unit_kept[ubase + u];
     if (off + n > fa.out_cap) return;
     const uint4* region = reinterpret_cast<const uint4*>(gv.tables + ((int64_t)gv.chunk_group * pb.max_units + unit) * gv.hash_cap);
-    for (int a = 0; a < n; a += EMIT_TILE) {
-        const int m = min(EMIT_TILE, n - a);
-        __syncthreads();
-        for (int i = threadIdx.x; i < m; i += blockDim.x) s_ent[i] = __ldcs(region + a + i);  // read once: not kept in L2
-        __syncthreads();
-        for (int li = threadIdx.x; li < m; li += blockDim.x) {
-            const uint4 raw = s_ent[li];
-            const unsigned key1 = raw.x, rank = raw.y, bucket = (key1 - 1u) >> 15;
-            // the other entries of the same time bucket: to the left and to the right (beyond the tile: from global memory)
-            int first = a + li, smaller = 0;
-            for (int j = a + li - 1; j >= 0; --j) {
-                const unsigned kj = j >= a ? s_ent[j - a].x : __ldg(&region[j].x);
-                if ((kj - 1u) >> 15 != bucket) break;
-                smaller += kj < key1;
-                first = j;
-            }
-            for (int j = a + li + 1; j < n; ++j) {
-                const unsigned kj = j < a + m ? s_ent[j - a].x : __ldg(&region[j].x);
-                if ((kj - 1u) >> 15 != bucket) break;
-                smaller += kj < key1;
-            }
-            const int64_t row_at = off + first + smaller;
-            const unsigned long long charge = ((unsigned long long)raw.w << 32) | raw.z;
-            const unsigned tb = bucket, pad = (key1 - 1u) & 0x7FFFu;
-            const unsigned key = szudzik_pair(tb, pad);
-            const double u = wiggle_of(fa, slot_event, key, ctr);
-            const int64_t label = fa.label_of_event_rank
-                                      ? (int64_t)fa.label_of_event_rank[(int64_t)slot_event * fa.n_tracks_per_event + rank]
-                                      : (int64_t)fa.label_of_rank[rank];
-            if (fa.cloud) {
-                double* row = fa.cloud + row_at * 3;
-                row[0] = (double)pad;
-                row[1] = (double)tb + u;
-                row[2] = (double)(long long)charge;
-                fa.labels[row_at] = label;
-            }
-            if (fa.col_pad) {
-                fa.col_pad[row_at] = (int16_t)pad;
-                fa.col_tb_q16[row_at] = (tb << 16) | (uint32_t)(u * 65536.0);
-                fa.col_label[row_at] = (int8_t)label;
-                if (fa.col_electrons) fa.col_electrons[row_at] = (long long)charge;
-                if (fa.col_electrons32) {
-                    fa.col_electrons32[row_at] = (uint32_t)charge;
-                    if (charge >> 32) {
-                        const unsigned long long k = atomicAdd(fa.big_count, 1ULL);
-                        if ((int64_t)k < fa.big_cap) {
-                            fa.big_rows[k] = row_at;
-                            fa.big_electrons[k] = (long long)charge;
-                        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_seg = (int)pb.unit_nseg[ubase + unit];
+    const unsigned* segend = pb.unit_segend + (ubase + unit) * MAX_SEGMENTS;
+    const bool use_bitmap = P.n_pads <= BITMAP_PADS;
+
+    auto write_row = [&](const uint4 raw, int64_t row_at) {
+        const unsigned key1 = raw.x, rank = raw.y;
+        const unsigned long long charge = ((unsigned long long)raw.w << 32) | raw.z;
+        const unsigned tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
+        const double u = wiggle_of(fa, slot_event, szudzik_pair(tb, pad), ctr);
+        const int64_t label = fa.label_of_event_rank
+                                  ? (int64_t)fa.label_of_event_rank[(int64_t)slot_event * fa.n_tracks_per_event + rank]
+                                  : (int64_t)fa.label_of_rank[rank];
+        if (fa.cloud) {
+            double* row = fa.cloud + row_at * 3;
+            row[0] = (double)pad;
+            row[1] = (double)tb + u;
+            row[2] = (double)(long long)charge;
+            fa.labels[row_at] = label;
+        }
+        if (fa.col_pad) {
+            fa.col_pad[row_at] = (int16_t)pad;
+            fa.col_tb_q16[row_at] = (tb << 16) | (uint32_t)(u * 65536.0);
+            fa.col_label[row_at] = (int8_t)label;
+            if (fa.col_electrons) fa.col_electrons[row_at] = (long long)charge;
+            if (fa.col_electrons32) {
+                fa.col_electrons32[row_at] = (uint32_t)charge;
+                if (charge >> 32) {
+                    const unsigned long long k = atomicAdd(fa.big_count, 1ULL);
+                    if ((int64_t)k < fa.big_cap) {
+                        fa.big_rows[k] = row_at;
+                        fa.big_electrons[k] = (long long)charge;
                     }
                 }
             }
         }
+    };
+
+    if (n_seg == 0) {  // fixup_kernel left the rows in final order
+        for (int i = threadIdx.x; i < n; i += FINALIZE_THREADS) write_row(__ldcs(region + i), off + i);
+        return;
+    }
+    for (int sgm = 0; sgm < n_seg; ++sgm) {
+        const int s0 = sgm ? (int)segend[sgm - 1] : 0;
+        const int m = min((int)segend[sgm], n) - s0;  // (<= EMIT_SEG_CAP: one table)
+        if (m <= 0) continue;
+        if (m > EMIT_SEG_CAP) {  // cannot happen (a segment is one table); never write past the shared arrays
+            if (threadIdx.x == 0) ctr->overflow_out = 1;
+            return;
+        }
+        __syncthreads();  // the previous segment is done with the shared arrays
+        // (1) keys of the segment, its first time bucket
+        unsigned lo = 0xFFFFFFFFu;
+        for (int i = threadIdx.x; i < m; i += FINALIZE_THREADS) {
+            const unsigned key1 = __ldg(&region[s0 + i].x);
+            sh.key[i] = key1;
+            lo = min(lo, (key1 - 1u) >> 15);
+        }
+        for (int i = threadIdx.x; i < EMIT_BINS; i += FINALIZE_THREADS) sh.hist[i] = 0u;
+        lo = __reduce_min_sync(FULL, lo);
+        if (lane == 0) sh.wsum[warp] = lo;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned v = 0xFFFFFFFFu;
+            for (int w = 0; w < EMIT_WARPS; ++w) v = min(v, sh.wsum[w]);
+            sh.lo_tb = v;
+        }
+        __syncthreads();
+        const unsigned lo_tb = sh.lo_tb;
+        // (2) entries per time bucket, exclusive scan (four bins per thread)
+        for (int i = threadIdx.x; i < m; i += FINALIZE_THREADS)
+            atomicAdd(&sh.hist[min(((sh.key[i] - 1u) >> 15) - lo_tb, (unsigned)EMIT_BINS - 1u)], 1u);
+        __syncthreads();
+        {
+            constexpr int PER = EMIT_BINS / FINALIZE_THREADS;
+            unsigned local[PER], sum = 0;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                local[k] = sh.hist[threadIdx.x * PER + k];
+                sum += local[k];
+            }
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) sh.wsum[warp] = incl;
+            __syncthreads();
+            unsigned run = incl - sum;
+            for (int w = 0; w < warp; ++w) run += sh.wsum[w];
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                sh.hist[threadIdx.x * PER + k] = run;
+                run += local[k];
+            }
+            __syncthreads();
+        }
+        // (3) entry indices bucket by bucket (hist[b] becomes the END of bucket b)
+        for (int i = threadIdx.x; i < m; i += FINALIZE_THREADS)
+            sh.list[atomicAdd(&sh.hist[min(((sh.key[i] - 1u) >> 15) - lo_tb, (unsigned)EMIT_BINS - 1u)], 1u)] = (uint16_t)i;
+        __syncthreads();
+        // (4) one warp per bucket: the place of every entry = bucket start + pads of the bucket below its own
+        {
+            unsigned* bm = sh.bitmap[warp];
+            uint16_t* pre = sh.prefix[warp];
+            constexpr int WPL = BITMAP_WORDS / 32;  // bitmap words per lane: lane l holds words 10 l .. 10 l + 9
+            for (int k = 0; k < WPL; ++k) bm[lane * WPL + k] = 0u;
+            __syncwarp();
+            // bucket b belongs to warp b % EMIT_WARPS (a segment covers a short run of consecutive time buckets: they
+            // must not all fall to the same warp); 32 of a warp's buckets at a time: skip the empty ones
+            for (unsigned b0 = 0; b0 < (unsigned)EMIT_BINS; b0 += EMIT_WARPS * 32) {
+                const unsigned mb = b0 + (unsigned)lane * EMIT_WARPS + (unsigned)warp;
+                const unsigned mlo = mb ? sh.hist[mb - 1] : 0u, mhi = sh.hist[mb];
+                unsigned todo = __ballot_sync(FULL, mhi > mlo);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1u;
+                    const unsigned blo = __shfl_sync(FULL, mlo, src), bhi = __shfl_sync(FULL, mhi, src);
+                    const bool mixed = b0 + (unsigned)src * EMIT_WARPS + (unsigned)warp == (unsigned)EMIT_BINS - 1u;  // the last bin may hold several time buckets
+                    if (bhi - blo <= 32u) {  // one key per lane: count the smaller ones as every lane shows its own
+                        const unsigned cnt = bhi - blo;
+                        const bool have = (unsigned)lane < cnt;
+                        const unsigned me = have ? sh.list[blo + lane] : 0u;
+                        const unsigned key1 = have ? sh.key[me] : 0xFFFFFFFFu;
+                        unsigned below = 0;
+                        for (unsigned j = 0; j < cnt; ++j) below += __shfl_sync(FULL, key1, j) < key1;
+                        __syncwarp();
+                        if (have) sh.key[me] = blo + below;
+                    } else if (!use_bitmap || mixed) {  // by counting, on the full key
+                        for (unsigned i = blo + lane; i < bhi; i += 32) {
+                            const unsigned me = sh.list[i], key1 = __ldg(&region[s0 + me].x);
+                            unsigned below = 0;
+                            for (unsigned j = blo; j < bhi; ++j) below += __ldg(&region[s0 + sh.list[j]].x) < key1;
+                            sh.key[me] = blo + below;  // (sh.key of this bucket is not read by anybody else any more)
+                        }
+                    } else {
+                        for (unsigned i = blo + lane; i < bhi; i += 32) {
+                            const unsigned pad = (sh.key[sh.list[i]] - 1u) & 0x7FFFu;
+                            atomicOr(&bm[pad >> 5], 1u << (pad & 31));
+                        }
+                        __syncwarp();
+                        unsigned cnt[WPL], mine = 0;
+#pragma unroll
+                        for (int k = 0; k < WPL; ++k) {
+                            cnt[k] = __popc(bm[lane * WPL + k]);
+                            mine += cnt[k];
+                        }
+                        unsigned incl = mine;
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const unsigned v = __shfl_up_sync(FULL, incl, o);
+                            if (lane >= o) incl += v;
+                        }
+                        unsigned run = incl - mine;
+#pragma unroll
+                        for (int k = 0; k < WPL; ++k) {
+                            pre[lane * WPL + k] = (uint16_t)run;
+                            run += cnt[k];
+                        }
+                        __syncwarp();
+                        for (unsigned i = blo + lane; i < bhi; i += 32) {
+                            const unsigned me = sh.list[i], pad = (sh.key[me] - 1u) & 0x7FFFu, word = pad >> 5;
+                            sh.key[me] = blo + pre[word] + __popc(bm[word] & ((1u << (pad & 31)) - 1u));
+                            // (the keys of this bucket have all been read: the same array now holds the places)
+                        }
+                        __syncwarp();
+                        for (unsigned i = blo + lane; i < bhi; i += 32) {  // leave the bitmap empty for the next bucket
+                            const unsigned me = sh.list[i];
+                            const unsigned pad = (__ldg(&region[s0 + me].x) - 1u) & 0x7FFFu;
+                            bm[pad >> 5] = 0u;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // (5) the rows, each at its place
+        for (int i = threadIdx.x; i < m; i += FINALIZE_THREADS) write_row(__ldcs(region + s0 + i), off + s0 + sh.key[i]);
     }
 }
 

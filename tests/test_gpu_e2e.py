@@ -95,8 +95,10 @@ def test_work_splitting_is_invisible(dist, name, n):
         split = simulate_batch(m, v, zs, as_, cfg, 9, idx, **tuning)
         assert np.array_equal(base.offsets, split.offsets), tuning
         assert np.array_equal(base.cloud, split.cloud) and np.array_equal(base.labels, split.labels), tuning
-        if "table_spill_keys" in tuning:
+        if tuning == dict(table_spill_keys=150):
             assert split.stats["n_table_flushes"] > n  # the stress really went through many flushes per unit
+        elif "table_spill_keys" in tuning:
+            assert split.stats["n_table_flushes"] > 0
         if "table_max_probe" in tuning:
             assert split.stats["n_dirty_units"] > 0 and split.stats["n_raw_entries"] > 0
 
