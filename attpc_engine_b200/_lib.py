@@ -24,6 +24,7 @@ SKIP_CLOUD_COPY = 1 << 5
 COLUMNS = 1 << 6
 EXACT_MESH = 1 << 7
 COLUMNS32 = 1 << 8
+SPYRAL_COLUMNS = 1 << 9
 
 
 class AttpcConfig(C.Structure):
@@ -52,8 +53,6 @@ class AttpcConfig(C.Structure):
         ("copy_events_per_launch", C.c_int32),
         ("unit_points", C.c_int32),
         ("table_spill_keys", C.c_int32),
-        ("table_hard_keys", C.c_int32),
-        ("table_max_probe", C.c_int32),
     ]
 
 
@@ -110,7 +109,7 @@ class AttpcResult(C.Structure):
         ("n_group_launches", C.c_int32),
         ("n_hash_probes", C.c_int64),
         ("hash_capacity", C.c_int32),
-        ("n_dirty_units", C.c_int32),
+        ("reserved1", C.c_int32),
         ("n_table_flushes", C.c_int64),
         ("col_pad", C.POINTER(C.c_int16)),
         ("col_tb_q16", C.POINTER(C.c_uint32)),
@@ -125,7 +124,11 @@ class AttpcResult(C.Structure):
         ("big_electrons", C.POINTER(C.c_int64)),
         ("ms_order", C.c_float),
         ("reserved2", C.c_float),
-        ("n_raw_entries", C.c_int64),
+        ("row_col_pad", C.POINTER(C.c_int16)),
+        ("row_col_tb_q16", C.POINTER(C.c_uint32)),
+        ("row_col_e_lo", C.POINTER(C.c_uint32)),
+        ("row_col_e_hi", C.POINTER(C.c_uint16)),
+        ("row_col_label", C.POINTER(C.c_int8)),
     ]
 
 

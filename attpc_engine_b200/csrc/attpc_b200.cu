@@ -101,11 +101,8 @@ struct AttpcSim {
     int32_t copy_launch_events = 2048;
     int32_t group_events = 2048;
     int32_t chunk_groups = 16;  // groups per kernel launch when the rows stay on the device
-    int32_t unit_points = UNIT_POINTS;     // test knobs (AttpcConfig.unit_points / table_spill_keys / ...)
+    int32_t unit_points = UNIT_POINTS;     // test knobs (AttpcConfig.unit_points / table_spill_keys)
     int32_t spill_keys = SMEM_SPILL_DEFAULT;
-    int32_t hard_keys = SMEM_HARD_DEFAULT;
-    int32_t max_probe = MAX_PROBE_DEFAULT;
-    int32_t fixup_ctas = 64;               // persistent CTAs (and scratch slabs) of fixup_kernel
     int64_t big_cap = ATTPC_BIG_CAP;             // exceptions accepted before a call returns the int64 column (<= ATTPC_BIG_CAP)
     int32_t hash_cap = 16384;
     int64_t group_point_cap = 0;
@@ -136,14 +133,12 @@ struct AttpcSim {
     PinnedArray<unsigned long long> chunk_totals;  // running CSR total after each chunk of groups (mapped)
     DevArray<double> geom;
     DevArray<uint32_t> rec;
-    DevArray<uint32_t> perm;
-    DevArray<int32_t> unit_event, unit_first, unit_count, unit_order, n_units, event_unit0, event_nunits;
-    DevArray<unsigned> pstart, unit_kept, unit_raw, unit_nseg, unit_segend, dirty;
-    DevArray<uint32_t> tbend;
+    DevArray<int32_t> unit_event, unit_first, unit_count, unit_order, n_units;
+    DevArray<unsigned> pstart, n_entries, mode;
     int32_t ranks = 1;
     int32_t max_units = 0;
-    DevArray<HashEntry> hash, fix_rows;
-    DevArray<uint64_t> fix_items;
+    DevArray<HashEntry> hash;
+    DevArray<uint64_t> sort_items;
     DevArray<unsigned> kept;
     DevArray<double> in_momenta, in_vertices;
 
@@ -165,6 +160,15 @@ struct AttpcSim {
     DevArray<unsigned> row_kept;
     DevArray<uint64_t> row_sort_keys;
     DevArray<uint32_t> row_sort_idx;
+    // thresholded, z-ordered Spyral rows as typed columns (ATTPC_SPYRAL_COLUMNS)
+    DevArray<int16_t> rcol_pad_dev;
+    DevArray<uint32_t> rcol_tbq_dev, rcol_elo_dev;
+    DevArray<uint16_t> rcol_ehi_dev;
+    DevArray<int8_t> rcol_label_dev;
+    PinnedArray<int16_t> rcol_pad_host;
+    PinnedArray<uint32_t> rcol_tbq_host, rcol_elo_host;
+    PinnedArray<uint16_t> rcol_ehi_host;
+    PinnedArray<int8_t> rcol_label_host;
     PinnedArray<int64_t> offsets_host, labels_host, row_offsets_host, row_labels_host;
     PinnedArray<double> cloud_host, rows_host;
 
@@ -239,32 +243,23 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     }
     CU(sim->geom.reserve(pts * GEOM_DOUBLES));
     CU(sim->rec.reserve(pts * REC_WORDS));
-    CU(sim->perm.reserve(pts));
-    CU(sim->tbend.reserve(pts));
-    // a unit is a time-bucket range of one event: at most one per event plus one per unit_points points
     sim->max_units = (int32_t)(sim->group_events + sim->group_point_cap / sim->unit_points + 1);
     CU(sim->unit_event.reserve(n_groups * sim->max_units));
     CU(sim->unit_first.reserve(n_groups * sim->max_units));
     CU(sim->unit_count.reserve(n_groups * sim->max_units));
     CU(sim->unit_order.reserve(n_groups * sim->max_units));
-    CU(sim->unit_kept.reserve(n_groups * sim->max_units));
-    CU(sim->unit_raw.reserve(n_groups * sim->max_units));
-    CU(sim->unit_nseg.reserve(n_groups * sim->max_units));
-    CU(sim->unit_segend.reserve(n_groups * sim->max_units * MAX_SEGMENTS));
-    CU(sim->dirty.reserve(n_groups * sim->max_units + 2));
     CU(sim->n_units.reserve(n_groups));
-    CU(sim->event_unit0.reserve(launch_events));
-    CU(sim->event_nunits.reserve(launch_events));
     CU(sim->pstart.reserve(launch_events * ranks));
-    // unit regions for one chunk of groups (run_groups) and the scratch slabs of fixup_kernel
+    CU(sim->n_entries.reserve(launch_events));
+    CU(sim->mode.reserve(launch_events));
+    // tables and sort scratch for one chunk of groups (run_groups)
     const int64_t copy_groups = (sim->copy_launch_events + sim->group_events - 1) / sim->group_events;
     const int64_t table_groups = std::min<int64_t>(n_groups, std::max<int64_t>(sim->chunk_groups, copy_groups));
-    CU(sim->hash.reserve(table_groups * sim->max_units * sim->hash_cap));
-    CU(sim->fix_rows.reserve((int64_t)sim->fixup_ctas * sim->hash_cap));
-    CU(sim->fix_items.reserve((int64_t)sim->fixup_ctas * sim->hash_cap * 2));
-    CU(sim->csr_total.reserve(2));
-    CU(sim->csr_host.reserve(2));
-    CU(sim->chunk_totals.reserve(n_groups + 1));
+    CU(sim->hash.reserve(table_groups * sim->group_events * sim->hash_cap));
+    CU(sim->sort_items.reserve(table_groups * sim->group_events * sim->hash_cap * 2));
+    CU(sim->csr_total.reserve(3));  // cloud rows, electron counts >= 2^32, Spyral rows
+    CU(sim->csr_host.reserve(3));
+    CU(sim->chunk_totals.reserve(2 * (n_groups + 1)));
     return ATTPC_OK;
 }
 
@@ -304,16 +299,6 @@ PointBuf point_buf(AttpcSim* sim, int which) {
     pb.unit_first = sim->unit_first.p;
     pb.unit_count = sim->unit_count.p;
     pb.unit_order = sim->unit_order.p;
-    pb.unit_kept = sim->unit_kept.p;
-    pb.unit_raw = sim->unit_raw.p;
-    pb.perm = sim->perm.p;
-    pb.tbend = sim->tbend.p;
-    pb.unit_nseg = sim->unit_nseg.p;
-    pb.unit_segend = sim->unit_segend.p;
-    pb.event_unit0 = sim->event_unit0.p;
-    pb.event_nunits = sim->event_nunits.p;
-    pb.dirty = sim->dirty.p;
-    pb.dirty_cap = (int32_t)std::min<int64_t>(sim->dirty.n - 2, INT32_MAX);
     pb.n_units = sim->n_units.p;
     pb.max_units = sim->max_units;
     pb.unit_points = sim->unit_points;
@@ -350,6 +335,12 @@ int launch_tracks(AttpcSim* sim, const TrackBatch& tb, int64_t n_tracks, int whi
     return ATTPC_OK;
 }
 
+struct SpyralPass {  // what run_groups needs to add the Spyral passes of a chunk (null: none)
+    bool typed;
+};
+SpyralArgs spyral_args(AttpcSim* sim, int64_t first, int64_t n_events, bool typed, bool keep_all, const Counters* ctr);
+int launch_spyral(AttpcSim* sim, const SpyralArgs& sa);
+
 // deposit + finalize of every group of one launch; the track/replay kernel has already filled the point buffers.
 // One entry per chunk of groups whose rows can be copied to the host as soon as `done` has fired.
 struct ChunkFence {
@@ -362,17 +353,17 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
                std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& ord_marks,
                std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& dep_marks,
                std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& fin_marks, int groups_per_chunk,
-               std::vector<ChunkFence>* fences) {
+               std::vector<ChunkFence>* fences, const SpyralPass* spyral, int64_t launch_first_event) {
     PointBuf pb = point_buf(sim, which);
     Counters* ctr = sim->slot[which].counters.p;
     const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
-    const size_t fix_smem = (size_t)FIXUP_SMEM_ITEMS * sizeof(uint64_t);
-    const size_t emit_smem = sizeof(EmitShared);
-    CU(cudaFuncSetAttribute(emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem));
+    fa.sort_items = sim->sort_items.p;
+    const size_t sort_smem = (size_t)SORT_SMEM_ITEMS * sizeof(uint64_t);
+    CU(cudaFuncSetAttribute(collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
     CU(cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEPOSIT_SMEM_BYTES));
     // Groups are processed in chunks: every kernel is launched once per chunk with one grid row per group, so the
     // ramp-up and tail of a launch are paid once per chunk.  When rows go to the host a chunk is what is copied while
-    // the next chunk computes; otherwise it is as many groups as the unit regions are sized for.
+    // the next chunk computes; otherwise it is as many groups as the tables are sized for.
     const int64_t gpc = std::max<int64_t>(1, fences ? groups_per_chunk : sim->chunk_groups);
     for (int64_t g0 = 0; g0 < n_groups; g0 += gpc) {
         const int64_t ng = std::min<int64_t>(gpc, n_groups - g0);
@@ -382,41 +373,38 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         gv.group = (int32_t)g0;
         gv.hash_cap = sim->hash_cap;
         gv.tables = sim->hash.p;
+        gv.n_entries = sim->n_entries.p;
+        gv.mode = sim->mode.p;
         gv.exact_mesh = (fa.flags & ATTPC_EXACT_MESH) ? 1 : 0;
         gv.group_events = sim->group_events;
-        gv.chunk_group = 0;
+        gv.chunk_e0 = 0;
         gv.spill_keys = sim->spill_keys;
-        gv.hard_keys = sim->hard_keys;
-        gv.max_probe = sim->max_probe;
         const dim3 per_event((unsigned)std::min<int64_t>(sim->group_events, gv.n_events), (unsigned)ng);
-        const dim3 per_unit((unsigned)sim->max_units, (unsigned)ng);
         cudaEvent_t d0 = sim->mark();
-        CU(cudaMemsetAsync(sim->n_units.p + g0, 0, (size_t)ng * sizeof(int32_t), sim->stream));
-        CU(cudaMemsetAsync(sim->unit_raw.p + g0 * sim->max_units, 0, (size_t)ng * sim->max_units * sizeof(unsigned),
-                           sim->stream));
-        CU(cudaMemsetAsync(sim->dirty.p, 0, 2 * sizeof(unsigned), sim->stream));
-        CU(cudaMemsetAsync(fa.kept + gv.first_slot, 0, (size_t)gv.n_events * sizeof(unsigned), sim->stream));
         point_scan_kernel<<<(unsigned)ng, 1024, 0, sim->stream>>>(pb, gv, ctr);
         point_order_kernel<<<dim3((unsigned)std::max<int64_t>(1, sim->sm_count * 4 / ng), (unsigned)ng), 256, 0,
                              sim->stream>>>(sim->P, pb, gv, ctr);
-        event_sort_kernel<<<per_event, SORT_THREADS, 0, sim->stream>>>(sim->P, pb, gv, ctr);
-        unit_order_kernel<<<(unsigned)ng, 1024, 0, sim->stream>>>(pb, gv, ctr);
+        CU(cudaMemsetAsync(sim->n_entries.p + gv.first_slot, 0, (size_t)gv.n_events * sizeof(unsigned), sim->stream));
         cudaEvent_t k0 = sim->mark();
-        deposit_kernel<<<per_unit, DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES, sim->stream>>>(sim->P, fa, pb, gv, ctr);
+        deposit_kernel<<<dim3((unsigned)sim->max_units, (unsigned)ng), DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES,
+                         sim->stream>>>(sim->P, pb, gv, ctr);
         cudaEvent_t d1 = sim->mark();
-        FixupArgs fx{sim->fix_items.p, sim->fix_rows.p};
-        fixup_kernel<<<(unsigned)sim->fixup_ctas, FINALIZE_THREADS, fix_smem, sim->stream>>>(sim->P, fa, pb, gv, fx, ctr);
+        collect_kernel<<<per_event, FINALIZE_THREADS, sort_smem, sim->stream>>>(sim->P, fa, gv, ctr);
         scan_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, ctr, sim->csr_total.p);
-        emit_kernel<<<per_unit, FINALIZE_THREADS, emit_smem, sim->stream>>>(sim->P, fa, pb, gv, ctr);
+        emit_kernel<<<per_event, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
+        sim->launches += 6;
+        if (spyral) {  // electronics response, ADC threshold, z order of the chunk's events (detector/writer.py:61-112, 232-238)
+            int rc = launch_spyral(sim, spyral_args(sim, launch_first_event + gv.first_slot, gv.n_events, spyral->typed, false, ctr));
+            if (rc) return rc;
+        }
         cudaEvent_t f1 = sim->mark();
-        sim->launches += 8;
         ord_marks.push_back({d0, k0});
         dep_marks.push_back({k0, d1});
         fin_marks.push_back({d1, f1});
         if (fences) {
             const int slot = (int)fences->size();
-            if (slot < (int)sim->chunk_totals.n) {
-                publish_total_kernel<<<1, 1, 0, sim->stream>>>(sim->csr_total.p, sim->chunk_totals.p + slot);
+            if (2 * slot + 1 < (int)sim->chunk_totals.n) {
+                publish_total_kernel<<<1, 1, 0, sim->stream>>>(sim->csr_total.p, sim->chunk_totals.p + 2 * slot);
                 sim->launches += 1;
                 fences->push_back({sim->fence(sim->stream), gv.first_slot + (int64_t)gv.n_events, slot});
             }
@@ -435,19 +423,39 @@ float sum_ms(const std::vector<std::pair<cudaEvent_t, cudaEvent_t>>& marks) {
     return total;
 }
 
-int run_spyral(AttpcSim* sim, int64_t n_events, int64_t n_points, AttpcResult* res, bool copy_host,
-               bool keep_all = false) {
+// Buffers of the Spyral passes for clouds of up to n_points rows; `typed`: the typed-column sink as well.
+int ensure_spyral_buffers(AttpcSim* sim, int64_t n_events, int64_t n_points, bool typed, bool f64_rows) {
+    n_points = std::max<int64_t>(1, n_points);
     CU(sim->row_kept.reserve(n_events + 1));
     CU(sim->row_offsets_dev.reserve(n_events + 1));
-    CU(sim->rows_dev.reserve(std::max<int64_t>(1, n_points) * 8));
-    CU(sim->row_labels_dev.reserve(std::max<int64_t>(1, n_points)));
-    CU(sim->row_sort_keys.reserve(std::max<int64_t>(1, n_points) * 2));
-    CU(sim->row_sort_idx.reserve(std::max<int64_t>(1, n_points) * 2));
+    CU(sim->row_sort_keys.reserve(n_points * 2));
+    CU(sim->row_sort_idx.reserve(n_points * 2));
+    if (f64_rows) {
+        CU(sim->rows_dev.reserve(n_points * 8));
+        CU(sim->row_labels_dev.reserve(n_points));
+    }
+    if (typed) {
+        CU(sim->rcol_pad_dev.reserve(n_points));
+        CU(sim->rcol_tbq_dev.reserve(n_points));
+        CU(sim->rcol_elo_dev.reserve(n_points));
+        CU(sim->rcol_ehi_dev.reserve(n_points));
+        CU(sim->rcol_label_dev.reserve(n_points));
+    }
+    return ATTPC_OK;
+}
+
+SpyralArgs spyral_args(AttpcSim* sim, int64_t first, int64_t n_events, bool typed, bool keep_all, const Counters* ctr) {
     SpyralArgs sa;
+    memset(&sa, 0, sizeof sa);
     sa.offsets = sim->offsets_dev.p;
     sa.cloud = sim->cloud_dev.p;
     sa.labels = sim->labels_dev.p;
     sa.n_events = n_events;
+    sa.first = first;
+    sa.total = sim->csr_total.p + 2;
+    sa.scratch_rows = sim->row_sort_keys.n / 2;
+    sa.ctr = ctr;
+    sa.cloud_cap = std::min<int64_t>(sim->labels_dev.n, sa.scratch_rows);
     sa.kept = sim->row_kept.p;
     sa.row_offsets = sim->row_offsets_dev.p;
     sa.rows = sim->rows_dev.p;
@@ -455,17 +463,40 @@ int run_spyral(AttpcSim* sim, int64_t n_events, int64_t n_points, AttpcResult* r
     sa.sort_keys = sim->row_sort_keys.p;
     sa.sort_idx = sim->row_sort_idx.p;
     sa.keep_all = keep_all ? 1 : 0;
+    if (typed) {
+        sa.out_pad = sim->rcol_pad_dev.p;
+        sa.out_tb_q16 = sim->rcol_tbq_dev.p;
+        sa.out_e_lo = sim->rcol_elo_dev.p;
+        sa.out_e_hi = sim->rcol_ehi_dev.p;
+        sa.out_label = sim->rcol_label_dev.p;
+    }
+    return sa;
+}
+
+// detector/response.py:35-57 + detector/writer.py:61-112, 232-238 for events first .. first + n_events - 1 of the cloud
+// in device memory: amplitude / threshold count, running row offsets, rows in z order.
+int launch_spyral(AttpcSim* sim, const SpyralArgs& sa) {
+    if (sa.n_events <= 0) return ATTPC_OK;
     const size_t smem = (size_t)SPYRAL_SMEM_ITEMS * (sizeof(uint64_t) + sizeof(uint32_t));
     CU(cudaFuncSetAttribute(spyral_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (n_events > 0) {
-        spyral_count_kernel<<<(unsigned)n_events, 256, 0, sim->stream>>>(sim->P, sa);
-        spyral_scan_kernel<<<1, 1024, 0, sim->stream>>>(sa);
-        spyral_rows_kernel<<<(unsigned)n_events, 256, smem, sim->stream>>>(sim->P, sa);
-        sim->launches += 3;
-        CU(cudaGetLastError());
-    } else {
-        CU(cudaMemsetAsync(sim->row_offsets_dev.p, 0, sizeof(int64_t), sim->stream));
-    }
+    spyral_count_kernel<<<(unsigned)sa.n_events, 256, 0, sim->stream>>>(sim->P, sa);
+    spyral_scan_kernel<<<1, 1024, 0, sim->stream>>>(sa);
+    spyral_rows_kernel<<<(unsigned)sa.n_events, 256, smem, sim->stream>>>(sim->P, sa);
+    sim->launches += 3;
+    CU(cudaGetLastError());
+    return ATTPC_OK;
+}
+
+// attpc_convert_to_spyral: the whole (host-supplied) cloud in one pass, float64 rows back to the host.
+int run_spyral(AttpcSim* sim, int64_t n_events, int64_t n_points, AttpcResult* res, bool copy_host,
+               bool keep_all = false) {
+    int rc = ensure_spyral_buffers(sim, n_events, n_points, false, true);
+    if (rc) return rc;
+    CU(sim->csr_total.reserve(3));
+    CU(cudaMemsetAsync(sim->csr_total.p + 2, 0, sizeof(unsigned long long), sim->stream));
+    CU(cudaMemsetAsync(sim->row_offsets_dev.p, 0, sizeof(int64_t), sim->stream));
+    rc = launch_spyral(sim, spyral_args(sim, 0, n_events, false, keep_all, nullptr));
+    if (rc) return rc;
     CU(sim->row_offsets_host.reserve(n_events + 1));
     CU(cudaMemcpyAsync(sim->row_offsets_host.p, sim->row_offsets_dev.p, (size_t)(n_events + 1) * sizeof(int64_t),
                        cudaMemcpyDeviceToHost, sim->stream));
@@ -521,8 +552,12 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     const bool copy_host = !(flags & ATTPC_SKIP_HOST_COPY);
     const bool use_columns = copy_host && (flags & ATTPC_COLUMNS);
     const bool use_q32 = use_columns && (flags & ATTPC_COLUMNS32) && !sim->q32_off;
-    const bool copy_cloud =
-        copy_host && !use_columns && !((flags & ATTPC_SKIP_CLOUD_COPY) && (flags & ATTPC_SPYRAL_ROWS));
+    const bool spy_cols = (flags & ATTPC_SPYRAL_COLUMNS) != 0;            // Spyral rows as typed columns
+    const bool spy_rows = (flags & ATTPC_SPYRAL_ROWS) != 0 && !spy_cols;  // ... as float64 [M, 8]
+    const bool spy = spy_cols || spy_rows;
+    const bool copy_cloud = copy_host && !use_columns && !((flags & ATTPC_SKIP_CLOUD_COPY) && spy);
+    // the float64 rows on the device: the product of a device-resident call, the input of the Spyral passes
+    const bool want_cloud = !use_columns || spy;
     if (use_columns) sim->columns = true;
     int64_t out_cap = std::max<int64_t>(sim->labels_dev.n, std::max<int64_t>(n_events * 2048, 1 << 20));
     int rc = ensure_out_buffers(sim, n_events, out_cap, false);
@@ -547,8 +582,31 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         else CU(sim->col_q_host.reserve(sim->labels_dev.n));
         CU(sim->col_label_host.reserve(sim->labels_dev.n));
     }
+    auto reserve_spyral = [&](bool keep) -> int {  // the rows of an event are a subset of its cloud points
+        int r = ensure_spyral_buffers(sim, n_events, sim->labels_dev.n, spy_cols, spy_rows);
+        if (r) return r;
+        if (!copy_host) return ATTPC_OK;
+        CU(sim->row_offsets_host.reserve(n_events + 1, keep));
+        if (spy_rows) {
+            CU(sim->rows_host.reserve(sim->labels_dev.n * 8, keep));
+            CU(sim->row_labels_host.reserve(sim->labels_dev.n, keep));
+        } else {
+            CU(sim->rcol_pad_host.reserve(sim->labels_dev.n, keep));
+            CU(sim->rcol_tbq_host.reserve(sim->labels_dev.n, keep));
+            CU(sim->rcol_elo_host.reserve(sim->labels_dev.n, keep));
+            CU(sim->rcol_ehi_host.reserve(sim->labels_dev.n, keep));
+            CU(sim->rcol_label_host.reserve(sim->labels_dev.n, keep));
+        }
+        return ATTPC_OK;
+    };
+    if (spy) {
+        rc = reserve_spyral(false);
+        if (rc) return rc;
+    }
+    const SpyralPass spyral_pass{spy_cols};
     cudaStream_t G = sim->stream, T = sim->stream_t, C = sim->stream_c;
-    CU(cudaMemsetAsync(sim->csr_total.p, 0, 2 * sizeof(unsigned long long), G));
+    CU(cudaMemsetAsync(sim->csr_total.p, 0, 3 * sizeof(unsigned long long), G));
+    if (spy) CU(cudaMemsetAsync(sim->row_offsets_dev.p, 0, sizeof(int64_t), G));
     CU(cudaMemsetAsync(sim->offsets_dev.p, 0, sizeof(int64_t), G));
     cudaEvent_t t_begin = sim->mark(G);
     CU(cudaStreamWaitEvent(T, t_begin, 0));
@@ -574,6 +632,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     memset(&totals, 0, sizeof totals);
     unsigned long long csr_before = 0;  // rows emitted by the launches completed so far
     unsigned long long big_before = 0;  // ... and electron counts >= 2^32 among them
+    unsigned long long rows_before = 0; // ... and Spyral rows
     int retries = 0;
     int64_t next_track = 0;  // launches whose track kernel is enqueued
 
@@ -645,9 +704,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         fa.flags = flags;
         fa.kept = sim->kept.p + b0;
         fa.offsets = sim->offsets_dev.p + b0;
-        // typed columns only: the float64 rows are neither written nor copied (nothing reads them)
-        const bool want_cloud = !use_columns || (flags & ATTPC_SPYRAL_ROWS);
-        fa.cloud = want_cloud ? sim->cloud_dev.p : nullptr;
+        fa.cloud = want_cloud ? sim->cloud_dev.p : nullptr;  // typed columns only: the float64 rows are not written
         fa.labels = want_cloud ? sim->labels_dev.p : nullptr;
         fa.out_cap = sim->labels_dev.n;
         if (use_columns) {
@@ -677,7 +734,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         const size_t ord_before = ord_marks.size();
         std::vector<ChunkFence> fences;
         rc = run_groups(sim, nb, fa, which, ord_marks, dep_marks, fin_marks, groups_per_chunk,
-                        copy_host ? &fences : nullptr);
+                        copy_host ? &fences : nullptr, spy ? &spyral_pass : nullptr, b0);
         if (rc) return rc;
         publish_kernel<<<1, 1, 0, G>>>(ls.counters.p, sim->csr_total.p, ls.counters_host.p, sim->csr_host.p);
         sim->launches += 1;
@@ -687,15 +744,39 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             if (rc) return rc;
         }
         // rows of finished chunks go home while the later groups (and the next launch's tracks) compute
-        unsigned long long copied = csr_before;
+        unsigned long long copied = csr_before, rows_copied = rows_before;
         int64_t copied_events = 0;  // events of this launch whose offsets are on the host
-        auto copy_rows = [&](unsigned long long upto, int64_t upto_event) -> int {
+        auto copy_rows = [&](unsigned long long upto, unsigned long long rows_upto, int64_t upto_event) -> int {
             cudaEvent_t c0 = sim->mark(C);
             const int64_t first_off = (b0 + copied_events == 0) ? 0 : b0 + copied_events + 1;
             const int64_t end_off = b0 + upto_event + 1;
-            if (end_off > first_off)
+            if (end_off > first_off) {
                 CU(cudaMemcpyAsync(sim->offsets_host.p + first_off, sim->offsets_dev.p + first_off,
                                    (size_t)(end_off - first_off) * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+                if (spy)
+                    CU(cudaMemcpyAsync(sim->row_offsets_host.p + first_off, sim->row_offsets_dev.p + first_off,
+                                       (size_t)(end_off - first_off) * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+            }
+            const int64_t r_new = (int64_t)(rows_upto - rows_copied);
+            if (r_new > 0 && spy_rows) {
+                CU(cudaMemcpyAsync(sim->rows_host.p + rows_copied * 8, sim->rows_dev.p + rows_copied * 8,
+                                   (size_t)r_new * 8 * sizeof(double), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->row_labels_host.p + rows_copied, sim->row_labels_dev.p + rows_copied,
+                                   (size_t)r_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+            }
+            if (r_new > 0 && spy_cols) {
+                CU(cudaMemcpyAsync(sim->rcol_pad_host.p + rows_copied, sim->rcol_pad_dev.p + rows_copied,
+                                   (size_t)r_new * sizeof(int16_t), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->rcol_tbq_host.p + rows_copied, sim->rcol_tbq_dev.p + rows_copied,
+                                   (size_t)r_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->rcol_elo_host.p + rows_copied, sim->rcol_elo_dev.p + rows_copied,
+                                   (size_t)r_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->rcol_ehi_host.p + rows_copied, sim->rcol_ehi_dev.p + rows_copied,
+                                   (size_t)r_new * sizeof(uint16_t), cudaMemcpyDeviceToHost, C));
+                CU(cudaMemcpyAsync(sim->rcol_label_host.p + rows_copied, sim->rcol_label_dev.p + rows_copied,
+                                   (size_t)r_new * sizeof(int8_t), cudaMemcpyDeviceToHost, C));
+            }
+            rows_copied = rows_upto;
             const int64_t n_new = (int64_t)(upto - copied);
             if (n_new > 0 && copy_cloud) {
                 CU(cudaMemcpyAsync(sim->cloud_host.p + copied * 3, sim->cloud_dev.p + copied * 3,
@@ -724,10 +805,10 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         };
         for (const ChunkFence& cf : fences) {
             CU(cudaEventSynchronize(cf.done));
-            const unsigned long long upto = sim->chunk_totals.p[cf.slot];
+            const unsigned long long upto = sim->chunk_totals.p[2 * cf.slot];
             if ((int64_t)upto > sim->labels_dev.n) break;  // output overflow: the launch will be redone below
             CU(cudaStreamWaitEvent(C, cf.done, 0));
-            rc = copy_rows(upto, cf.last_event);
+            rc = copy_rows(upto, sim->chunk_totals.p[2 * cf.slot + 1], cf.last_event);
             if (rc) return rc;
         }
         CU(cudaEventSynchronize(groups_done));
@@ -746,7 +827,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             if (now.overflow_points) {
                 sim->group_point_cap *= 2;
                 for (auto& s2 : sim->slot) s2.release_points();
-                sim->geom.release(); sim->rec.release(); sim->perm.release(); sim->tbend.release(); sim->hash.release();
+                sim->geom.release(); sim->rec.release();
                 sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release();
                 sim->unit_order.release();
             }
@@ -754,8 +835,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 if (sim->hash_cap >= (1 << 20)) return sim->fail(ATTPC_E_CAPACITY, "event needs > 2^20 hash slots");
                 sim->hash_cap *= 2;
                 sim->hash.release();
-                sim->fix_rows.release();
-                sim->fix_items.release();
+                sim->sort_items.release();
             }
             if (now.overflow_out) {
                 out_cap = std::max<int64_t>(sim->labels_dev.n * 2, (int64_t)sim->csr_host.p[0] + (1 << 20));
@@ -772,12 +852,27 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                     else CU(sim->col_q_host.reserve(sim->labels_dev.n, true));
                     CU(sim->col_label_host.reserve(sim->labels_dev.n, true));
                 }
+                if (spy) {  // the row buffers follow the cloud buffers (device side: rows of finished launches are kept)
+                    if (spy_rows) {
+                        CU(sim->rows_dev.reserve(sim->labels_dev.n * 8, true, sim->stream));
+                        CU(sim->row_labels_dev.reserve(sim->labels_dev.n, true, sim->stream));
+                    } else {
+                        CU(sim->rcol_pad_dev.reserve(sim->labels_dev.n, true, sim->stream));
+                        CU(sim->rcol_tbq_dev.reserve(sim->labels_dev.n, true, sim->stream));
+                        CU(sim->rcol_elo_dev.reserve(sim->labels_dev.n, true, sim->stream));
+                        CU(sim->rcol_ehi_dev.reserve(sim->labels_dev.n, true, sim->stream));
+                        CU(sim->rcol_label_dev.reserve(sim->labels_dev.n, true, sim->stream));
+                    }
+                    rc = reserve_spyral(true);
+                    if (rc) return rc;
+                }
             }
             rc = ensure_work_buffers(sim, std::min<int64_t>(n_events, launch_cap), ranks);
             if (rc) return rc;
             sim->csr_host.p[0] = csr_before;  // forget the rows (and the big-count exceptions) of the failed attempt
             sim->csr_host.p[1] = big_before;
-            CU(cudaMemcpyAsync(sim->csr_total.p, sim->csr_host.p, 2 * sizeof(unsigned long long),
+            sim->csr_host.p[2] = rows_before;
+            CU(cudaMemcpyAsync(sim->csr_total.p, sim->csr_host.p, 3 * sizeof(unsigned long long),
                                cudaMemcpyHostToDevice, G));
             CU(cudaStreamSynchronize(G));
             next_track = i;  // redo this launch (and the one that was running ahead)
@@ -790,29 +885,24 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         totals.keys += now.keys;
         totals.probes += now.probes;
         totals.flushes += now.flushes;
-        totals.raw_entries += now.raw_entries;
-        for (int k = 0; k < 3; ++k) totals.raw_by_cause[k] += now.raw_by_cause[k];
-        totals.postponed += now.postponed;
-        totals.max_keys = std::max(totals.max_keys, now.max_keys);
-        totals.max_carried = std::max(totals.max_carried, now.max_carried);
-        totals.dirty_units += now.dirty_units;
         totals.rk_steps += now.rk_steps;
         totals.rk_rejects += now.rk_rejects;
         totals.max_track_passes = std::max(totals.max_track_passes, now.max_track_passes);
-        const unsigned long long csr_after = sim->csr_host.p[0];
+        const unsigned long long csr_after = sim->csr_host.p[0], rows_after = sim->csr_host.p[2];
         big_before = sim->csr_host.p[1];
-        if (copy_host && (copied < csr_after || copied_events < nb)) {  // whatever the chunk copies did not cover
+        if (copy_host && (copied < csr_after || rows_copied < rows_after || copied_events < nb)) {  // whatever the chunk copies did not cover
             CU(cudaStreamWaitEvent(C, groups_done, 0));
-            rc = copy_rows(csr_after, nb);
+            rc = copy_rows(csr_after, rows_after, nb);
             if (rc) return rc;
         }
         csr_before = csr_after;
+        rows_before = rows_after;
         ++i;
     }
     const int64_t n_points = (int64_t)csr_before;
     res->n_points = n_points;
     res->offsets_dev = sim->offsets_dev.p;
-    if (!use_columns || (flags & ATTPC_SPYRAL_ROWS)) {
+    if (want_cloud) {
         res->cloud_dev = sim->cloud_dev.p;
         res->labels_dev = sim->labels_dev.p;
     }
@@ -823,16 +913,10 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     res->n_keys = (int64_t)totals.keys;
     res->n_hash_probes = (int64_t)totals.probes;
     res->n_table_flushes = (int64_t)totals.flushes;
-    res->n_dirty_units = (int32_t)std::min<unsigned long long>(totals.dirty_units, INT32_MAX);
-    res->n_raw_entries = (int64_t)totals.raw_entries;
     res->n_rk_steps = (int64_t)totals.rk_steps;
     res->n_rk_rejects = (int64_t)totals.rk_rejects;
     res->max_track_passes = (int64_t)totals.max_track_passes;
     res->n_retries = retries;
-    if (getenv("ATTPC_DEBUG"))
-        fprintf(stderr, "[attpc] events %lld flushes %llu postponed %llu dirty units %llu raw %llu (no slot %llu, not carried %llu, list full %llu) fullest table %llu most carried %llu\n",
-                (long long)n_events, totals.flushes, totals.postponed, totals.dirty_units, totals.raw_entries,
-                totals.raw_by_cause[0], totals.raw_by_cause[1], totals.raw_by_cause[2], totals.max_keys, totals.max_carried);
     if (copy_host) {
         if (n_events == 0) {
             CU(cudaMemcpyAsync(sim->offsets_host.p, sim->offsets_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, C));
@@ -870,9 +954,23 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             res->col_label = sim->col_label_host.p;
         }
     }
-    if (flags & ATTPC_SPYRAL_ROWS) {
-        rc = run_spyral(sim, n_events, n_points, res, copy_host);
-        if (rc) return rc;
+    if (spy) {
+        res->n_rows = (int64_t)rows_before;
+        if (copy_host) {
+            if (n_events == 0)
+                CU(cudaMemcpyAsync(sim->row_offsets_host.p, sim->row_offsets_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, C));
+            res->row_offsets = sim->row_offsets_host.p;
+            if (spy_rows) {
+                res->rows = sim->rows_host.p;
+                res->row_labels = sim->row_labels_host.p;
+            } else {
+                res->row_col_pad = sim->rcol_pad_host.p;
+                res->row_col_tb_q16 = sim->rcol_tbq_host.p;
+                res->row_col_e_lo = sim->rcol_elo_host.p;
+                res->row_col_e_hi = sim->rcol_ehi_host.p;
+                res->row_col_label = sim->rcol_label_host.p;
+            }
+        }
     }
     // close the timeline on G after the other two streams have drained
     CU(cudaStreamWaitEvent(G, sim->fence(T), 0));
@@ -937,18 +1035,18 @@ void attpc_destroy(AttpcSim* sim) {
     if (sim->stream_c) cudaStreamDestroy(sim->stream_c);
     sim->lut.release(); sim->pad_xy.release(); sim->pad_scale.release(); sim->response.release();
     sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release(); sim->stop_ns.release(); sim->plan_cls.release(); sim->plan_counts.release(); sim->plan_order.release();
-    sim->hash.release(); sim->fix_rows.release(); sim->fix_items.release(); sim->perm.release();
-    sim->unit_kept.release(); sim->unit_raw.release(); sim->dirty.release(); sim->event_unit0.release();
-    sim->unit_nseg.release(); sim->unit_segend.release(); sim->tbend.release();
-    sim->event_nunits.release();
+    sim->hash.release(); sim->sort_items.release();
     sim->geom.release(); sim->rec.release();
     sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release(); sim->unit_order.release();
     sim->n_units.release();
-    sim->pstart.release();
+    sim->pstart.release(); sim->n_entries.release(); sim->mode.release();
     sim->kept.release(); sim->in_momenta.release(); sim->in_vertices.release();
     sim->offsets_dev.release(); sim->labels_dev.release(); sim->row_offsets_dev.release();
     sim->row_labels_dev.release(); sim->cloud_dev.release(); sim->rows_dev.release(); sim->row_kept.release();
     sim->row_sort_keys.release(); sim->row_sort_idx.release();
+    sim->rcol_pad_dev.release(); sim->rcol_tbq_dev.release(); sim->rcol_elo_dev.release(); sim->rcol_ehi_dev.release();
+    sim->rcol_label_dev.release(); sim->rcol_pad_host.release(); sim->rcol_tbq_host.release(); sim->rcol_elo_host.release();
+    sim->rcol_ehi_host.release(); sim->rcol_label_host.release();
     sim->col_pad_dev.release(); sim->col_tbq_dev.release(); sim->col_q_dev.release(); sim->col_q32_dev.release(); sim->big_rows_dev.release(); sim->big_q_dev.release(); sim->col_label_dev.release();
     sim->col_pad_host.release(); sim->col_tbq_host.release(); sim->col_q_host.release(); sim->col_q32_host.release(); sim->big_rows_host.release(); sim->big_q_host.release(); sim->col_label_host.release();
     sim->offsets_host.release(); sim->labels_host.release(); sim->row_offsets_host.release();
@@ -1033,14 +1131,11 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
     P.n_species = n_species;
     P.n_pads = n_pads;
     P.n_response = n_response;
-    P.n_bins = std::min(TB_BINS, std::max(2, std::max(cfg->micromegas_edge, cfg->windows_edge) + 2));
     if (cfg->max_events_per_launch > 0) sim->launch_events = cfg->max_events_per_launch;
     if (cfg->copy_events_per_launch > 0) sim->copy_launch_events = cfg->copy_events_per_launch;  // events per launch when rows go to the host
     if (cfg->hash_capacity > 0) sim->hash_cap = next_pow2(cfg->hash_capacity);
     if (cfg->unit_points > 0) sim->unit_points = std::min<int32_t>(cfg->unit_points, UNIT_POINTS);
-    if (cfg->table_spill_keys > 0) sim->spill_keys = std::min<int32_t>(cfg->table_spill_keys, SMEM_HARD_DEFAULT);
-    if (cfg->table_hard_keys > 0) sim->hard_keys = std::min<int32_t>(cfg->table_hard_keys, SMEM_HARD_DEFAULT);
-    if (cfg->table_max_probe > 0) sim->max_probe = std::min<int32_t>(cfg->table_max_probe, SMEM_SLOTS);
+    if (cfg->table_spill_keys > 0) sim->spill_keys = std::min<int32_t>(cfg->table_spill_keys, SMEM_SPILL_AT);
     sim->group_events = std::min(sim->group_events, sim->launch_events);
     if (const char* env = getenv("ATTPC_CHUNK_GROUPS")) sim->chunk_groups = std::max(1, atoi(env));  // tuning aid
     if (const char* env = getenv("ATTPC_BIG_CAP")) sim->big_cap = std::min<int64_t>(ATTPC_BIG_CAP, std::max(0, atoi(env)));  // tests

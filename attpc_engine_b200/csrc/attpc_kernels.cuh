@@ -7,19 +7,13 @@
 //                     electrons, >=1 mask, gain, z -> time bucket (detector/solver.py:19-76, 243-305, 308-347, 386-398).
 //   replay_kernel     the same electron/mask/gain/time arithmetic from GIVEN trajectory rows and normals, in the
 //                     reference's exact operation order (parity part (a)).
-//   point_scan/order  points into (event, rank, arrival) order, sigma_t and the pad-table rows and columns of the 10x10
-//                     mesh of every point (detector/transporter.py:78-120, 217-226, 301).
-//   event_sort        per event: its points in ascending time-bucket order (counting sort, shared memory) and the work
-//                     units of the deposit kernel = time-bucket ranges of the event; unit_order: longest unit first.
+//   point_scan/order  per-event work units, points into (event, rank, arrival) order, sigma_t and the pad-table rows and
+//                     columns of the 10x10 mesh of every point (detector/transporter.py:78-120, 217-226, 301).
 //   deposit_kernel    one CTA per work unit, one lane per mesh row: pad lookup, bivariate-normal share, accumulation
-//                     per (pad, time bucket) in a shared-memory open-addressing table.  Points arrive in time-bucket
-//                     order, so every key below the time bucket of the next point is FINAL: whenever the table fills,
-//                     and at the end, the CTA masks (0 <= tb < 512), sorts (time bucket, pad) in shared memory and
-//                     appends the finished rows to the unit's region (detector/transporter.py:11-41, 123-249, 252-317;
-//                     pairing.py:6-28; simulator.py:111-113).  fixup_kernel: the rare unit whose table overflowed.
-//   scan/emit         CSR offsets from the rows per event, TB wiggle, final [pad, tb + u, electrons] rows + labels
-//                     and / or typed columns (detector/simulator.py:19-49, 104-115); optional Spyral rows
-//                     (detector/writer.py:61-112).
+//                     per (pad, time bucket) in a shared-memory open-addressing table that is appended to the event's
+//                     entry list in dense segments (detector/transporter.py:11-41, 123-249, 252-317; pairing.py:6-28).
+//   collect/scan/emit TB wiggle, 0 <= tb < 512 mask, canonical (ascending time bucket, pad) order, CSR compaction
+//                     (detector/simulator.py:19-49, 104-115); optional Spyral rows (detector/writer.py:61-112).
 //
 // Arithmetic that decides a pad id, a time bucket or an integer charge is written with the _rn intrinsics so that
 // nvcc cannot contract it into FMAs: it must round exactly like the reference's numpy/numba code.
@@ -61,8 +55,7 @@ struct SimParams {
     double adc_threshold;
     double rtol, atol, freeze_ke;
     int32_t lm, e_min, n_oct, n_nodes;
-    int32_t n_species, n_pads, n_response;
-    int32_t n_bins;  // time-bucket bins of the per-event ordering (<= TB_BINS); the last bin collects everything above
+    int32_t n_species, n_pads, n_response, pad0;
     SpeciesDev sp[MAX_SPECIES];
     const int16_t* lut;
     const double* tables;  // [n_species][n_nodes]: dE/dx * MEV_2_JOULE * density * 100 / (m_kg c)  -> d(gamma beta)/dt
@@ -94,27 +87,17 @@ struct PointBuf {
     unsigned* start;    // [launch events * ranks] first position of the list inside the group's ordered run
     double* geom;       // ordered: GEOM_DOUBLES per point, the per-point constants of the drift mesh (exact path)
     uint32_t* rec;      // ordered: REC_WORDS per point, what the deposit kernel reads (see make_point)
-    uint32_t* perm;     // ordered: per event, the indices of its depositing points in ascending time-bucket order
-    uint32_t* tbend;    // ordered: per position of that list, the position where the next time bucket starts
-    // work units of the deposit kernel (one CTA each): a time-bucket range of one event (event_sort_kernel)
-    int32_t* unit_event;   // [n_groups][max_units] event index inside the group
-    int32_t* unit_first;   // first position of the range inside the event's time-bucket-ordered list (perm)
-    int32_t* unit_count;
-    int32_t* unit_order;   // units by decreasing size (longest first)
-    unsigned* unit_kept;   // rows the unit left in its region (after the time-bucket mask), in final order
-    unsigned* unit_raw;    // entries the unit had to leave unmerged at the top of its region (fixup_kernel)
-    unsigned* unit_nseg;   // segments (flushes) the unit's rows were written in; 0 = the rows are already in final order
-    unsigned* unit_segend; // [max_units][MAX_SEGMENTS] end of every segment inside the region
+    // work units of the deposit kernel (one CTA each): a slice of <= UNIT_POINTS points of one event
+    int32_t* unit_event;   // [max_units] event index inside the group
+    int32_t* unit_first;   // [max_units] first point of the slice inside the event's ordered run
+    int32_t* unit_count;   // [max_units]
+    int32_t* unit_order;   // [max_units] units by decreasing size (longest first)
     int32_t* n_units;      // [n_groups]
-    int32_t* event_unit0;  // [launch events] first unit of the event (its units are consecutive, ascending time bucket)
-    int32_t* event_nunits; // [launch events]
-    unsigned* dirty;       // [0] number of units with raw entries, [1] cursor of fixup_kernel, [2..] their ids
     int64_t group_cap;  // points per group
     int32_t group_events;
     int32_t ranks;      // tracks per event
     int32_t max_units;  // capacity of the unit arrays per group
-    int32_t unit_points;  // target size of a work unit (a unit ends at a time-bucket boundary, so it can be longer)
-    int32_t dirty_cap;    // capacity of the dirty list
+    int32_t unit_points;  // longest slice of one event handled by one CTA of the deposit kernel (<= UNIT_POINTS)
 };
 
 // Per-launch counters (one set per in-flight launch; zeroed when the launch starts).
@@ -125,10 +108,6 @@ struct Counters {
     // integrator probes: Dormand-Prince steps tried / rejected, and the most loop passes any one track needed (the
     // serial critical path of a launch)
     unsigned long long rk_steps, rk_rejects, max_track_passes;
-    unsigned long long raw_entries, dirty_units;  // deposit kernel: entries / units that took the fixup path
-    unsigned long long raw_by_cause[3];           // ... of which: insert found no slot, flush could not carry, list full
-    unsigned long long postponed;                 // flushes postponed because little was finished yet
-    unsigned long long max_keys, max_carried;     // fullest table seen by a flush, most keys carried over by one
 };
 
 // Publish a launch's counters and the running CSR totals into mapped host memory.  A copy-engine transfer would
@@ -138,12 +117,14 @@ __global__ void publish_kernel(const Counters* ctr, const unsigned long long* cs
     *host_ctr = *ctr;
     host_csr[0] = csr[0];
     host_csr[1] = csr[1];
+    host_csr[2] = csr[2];
     __threadfence_system();
 }
 
 // Running CSR total after a chunk of groups, published for the host so that it can start copying the finished rows.
 __global__ void publish_total_kernel(const unsigned long long* csr, unsigned long long* host_slot) {
-    *host_slot = csr[0];
+    host_slot[0] = csr[0];  // cloud rows so far
+    host_slot[1] = csr[2];  // Spyral rows so far
     __threadfence_system();
 }
 
@@ -970,14 +951,15 @@ struct GroupView {
     int32_t first_slot;   // first event slot of the group inside the launch batch
     int32_t n_events;     // events in this group
     int32_t group;        // group index (selects the PointBuf region)
-    int32_t hash_cap;     // entries per unit region
-    HashEntry* tables;    // [chunk groups][max_units][hash_cap]: finished rows of every work unit, in final order
+    int32_t hash_cap;     // entries per event region (power of two)
+    HashEntry* tables;    // [chunk events][hash_cap]: entry list of every event
+    unsigned* n_entries;  // [launch events] entries of the list (zeroed before the deposit kernel)
+    unsigned* mode;       // [launch events] 0 = every key once, 1 = a key may appear several times (the event was
+                          // deposited in several segments: dense event, or split over several units)
     int32_t exact_mesh;   // ATTPC_EXACT_MESH: every pixel through the reference's own expression (validation)
     int32_t group_events; // events per full group
-    int32_t chunk_group;  // index of the group inside the chunk (selects the block of unit regions)
-    int32_t spill_keys;   // keys in a CTA's shared-memory table that trigger a flush of the finished time buckets
-    int32_t hard_keys;    // keys above which a flush may no longer be postponed
-    int32_t max_probe;    // probes after which an insert gives up and leaves a raw entry (test knob)
+    int32_t chunk_e0;     // first event of the group inside the chunk (row of `tables` and of the sort scratch)
+    int32_t spill_keys;   // keys in a CTA's shared-memory table that trigger a segment append (<= SMEM_SPILL_AT)
 };
 
 // The host describes a CHUNK of consecutive groups (first_slot / group / n_events of the whole chunk) and launches
@@ -987,29 +969,38 @@ __device__ __forceinline__ GroupView sub_group(GroupView gv, int dy) {
     gv.group += dy;
     gv.first_slot += skip;
     gv.n_events = max(0, min(gv.group_events, gv.n_events - skip));
-    gv.chunk_group = dy;
+    gv.chunk_e0 = skip;
     return gv;
 }
 
 // ------------------------------------------------------------------------------------------- ordering of points
-constexpr int UNIT_POINTS = 1024;   // default target size of a work unit of the deposit kernel
+constexpr int UNIT_POINTS = 1024;   // longest slice of one event handled by one CTA of the deposit kernel
 constexpr int MAX_UNITS_SORT = 8192;
 constexpr int GEOM_DOUBLES = 12;
-constexpr int REC_WORDS = 16;       // words of an ordered point record (make_point)
-constexpr int TB_BINS = 1024;       // bins of the per-event counting sort on the time bucket (SimParams.n_bins <= TB_BINS)
-constexpr int MAX_SEGMENTS = 64;    // flushes of one work unit emit_kernel can order one by one (more: fixup_kernel)
 
-// Per group, single CTA: exclusive scan of the (event, rank) list lengths -> start of every list in the group's
-// ordered run (the lists of one event are consecutive: the event's points form one contiguous run).
+// Per group, single CTA: (1) exclusive scan of the (event, rank) list lengths -> start of every list in the group's
+// ordered run; (2) split every event into work units of <= UNIT_POINTS points; (3) order the units by decreasing
+// size so that the longest start first (the per-event cost varies by 100x between a short recoil and a stopped ion).
 __global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView chunk, const Counters* ctr) {
     const GroupView gv = sub_group(chunk, blockIdx.x);
     __shared__ unsigned s_part[1024];
-    __shared__ unsigned s_base;
+    __shared__ unsigned s_base, s_ubase;
+    __shared__ uint32_t s_sort[MAX_UNITS_SORT];
     const int tid = threadIdx.x;
-    if (ctr->overflow_points) return;  // the point lists are incomplete: the host will redo the launch with bigger buffers
+    if (ctr->overflow_points) {  // the point lists are incomplete: the host will redo the launch with bigger buffers
+        if (tid == 0) pb.n_units[gv.group] = 0;
+        return;
+    }
     const int n = gv.n_events * pb.ranks;
     const int64_t first = (int64_t)gv.first_slot * pb.ranks;
-    if (tid == 0) s_base = 0;
+    int32_t* u_event = pb.unit_event + (int64_t)gv.group * pb.max_units;
+    int32_t* u_first = pb.unit_first + (int64_t)gv.group * pb.max_units;
+    int32_t* u_count = pb.unit_count + (int64_t)gv.group * pb.max_units;
+    int32_t* u_order = pb.unit_order + (int64_t)gv.group * pb.max_units;
+    if (tid == 0) {
+        s_base = 0;
+        s_ubase = 0;
+    }
     __syncthreads();
     for (int start = 0; start < n; start += 1024) {
         const int i = start + tid;
@@ -1027,169 +1018,47 @@ __global__ void __launch_bounds__(1024) point_scan_kernel(PointBuf pb, GroupView
         if (tid == 0) s_base += s_part[1023];
         __syncthreads();
     }
-}
-
-// The deposit kernel walks the points of an event in ascending time-bucket order: every key (pad, time bucket) below
-// the time bucket of the next point is then final and can leave the CTA's table for good.  Bin of a time bucket:
-__device__ __forceinline__ int tb_bin(const SimParams& P, unsigned tb) { return (int)min(tb, (unsigned)P.n_bins - 1u); }
-
-// One CTA per event: counting sort of its depositing points on the time bucket (order inside a bucket is arbitrary:
-// integer adds commute and the label is a maximum) -> pb.perm, and the event's work units: consecutive time-bucket
-// ranges of about unit_points points (bin b belongs to unit floor(start[b] / unit_points), so a unit always ends at a
-// bucket boundary and two units never share a key).
-constexpr int SORT_THREADS = 128;
-__global__ void __launch_bounds__(SORT_THREADS)
-event_sort_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk, Counters* ctr) {
-    const GroupView gv = sub_group(chunk, blockIdx.y);
-    if ((int)blockIdx.x >= gv.n_events || ctr->overflow_points) return;
-    constexpr int PER = TB_BINS / SORT_THREADS;
-    __shared__ unsigned s_start[TB_BINS + 1], s_fill[TB_BINS];
-    __shared__ unsigned s_wsum[SORT_THREADS / 32], s_wuid[SORT_THREADS / 32], s_wopen[SORT_THREADS / 32];
-    __shared__ unsigned s_u0;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int slot_event = gv.first_slot + (int)blockIdx.x;
-    const int64_t l0 = (int64_t)slot_event * pb.ranks;
-    unsigned n = 0;
-    for (int r = 0; r < pb.ranks; ++r) n += pb.cnt[l0 + r];
-    if (n == 0) {
-        if (tid == 0) {
-            pb.event_unit0[slot_event] = 0;
-            pb.event_nunits[slot_event] = 0;
+    // units: event e has ceil(points / UNIT_POINTS) of them (at least one, so that empty events still get their
+    // zero-length entry list written)
+    for (int start = 0; start < gv.n_events; start += 1024) {
+        const int e = start + tid;
+        unsigned pts = 0;
+        if (e < gv.n_events)
+            for (int r = 0; r < pb.ranks; ++r) pts += pb.cnt[first + (int64_t)e * pb.ranks + r];
+        const unsigned up = (unsigned)pb.unit_points;
+        const unsigned nu = e < gv.n_events ? max(1u, (pts + up - 1u) / up) : 0u;
+        s_part[tid] = nu;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned add = tid >= o ? s_part[tid - o] : 0u;
+            __syncthreads();
+            s_part[tid] += add;
+            __syncthreads();
         }
-        return;
-    }
-    const int64_t base = (int64_t)gv.group * pb.group_cap + pb.start[l0];
-    for (int i = tid; i < TB_BINS; i += SORT_THREADS) s_fill[i] = 0;
-    __syncthreads();
-    for (unsigned p = tid; p < n; p += SORT_THREADS) {
-        const unsigned w = __ldg(pb.rec + (base + p) * REC_WORDS);
-        if (w >> 30) atomicAdd(&s_fill[tb_bin(P, w & 0x1FFFFFFFu)], 1u);  // kind 0 never deposits
-    }
-    __syncthreads();
-    // exclusive scan of the bin counts: PER consecutive bins per thread
-    unsigned cnt[PER], sum = 0;
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        cnt[k] = s_fill[tid * PER + k];
-        sum += cnt[k];
-    }
-    unsigned incl = sum;
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_wsum[warp] = incl;
-    __syncthreads();
-    unsigned run = incl - sum;
-    for (int w = 0; w < warp; ++w) run += s_wsum[w];
-    const unsigned up = (unsigned)max(pb.unit_points, 1);
-    // unit id of a non-empty bin = start / up; a bin OPENS a unit when its id differs from the previous non-empty bin's
-    unsigned start[PER], last_uid = 0xFFFFFFFFu;  // id of this thread's last non-empty bin
-#pragma unroll
-    for (int k = 0; k < PER; ++k) {
-        start[k] = run;
-        s_start[tid * PER + k] = run;
-        s_fill[tid * PER + k] = run;
-        if (cnt[k]) last_uid = run / up;
-        run += cnt[k];
-    }
-    if (tid == SORT_THREADS - 1) s_start[TB_BINS] = run;  // live points of the event
-    // id of the last non-empty bin BEFORE this thread's bins (ids never decrease: a running maximum, -1 = none)
-    int prev = (int)last_uid;
-    for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(FULL, prev, o);
-        if (lane >= o) prev = max(prev, v);
-    }
-    if (lane == 31) s_wuid[warp] = (unsigned)prev;
-    __syncthreads();
-    int before = __shfl_up_sync(FULL, prev, 1);
-    if (lane == 0) before = -1;
-    for (int w = 0; w < warp; ++w) before = max(before, (int)s_wuid[w]);
-    unsigned opens = 0, open_mask = 0;
-    {
-        int uid_prev = before;
-#pragma unroll
-        for (int k = 0; k < PER; ++k)
-            if (cnt[k]) {
-                const int uid = (int)(start[k] / up);
-                if (uid != uid_prev) {
-                    opens += 1;
-                    open_mask |= 1u << k;
+        if (e < gv.n_events) {
+            unsigned u0 = s_ubase + s_part[tid] - nu;
+            gv.mode[gv.first_slot + e] = nu > 1 ? 1u : 0u;  // several units: a key may be listed once per unit
+            for (unsigned k = 0; k < nu; ++k) {
+                const unsigned u = u0 + k;
+                if (u < (unsigned)pb.max_units) {
+                    u_event[u] = e;
+                    u_first[u] = (int32_t)(k * up);
+                    u_count[u] = (int32_t)min(up, pts - min(pts, k * up));
                 }
-                uid_prev = uid;
             }
-    }
-    unsigned oincl = opens;
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned v = __shfl_up_sync(FULL, oincl, o);
-        if (lane >= o) oincl += v;
-    }
-    if (lane == 31) s_wopen[warp] = oincl;
-    __syncthreads();
-    unsigned kbase = oincl - opens, nu = 0;
-    for (int w = 0; w < SORT_THREADS / 32; ++w) {
-        if (w < warp) kbase += s_wopen[w];
-        nu += s_wopen[w];
-    }
-    if (tid == 0) {
-        s_u0 = nu ? atomicAdd((unsigned*)&pb.n_units[gv.group], nu) : 0u;
-        pb.event_nunits[slot_event] = (int32_t)nu;
-    }
-    __syncthreads();
-    const unsigned u0 = s_u0;
-    if (tid == 0) pb.event_unit0[slot_event] = (int32_t)u0;
-    const int64_t ubase = (int64_t)gv.group * pb.max_units;
-    if (u0 + nu > (unsigned)pb.max_units) {  // cannot happen: units <= events + points / unit_points (host sizing)
-        if (tid == 0) ctr->overflow_points = 1;
-        return;
-    }
-    // unit k starts at the start of its opening bin and ends where unit k + 1 starts: write the firsts, then the counts
-    {
-        unsigned k = kbase;
-#pragma unroll
-        for (int j = 0; j < PER; ++j)
-            if ((open_mask >> j) & 1u) {
-                pb.unit_event[ubase + u0 + k] = (int32_t)blockIdx.x;
-                pb.unit_first[ubase + u0 + k] = (int32_t)start[j];
-                k += 1;
-            }
-    }
-    // scatter the point indices into time-bucket order
-    uint32_t* perm = pb.perm + base;
-    uint32_t* tbend = pb.tbend + base;
-    for (unsigned p = tid; p < n; p += SORT_THREADS) {
-        const unsigned w = __ldg(pb.rec + (base + p) * REC_WORDS);
-        if (w >> 30) {
-            const int bin = tb_bin(P, w & 0x1FFFFFFFu);
-            const unsigned at = atomicAdd(&s_fill[bin], 1u);
-            perm[at] = p;
-            tbend[at] = s_start[bin + 1];  // first position of the next bin (bins are time buckets but for the last one)
         }
+        __syncthreads();
+        if (tid == 0) s_ubase += s_part[1023];
+        __syncthreads();
     }
-    __syncthreads();  // (also orders the unit_first stores of this CTA before the reads below)
-    const unsigned live = s_start[TB_BINS];
-    for (unsigned k = tid; k < nu; k += SORT_THREADS) {
-        const unsigned f = (unsigned)pb.unit_first[ubase + u0 + k];
-        const unsigned g = k + 1 < nu ? (unsigned)pb.unit_first[ubase + u0 + k + 1] : live;
-        pb.unit_count[ubase + u0 + k] = (int32_t)(g - f);
-    }
-}
-
-// Per group, single CTA: units by decreasing size, so that the longest start first (the per-event cost varies by 100x
-// between a short recoil and a stopped ion).  Bitonic sort of (size, unit) ... only when it fits the sort buffer.
-__global__ void __launch_bounds__(1024) unit_order_kernel(PointBuf pb, GroupView chunk, const Counters* ctr) {
-    const GroupView gv = sub_group(chunk, blockIdx.x);
-    __shared__ uint32_t s_sort[MAX_UNITS_SORT];
-    const int tid = threadIdx.x;
-    if (ctr->overflow_points) return;
-    const int32_t* u_count = pb.unit_count + (int64_t)gv.group * pb.max_units;
-    int32_t* u_order = pb.unit_order + (int64_t)gv.group * pb.max_units;
-    const int total = min(pb.n_units[gv.group], pb.max_units);
+    const int total = min((int)s_ubase, pb.max_units);
+    if (tid == 0) pb.n_units[gv.group] = total;
+    // longest first: bitonic sort of (UNIT_POINTS - count) << 16 | unit ... only when it fits the sort buffer
     if (total <= MAX_UNITS_SORT) {
         int n2 = 1;
         while (n2 < total) n2 <<= 1;
         for (int i = tid; i < n2; i += 1024)
-            s_sort[i] = i < total ? ((uint32_t)(0x7FFFF - min(u_count[i], 0x7FFFF)) << 13) | (uint32_t)i : 0xFFFFFFFFu;
+            s_sort[i] = i < total ? ((uint32_t)(UNIT_POINTS - u_count[i]) << 16) | (uint32_t)i : 0xFFFFFFFFu;
         __syncthreads();
         for (int k = 2; k <= n2; k <<= 1)
             for (int j = k >> 1; j > 0; j >>= 1) {
@@ -1205,7 +1074,7 @@ __global__ void __launch_bounds__(1024) unit_order_kernel(PointBuf pb, GroupView
                 }
                 __syncthreads();
             }
-        for (int i = tid; i < total; i += 1024) u_order[i] = (int32_t)(s_sort[i] & 0x1FFFu);
+        for (int i = tid; i < total; i += 1024) u_order[i] = (int32_t)(s_sort[i] & 0xFFFFu);
     } else {
         for (int i = tid; i < total; i += 1024) u_order[i] = i;
     }
@@ -1245,6 +1114,7 @@ __device__ __forceinline__ int lut_index(const SimParams& P, double coord_m) {
 //   words 4-8   int16 iy[10]: pad-table column of mesh column j (-1 = outside), kind 1: iy[0] of the point itself
 //   words 9-13  int16 ix[10]: pad-table row of mesh row i
 //   word 14     rank of the track (position in `indices`)
+constexpr int REC_WORDS = 16;
 
 __device__ __forceinline__ void make_point(const SimParams& P, double cx, double cy, double time, long long q,
                                            bool exact_mesh, double* g, uint32_t* rec) {
@@ -1341,7 +1211,324 @@ __global__ void __launch_bounds__(256) point_order_kernel(const __grid_constant_
     }
 }
 
-// ------------------------------------------------------------------------- finalize arguments (mask, wiggle, output)
+// ---------------------------------------------------------------------------------------- shared-memory accumulate
+constexpr int DEPOSIT_THREADS = 256;
+constexpr int DEPOSIT_WARPS = DEPOSIT_THREADS / 32;
+constexpr int POINTS_PER_WARP = 3;   // three active points per warp pass: 3 x 10 mesh rows on 30 lanes
+constexpr int POINTS_PER_ITER = DEPOSIT_WARPS * POINTS_PER_WARP;
+constexpr int QUEUE_SLOTS = 64;      // per-warp ring of finished (key, charge) runs waiting for a full 32-lane insert
+constexpr int SMEM_SLOTS = 4864;     // per-CTA table in shared memory: 10 B per slot = 47.5 KB, four CTAs per SM
+// fill check once per pass of the CTA: a pass adds at most 100 keys per point plus what the rings still hold
+constexpr int SMEM_SPILL_AT = SMEM_SLOTS - 100 * POINTS_PER_ITER - DEPOSIT_WARPS * QUEUE_SLOTS - 512;
+// That is the highest safe threshold.  The default is lower: a table at 30 % load answers most inserts with one probe,
+// and the appends it costs are cheap (measured optimum over the four workloads; AttpcConfig.table_spill_keys).
+constexpr int SMEM_SPILL_DEFAULT = 2000 < SMEM_SPILL_AT ? 2000 : SMEM_SPILL_AT;
+constexpr size_t DEPOSIT_SMEM_BYTES = (size_t)SMEM_SLOTS * (2 * sizeof(unsigned) + sizeof(uint16_t));
+constexpr unsigned SMEM_KEY_MASK = 0x0FFFFFFFu;  // low 28 bits: ((tb << 15) | pad) + 1; top 4 bits: track rank
+
+// Slot word = compact key (time bucket < 8192, pad id < 32768) + 1 in the low 28 bits, 0 = empty, and in the top four
+// bits the rank of the last track that touched the slot.  Tracks are processed in rank order, so the rank is kept
+// current with a plain store of the whole word (every writer of a phase stores the same value; a concurrent CAS on
+// a non-empty word simply fails and re-reads it).  The charge is a 48-bit sum: 32 low bits + 16 high bits packed two
+// per word (max 2.8e14 electrons per pad and time bucket, far above anything physical; overflow is flagged).
+struct SmemTable {
+    unsigned* word;   // key + rank
+    unsigned* lo;     // charge bits 0..31
+    unsigned* hi2;    // charge bits 32..47, two slots per 32-bit word
+};
+
+__device__ __forceinline__ unsigned smem_key(unsigned tb, unsigned pad) { return ((tb << 15) | pad) + 1u; }
+
+__device__ __forceinline__ unsigned smem_home(unsigned key1) {
+    return __umulhi(key1 * 2654435761u, (unsigned)SMEM_SLOTS);  // multiply-shift range reduction, no division
+}
+
+// Find the slot of `key1`, claiming an empty one if it is new (counted in the lane's `n_new`; the warp publishes the
+// sum before every fill check).  The table is flushed long before it can fill.
+__device__ __forceinline__ unsigned smem_find(const SmemTable& t, unsigned key1, unsigned rank, unsigned& n_new,
+                                              unsigned& probes) {
+    unsigned slot = smem_home(key1);
+#pragma unroll 1
+    for (unsigned probe = 0; probe < (unsigned)SMEM_SLOTS; ++probe) {
+        unsigned w = *(volatile unsigned*)&t.word[slot];
+        if ((w & SMEM_KEY_MASK) == key1) break;  // the common case: the key is there, at its home slot
+        if (w == 0u) {
+            w = atomicCAS(&t.word[slot], 0u, key1 | (rank << 28));
+            if (w == 0u) {
+                n_new += 1u;
+                break;
+            }
+            if ((w & SMEM_KEY_MASK) == key1) break;
+        }
+        probes += 1u;  // (extra probes; the first probe of every insert is counted from the number of pushes)
+        slot = slot + 1u == (unsigned)SMEM_SLOTS ? 0u : slot + 1u;
+    }
+    return slot;
+}
+
+// Exact accumulate from native 32-bit shared-memory atomics (carry into the 16-bit high part).
+__device__ __forceinline__ void smem_charge(const SmemTable& t, unsigned slot, unsigned long long q, int* overflow) {
+    const unsigned vlo = (unsigned)q, vhi = (unsigned)(q >> 32);
+    unsigned carry = 0u;
+    if (vlo) carry = atomicAdd(&t.lo[slot], vlo) > ~vlo ? 1u : 0u;
+    const unsigned add = vhi + carry;
+    if (add) {
+        const unsigned shift = (slot & 1u) * 16u;
+        const unsigned old = (atomicAdd(&t.hi2[slot >> 1], add << shift) >> shift) & 0xFFFFu;
+        if (add > 0xFFFFu || old + add > 0xFFFFu) *overflow = 1;
+    }
+}
+
+__device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t, unsigned slot) {
+    const unsigned hi = (t.hi2[slot >> 1] >> ((slot & 1u) * 16u)) & 0xFFFFu;
+    return ((unsigned long long)hi << 32) | t.lo[slot];
+}
+
+// One CTA per work unit (a slice of one event's points, all tracks together; label = last track in `indices` order
+// to touch a key, detector/transporter.py:166-169, 247-249 = the highest rank, kept with an atomicMax).
+//
+// A warp takes three active points per pass; lane (s, i) owns row i (one x of the 10x10 mesh) of point s and walks
+// the ten y of that row in the reference's pixel order.  Neighbouring pixels of a row usually fall on the same pad, so
+// the lane sums the integer shares of such a run in registers (integer adds commute and every share is truncated
+// on its own first, exactly as transporter.py:240-248 does) and only a finished run (key, charge) is pushed into the
+// warp's ring in shared memory.  Whenever the ring holds 32 runs, all 32 lanes insert one each into the CTA's
+// open-addressing table: the insert code (probe loop, two atomics) runs once per 32 runs instead of once per 32
+// pixels.  The table is appended to the event's entry list as a dense segment whenever it reaches the spill threshold
+// and at the end; events deposited in several segments (dense events, events split over several units) may then list
+// a key several times, which collect_kernel merges after sorting.
+__global__ void __launch_bounds__(DEPOSIT_THREADS, 4)
+deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk, Counters* ctr) {
+    const GroupView gv = sub_group(chunk, blockIdx.y);
+    extern __shared__ __align__(16) unsigned s_raw[];
+    __shared__ unsigned s_nkeys, s_out, s_flush, s_base;
+    __shared__ unsigned s_qkey[DEPOSIT_WARPS][QUEUE_SLOTS], s_qlo[DEPOSIT_WARPS][QUEUE_SLOTS],
+        s_qhi[DEPOSIT_WARPS][QUEUE_SLOTS];
+    if ((int)blockIdx.x >= pb.n_units[gv.group]) return;
+    const int64_t ubase = (int64_t)gv.group * pb.max_units;
+    const int unit = pb.unit_order[ubase + blockIdx.x];
+    const int e = pb.unit_event[ubase + unit];
+    const int u_first = pb.unit_first[ubase + unit], u_count = pb.unit_count[ubase + unit];
+    SmemTable t;
+    t.word = s_raw;
+    t.lo = s_raw + SMEM_SLOTS;
+    t.hi2 = s_raw + 2 * SMEM_SLOTS;
+    const int slot_event = gv.first_slot + e;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    HashEntry* region = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
+    const int64_t base = (int64_t)gv.group * pb.group_cap;
+    constexpr int TABLE_VEC4 = (2 * SMEM_SLOTS + SMEM_SLOTS / 2) / 4;
+    auto clear_table = [&]() {
+        uint4* v = reinterpret_cast<uint4*>(s_raw);
+        for (int i = threadIdx.x; i < TABLE_VEC4; i += blockDim.x) v[i] = make_uint4(0u, 0u, 0u, 0u);
+    };
+    clear_table();
+    if (threadIdx.x == 0) {
+        s_nkeys = 0;
+        s_out = 0;
+        s_flush = 0;
+    }
+    __syncthreads();
+    unsigned n_dep = 0, n_probe = 0, n_new = 0;
+    const int sub = lane / MESH_N;                                  // point of the warp's triple; 3 = idle lanes 30, 31
+    const int row = lane - sub * MESH_N;                            // mesh row (x index) of this lane
+    // constant mesh weights: the rows differ from lane to lane, so they are read from shared memory (row stride 11
+    // doubles: the ten rows start in ten different bank pairs), not through the constant cache
+    __shared__ double s_w[MESH_N][MESH_N + 1];
+    for (int k = threadIdx.x; k < MESH_N * MESH_N; k += blockDim.x) s_w[k / MESH_N][k % MESH_N] = P.mesh_w[k];
+    __syncthreads();
+    const double* wrow = s_w[row];
+    const bool exact_mesh = gv.exact_mesh != 0;
+    unsigned* qkey = s_qkey[warp];
+    unsigned* qlo = s_qlo[warp];
+    unsigned* qhi = s_qhi[warp];
+    unsigned q_head = 0, q_tail = 0;  // warp-uniform ring positions
+    const unsigned lanes_below = lanemask_lt();
+
+    auto drain = [&](unsigned n) {  // whole warp: insert ring entries [q_head, q_head + n), n <= 32
+        __syncwarp();
+        if ((unsigned)lane < n) {
+            const unsigned at = (q_head + (unsigned)lane) & (QUEUE_SLOTS - 1);
+            const unsigned kw = qkey[at];
+            const unsigned long long q = ((unsigned long long)qhi[at] << 32) | qlo[at];
+            const unsigned slot = smem_find(t, kw & SMEM_KEY_MASK, kw >> 28, n_new, n_probe);
+            smem_charge(t, slot, q, &ctr->overflow_charge);
+            atomicMax(&t.word[slot], kw);  // same key bits: the highest rank wins (transporter.py:247-249)
+        }
+        __syncwarp();
+        q_head += n;
+    };
+    auto publish_new_keys = [&]() {  // whole warp, before a barrier that precedes a read of s_nkeys
+        const unsigned total = __reduce_add_sync(FULL, n_new);
+        if (lane == 0 && total) atomicAdd(&s_nkeys, total);
+        n_new = 0;
+    };
+
+    // Append the table as one dense SEGMENT to the event's entry list and clear it (all threads, after a barrier that
+    // follows every warp's publish_new_keys).  The position comes from the event's entry counter, which the units
+    // of a split event share.  A key can then sit in several segments of the list: gv.mode marks such events and
+    // collect_kernel merges the copies after sorting (integer adds commute, the label is a maximum).
+    auto append_segment = [&](bool last) {
+        if (threadIdx.x == 0) {
+            s_base = atomicAdd(&gv.n_entries[slot_event], s_nkeys);
+            if (!last) {
+                gv.mode[slot_event] = 1u;
+                atomicAdd(&ctr->flushes, 1ULL);
+            }
+        }
+        __syncthreads();
+        const unsigned seg0 = s_base;
+        if (seg0 + s_nkeys > (unsigned)gv.hash_cap) {  // the list does not fit the event's region: the host grows it
+            if (threadIdx.x == 0) ctr->overflow_hash = 1;
+        } else {
+            const uint4* words = reinterpret_cast<const uint4*>(t.word);
+            for (int i = threadIdx.x; i < SMEM_SLOTS / 4; i += blockDim.x) {
+                const uint4 w4 = words[i];
+                const unsigned w[4] = {w4.x, w4.y, w4.z, w4.w};
+                const unsigned cnt = (w4.x != 0u) + (w4.y != 0u) + (w4.z != 0u) + (w4.w != 0u);
+                if (cnt) {
+                    unsigned pos = seg0 + atomicAdd(&s_out, cnt);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (w[k])
+                            region[pos++] = HashEntry{w[k] & SMEM_KEY_MASK, w[k] >> 28, smem_charge_of(t, 4 * i + k)};
+                }
+            }
+        }
+        if (last) return;
+        __syncthreads();
+        clear_table();
+        if (threadIdx.x == 0) {
+            s_nkeys = 0;
+            s_out = 0;
+            s_flush = 0;
+        }
+        __syncthreads();
+    };
+
+    // The unit's slice [u_first, u_first + u_count) of the event's run, all tracks together: the label of a key is
+    // the highest rank that touched it (atomicMax on the slot word), so points need no ordering.  Warps run freely:
+    // a warp that sees the table filling up raises s_flush, every warp notices at its next pass boundary and only
+    // then do they meet at a barrier (every barrier of this kernel is followed by the same uniform decision on
+    // s_flush, whichever call site a warp arrives from).
+    const int64_t run0 = pb.start[(int64_t)slot_event * pb.ranks];
+    const int end = u_first + u_count;
+    for (int p0 = u_first; p0 < end; p0 += POINTS_PER_ITER) {
+        const int w0 = p0 + warp * POINTS_PER_WARP;
+        if (w0 < end) {  // warp-uniform
+            const int pp = w0 + sub;
+            const bool have = sub < POINTS_PER_WARP && pp < end;
+            const int64_t p = base + run0 + (have ? pp : w0);
+            const uint4* rp = reinterpret_cast<const uint4*>(pb.rec + p * REC_WORDS);
+            uint4 head = __ldg(rp);
+            if (!have) head.x = 0u;
+            const unsigned r = __ldg(pb.rec + p * REC_WORDS + 14);  // rank of the point's track
+            const int kind = (int)(head.x >> 30), tb = (int)(head.x & 0x1FFFFFFFu);
+            const bool careful_point = (head.x >> 29) & 1u;
+            const unsigned keybase = (((unsigned)tb << 15) + 1u) | (r << 28);  // + pad = slot word
+            const double qd = kind == 2 ? __hiloint2double((int)head.w, (int)head.z) : 0.0;
+            const double guard = exact_mesh ? 2.0 : (double)__uint_as_float(head.y);
+            int cur = -1;         // pad of the run being summed
+            long long acc = 0;    // its charge so far
+            int pad[MESH_N];
+#pragma unroll
+            for (int j = 0; j < MESH_N; ++j) pad[j] = -1;
+            if (kind != 0) {
+                // pad-table row of this lane's mesh row, columns of the ten mesh columns (make_point)
+                const uint4 cols = __ldg(rp + 1);
+                const uint2 tail = __ldg(reinterpret_cast<const uint2*>(rp + 2));  // iy[8], iy[9] | ix[0], ix[1]
+                const int ix = (int)__ldg(reinterpret_cast<const int16_t*>(rp) + 18 + row);
+                const unsigned cw[5] = {cols.x, cols.y, cols.z, cols.w, tail.x};
+                const int16_t* lut_row = P.lut + (int64_t)max(ix, 0) * P.lut_n;
+                if (kind == 2) {
+#pragma unroll
+                    for (int j = 0; j < MESH_N; ++j) {  // all pad lookups first: independent loads in flight
+                        const int iy = (j & 1) ? (int)cw[j / 2] >> 16 : (int)(int16_t)(cw[j / 2] & 0xFFFFu);
+                        if (ix >= 0 && iy >= 0) pad[j] = (int)__ldg(lut_row + iy);
+                    }
+                } else if (row == 0) {  // detector/transporter.py:123-169: all electrons on one pad
+                    const int iy = (int)(int16_t)(cw[0] & 0xFFFFu);
+                    if (ix >= 0 && iy >= 0) cur = (int)__ldg(lut_row + iy);
+                    acc = (long long)__hiloint2double((int)head.w, (int)head.z);
+                    n_dep += cur >= 0;
+                }
+            }
+            // detector/transporter.py:240-246: int(pdf * step^2 * electrons).  pdf * step^2 is the constant mesh
+            // weight up to rounding (see make_point); the reference's own expression is evaluated only where the
+            // rounding could change the truncation -- rare, so the warp then takes a second copy of the loop.
+            unsigned risky = 0u;
+            const bool careful_warp = __any_sync(FULL, careful_point);
+            if (careful_warp && careful_point) {
+#pragma unroll
+                for (int j = 0; j < MESH_N; ++j) {
+                    const double v = __dmul_rn(wrow[j], qd);
+                    if (!(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v)) && pad[j] >= 0) risky |= 1u << j;
+                }
+            }
+            const double* g = pb.geom + p * GEOM_DOUBLES;
+            auto walk_row = [&](auto careful) {
+                // j == MESH_N is the sentinel that pushes the last run of the row
+#pragma unroll
+                for (int j = 0; j <= MESH_N; ++j) {
+                    const int pj = j < MESH_N ? pad[j] : -1;
+                    long long share = 0;  // (of a pixel without pad: added to a run that is never pushed)
+                    if (j < MESH_N) {
+                        share = (long long)__dmul_rn(wrow[j], qd);
+                        if (decltype(careful)::value) {
+                            if ((risky >> j) & 1u) share = exact_share(g, row, j);
+                        }
+                        n_dep += pj >= 0;
+                    }
+                    const bool change = pj != cur;
+                    const bool push = change && cur >= 0;
+                    const unsigned m = __ballot_sync(FULL, push);
+                    if (m) {  // warp-uniform
+                        if (push) {
+                            const unsigned at = (q_tail + __popc(m & lanes_below)) & (QUEUE_SLOTS - 1);
+                            qkey[at] = keybase + (unsigned)cur;
+                            qlo[at] = (unsigned)acc;
+                            qhi[at] = (unsigned)((unsigned long long)acc >> 32);
+                        }
+                        q_tail += __popc(m);
+                        if (q_tail - q_head >= 32u) drain(32u);
+                    }
+                    if (change) {
+                        cur = pj;
+                        acc = 0;
+                    }
+                    acc += share;
+                }
+            };
+            if (careful_warp && __any_sync(FULL, risky != 0u)) walk_row(std::true_type{});
+            else walk_row(std::false_type{});
+        }
+        publish_new_keys();
+        if (*(volatile unsigned*)&s_nkeys > (unsigned)gv.spill_keys) *(volatile unsigned*)&s_flush = 1u;
+        if (__any_sync(FULL, *(volatile unsigned*)&s_flush != 0u)) {
+            __syncthreads();
+            append_segment(false);
+        }
+    }
+    while (q_tail != q_head) drain(min(32u, q_tail - q_head));
+    publish_new_keys();
+    if (*(volatile unsigned*)&s_nkeys > (unsigned)gv.spill_keys) *(volatile unsigned*)&s_flush = 1u;
+    while (true) {
+        __syncthreads();
+        if (*(volatile unsigned*)&s_flush == 0u) break;
+        append_segment(false);
+    }
+    append_segment(true);
+    unsigned long long n_dep64 = n_dep, n_probe64 = n_probe + (lane == 0 ? q_tail : 0u);  // q_tail: runs pushed = inserts
+    for (int o = 16; o > 0; o >>= 1) {
+        n_dep64 += __shfl_xor_sync(FULL, n_dep64, o);
+        n_probe64 += __shfl_xor_sync(FULL, n_probe64, o);
+    }
+    if (lane == 0 && n_dep64) {
+        atomicAdd(&ctr->deposits, n_dep64);
+        atomicAdd(&ctr->probes, n_probe64);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- finalize
 struct ReplayUniforms {
     const int64_t* offsets;  // [n_events + 1] or null
     const int64_t* keys;
@@ -1356,15 +1543,16 @@ struct FinalizeArgs {
     int32_t label_of_rank[MAX_TRACKS_PER_EVENT];
     const int32_t* label_of_event_rank;  // replay: [n_events, n_tracks_per_event] or null
     ReplayUniforms replay;
+    uint64_t* sort_items;     // [group_events][2 * hash_cap] scratch: ordered items, then unordered survivors
     unsigned* kept;           // [launch events] rows kept per event
     int64_t* offsets;         // [launch events + 1] CSR offsets (global across groups of the launch)
-    double* cloud;            // [out_cap, 3] or null (typed columns only)
-    int64_t* labels;          // [out_cap] or null
+    double* cloud;            // [out_cap, 3]
+    int64_t* labels;          // [out_cap]
     int64_t out_cap;
-    // optional columnar copy of the same rows in their natural types (11 / 15 B instead of 32 B per row on the wire).
+    // optional columnar copy of the same rows in their natural types (15 B instead of 32 B per row on the wire).
     // col_tb_q16 = (time bucket << 16) | (wiggle * 2^16): time bucket + wiggle == col_tb_q16 / 65536 exactly for the
     // library's own 16-bit wiggle; a replayed 53-bit uniform is truncated to 16 bits there (replay tests read the
-    // float64 cloud).  Null pointers are columns nobody asked for.
+    // float64 cloud).
     int16_t* col_pad;
     uint32_t* col_tb_q16;
     int64_t* col_electrons;
@@ -1396,741 +1584,201 @@ __device__ __forceinline__ double wiggle_of(const FinalizeArgs& fa, int slot_eve
     return philox_uniform16(fa.seed, (uint64_t)(fa.first_event + slot_event), STREAM_WIGGLE, key);
 }
 
-// detector/simulator.py:108-113: keep 0 <= tb + u < 512 with u in [0, 1).  Only the last bucket needs u (a replayed
-// 53-bit uniform can round 511 + u up to 512.0); emit_kernel draws the wiggle of the rows it writes.
-__device__ __forceinline__ bool keeps_row(const FinalizeArgs& fa, int slot_event, unsigned tb, unsigned pad, Counters* ctr) {
-    if ((fa.flags & F_KEEP_ALL_TB) || tb < (unsigned)NUM_TB - 1u) return true;
-    if (tb != (unsigned)NUM_TB - 1u) return false;
-    return (double)tb + wiggle_of(fa, slot_event, szudzik_pair(tb, pad), ctr) < (double)NUM_TB;
-}
-
-// ---------------------------------------------------------------------------------------- shared-memory accumulate
-constexpr int DEPOSIT_THREADS = 256;
-constexpr int DEPOSIT_WARPS = DEPOSIT_THREADS / 32;
-constexpr int POINTS_PER_WARP = 3;   // three active points per warp pass: 3 x 10 mesh rows on 30 lanes
-constexpr int POINTS_PER_ITER = DEPOSIT_WARPS * POINTS_PER_WARP;
-constexpr int QUEUE_SLOTS = 64;      // per-warp ring of finished (key, charge) runs waiting for a full 32-lane insert
-constexpr int SMEM_SLOTS = 4864;     // per-CTA table in shared memory: 10 B per slot = 47.5 KB, four CTAs per SM
-constexpr int SMEM_SPILL_DEFAULT = 1600;  // keys that trigger a flush of the finished time buckets
-constexpr int SMEM_HARD_DEFAULT = 2800;   // keys above which a flush is no longer postponed (58 % load)
-constexpr int MAX_PROBE_DEFAULT = SMEM_SLOTS;  // an insert only gives up on a table that is completely full
-constexpr int CARRY_SLOTS = 512;     // unfinished keys whose slots a flush remembers (more: found again by a rescan)
-constexpr int DEPOSIT_TABLE_WORDS = 2 * SMEM_SLOTS + SMEM_SLOTS / 2;  // key words, charge low words, charge high halves
-constexpr unsigned SMEM_KEY_MASK = 0x0FFFFFFFu;  // low 28 bits: ((tb << 15) | pad) + 1; top 4 bits: track rank
-static_assert(SMEM_SLOTS % 8 == 0, "table size: uint4 loads of the key words, 16-byte sub-arrays");
-
-// Slot word = compact key (time bucket < 8192, pad id < 32768) + 1 in the low 28 bits, 0 = empty, and in the top four
-// bits the rank of the last track that touched the slot (atomicMax: same key bits, the highest rank wins).  The charge
-// is a 48-bit sum: 32 low bits + 16 high bits packed two per word (max 2.8e14 electrons per pad and time bucket, far
-// above anything physical; overflow is flagged).
-struct SmemTable {
-    unsigned* word;   // key + rank
-    unsigned* lo;     // charge bits 0..31
-    unsigned* hi2;    // charge bits 32..47, two slots per 32-bit word
-};
-
-__device__ __forceinline__ unsigned smem_key(unsigned tb, unsigned pad) { return ((tb << 15) | pad) + 1u; }
-
-__device__ __forceinline__ unsigned smem_home(unsigned key1) {
-    // The keys of a unit form a lattice ((time bucket << 15) | pad with both running over short ranges); a plain
-    // multiplicative hash maps such a lattice onto a lattice of slots with long probe chains.  One xor-shift between
-    // two multiplications breaks that up.
-    unsigned h = key1 * 0x9E3779B1u;
-    h ^= h >> 15;
-    h *= 0x85EBCA6Bu;
-    return __umulhi(h, (unsigned)SMEM_SLOTS);  // multiply-shift range reduction, no division
-}
-
-// Find the slot of `key1`, claiming an empty one if it is new (counted in the lane's `n_new`; the warp publishes the
-// sum before every fill check).  Gives up after max_probe probes (returns SMEM_SLOTS): the caller then leaves the
-// deposit as a raw entry in the unit's region and fixup_kernel merges it later -- never reached with the default
-// thresholds (the table is flushed at 44 % load), but no input can make an insert spin or lose charge.
-__device__ __forceinline__ unsigned smem_find(const SmemTable& t, unsigned key1, unsigned rank, unsigned max_probe,
-                                              unsigned& n_new, unsigned& probes) {
-    unsigned slot = smem_home(key1);
-    bool found = false;  // (single exit: the lanes of a drain reconverge before the atomics that follow)
-#pragma unroll 1
-    for (unsigned probe = 0; probe < max_probe; ++probe) {
-        unsigned w = *(volatile unsigned*)&t.word[slot];
-        if ((w & SMEM_KEY_MASK) == key1) {  // the common case: the key is there, at its home slot
-            found = true;
-            break;
-        }
-        if (w == 0u) {
-            w = atomicCAS(&t.word[slot], 0u, key1 | (rank << 28));
-            if (w == 0u) {
-                n_new += 1u;
-                found = true;
-                break;
-            }
-            if ((w & SMEM_KEY_MASK) == key1) {
-                found = true;
-                break;
-            }
-        }
-        probes += 1u;  // (extra probes; the first probe of every insert is counted from the number of pushes)
-        slot = slot + 1u == (unsigned)SMEM_SLOTS ? 0u : slot + 1u;
-    }
-    return found ? slot : (unsigned)SMEM_SLOTS;
-}
-
-// Exact accumulate from native 32-bit shared-memory atomics (carry into the 16-bit high part).
-__device__ __forceinline__ void smem_charge(const SmemTable& t, unsigned slot, unsigned long long q, int* overflow) {
-    const unsigned vlo = (unsigned)q, vhi = (unsigned)(q >> 32);
-    unsigned carry = 0u;
-    if (vlo) carry = atomicAdd(&t.lo[slot], vlo) > ~vlo ? 1u : 0u;
-    const unsigned add = vhi + carry;
-    if (add) {
-        const unsigned shift = (slot & 1u) * 16u;
-        const unsigned old = (atomicAdd(&t.hi2[slot >> 1], add << shift) >> shift) & 0xFFFFu;
-        if (add > 0xFFFFu || old + add > 0xFFFFu) *overflow = 1;
-    }
-}
-
-__device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t, unsigned slot) {
-    const unsigned hi = (t.hi2[slot >> 1] >> ((slot & 1u) * 16u)) & 0xFFFFu;
-    return ((unsigned long long)hi << 32) | t.lo[slot];
-}
-
-// Everything a CTA of the deposit kernel keeps in (static) shared memory besides its table.
-struct DepositShared {
-    unsigned ring[3][DEPOSIT_WARPS][QUEUE_SLOTS];  // key word, charge low, charge high of the queued runs
-    double w[MESH_N][MESH_N + 1];                  // constant mesh weights, row stride 11 doubles
-    uint16_t carry[CARRY_SLOTS];                   // flush: slots of the unfinished keys
-    unsigned next[DEPOSIT_WARPS];                  // list position every warp stands at when a flush is called
-    unsigned nkeys, flush, rows, trigger, frontier, nsurv, nfinal, nsv, mode, nkept, nseg, last_pos;
-};
-
-// What the out-of-line helpers of the deposit kernel need to know about the CTA's work unit (kept in shared memory:
-// the same for every thread, and a reference to a local copy would turn every field access into a local-memory load).
-struct DepositCtx {
-    HashEntry* region;       // the unit's rows (from the bottom) and raw entries (from the top)
-    unsigned* raw_counter;
-    Counters* ctr;
-    unsigned* segend;        // ends of the unit's segments inside the region
-    const uint32_t* perm;    // the event's points in time-bucket order
-    const uint32_t* rec0;    // record of the event's first point
-    unsigned cap, max_probe;
-    int end, slot_event, spill_keys, hard_keys;
-};
-// Dynamic shared memory of a deposit CTA: the table, then DepositShared, then DepositCtx.  The out-of-line helpers
-// reach all three through the one extern array, i.e. at addresses known at compile time.
-constexpr size_t DEPOSIT_SHARED_AT = (size_t)DEPOSIT_TABLE_WORDS * sizeof(unsigned);
-constexpr size_t DEPOSIT_CTX_AT = (DEPOSIT_SHARED_AT + sizeof(DepositShared) + 15) / 16 * 16;
-constexpr size_t DEPOSIT_SMEM_BYTES = DEPOSIT_CTX_AT + sizeof(DepositCtx);
-static_assert(DEPOSIT_SMEM_BYTES + 1024 <= 233472 / 4, "four deposit CTAs per SM");
-static_assert(DEPOSIT_SHARED_AT % 16 == 0, "alignment of DepositShared");
-
-__device__ __forceinline__ unsigned* dep_smem() {
-    extern __shared__ __align__(16) unsigned s_dep[];
-    return s_dep;
-}
-__device__ __forceinline__ SmemTable dep_table() {
-    unsigned* base = dep_smem();
-    return SmemTable{base, base + SMEM_SLOTS, base + 2 * SMEM_SLOTS};
-}
-__device__ __forceinline__ DepositShared& dep_shared() {
-    return *reinterpret_cast<DepositShared*>(reinterpret_cast<unsigned char*>(dep_smem()) + DEPOSIT_SHARED_AT);
-}
-__device__ __forceinline__ DepositCtx& dep_ctx() {
-    return *reinterpret_cast<DepositCtx*>(reinterpret_cast<unsigned char*>(dep_smem()) + DEPOSIT_CTX_AT);
-}
-
-struct WarpStats {
-    unsigned n_new, n_probe, n_raw;
-};
-
-// A deposit the table could not take (or a key a flush could not finish): left as a raw entry at the top of the
-// unit's region, merged by fixup_kernel.
-__device__ __forceinline__ void raw_entry(unsigned word, unsigned long long q, unsigned& n_raw, int cause) {
-    const DepositCtx& c = dep_ctx();
-    const unsigned r = atomicAdd(c.raw_counter, 1u);
-    n_raw += 1u;
-    atomicAdd(&c.ctr->raw_by_cause[cause], 1ULL);  // (rare path)
-    if (r >= c.cap) {
-        c.ctr->overflow_hash = 1;
-        return;
-    }
-    c.region[c.cap - 1u - r] = HashEntry{word & SMEM_KEY_MASK, word >> 28, q};
-}
-
-// Whole warp: insert ring entries [q_head, q_head + n), n <= 32, one per lane.  Out of line on purpose: the call sits
-// in the unrolled pixel loop and the kernel must stay inside the instruction cache.
-__device__ __noinline__ void drain_ring(int warp, unsigned q_head, unsigned n, WarpStats& st) {
-    const int lane = threadIdx.x & 31;
-    const SmemTable t = dep_table();
-    DepositShared& sh = dep_shared();
-    __syncwarp();
-    const bool mine = (unsigned)lane < n;
-    unsigned kw = 0u, slot = (unsigned)SMEM_SLOTS;
-    unsigned long long q = 0ULL;
-    if (mine) {
-        const unsigned at = (q_head + (unsigned)lane) & (QUEUE_SLOTS - 1);
-        kw = sh.ring[0][warp][at];
-        q = ((unsigned long long)sh.ring[2][warp][at] << 32) | sh.ring[1][warp][at];
-        slot = smem_find(t, kw & SMEM_KEY_MASK, kw >> 28, dep_ctx().max_probe, st.n_new, st.n_probe);
-    }
-    __syncwarp();  // the probe loops end at different times: all lanes together again before the atomics
-    if (mine) {
-        if (slot < (unsigned)SMEM_SLOTS) {
-            smem_charge(t, slot, q, &dep_ctx().ctr->overflow_charge);
-            atomicMax(&t.word[slot], kw);  // same key bits: the highest rank wins (transporter.py:247-249)
-        } else {
-            raw_entry(kw, q, st.n_raw, 0);
-        }
-    }
-    __syncwarp();
-}
-
-// FLUSH (all threads of the CTA, after a barrier that follows every warp's drain; every point of the unit's list
-// before position `next` has been deposited, none at or after it).  Keys in time buckets below the bucket of point
-// `next` can receive nothing more (points are ordered, units never share a bucket): they are masked (0 <= tb < 512,
-// detector/simulator.py:111-113) and appended to the unit's region as one SEGMENT, in table order; emit_kernel puts
-// every segment into (time bucket, pad) order when it reads it.  Segments of successive flushes hold disjoint,
-// ascending ranges of time buckets, so their concatenation is the unit's rows.  The caller flushes at the start of
-// a time bucket whenever it can, so that normally NO key is unfinished and the table starts over empty; otherwise the
-// keys at or above the frontier are parked in global memory while the table is cleared and re-inserted.  Escapes
-// that keep every input correct: a flush that would finish less than a quarter of the keys is postponed while the
-// table has room; past `hard_keys` the unfinished keys are left as RAW entries at the top of the region, and so is
-// everything once a unit has used up its MAX_SEGMENTS segments (fixup_kernel merges and sorts such a unit).
-__device__ __noinline__ void flush_table(const SimParams& P, const FinalizeArgs& fa, bool all_final, unsigned next,
-                                         WarpStats& st) {
-    DepositShared& sh = dep_shared();
-    const DepositCtx& c = dep_ctx();
-    const SmemTable t = dep_table();
-    const int lane = threadIdx.x & 31;
-    const uint4* words4 = reinterpret_cast<const uint4*>(t.word);
-    if (threadIdx.x == 0) {
-        unsigned fb = 0xFFFFFFFFu;  // everything is final
-        if (!all_final && next < (unsigned)c.end)
-            fb = (unsigned)tb_bin(P, __ldg(c.rec0 + (int64_t)c.perm[next] * REC_WORDS) & 0x1FFFFFFFu);
-        sh.frontier = fb;
-        sh.nsurv = 0;
-        sh.nfinal = 0;
-        sh.nsv = 0;
-        sh.nkept = 0;
-        sh.mode = sh.nseg >= (unsigned)MAX_SEGMENTS ? 3u : 0u;
-    }
-    __syncthreads();
-    const unsigned fb = sh.frontier;
-    if (fb != 0xFFFFFFFFu) {
-        // (1) a flush inside a time bucket: how many keys are finished, how many are not?
-        unsigned my_surv = 0, my_final = 0;
-        for (int v = threadIdx.x; v < SMEM_SLOTS / 4; v += DEPOSIT_THREADS) {
-            const uint4 w4 = words4[v];
-            const unsigned ws[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (ws[k]) {
-                    if ((unsigned)tb_bin(P, ((ws[k] & SMEM_KEY_MASK) - 1u) >> 15) >= fb) my_surv += 1;
-                    else my_final += 1;
-                }
-        }
-        my_surv = __reduce_add_sync(FULL, my_surv);
-        my_final = __reduce_add_sync(FULL, my_final);
-        if (lane == 0) {
-            if (my_surv) atomicAdd(&sh.nsurv, my_surv);
-            if (my_final) atomicAdd(&sh.nfinal, my_final);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            // 0: append the finished keys as a segment, carry the others over; 1: postpone (little is finished yet
-            // and the table has room); 2: append the finished keys, leave the others as raw entries (only a table
-            // that fills up with the keys of ONE time bucket gets here); 3: the unit has no segment left: all raw
-            unsigned mode = 0;
-            const unsigned total = sh.nsurv + sh.nfinal;
-            atomicMax(&c.ctr->max_carried, (unsigned long long)sh.nsurv);
-            if (4u * sh.nfinal < total) mode = total <= (unsigned)c.hard_keys ? 1u : 2u;
-            if (mode != 1u && sh.nseg >= (unsigned)MAX_SEGMENTS) mode = 3u;
-            sh.mode = mode;
-            sh.nfinal = 0;  // (counted again below, for the statistics)
-        }
-        __syncthreads();
-    }
-    const unsigned mode = sh.mode;
-    if (mode == 1u) {
-        if (threadIdx.x == 0) {
-            sh.trigger = min((unsigned)c.hard_keys, sh.nkeys + (unsigned)max(c.spill_keys / 2, 1));
-            sh.flush = 0;
-            atomicAdd(&c.ctr->postponed, 1ULL);
-        }
-        __syncthreads();
-        return;
-    }
-    // (2) the finished keys that survive the mask go to the region in table order (four slots per thread and round,
-    // one shared-memory atomic per warp and round); the slots of the unfinished keys are remembered (or the keys left
-    // as raw entries)
-    const unsigned seg0 = sh.rows;
-    const unsigned room = c.cap - min(c.cap, __ldcg(c.raw_counter) + (mode >= 2u ? sh.nsurv : 0u));  // rows may not reach the raw entries
-    unsigned my_final = 0;
-    for (int v = threadIdx.x; v < SMEM_SLOTS / 4; v += DEPOSIT_THREADS) {
-        const uint4 w4 = words4[v];
-        const unsigned ws[4] = {w4.x, w4.y, w4.z, w4.w};
-        unsigned outmask = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned w = ws[k];
-            if (!w) continue;
-            const unsigned key1 = w & SMEM_KEY_MASK, tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
-            const unsigned slot = 4u * (unsigned)v + (unsigned)k;
-            const bool unfinished = (unsigned)tb_bin(P, tb) >= fb;
-            my_final += !unfinished;
-            if (mode == 3u) {
-                if (unfinished || keeps_row(fa, c.slot_event, tb, pad, c.ctr)) raw_entry(w, smem_charge_of(t, slot), st.n_raw, 2);
-            } else if (unfinished) {
-                if (mode == 2u) raw_entry(w, smem_charge_of(t, slot), st.n_raw, 1);
-                else sh.carry[atomicAdd(&sh.nsv, 1u) & (CARRY_SLOTS - 1)] = (uint16_t)slot;  // (more than CARRY_SLOTS: rescan below)
-            } else if (keeps_row(fa, c.slot_event, tb, pad, c.ctr)) {
-                outmask |= 1u << k;
-            }
-        }
-        const unsigned cnt = __popc(outmask);
-        unsigned incl = cnt;
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned x = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += x;
-        }
-        const unsigned total = __shfl_sync(FULL, incl, 31);
-        if (total) {  // warp-uniform
-            unsigned at = 0;
-            if (lane == 31) at = atomicAdd(&sh.nkept, total);
-            at = seg0 + __shfl_sync(FULL, at, 31) + incl - cnt;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if ((outmask >> k) & 1u) {
-                    const unsigned slot = 4u * (unsigned)v + (unsigned)k;
-                    if (at < room) c.region[at] = HashEntry{ws[k] & SMEM_KEY_MASK, ws[k] >> 28, smem_charge_of(t, slot)};
-                    else c.ctr->overflow_hash = 1;  // the host grows the regions and redoes the launch
-                    at += 1;
-                }
-        }
-    }
-    my_final = __reduce_add_sync(FULL, my_final);
-    if (lane == 0 && my_final) atomicAdd(&sh.nfinal, my_final);
-    __syncthreads();
-    // (3) the unfinished keys wait in global memory (in the region, above the rows just written) while the table is
-    // cleared; the first CARRY_SLOTS of them are found through the slot list, more than that by a rescan
-    const unsigned n = sh.nkept;
-    const unsigned n_sv = (mode == 0u && seg0 + n + sh.nsurv <= room) ? sh.nsurv : 0u;
-    if (mode == 0u && n_sv != sh.nsurv && threadIdx.x == 0) c.ctr->overflow_hash = 1;
-    HashEntry* parked = c.region + seg0 + n;
-    if (n_sv > (unsigned)CARRY_SLOTS) {
-        if (threadIdx.x == 0) sh.nsv = 0;
-        __syncthreads();
-        for (int slot = threadIdx.x; slot < SMEM_SLOTS; slot += DEPOSIT_THREADS) {
-            const unsigned w = t.word[slot];
-            if (!w) continue;
-            const unsigned key1 = w & SMEM_KEY_MASK;
-            if ((unsigned)tb_bin(P, (key1 - 1u) >> 15) < fb) continue;
-            parked[atomicAdd(&sh.nsv, 1u)] = HashEntry{key1, w >> 28, smem_charge_of(t, slot)};
-        }
-    } else {
-        for (unsigned i = threadIdx.x; i < n_sv; i += DEPOSIT_THREADS) {
-            const unsigned slot = sh.carry[i];
-            const unsigned w = t.word[slot];
-            parked[i] = HashEntry{w & SMEM_KEY_MASK, w >> 28, smem_charge_of(t, slot)};
-        }
-    }
-    __syncthreads();
-    {
-        uint4* v = reinterpret_cast<uint4*>(t.word);
-        for (int i = threadIdx.x; i < DEPOSIT_TABLE_WORDS / 4; i += DEPOSIT_THREADS) v[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    if (threadIdx.x == 0) {
-        if (n > 0u && seg0 + n <= room) {  // one more segment
-            c.segend[sh.nseg] = seg0 + n;
-            sh.nseg += 1;
-            sh.rows = seg0 + n;
-        }
-        sh.nkeys = n_sv;
-        sh.trigger = min((unsigned)c.hard_keys, n_sv + (unsigned)c.spill_keys);
-        sh.last_pos = min(next, (unsigned)c.end);
-        sh.flush = 0;
-        atomicAdd(&c.ctr->keys, (unsigned long long)sh.nfinal);
-        atomicMax(&c.ctr->max_keys, (unsigned long long)(sh.nfinal + sh.nsurv));
-        if (next < (unsigned)c.end) atomicAdd(&c.ctr->flushes, 1ULL);
-    }
-    __syncthreads();
-    for (unsigned i = threadIdx.x; i < n_sv; i += DEPOSIT_THREADS) {
-        const HashEntry en = parked[i];
-        const unsigned w = en.key1 | (en.rank << 28);
-        unsigned slot = smem_home(en.key1);
-        while (atomicCAS(&t.word[slot], 0u, w) != 0u) slot = slot + 1u == (unsigned)SMEM_SLOTS ? 0u : slot + 1u;  // distinct keys
-        t.lo[slot] = (unsigned)en.charge;
-        const unsigned hi = (unsigned)(en.charge >> 32);
-        if (hi) atomicAdd(&t.hi2[slot >> 1], hi << ((slot & 1u) * 16u));
-    }
-    __syncthreads();
-}
-
-// One CTA per work unit = a time-bucket range of one event, all tracks together, points in ascending time-bucket
-// order (event_sort_kernel).  Label = last track in `indices` order to touch a key, detector/transporter.py:166-169,
-// 247-249 = the highest rank, kept with an atomicMax.
-//
-// A warp takes three active points per pass; lane (s, i) owns row i (one x of the 10x10 mesh) of point s and walks
-// the ten y of that row in the reference's pixel order.  Neighbouring pixels of a row usually fall on the same pad, so
-// the lane sums the integer shares of such a run in registers (integer adds commute and every share is truncated
-// on its own first, exactly as transporter.py:240-248 does) and only a finished run (key, charge) is pushed into the
-// warp's ring in shared memory.  Whenever the ring holds 32 runs, all 32 lanes insert one each into the CTA's
-// open-addressing table (drain_ring): the insert code (probe loop, two atomics) runs once per 32 runs instead of once
-// per 32 pixels.
-//
-// Warps run freely; a warp that sees the table filling up raises `flush`, every warp notices at its next pass
-// boundary and they meet at a barrier.  The warps behind then catch up with the leading one, so that the flush
-// (flush_table) sees every point before ONE list position deposited and none after it.
-__global__ void __launch_bounds__(DEPOSIT_THREADS, 4)
-deposit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, PointBuf pb,
-               GroupView chunk, Counters* ctr) {
-    const GroupView gv = sub_group(chunk, blockIdx.y);
-    if ((int)blockIdx.x >= pb.n_units[gv.group] || ctr->overflow_points) return;
-    unsigned* s_raw = dep_smem();
-    DepositShared& sh = dep_shared();
-    DepositCtx& c = dep_ctx();
-    const int64_t ubase = (int64_t)gv.group * pb.max_units;
-    const int unit = pb.unit_order[ubase + blockIdx.x];
-    const int e = pb.unit_event[ubase + unit];
-    const int u_first = pb.unit_first[ubase + unit], u_count = pb.unit_count[ubase + unit];
-    const int slot_event = gv.first_slot + e;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t base = (int64_t)gv.group * pb.group_cap + pb.start[(int64_t)slot_event * pb.ranks];  // first record (and perm entry) of the event
-    const int end = u_first + u_count;
-    const uint32_t* perm = pb.perm + base;
-    const uint32_t* rec0 = pb.rec + base * REC_WORDS;
-    if (threadIdx.x == 0) {
-        c.region = gv.tables + ((int64_t)gv.chunk_group * pb.max_units + unit) * gv.hash_cap;
-        c.raw_counter = pb.unit_raw + ubase + unit;
-        c.segend = pb.unit_segend + (ubase + unit) * MAX_SEGMENTS;
-        c.ctr = ctr;
-        c.perm = perm;
-        c.rec0 = rec0;
-        c.cap = (unsigned)gv.hash_cap;
-        c.max_probe = (unsigned)gv.max_probe;
-        c.end = end;
-        c.slot_event = slot_event;
-        c.spill_keys = gv.spill_keys;
-        c.hard_keys = gv.hard_keys;
-    }
-    {
-        uint4* v = reinterpret_cast<uint4*>(s_raw);
-        for (int i = threadIdx.x; i < DEPOSIT_TABLE_WORDS / 4; i += DEPOSIT_THREADS) v[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    if (threadIdx.x == 0) {
-        sh.nkeys = 0;
-        sh.flush = 0;
-        sh.rows = 0;
-        sh.trigger = (unsigned)min(gv.spill_keys, gv.hard_keys);
-        sh.nseg = 0;
-        sh.last_pos = (unsigned)u_first;
-    }
-    // constant mesh weights: the rows differ from lane to lane, so they are read from shared memory (row stride 11
-    // doubles: the ten rows start in ten different bank pairs), not through the constant cache
-    for (int k = threadIdx.x; k < MESH_N * MESH_N; k += DEPOSIT_THREADS) sh.w[k / MESH_N][k % MESH_N] = P.mesh_w[k];
-    __syncthreads();
-    WarpStats st{0u, 0u, 0u};
-    unsigned n_dep = 0;
-    const int sub = lane / MESH_N;                                  // point of the warp's triple; 3 = idle lanes 30, 31
-    const int row = lane - sub * MESH_N;                            // mesh row (x index) of this lane
-    const double* wrow = sh.w[row];
-    const bool exact_mesh = gv.exact_mesh != 0;
-    unsigned* qkey = sh.ring[0][warp];
-    unsigned* qlo = sh.ring[1][warp];
-    unsigned* qhi = sh.ring[2][warp];
-    unsigned q_head = 0, q_tail = 0;  // warp-uniform ring positions
-    const unsigned lanes_below = lanemask_lt();
-    auto drain_all = [&]() {
-        while (q_tail != q_head) {
-            const unsigned n = min(32u, q_tail - q_head);
-            drain_ring(warp, q_head, n, st);
-            q_head += n;
-        }
-    };
-    auto publish_new_keys = [&]() {  // whole warp, before a barrier that precedes a read of sh.nkeys
-        const unsigned total = __reduce_add_sync(FULL, st.n_new);
-        if (lane == 0 && total) atomicAdd(&sh.nkeys, total);
-        st.n_new = 0;
-    };
-    int p0 = u_first;
-    unsigned target = 0;      // > 0: a flush has been called for list position `target`; this warp is catching up
-    bool clean = false;       // ... and `target` is the start of a time bucket: no key will be unfinished there
-    bool closing = false;     // the points are done: the last flush is being arranged
-    while (true) {
-        if (p0 < end) {
-            // ---- this warp's three points of the CTA pass that starts at list position p0 (a pass before a flush
-            // stops at the flush position; the next one starts there)
-            const int limit = target ? min(end, (int)target) : end;
-            const int w0 = p0 + warp * POINTS_PER_WARP;
-            if (w0 < limit) {  // warp-uniform
-                const int pp = w0 + sub;
-                const bool have = sub < POINTS_PER_WARP && pp < limit;
-                const int64_t p = (int64_t)__ldg(perm + (have ? pp : w0));
-                const uint4* rp = reinterpret_cast<const uint4*>(rec0 + p * REC_WORDS);
-                uint4 head = __ldg(rp);
-                if (!have) head.x = 0u;
-                const unsigned r = __ldg(rec0 + p * REC_WORDS + 14);  // rank of the point's track
-                const int kind = (int)(head.x >> 30), tb = (int)(head.x & 0x1FFFFFFFu);
-                const bool careful_point = (head.x >> 29) & 1u;
-                const unsigned keybase = (((unsigned)tb << 15) + 1u) | (r << 28);  // + pad = slot word
-                const double qd = kind == 2 ? __hiloint2double((int)head.w, (int)head.z) : 0.0;
-                const double guard = exact_mesh ? 2.0 : (double)__uint_as_float(head.y);
-                int cur = -1;         // pad of the run being summed
-                long long acc = 0;    // its charge so far
-                int pad[MESH_N];
-#pragma unroll
-                for (int j = 0; j < MESH_N; ++j) pad[j] = -1;
-                if (kind != 0) {
-                    // pad-table row of this lane's mesh row, columns of the ten mesh columns (make_point)
-                    const uint4 cols = __ldg(rp + 1);
-                    const uint2 tail = __ldg(reinterpret_cast<const uint2*>(rp + 2));  // iy[8], iy[9] | ix[0], ix[1]
-                    const int ix = (int)__ldg(reinterpret_cast<const int16_t*>(rp) + 18 + row);
-                    const unsigned cw[5] = {cols.x, cols.y, cols.z, cols.w, tail.x};
-                    const int16_t* lut_row = P.lut + (int64_t)max(ix, 0) * P.lut_n;
-                    if (kind == 2) {
-#pragma unroll
-                        for (int j = 0; j < MESH_N; ++j) {  // all pad lookups first: independent loads in flight
-                            const int iy = (j & 1) ? (int)cw[j / 2] >> 16 : (int)(int16_t)(cw[j / 2] & 0xFFFFu);
-                            if (ix >= 0 && iy >= 0) pad[j] = (int)__ldg(lut_row + iy);
-                        }
-                    } else if (row == 0) {  // detector/transporter.py:123-169: all electrons on one pad
-                        const int iy = (int)(int16_t)(cw[0] & 0xFFFFu);
-                        if (ix >= 0 && iy >= 0) cur = (int)__ldg(lut_row + iy);
-                        acc = (long long)__hiloint2double((int)head.w, (int)head.z);
-                        n_dep += cur >= 0;
-                    }
-                }
-                // detector/transporter.py:240-246: int(pdf * step^2 * electrons).  pdf * step^2 is the constant mesh
-                // weight up to rounding (see make_point); the reference's own expression is evaluated only where the
-                // rounding could change the truncation (rare).
-                unsigned risky = 0u;
-                if (__any_sync(FULL, careful_point) && careful_point) {
-#pragma unroll
-                    for (int j = 0; j < MESH_N; ++j) {
-                        const double v = __dmul_rn(wrow[j], qd);
-                        if (!(fabs(__dsub_rn(v, rint(v))) > __dmul_rn(guard, v)) && pad[j] >= 0) risky |= 1u << j;
-                    }
-                }
-                const bool any_risky = __any_sync(FULL, risky != 0u);
-                const double* g = pb.geom + (base + p) * GEOM_DOUBLES;
-                // j == MESH_N is the sentinel that pushes the last run of the row
-#pragma unroll
-                for (int j = 0; j <= MESH_N; ++j) {
-                    const int pj = j < MESH_N ? pad[j] : -1;
-                    long long share = 0;  // (of a pixel without pad: added to a run that is never pushed)
-                    if (j < MESH_N) {
-                        share = (long long)__dmul_rn(wrow[j], qd);
-                        if (any_risky && ((risky >> j) & 1u)) share = exact_share(g, row, j);
-                        n_dep += pj >= 0;
-                    }
-                    const bool change = pj != cur;
-                    const bool push = change && cur >= 0;
-                    const unsigned m = __ballot_sync(FULL, push);
-                    if (m) {  // warp-uniform
-                        if (push) {
-                            const unsigned at = (q_tail + __popc(m & lanes_below)) & (QUEUE_SLOTS - 1);
-                            qkey[at] = keybase + (unsigned)cur;
-                            qlo[at] = (unsigned)acc;
-                            qhi[at] = (unsigned)((unsigned long long)acc >> 32);
-                        }
-                        q_tail += __popc(m);
-                        if (q_tail - q_head >= 32u) {
-                            drain_ring(warp, q_head, 32u, st);
-                            q_head += 32u;
-                        }
-                    }
-                    if (change) {
-                        cur = pj;
-                        acc = 0;
-                    }
-                    acc += share;
-                }
-            }
-            p0 += POINTS_PER_ITER;
-            publish_new_keys();
-            if (target == 0u && *(volatile unsigned*)&sh.nkeys > *(volatile unsigned*)&sh.trigger)
-                *(volatile unsigned*)&sh.flush = 1u;
-        }
-        // ---- meet the other warps?  (every path below that reaches a barrier is taken by all warps of the CTA together)
-        if (target == 0u) {
-            const bool done = p0 >= end;
-            if (!done && !__any_sync(FULL, *(volatile unsigned*)&sh.flush != 0u)) continue;
-            if (done && !closing) {  // the first time: nothing of this warp may stay in its ring
-                drain_all();
-                publish_new_keys();
-                closing = true;
-            }
-            if (lane == 0) sh.next[warp] = done ? 0xFFFFFFFFu : (unsigned)p0;
-            __syncthreads();
-            unsigned lead = 0, all_done = 1;
-            for (int w = 0; w < DEPOSIT_WARPS; ++w) {
-                lead = max(lead, min(sh.next[w], (unsigned)end));
-                all_done &= sh.next[w] == 0xFFFFFFFFu;
-            }
-            const bool wanted = *(volatile unsigned*)&sh.flush != 0u;
-            __syncthreads();  // (sh.next may be rewritten only after everybody has read it)
-            if (!wanted && !all_done) continue;  // a finished warp waiting for the others: back to the barrier
-            if (all_done) {  // every point of the unit is in the table: the last flush(es)
-                flush_table(P, fa, true, 0xFFFFFFFFu, st);
-                break;
-            }
-            // The warps behind catch up with the leading one first -- and all go on to the start of the next time
-            // bucket if that is near: a flush there leaves no key unfinished and the table starts over empty.
-            target = lead;
-            clean = lead >= (unsigned)end;
-            if (!clean) {
-                const unsigned boundary = __ldg(pb.tbend + base + lead);  // (<= end: a unit ends at a bucket boundary)
-                const unsigned keys_now = *(volatile unsigned*)&sh.nkeys;  // (nobody inserts between the two barriers)
-                const unsigned per_point = keys_now / max(lead - sh.last_pos, 1u) + 1u;  // keys a point has brought so far
-                if (keys_now + (boundary - lead) * per_point <= (unsigned)gv.hard_keys) {
-                    target = boundary;
-                    clean = true;
-                }
-            }
-        }
-        if ((unsigned)p0 >= target || p0 >= end) {
-            drain_all();
-            publish_new_keys();
-            __syncthreads();
-            flush_table(P, fa, clean, target, st);
-            p0 = (int)target;  // every warp goes on from the flush position
-            target = 0u;
-            closing = false;
-        }
-    }
-    if (threadIdx.x == 0) {
-        const unsigned rows = sh.rows;
-        const unsigned raw = atomicAdd(pb.unit_raw + ubase + unit, 0u);
-        pb.unit_kept[ubase + unit] = rows;
-        pb.unit_nseg[ubase + unit] = sh.nseg;
-        if (rows) atomicAdd(&fa.kept[slot_event], rows);
-        if (rows + raw > (unsigned)gv.hash_cap) ctr->overflow_hash = 1;
-        if (raw) {  // fixup_kernel merges the raw entries into the rows
-            const unsigned d = atomicAdd(&pb.dirty[0], 1u);
-            if ((int)d < pb.dirty_cap) pb.dirty[2 + d] = (unsigned)(gv.group * pb.max_units + unit);
-            atomicAdd(&ctr->dirty_units, 1ULL);
-        }
-    }
-    unsigned long long n_dep64 = n_dep, n_probe64 = st.n_probe + (lane == 0 ? q_tail : 0u);  // q_tail: runs pushed = inserts
-    unsigned long long n_raw64 = st.n_raw;
-    for (int o = 16; o > 0; o >>= 1) {
-        n_dep64 += __shfl_xor_sync(FULL, n_dep64, o);
-        n_probe64 += __shfl_xor_sync(FULL, n_probe64, o);
-        n_raw64 += __shfl_xor_sync(FULL, n_raw64, o);
-    }
-    if (lane == 0 && n_dep64) {
-        atomicAdd(&ctr->deposits, n_dep64);
-        atomicAdd(&ctr->probes, n_probe64);
-    }
-    if (lane == 0 && n_raw64) atomicAdd(&ctr->raw_entries, n_raw64);
-}
-
-// ---------------------------------------------------------------------------------------------------- finalize
 constexpr int FINALIZE_THREADS = 256;
-constexpr int FIXUP_SMEM_ITEMS = 4096;  // 32 KB of shared memory; larger units sort in a global scratch slab
+constexpr int SORT_SMEM_ITEMS = 6144;  // 48 KB of shared memory for the in-CTA ordering
+constexpr int TB_BINS = 1024;          // counting-sort bins over the integer time bucket (last bin collects tb >= 1023)
 
-// Canonical row order of an event: ascending (time bucket, pad).  64-bit item = (key1 << 32) | position in the region.
+// Canonical row order of an event: ascending (time bucket, pad).  64-bit item = (tb << 47) | (pad << 32) | slot
+// (pad ids are int16 in the pad grid, so 15 bits hold them).
+__device__ __forceinline__ uint64_t make_item(unsigned tb, unsigned pad, unsigned slot) {
+    return ((uint64_t)tb << 47) | ((uint64_t)pad << 32) | (uint64_t)slot;
+}
 
-// The rare unit that could not finish all its keys in shared memory (raw entries at the top of its region): merge
-// the copies of a key (integer adds commute, the label is a maximum), apply the time-bucket mask to the raw entries
-// and restore the canonical order.  A few persistent CTAs walk the list of such units; speed is not a concern here,
-// any input must come out right.
-struct FixupArgs {
-    uint64_t* scratch_items;  // [grid][2 * hash_cap]
-    HashEntry* scratch_rows;  // [grid][hash_cap]
-};
-
+// One CTA per event: gather the occupied slots that survive the time-bucket mask (detector/simulator.py:104-113)
+// and put them in canonical order: counting sort on the time bucket (exact, O(n)), then rank-by-counting inside each
+// bucket's handful of pads.  No power-of-two padding and no dependence on which thread found which slot.
 __global__ void __launch_bounds__(FINALIZE_THREADS)
-fixup_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, PointBuf pb, GroupView chunk,
-             FixupArgs fx, Counters* ctr) {
+collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView chunk,
+               Counters* ctr) {
+    const GroupView gv = sub_group(chunk, blockIdx.y);
+    if ((int)blockIdx.x >= gv.n_events) return;
     extern __shared__ uint64_t s_items[];
-    __shared__ unsigned s_unit, s_count;
-    if (ctr->overflow_points | ctr->overflow_hash) return;
-    const unsigned n_dirty = min(pb.dirty[0], (unsigned)pb.dirty_cap);
-    const unsigned cap = (unsigned)chunk.hash_cap;
-    while (true) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_unit = atomicAdd(&pb.dirty[1], 1u);
-        __syncthreads();
-        if (s_unit >= n_dirty) return;
-        const unsigned id = pb.dirty[2 + s_unit];
-        const int group = (int)(id / (unsigned)pb.max_units), unit = (int)(id % (unsigned)pb.max_units);
-        const int dy = group - chunk.group;
-        const GroupView gv = sub_group(chunk, dy);
-        const int64_t ubase = (int64_t)group * pb.max_units;
-        const int slot_event = gv.first_slot + pb.unit_event[ubase + unit];
-        HashEntry* region = gv.tables + ((int64_t)dy * pb.max_units + unit) * gv.hash_cap;
-        const unsigned n_rows = pb.unit_kept[ubase + unit], n_raw = min(pb.unit_raw[ubase + unit], cap);
-        // items: finished rows first, then the raw entries that survive the mask
-        unsigned n_all = n_rows + n_raw, n2 = 1;
-        while (n2 < n_all) n2 <<= 1;
-        uint64_t* items = n2 <= (unsigned)FIXUP_SMEM_ITEMS ? s_items : fx.scratch_items + (int64_t)blockIdx.x * 2 * cap;
-        HashEntry* out = fx.scratch_rows + (int64_t)blockIdx.x * cap;
-        for (unsigned i = threadIdx.x; i < n2; i += blockDim.x) {
-            uint64_t it = ~0ULL;  // padding sorts last
-            if (i < n_all) {
-                const unsigned at = i < n_rows ? i : cap - 1u - (i - n_rows);
-                const unsigned key1 = region[at].key1;
-                const unsigned tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
-                if (i < n_rows || keeps_row(fa, slot_event, tb, pad, ctr)) it = ((uint64_t)key1 << 32) | at;
-            }
-            items[i] = it;
+    __shared__ unsigned s_hist[TB_BINS + 1];
+    __shared__ unsigned s_fill[TB_BINS];
+    __shared__ unsigned s_n, s_keys;
+    const int e = blockIdx.x;
+    const int slot_event = gv.first_slot + e;
+    if (ctr->overflow_points | ctr->overflow_hash) {  // this attempt is void: nothing below may be trusted
+        if (threadIdx.x == 0) fa.kept[slot_event] = 0u;
+        return;
+    }
+    const HashEntry* tab = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
+    uint64_t* sorted = fa.sort_items + (int64_t)(gv.chunk_e0 + e) * 2 * gv.hash_cap;  // final order, read by emit_kernel
+    uint64_t* stash = sorted + gv.hash_cap;                           // unordered survivors
+    for (int i = threadIdx.x; i <= TB_BINS; i += blockDim.x) s_hist[i] = 0;
+    if (threadIdx.x == 0) {
+        s_n = 0;
+        s_keys = 0;
+    }
+    __syncthreads();
+    unsigned occupied = 0;
+    const bool dup = gv.mode[slot_event] != 0u;  // the list may hold a key several times
+    const int limit = (int)min(gv.n_entries[slot_event], (unsigned)gv.hash_cap);
+    auto take = [&](int i, unsigned key1) {
+        if (key1 == 0u) return;
+        occupied += 1;
+        const unsigned tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
+        // detector/simulator.py:108-113: keep 0 <= tb + u < 512 with u in [0, 1).  Only the last bucket needs u (a
+        // replayed 53-bit uniform can round 511 + u up to 512.0); emit_kernel draws the wiggle of the rows it writes.
+        bool keep = (fa.flags & F_KEEP_ALL_TB) || tb < (unsigned)NUM_TB - 1u;
+        if (!keep && tb == (unsigned)NUM_TB - 1u) {
+            const unsigned key = szudzik_pair(tb, pad);  // detector/pairing.py: id of the (tb, pad) cell
+            keep = (double)tb + wiggle_of(fa, slot_event, key, ctr) < (double)NUM_TB;
         }
-        __syncthreads();
-        for (unsigned k = 2; k <= n2; k <<= 1)
-            for (unsigned j = k >> 1; j > 0; j >>= 1) {
-                for (unsigned i = threadIdx.x; i < n2; i += blockDim.x) {
-                    const unsigned l = i ^ j;
-                    if (l > i) {
-                        const uint64_t a = items[i], b = items[l];
-                        if ((a > b) == ((i & k) == 0)) {
-                            items[i] = b;
-                            items[l] = a;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
-        // heads of the runs of equal keys, compacted in order (single pass: a running count in shared memory)
-        if (threadIdx.x == 0) s_count = 0;
-        __syncthreads();
-        for (unsigned start = 0; start < n_all; start += blockDim.x) {
-            const unsigned i = start + threadIdx.x;
-            const uint64_t it = i < n_all ? items[i] : ~0ULL;
-            const bool live = it != ~0ULL;
-            const unsigned key1 = (unsigned)(it >> 32);
-            const bool head = live && (i == 0 || (unsigned)(items[i - 1] >> 32) != key1);
-            HashEntry en{};
-            if (head) {
-                en = region[(unsigned)it];
-                for (unsigned j = i + 1; j < n_all && (unsigned)(items[j] >> 32) == key1; ++j) {
-                    const HashEntry other = region[(unsigned)items[j]];
-                    en.charge += other.charge;
-                    en.rank = max(en.rank, other.rank);
-                }
-            }
-            // block-wide exclusive count of the heads of this tile
-            const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-            __shared__ unsigned s_w[FINALIZE_THREADS / 32];
-            const unsigned m = __ballot_sync(FULL, head);
-            if (lane == 0) s_w[warp] = __popc(m);
-            __syncthreads();
-            unsigned pos = s_count + __popc(m & ((1u << lane) - 1u));
-            for (unsigned w = 0; w < warp; ++w) pos += s_w[w];
-            if (head) out[pos] = en;
-            __syncthreads();
-            if (threadIdx.x == blockDim.x - 1) s_count = pos + (head ? 1u : 0u);
-            __syncthreads();
+        if (keep) {
+            atomicAdd(&s_hist[min(tb, (unsigned)TB_BINS - 1u)], 1u);
+            stash[atomicAdd(&s_n, 1u)] = make_item(tb, pad, (unsigned)i);
         }
-        const unsigned n_final = s_count;
-        for (unsigned i = threadIdx.x; i < n_final; i += blockDim.x) region[i] = out[i];
+    };
+    for (int i0 = threadIdx.x; i0 < limit; i0 += 4 * blockDim.x) {  // four loads in flight per thread
+        unsigned k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            k[u] = i < limit ? tab[i].key1 : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) take(i0 + u * (int)blockDim.x, k[u]);
+    }
+    if (occupied) atomicAdd(&s_keys, occupied);
+    __syncthreads();
+    const int n = (int)s_n;
+    if (threadIdx.x == 0) {
+        fa.kept[slot_event] = (unsigned)n;  // (events with copies: corrected after the merge below)
+        atomicAdd(&ctr->keys, (unsigned long long)s_keys);
+    }
+    if (n == 0) return;
+    // exclusive scan of the histogram: 4 bins per thread, warp scan, carry across warps through shared memory
+    {
+        const int b0 = threadIdx.x * (TB_BINS / FINALIZE_THREADS);
+        unsigned local[TB_BINS / FINALIZE_THREADS], sum = 0;
+#pragma unroll
+        for (int k = 0; k < TB_BINS / FINALIZE_THREADS; ++k) {
+            local[k] = s_hist[b0 + k];
+            sum += local[k];
+        }
+        unsigned incl = sum;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __shared__ unsigned s_warp[FINALIZE_THREADS / 32];
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned base = incl - sum;
+        for (int w = 0; w < warp; ++w) base += s_warp[w];
+#pragma unroll
+        for (int k = 0; k < TB_BINS / FINALIZE_THREADS; ++k) {
+            s_hist[b0 + k] = base;
+            s_fill[b0 + k] = base;
+            base += local[k];
+        }
+        if (threadIdx.x == FINALIZE_THREADS - 1) s_hist[TB_BINS] = base;
+        __syncthreads();
+    }
+    const bool in_smem = n <= SORT_SMEM_ITEMS;
+    uint64_t* buf = in_smem ? s_items : sorted;  // bucketed, unordered inside a bucket
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {  // four loads in flight per thread
+        uint64_t it[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * (int)blockDim.x;
+            it[u] = i < n ? stash[i] : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (i0 + u * (int)blockDim.x < n)
+                buf[atomicAdd(&s_fill[min((unsigned)(it[u] >> 47), (unsigned)TB_BINS - 1u)], 1u)] = it[u];
+    }
+    __syncthreads();
+    // order every bucket: one thread per item counts the smaller pads of its bucket (items are distinct; a bucket
+    // holds the pads hit in one time bucket, a handful for most tracks, so neighbouring threads walk the same few
+    // items and the reads are broadcasts)
+    uint64_t* dst = in_smem ? sorted : stash;
+    const uint32_t* key_words = reinterpret_cast<const uint32_t*>(buf) + 1;  // (tb << 15) | pad of item j at [2 j]
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t v = buf[i];
+        const unsigned bin = min((unsigned)(v >> 47), (unsigned)TB_BINS - 1u);
+        const int lo = (int)s_hist[bin], hi = (int)s_hist[bin + 1];
+        int rank = 0;
+        if (!dup) {  // distinct keys: compare the (time bucket, pad) words only
+            const uint32_t vp = (uint32_t)(v >> 32);
+#pragma unroll 4
+            for (int j = lo; j < hi; ++j) rank += key_words[2 * j] < vp;
+        } else {  // whole items: copies of a key are ordered by their position in the list
+            for (int j = lo; j < hi; ++j) rank += buf[j] < v;
+        }
+        dst[lo + rank] = v;
+    }
+    int n_final = n;
+    if (dup) {
+        // Copies of a key are now neighbours.  The first one becomes the row: it takes the summed charge and the
+        // highest rank (written into its own list entry, which emit_kernel reads), the others are dropped and the
+        // sequence is compacted in place, 256 items at a time.
+        HashEntry* wtab = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
+        __shared__ unsigned s_wsum[FINALIZE_THREADS / 32];
+        __shared__ unsigned s_done, s_prev_key;
         if (threadIdx.x == 0) {
-            pb.unit_kept[ubase + unit] = n_final;
-            pb.unit_nseg[ubase + unit] = 0u;  // emit_kernel: these rows are in final order
-            if (n_final >= n_rows) atomicAdd(&fa.kept[slot_event], n_final - n_rows);
-            else atomicSub(&fa.kept[slot_event], n_rows - n_final);
+            s_done = 0;
+            s_prev_key = 0xFFFFFFFFu;  // no item has this key word (time bucket < 1024)
         }
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int start = 0; start < n; start += FINALIZE_THREADS) {
+            const int i = start + threadIdx.x;
+            const uint64_t v = i < n ? dst[i] : 0ull;
+            const uint32_t kw = i < n ? (uint32_t)(v >> 32) : 0xFFFFFFFEu;
+            // neighbours' keys from the lanes beside; only the edge lanes of a warp read them from memory
+            uint32_t before = __shfl_up_sync(FULL, kw, 1), after = __shfl_down_sync(FULL, kw, 1);
+            if (lane == 0 && i < n) before = threadIdx.x == 0 ? s_prev_key : (uint32_t)(dst[i - 1] >> 32);
+            if (lane == 31) after = i + 1 < n ? (uint32_t)(dst[i + 1] >> 32) : 0xFFFFFFFEu;
+            const bool head = i < n && kw != before;
+            if (head && after == kw) {  // copies follow (rare): fold them into this entry
+                unsigned long long extra = 0;
+                unsigned rank = wtab[(unsigned)v].rank;
+                for (int j = i + 1; j < n && (uint32_t)(dst[j] >> 32) == kw; ++j) {
+                    const HashEntry other = wtab[(unsigned)dst[j]];
+                    extra += other.charge;
+                    rank = max(rank, other.rank);
+                }
+                wtab[(unsigned)v].charge += extra;
+                wtab[(unsigned)v].rank = rank;
+            }
+            const unsigned heads = __ballot_sync(FULL, head);
+            if (lane == 0) s_wsum[warp] = __popc(heads);
+            __syncthreads();  // every read of this tile (and of its right neighbours) is done
+            unsigned pos = s_done + __popc(heads & ((1u << lane) - 1u));
+            for (int w = 0; w < warp; ++w) pos += s_wsum[w];
+            if (head) dst[pos] = v;
+            __syncthreads();
+            if (threadIdx.x == FINALIZE_THREADS - 1) {
+                unsigned total = pos + (head ? 1u : 0u);  // last thread: its prefix covers the whole tile
+                s_done = total;
+                if (i < n) s_prev_key = (uint32_t)(v >> 32);
+            }
+            __syncthreads();
+        }
+        n_final = (int)s_done;
+        if (threadIdx.x == 0) fa.kept[slot_event] = (unsigned)n_final;
+    }
+    if (!in_smem) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_final; i += blockDim.x) sorted[i] = stash[i];
     }
 }
 
-// Exclusive scan of the kept counts of a chunk of groups onto the running CSR total (single CTA).
+// Exclusive scan of the kept counts of one group onto the running CSR total (single CTA).
 __global__ void __launch_bounds__(1024)
 scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr, unsigned long long* csr_total) {
     __shared__ unsigned long long s_part[1024];
@@ -2138,10 +1786,9 @@ scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr, unsigned long long* cs
     const int tid = threadIdx.x;
     if (tid == 0) s_base = *csr_total;
     __syncthreads();
-    const bool bad = ctr->overflow_points | ctr->overflow_hash;  // this attempt is void: nothing may be trusted
     for (int start = 0; start < gv.n_events; start += 1024) {
         const int i = start + tid;
-        const unsigned long long v = i < gv.n_events && !bad ? fa.kept[gv.first_slot + i] : 0ULL;
+        const unsigned long long v = i < gv.n_events ? fa.kept[gv.first_slot + i] : 0ULL;
         s_part[tid] = v;
         __syncthreads();
         for (int o = 1; o < 1024; o <<= 1) {
@@ -2162,226 +1809,53 @@ scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr, unsigned long long* cs
     }
 }
 
-// One CTA per work unit.  Its region holds the unit's rows as SEGMENTS (one per flush of the deposit kernel) that cover
-// disjoint, ascending ranges of time buckets; the units of an event are consecutive and ascending in time bucket, so
-// the event's rows are the concatenation of all those segments once every segment is in (time bucket, pad) order.
-// Per segment: counting sort on the time bucket in shared memory (histogram, scan, scatter of the entry indices),
-// then one warp per bucket orders its pads through a bitmap over the pad ids: all keys of a bucket share the time
-// bucket, so the place of a pad is the bucket's start plus the number of smaller pads present (prefix population
-// count).  Linear in the number of rows, whatever the shape of the event.  Then [pad, tb + u, electrons] rows and labels
-// (detector/simulator.py:19-49, 104-115) and / or the typed columns are written at their final places.
-constexpr int EMIT_SEG_CAP = SMEM_SLOTS;   // a segment is one table: at most SMEM_SLOTS entries
-constexpr int EMIT_BINS = 1024;            // time buckets of a segment relative to its first one; the last bin collects
-                                           // everything above (ordered by full key there)
-constexpr int EMIT_WARPS = FINALIZE_THREADS / 32;
-constexpr int BITMAP_PADS = 10240;         // pad ids the bitmap covers (the AT-TPC pad plane); larger pad maps: by counting
-constexpr int BITMAP_WORDS = BITMAP_PADS / 32;
-static_assert(BITMAP_WORDS % 32 == 0 && BITMAP_WORDS / 32 == 10, "lane l owns bitmap words 10 l .. 10 l + 9");
-
-struct EmitShared {
-    unsigned key[EMIT_SEG_CAP];            // key word of every entry of the segment; later its place in the segment
-    uint16_t list[EMIT_SEG_CAP];           // entry indices bucket by bucket
-    unsigned hist[EMIT_BINS];              // entries per bucket -> bucket ends
-    unsigned bitmap[EMIT_WARPS][BITMAP_WORDS];
-    uint16_t prefix[EMIT_WARPS][BITMAP_WORDS];  // pads present below each bitmap word
-    unsigned wsum[EMIT_WARPS];
-    unsigned lo_tb;
-};
-
+// One CTA per event: write [pad, tb + u, electrons] rows and labels in ascending (time bucket, pad) order
+// (detector/simulator.py:19-49, 104-115).
 __global__ void __launch_bounds__(FINALIZE_THREADS)
-emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, PointBuf pb, GroupView chunk,
+emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView chunk,
             Counters* ctr) {
-    extern __shared__ __align__(16) unsigned char s_emit_raw[];
-    EmitShared& sh = *reinterpret_cast<EmitShared*>(s_emit_raw);
     const GroupView gv = sub_group(chunk, blockIdx.y);
-    if ((int)blockIdx.x >= pb.n_units[gv.group] || (ctr->overflow_points | ctr->overflow_hash)) return;
-    const int64_t ubase = (int64_t)gv.group * pb.max_units;
-    const int unit = blockIdx.x;
-    const int slot_event = gv.first_slot + pb.unit_event[ubase + unit];
-    const int n = (int)pb.unit_kept[ubase + unit];
-    if (n == 0) return;
-    int64_t off = fa.offsets[slot_event];
-    for (int u = pb.event_unit0[slot_event]; u < unit; ++u) off += pb.unit_kept[ubase + u];
+    if ((int)blockIdx.x >= gv.n_events) return;
+    const int e = blockIdx.x;
+    const int slot_event = gv.first_slot + e;
+    const int n = (int)fa.kept[slot_event];
+    const int64_t off = fa.offsets[slot_event];
     if (off + n > fa.out_cap) return;
-    const uint4* region = reinterpret_cast<const uint4*>(gv.tables + ((int64_t)gv.chunk_group * pb.max_units + unit) * gv.hash_cap);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_seg = (int)pb.unit_nseg[ubase + unit];
-    const unsigned* segend = pb.unit_segend + (ubase + unit) * MAX_SEGMENTS;
-    const bool use_bitmap = P.n_pads <= BITMAP_PADS;
-
-    auto write_row = [&](const uint4 raw, int64_t row_at) {
-        const unsigned key1 = raw.x, rank = raw.y;
-        const unsigned long long charge = ((unsigned long long)raw.w << 32) | raw.z;
-        const unsigned tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
-        const double u = wiggle_of(fa, slot_event, szudzik_pair(tb, pad), ctr);
+    const HashEntry* tab = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
+    const uint64_t* items = fa.sort_items + (int64_t)(gv.chunk_e0 + e) * 2 * gv.hash_cap;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint64_t it = items[i];
+        const unsigned tb = (unsigned)(it >> 47), pad = (unsigned)(it >> 32) & 0x7FFFu;
+        const unsigned key = szudzik_pair(tb, pad);
+        const HashEntry en = tab[(unsigned)it];
+        const double u = wiggle_of(fa, slot_event, key, ctr);
+        const double tbf = (double)tb + u;
         const int64_t label = fa.label_of_event_rank
-                                  ? (int64_t)fa.label_of_event_rank[(int64_t)slot_event * fa.n_tracks_per_event + rank]
-                                  : (int64_t)fa.label_of_rank[rank];
-        if (fa.cloud) {
-            double* row = fa.cloud + row_at * 3;
+                                  ? (int64_t)fa.label_of_event_rank[(int64_t)slot_event * fa.n_tracks_per_event + en.rank]
+                                  : (int64_t)fa.label_of_rank[en.rank];
+        if (fa.cloud) {  // (null: typed columns only, nobody reads the float64 rows)
+            double* row = fa.cloud + (off + i) * 3;
             row[0] = (double)pad;
-            row[1] = (double)tb + u;
-            row[2] = (double)(long long)charge;
-            fa.labels[row_at] = label;
+            row[1] = tbf;
+            row[2] = (double)(long long)en.charge;
+            fa.labels[off + i] = label;
         }
-        if (fa.col_pad) {
-            fa.col_pad[row_at] = (int16_t)pad;
-            fa.col_tb_q16[row_at] = (tb << 16) | (uint32_t)(u * 65536.0);
-            fa.col_label[row_at] = (int8_t)label;
-            if (fa.col_electrons) fa.col_electrons[row_at] = (long long)charge;
+        if (fa.col_pad) {  // only the columns that will be copied are written
+            fa.col_pad[off + i] = (int16_t)pad;
+            fa.col_tb_q16[off + i] = (tb << 16) | (uint32_t)(u * 65536.0);
+            fa.col_label[off + i] = (int8_t)label;
+            if (fa.col_electrons) fa.col_electrons[off + i] = (long long)en.charge;
             if (fa.col_electrons32) {
-                fa.col_electrons32[row_at] = (uint32_t)charge;
-                if (charge >> 32) {
+                fa.col_electrons32[off + i] = (uint32_t)en.charge;
+                if (en.charge >> 32) {
                     const unsigned long long k = atomicAdd(fa.big_count, 1ULL);
                     if ((int64_t)k < fa.big_cap) {
-                        fa.big_rows[k] = row_at;
-                        fa.big_electrons[k] = (long long)charge;
+                        fa.big_rows[k] = off + i;
+                        fa.big_electrons[k] = (long long)en.charge;
                     }
                 }
             }
         }
-    };
-
-    if (n_seg == 0) {  // fixup_kernel left the rows in final order
-        for (int i = threadIdx.x; i < n; i += FINALIZE_THREADS) write_row(__ldcs(region + i), off + i);
-        return;
-    }
-    for (int sgm = 0; sgm < n_seg; ++sgm) {
-        const int s0 = sgm ? (int)segend[sgm - 1] : 0;
-        const int m = min((int)segend[sgm], n) - s0;  // (<= EMIT_SEG_CAP: one table)
-        if (m <= 0) continue;
-        if (m > EMIT_SEG_CAP) {  // cannot happen (a segment is one table); never write past the shared arrays
-            if (threadIdx.x == 0) ctr->overflow_out = 1;
-            return;
-        }
-        __syncthreads();  // the previous segment is done with the shared arrays
-        // (1) keys of the segment, its first time bucket
-        unsigned lo = 0xFFFFFFFFu;
-        for (int i = threadIdx.x; i < m; i += FINALIZE_THREADS) {
-            const unsigned key1 = __ldg(&region[s0 + i].x);
-            sh.key[i] = key1;
-            lo = min(lo, (key1 - 1u) >> 15);
-        }
-        for (int i = threadIdx.x; i < EMIT_BINS; i += FINALIZE_THREADS) sh.hist[i] = 0u;
-        lo = __reduce_min_sync(FULL, lo);
-        if (lane == 0) sh.wsum[warp] = lo;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned v = 0xFFFFFFFFu;
-            for (int w = 0; w < EMIT_WARPS; ++w) v = min(v, sh.wsum[w]);
-            sh.lo_tb = v;
-        }
-        __syncthreads();
-        const unsigned lo_tb = sh.lo_tb;
-        // (2) entries per time bucket, exclusive scan (four bins per thread)
-        for (int i = threadIdx.x; i < m; i += FINALIZE_THREADS)
-            atomicAdd(&sh.hist[min(((sh.key[i] - 1u) >> 15) - lo_tb, (unsigned)EMIT_BINS - 1u)], 1u);
-        __syncthreads();
-        {
-            constexpr int PER = EMIT_BINS / FINALIZE_THREADS;
-            unsigned local[PER], sum = 0;
-#pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                local[k] = sh.hist[threadIdx.x * PER + k];
-                sum += local[k];
-            }
-            unsigned incl = sum;
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (lane == 31) sh.wsum[warp] = incl;
-            __syncthreads();
-            unsigned run = incl - sum;
-            for (int w = 0; w < warp; ++w) run += sh.wsum[w];
-#pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                sh.hist[threadIdx.x * PER + k] = run;
-                run += local[k];
-            }
-            __syncthreads();
-        }
-        // (3) entry indices bucket by bucket (hist[b] becomes the END of bucket b)
-        for (int i = threadIdx.x; i < m; i += FINALIZE_THREADS)
-            sh.list[atomicAdd(&sh.hist[min(((sh.key[i] - 1u) >> 15) - lo_tb, (unsigned)EMIT_BINS - 1u)], 1u)] = (uint16_t)i;
-        __syncthreads();
-        // (4) one warp per bucket: the place of every entry = bucket start + pads of the bucket below its own
-        {
-            unsigned* bm = sh.bitmap[warp];
-            uint16_t* pre = sh.prefix[warp];
-            constexpr int WPL = BITMAP_WORDS / 32;  // bitmap words per lane: lane l holds words 10 l .. 10 l + 9
-            for (int k = 0; k < WPL; ++k) bm[lane * WPL + k] = 0u;
-            __syncwarp();
-            // bucket b belongs to warp b % EMIT_WARPS (a segment covers a short run of consecutive time buckets: they
-            // must not all fall to the same warp); 32 of a warp's buckets at a time: skip the empty ones
-            for (unsigned b0 = 0; b0 < (unsigned)EMIT_BINS; b0 += EMIT_WARPS * 32) {
-                const unsigned mb = b0 + (unsigned)lane * EMIT_WARPS + (unsigned)warp;
-                const unsigned mlo = mb ? sh.hist[mb - 1] : 0u, mhi = sh.hist[mb];
-                unsigned todo = __ballot_sync(FULL, mhi > mlo);
-                while (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1u;
-                    const unsigned blo = __shfl_sync(FULL, mlo, src), bhi = __shfl_sync(FULL, mhi, src);
-                    const bool mixed = b0 + (unsigned)src * EMIT_WARPS + (unsigned)warp == (unsigned)EMIT_BINS - 1u;  // the last bin may hold several time buckets
-                    if (bhi - blo <= 32u) {  // one key per lane: count the smaller ones as every lane shows its own
-                        const unsigned cnt = bhi - blo;
-                        const bool have = (unsigned)lane < cnt;
-                        const unsigned me = have ? sh.list[blo + lane] : 0u;
-                        const unsigned key1 = have ? sh.key[me] : 0xFFFFFFFFu;
-                        unsigned below = 0;
-                        for (unsigned j = 0; j < cnt; ++j) below += __shfl_sync(FULL, key1, j) < key1;
-                        __syncwarp();
-                        if (have) sh.key[me] = blo + below;
-                    } else if (!use_bitmap || mixed) {  // by counting, on the full key
-                        for (unsigned i = blo + lane; i < bhi; i += 32) {
-                            const unsigned me = sh.list[i], key1 = __ldg(&region[s0 + me].x);
-                            unsigned below = 0;
-                            for (unsigned j = blo; j < bhi; ++j) below += __ldg(&region[s0 + sh.list[j]].x) < key1;
-                            sh.key[me] = blo + below;  // (sh.key of this bucket is not read by anybody else any more)
-                        }
-                    } else {
-                        for (unsigned i = blo + lane; i < bhi; i += 32) {
-                            const unsigned pad = (sh.key[sh.list[i]] - 1u) & 0x7FFFu;
-                            atomicOr(&bm[pad >> 5], 1u << (pad & 31));
-                        }
-                        __syncwarp();
-                        unsigned cnt[WPL], mine = 0;
-#pragma unroll
-                        for (int k = 0; k < WPL; ++k) {
-                            cnt[k] = __popc(bm[lane * WPL + k]);
-                            mine += cnt[k];
-                        }
-                        unsigned incl = mine;
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const unsigned v = __shfl_up_sync(FULL, incl, o);
-                            if (lane >= o) incl += v;
-                        }
-                        unsigned run = incl - mine;
-#pragma unroll
-                        for (int k = 0; k < WPL; ++k) {
-                            pre[lane * WPL + k] = (uint16_t)run;
-                            run += cnt[k];
-                        }
-                        __syncwarp();
-                        for (unsigned i = blo + lane; i < bhi; i += 32) {
-                            const unsigned me = sh.list[i], pad = (sh.key[me] - 1u) & 0x7FFFu, word = pad >> 5;
-                            sh.key[me] = blo + pre[word] + __popc(bm[word] & ((1u << (pad & 31)) - 1u));
-                            // (the keys of this bucket have all been read: the same array now holds the places)
-                        }
-                        __syncwarp();
-                        for (unsigned i = blo + lane; i < bhi; i += 32) {  // leave the bitmap empty for the next bucket
-                            const unsigned me = sh.list[i];
-                            const unsigned pad = (__ldg(&region[s0 + me].x) - 1u) & 0x7FFFu;
-                            bm[pad >> 5] = 0u;
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        // (5) the rows, each at its place
-        for (int i = threadIdx.x; i < m; i += FINALIZE_THREADS) write_row(__ldcs(region + s0 + i), off + s0 + sh.key[i]);
     }
 }
 
@@ -2390,7 +1864,20 @@ struct SpyralArgs {
     const int64_t* offsets;   // [n_events + 1] input cloud CSR
     const double* cloud;      // [n, 3]
     const int64_t* labels;    // [n]
-    int64_t n_events;
+    int64_t n_events;         // events of this pass: first .. first + n_events - 1 of the arrays below
+    int64_t first;
+    unsigned long long* total;  // running number of rows before event `first` (device; updated by the scan)
+    int64_t scratch_rows;     // rows of sort_keys / sort_idx per half
+    const Counters* ctr;      // launch counters (null: none): a launch that overflowed a buffer is void and will be redone
+    int64_t cloud_cap;        // rows the cloud buffer holds
+    // typed sink (ATTPC_SPYRAL_COLUMNS): pad, time bucket Q16.16, electrons as 32 low + 16 high bits, label; null = the
+    // float64 rows below.  Amplitude and integral follow from the electrons alone, x / y / pad size from the pad id and
+    // z from the time bucket, so the host rebuilds the eight columns bit for bit (engine.SimBatch.spyral_rows).
+    int16_t* out_pad;
+    uint32_t* out_tb_q16;
+    uint32_t* out_e_lo;
+    uint16_t* out_e_hi;
+    int8_t* out_label;
     unsigned* kept;           // [n_events]
     int64_t* row_offsets;     // [n_events + 1]
     double* rows;             // [n, 8] (capacity = input points)
@@ -2411,7 +1898,9 @@ __device__ __forceinline__ void shaped(const SimParams& P, double electrons, dou
         const int mid = (lo + hi) >> 1;
         if (__dmul_rn(P.resp_sorted[mid], electrons) > 4095.0) lo = mid + 1; else hi = mid;
     }
-    integral = 4095.0 * (double)lo + electrons * (P.resp_prefix[P.n_response] - P.resp_prefix[lo]);
+    // (explicitly rounded operations: the host rebuilds this value from the typed columns and must get the same bits)
+    integral = __dadd_rn(__dmul_rn(4095.0, (double)lo),
+                         __dmul_rn(electrons, __dsub_rn(P.resp_prefix[P.n_response], P.resp_prefix[lo])));
 }
 
 __device__ __forceinline__ uint64_t orderable(double v) {
@@ -2421,11 +1910,16 @@ __device__ __forceinline__ uint64_t orderable(double v) {
 
 // pass 1: per point amplitude/threshold (detector/writer.py:232), count kept rows per event
 __global__ void __launch_bounds__(256) spyral_count_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
-    const int e = blockIdx.x;
+    const int64_t e = sa.first + blockIdx.x;
     __shared__ unsigned s_n;
     if (threadIdx.x == 0) s_n = 0;
     __syncthreads();
     const int64_t a = sa.offsets[e], b = sa.offsets[e + 1];
+    const bool bad = (sa.ctr && (sa.ctr->overflow_points | sa.ctr->overflow_hash | sa.ctr->overflow_out)) || b > sa.cloud_cap;
+    if (bad) {  // the rows of this attempt were never written
+        if (threadIdx.x == 0) sa.kept[e] = 0;
+        return;
+    }
     unsigned mine = 0;
     for (int64_t i = a + threadIdx.x; i < b; i += blockDim.x) {
         const double amp = fmin(__dmul_rn(P.resp_max, sa.cloud[i * 3 + 2]), 4095.0);
@@ -2440,8 +1934,10 @@ __global__ void __launch_bounds__(1024) spyral_scan_kernel(SpyralArgs sa) {
     __shared__ unsigned long long s_part[1024];
     __shared__ unsigned long long s_base;
     const int tid = threadIdx.x;
-    if (tid == 0) s_base = 0;
+    if (tid == 0) s_base = *sa.total;
     __syncthreads();
+    sa.kept += sa.first;
+    sa.row_offsets += sa.first;
     for (int64_t start = 0; start < sa.n_events; start += 1024) {
         const int64_t i = start + tid;
         const unsigned long long v = i < sa.n_events ? sa.kept[i] : 0ULL;
@@ -2458,7 +1954,10 @@ __global__ void __launch_bounds__(1024) spyral_scan_kernel(SpyralArgs sa) {
         if (tid == 0) s_base += s_part[1023];
         __syncthreads();
     }
-    if (tid == 0) sa.row_offsets[sa.n_events] = (int64_t)s_base;
+    if (tid == 0) {
+        sa.row_offsets[sa.n_events] = (int64_t)s_base;
+        *sa.total = s_base;
+    }
 }
 
 constexpr int SPYRAL_SMEM_ITEMS = 4096;  // 48 KB: 8 B z-bits + 4 B point index each
@@ -2475,13 +1974,13 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
     __shared__ unsigned s_fill[TB_BINS];
     __shared__ unsigned s_n;
     __shared__ unsigned s_warp[8];
-    const int e = blockIdx.x;
+    const int64_t e = sa.first + blockIdx.x;
     const int64_t a = sa.offsets[e], b = sa.offsets[e + 1];
     const int64_t out0 = sa.row_offsets[e];
     const int n = (int)sa.kept[e];
     if (n == 0) return;
     const double span = (double)(P.win_edge - P.mm_edge);
-    const int64_t total = sa.offsets[sa.n_events];
+    const int64_t total = sa.scratch_rows;
     uint64_t* stash_k = sa.sort_keys + a;           // unordered survivors
     uint32_t* stash_v = sa.sort_idx + a;
     const bool in_smem = n <= SPYRAL_SMEM_ITEMS;
@@ -2558,6 +2057,16 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
             place = lo + before;
         }
         const int pad = (int)padf;
+        if (sa.out_pad) {  // typed columns: what the eight columns are functions of
+            const int64_t at = out0 + place;
+            const unsigned long long q = (unsigned long long)(long long)el;
+            sa.out_pad[at] = (int16_t)pad;
+            sa.out_tb_q16[at] = (uint32_t)(tbf * 65536.0);  // exact for the library's 16-bit wiggle
+            sa.out_e_lo[at] = (uint32_t)q;
+            sa.out_e_hi[at] = (uint16_t)(q >> 32);
+            sa.out_label[at] = (int8_t)sa.labels[src];
+            continue;
+        }
         double amp, integral;
         shaped(P, el, amp, integral);
         double* row = sa.rows + (out0 + place) * 8;

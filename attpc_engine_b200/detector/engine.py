@@ -74,16 +74,41 @@ class SimBatch:
     """
 
     def __init__(self, first_event, offsets, cloud=None, labels=None, row_offsets=None, rows=None, row_labels=None,
-                 stats=None, columns=None):  # fmt: skip
+                 stats=None, columns=None, row_columns=None, row_builder=None):  # fmt: skip
         self.first_event = first_event
         self.offsets = offsets
         self._cloud = cloud
         self._labels = labels
         self.row_offsets = row_offsets
-        self.rows = rows  # [M, 8] Spyral rows
-        self.row_labels = row_labels
+        self._rows = rows  # [M, 8] Spyral rows
+        self._row_labels = row_labels
         self.stats = {} if stats is None else stats
         self.columns = columns  # dict(pad, tb_q16, label8, and electrons or electrons_u32 + big_rows + big_electrons) or None
+        #: Spyral rows (after ADC threshold, z-sorted) as typed columns: dict(pad int16, tb_q16 uint32, e_lo uint32,
+        #: e_hi uint16, label8 int8) -- 13 B/row over PCIe instead of 72; ``rows`` / ``row_labels`` / ``event_rows`` rebuild
+        #: the float64 arrays from them on demand, bit for bit (`Engine.rows_from_columns`)
+        self.row_columns = row_columns
+        self._row_builder = row_builder
+
+    @property
+    def rows(self):
+        if self._rows is None and self.row_columns is not None:
+            self._rows, self._row_labels = self._row_builder(self.row_columns)
+        return self._rows
+
+    @rows.setter
+    def rows(self, value):
+        self._rows = value
+
+    @property
+    def row_labels(self):
+        if self._row_labels is None and self.row_columns is not None:
+            self._rows, self._row_labels = self._row_builder(self.row_columns)
+        return self._row_labels
+
+    @row_labels.setter
+    def row_labels(self, value):
+        self._row_labels = value
 
     def __len__(self) -> int:
         return len(self.offsets) - 1
@@ -133,7 +158,10 @@ class SimBatch:
         return self.cloud[a:b], self.labels[a:b]
 
     def event_rows(self, e: int) -> tuple[np.ndarray, np.ndarray]:
+        """``(rows [n, 8] float64, labels [n] int64)`` of event ``e`` as `SpyralWriter.write` stores them."""
         a, b = self.row_offsets[e], self.row_offsets[e + 1]
+        if self._rows is None and self.row_columns is not None:  # only this event's rows are materialised
+            return self._row_builder({k: v[a:b] for k, v in self.row_columns.items()})
         return self.rows[a:b], self.row_labels[a:b]
 
 
@@ -145,7 +173,7 @@ _STAT_FIELDS = (
     "n_tracks", "n_trajectory_points", "n_active_points", "n_primary_electrons", "n_deposits", "n_keys",
     "ms_h2d", "ms_tracks", "ms_deposit", "ms_finalize", "ms_d2h", "ms_total", "n_kernel_launches", "n_retries",
     "n_track_launches", "n_group_launches", "n_hash_probes", "hash_capacity", "n_table_flushes",
-    "n_rk_steps", "n_rk_rejects", "max_track_passes", "ms_order", "n_big", "n_dirty_units", "n_raw_entries",
+    "n_rk_steps", "n_rk_rejects", "max_track_passes", "ms_order", "n_big",
 )  # fmt: skip
 
 
@@ -165,8 +193,6 @@ class Engine:
         copy_events_per_launch: int = 0,
         unit_points: int = 0,
         table_spill_keys: int = 0,
-        table_hard_keys: int = 0,
-        table_max_probe: int = 0,
     ):
         if config.pad_grid is None or config.pad_grid_edges is None:
             raise ValueError("Pad grid is not loaded")  # solver.py:400-401
@@ -217,8 +243,6 @@ class Engine:
         cfg.copy_events_per_launch = int(copy_events_per_launch)
         cfg.unit_points = int(unit_points)
         cfg.table_spill_keys = int(table_spill_keys)
-        cfg.table_hard_keys = int(table_hard_keys)
-        cfg.table_max_probe = int(table_max_probe)
 
         sp = (_lib.AttpcSpecies * len(self.species))()
         for i, (nuc, tab) in enumerate(zip(self.species, tables)):
@@ -322,7 +346,17 @@ class Engine:
         else:
             cloud, labels = np.zeros((0, 3)), np.zeros(0, np.int64)
         out = SimBatch(first_event, offsets, cloud, labels, stats=dict(stats, n_points=n_pts), columns=columns)
-        if rows:
+        if rows and res.row_col_pad:
+            n_rows = int(res.n_rows)
+            out.row_offsets = grab(np.ctypeslib.as_array(res.row_offsets, shape=(n_ev + 1,)))
+            names = (("pad", res.row_col_pad, np.int16), ("tb_q16", res.row_col_tb_q16, np.uint32),
+                     ("e_lo", res.row_col_e_lo, np.uint32), ("e_hi", res.row_col_e_hi, np.uint16),
+                     ("label8", res.row_col_label, np.int8))  # fmt: skip
+            out.row_columns = {k: (grab(np.ctypeslib.as_array(ptr, shape=(n_rows,))) if n_rows else np.zeros(0, dt))
+                               for k, ptr, dt in names}  # fmt: skip
+            out._row_builder = self.rows_from_columns
+            out.stats["n_rows"] = n_rows
+        elif rows:
             n_rows = int(res.n_rows)
             out.row_offsets = grab(np.ctypeslib.as_array(res.row_offsets, shape=(n_ev + 1,)))
             if n_rows > 0:
@@ -332,6 +366,50 @@ class Engine:
                 out.rows, out.row_labels = np.zeros((0, 8)), np.zeros(0, np.int64)
             out.stats["n_rows"] = n_rows
         return out
+
+    def rows_from_columns(self, cols: dict) -> tuple[np.ndarray, np.ndarray]:
+        """The eight Spyral columns (`writer.py:61-112`) from the typed columns of ``ATTPC_SPYRAL_COLUMNS``.
+
+        Every column is a function of (pad, time bucket, electrons): x, y, pad size are table lookups, z is
+        `writer.py:101-103`, amplitude and integral are `response.py:35-57` in the closed form the device uses
+        (``min(r_max e, 4095)`` and ``4095 k + e (S - S_k)`` over the descending-sorted response, with explicitly
+        rounded operations on both sides), so the result equals the device's float64 rows bit for bit
+        (`tests/test_gpu_e2e.py::test_spyral_columns_rebuild_the_float64_rows`).
+        """
+        if not hasattr(self, "_resp_sorted"):
+            self._resp_sorted = np.sort(self._response)[::-1].copy()
+            self._resp_prefix = np.concatenate([[0.0], np.cumsum(self._resp_sorted)])  # sequential, like the device's
+        cfg = self.config
+        win, mm = float(int(cfg.elec_params.windows_edge)), float(int(cfg.elec_params.micromegas_edge))
+        length = float(cfg.det_params.length)
+        pad = cols["pad"].astype(np.int64)
+        n = len(pad)
+        e = ((cols["e_hi"].astype(np.uint64) << np.uint64(32)) | cols["e_lo"].astype(np.uint64)).astype(np.float64)
+        tbf = cols["tb_q16"].astype(np.float64)
+        tbf *= 1.0 / 65536.0
+        rows = np.empty((n, 8), dtype=np.float64)
+        rows[:, 0] = self._pad_xy[pad, 0]
+        rows[:, 1] = self._pad_xy[pad, 1]
+        rows[:, 2] = (win - tbf) / (win - mm) * length * 1000.0
+        rs, pre = self._resp_sorted, self._resp_prefix
+        top = rs[0] * e
+        rows[:, 3] = np.minimum(top, 4095.0)
+        k = np.zeros(n, dtype=np.int64)  # response samples clipped at 4095: a prefix of the sorted response
+        hot = np.flatnonzero(top > 4095.0)
+        if len(hot):
+            eh = e[hot]
+            kk = np.searchsorted(-rs, -(4095.0 / eh), side="left")
+            for _ in range(4):  # settle the boundary with the device's own predicate r_i * e > 4095
+                down = (kk > 0) & (rs[np.maximum(kk - 1, 0)] * eh <= 4095.0)
+                kk = kk - down
+                up = (kk < len(rs)) & (rs[np.minimum(kk, len(rs) - 1)] * eh > 4095.0)
+                kk = kk + up
+            k[hot] = kk
+        rows[:, 4] = 4095.0 * k + e * (pre[len(rs)] - pre[k])
+        rows[:, 5] = pad
+        rows[:, 6] = tbf
+        rows[:, 7] = self._pad_scale[pad]
+        return rows, cols["label8"].astype(np.int64)
 
     #: validation switch: evaluate every mesh pixel with the reference's own expression (`transporter.py:36-41`)
     #: instead of the constant weight table + exactness guard.  Both give identical results.
@@ -356,11 +434,13 @@ class Engine:
         host_copy: bool = True,
         rows_only: bool = False,
         columns: bool = False,
+        row_columns: bool = False,
     ) -> SimBatch:
         """`simulate` (`simulator.py:52-115`) for ``B`` events at once: ``momenta [B, K, 4]``, ``vertices [B, 3]``.
 
         ``rows_only`` (with ``spyral_rows``): bring back offsets and Spyral rows but leave the raw cloud on the GPU.
         ``columns``: bring the rows back as typed columns (11 B/row instead of 32 B/row over PCIe), see `SimBatch`.
+        ``row_columns`` (with ``spyral_rows``): the Spyral rows as typed columns too (13 instead of 72 B/row).
         """
         momenta = np.ascontiguousarray(momenta, dtype=np.float64)
         vertices = np.ascontiguousarray(vertices, dtype=np.float64)
@@ -370,6 +450,8 @@ class Engine:
             raise ValueError("vertices must have shape [n_events, 3]")
         nucleus, spec = self._species_of(proton_numbers, mass_numbers, indices)
         flags = (_lib.SPYRAL_ROWS if spyral_rows else 0) | (_lib.KEEP_ALL_TB if keep_all_tb else 0)
+        if spyral_rows and row_columns:
+            flags |= _lib.SPYRAL_COLUMNS
         if not host_copy:
             flags |= _lib.SKIP_HOST_COPY
         if rows_only and spyral_rows:

@@ -67,6 +67,7 @@ def simulate_batch(
     nuclear_data=None,
     rows_only: bool = False,
     columns: bool = False,
+    row_columns: bool = False,
     **tuning,
 ) -> SimBatch:
     """Detector simulation of ``B`` kinematics events in one call.
@@ -89,7 +90,7 @@ def simulate_batch(
     engine = engine_for(config, charged, device=device, **tuning)
     return engine.simulate_batch(
         momenta, vertices, proton_numbers, mass_numbers, indices, seed=seed, first_event=first_event,
-        spyral_rows=spyral_rows, copy=copy, rows_only=rows_only, columns=columns,
+        spyral_rows=spyral_rows, copy=copy, rows_only=rows_only, columns=columns, row_columns=row_columns,
     )  # fmt: skip
 
 
@@ -209,6 +210,7 @@ def run_simulation(
             momenta, vertices, kin.proton_numbers, kin.mass_numbers, config, seed, nuclei_to_sim,
             first_event=start, device=device, spyral_rows=want_rows, copy=not views_ok,
             rows_only=want_rows and bool(getattr(writer, "rows_only", False)),
+            row_columns=want_rows,  # 13 instead of 72 B/row over PCIe; `SimBatch.event_rows` rebuilds the float64 rows
             # per-event writers get their arrays built event by event anyway; batch writers say if they want columns
             columns=not batched or bool(getattr(writer, "wants_columns", False)),
         )  # fmt: skip

@@ -154,7 +154,7 @@ class SpyralWriter:
 
     def write_batch(self, batch: SimBatch, config: Config) -> None:
         """Batch hook of `run_simulation`: rows were already produced on the GPU."""
-        if batch.rows is None:
+        if batch.row_offsets is None:
             raise ValueError("SpyralWriter.write_batch needs a batch simulated with spyral_rows=True")
         for e in range(len(batch)):
             if batch.offsets[e + 1] == batch.offsets[e]:  # empty clouds are skipped (`simulator.py:204`)

@@ -275,6 +275,7 @@ def run_ours(args):
     def step_e2e(i):
         return eng.simulate_batch(mom_pin.numpy(), vtx_pin.numpy(), zs, as_, indices, seed=seed + i, first_event=first,
                                   copy=False, spyral_rows=args.spyral, rows_only=args.spyral,
+                                  row_columns=args.spyral and not args.float64_rows,
                                   columns=not args.float64_rows).stats  # fmt: skip
 
     sampler = ClockSampler(local)
@@ -320,7 +321,8 @@ def run_ours(args):
     points = reduce_sum(dist, stats_sum["n_points"], local)
     deposits = reduce_sum(dist, stats_sum["n_deposits"], local)
     # bytes this rank brought to the host per step of the e2e loop (rows + CSR offsets), summed over the ranks
-    row_bytes = e2e_rows * 72 if args.spyral else e2e_points * (32 if args.float64_rows else 11) + 16 * e2e_big
+    row_bytes = (e2e_rows * (72 if args.float64_rows else 13) if args.spyral
+                 else e2e_points * (32 if args.float64_rows else 11) + 16 * e2e_big)
     d2h_local = 0.0 if args.no_e2e else row_bytes / max(1, args.steps) + (B + 1) * 8 * (2 if args.spyral else 1)
     d2h_total = reduce_sum(dist, d2h_local, local)
 
@@ -377,13 +379,13 @@ def run_ours(args):
                       "trajectory_points": round(stats_sum["n_trajectory_points"] / n_ev_rank, 1),
                       "primary_electrons": round(stats_sum["n_primary_electrons"] / n_ev_rank, 1),
                       "table_flushes": round(stats_sum["n_table_flushes"] / n_ev_rank, 4),
-                      "dirty_units": round(stats_sum["n_dirty_units"] / n_ev_rank, 6),
-                      "raw_entries": round(stats_sum["n_raw_entries"] / n_ev_rank, 6),
                       "rhs_evals_per_track": round((6 * stats_sum["n_rk_steps"] + stats_sum["n_tracks"]) / max(1, stats_sum["n_tracks"]), 1)},
         "wall_s_device_loop": round(wall_dev, 3),
         "e2e": {"value": None if args.no_e2e else round(total_events / e2e_s, 1), "unit": "events/s",
                 "h2d_bytes_per_step": int(momenta.nbytes + vertices.nbytes) * world,
-                "result": ("Spyral rows float64[M,8] + labels" if args.spyral else
+                "result": ("Spyral rows float64[M,8] + labels" if args.spyral and args.float64_rows else
+                           "Spyral rows (ADC threshold, z-sorted) as typed columns: pad int16, time bucket uint32 Q16.16, "
+                           "electrons uint32 + uint16, label int8; the host rebuilds the 8 float64 columns bit for bit" if args.spyral else
                            "cloud float64[N,3] + int64 labels" if args.float64_rows else
                            "typed columns: pad int16, time bucket uint32 Q16.16, electrons uint32 + list of the counts >= 2^32, label int8"),
                 "d2h_bytes_per_step": int(d2h_total)},

@@ -43,6 +43,10 @@ enum {
     ATTPC_COLUMNS32 = 1u << 8,     /* with ATTPC_COLUMNS: electrons as uint32 (low 32 bits) + a list of the (row, count)
                                       pairs that need more: 11 B/row.  A call with more than 2^20 such rows returns
                                       the int64 column instead (and so do the later calls on the handle) */
+    ATTPC_SPYRAL_COLUMNS = 1u << 9,/* the Spyral rows (after ADC threshold, z-sorted) as typed columns instead of float64
+                                      [M, 8]: row_col_* of AttpcResult, 13 B/row.  x, y, pad size follow from the pad id,
+                                      z from the time bucket, amplitude and integral from the electrons: the host rebuilds
+                                      the eight columns bit for bit */
     ATTPC_EXACT_MESH = 1u << 7     /* validation: evaluate every mesh pixel with the reference's own expression
                                       (detector/transporter.py:36-41, 240-246).  The default reads pdf * step^2 from
                                       the constant 10x10 weight table and falls back to that expression only where
@@ -74,13 +78,11 @@ typedef struct AttpcConfig {
                                stalled track early (0 = integrate to 1 us like the reference) */
     /* capacities (0 = library default); they grow automatically on overflow */
     int32_t max_events_per_launch;
-    int32_t hash_capacity;          /* rows per work-unit region (a unit is <= ~1024 track points of one event), power of two */
+    int32_t hash_capacity;          /* slots per event, power of two */
     int32_t copy_events_per_launch; /* events per host-copy chunk: rows are copied while later groups compute */
     /* stress knobs for tests (0 = library default; values above the default are clamped): results never depend on them */
-    int32_t unit_points;            /* target number of points of one work unit (one CTA) of the deposit kernel (default 1024) */
-    int32_t table_spill_keys;       /* keys in a CTA's shared-memory table that trigger a flush of the finished time buckets */
-    int32_t table_hard_keys;        /* keys above which a flush is no longer postponed: unfinished keys leave as raw entries */
-    int32_t table_max_probe;        /* probes after which an insert leaves a raw entry instead (default 128) */
+    int32_t unit_points;            /* points of one event handled by one CTA of the deposit kernel (default 1024) */
+    int32_t table_spill_keys;       /* keys in a CTA's shared-memory table that trigger an append to the event's list */
 } AttpcConfig;
 
 /* One ion species: the dE/dx table of attpc_engine_b200/target.py:DedxTable (pseudo-log grid). */
@@ -133,9 +135,9 @@ typedef struct AttpcResult {
     int32_t n_track_launches;    /* launches of the track (or replay) kernel */
     int32_t n_group_launches;    /* launches of the deposit kernel (= event groups processed) */
     int64_t n_hash_probes;       /* table slots inspected by the deposits (n_hash_probes / n_deposits ~ 1 is healthy) */
-    int32_t hash_capacity;       /* rows per work-unit region in use at the end of the call */
-    int32_t n_dirty_units;       /* work units that left raw entries and went through the merge kernel (0 in normal operation) */
-    int64_t n_table_flushes;     /* flushes of a shared-memory table before the end of its work unit */
+    int32_t hash_capacity;       /* slots per event in use at the end of the call */
+    int32_t reserved1;
+    int64_t n_table_flushes;     /* shared-memory tables appended to an event's entry list before the end of their work unit */
     /* ATTPC_COLUMNS: the rows of `cloud` / `labels` as typed columns (pinned host memory) */
     const int16_t* col_pad;      /* [n_points] pad id */
     const uint32_t* col_tb_q16;  /* [n_points] time bucket + wiggle as Q16.16 fixed point: cloud[:, 1] == col_tb_q16 / 65536
@@ -154,7 +156,12 @@ typedef struct AttpcResult {
     float ms_order;              /* device time of the point ordering kernels (scan + scatter) before the deposit kernel;
                                     ms_deposit is the deposit kernel alone */
     float reserved2;
-    int64_t n_raw_entries;       /* deposits that could not be accumulated in shared memory (merged by the fixup kernel) */
+    /* ATTPC_SPYRAL_COLUMNS: rows [row_offsets[e], row_offsets[e+1]) of event e, in the order of `rows` */
+    const int16_t* row_col_pad;      /* [n_rows] pad id */
+    const uint32_t* row_col_tb_q16;  /* [n_rows] time bucket + wiggle, Q16.16 */
+    const uint32_t* row_col_e_lo;    /* [n_rows] electrons (after gain), bits 0..31 */
+    const uint16_t* row_col_e_hi;    /* [n_rows] electrons, bits 32..47 */
+    const int8_t* row_col_label;     /* [n_rows] */
 } AttpcResult;
 
 typedef struct AttpcSim AttpcSim;

