@@ -640,13 +640,14 @@ def config_fingerprint(config: Config, nuclei: list) -> tuple:
     return scalars + (id(target), float(target.density), probes, arrays[1])
 
 
-def engine_for(config: Config, nuclei: list, device: int = 0, **tuning) -> Engine:
+def engine_for(config: Config, nuclei: list, device: int = 0, instance: int = 0, **tuning) -> Engine:
     """Engine cached on the Config object, keyed by device, species set and tuning; rebuilt when a baked value changed.
 
-    (In-place edits of the pad arrays are not seen -- replace the array, as ``load_pad_grid`` does.)
+    A handle must not be used from two threads at once: concurrent callers on the SAME device ask for different
+    ``instance`` numbers.  (In-place edits of the pad arrays are not seen -- replace the array, as ``load_pad_grid`` does.)
     """
     cache = config.__dict__.setdefault("_b200_engines", {})
-    key = (int(device), tuple(sorted((int(n.Z), int(n.A)) for n in nuclei)), tuple(sorted(tuning.items())))
+    key = (int(device), int(instance), tuple(sorted((int(n.Z), int(n.A)) for n in nuclei)), tuple(sorted(tuning.items())))
     uniq = {}
     for n in nuclei:
         uniq.setdefault((int(n.Z), int(n.A)), n)

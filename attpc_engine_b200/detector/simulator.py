@@ -68,6 +68,7 @@ def simulate_batch(
     rows_only: bool = False,
     columns: bool = False,
     row_columns: bool = False,
+    engine_instance: int = 0,
     **tuning,
 ) -> SimBatch:
     """Detector simulation of ``B`` kinematics events in one call.
@@ -87,7 +88,7 @@ def simulate_batch(
         if spyral_rows:
             empty.row_offsets, empty.rows, empty.row_labels = empty.offsets.copy(), np.zeros((0, 8)), empty.labels
         return empty
-    engine = engine_for(config, charged, device=device, **tuning)
+    engine = engine_for(config, charged, device=device, instance=engine_instance, **tuning)
     return engine.simulate_batch(
         momenta, vertices, proton_numbers, mass_numbers, indices, seed=seed, first_event=first_event,
         spyral_rows=spyral_rows, copy=copy, rows_only=rows_only, columns=columns, row_columns=row_columns,
@@ -168,6 +169,63 @@ def _open_kinematics(input_path):
     return _Hdf5Kinematics(path)
 
 
+class _OrderedFanIn:
+    """Batches simulated by one worker thread per GPU, handed to the writer in ascending batch order.
+
+    Batch ``k`` goes to device ``k mod G``.  A worker starts its next batch only after the writer has taken the
+    previous one, so a batch may hold views of its engine's pinned buffers until then (no copy), and at most one
+    finished batch per GPU waits in host memory.  An exception in a worker is re-raised in the caller.
+    """
+
+    def __init__(self, n_batches: int, devices: list[int], work):
+        import threading
+
+        self.n_batches, self.devices, self.work = n_batches, list(devices), work
+        self.cond = threading.Condition()
+        self.ready: dict[int, object] = {}
+        self.taken = -1  # highest batch index the writer is done with
+        self.error: BaseException | None = None
+        self.threads = [threading.Thread(target=self._run, args=(g,), daemon=True) for g in range(len(self.devices))]
+        for t in self.threads:
+            t.start()
+
+    def _run(self, g: int) -> None:
+        try:
+            for k in range(g, self.n_batches, len(self.devices)):
+                with self.cond:  # the writer must be done with this worker's previous batch (it may be a view)
+                    self.cond.wait_for(lambda: self.taken >= k - len(self.devices) or self.error is not None)
+                    if self.error is not None:
+                        return
+                batch = self.work(k, g)
+                with self.cond:
+                    self.ready[k] = batch
+                    self.cond.notify_all()
+        except BaseException as exc:  # noqa: BLE001 - handed to the caller
+            with self.cond:
+                self.error = exc
+                self.cond.notify_all()
+
+    def __iter__(self):
+        for k in range(self.n_batches):
+            with self.cond:
+                self.cond.wait_for(lambda: k in self.ready or self.error is not None)
+                if self.error is not None:
+                    raise self.error
+                batch = self.ready.pop(k)
+            yield k, batch
+            with self.cond:
+                self.taken = k
+                self.cond.notify_all()
+
+    def close(self) -> None:
+        with self.cond:
+            if self.error is None:
+                self.error = GeneratorExit()
+            self.cond.notify_all()
+        for t in self.threads:
+            t.join(timeout=60)
+
+
 def run_simulation(
     config: Config,
     input_path: Path,
@@ -177,6 +235,7 @@ def run_simulation(
     batch_size: int = 16384,
     device: int = 0,
     verbose: bool = True,
+    devices: list[int] | None = None,
 ) -> None:
     """Run the detector simulation over a kinematics file (`simulator.py:118-210`).
 
@@ -190,38 +249,65 @@ def run_simulation(
     ``accepts_views = True``: it is then handed views of the engine's pinned host buffers, valid only until
     the next batch is simulated (no copy; the built-in writers do this).
     ``seed=None`` draws one from the OS, like the reference's unseeded generator.
+
+    ``devices=[0, 1, ...]``: the event ranges (batches of ``batch_size`` events) are dealt round-robin to one worker
+    thread and one engine per listed GPU; the writer still sees every event in ascending order, and -- every random
+    draw being addressed by the global event number -- the output does not depend on the number of GPUs.
     """
     kin = _open_kinematics(input_path)
+    devices = [int(device)] if not devices else [int(d) for d in devices]
     if verbose:
         print("------- AT-TPC Simulation Engine (B200) -------")
         print(f"Applying detector effects to kinematics from file: {input_path}")
         print(f"Found {kin.n_events} kinematics events.")
         print(f"Output will be written to {writer.get_directory_name()}.")
+        if len(devices) > 1:
+            print(f"Event ranges of {batch_size} events are dealt to GPUs {devices}.")
     nuclei_to_sim = list(indices) if indices is not None else default_indices(len(kin.proton_numbers))
     if seed is None:
         seed = int(default_rng().integers(0, 2**63 - 1))
     batched = hasattr(writer, "write_batch")
     want_rows = bool(getattr(writer, "wants_spyral_rows", False)) and batched
     views_ok = not batched or bool(getattr(writer, "accepts_views", False))  # per-event arrays are built fresh anyway
-    for start in range(0, kin.n_events, batch_size):
+    starts = list(range(0, kin.n_events, batch_size))
+    import threading
+
+    read_lock = threading.Lock()  # (h5py handles are not thread-safe)
+
+    def work(k: int, g: int) -> SimBatch:  # batch k on worker g (its own engine on devices[g])
+        start = starts[k]
         stop = min(start + batch_size, kin.n_events)
-        momenta, vertices = kin.read(start, stop)
-        batch = simulate_batch(
+        with read_lock:
+            momenta, vertices = kin.read(start, stop)
+        return simulate_batch(
             momenta, vertices, kin.proton_numbers, kin.mass_numbers, config, seed, nuclei_to_sim,
-            first_event=start, device=device, spyral_rows=want_rows, copy=not views_ok,
+            first_event=start, device=devices[g], engine_instance=g, spyral_rows=want_rows, copy=not views_ok,
             rows_only=want_rows and bool(getattr(writer, "rows_only", False)),
             row_columns=want_rows,  # 13 instead of 72 B/row over PCIe; `SimBatch.event_rows` rebuilds the float64 rows
             # per-event writers get their arrays built event by event anyway; batch writers say if they want columns
             columns=not batched or bool(getattr(writer, "wants_columns", False)),
         )  # fmt: skip
+
+    def consume(k: int, batch: SimBatch) -> None:
         if batched:
             writer.write_batch(batch, config)
-            continue
+            return
         for e in range(len(batch)):
             cloud, labels = batch.event(e)
             if len(cloud) == 0:  # `simulator.py:204`
                 continue
-            writer.write(np.array(cloud), np.array(labels), config, start + e)
+            writer.write(np.array(cloud), np.array(labels), config, starts[k] + e)
+
+    if len(devices) == 1:
+        for k in range(len(starts)):
+            consume(k, work(k, 0))
+    else:
+        fan_in = _OrderedFanIn(len(starts), devices, work)
+        try:
+            for k, batch in fan_in:
+                consume(k, batch)
+        finally:
+            fan_in.close()
     writer.close()
     if verbose:
         print("Done.")

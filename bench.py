@@ -39,6 +39,12 @@ WORKLOADS = {
         gas=([(1, 2, 2)], 600.0), reaction=((1, 2), (6, 16), (1, 2)), decays=[], excitations=[("gauss", 0.0, 0.001)],
         beam=184.131, config_id=1,
     ),
+    "c16dd_sweep": dict(
+        desc="16C(d,d')16C*, excitation energy swept uniformly over 0-10 MeV (BASELINE config 5), 184.131 MeV 16C on D2 "
+             "600 Torr, B=3 T; tracks [2,3]",
+        gas=([(1, 2, 2)], 600.0), reaction=((1, 2), (6, 16), (1, 2)), decays=[], excitations=[("uniform", 0.0, 10.0)],
+        beam=184.131, config_id=5,
+    ),
     "c14dp": dict(
         desc="14C(d,p)15C* -> 14C + n, 161 MeV 14C on D2 600 Torr, B=3 T; tracks [2,4,5] (neutron skipped)",
         gas=([(1, 2, 2)], 600.0), reaction=((1, 2), (6, 14), (1, 1)), decays=[((6, 15), (6, 14))],
@@ -57,13 +63,11 @@ WORKLOADS = {
 }  # fmt: skip
 
 
-def build_workload(name: str, n_events: int, seed_offset: int = 0):
-    """Synthetic kinematics of a named reaction + the detector Config (SURVEY.md 8(d))."""
+def make_pipeline(name: str):
+    """The vectorised kinematics pipeline of a named reaction and its gas."""
     from attpc_engine_b200 import nuclear_map as nm
-    from attpc_engine_b200.detector import Config, DetectorParams, ElectronicsParams, PadParams
-    from attpc_engine_b200.detector.simulator import default_indices
     from attpc_engine_b200.kinematics import (
-        Decay, ExcitationGaussian, KinematicsPipeline, KinematicsTargetMaterial, PolarUniform, Reaction,
+        Decay, ExcitationGaussian, ExcitationUniform, KinematicsPipeline, KinematicsTargetMaterial, PolarUniform, Reaction,
     )  # fmt: skip
     from attpc_engine_b200.target import AnalyticGasTarget, TableGasTarget
 
@@ -73,9 +77,24 @@ def build_workload(name: str, n_events: int, seed_offset: int = 0):
     steps = [Reaction(target=t, projectile=p, ejectile=e)]
     steps += [Decay(parent=nm.get_data(*a), residual_1=nm.get_data(*b)) for a, b in w["decays"]]
     pipeline = KinematicsPipeline(
-        steps, [ExcitationGaussian(c, fwhm) for _, c, fwhm in w["excitations"]], [PolarUniform(0.0, np.pi)] * len(steps),
+        steps, [ExcitationUniform(a, b) if kind == "uniform" else ExcitationGaussian(a, b) for kind, a, b in w["excitations"]],
+        [PolarUniform(0.0, np.pi)] * len(steps),
         beam_energy=w["beam"], target_material=KinematicsTargetMaterial(gas, (0.0, 1.0), 0.007),
-    ).seed(20260101 + w["config_id"] + 7919 * seed_offset)  # fmt: skip
+    )  # fmt: skip
+    return pipeline, gas
+
+
+def workload_seed(name: str, seed_offset: int = 0) -> int:
+    return 20260101 + WORKLOADS[name]["config_id"] + 7919 * seed_offset
+
+
+def build_workload(name: str, n_events: int, seed_offset: int = 0):
+    """Synthetic kinematics of a named reaction + the detector Config (SURVEY.md 8(d))."""
+    from attpc_engine_b200.detector import Config, DetectorParams, ElectronicsParams, PadParams
+    from attpc_engine_b200.detector.simulator import default_indices
+
+    pipeline, gas = make_pipeline(name)
+    pipeline.seed(workload_seed(name, seed_offset))
     vertices, momenta = pipeline.run_batch(n_events)
     det = DetectorParams(length=1.0, efield=45000.0, bfield=3.0, mpgd_gain=175000, gas_target=gas, diffusion=0.277,
                          fano_factor=0.2, w_value=34.0)  # fmt: skip
@@ -272,11 +291,14 @@ def run_ours(args):
         return eng.simulate_device(mom_dev.data_ptr(), vtx_dev.data_ptr(), B, K, zs, as_, indices, seed=seed + i,
                                    first_event=first, spyral_rows=args.spyral).stats  # fmt: skip
 
-    def step_e2e(i):
+    def batch_e2e(i):
         return eng.simulate_batch(mom_pin.numpy(), vtx_pin.numpy(), zs, as_, indices, seed=seed + i, first_event=first,
                                   copy=False, spyral_rows=args.spyral, rows_only=args.spyral,
                                   row_columns=args.spyral and not args.float64_rows,
-                                  columns=not args.float64_rows).stats  # fmt: skip
+                                  columns=not args.float64_rows)  # fmt: skip
+
+    def step_e2e(i):
+        return batch_e2e(i).stats
 
     sampler = ClockSampler(local)
     sampler.start()  # nvidia-smi needs a moment to come up: started before the warm-up, read after the timed loops
@@ -313,6 +335,19 @@ def run_ours(args):
         e2e_rows += st.get("n_rows", 0)
     barrier()
     clocks = sampler.stop()
+    # e2e_decoded: the same call plus the decode of the wire format into the arrays `SimulationWriter.write` receives
+    # (float64 [N, 3] + int64 [N]; or the float64 [M, 8] Spyral rows), on one host thread; one step, rank-local
+    decoded_s = None
+    if not args.no_e2e and not args.float64_rows:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        b = batch_e2e(999)
+        if args.spyral:
+            _ = b.rows, b.row_labels
+        else:
+            _ = b.cloud, b.labels
+        decoded_s = time.perf_counter() - t0
+        del b, _
 
     dev_s = reduce_max(dist, dev_ms / 1e3, local)
     e2e_s = reduce_max(dist, e2e_s, local) if not args.no_e2e else float("nan")
@@ -331,7 +366,8 @@ def run_ours(args):
     peak, peak_src = measured_peak_hbm()
     # dominant kernel by device time (CUDA events recorded by the library around each stage, on its own stream)
     stage_ms = {"track_kernel": stats_sum["ms_tracks"], "point_scan+point_order": stats_sum["ms_order"],
-                "deposit_kernel": stats_sum["ms_deposit"], "finalize (collect+scan+emit)": stats_sum["ms_finalize"]}  # fmt: skip
+                "deposit_kernel": stats_sum["ms_deposit"],
+                "finalize (collect+scan+emit" + ("+spyral)" if args.spyral else ")"): stats_sum["ms_finalize"]}  # fmt: skip
     dominant = max(stage_ms, key=stage_ms.get)
     n_ev_rank = B * args.steps
     n_out = stats_sum["n_points"] / n_ev_rank
@@ -353,15 +389,44 @@ def run_ours(args):
                                 f"{rec['events_per_launch']} events; issue slots busy {rec.get('issue_active_pct')} %")
         except Exception as exc:  # a malformed file must not break the benchmark
             traffic_note = f"profiles/traffic.json unreadable: {exc}"
-    roofline = {
-        "kernel": dominant, "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 6), "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
-        "bytes_per_event": round(bytes_per_event, 1), "events_per_launch": round(events_per_launch, 1),
-        "avg_launch_ms": round(avg_launch_ms, 4),
-        "note": "path is instruction-issue / shared-memory-atomic bound, not HBM bound (SURVEY.md 8d); profiles/ holds "
-                "the ncu issue-slot utilisation of every kernel",
-        "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage_ms.items()},
-    }  # fmt: skip
+    # The path is bound by instruction issue, not by HBM: the roofline of the dominant kernel is its
+    # issued warp instructions per second (count from the committed ncu capture, scaled to this launch size, over the
+    # launch duration measured live) against 148 SMs x 4 schedulers x 1 warp instruction per clock; the HBM figure of
+    # the whole step (algorithmic bytes over step time against the measured copy bandwidth) stands beside it.
+    rec = None
+    if tj.exists():
+        try:
+            rec = json.loads(tj.read_text()).get(dominant if dominant in ("track_kernel", "deposit_kernel") else "")
+        except Exception:
+            rec = None
+    step_bytes = bytes_per_event * n_ev_rank / args.steps
+    hbm = {"achieved": round(step_bytes / (dev_ms / args.steps * 1e-3) / 1e9, 2), "peak": peak, "unit": "GB/s",
+           "frac": round(step_bytes / (dev_ms / args.steps * 1e-3) / 1e9 / peak, 5), "peak_source": peak_src,
+           "what": "algorithmic bytes of the whole step (8 (4K + 3) + 32 N_out per event) over the step time"}  # fmt: skip
+    sm_mhz = clocks.get("sm_max_mhz") or 1965.0
+    issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9  # G warp instructions / s
+    if rec and rec.get("workload") == args.workload and rec.get("warp_inst_per_launch"):
+        inst = rec["warp_inst_per_launch"] * events_per_launch / rec["events_per_launch"]
+        issue_achieved = inst / (avg_launch_ms * 1e-3) / 1e9
+        roofline = {
+            "kernel": dominant, "bound": "issue", "achieved": round(issue_achieved, 2), "peak": round(issue_peak, 1),
+            "unit": "G warp-instructions/s", "frac": round(issue_achieved / issue_peak, 4),
+            "peak_source": f"148 SMs x 4 schedulers x {sm_mhz:.0f} MHz", "traffic": traffic, "traffic_note": traffic_note,
+            "instructions_note": f"{rec['warp_inst_per_launch']:.4g} warp instructions per {rec['events_per_launch']}-event launch "
+                                 f"({rec['source']}; ncu issue-slot utilisation there: {rec.get('issue_active_pct')} %)",
+            "events_per_launch": round(events_per_launch, 1), "avg_launch_ms": round(avg_launch_ms, 4), "hbm": hbm,
+            "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage_ms.items()},
+        }  # fmt: skip
+    else:
+        roofline = {
+            "kernel": dominant, "bound": "hbm", "achieved": round(achieved, 3), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 6), "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+            "bytes_per_event": round(bytes_per_event, 1), "events_per_launch": round(events_per_launch, 1),
+            "avg_launch_ms": round(avg_launch_ms, 4), "hbm": hbm,
+            "note": "no committed ncu instruction count for this kernel / workload: algorithmic bytes of the path over "
+                    "the kernel's time; the path is instruction-issue bound, not HBM bound (SURVEY.md 8d)",
+            "stage_ms_per_step": {k: round(v / args.steps, 3) for k, v in stage_ms.items()},
+        }  # fmt: skip
     out = {
         "metric": "detector-simulated events/s", "value": round(total_events / dev_s, 1), "unit": "events/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_s / args.steps * 1e3, 3),
@@ -389,10 +454,159 @@ def run_ours(args):
                            "cloud float64[N,3] + int64 labels" if args.float64_rows else
                            "typed columns: pad int16, time bucket uint32 Q16.16, electrons uint32 + list of the counts >= 2^32, label int8"),
                 "d2h_bytes_per_step": int(d2h_total)},
+        "e2e_decoded": None if decoded_s is None else {
+            "value": round(B / decoded_s, 1), "unit": "events/s per rank",
+            "what": "one e2e step plus the host-side decode of the typed columns into the float64 / int64 arrays of the "
+                    "reference's writer protocol (numpy, one thread)"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
     }  # fmt: skip
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(args, momenta, vertices)
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_pipeline(args):
+    """BASELINE config 5 end to end: kinematics -> detector simulation -> host, sharded by event range.
+
+    `--events-total` events (default 10 M) of `--workload` (default c16dd_sweep) are cut into chunks of `--events`;
+    rank r of N takes a contiguous range of chunks (one process per GPU, no collective on the data path).  Per chunk:
+    the vectorised `KinematicsPipeline.run_batch` (two prefetch threads; a chunk's seed depends on the chunk alone, so
+    the events do not depend on N), `simulate_batch` with host inputs and the typed columns back in pinned host memory,
+    and a gather step that keeps the CSR offsets and per-chunk totals.  The real bulk writer (`ParquetCloudWriter`, zstd) is timed on the
+    first `--writer-chunks` chunks of rank 0 into a scratch directory and reported beside it: a full 10 M-event cloud is
+    ~0.9 TB as float64 rows (0.3 TB as typed columns), more than the box can hold or write in minutes.
+    """
+    import queue
+    import shutil
+    import tempfile
+    import threading
+
+    import torch
+
+    from attpc_engine_b200 import nuclear_map
+    from attpc_engine_b200.detector.engine import engine_for
+    from attpc_engine_b200.detector.sharding import shard_range
+    from attpc_engine_b200.detector.simulator import _nuclei_for
+
+    local_env = int(os.environ.get("LOCAL_RANK", "0"))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not args.no_numa:
+        from attpc_engine_b200.detector.sharding import bind_to_gpu_numa_node
+
+        bind_to_gpu_numa_node(local_env)
+    rank, world, local, dist = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
+    name = args.workload
+    B = args.events
+    n_chunks = -(-args.events_total // B)
+    c0, c1 = shard_range(n_chunks, rank, world)
+    config, m0, v0, zs, as_, indices = build_workload(name, 8)
+    eng = engine_for(config, _nuclei_for(zs, as_, indices, nuclear_map), device=local)
+    K = m0.shape[1]
+
+    def kinematics(c):
+        pipeline, _ = make_pipeline(name)  # (cheap: tables are cached per process)
+        pipeline.seed(workload_seed(name, 1000 + c))
+        n = min(B, args.events_total - c * B)
+        t0 = time.perf_counter()
+        vertices, momenta = pipeline.run_batch(n)
+        return c, momenta, vertices, time.perf_counter() - t0
+
+    def producer(chunks, out):
+        for c in chunks:
+            out.put(kinematics(c))
+        out.put(None)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # warm-up: buffers sized, kernels loaded
+    _, m, v, _ = kinematics(c0)
+    for _ in range(max(1, args.warmup)):
+        eng.simulate_batch(m, v, zs, as_, indices, seed=1, first_event=c0 * B, copy=False, columns=True)
+    barrier()
+    wall0 = time.perf_counter()
+    q = queue.Queue(maxsize=4)
+    lanes = 2
+    threads = [threading.Thread(target=producer, args=(range(c0 + k, c1, lanes), q), daemon=True) for k in range(lanes)]
+    for t in threads:
+        t.start()
+    done, t_kin, t_sim, t_gather, events, points, electrons = 0, 0.0, 0.0, 0.0, 0, 0, 0
+    check = np.zeros(2, dtype=np.uint64)
+    while done < lanes:
+        item = q.get()
+        if item is None:
+            done += 1
+            continue
+        c, momenta, vertices, dt = item
+        t_kin += dt
+        t0 = time.perf_counter()
+        batch = eng.simulate_batch(momenta, vertices, zs, as_, indices, seed=20260101, first_event=c * B, copy=False,
+                                   columns=True)  # fmt: skip
+        t1 = time.perf_counter()
+        # gather: what a shard hands to the collector -- the CSR offsets and a checksum over the head of two columns
+        # (reading every byte is the writer's job: see writer_sample)
+        cols = batch.columns
+        check[0] += np.uint64(int(np.add.reduce(cols["pad"][: 1 << 20], dtype=np.int64)) & (2**63 - 1))
+        check[1] += np.uint64(int(batch.offsets[-1]))
+        t2 = time.perf_counter()
+        t_sim += t1 - t0
+        t_gather += t2 - t1
+        events += len(batch)
+        points += batch.stats["n_points"]
+        electrons += batch.stats["n_primary_electrons"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    wall = reduce_max(dist, wall, local)
+    total_events = reduce_sum(dist, events, local)
+    total_points = reduce_sum(dist, points, local)
+    total_electrons = reduce_sum(dist, electrons, local)
+    if rank != 0:
+        return
+    # the real bulk writer on a bounded sample (rank 0)
+    writer_info = None
+    if args.writer_chunks > 0:
+        from attpc_engine_b200.detector import ParquetCloudWriter
+
+        tmp = Path(tempfile.mkdtemp(prefix="attpc_bench_"))
+        try:
+            w = ParquetCloudWriter(tmp)
+            n_w = min(args.writer_chunks, c1 - c0)
+            ev_w = rows_w = 0
+            t_w = 0.0
+            for c in range(c0, c0 + n_w):
+                _, momenta, vertices, _ = kinematics(c)
+                batch = eng.simulate_batch(momenta, vertices, zs, as_, indices, seed=20260101, first_event=c * B,
+                                           copy=False, columns=True)  # fmt: skip
+                t0 = time.perf_counter()
+                w.write_batch(batch, config)
+                t_w += time.perf_counter() - t0
+                ev_w += len(batch)
+                rows_w += batch.stats["n_points"]
+            t0 = time.perf_counter()
+            w.close()
+            t_w += time.perf_counter() - t0
+            size = sum(f.stat().st_size for f in tmp.glob("*.parquet"))
+            writer_info = {"writer": "ParquetCloudWriter (zstd), one process", "events": ev_w, "rows": int(rows_w),
+                           "seconds": round(t_w, 3), "events_per_s": round(ev_w / t_w, 1),
+                           "bytes_written": int(size), "bytes_per_event": round(size / max(1, ev_w), 1)}  # fmt: skip
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+    out = {
+        "metric": "detector-simulated events/s (pipeline: kinematics -> simulate -> host gather)",
+        "value": round(total_events / wall, 1), "unit": "events/s", "n_gpus": world, "higher_is_better": True,
+        "scaling": "strong", "dtype": "f64", "data": "synthetic", "mode": "pipeline",
+        "config": {"workload": f"{name}: {WORKLOADS[name]['desc']}", "events_total": int(total_events),
+                   "events_per_chunk": B, "chunks_per_rank": c1 - c0, "parallelism": f"event-range shards x{world}",
+                   "result": "typed columns in pinned host memory, per-chunk totals gathered"},
+        "wall_s": round(wall, 3), "cloud_points": int(total_points), "electrons_per_s": round(total_electrons / wall, 1),
+        "rank0_seconds": {"kinematics (2 prefetch threads, summed)": round(t_kin, 3), "simulate_batch (host in, host out)": round(t_sim, 3),
+                          "gather": round(t_gather, 3)},
+        "checksum": [int(check[0]), int(check[1])], "writer_sample": writer_info,
+    }  # fmt: skip
     print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -463,11 +677,19 @@ def main():
     ap.add_argument("--no-numa", action="store_true", help="multi-GPU: do not bind each rank to the CPUs next to its GPU")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: only the device-resident steps")
     ap.add_argument("--spyral", action="store_true", help="also produce the Spyral 8-column rows (full pad-plane response)")
+    ap.add_argument("--pipeline", action="store_true",
+                    help="BASELINE config 5: kinematics -> simulate -> host for --events-total events, sharded over the ranks")
+    ap.add_argument("--events-total", type=int, default=10_000_000, help="--pipeline: events of the whole job")
+    ap.add_argument("--writer-chunks", type=int, default=1, help="--pipeline: chunks also written with ParquetCloudWriter (rank 0)")
     ap.add_argument("--float64-rows", action="store_true",
                     help="e2e: bring the cloud back as float64[N,3] + int64 labels (32 B/row) instead of typed columns")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.pipeline:
+        if args.workload == "c16dd":
+            args.workload = "c16dd_sweep"
+        run_pipeline(args)
     else:
         run_ours(args)
 

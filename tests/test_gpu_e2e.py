@@ -162,6 +162,44 @@ def test_run_simulation_with_array_writer(dist, tmp_path):
     assert np.array_equal(np.concatenate([s[1] for s in w.seen]), direct.cloud)
 
 
+def test_run_simulation_over_several_devices(dist, tmp_path):
+    """`run_simulation(devices=[...])`: one worker thread and one engine per entry (here two engines on the one GPU of
+    the test box), event ranges dealt round-robin, the writer fed in event order: the same files as a one-device run."""
+    from attpc_engine_b200.kinematics import save_kinematics_npz
+
+    cfg, m, v, zs, as_, idx = _workload(dist, "c16dd", 150)
+    path = tmp_path / "kin.npz"
+    save_kinematics_npz(path, v, m, zs, as_)
+    one = ArrayWriter(None, cfg, max_events_per_file=1000)
+    run_simulation(cfg, path, one, seed=5, batch_size=16, verbose=False)
+    two = ArrayWriter(None, cfg, max_events_per_file=1000)
+    run_simulation(cfg, path, two, seed=5, batch_size=16, verbose=False, devices=[0, 0, 0])
+    assert len(one.files) == len(two.files) == 1
+    for key in ("event_numbers", "offsets", "rows", "labels"):
+        assert np.array_equal(one.files[0][key], two.files[0][key]), key
+    assert len(one.files[0]["event_numbers"]) > 100
+
+    class PerEvent:  # the reference's per-event protocol, raw clouds
+        def __init__(self):
+            self.seen = []
+
+        def write(self, data, labels, config, event_number):
+            self.seen.append((event_number, data, labels))
+
+        def get_directory_name(self):
+            return tmp_path
+
+        def close(self):
+            pass
+
+    a, b = PerEvent(), PerEvent()
+    run_simulation(cfg, path, a, seed=5, batch_size=32, verbose=False)
+    run_simulation(cfg, path, b, seed=5, batch_size=8, verbose=False, devices=[0, 0])
+    assert [e for e, _, _ in a.seen] == [e for e, _, _ in b.seen] == sorted(e for e, _, _ in a.seen)
+    for (_, c1, l1), (_, c2, l2) in zip(a.seen, b.seen):
+        assert np.array_equal(c1, c2) and np.array_equal(l1, l2)
+
+
 def test_run_simulation_with_parquet_writer(dist, tmp_path):
     """run_simulation -> typed columns over PCIe -> ParquetCloudWriter: the file holds what simulate_batch returns."""
     pytest.importorskip("pyarrow")

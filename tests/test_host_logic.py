@@ -291,3 +291,43 @@ def test_config_fingerprint_sees_every_baked_value():
     assert config_fingerprint(cfg, nuclei) != base
     other_gas = make_config("He4_600")
     assert config_fingerprint(other_gas, nuclei) != base
+
+
+def test_ordered_fan_in_of_the_multi_gpu_driver():
+    """`run_simulation(devices=[...])`: batches come back in order whatever the workers' speed; a worker starts its
+    next batch only after the writer took its previous one (the batch may be a view); errors reach the caller."""
+    import threading
+    import time
+
+    from attpc_engine_b200.detector.simulator import _OrderedFanIn
+
+    log, lock = [], threading.Lock()
+
+    def work(k, g):
+        time.sleep(0.002 * ((7 * k) % 5))  # uneven speeds
+        with lock:
+            log.append(("start", k, g))
+        return k * 10
+
+    fan = _OrderedFanIn(23, [0, 1, 2], work)
+    seen = []
+    for k, batch in fan:
+        with lock:
+            log.append(("take", k))
+        seen.append((k, batch))
+    fan.close()
+    assert seen == [(k, 10 * k) for k in range(23)]
+    for k in range(3, 23):  # worker g = k % 3 started batch k only after batch k - 3 had been taken
+        assert log.index(("take", k - 3)) < log.index(("start", k, k % 3))
+    assert {g for _, k, g in (e for e in log if e[0] == "start") if True} == {0, 1, 2}
+
+    def failing(k, g):
+        if k == 5:
+            raise ValueError("boom")
+        return k
+
+    fan = _OrderedFanIn(9, [0, 1], failing)
+    with pytest.raises(ValueError, match="boom"):
+        for _ in fan:
+            pass
+    fan.close()

@@ -6,7 +6,11 @@ import subprocess
 import sys
 from pathlib import Path
 
+import os
+
 OUT = Path(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out")
+TAG = os.environ.get("TAG", "")  # file prefix of tools/profile_r2.sh, e.g. TAG=r2p -> r2p_launches.csv, r2p_prof_*.ncu-rep
+PRE = TAG + "_" if TAG else ""
 WANT = [
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
     "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -25,7 +29,7 @@ WANT = [
 
 
 def launches():
-    f = OUT / "launches.csv"
+    f = OUT / f"{PRE}launches.csv"
     if not f.exists():
         return
     rows = list(csv.reader(open(f)))
@@ -51,7 +55,7 @@ TRAFFIC = {}
 
 
 def reports():
-    for rep in sorted(OUT.glob("prof_*.ncu-rep")):
+    for rep in sorted(OUT.glob(f"{PRE}prof_*.ncu-rep")):
         txt = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(txt.splitlines()))
         if len(rows) < 3:
@@ -62,12 +66,13 @@ def reports():
             scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             rd, wr = h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
             total = float(rows[2][rd].replace(",", "")) * scale[units[rd]] + float(rows[2][wr].replace(",", "")) * scale[units[wr]]
-            name = rep.name[len("prof_"):-len(".ncu-rep")]
+            name = rep.name[len(PRE + "prof_"):-len(".ncu-rep")]
             TRAFFIC[name] = {
                 "dram_bytes_per_launch": total,
                 "duration_us": rows[2][h.index("gpu__time_duration.sum")] + " " + units[h.index("gpu__time_duration.sum")],
                 "issue_active_pct": round(float(rows[2][h.index("smsp__issue_active.avg.pct_of_peak_sustained_active")]), 1),
                 "grid": rows[2][h.index("launch__grid_size")],
+                "warp_inst_per_launch": float(rows[2][h.index("smsp__inst_executed.sum")].replace(",", "")),
             }
         except (ValueError, KeyError) as exc:
             print("  (no traffic record:", exc, ")")
