@@ -429,7 +429,7 @@ int ensure_spyral_buffers(AttpcSim* sim, int64_t n_events, int64_t n_points, boo
     CU(sim->row_kept.reserve(n_events + 1));
     CU(sim->row_offsets_dev.reserve(n_events + 1));
     CU(sim->row_sort_keys.reserve(n_points * 2));
-    CU(sim->row_sort_idx.reserve(n_points * 2));
+    CU(sim->row_sort_idx.reserve(n_points * 2 + n_events + 1));
     if (f64_rows) {
         CU(sim->rows_dev.reserve(n_points * 8));
         CU(sim->row_labels_dev.reserve(n_points));
@@ -477,6 +477,14 @@ SpyralArgs spyral_args(AttpcSim* sim, int64_t first, int64_t n_events, bool type
 // in device memory: amplitude / threshold count, running row offsets, rows in z order.
 int launch_spyral(AttpcSim* sim, const SpyralArgs& sa) {
     if (sa.n_events <= 0) return ATTPC_OK;
+    if (sa.ctr) {  // inside the pipeline: canonical row order, kept rows per event already counted by emit_kernel
+        const size_t pre_smem = (size_t)SPYRAL_PREFIX_SMEM * sizeof(unsigned);
+        spyral_scan_kernel<<<1, 1024, 0, sim->stream>>>(sa);
+        spyral_ordered_kernel<<<(unsigned)sa.n_events, 256, pre_smem, sim->stream>>>(sim->P, sa);
+        sim->launches += 2;
+        CU(cudaGetLastError());
+        return ATTPC_OK;
+    }
     const size_t smem = (size_t)SPYRAL_SMEM_ITEMS * (sizeof(uint64_t) + sizeof(uint32_t));
     CU(cudaFuncSetAttribute(spyral_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     spyral_count_kernel<<<(unsigned)sa.n_events, 256, 0, sim->stream>>>(sim->P, sa);
@@ -721,6 +729,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 fa.col_electrons = sim->col_q_dev.p;
             }
         }
+        if (spy) fa.row_kept = sim->row_kept.p + b0;
         fa.replay = plan.uniforms;
         if (fa.replay.offsets) fa.replay.offsets += b0;
         fa.n_tracks_per_event = plan.n_tracks_per_event;
@@ -1160,6 +1169,21 @@ int attpc_create(const AttpcConfig* cfg, const int16_t* pad_lut, const double* p
         CUC(cudaMemcpy(sim->resp_prefix.p, prefix.data(), (size_t)(n_response + 1) * sizeof(double),
                        cudaMemcpyHostToDevice));
         P.resp_max = sorted[0];
+        // smallest electron count that passes the ADC threshold (detector/writer.py:232): amp = min(r_max e, 4095) is
+        // monotone in e, so the comparison can be made on the integer charge
+        {
+            const double thr = cfg->adc_threshold;
+            long long keep = 0;
+            if (!(thr < 4095.0)) {
+                keep = INT64_MAX;
+            } else if (thr >= 0.0 && sorted[0] > 0.0) {
+                keep = std::max<long long>(0, (long long)std::floor(thr / sorted[0]) - 2);
+                while (!(std::fmin(sorted[0] * (double)keep, 4095.0) > thr)) ++keep;
+            } else if (thr >= 0.0) {
+                keep = INT64_MAX;  // a null response never passes a non-negative threshold
+            }
+            P.e_keep_min = keep;
+        }
     }
     {
         // deceleration tables: dE/dx [MeV/(g/cm^2)] * MEV_2_JOULE * density * 100 / m_kg / c  (detector/solver.py:64-76)

@@ -66,6 +66,7 @@ struct SimParams {
     const double* resp_sorted;   // response sorted descending
     const double* resp_prefix;   // prefix sums of resp_sorted, [n_response + 1]
     double resp_max;
+    long long e_keep_min;     // smallest electron count whose amplitude min(resp_max * e, 4095) exceeds adc_threshold
     double mesh_w[MESH_N * MESH_N];  // (2 / (9 pi)) exp(-(a_i^2 + a_j^2) / 2), a_i = -3 + 6 i / 9: pdf * step^2 of the mesh
     double mesh_w_unique[MESH_N * MESH_N];  // its distinct values (15 for the symmetric 10 x 10 mesh)
     int32_t n_mesh_w_unique, pad1;
@@ -1564,6 +1565,7 @@ struct FinalizeArgs {
     int64_t* big_electrons;
     unsigned long long* big_count;  // running number of exceptions of the call (also counts what did not fit)
     int64_t big_cap;
+    unsigned* row_kept;       // [launch events] rows above the ADC threshold (Spyral passes follow), or null
 };
 
 constexpr uint32_t F_KEEP_ALL_TB = 1u, F_SPYRAL = 2u, F_NO_WIGGLE = 4u;
@@ -1820,14 +1822,19 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
     const int slot_event = gv.first_slot + e;
     const int n = (int)fa.kept[slot_event];
     const int64_t off = fa.offsets[slot_event];
-    if (off + n > fa.out_cap) return;
+    if (off + n > fa.out_cap) {
+        if (fa.row_kept && threadIdx.x == 0) fa.row_kept[slot_event] = 0;
+        return;
+    }
     const HashEntry* tab = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
     const uint64_t* items = fa.sort_items + (int64_t)(gv.chunk_e0 + e) * 2 * gv.hash_cap;
+    unsigned above = 0;  // rows whose amplitude passes the ADC threshold (detector/writer.py:232)
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint64_t it = items[i];
         const unsigned tb = (unsigned)(it >> 47), pad = (unsigned)(it >> 32) & 0x7FFFu;
         const unsigned key = szudzik_pair(tb, pad);
         const HashEntry en = tab[(unsigned)it];
+        above += (long long)en.charge >= P.e_keep_min;
         const double u = wiggle_of(fa, slot_event, key, ctr);
         const double tbf = (double)tb + u;
         const int64_t label = fa.label_of_event_rank
@@ -1856,6 +1863,15 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
                 }
             }
         }
+    }
+    if (fa.row_kept) {
+        __shared__ unsigned s_above;
+        if (threadIdx.x == 0) s_above = 0;
+        __syncthreads();
+        above = __reduce_add_sync(FULL, above);
+        if ((threadIdx.x & 31) == 0 && above) atomicAdd(&s_above, above);
+        __syncthreads();
+        if (threadIdx.x == 0) fa.row_kept[slot_event] = s_above;
     }
 }
 
@@ -2079,6 +2095,88 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
         row[6] = tbf;
         row[7] = P.pad_scale[pad];
         sa.row_labels[out0 + place] = sa.labels[src];
+    }
+}
+
+// The Spyral rows of clouds that are in the engine's canonical order (ascending time bucket, then pad): detector/
+// writer.py:232-238 without a sort.  z falls as the time bucket rises, so the z order is the time buckets backwards and,
+// inside a bucket, the wiggle backwards; the rows of a bucket are neighbours in the cloud.  A kept row goes to
+//   (kept rows in later buckets) + (kept rows of its own bucket with a larger time, or the same time and a lower index)
+// where the first term is the event's kept total minus the running count of kept rows at the end of the bucket.
+// sa.kept holds the kept rows per event (counted by emit_kernel), sa.row_offsets their running sum.
+constexpr int SPYRAL_PREFIX_SMEM = 8192;  // rows of an event whose running counts fit shared memory (32 KB)
+
+__global__ void __launch_bounds__(256) spyral_ordered_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
+    extern __shared__ unsigned s_pre[];  // [n + 1] kept rows before row i
+    __shared__ unsigned s_warp[8];
+    __shared__ unsigned s_run;
+    const int64_t e = sa.first + blockIdx.x;
+    const int kept = (int)sa.kept[e];
+    if (kept == 0) return;
+    const int64_t a = sa.offsets[e];
+    const int n = (int)(sa.offsets[e + 1] - a);
+    const int64_t out0 = sa.row_offsets[e];
+    unsigned* pre = n + 1 <= SPYRAL_PREFIX_SMEM ? s_pre : sa.sort_idx + a + e;  // (global scratch: n + 1 words per event)
+    const double* cloud = sa.cloud + a * 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double keep_min = (double)P.e_keep_min;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < n; t0 += 256) {
+        const int i = t0 + threadIdx.x;
+        const bool keep = i < n && cloud[i * 3 + 2] >= keep_min;
+        const unsigned m = __ballot_sync(FULL, keep);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        unsigned before = s_run + __popc(m & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) before += s_warp[w];
+        if (i < n) pre[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 255) s_run = before + (keep ? 1u : 0u);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) pre[n] = s_run;
+    __syncthreads();
+    const double span = (double)(P.win_edge - P.mm_edge);
+    for (int i = threadIdx.x; i < n; i += 256) {
+        if (pre[i + 1] == pre[i]) continue;  // below the ADC threshold
+        const double padf = cloud[i * 3], tbf = cloud[i * 3 + 1], el = cloud[i * 3 + 2];
+        const int tb = (int)tbf;
+        unsigned within = 0;
+        int j = i - 1;
+        for (; j >= 0; --j) {
+            const double tj = cloud[j * 3 + 1];
+            if ((int)tj != tb) break;
+            within += (pre[j + 1] != pre[j]) && tj >= tbf;  // (same time: the lower index goes first)
+        }
+        for (j = i + 1; j < n; ++j) {
+            const double tj = cloud[j * 3 + 1];
+            if ((int)tj != tb) break;
+            within += (pre[j + 1] != pre[j]) && tj > tbf;
+        }
+        const int64_t at = out0 + ((unsigned)kept - pre[j]) + within;  // pre[j]: kept rows up to the end of this bucket
+        const int pad = (int)padf;
+        if (sa.out_pad) {  // typed columns: what the eight columns are functions of
+            const unsigned long long q = (unsigned long long)(long long)el;
+            sa.out_pad[at] = (int16_t)pad;
+            sa.out_tb_q16[at] = (uint32_t)(tbf * 65536.0);  // exact for the library's 16-bit wiggle
+            sa.out_e_lo[at] = (uint32_t)q;
+            sa.out_e_hi[at] = (uint16_t)(q >> 32);
+            sa.out_label[at] = (int8_t)sa.labels[a + i];
+            continue;
+        }
+        double amp, integral;
+        shaped(P, el, amp, integral);
+        double* row = sa.rows + at * 8;
+        row[0] = P.pad_xy[2 * pad];
+        row[1] = P.pad_xy[2 * pad + 1];
+        row[2] = __dmul_rn(__dmul_rn(__ddiv_rn(__dsub_rn(P.win_edge, tbf), span), P.length), 1000.0);
+        row[3] = amp;
+        row[4] = integral;
+        row[5] = padf;
+        row[6] = tbf;
+        row[7] = P.pad_scale[pad];
+        sa.row_labels[at] = sa.labels[a + i];
     }
 }
 

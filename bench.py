@@ -612,6 +612,63 @@ def run_pipeline(args):
         dist.destroy_process_group()
 
 
+def run_threads(args):
+    """e2e with ONE process and one thread + engine per GPU (the `run_simulation(devices=[...])` arrangement), as a
+    counterpart to the one-process-per-GPU launch: does the host-side limit of a multi-GPU box depend on it?"""
+    import threading
+
+    import torch
+
+    from attpc_engine_b200 import nuclear_map
+    from attpc_engine_b200.detector.engine import engine_for
+    from attpc_engine_b200.detector.simulator import _nuclei_for
+
+    G, B = args.thread_gpus, args.events
+    config, momenta, vertices, zs, as_, indices = build_workload(args.workload, B)
+    nuclei = _nuclei_for(zs, as_, indices, nuclear_map)
+    engines = [engine_for(config, nuclei, device=g, instance=g, max_events_per_launch=args.launch_events,
+                          copy_events_per_launch=args.copy_events) for g in range(G)]  # fmt: skip
+    pins = [(torch.from_numpy(momenta).pin_memory(), torch.from_numpy(vertices).pin_memory()) for _ in range(G)]
+    barrier = threading.Barrier(G + 1)
+    spans, errors = [None] * G, []
+
+    def worker(g):
+        try:
+            torch.cuda.set_device(g)
+            m, v = pins[g]
+            for i in range(args.warmup):
+                engines[g].simulate_batch(m.numpy(), v.numpy(), zs, as_, indices, seed=i, first_event=g * B, copy=False,
+                                          columns=not args.float64_rows)  # fmt: skip
+            barrier.wait()
+            t0 = time.perf_counter()
+            pts = 0
+            for i in range(args.steps):
+                st = engines[g].simulate_batch(m.numpy(), v.numpy(), zs, as_, indices, seed=100 + i, first_event=g * B,
+                                               copy=False, columns=not args.float64_rows).stats  # fmt: skip
+                pts += st["n_points"]
+            spans[g] = (t0, time.perf_counter(), pts)
+        except BaseException as exc:  # noqa: BLE001
+            errors.append(exc)
+            barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(g,)) for g in range(G)]
+    for t in threads:
+        t.start()
+    barrier.wait()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    wall = max(s[1] for s in spans) - min(s[0] for s in spans)
+    points = sum(s[2] for s in spans)
+    out = {"metric": "detector-simulated events/s", "mode": "one process, one thread per GPU", "n_gpus": G,
+           "e2e": {"value": round(G * B * args.steps / wall, 1), "unit": "events/s",
+                   "d2h_bytes_per_step": int(points / args.steps * (32 if args.float64_rows else 11))},
+           "d2h_GBps": round(points * (32 if args.float64_rows else 11) / wall / 1e9, 2), "steps": args.steps,
+           "config": {"workload": args.workload, "events_per_gpu_per_step": B}}  # fmt: skip
+    print(json.dumps(out), flush=True)
+
+
 def cpu_baseline(args, momenta, vertices):
     arm = CpuArm(args.workload, args.cpu_cores or None)
     n = min(len(momenta), max(64, args.cpu_events_per_core * arm.cores))
@@ -681,11 +738,15 @@ def main():
                     help="BASELINE config 5: kinematics -> simulate -> host for --events-total events, sharded over the ranks")
     ap.add_argument("--events-total", type=int, default=10_000_000, help="--pipeline: events of the whole job")
     ap.add_argument("--writer-chunks", type=int, default=1, help="--pipeline: chunks also written with ParquetCloudWriter (rank 0)")
+    ap.add_argument("--thread-gpus", type=int, default=0,
+                    help="e2e only: ONE process with a thread and an engine per GPU (0 = off)")
     ap.add_argument("--float64-rows", action="store_true",
                     help="e2e: bring the cloud back as float64[N,3] + int64 labels (32 B/row) instead of typed columns")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.thread_gpus > 0:
+        run_threads(args)
     elif args.pipeline:
         if args.workload == "c16dd":
             args.workload = "c16dd_sweep"

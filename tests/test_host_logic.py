@@ -331,3 +331,55 @@ def test_ordered_fan_in_of_the_multi_gpu_driver():
         for _ in fan:
             pass
     fan.close()
+
+
+def test_hdf5_kinematics_reader_on_a_reference_written_file(monkeypatch):
+    """`_Hdf5Kinematics` (`detector/simulator.py:146-196` of the reference) on a file the REFERENCE's own
+    `run_kinematics_pipeline` wrote (tests/golden/make_kinematics_file.py; h5py replaced by the in-memory stand-in,
+    23 events in four chunk groups): attributes, chunk arithmetic, datasets and vertex attributes."""
+    import sys
+    import types
+
+    from attpc_engine_b200.detector.simulator import _Hdf5Kinematics, default_indices
+    from tests.common import GOLDEN
+
+    sys.path.insert(0, str(GOLDEN))
+    import ref_shim
+
+    with np.load(GOLDEN / "kinematics_file.npz") as f:
+        flat = {k: f[k] for k in f.files}
+    root = ref_shim.MemGroup()
+
+    def node(path):  # "/data/chunk_0" -> the MemGroup, created on the way
+        cur = root
+        for part in [p for p in path.split("/") if p]:
+            if part not in cur:
+                cur.create_group(part)
+            cur = cur[part]
+        return cur
+
+    for key in sorted(flat):
+        kind, path, *rest = key.split("|")
+        if kind == "group":
+            node(path)
+        elif kind == "data":
+            parent, name = path.rsplit("/", 1)
+            node(parent).create_dataset(name, data=flat[key])
+    for key in sorted(flat):
+        kind, path, *rest = key.split("|")
+        if kind == "attr":
+            parent, name = path.rsplit("/", 1) if "/" in path.strip("/") else ("", path.strip("/"))
+            target = node(parent)[name] if name in node(parent) else node(path)
+            value = flat[key]
+            target.attrs[rest[0]] = value.item() if value.ndim == 0 else value
+    fake = types.ModuleType("h5py")
+    fake.File = lambda path, mode="r": root
+    monkeypatch.setitem(sys.modules, "h5py", fake)
+    kin = _Hdf5Kinematics("whatever.h5")
+    assert kin.n_events == 23 and kin.chunk_size == 7
+    assert list(kin.proton_numbers) == [1, 6, 1, 6, 6, 0] and list(kin.mass_numbers) == [2, 14, 1, 15, 14, 1]
+    assert default_indices(len(kin.proton_numbers)) == [2, 4, 5]
+    data, vertices = kin.read(0, 23)
+    assert np.array_equal(data, flat["expected|momenta"]) and np.array_equal(vertices, flat["expected|vertices"])
+    data, vertices = kin.read(5, 16)  # a range that crosses two chunk boundaries
+    assert np.array_equal(data, flat["expected|momenta"][5:16]) and np.array_equal(vertices, flat["expected|vertices"][5:16])
