@@ -139,6 +139,7 @@ struct AttpcSim {
     int32_t max_units = 0;
     DevArray<HashEntry> hash;
     DevArray<uint64_t> sort_items;
+    DevArray<uint4> staged;  // ordered rows of the chunk's events between order_kernel and emit_kernel
     DevArray<unsigned> kept;
     DevArray<double> in_momenta, in_vertices;
 
@@ -223,6 +224,10 @@ int next_pow2(int64_t v) {
     return (int)p;
 }
 
+// 64-bit words of scratch per event for the entry lists that finalize_kernel cannot order in shared memory: two item
+// arrays and two bit-mask / running-count arrays
+int64_t scratch_stride(int64_t hash_cap) { return 2 * hash_cap + hash_cap / 32 + 2; }
+
 int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
     if (sim->group_point_cap == 0) sim->group_point_cap = (int64_t)sim->group_events * 1024;
@@ -256,7 +261,8 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     const int64_t copy_groups = (sim->copy_launch_events + sim->group_events - 1) / sim->group_events;
     const int64_t table_groups = std::min<int64_t>(n_groups, std::max<int64_t>(sim->chunk_groups, copy_groups));
     CU(sim->hash.reserve(table_groups * sim->group_events * sim->hash_cap));
-    CU(sim->sort_items.reserve(table_groups * sim->group_events * sim->hash_cap * 2));
+    CU(sim->sort_items.reserve(table_groups * sim->group_events * scratch_stride(sim->hash_cap)));
+    CU(sim->staged.reserve(table_groups * sim->group_events * sim->hash_cap));
     CU(sim->csr_total.reserve(3));  // cloud rows, electron counts >= 2^32, Spyral rows
     CU(sim->csr_host.reserve(3));
     CU(sim->chunk_totals.reserve(2 * (n_groups + 1)));
@@ -358,8 +364,10 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
     Counters* ctr = sim->slot[which].counters.p;
     const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
     fa.sort_items = sim->sort_items.p;
-    const size_t sort_smem = (size_t)SORT_SMEM_ITEMS * sizeof(uint64_t);
-    CU(cudaFuncSetAttribute(collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem));
+    fa.scratch_stride = scratch_stride(sim->hash_cap);
+    fa.staged = sim->staged.p;
+    fa.csr_total = sim->csr_total.p;
+    CU(cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM_BYTES));
     CU(cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEPOSIT_SMEM_BYTES));
     // Groups are processed in chunks: every kernel is launched once per chunk with one grid row per group, so the
     // ramp-up and tail of a launch are paid once per chunk.  When rows go to the host a chunk is what is copied while
@@ -379,7 +387,6 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         gv.group_events = sim->group_events;
         gv.chunk_e0 = 0;
         gv.spill_keys = sim->spill_keys;
-        const dim3 per_event((unsigned)std::min<int64_t>(sim->group_events, gv.n_events), (unsigned)ng);
         cudaEvent_t d0 = sim->mark();
         point_scan_kernel<<<(unsigned)ng, 1024, 0, sim->stream>>>(pb, gv, ctr);
         point_order_kernel<<<dim3((unsigned)std::max<int64_t>(1, sim->sm_count * 4 / ng), (unsigned)ng), 256, 0,
@@ -389,11 +396,11 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         deposit_kernel<<<dim3((unsigned)sim->max_units, (unsigned)ng), DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES,
                          sim->stream>>>(sim->P, pb, gv, ctr);
         cudaEvent_t d1 = sim->mark();
-        collect_kernel<<<per_event, FINALIZE_THREADS, sort_smem, sim->stream>>>(sim->P, fa, gv, ctr);
-        scan_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, ctr, sim->csr_total.p);
-        emit_kernel<<<per_event, FINALIZE_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
+        order_kernel<<<(unsigned)gv.n_events, FIN_THREADS, FIN_SMEM_BYTES, sim->stream>>>(sim->P, fa, gv, ctr);
+        offsets_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, ctr);
+        emit_kernel<<<(unsigned)gv.n_events, EMIT_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
         sim->launches += 6;
-        if (spyral) {  // electronics response, ADC threshold, z order of the chunk's events (detector/writer.py:61-112, 232-238)
+        if (spyral) {  // replayed uniforms have 53 bits: the Spyral passes read the float64 cloud instead (parity tests)
             int rc = launch_spyral(sim, spyral_args(sim, launch_first_event + gv.first_slot, gv.n_events, spyral->typed, false, ctr));
             if (rc) return rc;
         }
@@ -429,7 +436,7 @@ int ensure_spyral_buffers(AttpcSim* sim, int64_t n_events, int64_t n_points, boo
     CU(sim->row_kept.reserve(n_events + 1));
     CU(sim->row_offsets_dev.reserve(n_events + 1));
     CU(sim->row_sort_keys.reserve(n_points * 2));
-    CU(sim->row_sort_idx.reserve(n_points * 2 + n_events + 1));
+    CU(sim->row_sort_idx.reserve(n_points * 2));
     if (f64_rows) {
         CU(sim->rows_dev.reserve(n_points * 8));
         CU(sim->row_labels_dev.reserve(n_points));
@@ -477,14 +484,6 @@ SpyralArgs spyral_args(AttpcSim* sim, int64_t first, int64_t n_events, bool type
 // in device memory: amplitude / threshold count, running row offsets, rows in z order.
 int launch_spyral(AttpcSim* sim, const SpyralArgs& sa) {
     if (sa.n_events <= 0) return ATTPC_OK;
-    if (sa.ctr) {  // inside the pipeline: canonical row order, kept rows per event already counted by emit_kernel
-        const size_t pre_smem = (size_t)SPYRAL_PREFIX_SMEM * sizeof(unsigned);
-        spyral_scan_kernel<<<1, 1024, 0, sim->stream>>>(sa);
-        spyral_ordered_kernel<<<(unsigned)sa.n_events, 256, pre_smem, sim->stream>>>(sim->P, sa);
-        sim->launches += 2;
-        CU(cudaGetLastError());
-        return ATTPC_OK;
-    }
     const size_t smem = (size_t)SPYRAL_SMEM_ITEMS * (sizeof(uint64_t) + sizeof(uint32_t));
     CU(cudaFuncSetAttribute(spyral_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     spyral_count_kernel<<<(unsigned)sa.n_events, 256, 0, sim->stream>>>(sim->P, sa);
@@ -565,7 +564,11 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     const bool spy = spy_cols || spy_rows;
     const bool copy_cloud = copy_host && !use_columns && !((flags & ATTPC_SKIP_CLOUD_COPY) && spy);
     // the float64 rows on the device: the product of a device-resident call, the input of the Spyral passes
-    const bool want_cloud = !use_columns || spy;
+    // (replayed 53-bit uniforms and unmasked time buckets: separate passes over the float64 cloud)
+    const bool spy_fused = spy && !plan.replay && !(flags & ATTPC_KEEP_ALL_TB);
+    // nobody reads the float64 rows when the call returns typed columns, or only the Spyral rows, to the host
+    const bool cloud_unread = copy_host && (use_columns || ((flags & ATTPC_SKIP_CLOUD_COPY) && spy));
+    const bool want_cloud = !cloud_unread || (spy && !spy_fused);
     if (use_columns) sim->columns = true;
     int64_t out_cap = std::max<int64_t>(sim->labels_dev.n, std::max<int64_t>(n_events * 2048, 1 << 20));
     int rc = ensure_out_buffers(sim, n_events, out_cap, false);
@@ -729,7 +732,21 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 fa.col_electrons = sim->col_q_dev.p;
             }
         }
-        if (spy) fa.row_kept = sim->row_kept.p + b0;
+        if (spy_fused) {
+            fa.spyral = spy_cols ? 1u : 2u;
+            fa.row_kept = sim->row_kept.p + b0;
+            fa.row_offsets = sim->row_offsets_dev.p + b0;
+            if (spy_cols) {
+                fa.rcol_pad = sim->rcol_pad_dev.p;
+                fa.rcol_tb_q16 = sim->rcol_tbq_dev.p;
+                fa.rcol_e_lo = sim->rcol_elo_dev.p;
+                fa.rcol_e_hi = sim->rcol_ehi_dev.p;
+                fa.rcol_label = sim->rcol_label_dev.p;
+            } else {
+                fa.rows = sim->rows_dev.p;
+                fa.row_labels = sim->row_labels_dev.p;
+            }
+        }
         fa.replay = plan.uniforms;
         if (fa.replay.offsets) fa.replay.offsets += b0;
         fa.n_tracks_per_event = plan.n_tracks_per_event;
@@ -743,7 +760,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         const size_t ord_before = ord_marks.size();
         std::vector<ChunkFence> fences;
         rc = run_groups(sim, nb, fa, which, ord_marks, dep_marks, fin_marks, groups_per_chunk,
-                        copy_host ? &fences : nullptr, spy ? &spyral_pass : nullptr, b0);
+                        copy_host ? &fences : nullptr, spy && !spy_fused ? &spyral_pass : nullptr, b0);
         if (rc) return rc;
         publish_kernel<<<1, 1, 0, G>>>(ls.counters.p, sim->csr_total.p, ls.counters_host.p, sim->csr_host.p);
         sim->launches += 1;
@@ -845,6 +862,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 sim->hash_cap *= 2;
                 sim->hash.release();
                 sim->sort_items.release();
+                sim->staged.release();
             }
             if (now.overflow_out) {
                 out_cap = std::max<int64_t>(sim->labels_dev.n * 2, (int64_t)sim->csr_host.p[0] + (1 << 20));
@@ -1044,7 +1062,7 @@ void attpc_destroy(AttpcSim* sim) {
     if (sim->stream_c) cudaStreamDestroy(sim->stream_c);
     sim->lut.release(); sim->pad_xy.release(); sim->pad_scale.release(); sim->response.release();
     sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release(); sim->stop_ns.release(); sim->plan_cls.release(); sim->plan_counts.release(); sim->plan_order.release();
-    sim->hash.release(); sim->sort_items.release();
+    sim->hash.release(); sim->sort_items.release(); sim->staged.release();
     sim->geom.release(); sim->rec.release();
     sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release(); sim->unit_order.release();
     sim->n_units.release();

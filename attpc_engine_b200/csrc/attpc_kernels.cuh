@@ -24,6 +24,16 @@
 
 #include "philox.cuh"
 
+#ifndef ATTPC_FIN_THREADS
+#define ATTPC_FIN_THREADS 512  // threads of a finalize CTA (one event)
+#endif
+#ifndef ATTPC_FIN_MIN_CTAS
+#define ATTPC_FIN_MIN_CTAS 2   // CTAs per SM the register allocation of order_kernel aims at
+#endif
+#ifndef ATTPC_FIN_ITEMS
+#define ATTPC_FIN_ITEMS 5120   // longest entry list ordered in shared memory (12 B per entry)
+#endif
+
 namespace attpc {
 
 constexpr int MAX_SPECIES = 8;
@@ -1296,7 +1306,7 @@ __device__ __forceinline__ unsigned long long smem_charge_of(const SmemTable& t,
 // open-addressing table: the insert code (probe loop, two atomics) runs once per 32 runs instead of once per 32
 // pixels.  The table is appended to the event's entry list as a dense segment whenever it reaches the spill threshold
 // and at the end; events deposited in several segments (dense events, events split over several units) may then list
-// a key several times, which collect_kernel merges after sorting.
+// a key several times, which order_kernel merges after sorting.
 __global__ void __launch_bounds__(DEPOSIT_THREADS, 4)
 deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk, Counters* ctr) {
     const GroupView gv = sub_group(chunk, blockIdx.y);
@@ -1367,7 +1377,7 @@ deposit_kernel(const __grid_constant__ SimParams P, PointBuf pb, GroupView chunk
     // Append the table as one dense SEGMENT to the event's entry list and clear it (all threads, after a barrier that
     // follows every warp's publish_new_keys).  The position comes from the event's entry counter, which the units
     // of a split event share.  A key can then sit in several segments of the list: gv.mode marks such events and
-    // collect_kernel merges the copies after sorting (integer adds commute, the label is a maximum).
+    // order_kernel merges the copies after sorting (integer adds commute, the label is a maximum).
     auto append_segment = [&](bool last) {
         if (threadIdx.x == 0) {
             s_base = atomicAdd(&gv.n_entries[slot_event], s_nkeys);
@@ -1544,7 +1554,7 @@ struct FinalizeArgs {
     int32_t label_of_rank[MAX_TRACKS_PER_EVENT];
     const int32_t* label_of_event_rank;  // replay: [n_events, n_tracks_per_event] or null
     ReplayUniforms replay;
-    uint64_t* sort_items;     // [group_events][2 * hash_cap] scratch: ordered items, then unordered survivors
+    uint64_t* sort_items;     // [chunk events][scratch_stride] scratch of the events whose lists do not fit shared memory
     unsigned* kept;           // [launch events] rows kept per event
     int64_t* offsets;         // [launch events + 1] CSR offsets (global across groups of the launch)
     double* cloud;            // [out_cap, 3]
@@ -1565,10 +1575,27 @@ struct FinalizeArgs {
     int64_t* big_electrons;
     unsigned long long* big_count;  // running number of exceptions of the call (also counts what did not fit)
     int64_t big_cap;
-    unsigned* row_kept;       // [launch events] rows above the ADC threshold (Spyral passes follow), or null
+    unsigned long long* csr_total;  // running totals of the call {cloud rows, electron counts >= 2^32, Spyral rows}
+    uint4* staged;            // [chunk events][hash_cap] ordered rows of every event, 16 B each (order_kernel -> emit_kernel):
+                              //   x = time bucket << 16 | wiggle (16 bit);  y = electrons, low 32 bits;
+                              //   z = electrons bits 32..47 | pad << 16 | above-ADC-threshold << 31;  w = track rank | z-order place << 4
+    int64_t scratch_stride;   // 64-bit words of sort_items per event
+    // Spyral rows of the same events (detector/writer.py:61-112, 232-238), thresholded and in z order: 0 = none,
+    // 1 = typed columns (rcol_*), 2 = float64 rows
+    uint32_t spyral, pad_;
+    unsigned* row_kept;       // [launch events] rows above the ADC threshold
+    int64_t* row_offsets;     // [launch events + 1]
+    double* rows;             // [out_cap, 8]
+    int64_t* row_labels;
+    int16_t* rcol_pad;
+    uint32_t* rcol_tb_q16;
+    uint32_t* rcol_e_lo;
+    uint16_t* rcol_e_hi;
+    int8_t* rcol_label;
 };
 
 constexpr uint32_t F_KEEP_ALL_TB = 1u, F_SPYRAL = 2u, F_NO_WIGGLE = 4u;
+constexpr int TB_BINS = 1024;  // counting-sort bins over the integer time bucket (last bin collects tb >= 1023)
 
 __device__ __forceinline__ double wiggle_of(const FinalizeArgs& fa, int slot_event, unsigned key, Counters* ctr) {
     if (fa.flags & F_NO_WIGGLE) return 0.0;
@@ -1584,295 +1611,6 @@ __device__ __forceinline__ double wiggle_of(const FinalizeArgs& fa, int slot_eve
         return 0.0;
     }
     return philox_uniform16(fa.seed, (uint64_t)(fa.first_event + slot_event), STREAM_WIGGLE, key);
-}
-
-constexpr int FINALIZE_THREADS = 256;
-constexpr int SORT_SMEM_ITEMS = 6144;  // 48 KB of shared memory for the in-CTA ordering
-constexpr int TB_BINS = 1024;          // counting-sort bins over the integer time bucket (last bin collects tb >= 1023)
-
-// Canonical row order of an event: ascending (time bucket, pad).  64-bit item = (tb << 47) | (pad << 32) | slot
-// (pad ids are int16 in the pad grid, so 15 bits hold them).
-__device__ __forceinline__ uint64_t make_item(unsigned tb, unsigned pad, unsigned slot) {
-    return ((uint64_t)tb << 47) | ((uint64_t)pad << 32) | (uint64_t)slot;
-}
-
-// One CTA per event: gather the occupied slots that survive the time-bucket mask (detector/simulator.py:104-113)
-// and put them in canonical order: counting sort on the time bucket (exact, O(n)), then rank-by-counting inside each
-// bucket's handful of pads.  No power-of-two padding and no dependence on which thread found which slot.
-__global__ void __launch_bounds__(FINALIZE_THREADS)
-collect_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView chunk,
-               Counters* ctr) {
-    const GroupView gv = sub_group(chunk, blockIdx.y);
-    if ((int)blockIdx.x >= gv.n_events) return;
-    extern __shared__ uint64_t s_items[];
-    __shared__ unsigned s_hist[TB_BINS + 1];
-    __shared__ unsigned s_fill[TB_BINS];
-    __shared__ unsigned s_n, s_keys;
-    const int e = blockIdx.x;
-    const int slot_event = gv.first_slot + e;
-    if (ctr->overflow_points | ctr->overflow_hash) {  // this attempt is void: nothing below may be trusted
-        if (threadIdx.x == 0) fa.kept[slot_event] = 0u;
-        return;
-    }
-    const HashEntry* tab = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
-    uint64_t* sorted = fa.sort_items + (int64_t)(gv.chunk_e0 + e) * 2 * gv.hash_cap;  // final order, read by emit_kernel
-    uint64_t* stash = sorted + gv.hash_cap;                           // unordered survivors
-    for (int i = threadIdx.x; i <= TB_BINS; i += blockDim.x) s_hist[i] = 0;
-    if (threadIdx.x == 0) {
-        s_n = 0;
-        s_keys = 0;
-    }
-    __syncthreads();
-    unsigned occupied = 0;
-    const bool dup = gv.mode[slot_event] != 0u;  // the list may hold a key several times
-    const int limit = (int)min(gv.n_entries[slot_event], (unsigned)gv.hash_cap);
-    auto take = [&](int i, unsigned key1) {
-        if (key1 == 0u) return;
-        occupied += 1;
-        const unsigned tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
-        // detector/simulator.py:108-113: keep 0 <= tb + u < 512 with u in [0, 1).  Only the last bucket needs u (a
-        // replayed 53-bit uniform can round 511 + u up to 512.0); emit_kernel draws the wiggle of the rows it writes.
-        bool keep = (fa.flags & F_KEEP_ALL_TB) || tb < (unsigned)NUM_TB - 1u;
-        if (!keep && tb == (unsigned)NUM_TB - 1u) {
-            const unsigned key = szudzik_pair(tb, pad);  // detector/pairing.py: id of the (tb, pad) cell
-            keep = (double)tb + wiggle_of(fa, slot_event, key, ctr) < (double)NUM_TB;
-        }
-        if (keep) {
-            atomicAdd(&s_hist[min(tb, (unsigned)TB_BINS - 1u)], 1u);
-            stash[atomicAdd(&s_n, 1u)] = make_item(tb, pad, (unsigned)i);
-        }
-    };
-    for (int i0 = threadIdx.x; i0 < limit; i0 += 4 * blockDim.x) {  // four loads in flight per thread
-        unsigned k[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * (int)blockDim.x;
-            k[u] = i < limit ? tab[i].key1 : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) take(i0 + u * (int)blockDim.x, k[u]);
-    }
-    if (occupied) atomicAdd(&s_keys, occupied);
-    __syncthreads();
-    const int n = (int)s_n;
-    if (threadIdx.x == 0) {
-        fa.kept[slot_event] = (unsigned)n;  // (events with copies: corrected after the merge below)
-        atomicAdd(&ctr->keys, (unsigned long long)s_keys);
-    }
-    if (n == 0) return;
-    // exclusive scan of the histogram: 4 bins per thread, warp scan, carry across warps through shared memory
-    {
-        const int b0 = threadIdx.x * (TB_BINS / FINALIZE_THREADS);
-        unsigned local[TB_BINS / FINALIZE_THREADS], sum = 0;
-#pragma unroll
-        for (int k = 0; k < TB_BINS / FINALIZE_THREADS; ++k) {
-            local[k] = s_hist[b0 + k];
-            sum += local[k];
-        }
-        unsigned incl = sum;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
-        }
-        __shared__ unsigned s_warp[FINALIZE_THREADS / 32];
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        unsigned base = incl - sum;
-        for (int w = 0; w < warp; ++w) base += s_warp[w];
-#pragma unroll
-        for (int k = 0; k < TB_BINS / FINALIZE_THREADS; ++k) {
-            s_hist[b0 + k] = base;
-            s_fill[b0 + k] = base;
-            base += local[k];
-        }
-        if (threadIdx.x == FINALIZE_THREADS - 1) s_hist[TB_BINS] = base;
-        __syncthreads();
-    }
-    const bool in_smem = n <= SORT_SMEM_ITEMS;
-    uint64_t* buf = in_smem ? s_items : sorted;  // bucketed, unordered inside a bucket
-    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * blockDim.x) {  // four loads in flight per thread
-        uint64_t it[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * (int)blockDim.x;
-            it[u] = i < n ? stash[i] : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (i0 + u * (int)blockDim.x < n)
-                buf[atomicAdd(&s_fill[min((unsigned)(it[u] >> 47), (unsigned)TB_BINS - 1u)], 1u)] = it[u];
-    }
-    __syncthreads();
-    // order every bucket: one thread per item counts the smaller pads of its bucket (items are distinct; a bucket
-    // holds the pads hit in one time bucket, a handful for most tracks, so neighbouring threads walk the same few
-    // items and the reads are broadcasts)
-    uint64_t* dst = in_smem ? sorted : stash;
-    const uint32_t* key_words = reinterpret_cast<const uint32_t*>(buf) + 1;  // (tb << 15) | pad of item j at [2 j]
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint64_t v = buf[i];
-        const unsigned bin = min((unsigned)(v >> 47), (unsigned)TB_BINS - 1u);
-        const int lo = (int)s_hist[bin], hi = (int)s_hist[bin + 1];
-        int rank = 0;
-        if (!dup) {  // distinct keys: compare the (time bucket, pad) words only
-            const uint32_t vp = (uint32_t)(v >> 32);
-#pragma unroll 4
-            for (int j = lo; j < hi; ++j) rank += key_words[2 * j] < vp;
-        } else {  // whole items: copies of a key are ordered by their position in the list
-            for (int j = lo; j < hi; ++j) rank += buf[j] < v;
-        }
-        dst[lo + rank] = v;
-    }
-    int n_final = n;
-    if (dup) {
-        // Copies of a key are now neighbours.  The first one becomes the row: it takes the summed charge and the
-        // highest rank (written into its own list entry, which emit_kernel reads), the others are dropped and the
-        // sequence is compacted in place, 256 items at a time.
-        HashEntry* wtab = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
-        __shared__ unsigned s_wsum[FINALIZE_THREADS / 32];
-        __shared__ unsigned s_done, s_prev_key;
-        if (threadIdx.x == 0) {
-            s_done = 0;
-            s_prev_key = 0xFFFFFFFFu;  // no item has this key word (time bucket < 1024)
-        }
-        __syncthreads();
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int start = 0; start < n; start += FINALIZE_THREADS) {
-            const int i = start + threadIdx.x;
-            const uint64_t v = i < n ? dst[i] : 0ull;
-            const uint32_t kw = i < n ? (uint32_t)(v >> 32) : 0xFFFFFFFEu;
-            // neighbours' keys from the lanes beside; only the edge lanes of a warp read them from memory
-            uint32_t before = __shfl_up_sync(FULL, kw, 1), after = __shfl_down_sync(FULL, kw, 1);
-            if (lane == 0 && i < n) before = threadIdx.x == 0 ? s_prev_key : (uint32_t)(dst[i - 1] >> 32);
-            if (lane == 31) after = i + 1 < n ? (uint32_t)(dst[i + 1] >> 32) : 0xFFFFFFFEu;
-            const bool head = i < n && kw != before;
-            if (head && after == kw) {  // copies follow (rare): fold them into this entry
-                unsigned long long extra = 0;
-                unsigned rank = wtab[(unsigned)v].rank;
-                for (int j = i + 1; j < n && (uint32_t)(dst[j] >> 32) == kw; ++j) {
-                    const HashEntry other = wtab[(unsigned)dst[j]];
-                    extra += other.charge;
-                    rank = max(rank, other.rank);
-                }
-                wtab[(unsigned)v].charge += extra;
-                wtab[(unsigned)v].rank = rank;
-            }
-            const unsigned heads = __ballot_sync(FULL, head);
-            if (lane == 0) s_wsum[warp] = __popc(heads);
-            __syncthreads();  // every read of this tile (and of its right neighbours) is done
-            unsigned pos = s_done + __popc(heads & ((1u << lane) - 1u));
-            for (int w = 0; w < warp; ++w) pos += s_wsum[w];
-            if (head) dst[pos] = v;
-            __syncthreads();
-            if (threadIdx.x == FINALIZE_THREADS - 1) {
-                unsigned total = pos + (head ? 1u : 0u);  // last thread: its prefix covers the whole tile
-                s_done = total;
-                if (i < n) s_prev_key = (uint32_t)(v >> 32);
-            }
-            __syncthreads();
-        }
-        n_final = (int)s_done;
-        if (threadIdx.x == 0) fa.kept[slot_event] = (unsigned)n_final;
-    }
-    if (!in_smem) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < n_final; i += blockDim.x) sorted[i] = stash[i];
-    }
-}
-
-// Exclusive scan of the kept counts of one group onto the running CSR total (single CTA).
-__global__ void __launch_bounds__(1024)
-scan_kernel(FinalizeArgs fa, GroupView gv, Counters* ctr, unsigned long long* csr_total) {
-    __shared__ unsigned long long s_part[1024];
-    __shared__ unsigned long long s_base;
-    const int tid = threadIdx.x;
-    if (tid == 0) s_base = *csr_total;
-    __syncthreads();
-    for (int start = 0; start < gv.n_events; start += 1024) {
-        const int i = start + tid;
-        const unsigned long long v = i < gv.n_events ? fa.kept[gv.first_slot + i] : 0ULL;
-        s_part[tid] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const unsigned long long add = tid >= o ? s_part[tid - o] : 0ULL;
-            __syncthreads();
-            s_part[tid] += add;
-            __syncthreads();
-        }
-        if (i < gv.n_events) fa.offsets[gv.first_slot + i] = (int64_t)(s_base + s_part[tid] - v);
-        __syncthreads();
-        if (tid == 0) s_base += s_part[1023];
-        __syncthreads();
-    }
-    if (tid == 0) {
-        fa.offsets[gv.first_slot + gv.n_events] = (int64_t)s_base;
-        *csr_total = s_base;
-        if ((int64_t)s_base > fa.out_cap) ctr->overflow_out = 1;
-    }
-}
-
-// One CTA per event: write [pad, tb + u, electrons] rows and labels in ascending (time bucket, pad) order
-// (detector/simulator.py:19-49, 104-115).
-__global__ void __launch_bounds__(FINALIZE_THREADS)
-emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa, GroupView chunk,
-            Counters* ctr) {
-    const GroupView gv = sub_group(chunk, blockIdx.y);
-    if ((int)blockIdx.x >= gv.n_events) return;
-    const int e = blockIdx.x;
-    const int slot_event = gv.first_slot + e;
-    const int n = (int)fa.kept[slot_event];
-    const int64_t off = fa.offsets[slot_event];
-    if (off + n > fa.out_cap) {
-        if (fa.row_kept && threadIdx.x == 0) fa.row_kept[slot_event] = 0;
-        return;
-    }
-    const HashEntry* tab = gv.tables + (int64_t)(gv.chunk_e0 + e) * gv.hash_cap;
-    const uint64_t* items = fa.sort_items + (int64_t)(gv.chunk_e0 + e) * 2 * gv.hash_cap;
-    unsigned above = 0;  // rows whose amplitude passes the ADC threshold (detector/writer.py:232)
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint64_t it = items[i];
-        const unsigned tb = (unsigned)(it >> 47), pad = (unsigned)(it >> 32) & 0x7FFFu;
-        const unsigned key = szudzik_pair(tb, pad);
-        const HashEntry en = tab[(unsigned)it];
-        above += (long long)en.charge >= P.e_keep_min;
-        const double u = wiggle_of(fa, slot_event, key, ctr);
-        const double tbf = (double)tb + u;
-        const int64_t label = fa.label_of_event_rank
-                                  ? (int64_t)fa.label_of_event_rank[(int64_t)slot_event * fa.n_tracks_per_event + en.rank]
-                                  : (int64_t)fa.label_of_rank[en.rank];
-        if (fa.cloud) {  // (null: typed columns only, nobody reads the float64 rows)
-            double* row = fa.cloud + (off + i) * 3;
-            row[0] = (double)pad;
-            row[1] = tbf;
-            row[2] = (double)(long long)en.charge;
-            fa.labels[off + i] = label;
-        }
-        if (fa.col_pad) {  // only the columns that will be copied are written
-            fa.col_pad[off + i] = (int16_t)pad;
-            fa.col_tb_q16[off + i] = (tb << 16) | (uint32_t)(u * 65536.0);
-            fa.col_label[off + i] = (int8_t)label;
-            if (fa.col_electrons) fa.col_electrons[off + i] = (long long)en.charge;
-            if (fa.col_electrons32) {
-                fa.col_electrons32[off + i] = (uint32_t)en.charge;
-                if (en.charge >> 32) {
-                    const unsigned long long k = atomicAdd(fa.big_count, 1ULL);
-                    if ((int64_t)k < fa.big_cap) {
-                        fa.big_rows[k] = off + i;
-                        fa.big_electrons[k] = (long long)en.charge;
-                    }
-                }
-            }
-        }
-    }
-    if (fa.row_kept) {
-        __shared__ unsigned s_above;
-        if (threadIdx.x == 0) s_above = 0;
-        __syncthreads();
-        above = __reduce_add_sync(FULL, above);
-        if ((threadIdx.x & 31) == 0 && above) atomicAdd(&s_above, above);
-        __syncthreads();
-        if (threadIdx.x == 0) fa.row_kept[slot_event] = s_above;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------ Spyral rows
@@ -2098,85 +1836,429 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
     }
 }
 
-// The Spyral rows of clouds that are in the engine's canonical order (ascending time bucket, then pad): detector/
-// writer.py:232-238 without a sort.  z falls as the time bucket rises, so the z order is the time buckets backwards and,
-// inside a bucket, the wiggle backwards; the rows of a bucket are neighbours in the cloud.  A kept row goes to
-//   (kept rows in later buckets) + (kept rows of its own bucket with a larger time, or the same time and a lower index)
-// where the first term is the event's kept total minus the running count of kept rows at the end of the bucket.
-// sa.kept holds the kept rows per event (counted by emit_kernel), sa.row_offsets their running sum.
-constexpr int SPYRAL_PREFIX_SMEM = 8192;  // rows of an event whose running counts fit shared memory (32 KB)
+// ---------------------------------------------------------------------------------------------------- finalize
+// detector/simulator.py:19-49 (dict_to_points), :104-115 (time-bucket wiggle and mask) and, when asked for,
+// detector/response.py:35-57 + detector/writer.py:232-238 (amplitude, ADC threshold, z order) on the entry lists that
+// deposit_kernel left, in three launches per chunk of events:
+//
+// order_kernel, one CTA per event, no event waits for another:
+//   1  histogram of the entries over the integer time bucket (mask applied), keys staged in shared memory
+//   2  exclusive scan -> bucket starts;  3  entries into their buckets (items = pad | list index)
+//   4  rank by counting inside each bucket -> canonical order, ascending (time bucket, pad); copies of a key that sit
+//      in different segments of the list (events deposited in several segments) become neighbours, ordered by index
+//   5  the first copy of every key is the row: bit mask of the rows + running count (events with copies only)
+//   6  charge / label gathered while the list is still in L2, wiggle drawn, rows staged (16 B) in canonical order
+//   7  Spyral: kept rows per bucket -> suffix sums (z falls as the time bucket rises), rank inside the bucket by the
+//      wiggle -> place of every kept row in z order, stored with the staged row
+// offsets_kernel: running CSR offsets from the row counts.   emit_kernel: streams the staged rows to the sinks.
+//
+// Everything an event needs stays in shared memory when its list has at most FIN_ITEMS entries; longer lists (dense
+// events) run the same code on a scratch region in global memory with 64-bit items.
+constexpr int FIN_THREADS = ATTPC_FIN_THREADS;
+constexpr int FIN_ITEMS = ATTPC_FIN_ITEMS;
+constexpr size_t FIN_SMEM_BYTES = (size_t)(3 * FIN_ITEMS + 2 * (FIN_ITEMS / 32)) * sizeof(uint32_t);
+constexpr unsigned long long SCAN_AGGREGATE = 1ULL << 62, SCAN_PREFIX = 2ULL << 62, SCAN_VALUE = (1ULL << 62) - 1ULL;
+static_assert(TB_BINS % FIN_THREADS == 0 && FIN_ITEMS % 32 == 0, "finalize tiling");
 
-__global__ void __launch_bounds__(256) spyral_ordered_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
-    extern __shared__ unsigned s_pre[];  // [n + 1] kept rows before row i
-    __shared__ unsigned s_warp[8];
-    __shared__ unsigned s_run;
-    const int64_t e = sa.first + blockIdx.x;
-    const int kept = (int)sa.kept[e];
-    if (kept == 0) return;
-    const int64_t a = sa.offsets[e];
-    const int n = (int)(sa.offsets[e + 1] - a);
-    const int64_t out0 = sa.row_offsets[e];
-    unsigned* pre = n + 1 <= SPYRAL_PREFIX_SMEM ? s_pre : sa.sort_idx + a + e;  // (global scratch: n + 1 words per event)
-    const double* cloud = sa.cloud + a * 3;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double keep_min = (double)P.e_keep_min;
-    if (threadIdx.x == 0) s_run = 0;
+struct FinShared {
+    unsigned hist[TB_BINS + 1];  // bucket starts (sorted positions)
+    unsigned fill[TB_BINS];      // fill cursors, then kept rows per bucket, then kept rows in the later buckets
+    unsigned warp[FIN_THREADS / 32];
+    unsigned keys;
+};
+
+// Exclusive scan, in place, of a[at(0)], a[at(1)], ..., a[at(TB_BINS - 1)]; every thread of the CTA calls it after a
+// barrier that completed `a`; returns the total; ends with a barrier.
+template <typename Map>
+__device__ __forceinline__ unsigned scan_bins(unsigned* a, Map at, unsigned* s_warp) {
+    constexpr int PER = TB_BINS / FIN_THREADS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned local[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        local[k] = a[at(tid * PER + k)];
+        sum += local[k];
+    }
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    for (int t0 = 0; t0 < n; t0 += 256) {
-        const int i = t0 + threadIdx.x;
-        const bool keep = i < n && cloud[i * 3 + 2] >= keep_min;
-        const unsigned m = __ballot_sync(FULL, keep);
-        if (lane == 0) s_warp[warp] = __popc(m);
+    unsigned base = incl - sum, total = 0;
+#pragma unroll
+    for (int w = 0; w < FIN_THREADS / 32; ++w) {
+        const unsigned v = s_warp[w];
+        if (w < warp) base += v;
+        total += v;
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        a[at(tid * PER + k)] = base;
+        base += local[k];
+    }
+    __syncthreads();
+    return total;
+}
+
+// Exclusive scan of one value per thread; returns the thread's prefix, `total` for everybody; two barriers.
+__device__ __forceinline__ unsigned scan_threads(unsigned v, unsigned& total, unsigned* s_warp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // (the previous use of s_warp is over)
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned base = incl - v;
+    total = 0;
+#pragma unroll
+    for (int w = 0; w < FIN_THREADS / 32; ++w) {
+        const unsigned t = s_warp[w];
+        if (w < warp) base += t;
+        total += t;
+    }
+    return base;
+}
+
+template <typename Item, bool SMEM>
+__device__ __forceinline__ void order_event(const SimParams& P, const FinalizeArgs& fa, const GroupView& chunk,
+                                               Counters* ctr, FinShared& sh, const int L, const int limit,
+                                               const HashEntry* __restrict__ tab, Item* A, Item* B, uint32_t* C,
+                                               unsigned* H, unsigned* HP) {
+    constexpr int SH = SMEM ? 17 : 32;  // item = (pad << SH) | index in the list
+    constexpr Item IDX_MASK = ((Item)1 << SH) - 1;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int slot_event = chunk.first_slot + L;
+    const bool dup = chunk.mode[slot_event] != 0u;  // the list may hold a key several times
+    auto key_of = [&](unsigned i) -> unsigned { return SMEM ? C[i] : tab[i].key1; };
+    auto bin_of = [](unsigned key1) -> unsigned { return min((key1 - 1u) >> 15, (unsigned)TB_BINS - 1u); };
+    // detector/simulator.py:108-113: keep 0 <= tb + u < 512 with u in [0, 1).  Only the last bucket needs u (a replayed
+    // 53-bit uniform can round 511 + u up to 512.0)
+    auto masked = [&](unsigned key1) -> unsigned {
+        const unsigned tb = (key1 - 1u) >> 15;
+        if ((fa.flags & F_KEEP_ALL_TB) || tb < (unsigned)NUM_TB - 1u) return key1;
+        if (tb != (unsigned)NUM_TB - 1u) return 0u;
+        const unsigned pad = (key1 - 1u) & 0x7FFFu;
+        return (double)tb + wiggle_of(fa, slot_event, szudzik_pair(tb, pad), ctr) < (double)NUM_TB ? key1 : 0u;
+    };
+
+    // 1: histogram over the time bucket
+    unsigned occupied = 0;
+    for (int i0 = tid; i0 < limit; i0 += 4 * FIN_THREADS) {  // four loads in flight per thread
+        unsigned k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * FIN_THREADS;
+            k[u] = i < limit ? tab[i].key1 : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * FIN_THREADS;
+            if (i >= limit) break;
+            unsigned key1 = k[u];
+            if (key1) {
+                occupied += 1;
+                key1 = masked(key1);
+            }
+            if (SMEM) C[i] = key1;
+            if (key1) atomicAdd(&sh.hist[bin_of(key1)], 1u);
+        }
+    }
+    if (occupied) atomicAdd(&sh.keys, occupied);
+    __syncthreads();
+    // 2: bucket starts
+    const int n = (int)scan_bins(sh.hist, [](int b) { return b; }, sh.warp);
+    for (int b = tid; b < TB_BINS; b += FIN_THREADS) sh.fill[b] = sh.hist[b];
+    if (tid == 0) {
+        sh.hist[TB_BINS] = (unsigned)n;
+        if (sh.keys) atomicAdd(&ctr->keys, (unsigned long long)sh.keys);
+    }
+    __syncthreads();
+    // 3: entries into their buckets
+    for (int i = tid; i < limit; i += FIN_THREADS) {
+        unsigned key1 = SMEM ? C[i] : tab[i].key1;
+        if (!SMEM && key1) key1 = masked(key1);
+        if (key1) A[atomicAdd(&sh.fill[bin_of(key1)], 1u)] = ((Item)((key1 - 1u) & 0x7FFFu) << SH) | (Item)(unsigned)i;
+    }
+    __syncthreads();
+    // 4: order every bucket: one thread per item counts the smaller items of its bucket (a bucket holds the pads hit in
+    // one time bucket, a handful for most tracks; neighbouring threads walk the same items, the reads are broadcasts)
+    for (int i = tid; i < n; i += FIN_THREADS) {
+        const Item v = A[i];
+        const unsigned kv = key_of((unsigned)(v & IDX_MASK));
+        const unsigned bin = bin_of(kv);
+        const int lo = (int)sh.hist[bin], hi = (int)sh.hist[bin + 1];
+        int rank = 0;
+        if (bin != (unsigned)TB_BINS - 1u) {  // one time bucket: (pad, index) decides
+#pragma unroll 4
+            for (int j = lo; j < hi; ++j) rank += A[j] < v;
+        } else {  // time buckets >= 1023 share the last bin (ATTPC_KEEP_ALL_TB only): compare the whole key
+            for (int j = lo; j < hi; ++j) {
+                const Item w = A[j];
+                const unsigned kj = key_of((unsigned)(w & IDX_MASK));
+                rank += kj < kv || (kj == kv && w < v);
+            }
+        }
+        B[lo + rank] = v;
+    }
+    for (int b = tid; b < TB_BINS; b += FIN_THREADS) sh.fill[b] = 0u;  // (kept rows per bucket, step 7)
+    __syncthreads();
+    // 5: rows = first copies
+    int n_rows = n;
+    if (dup) {
+        for (int p = tid; p - lane < n; p += FIN_THREADS) {  // (warp-uniform trip count)
+            bool head = false;
+            if (p < n) head = p == 0 || key_of((unsigned)(B[p] & IDX_MASK)) != key_of((unsigned)(B[p - 1] & IDX_MASK));
+            const unsigned m = __ballot_sync(FULL, head);
+            if (lane == 0) H[p >> 5] = m;
+        }
         __syncthreads();
-        unsigned before = s_run + __popc(m & ((1u << lane) - 1u));
-        for (int w = 0; w < warp; ++w) before += s_warp[w];
-        if (i < n) pre[i] = before;
-        __syncthreads();
-        if (threadIdx.x == 255) s_run = before + (keep ? 1u : 0u);
+        const int n_words = (n + 31) >> 5;
+        unsigned done = 0;
+        for (int w0 = 0; w0 < n_words; w0 += FIN_THREADS) {
+            const int w = w0 + tid;
+            unsigned total;
+            const unsigned before = scan_threads(w < n_words ? (unsigned)__popc(H[w]) : 0u, total, sh.warp);
+            if (w < n_words) HP[w] = done + before;
+            done += total;
+        }
+        n_rows = (int)done;
         __syncthreads();
     }
-    if (threadIdx.x == 0) pre[n] = s_run;
+    auto is_row = [&](int p) -> bool { return !dup || ((H[p >> 5] >> (p & 31)) & 1u); };
+    if (tid == 0) fa.kept[slot_event] = (unsigned)n_rows;
+    // 6: the rows, in canonical order, into the event's staging region (16 B each; emit_kernel streams them to the
+    // sinks once the offsets of all events are known).  Charge and label of a row fold the copies of its key:
+    // integer adds commute, the label is the highest rank (detector/transporter.py:166-169, 247-249).
+    uint4* staged = fa.staged + (int64_t)L * chunk.hash_cap;
+    const bool spy = fa.spyral != 0u;
+    const bool draw = fa.replay.offsets == nullptr;  // (replayed uniforms have 53 bits: emit_kernel looks them up)
+    for (int p = tid; p < n; p += FIN_THREADS) {
+        Item w_out = 0;
+        if (is_row(p)) {
+            const uint4 en = __ldg(reinterpret_cast<const uint4*>(tab + (unsigned)(B[p] & IDX_MASK)));
+            const unsigned key1 = en.x;
+            unsigned rk = en.y;
+            unsigned long long q = ((unsigned long long)en.w << 32) | en.z;
+            if (dup)
+                for (int j = p + 1; j < n && !((H[j >> 5] >> (j & 31)) & 1u); ++j) {
+                    const uint4 o = __ldg(reinterpret_cast<const uint4*>(tab + (unsigned)(B[j] & IDX_MASK)));
+                    q += ((unsigned long long)o.w << 32) | o.z;
+                    rk = max(rk, o.y);
+                }
+            if (q >> 48) ctr->overflow_charge = 1;
+            const unsigned tb = (key1 - 1u) >> 15, pad = (key1 - 1u) & 0x7FFFu;
+            const uint32_t u16 = draw ? (uint32_t)(wiggle_of(fa, slot_event, szudzik_pair(tb, pad), ctr) * 65536.0) : 0u;
+            // amplitude above the ADC threshold (detector/writer.py:232) <=> electrons >= e_keep_min
+            const unsigned keep = spy && (long long)q >= P.e_keep_min ? 1u : 0u;
+            const int r = dup ? (int)(HP[p >> 5] + __popc(H[p >> 5] & ((1u << (p & 31)) - 1u))) : p;
+            staged[r] = make_uint4((tb << 16) | u16, (unsigned)q, (unsigned)(q >> 32) | (pad << 16) | (keep << 31), rk);
+            if (spy) {
+                const unsigned bin = min(tb, (unsigned)TB_BINS - 1u);
+                w_out = (Item)((rk << 27) | (bin << 17) | (keep << 16) | u16);
+                if (keep) atomicAdd(&sh.fill[bin], 1u);
+            }
+        }
+        if (spy) A[p] = w_out;
+    }
+    if (!spy) return;
+    // 7: place of every kept row in z order.  z falls as the time bucket rises (detector/writer.py:101-103, 236):
+    //   (kept rows of the later buckets) + (kept rows of its bucket with a larger wiggle, or the same and a lower position)
     __syncthreads();
-    const double span = (double)(P.win_edge - P.mm_edge);
-    for (int i = threadIdx.x; i < n; i += 256) {
-        if (pre[i + 1] == pre[i]) continue;  // below the ADC threshold
-        const double padf = cloud[i * 3], tbf = cloud[i * 3 + 1], el = cloud[i * 3 + 2];
-        const int tb = (int)tbf;
+    const unsigned n_kept = scan_bins(sh.fill, [](int b) { return TB_BINS - 1 - b; }, sh.warp);
+    if (tid == 0) fa.row_kept[slot_event] = n_kept;
+    for (int p = tid; p < n; p += FIN_THREADS) {
+        const unsigned w = (unsigned)A[p];
+        if (!((w >> 16) & 1u)) continue;  // below the ADC threshold, or not a row
+        const unsigned bin = (w >> 17) & 0x3FFu, wp = w & 0x1FFFFu;
+        const int lo = (int)sh.hist[bin], hi = (int)sh.hist[bin + 1];
         unsigned within = 0;
-        int j = i - 1;
-        for (; j >= 0; --j) {
-            const double tj = cloud[j * 3 + 1];
-            if ((int)tj != tb) break;
-            within += (pre[j + 1] != pre[j]) && tj >= tbf;  // (same time: the lower index goes first)
+#pragma unroll 4
+        for (int j = lo; j < hi; ++j) {
+            const unsigned wj = (unsigned)A[j] & 0x1FFFFu;  // (not kept: below 0x10000, never counted)
+            within += wj > wp || (wj == wp && j < p);
         }
-        for (j = i + 1; j < n; ++j) {
-            const double tj = cloud[j * 3 + 1];
-            if ((int)tj != tb) break;
-            within += (pre[j + 1] != pre[j]) && tj > tbf;
+        const int r = dup ? (int)(HP[p >> 5] + __popc(H[p >> 5] & ((1u << (p & 31)) - 1u)) ) : p;
+        reinterpret_cast<unsigned*>(staged + r)[3] = (w >> 27) | ((sh.fill[bin] + within) << 4);
+    }
+}
+
+// Kernel A of finalize: order the entry list of every event of the chunk (one CTA per event, no event waits for
+// another) and stage its rows.
+__global__ void __launch_bounds__(FIN_THREADS, ATTPC_FIN_MIN_CTAS)
+order_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa,
+             const __grid_constant__ GroupView chunk, Counters* ctr) {
+    extern __shared__ __align__(16) uint32_t s_fin[];
+    __shared__ FinShared sh;
+    const int tid = threadIdx.x;
+    if (tid == 0) sh.keys = 0;
+    for (int b = tid; b <= TB_BINS; b += FIN_THREADS) sh.hist[b] = 0;
+    __syncthreads();
+    const int L = (int)blockIdx.x;
+    const int slot_event = chunk.first_slot + L;
+    // an attempt that overflowed a buffer is void (the host redoes the launch)
+    const bool void_attempt = (ctr->overflow_points | ctr->overflow_hash) != 0;
+    const int limit = void_attempt ? 0 : (int)min(chunk.n_entries[slot_event], (unsigned)chunk.hash_cap);
+    const HashEntry* tab = chunk.tables + (int64_t)L * chunk.hash_cap;
+    if (limit <= FIN_ITEMS && chunk.hash_cap <= (1 << 17)) {
+        uint32_t* H = s_fin + 3 * FIN_ITEMS;
+        order_event<uint32_t, true>(P, fa, chunk, ctr, sh, L, limit, tab, s_fin, s_fin + FIN_ITEMS,
+                                    s_fin + 2 * FIN_ITEMS, H, H + FIN_ITEMS / 32);
+    } else {
+        uint64_t* scratch = fa.sort_items + (int64_t)L * fa.scratch_stride;
+        unsigned* H = reinterpret_cast<unsigned*>(scratch + 2 * (int64_t)chunk.hash_cap);
+        order_event<uint64_t, false>(P, fa, chunk, ctr, sh, L, limit, tab, scratch, scratch + chunk.hash_cap, nullptr,
+                                     H, H + chunk.hash_cap / 32 + 1);
+    }
+}
+
+// Running CSR offsets of the chunk's events from their row counts (cloud rows and, when asked for, Spyral rows), on
+// top of the totals of the call so far.  One CTA: a thread sums a run of consecutive events, the CTA scans the sums.
+__global__ void __launch_bounds__(1024) offsets_kernel(FinalizeArgs fa, GroupView chunk, Counters* ctr) {
+    __shared__ unsigned long long s_warp[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = chunk.n_events;
+    const int per = (n + 1023) / 1024;
+    const int e0 = min(n, tid * per), e1 = min(n, e0 + per);
+    const bool spy = fa.spyral != 0u;
+    const unsigned* kept = fa.kept + chunk.first_slot;
+    const unsigned* rkept = fa.row_kept + chunk.first_slot;
+    unsigned long long sum[2] = {0ULL, 0ULL};
+    for (int e = e0; e < e1; ++e) {
+        sum[0] += kept[e];
+        if (spy) sum[1] += rkept[e];
+    }
+    unsigned long long incl[2] = {sum[0], sum[1]};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const unsigned long long v = __shfl_up_sync(FULL, incl[c], o);
+            if (lane >= o) incl[c] += v;
         }
-        const int64_t at = out0 + ((unsigned)kept - pre[j]) + within;  // pre[j]: kept rows up to the end of this bucket
-        const int pad = (int)padf;
-        if (sa.out_pad) {  // typed columns: what the eight columns are functions of
-            const unsigned long long q = (unsigned long long)(long long)el;
-            sa.out_pad[at] = (int16_t)pad;
-            sa.out_tb_q16[at] = (uint32_t)(tbf * 65536.0);  // exact for the library's 16-bit wiggle
-            sa.out_e_lo[at] = (uint32_t)q;
-            sa.out_e_hi[at] = (uint16_t)(q >> 32);
-            sa.out_label[at] = (int8_t)sa.labels[a + i];
-            continue;
+    if (lane == 31) {
+        s_warp[0][warp] = incl[0];
+        s_warp[1][warp] = incl[1];
+    }
+    __syncthreads();
+    unsigned long long base[2], total[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        base[c] = fa.csr_total[2 * c] + incl[c] - sum[c];
+        total[c] = fa.csr_total[2 * c];
+        for (int w = 0; w < 32; ++w) {
+            const unsigned long long v = s_warp[c][w];
+            if (w < warp) base[c] += v;
+            total[c] += v;
         }
-        double amp, integral;
-        shaped(P, el, amp, integral);
-        double* row = sa.rows + at * 8;
-        row[0] = P.pad_xy[2 * pad];
-        row[1] = P.pad_xy[2 * pad + 1];
-        row[2] = __dmul_rn(__dmul_rn(__ddiv_rn(__dsub_rn(P.win_edge, tbf), span), P.length), 1000.0);
-        row[3] = amp;
-        row[4] = integral;
-        row[5] = padf;
-        row[6] = tbf;
-        row[7] = P.pad_scale[pad];
-        sa.row_labels[at] = sa.labels[a + i];
+    }
+    __syncthreads();  // (every thread has read csr_total)
+    int64_t* offsets = fa.offsets + chunk.first_slot;
+    int64_t* roffsets = fa.row_offsets + chunk.first_slot;
+    for (int e = e0; e < e1; ++e) {
+        offsets[e] = (int64_t)base[0];
+        base[0] += kept[e];
+        if (spy) {
+            roffsets[e] = (int64_t)base[1];
+            base[1] += rkept[e];
+        }
+    }
+    if (tid == 0) {
+        offsets[n] = (int64_t)total[0];
+        fa.csr_total[0] = total[0];
+        if ((int64_t)total[0] > fa.out_cap) ctr->overflow_out = 1;
+        if (spy) {
+            roffsets[n] = (int64_t)total[1];
+            fa.csr_total[2] = total[1];
+            if ((int64_t)total[1] > fa.out_cap) ctr->overflow_out = 1;
+        }
+    }
+}
+
+// Kernel B of finalize: stream the staged rows of every event to the sinks (one CTA per event): [pad, tb + u,
+// electrons] rows and labels (detector/simulator.py:19-49, 104-115), the typed columns, and the Spyral rows
+// (detector/response.py:35-57, detector/writer.py:61-112, 232-238) at their place in z order.
+constexpr int EMIT_THREADS = 256;
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa,
+            const __grid_constant__ GroupView chunk, Counters* ctr) {
+    const int L = (int)blockIdx.x;
+    const int slot_event = chunk.first_slot + L;
+    const int n = (int)fa.kept[slot_event];
+    const int64_t off = fa.offsets[slot_event];
+    if (off + n > fa.out_cap) return;  // (offsets_kernel has raised overflow_out)
+    const bool spy = fa.spyral != 0u && fa.row_offsets[slot_event] + (int64_t)fa.row_kept[slot_event] <= fa.out_cap;
+    const int64_t roff = fa.spyral ? fa.row_offsets[slot_event] : 0;
+    const uint4* staged = fa.staged + (int64_t)L * chunk.hash_cap;
+    const bool replayed = fa.replay.offsets != nullptr;
+    const double span = (double)(P.win_edge - P.mm_edge);
+    for (int i = threadIdx.x; i < n; i += EMIT_THREADS) {
+        const uint4 s = __ldcs(staged + i);
+        const unsigned tb = s.x >> 16, pad = (s.z >> 16) & 0x7FFFu, rk = s.w & 0xFu;
+        const unsigned long long q = ((unsigned long long)(s.z & 0xFFFFu) << 32) | s.y;
+        uint32_t u16 = s.x & 0xFFFFu;
+        double u = (double)u16 * (1.0 / 65536.0);
+        if (replayed) {
+            u = wiggle_of(fa, slot_event, szudzik_pair(tb, pad), ctr);
+            u16 = (uint32_t)(u * 65536.0);
+        }
+        const double tbf = (double)tb + u;
+        const int64_t label = fa.label_of_event_rank
+                                  ? (int64_t)fa.label_of_event_rank[(int64_t)slot_event * fa.n_tracks_per_event + rk]
+                                  : (int64_t)fa.label_of_rank[rk];
+        const int64_t r = off + i;
+        if (fa.cloud) {  // (null: typed columns only, nobody reads the float64 rows)
+            double* row = fa.cloud + r * 3;
+            row[0] = (double)pad;
+            row[1] = tbf;
+            row[2] = (double)(long long)q;
+            fa.labels[r] = label;
+        }
+        if (fa.col_pad) {  // only the columns that will be copied are written
+            fa.col_pad[r] = (int16_t)pad;
+            fa.col_tb_q16[r] = (tb << 16) | u16;
+            fa.col_label[r] = (int8_t)label;
+            if (fa.col_electrons) fa.col_electrons[r] = (long long)q;
+            if (fa.col_electrons32) {
+                fa.col_electrons32[r] = (uint32_t)q;
+                if (q >> 32) {
+                    const unsigned long long k = atomicAdd(fa.big_count, 1ULL);
+                    if ((int64_t)k < fa.big_cap) {
+                        fa.big_rows[k] = r;
+                        fa.big_electrons[k] = (long long)q;
+                    }
+                }
+            }
+        }
+        if (spy && (s.z >> 31)) {
+            const int64_t at = roff + (s.w >> 4);
+            if (fa.rcol_pad) {  // typed columns: what the eight columns are functions of
+                fa.rcol_pad[at] = (int16_t)pad;
+                fa.rcol_tb_q16[at] = (tb << 16) | u16;
+                fa.rcol_e_lo[at] = (uint32_t)q;
+                fa.rcol_e_hi[at] = (uint16_t)(q >> 32);
+                fa.rcol_label[at] = (int8_t)label;
+            } else {
+                double amp, integral;
+                shaped(P, (double)(long long)q, amp, integral);
+                double* row = fa.rows + at * 8;
+                row[0] = P.pad_xy[2 * pad];
+                row[1] = P.pad_xy[2 * pad + 1];
+                row[2] = __dmul_rn(__dmul_rn(__ddiv_rn(__dsub_rn(P.win_edge, tbf), span), P.length), 1000.0);
+                row[3] = amp;
+                row[4] = integral;
+                row[5] = (double)pad;
+                row[6] = tbf;
+                row[7] = P.pad_scale[pad];
+                fa.row_labels[at] = label;
+            }
+        }
     }
 }
 
