@@ -1,7 +1,7 @@
 """Detector effects (mirror of `attpc_engine.detector`, reference `detector/__init__.py:3-21`)."""
 
 from .parameters import Config, DetectorParams, ElectronicsParams, PadParams
-from .simulator import SimEvent, run_simulation, simulate, simulate_batch
+from .simulator import SimEvent, run_simulation, simulate, simulate_batch, simulate_stream
 from .writer import (
     ArrayWriter,
     ParquetCloudWriter,
@@ -15,6 +15,7 @@ __all__ = [
     "run_simulation",
     "simulate",
     "simulate_batch",
+    "simulate_stream",
     "SimEvent",
     "DetectorParams",
     "ElectronicsParams",

@@ -226,6 +226,64 @@ class _OrderedFanIn:
             t.join(timeout=60)
 
 
+def _workers(devices, engines_per_device: int) -> list[int]:
+    """Device of every worker: the GPUs in turn, `engines_per_device` times (consecutive batches go to different GPUs)."""
+    if engines_per_device < 1:
+        raise ValueError("engines_per_device must be at least 1")
+    return [int(d) for _ in range(int(engines_per_device)) for d in devices]
+
+
+def simulate_stream(
+    batches,
+    proton_numbers: np.ndarray,
+    mass_numbers: np.ndarray,
+    config: Config,
+    seed: int,
+    indices: list[int],
+    devices=(0,),
+    engines_per_device: int = 2,
+    **batch_options,
+):
+    """Pipelined `simulate_batch` over a sequence of batches: yields ``(k, SimBatch)`` in ascending ``k``.
+
+    ``batches[k]`` is ``(momenta [B, K, 4], vertices [B, 3], first_event)`` or a callable returning that (called in
+    the worker, e.g. to read a chunk of a file; one at a time unless it has a true ``thread_safe`` attribute).  Batch ``k`` goes to worker ``k mod W``, ``W = len(devices) *
+    engines_per_device`` workers, each a host thread with its own engine (its own streams and pinned buffers).  Two
+    engines on one GPU overlap the device-to-host copy of one batch with the kernels of the next: the end-to-end
+    rate of a single GPU is otherwise bounded by ``compute + copy`` of one batch at a time.  A yielded batch is valid
+    until the consumer asks for the next one (its worker starts on batch ``k + W`` only then), so ``copy=False``
+    views are safe; ``batch_options`` are those of `simulate_batch`.  Every random draw is addressed by the global
+    event number: the output does not depend on ``devices`` or ``engines_per_device``.
+    """
+    import threading
+
+    batches = list(batches) if not hasattr(batches, "__getitem__") else batches
+    workers = _workers(devices, engines_per_device)
+    read_lock = threading.Lock()  # (h5py handles are not thread-safe)
+
+    def work(k: int, g: int) -> SimBatch:
+        item = batches[k]
+        if callable(item):
+            if getattr(item, "thread_safe", False):
+                item = item()
+            else:
+                with read_lock:
+                    item = item()
+        momenta, vertices, first_event = item
+        return simulate_batch(momenta, vertices, proton_numbers, mass_numbers, config, seed, indices,
+                              first_event=first_event, device=workers[g], engine_instance=g, **batch_options)  # fmt: skip
+
+    if len(workers) == 1:
+        for k in range(len(batches)):
+            yield k, work(k, 0)
+        return
+    fan_in = _OrderedFanIn(len(batches), workers, work)
+    try:
+        yield from fan_in
+    finally:
+        fan_in.close()
+
+
 def run_simulation(
     config: Config,
     input_path: Path,
@@ -236,6 +294,7 @@ def run_simulation(
     device: int = 0,
     verbose: bool = True,
     devices: list[int] | None = None,
+    engines_per_device: int = 2,
 ) -> None:
     """Run the detector simulation over a kinematics file (`simulator.py:118-210`).
 
@@ -253,6 +312,8 @@ def run_simulation(
     ``devices=[0, 1, ...]``: the event ranges (batches of ``batch_size`` events) are dealt round-robin to one worker
     thread and one engine per listed GPU; the writer still sees every event in ascending order, and -- every random
     draw being addressed by the global event number -- the output does not depend on the number of GPUs.
+    ``engines_per_device`` (default 2): engines, each with its own worker thread, per GPU, so that the copy of one batch
+    to the host and the writer overlap the kernels of the next batch (`simulate_stream`).
     """
     kin = _open_kinematics(input_path)
     devices = [int(device)] if not devices else [int(d) for d in devices]
@@ -261,8 +322,8 @@ def run_simulation(
         print(f"Applying detector effects to kinematics from file: {input_path}")
         print(f"Found {kin.n_events} kinematics events.")
         print(f"Output will be written to {writer.get_directory_name()}.")
-        if len(devices) > 1:
-            print(f"Event ranges of {batch_size} events are dealt to GPUs {devices}.")
+        if len(devices) * engines_per_device > 1:
+            print(f"Event ranges of {batch_size} events are dealt to GPUs {devices}, {engines_per_device} engine(s) each.")
     nuclei_to_sim = list(indices) if indices is not None else default_indices(len(kin.proton_numbers))
     if seed is None:
         seed = int(default_rng().integers(0, 2**63 - 1))
@@ -270,23 +331,23 @@ def run_simulation(
     want_rows = bool(getattr(writer, "wants_spyral_rows", False)) and batched
     views_ok = not batched or bool(getattr(writer, "accepts_views", False))  # per-event arrays are built fresh anyway
     starts = list(range(0, kin.n_events, batch_size))
-    import threading
 
-    read_lock = threading.Lock()  # (h5py handles are not thread-safe)
-
-    def work(k: int, g: int) -> SimBatch:  # batch k on worker g (its own engine on devices[g])
-        start = starts[k]
-        stop = min(start + batch_size, kin.n_events)
-        with read_lock:
+    def reader(k: int):  # batch k, read in the worker that simulates it
+        def read():
+            start, stop = starts[k], min(starts[k] + batch_size, kin.n_events)
             momenta, vertices = kin.read(start, stop)
-        return simulate_batch(
-            momenta, vertices, kin.proton_numbers, kin.mass_numbers, config, seed, nuclei_to_sim,
-            first_event=start, device=devices[g], engine_instance=g, spyral_rows=want_rows, copy=not views_ok,
-            rows_only=want_rows and bool(getattr(writer, "rows_only", False)),
-            row_columns=want_rows,  # 13 instead of 72 B/row over PCIe; `SimBatch.event_rows` rebuilds the float64 rows
-            # per-event writers get their arrays built event by event anyway; batch writers say if they want columns
-            columns=not batched or bool(getattr(writer, "wants_columns", False)),
-        )  # fmt: skip
+            return momenta, vertices, start
+
+        return read
+
+    stream = simulate_stream(
+        [reader(k) for k in range(len(starts))], kin.proton_numbers, kin.mass_numbers, config, seed, nuclei_to_sim,
+        devices=devices, engines_per_device=engines_per_device, spyral_rows=want_rows, copy=not views_ok,
+        rows_only=want_rows and bool(getattr(writer, "rows_only", False)),
+        row_columns=want_rows,  # 13 instead of 72 B/row over PCIe; `SimBatch.event_rows` rebuilds the float64 rows
+        # per-event writers get their arrays built event by event anyway; batch writers say if they want columns
+        columns=not batched or bool(getattr(writer, "wants_columns", False)),
+    )  # fmt: skip
 
     def consume(k: int, batch: SimBatch) -> None:
         if batched:
@@ -298,16 +359,11 @@ def run_simulation(
                 continue
             writer.write(np.array(cloud), np.array(labels), config, starts[k] + e)
 
-    if len(devices) == 1:
-        for k in range(len(starts)):
-            consume(k, work(k, 0))
-    else:
-        fan_in = _OrderedFanIn(len(starts), devices, work)
-        try:
-            for k, batch in fan_in:
-                consume(k, batch)
-        finally:
-            fan_in.close()
+    try:
+        for k, batch in stream:
+            consume(k, batch)
+    finally:
+        stream.close()
     writer.close()
     if verbose:
         print("Done.")

@@ -266,9 +266,9 @@ def run_ours(args):
     B = args.events
     config, momenta, vertices, zs, as_, indices = build_workload(args.workload, B, seed_offset=rank)
     K = momenta.shape[1]
-    eng = engine_for(config, _nuclei_for(zs, as_, indices, nuclear_map), device=local,
-                     max_events_per_launch=args.launch_events, copy_events_per_launch=args.copy_events,
-                     **{k: int(v) for k, v in (kv.split("=") for kv in args.tune)})  # fmt: skip
+    tuning = dict(max_events_per_launch=args.launch_events, copy_events_per_launch=args.copy_events,
+                  **{k: int(v) for k, v in (kv.split("=") for kv in args.tune)})  # fmt: skip
+    eng = engine_for(config, _nuclei_for(zs, as_, indices, nuclear_map), device=local, **tuning)
     # pinned host inputs (e2e) and device-resident inputs (value)
     mom_pin = torch.from_numpy(momenta).pin_memory()
     vtx_pin = torch.from_numpy(vertices).pin_memory()
@@ -300,12 +300,31 @@ def run_ours(args):
     def step_e2e(i):
         return batch_e2e(i).stats
 
+    def stream_e2e(n_steps, step0):
+        """n_steps batches through `simulate_stream` (the pipelined public call that `run_simulation` uses): engines
+        alternate on this GPU, the copy of one batch to the host overlaps the kernels of the next.  Every batch is
+        this rank's B events under fresh global event numbers (fresh random streams)."""
+        from attpc_engine_b200.detector import simulate_stream
+
+        batches = [(mom_pin.numpy(), vtx_pin.numpy(), (step0 + k) * world * B + first) for k in range(n_steps)]
+        pts = rows = big = 0
+        for _, b in simulate_stream(batches, zs, as_, config, seed, indices, devices=[local],
+                                    engines_per_device=args.e2e_engines, copy=False, spyral_rows=args.spyral,
+                                    rows_only=args.spyral, row_columns=args.spyral and not args.float64_rows,
+                                    columns=not args.float64_rows, **tuning):  # fmt: skip
+            pts += b.stats["n_points"]
+            big += b.stats.get("n_big", 0)
+            rows += b.stats.get("n_rows", 0)
+        return pts, rows, big
+
     sampler = ClockSampler(local)
     sampler.start()  # nvidia-smi needs a moment to come up: started before the warm-up, read after the timed loops
     for i in range(args.warmup):
         step_device(i)
         if not args.no_e2e:
             step_e2e(i)
+    if not args.no_e2e and args.e2e_engines > 1:
+        stream_e2e(max(args.warmup, args.e2e_engines), 0)  # builds the other engines, sizes their buffers
 
     # ---- value: device-resident
     barrier()
@@ -334,6 +353,16 @@ def run_ours(args):
         e2e_big += st.get("n_big", 0)
         e2e_rows += st.get("n_rows", 0)
     barrier()
+    # ---- e2e, pipelined: the same steps through simulate_stream (one call after the other above: e2e_sync)
+    piped_s = None
+    if not args.no_e2e and args.e2e_engines > 1:
+        flush_l2()
+        barrier()
+        t0 = time.perf_counter()
+        p_points, p_rows, p_big = stream_e2e(args.steps, 1000)
+        torch.cuda.synchronize()
+        piped_s = time.perf_counter() - t0
+        barrier()
     clocks = sampler.stop()
     # e2e_decoded: the same call plus the decode of the wire format into the arrays `SimulationWriter.write` receives
     # (float64 [N, 3] + int64 [N]; or the float64 [M, 8] Spyral rows), on one host thread; one step, rank-local
@@ -351,6 +380,10 @@ def run_ours(args):
 
     dev_s = reduce_max(dist, dev_ms / 1e3, local)
     e2e_s = reduce_max(dist, e2e_s, local) if not args.no_e2e else float("nan")
+    e2e_sync_s = e2e_s
+    if piped_s is not None:  # the headline e2e is the pipelined call; its bytes are counted from its own batches
+        e2e_s = reduce_max(dist, piped_s, local)
+        e2e_points, e2e_rows, e2e_big = p_points, p_rows, p_big
     total_events = B * world * args.steps
     electrons = reduce_sum(dist, stats_sum["n_primary_electrons"], local)
     points = reduce_sum(dist, stats_sum["n_points"], local)
@@ -367,7 +400,7 @@ def run_ours(args):
     # dominant kernel by device time (CUDA events recorded by the library around each stage, on its own stream)
     stage_ms = {"track_kernel": stats_sum["ms_tracks"], "point_scan+point_order": stats_sum["ms_order"],
                 "deposit_kernel": stats_sum["ms_deposit"],
-                "finalize (collect+scan+emit" + ("+spyral)" if args.spyral else ")"): stats_sum["ms_finalize"]}  # fmt: skip
+                "finalize (order+offsets+emit" + (", Spyral rows)" if args.spyral else ")"): stats_sum["ms_finalize"]}  # fmt: skip
     dominant = max(stage_ms, key=stage_ms.get)
     n_ev_rank = B * args.steps
     n_out = stats_sum["n_points"] / n_ev_rank
@@ -453,7 +486,14 @@ def run_ours(args):
                            "electrons uint32 + uint16, label int8; the host rebuilds the 8 float64 columns bit for bit" if args.spyral else
                            "cloud float64[N,3] + int64 labels" if args.float64_rows else
                            "typed columns: pad int16, time bucket uint32 Q16.16, electrons uint32 + list of the counts >= 2^32, label int8"),
-                "d2h_bytes_per_step": int(d2h_total)},
+                "d2h_bytes_per_step": int(d2h_total),
+                "call": (f"simulate_stream, {args.e2e_engines} engines per GPU: steps pipelined (the copy of one step to the "
+                         "host overlaps the kernels of the next); inputs are read from pinned host memory and results "
+                         "land in pinned host memory every step; working set per step >> L2" if piped_s is not None
+                         else "simulate_batch, one call after the other; L2 flushed between steps")},
+        "e2e_sync": None if args.no_e2e else {
+            "value": round(total_events / e2e_sync_s, 1), "unit": "events/s",
+            "what": "simulate_batch, one synchronous call per step, L2 flushed between steps"},
         "e2e_decoded": None if decoded_s is None else {
             "value": round(B / decoded_s, 1), "unit": "events/s per rank",
             "what": "one e2e step plus the host-side decode of the typed columns into the float64 / int64 arrays of the "
@@ -473,7 +513,7 @@ def run_pipeline(args):
     `--events-total` events (default 10 M) of `--workload` (default c16dd_sweep) are cut into chunks of `--events`;
     rank r of N takes a contiguous range of chunks (one process per GPU, no collective on the data path).  Per chunk:
     the vectorised `KinematicsPipeline.run_batch` (two prefetch threads; a chunk's seed depends on the chunk alone, so
-    the events do not depend on N), `simulate_batch` with host inputs and the typed columns back in pinned host memory,
+    the events do not depend on N), `simulate_stream` (pipelined `simulate_batch`) with host inputs and the typed columns back in pinned host memory,
     and a gather step that keeps the CSR offsets and per-chunk totals.  The real bulk writer (`ParquetCloudWriter`, zstd) is timed on the
     first `--writer-chunks` chunks of rank 0 into a scratch directory and reported beside it: a full 10 M-event cloud is
     ~0.9 TB as float64 rows (0.3 TB as typed columns), more than the box can hold or write in minutes.
@@ -502,7 +542,6 @@ def run_pipeline(args):
     n_chunks = -(-args.events_total // B)
     c0, c1 = shard_range(n_chunks, rank, world)
     config, m0, v0, zs, as_, indices = build_workload(name, 8)
-    eng = engine_for(config, _nuclei_for(zs, as_, indices, nuclear_map), device=local)
     K = m0.shape[1]
 
     def kinematics(c):
@@ -513,51 +552,59 @@ def run_pipeline(args):
         vertices, momenta = pipeline.run_batch(n)
         return c, momenta, vertices, time.perf_counter() - t0
 
-    def producer(chunks, out):
-        for c in chunks:
-            out.put(kinematics(c))
-        out.put(None)
-
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
 
-    # warm-up: buffers sized, kernels loaded
+    from concurrent.futures import ThreadPoolExecutor
+
+    from attpc_engine_b200.detector import simulate_stream
+
+    # warm-up: engines built, buffers sized, kernels loaded
     _, m, v, _ = kinematics(c0)
-    for _ in range(max(1, args.warmup)):
-        eng.simulate_batch(m, v, zs, as_, indices, seed=1, first_event=c0 * B, copy=False, columns=True)
+    warm = [(m, v, c0 * B)] * max(args.e2e_engines, args.warmup)
+    for _ in simulate_stream(warm, zs, as_, config, 1, indices, devices=[local], engines_per_device=args.e2e_engines,
+                             copy=False, columns=True):  # fmt: skip
+        pass
     barrier()
     wall0 = time.perf_counter()
-    q = queue.Queue(maxsize=4)
-    lanes = 2
-    threads = [threading.Thread(target=producer, args=(range(c0 + k, c1, lanes), q), daemon=True) for k in range(lanes)]
-    for t in threads:
-        t.start()
-    done, t_kin, t_sim, t_gather, events, points, electrons = 0, 0.0, 0.0, 0.0, 0, 0, 0
+    # kinematics of the next chunks on two prefetch threads, the chunks through the pipelined public call
+    pool = ThreadPoolExecutor(max_workers=2)
+    chunks = list(range(c0, c1))
+    futures, submitted, kin_lock = {}, [0], threading.Lock()
+    t_kin_box = [0.0]
+
+    def reader(k):
+        def read():
+            with kin_lock:
+                while submitted[0] < min(len(chunks), k + 5):
+                    futures[submitted[0]] = pool.submit(kinematics, chunks[submitted[0]])
+                    submitted[0] += 1
+                fut = futures.pop(k)
+            c, momenta, vertices, dt = fut.result()
+            t_kin_box[0] += dt
+            return momenta, vertices, c * B
+
+        read.thread_safe = True
+        return read
+
+    t_gather, events, points, electrons = 0.0, 0, 0, 0
     check = np.zeros(2, dtype=np.uint64)
-    while done < lanes:
-        item = q.get()
-        if item is None:
-            done += 1
-            continue
-        c, momenta, vertices, dt = item
-        t_kin += dt
-        t0 = time.perf_counter()
-        batch = eng.simulate_batch(momenta, vertices, zs, as_, indices, seed=20260101, first_event=c * B, copy=False,
-                                   columns=True)  # fmt: skip
+    for _, batch in simulate_stream([reader(k) for k in range(len(chunks))], zs, as_, config, 20260101, indices,
+                                    devices=[local], engines_per_device=args.e2e_engines, copy=False, columns=True):  # fmt: skip
         t1 = time.perf_counter()
         # gather: what a shard hands to the collector -- the CSR offsets and a checksum over the head of two columns
         # (reading every byte is the writer's job: see writer_sample)
         cols = batch.columns
         check[0] += np.uint64(int(np.add.reduce(cols["pad"][: 1 << 20], dtype=np.int64)) & (2**63 - 1))
         check[1] += np.uint64(int(batch.offsets[-1]))
-        t2 = time.perf_counter()
-        t_sim += t1 - t0
-        t_gather += t2 - t1
+        t_gather += time.perf_counter() - t1
         events += len(batch)
         points += batch.stats["n_points"]
         electrons += batch.stats["n_primary_electrons"]
+    pool.shutdown()
+    t_kin = t_kin_box[0]
     barrier()
     wall = time.perf_counter() - wall0
     wall = reduce_max(dist, wall, local)
@@ -603,8 +650,8 @@ def run_pipeline(args):
                    "events_per_chunk": B, "chunks_per_rank": c1 - c0, "parallelism": f"event-range shards x{world}",
                    "result": "typed columns in pinned host memory, per-chunk totals gathered"},
         "wall_s": round(wall, 3), "cloud_points": int(total_points), "electrons_per_s": round(total_electrons / wall, 1),
-        "rank0_seconds": {"kinematics (2 prefetch threads, summed)": round(t_kin, 3), "simulate_batch (host in, host out)": round(t_sim, 3),
-                          "gather": round(t_gather, 3)},
+        "rank0_seconds": {"kinematics (2 prefetch threads, summed)": round(t_kin, 3), "gather": round(t_gather, 3)},
+        "call": f"simulate_stream, {args.e2e_engines} engines per GPU (host in, typed columns in pinned host memory out)",
         "checksum": [int(check[0]), int(check[1])], "writer_sample": writer_info,
     }  # fmt: skip
     print(json.dumps(out), flush=True)
@@ -733,6 +780,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-numa", action="store_true", help="multi-GPU: do not bind each rank to the CPUs next to its GPU")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: only the device-resident steps")
+    ap.add_argument("--e2e-engines", type=int, default=2,
+                    help="engines per GPU of the pipelined e2e call (simulate_stream); 1 = synchronous calls only")
     ap.add_argument("--spyral", action="store_true", help="also produce the Spyral 8-column rows (full pad-plane response)")
     ap.add_argument("--pipeline", action="store_true",
                     help="BASELINE config 5: kinematics -> simulate -> host for --events-total events, sharded over the ranks")

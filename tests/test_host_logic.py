@@ -383,3 +383,34 @@ def test_hdf5_kinematics_reader_on_a_reference_written_file(monkeypatch):
     assert np.array_equal(data, flat["expected|momenta"]) and np.array_equal(vertices, flat["expected|vertices"])
     data, vertices = kin.read(5, 16)  # a range that crosses two chunk boundaries
     assert np.array_equal(data, flat["expected|momenta"][5:16]) and np.array_equal(vertices, flat["expected|vertices"][5:16])
+
+
+def test_simulate_stream_deals_batches_to_workers_and_keeps_order(monkeypatch):
+    """`simulate_stream`: batch k -> worker k mod W (GPUs in turn, `engines_per_device` engines each), results in
+    ascending order, callables are read inside the worker; one worker means no threads at all."""
+    import threading
+
+    from attpc_engine_b200.detector import simulator
+
+    calls = []
+
+    def fake(momenta, vertices, zs, as_, config, seed, indices, first_event=0, device=0, engine_instance=0, **kw):
+        calls.append((first_event, device, engine_instance, threading.current_thread() is threading.main_thread(), kw))
+        return ("batch", first_event)
+
+    monkeypatch.setattr(simulator, "simulate_batch", fake)
+    assert simulator._workers([0, 1], 2) == [0, 1, 0, 1]
+    with pytest.raises(ValueError):
+        simulator._workers([0], 0)
+    batches = [(lambda k=k: (np.zeros((4, 2, 4)), np.zeros((4, 3)), 100 * k)) if k % 2 else
+               (np.zeros((4, 2, 4)), np.zeros((4, 3)), 100 * k) for k in range(11)]
+    out = list(simulator.simulate_stream(batches, [1, 6], [2, 16], None, 7, [0, 1], devices=[3, 5], engines_per_device=2,
+                                         columns=True))
+    assert out == [(k, ("batch", 100 * k)) for k in range(11)]
+    by_event = {c[0]: c for c in calls}
+    for k in range(11):
+        first, device, instance, on_main, kw = by_event[100 * k]
+        assert (device, instance) == ([3, 5, 3, 5][k % 4], k % 4) and not on_main and kw == {"columns": True}
+    calls.clear()
+    out = list(simulator.simulate_stream(batches[:3], [1, 6], [2, 16], None, 7, [0, 1], devices=[2], engines_per_device=1))
+    assert [o[0] for o in out] == [0, 1, 2] and all(c[3] and c[1:3] == (2, 0) for c in calls)
