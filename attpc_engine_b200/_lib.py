@@ -12,7 +12,7 @@ from pathlib import Path
 
 LIB_NAME = "libattpc_b200.so"
 LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # flags (include/attpc_b200.h)
 KEEP_ALL_TB = 1 << 0
@@ -25,6 +25,7 @@ COLUMNS = 1 << 6
 EXACT_MESH = 1 << 7
 COLUMNS32 = 1 << 8
 SPYRAL_COLUMNS = 1 << 9
+COLUMNS_PACKED = 1 << 10
 
 
 class AttpcConfig(C.Structure):
@@ -129,6 +130,10 @@ class AttpcResult(C.Structure):
         ("row_col_e_lo", C.POINTER(C.c_uint32)),
         ("row_col_e_hi", C.POINTER(C.c_uint16)),
         ("row_col_label", C.POINTER(C.c_int8)),
+        ("col_wiggle", C.POINTER(C.c_uint16)),
+        ("tb_counts", C.POINTER(C.c_uint16)),
+        ("pad_rank_shift", C.c_int32),
+        ("reserved3", C.c_int32),
     ]
 
 

@@ -149,6 +149,8 @@ struct AttpcSim {
     DevArray<int64_t> col_q_dev, big_rows_dev, big_q_dev;
     DevArray<uint32_t> col_q32_dev;
     DevArray<int8_t> col_label_dev;
+    DevArray<uint16_t> col_wig_dev, tbc_dev;      // ATTPC_COLUMNS_PACKED: wiggle, rows per (event, time bucket)
+    PinnedArray<uint16_t> col_wig_host, tbc_host;
     PinnedArray<int16_t> col_pad_host;
     PinnedArray<uint32_t> col_tbq_host;
     PinnedArray<int64_t> col_q_host, big_rows_host, big_q_host;
@@ -282,6 +284,8 @@ int ensure_out_buffers(AttpcSim* sim, int64_t n_events, int64_t n_points, bool k
         CU(sim->big_rows_dev.reserve(ATTPC_BIG_CAP));
         CU(sim->big_q_dev.reserve(ATTPC_BIG_CAP));
         CU(sim->col_label_dev.reserve(sim->labels_dev.n, keep, sim->stream));
+        CU(sim->col_wig_dev.reserve(sim->labels_dev.n, keep, sim->stream));
+        CU(sim->tbc_dev.reserve((n_events + 1) * NUM_TB, keep, sim->stream));
     }
     return ATTPC_OK;
 }
@@ -559,6 +563,9 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     const bool copy_host = !(flags & ATTPC_SKIP_HOST_COPY);
     const bool use_columns = copy_host && (flags & ATTPC_COLUMNS);
     const bool use_q32 = use_columns && (flags & ATTPC_COLUMNS32) && !sim->q32_off;
+    // packed columns: pad ids and track ranks share 16 bits, the library's own 16-bit wiggle, masked time buckets
+    const bool use_packed = use_columns && (flags & ATTPC_COLUMNS_PACKED) && !plan.replay &&
+                            !(flags & ATTPC_KEEP_ALL_TB) && sim->P.n_pads <= (1 << 14) && plan.n_tracks_per_event <= 4;
     const bool spy_cols = (flags & ATTPC_SPYRAL_COLUMNS) != 0;            // Spyral rows as typed columns
     const bool spy_rows = (flags & ATTPC_SPYRAL_ROWS) != 0 && !spy_cols;  // ... as float64 [M, 8]
     const bool spy = spy_cols || spy_rows;
@@ -592,6 +599,10 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         if (use_q32) CU(sim->col_q32_host.reserve(sim->labels_dev.n));
         else CU(sim->col_q_host.reserve(sim->labels_dev.n));
         CU(sim->col_label_host.reserve(sim->labels_dev.n));
+        if (use_packed) {
+            CU(sim->col_wig_host.reserve(sim->labels_dev.n));
+            CU(sim->tbc_host.reserve(sim->tbc_dev.n));
+        }
     }
     auto reserve_spyral = [&](bool keep) -> int {  // the rows of an event are a subset of its cloud points
         int r = ensure_spyral_buffers(sim, n_events, sim->labels_dev.n, spy_cols, spy_rows);
@@ -720,8 +731,14 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         fa.out_cap = sim->labels_dev.n;
         if (use_columns) {
             fa.col_pad = sim->col_pad_dev.p;
-            fa.col_tb_q16 = sim->col_tbq_dev.p;
-            fa.col_label = sim->col_label_dev.p;
+            if (use_packed) {
+                fa.col_wiggle = sim->col_wig_dev.p;
+                fa.tb_counts = sim->tbc_dev.p + b0 * NUM_TB;
+                fa.rank_shift = 14;
+            } else {
+                fa.col_tb_q16 = sim->col_tbq_dev.p;
+                fa.col_label = sim->col_label_dev.p;
+            }
             if (use_q32) {
                 fa.col_electrons32 = sim->col_q32_dev.p;
                 fa.big_rows = sim->big_rows_dev.p;
@@ -783,6 +800,11 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                     CU(cudaMemcpyAsync(sim->row_offsets_host.p + first_off, sim->row_offsets_dev.p + first_off,
                                        (size_t)(end_off - first_off) * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
             }
+            if (use_packed && upto_event > copied_events)
+                CU(cudaMemcpyAsync(sim->tbc_host.p + (b0 + copied_events) * NUM_TB,
+                                   sim->tbc_dev.p + (b0 + copied_events) * NUM_TB,
+                                   (size_t)(upto_event - copied_events) * NUM_TB * sizeof(uint16_t),
+                                   cudaMemcpyDeviceToHost, C));
             const int64_t r_new = (int64_t)(rows_upto - rows_copied);
             if (r_new > 0 && spy_rows) {
                 CU(cudaMemcpyAsync(sim->rows_host.p + rows_copied * 8, sim->rows_dev.p + rows_copied * 8,
@@ -813,16 +835,21 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
             if (n_new > 0 && use_columns) {
                 CU(cudaMemcpyAsync(sim->col_pad_host.p + copied, sim->col_pad_dev.p + copied,
                                    (size_t)n_new * sizeof(int16_t), cudaMemcpyDeviceToHost, C));
-                CU(cudaMemcpyAsync(sim->col_tbq_host.p + copied, sim->col_tbq_dev.p + copied,
-                                   (size_t)n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, C));
+                if (use_packed)
+                    CU(cudaMemcpyAsync(sim->col_wig_host.p + copied, sim->col_wig_dev.p + copied,
+                                       (size_t)n_new * sizeof(uint16_t), cudaMemcpyDeviceToHost, C));
+                else
+                    CU(cudaMemcpyAsync(sim->col_tbq_host.p + copied, sim->col_tbq_dev.p + copied,
+                                       (size_t)n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, C));
                 if (use_q32)
                     CU(cudaMemcpyAsync(sim->col_q32_host.p + copied, sim->col_q32_dev.p + copied,
                                        (size_t)n_new * sizeof(uint32_t), cudaMemcpyDeviceToHost, C));
                 else
                     CU(cudaMemcpyAsync(sim->col_q_host.p + copied, sim->col_q_dev.p + copied,
                                        (size_t)n_new * sizeof(int64_t), cudaMemcpyDeviceToHost, C));
-                CU(cudaMemcpyAsync(sim->col_label_host.p + copied, sim->col_label_dev.p + copied,
-                                   (size_t)n_new * sizeof(int8_t), cudaMemcpyDeviceToHost, C));
+                if (!use_packed)
+                    CU(cudaMemcpyAsync(sim->col_label_host.p + copied, sim->col_label_dev.p + copied,
+                                       (size_t)n_new * sizeof(int8_t), cudaMemcpyDeviceToHost, C));
             }
             copy_marks.push_back({c0, sim->mark(C)});
             copied = upto;
@@ -878,6 +905,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                     if (use_q32) CU(sim->col_q32_host.reserve(sim->labels_dev.n, true));
                     else CU(sim->col_q_host.reserve(sim->labels_dev.n, true));
                     CU(sim->col_label_host.reserve(sim->labels_dev.n, true));
+                    if (use_packed) CU(sim->col_wig_host.reserve(sim->labels_dev.n, true));
                 }
                 if (spy) {  // the row buffers follow the cloud buffers (device side: rows of finished launches are kept)
                     if (spy_rows) {
@@ -955,7 +983,13 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
         }
         if (use_columns) {
             res->col_pad = sim->col_pad_host.p;
-            res->col_tb_q16 = sim->col_tbq_host.p;
+            if (use_packed) {
+                res->col_wiggle = sim->col_wig_host.p;
+                res->tb_counts = sim->tbc_host.p;
+                res->pad_rank_shift = 14;
+            } else {
+                res->col_tb_q16 = sim->col_tbq_host.p;
+            }
             if (!use_q32) {
                 res->col_electrons = sim->col_q_host.p;
             } else if ((int64_t)big_before <= sim->big_cap) {
@@ -978,7 +1012,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                 CU(cudaStreamSynchronize(G));
                 return run_batch(sim, plan, n_events, flags, res, ms_h2d);
             }
-            res->col_label = sim->col_label_host.p;
+            if (!use_packed) res->col_label = sim->col_label_host.p;
         }
     }
     if (spy) {
@@ -1075,6 +1109,7 @@ void attpc_destroy(AttpcSim* sim) {
     sim->rcol_label_dev.release(); sim->rcol_pad_host.release(); sim->rcol_tbq_host.release(); sim->rcol_elo_host.release();
     sim->rcol_ehi_host.release(); sim->rcol_label_host.release();
     sim->col_pad_dev.release(); sim->col_tbq_dev.release(); sim->col_q_dev.release(); sim->col_q32_dev.release(); sim->big_rows_dev.release(); sim->big_q_dev.release(); sim->col_label_dev.release();
+    sim->col_wig_dev.release(); sim->tbc_dev.release(); sim->col_wig_host.release(); sim->tbc_host.release();
     sim->col_pad_host.release(); sim->col_tbq_host.release(); sim->col_q_host.release(); sim->col_q32_host.release(); sim->big_rows_host.release(); sim->big_q_host.release(); sim->col_label_host.release();
     sim->offsets_host.release(); sim->labels_host.release(); sim->row_offsets_host.release();
     sim->row_labels_host.release(); sim->cloud_host.release(); sim->rows_host.release();

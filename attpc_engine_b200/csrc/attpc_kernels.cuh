@@ -1575,6 +1575,11 @@ struct FinalizeArgs {
     int64_t* big_electrons;
     unsigned long long* big_count;  // running number of exceptions of the call (also counts what did not fit)
     int64_t big_cap;
+    // packed columns (ATTPC_COLUMNS_PACKED): col_pad = pad | rank << rank_shift, the wiggle alone, rows per time
+    // bucket and event; col_tb_q16 / col_label are then null
+    uint16_t* col_wiggle;
+    uint16_t* tb_counts;      // [launch events][NUM_TB]
+    int32_t rank_shift, pad2_;
     unsigned long long* csr_total;  // running totals of the call {cloud rows, electron counts >= 2^32, Spyral rows}
     uint4* staged;            // [chunk events][hash_cap] ordered rows of every event, 16 B each (order_kernel -> emit_kernel):
                               //   x = time bucket << 16 | wiggle (16 bit);  y = electrons, low 32 bits;
@@ -2198,9 +2203,23 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
     const uint4* staged = fa.staged + (int64_t)L * chunk.hash_cap;
     const bool replayed = fa.replay.offsets != nullptr;
     const double span = (double)(P.win_edge - P.mm_edge);
-    for (int i = threadIdx.x; i < n; i += EMIT_THREADS) {
-        const uint4 s = __ldcs(staged + i);
+    const bool packed = fa.col_wiggle != nullptr;
+    __shared__ unsigned s_tb[NUM_TB];  // packed columns: rows of the event per time bucket
+    if (packed) {
+        for (int b = threadIdx.x; b < NUM_TB; b += EMIT_THREADS) s_tb[b] = 0u;
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    for (int i0 = threadIdx.x - lane; i0 < n; i0 += EMIT_THREADS) {  // (warp-uniform trip count)
+        const int i = i0 + lane;
+        const bool valid = i < n;
+        const uint4 s = valid ? __ldcs(staged + i) : make_uint4(0xFFFF0000u, 0u, 0u, 0u);
         const unsigned tb = s.x >> 16, pad = (s.z >> 16) & 0x7FFFu, rk = s.w & 0xFu;
+        if (packed) {  // rows come in time-bucket order: a warp sees a few runs, one shared-memory add per run
+            const unsigned peers = __match_any_sync(FULL, tb);
+            if (valid && lane == __ffs(peers) - 1) atomicAdd(&s_tb[min(tb, (unsigned)NUM_TB - 1u)], (unsigned)__popc(peers));
+        }
+        if (!valid) continue;
         const unsigned long long q = ((unsigned long long)(s.z & 0xFFFFu) << 32) | s.y;
         uint32_t u16 = s.x & 0xFFFFu;
         double u = (double)u16 * (1.0 / 65536.0);
@@ -2221,9 +2240,14 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
             fa.labels[r] = label;
         }
         if (fa.col_pad) {  // only the columns that will be copied are written
-            fa.col_pad[r] = (int16_t)pad;
-            fa.col_tb_q16[r] = (tb << 16) | u16;
-            fa.col_label[r] = (int8_t)label;
+            if (packed) {
+                fa.col_pad[r] = (int16_t)(pad | (rk << fa.rank_shift));
+                fa.col_wiggle[r] = (uint16_t)u16;
+            } else {
+                fa.col_pad[r] = (int16_t)pad;
+                fa.col_tb_q16[r] = (tb << 16) | u16;
+                fa.col_label[r] = (int8_t)label;
+            }
             if (fa.col_electrons) fa.col_electrons[r] = (long long)q;
             if (fa.col_electrons32) {
                 fa.col_electrons32[r] = (uint32_t)q;
@@ -2259,6 +2283,11 @@ emit_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finaliz
                 fa.row_labels[at] = label;
             }
         }
+    }
+    if (packed) {
+        __syncthreads();
+        uint16_t* counts = fa.tb_counts + (int64_t)slot_event * NUM_TB;
+        for (int b = threadIdx.x; b < NUM_TB; b += EMIT_THREADS) counts[b] = (uint16_t)s_tb[b];
     }
 }
 

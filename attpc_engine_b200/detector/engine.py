@@ -71,10 +71,15 @@ class SimBatch:
     2^32) plus the sorted ``big_rows`` / ``big_electrons`` of the rows that need more: 11 instead of 32 bytes per row
     over PCIe).  ``cloud`` / ``labels`` / ``event(e)`` work in both
     cases; with columns they are materialised on demand.
+
+    The engine ships the columns in a packed form when it can (``packed``: 8 B/row + 1 KB/event): rows are in ascending
+    time-bucket order, so the integer time bucket travels as ``tb_counts [B, 512]`` (rows per time bucket and event), the
+    wiggle as ``wiggle`` uint16, and the track rank sits in the two bits above the 14-bit pad id (``pad_rank`` uint16;
+    ``labels_of_rank`` maps it to the nucleus index).  ``columns`` then decodes them on first use.
     """
 
     def __init__(self, first_event, offsets, cloud=None, labels=None, row_offsets=None, rows=None, row_labels=None,
-                 stats=None, columns=None, row_columns=None, row_builder=None):  # fmt: skip
+                 stats=None, columns=None, row_columns=None, row_builder=None, packed=None):  # fmt: skip
         self.first_event = first_event
         self.offsets = offsets
         self._cloud = cloud
@@ -83,12 +88,45 @@ class SimBatch:
         self._rows = rows  # [M, 8] Spyral rows
         self._row_labels = row_labels
         self.stats = {} if stats is None else stats
-        self.columns = columns  # dict(pad, tb_q16, label8, and electrons or electrons_u32 + big_rows + big_electrons) or None
+        self._columns = columns  # dict(pad, tb_q16, label8, and electrons or electrons_u32 + big_rows + big_electrons) or None
+        #: packed wire form of the same columns: dict(pad_rank uint16, wiggle uint16, tb_counts uint16 [B, 512],
+        #: labels_of_rank int8 [4], rank_shift, and the electron columns) or None
+        self.packed = packed
         #: Spyral rows (after ADC threshold, z-sorted) as typed columns: dict(pad int16, tb_q16 uint32, e_lo uint32,
         #: e_hi uint16, label8 int8) -- 13 B/row over PCIe instead of 72; ``rows`` / ``row_labels`` / ``event_rows`` rebuild
         #: the float64 arrays from them on demand, bit for bit (`Engine.rows_from_columns`)
         self.row_columns = row_columns
         self._row_builder = row_builder
+
+    @property
+    def columns(self):
+        if self._columns is None and self.packed is not None:
+            self._columns = self._unpack(0, len(self), 0, len(self.packed["pad_rank"]))
+        return self._columns
+
+    @columns.setter
+    def columns(self, value):
+        self._columns = value
+
+    def _unpack(self, e0: int, e1: int, a: int, b: int) -> dict:
+        """Typed columns of events ``e0:e1`` (rows ``a:b``) from the packed wire form."""
+        p = self.packed
+        shift = p["rank_shift"]
+        pad_rank = p["pad_rank"][a:b]
+        counts = p["tb_counts"][e0:e1]
+        tb = np.repeat(np.tile(np.arange(counts.shape[1], dtype=np.uint32), e1 - e0), counts.ravel())
+        out = dict(
+            pad=(pad_rank & np.uint16((1 << shift) - 1)).astype(np.int16),
+            tb_q16=(tb << np.uint32(16)) | p["wiggle"][a:b],
+            label8=p["labels_of_rank"][pad_rank >> np.uint16(shift)],
+        )
+        if "electrons" in p:
+            out["electrons"] = p["electrons"][a:b]
+        else:
+            lo, hi = np.searchsorted(p["big_rows"], [a, b])
+            out.update(electrons_u32=p["electrons_u32"][a:b], big_rows=p["big_rows"][lo:hi] - a,
+                       big_electrons=p["big_electrons"][lo:hi])  # fmt: skip
+        return out
 
     @property
     def rows(self):
@@ -147,6 +185,9 @@ class SimBatch:
     def event(self, e: int) -> tuple[np.ndarray, np.ndarray]:
         """``(cloud [n, 3] float64, labels [n] int64)`` of event ``e``, like `simulate` returns them."""
         a, b = self.offsets[e], self.offsets[e + 1]
+        if self._cloud is None and self._columns is None and self.packed is not None:  # only this event is decoded
+            one = SimBatch(self.first_event + e, np.array([0, b - a]), columns=self._unpack(e, e + 1, int(a), int(b)))
+            return one.cloud, one.labels
         if self._cloud is None and self.columns is not None:
             c = self.columns
             cloud = np.empty((b - a, 3), dtype=np.float64)
@@ -314,7 +355,7 @@ class Engine:
                 spec[t] = self.species_index[(z, a)]
         return np.ascontiguousarray(nucleus), spec
 
-    def _collect(self, res: _lib.AttpcResult, first_event: int, copy: bool, rows: bool) -> SimBatch:
+    def _collect(self, res: _lib.AttpcResult, first_event: int, copy: bool, rows: bool, track_labels=()) -> SimBatch:
         n_ev, n_pts = int(res.n_events), int(res.n_points)
         stats = {k: getattr(res, k) for k in _STAT_FIELDS}
         if not res.offsets:  # SKIP_HOST_COPY
@@ -322,14 +363,24 @@ class Engine:
                             stats=dict(stats, n_points=n_pts))  # fmt: skip
         grab = (lambda a: a.copy()) if copy else (lambda a: a)
         offsets = grab(np.ctypeslib.as_array(res.offsets, shape=(n_ev + 1,)))
-        columns = None
+        columns = packed = None
         if res.col_pad:
             take = (lambda p: grab(np.ctypeslib.as_array(p, shape=(n_pts,)))) if n_pts > 0 else None
-            columns = dict(
-                pad=take(res.col_pad) if take else np.zeros(0, np.int16),
-                tb_q16=take(res.col_tb_q16) if take else np.zeros(0, np.uint32),
-                label8=take(res.col_label) if take else np.zeros(0, np.int8),
-            )
+            if res.col_wiggle:  # ATTPC_COLUMNS_PACKED
+                labels_of_rank = np.zeros(4, dtype=np.int8)
+                labels_of_rank[: len(track_labels)] = track_labels
+                columns = packed = dict(
+                    pad_rank=take(res.col_pad).view(np.uint16) if take else np.zeros(0, np.uint16),
+                    wiggle=take(res.col_wiggle) if take else np.zeros(0, np.uint16),
+                    tb_counts=grab(np.ctypeslib.as_array(res.tb_counts, shape=(n_ev, NUM_TB))) if n_ev else np.zeros((0, NUM_TB), np.uint16),
+                    labels_of_rank=labels_of_rank, rank_shift=int(res.pad_rank_shift),
+                )  # fmt: skip
+            else:
+                columns = dict(
+                    pad=take(res.col_pad) if take else np.zeros(0, np.int16),
+                    tb_q16=take(res.col_tb_q16) if take else np.zeros(0, np.uint32),
+                    label8=take(res.col_label) if take else np.zeros(0, np.int8),
+                )
             if res.col_electrons32:  # compact: low 32 bits + the (row, count) pairs of the counts that need more
                 n_big = int(res.n_big)
                 rows_big = np.ctypeslib.as_array(res.big_rows, shape=(n_big,)).copy() if n_big else np.zeros(0, np.int64)
@@ -345,7 +396,8 @@ class Engine:
             labels = grab(np.ctypeslib.as_array(res.labels, shape=(n_pts,)))
         else:
             cloud, labels = np.zeros((0, 3)), np.zeros(0, np.int64)
-        out = SimBatch(first_event, offsets, cloud, labels, stats=dict(stats, n_points=n_pts), columns=columns)
+        out = SimBatch(first_event, offsets, cloud, labels, stats=dict(stats, n_points=n_pts, packed=int(packed is not None)),
+                       columns=None if packed is not None else columns, packed=packed)
         if rows and res.row_col_pad:
             n_rows = int(res.n_rows)
             out.row_offsets = grab(np.ctypeslib.as_array(res.row_offsets, shape=(n_ev + 1,)))
@@ -435,12 +487,15 @@ class Engine:
         rows_only: bool = False,
         columns: bool = False,
         row_columns: bool = False,
+        packed: bool = True,
     ) -> SimBatch:
         """`simulate` (`simulator.py:52-115`) for ``B`` events at once: ``momenta [B, K, 4]``, ``vertices [B, 3]``.
 
         ``rows_only`` (with ``spyral_rows``): bring back offsets and Spyral rows but leave the raw cloud on the GPU.
         ``columns``: bring the rows back as typed columns (11 B/row instead of 32 B/row over PCIe), see `SimBatch`.
         ``row_columns`` (with ``spyral_rows``): the Spyral rows as typed columns too (13 instead of 72 B/row).
+        ``packed`` (with ``columns``, default): let the library pack the columns further when it can (8 B/row + 1 KB/event,
+        `SimBatch.packed`); ``batch.columns`` decodes them on first use.
         """
         momenta = np.ascontiguousarray(momenta, dtype=np.float64)
         vertices = np.ascontiguousarray(vertices, dtype=np.float64)
@@ -457,7 +512,7 @@ class Engine:
         if rows_only and spyral_rows:
             flags |= _lib.SKIP_CLOUD_COPY
         elif columns:
-            flags |= _lib.COLUMNS | _lib.COLUMNS32
+            flags |= _lib.COLUMNS | _lib.COLUMNS32 | (_lib.COLUMNS_PACKED if packed else 0)
         flags |= self._mesh_flag()
         res = _lib.AttpcResult()
         code = self.lib.attpc_simulate(
@@ -466,7 +521,7 @@ class Engine:
             flags, C.byref(res),
         )  # fmt: skip
         _lib.check(code, self.handle)
-        return self._collect(res, first_event, copy, spyral_rows)
+        return self._collect(res, first_event, copy, spyral_rows, track_labels=nucleus)
 
     def simulate_device(
         self, momenta_ptr: int, vertices_ptr: int, n_events: int, n_nuclei: int, proton_numbers, mass_numbers,

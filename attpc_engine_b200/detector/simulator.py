@@ -69,6 +69,7 @@ def simulate_batch(
     columns: bool = False,
     row_columns: bool = False,
     engine_instance: int = 0,
+    packed: bool = True,
     **tuning,
 ) -> SimBatch:
     """Detector simulation of ``B`` kinematics events in one call.
@@ -91,7 +92,7 @@ def simulate_batch(
     engine = engine_for(config, charged, device=device, instance=engine_instance, **tuning)
     return engine.simulate_batch(
         momenta, vertices, proton_numbers, mass_numbers, indices, seed=seed, first_event=first_event,
-        spyral_rows=spyral_rows, copy=copy, rows_only=rows_only, columns=columns, row_columns=row_columns,
+        spyral_rows=spyral_rows, copy=copy, rows_only=rows_only, columns=columns, row_columns=row_columns, packed=packed,
     )  # fmt: skip
 
 

@@ -297,8 +297,13 @@ def run_ours(args):
                                   row_columns=args.spyral and not args.float64_rows,
                                   columns=not args.float64_rows)  # fmt: skip
 
+    e2e_packed = False
+
     def step_e2e(i):
-        return batch_e2e(i).stats
+        nonlocal e2e_packed
+        st = batch_e2e(i).stats
+        e2e_packed = bool(st.get("packed", 0))
+        return st
 
     def stream_e2e(n_steps, step0):
         """n_steps batches through `simulate_stream` (the pipelined public call that `run_simulation` uses): engines
@@ -308,6 +313,7 @@ def run_ours(args):
 
         batches = [(mom_pin.numpy(), vtx_pin.numpy(), (step0 + k) * world * B + first) for k in range(n_steps)]
         pts = rows = big = 0
+        nonlocal e2e_packed
         for _, b in simulate_stream(batches, zs, as_, config, seed, indices, devices=[local],
                                     engines_per_device=args.e2e_engines, copy=False, spyral_rows=args.spyral,
                                     rows_only=args.spyral, row_columns=args.spyral and not args.float64_rows,
@@ -315,6 +321,7 @@ def run_ours(args):
             pts += b.stats["n_points"]
             big += b.stats.get("n_big", 0)
             rows += b.stats.get("n_rows", 0)
+            e2e_packed = bool(b.stats.get("packed", 0))
         return pts, rows, big
 
     sampler = ClockSampler(local)
@@ -390,7 +397,8 @@ def run_ours(args):
     deposits = reduce_sum(dist, stats_sum["n_deposits"], local)
     # bytes this rank brought to the host per step of the e2e loop (rows + CSR offsets), summed over the ranks
     row_bytes = (e2e_rows * (72 if args.float64_rows else 13) if args.spyral
-                 else e2e_points * (32 if args.float64_rows else 11) + 16 * e2e_big)
+                 else e2e_points * (32 if args.float64_rows else 8 if e2e_packed else 11) + 16 * e2e_big
+                 + (1024 * B * args.steps if e2e_packed and not args.float64_rows else 0))
     d2h_local = 0.0 if args.no_e2e else row_bytes / max(1, args.steps) + (B + 1) * 8 * (2 if args.spyral else 1)
     d2h_total = reduce_sum(dist, d2h_local, local)
 
@@ -485,6 +493,8 @@ def run_ours(args):
                            "Spyral rows (ADC threshold, z-sorted) as typed columns: pad int16, time bucket uint32 Q16.16, "
                            "electrons uint32 + uint16, label int8; the host rebuilds the 8 float64 columns bit for bit" if args.spyral else
                            "cloud float64[N,3] + int64 labels" if args.float64_rows else
+                           "packed typed columns: pad id + track rank uint16, wiggle uint16, electrons uint32 + list of the "
+                           "counts >= 2^32, rows per (event, time bucket) uint16 [B, 512]: 8 B/row + 1 KB/event, lossless" if e2e_packed else
                            "typed columns: pad int16, time bucket uint32 Q16.16, electrons uint32 + list of the counts >= 2^32, label int8"),
                 "d2h_bytes_per_step": int(d2h_total),
                 "call": (f"simulate_stream, {args.e2e_engines} engines per GPU: steps pipelined (the copy of one step to the "
@@ -518,7 +528,6 @@ def run_pipeline(args):
     first `--writer-chunks` chunks of rank 0 into a scratch directory and reported beside it: a full 10 M-event cloud is
     ~0.9 TB as float64 rows (0.3 TB as typed columns), more than the box can hold or write in minutes.
     """
-    import queue
     import shutil
     import tempfile
     import threading
@@ -596,8 +605,8 @@ def run_pipeline(args):
         t1 = time.perf_counter()
         # gather: what a shard hands to the collector -- the CSR offsets and a checksum over the head of two columns
         # (reading every byte is the writer's job: see writer_sample)
-        cols = batch.columns
-        check[0] += np.uint64(int(np.add.reduce(cols["pad"][: 1 << 20], dtype=np.int64)) & (2**63 - 1))
+        head = batch.packed["pad_rank"] if batch.packed is not None else batch.columns["pad"]
+        check[0] += np.uint64(int(np.add.reduce(head[: 1 << 20], dtype=np.int64)) & (2**63 - 1))
         check[1] += np.uint64(int(batch.offsets[-1]))
         t_gather += time.perf_counter() - t1
         events += len(batch)
@@ -616,7 +625,7 @@ def run_pipeline(args):
     # the real bulk writer on a bounded sample (rank 0)
     writer_info = None
     if args.writer_chunks > 0:
-        from attpc_engine_b200.detector import ParquetCloudWriter
+        from attpc_engine_b200.detector import ParquetCloudWriter, simulate_batch
 
         tmp = Path(tempfile.mkdtemp(prefix="attpc_bench_"))
         try:
@@ -626,8 +635,8 @@ def run_pipeline(args):
             t_w = 0.0
             for c in range(c0, c0 + n_w):
                 _, momenta, vertices, _ = kinematics(c)
-                batch = eng.simulate_batch(momenta, vertices, zs, as_, indices, seed=20260101, first_event=c * B,
-                                           copy=False, columns=True)  # fmt: skip
+                batch = simulate_batch(momenta, vertices, zs, as_, config, 20260101, indices, first_event=c * B,
+                                       device=local, copy=False, columns=True)  # fmt: skip
                 t0 = time.perf_counter()
                 w.write_batch(batch, config)
                 t_w += time.perf_counter() - t0
@@ -780,7 +789,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-numa", action="store_true", help="multi-GPU: do not bind each rank to the CPUs next to its GPU")
     ap.add_argument("--no-e2e", action="store_true", help="profiling aid: only the device-resident steps")
-    ap.add_argument("--e2e-engines", type=int, default=2,
+    ap.add_argument("--e2e-engines", type=int, default=3,
                     help="engines per GPU of the pipelined e2e call (simulate_stream); 1 = synchronous calls only")
     ap.add_argument("--spyral", action="store_true", help="also produce the Spyral 8-column rows (full pad-plane response)")
     ap.add_argument("--pipeline", action="store_true",

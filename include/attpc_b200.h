@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define ATTPC_ABI_VERSION 6
+#define ATTPC_ABI_VERSION 7
 
 enum {
     ATTPC_OK = 0,
@@ -47,6 +47,13 @@ enum {
                                       [M, 8]: row_col_* of AttpcResult, 13 B/row.  x, y, pad size follow from the pad id,
                                       z from the time bucket, amplitude and integral from the electrons: the host rebuilds
                                       the eight columns bit for bit */
+    ATTPC_COLUMNS_PACKED = 1u << 10,/* with ATTPC_COLUMNS: 8 B/row + 1 KB/event instead of 11 B/row.  Rows are in ascending
+                                      time-bucket order, so the integer time bucket travels as the number of rows per
+                                      time bucket and event (tb_counts [n_events, 512] uint16), the wiggle as col_wiggle
+                                      (uint16, k / 65536), and the track rank in the two bits above the 14-bit pad id
+                                      (pad_rank_shift = 14; label = the nucleus index of that rank).  Only when pad ids
+                                      are below 16384, at most four tracks per event, the library's own wiggle and the
+                                      time-bucket mask are in force; otherwise the call returns the columns above */
     ATTPC_EXACT_MESH = 1u << 7     /* validation: evaluate every mesh pixel with the reference's own expression
                                       (detector/transporter.py:36-41, 240-246).  The default reads pdf * step^2 from
                                       the constant 10x10 weight table and falls back to that expression only where
@@ -162,6 +169,12 @@ typedef struct AttpcResult {
     const uint32_t* row_col_e_lo;    /* [n_rows] electrons (after gain), bits 0..31 */
     const uint16_t* row_col_e_hi;    /* [n_rows] electrons, bits 32..47 */
     const int8_t* row_col_label;     /* [n_rows] */
+    /* ATTPC_COLUMNS_PACKED (set only when the call could use it; col_tb_q16 and col_label are then null):
+       col_pad = pad | rank << pad_rank_shift */
+    const uint16_t* col_wiggle;      /* [n_points] wiggle * 65536 */
+    const uint16_t* tb_counts;       /* [n_events, 512] rows of event e in time bucket t */
+    int32_t pad_rank_shift;          /* 14, or 0 when the call is not packed */
+    int32_t reserved3;
 } AttpcResult;
 
 typedef struct AttpcSim AttpcSim;

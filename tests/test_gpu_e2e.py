@@ -337,6 +337,31 @@ def test_typed_columns_hold_the_same_rows(dist):
     assert np.array_equal(cols.cloud, plain.cloud) and np.array_equal(cols.labels, plain.labels)
 
 
+@pytest.mark.parametrize("name", ["c16dd", "c12aa", "sn132dp"])
+def test_packed_columns_hold_the_same_rows(dist, name):
+    """The packed wire form (8 B/row + 1 KB/event: rows per time bucket, wiggle, pad id + track rank in 16 bits) decodes
+    to the typed columns of an unpacked call, and both to the float64 cloud; small launches and copy chunks, so that the
+    per-event counts of many chunks land in the right places."""
+    cfg, m, v, zs, as_, idx = _workload(dist, name, 300)
+    n = len(m)
+    plain = simulate_batch(m, v, zs, as_, cfg, 31, idx)
+    loose = simulate_batch(m, v, zs, as_, cfg, 31, idx, columns=True, packed=False)
+    tight = simulate_batch(m, v, zs, as_, cfg, 31, idx, columns=True, max_events_per_launch=64, copy_events_per_launch=64)
+    assert loose.packed is None and loose.columns is not None
+    if len(idx) <= 4:
+        assert tight.packed is not None and tight.packed["tb_counts"].shape == (n, 512)
+        assert np.array_equal(tight.packed["tb_counts"].sum(axis=1), np.diff(plain.offsets))
+    else:  # more than four tracks: ranks do not fit above the pad id, the library answers with the plain columns
+        assert tight.packed is None
+    assert np.array_equal(tight.offsets, plain.offsets)
+    for e in (0, 17, n - 1):
+        assert np.array_equal(tight.event(e)[0], plain.event(e)[0]) and np.array_equal(tight.event(e)[1], plain.event(e)[1])
+    assert tight.columns.keys() == loose.columns.keys()
+    for key in loose.columns:
+        assert np.array_equal(tight.columns[key], loose.columns[key]) and tight.columns[key].dtype == loose.columns[key].dtype, key
+    assert np.array_equal(tight.cloud, plain.cloud) and np.array_equal(tight.labels, plain.labels)
+
+
 @pytest.mark.parametrize("name, n", [("c16dd", 300), ("sn132dp", 150), ("c12aa", 60)])
 def test_spyral_columns_rebuild_the_float64_rows(name, n):
     """`row_columns=True` ships the thresholded, z-sorted Spyral rows as typed columns (13 instead of 72 B/row); the

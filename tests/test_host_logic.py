@@ -414,3 +414,44 @@ def test_simulate_stream_deals_batches_to_workers_and_keeps_order(monkeypatch):
     calls.clear()
     out = list(simulator.simulate_stream(batches[:3], [1, 6], [2, 16], None, 7, [0, 1], devices=[2], engines_per_device=1))
     assert [o[0] for o in out] == [0, 1, 2] and all(c[3] and c[1:3] == (2, 0) for c in calls)
+
+
+def test_packed_columns_decode():
+    """`SimBatch` with the packed wire form (pad id + rank in 16 bits, wiggle, rows per time bucket and event): the
+    typed columns, the float64 cloud and single events decoded from it."""
+    from attpc_engine_b200.detector.engine import SimBatch
+
+    rng = np.random.default_rng(3)
+    n_ev = 5
+    counts = np.zeros((n_ev, 512), dtype=np.uint16)
+    for e in range(n_ev):
+        tbs = rng.choice(512, size=rng.integers(0, 40), replace=False)
+        counts[e, tbs] = rng.integers(1, 9, size=len(tbs))
+    counts[3] = 0  # an empty event
+    per_event = counts.sum(axis=1).astype(np.int64)
+    offsets = np.concatenate([[0], np.cumsum(per_event)])
+    n = int(offsets[-1])
+    pad = rng.integers(0, 10240, size=n).astype(np.uint16)
+    rank = rng.integers(0, 3, size=n).astype(np.uint16)
+    wiggle = rng.integers(0, 65536, size=n).astype(np.uint16)
+    e32 = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    big_rows = np.sort(rng.choice(n, size=7, replace=False)).astype(np.int64)
+    big_e = (rng.integers(1, 2**10, size=7).astype(np.int64) << 32) | e32[big_rows].astype(np.int64)
+    packed = dict(pad_rank=pad | (rank << 14), wiggle=wiggle, tb_counts=counts, rank_shift=14,
+                  labels_of_rank=np.array([2, 3, 5, 0], dtype=np.int8), electrons_u32=e32, big_rows=big_rows,
+                  big_electrons=big_e)  # fmt: skip
+    tb = np.concatenate([np.repeat(np.arange(512), counts[e]) for e in range(n_ev)])
+    electrons = e32.astype(np.float64)
+    electrons[big_rows] = big_e
+    batch = SimBatch(100, offsets, packed=packed)
+    for e in range(n_ev):  # single events first: nothing else is decoded
+        a, b = offsets[e], offsets[e + 1]
+        cloud, labels = batch.event(e)
+        assert batch._columns is None
+        assert np.array_equal(cloud[:, 0], pad[a:b]) and np.array_equal(cloud[:, 1], tb[a:b] + wiggle[a:b] / 65536.0)
+        assert np.array_equal(cloud[:, 2], electrons[a:b])
+        assert np.array_equal(labels, np.array([2, 3, 5])[rank[a:b]]) and labels.dtype == np.int64
+    cols = batch.columns
+    assert cols["pad"].dtype == np.int16 and cols["tb_q16"].dtype == np.uint32 and cols["label8"].dtype == np.int8
+    assert np.array_equal(cols["pad"], pad) and np.array_equal(cols["tb_q16"], (tb.astype(np.uint32) << 16) | wiggle)
+    assert np.array_equal(batch.cloud[:, 2], electrons) and np.array_equal(batch.labels, np.array([2, 3, 5])[rank])
