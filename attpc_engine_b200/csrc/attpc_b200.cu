@@ -230,7 +230,9 @@ int next_pow2(int64_t v) {
 // arrays and two bit-mask / running-count arrays
 int64_t scratch_stride(int64_t hash_cap) { return 2 * hash_cap + hash_cap / 32 + 2; }
 
-int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
+// `chunk_groups`: groups whose kernels run in one launch (run_groups): sizes the per-event entry lists, the ordering
+// scratch and the staged rows -- the big buffers (16 B x hash_cap per event each).
+int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks, int64_t chunk_groups) {
     const int64_t n_groups = (launch_events + sim->group_events - 1) / sim->group_events;
     if (sim->group_point_cap == 0) sim->group_point_cap = (int64_t)sim->group_events * 1024;
     const int64_t pts = n_groups * sim->group_point_cap;
@@ -260,8 +262,7 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks) {
     CU(sim->n_entries.reserve(launch_events));
     CU(sim->mode.reserve(launch_events));
     // tables and sort scratch for one chunk of groups (run_groups)
-    const int64_t copy_groups = (sim->copy_launch_events + sim->group_events - 1) / sim->group_events;
-    const int64_t table_groups = std::min<int64_t>(n_groups, std::max<int64_t>(sim->chunk_groups, copy_groups));
+    const int64_t table_groups = std::min<int64_t>(n_groups, std::max<int64_t>(1, chunk_groups));
     CU(sim->hash.reserve(table_groups * sim->group_events * sim->hash_cap));
     CU(sim->sort_items.reserve(table_groups * sim->group_events * scratch_stride(sim->hash_cap)));
     CU(sim->staged.reserve(table_groups * sim->group_events * sim->hash_cap));
@@ -586,7 +587,9 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
     const int groups_per_chunk =
         std::max<int>(1, (int)((sim->copy_launch_events + sim->group_events - 1) / sim->group_events));
     const int32_t ranks = std::max<int32_t>(1, plan.n_tracks_per_event);
-    rc = ensure_work_buffers(sim, std::min<int64_t>(std::max<int64_t>(n_events, 1), launch_cap), ranks);
+    // a call that copies its rows to the host works in chunks of a few groups: its engine needs an eighth of the memory
+    const int64_t table_groups = copy_host ? groups_per_chunk : sim->chunk_groups;
+    rc = ensure_work_buffers(sim, std::min<int64_t>(std::max<int64_t>(n_events, 1), launch_cap), ranks, table_groups);
     if (rc) return rc;
     if (copy_host) CU(sim->offsets_host.reserve(sim->offsets_dev.n));
     if (copy_cloud) {  // pinned mirrors are sized like the device buffers: (re)allocated only when those grow
@@ -922,7 +925,7 @@ int run_batch(AttpcSim* sim, const LaunchPlan& plan, int64_t n_events, uint32_t 
                     if (rc) return rc;
                 }
             }
-            rc = ensure_work_buffers(sim, std::min<int64_t>(n_events, launch_cap), ranks);
+            rc = ensure_work_buffers(sim, std::min<int64_t>(n_events, launch_cap), ranks, table_groups);
             if (rc) return rc;
             sim->csr_host.p[0] = csr_before;  // forget the rows (and the big-count exceptions) of the failed attempt
             sim->csr_host.p[1] = big_before;
@@ -1491,7 +1494,7 @@ int attpc_trajectories(AttpcSim* sim, const double* momenta, const double* verti
     for (int64_t t = 0; t < n_tracks; ++t)
         if (species[t] >= sim->P.n_species) return sim->fail(ATTPC_E_BADARG, "species[%lld] out of range", (long long)t);
     CU(cudaSetDevice(sim->device));
-    int rc = ensure_work_buffers(sim, 1, 1);
+    int rc = ensure_work_buffers(sim, 1, 1, 1);
     if (rc) return rc;
     DevArray<double> d_m, d_v, d_out;
     DevArray<int32_t> d_sp, d_cnt;

@@ -305,7 +305,7 @@ def run_ours(args):
         e2e_packed = bool(st.get("packed", 0))
         return st
 
-    def stream_e2e(n_steps, step0):
+    def stream_e2e(n_steps, step0, float64_rows=args.float64_rows, engines=None):
         """n_steps batches through `simulate_stream` (the pipelined public call that `run_simulation` uses): engines
         alternate on this GPU, the copy of one batch to the host overlaps the kernels of the next.  Every batch is
         this rank's B events under fresh global event numbers (fresh random streams)."""
@@ -313,16 +313,16 @@ def run_ours(args):
 
         batches = [(mom_pin.numpy(), vtx_pin.numpy(), (step0 + k) * world * B + first) for k in range(n_steps)]
         pts = rows = big = 0
-        nonlocal e2e_packed
+        was_packed = False
         for _, b in simulate_stream(batches, zs, as_, config, seed, indices, devices=[local],
-                                    engines_per_device=args.e2e_engines, copy=False, spyral_rows=args.spyral,
-                                    rows_only=args.spyral, row_columns=args.spyral and not args.float64_rows,
-                                    columns=not args.float64_rows, **tuning):  # fmt: skip
+                                    engines_per_device=engines or args.e2e_engines, copy=False, spyral_rows=args.spyral,
+                                    rows_only=args.spyral, row_columns=args.spyral and not float64_rows,
+                                    columns=not float64_rows, **tuning):  # fmt: skip
             pts += b.stats["n_points"]
             big += b.stats.get("n_big", 0)
             rows += b.stats.get("n_rows", 0)
-            e2e_packed = bool(b.stats.get("packed", 0))
-        return pts, rows, big
+            was_packed = bool(b.stats.get("packed", 0))
+        return pts, rows, big, was_packed
 
     sampler = ClockSampler(local)
     sampler.start()  # nvidia-smi needs a moment to come up: started before the warm-up, read after the timed loops
@@ -366,9 +366,20 @@ def run_ours(args):
         flush_l2()
         barrier()
         t0 = time.perf_counter()
-        p_points, p_rows, p_big = stream_e2e(args.steps, 1000)
+        p_points, p_rows, p_big, e2e_packed = stream_e2e(args.steps, 1000)
         torch.cuda.synchronize()
         piped_s = time.perf_counter() - t0
+        barrier()
+    # ---- e2e in the reference's own return type: float64 [N, 3] + int64 [N] (or float64 [M, 8] Spyral rows) straight
+    # from the device, 32 (72 + 8) B/row over PCIe -- what a `SimulationWriter.write` consumer gets without any decode
+    f64_s, f64_steps = None, min(args.steps, 4)
+    if not args.no_e2e and not args.float64_rows and args.e2e_engines > 1:
+        stream_e2e(2, 2000, float64_rows=True, engines=2)  # (sizes the pinned float64 buffers)
+        barrier()
+        t0 = time.perf_counter()
+        stream_e2e(f64_steps, 3000, float64_rows=True, engines=2)
+        torch.cuda.synchronize()
+        f64_s = time.perf_counter() - t0
         barrier()
     clocks = sampler.stop()
     # e2e_decoded: the same call plus the decode of the wire format into the arrays `SimulationWriter.write` receives
@@ -388,6 +399,8 @@ def run_ours(args):
     dev_s = reduce_max(dist, dev_ms / 1e3, local)
     e2e_s = reduce_max(dist, e2e_s, local) if not args.no_e2e else float("nan")
     e2e_sync_s = e2e_s
+    if f64_s is not None:
+        f64_s = reduce_max(dist, f64_s, local)
     if piped_s is not None:  # the headline e2e is the pipelined call; its bytes are counted from its own batches
         e2e_s = reduce_max(dist, piped_s, local)
         e2e_points, e2e_rows, e2e_big = p_points, p_rows, p_big
@@ -504,6 +517,11 @@ def run_ours(args):
         "e2e_sync": None if args.no_e2e else {
             "value": round(total_events / e2e_sync_s, 1), "unit": "events/s",
             "what": "simulate_batch, one synchronous call per step, L2 flushed between steps"},
+        "e2e_float64": None if f64_s is None else {
+            "value": round(B * world * f64_steps / f64_s, 1), "unit": "events/s", "steps": f64_steps,
+            "what": ("the same pipelined call returning the reference's own arrays, no decode on the host: "
+                     + ("Spyral rows float64 [M, 8] + int64 labels, 80 B/row" if args.spyral else
+                        "cloud float64 [N, 3] + int64 labels, 32 B/row") + " over PCIe (two engines)")},
         "e2e_decoded": None if decoded_s is None else {
             "value": round(B / decoded_s, 1), "unit": "events/s per rank",
             "what": "one e2e step plus the host-side decode of the typed columns into the float64 / int64 arrays of the "

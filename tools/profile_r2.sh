@@ -9,6 +9,7 @@ tail -1 gpurun_out/${TAG}_plain.log | cut -c1-200
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
 for k in ${KERNELS:-deposit_kernel emit_kernel track_kernel point_order_kernel event_sort_kernel}; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_$k $CMD > gpurun_out/${TAG}_ncu_$k.log 2>&1
+  n=${k//[^a-z_]/}
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_$n $CMD > gpurun_out/${TAG}_ncu_$n.log 2>&1
   echo "$k rc=$?"
 done
