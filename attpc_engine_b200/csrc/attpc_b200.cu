@@ -140,6 +140,8 @@ struct AttpcSim {
     DevArray<HashEntry> hash;
     DevArray<uint64_t> sort_items;
     DevArray<uint4> staged;  // ordered rows of the chunk's events between order_kernel and emit_kernel
+    DevArray<unsigned> big_list;  // events queued for order_big_kernel: [chunk events] + {count, cursor}
+    int64_t big_list_events = 0;
     DevArray<unsigned> kept;
     DevArray<double> in_momenta, in_vertices;
 
@@ -266,6 +268,8 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks, int
     CU(sim->hash.reserve(table_groups * sim->group_events * sim->hash_cap));
     CU(sim->sort_items.reserve(table_groups * sim->group_events * scratch_stride(sim->hash_cap)));
     CU(sim->staged.reserve(table_groups * sim->group_events * sim->hash_cap));
+    sim->big_list_events = std::max<int64_t>(sim->big_list_events, table_groups * sim->group_events);
+    CU(sim->big_list.reserve(sim->big_list_events + 2));
     CU(sim->csr_total.reserve(3));  // cloud rows, electron counts >= 2^32, Spyral rows
     CU(sim->csr_host.reserve(3));
     CU(sim->chunk_totals.reserve(2 * (n_groups + 1)));
@@ -372,7 +376,11 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
     fa.scratch_stride = scratch_stride(sim->hash_cap);
     fa.staged = sim->staged.p;
     fa.csr_total = sim->csr_total.p;
+    fa.big_list = sim->big_list.p;
+    fa.big_count_list = sim->big_list.p + sim->big_list_events;
+    fa.big_cursor = fa.big_count_list + 1;
     CU(cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM_BYTES));
+    CU(cudaFuncSetAttribute(order_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_BIG_SMEM_BYTES));
     CU(cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEPOSIT_SMEM_BYTES));
     // Groups are processed in chunks: every kernel is launched once per chunk with one grid row per group, so the
     // ramp-up and tail of a launch are paid once per chunk.  When rows go to the host a chunk is what is copied while
@@ -401,10 +409,12 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         deposit_kernel<<<dim3((unsigned)sim->max_units, (unsigned)ng), DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES,
                          sim->stream>>>(sim->P, pb, gv, ctr);
         cudaEvent_t d1 = sim->mark();
+        CU(cudaMemsetAsync(fa.big_count_list, 0, 2 * sizeof(unsigned), sim->stream));
         order_kernel<<<(unsigned)gv.n_events, FIN_THREADS, FIN_SMEM_BYTES, sim->stream>>>(sim->P, fa, gv, ctr);
+        order_big_kernel<<<(unsigned)sim->sm_count, FIN_BIG_THREADS, FIN_BIG_SMEM_BYTES, sim->stream>>>(sim->P, fa, gv, ctr);
         offsets_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, ctr);
         emit_kernel<<<(unsigned)gv.n_events, EMIT_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
-        sim->launches += 6;
+        sim->launches += 7;
         if (spyral) {  // replayed uniforms have 53 bits: the Spyral passes read the float64 cloud instead (parity tests)
             int rc = launch_spyral(sim, spyral_args(sim, launch_first_event + gv.first_slot, gv.n_events, spyral->typed, false, ctr));
             if (rc) return rc;
@@ -1099,7 +1109,7 @@ void attpc_destroy(AttpcSim* sim) {
     if (sim->stream_c) cudaStreamDestroy(sim->stream_c);
     sim->lut.release(); sim->pad_xy.release(); sim->pad_scale.release(); sim->response.release();
     sim->resp_sorted.release(); sim->resp_prefix.release(); sim->tables.release(); sim->stop_ns.release(); sim->plan_cls.release(); sim->plan_counts.release(); sim->plan_order.release();
-    sim->hash.release(); sim->sort_items.release(); sim->staged.release();
+    sim->hash.release(); sim->sort_items.release(); sim->staged.release(); sim->big_list.release();
     sim->geom.release(); sim->rec.release();
     sim->unit_event.release(); sim->unit_first.release(); sim->unit_count.release(); sim->unit_order.release();
     sim->n_units.release();

@@ -1585,6 +1585,9 @@ struct FinalizeArgs {
                               //   x = time bucket << 16 | wiggle (16 bit);  y = electrons, low 32 bits;
                               //   z = electrons bits 32..47 | pad << 16 | above-ADC-threshold << 31;  w = track rank | z-order place << 4
     int64_t scratch_stride;   // 64-bit words of sort_items per event
+    unsigned* big_list;       // [chunk events] events queued for order_big_kernel; big_count_list, big_cursor: zeroed per chunk
+    unsigned* big_count_list;
+    unsigned* big_cursor;
     // Spyral rows of the same events (detector/writer.py:61-112, 232-238), thresholded and in z order: 0 = none,
     // 1 = typed columns (rcol_*), 2 = float64 rows
     uint32_t spyral, pad_;
@@ -1862,21 +1865,26 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
 constexpr int FIN_THREADS = ATTPC_FIN_THREADS;
 constexpr int FIN_ITEMS = ATTPC_FIN_ITEMS;
 constexpr size_t FIN_SMEM_BYTES = (size_t)(3 * FIN_ITEMS + 2 * (FIN_ITEMS / 32)) * sizeof(uint32_t);
+// second shared-memory tier: the events whose lists exceed FIN_ITEMS are queued by order_kernel and taken, one CTA per
+// SM with (nearly) all of its shared memory, by order_big_kernel
+constexpr int FIN_BIG_THREADS = 1024;
+constexpr int FIN_BIG_ITEMS = 16384;
+constexpr size_t FIN_BIG_SMEM_BYTES = (size_t)(3 * FIN_BIG_ITEMS + 2 * (FIN_BIG_ITEMS / 32)) * sizeof(uint32_t);
 constexpr unsigned long long SCAN_AGGREGATE = 1ULL << 62, SCAN_PREFIX = 2ULL << 62, SCAN_VALUE = (1ULL << 62) - 1ULL;
-static_assert(TB_BINS % FIN_THREADS == 0 && FIN_ITEMS % 32 == 0, "finalize tiling");
+static_assert(TB_BINS % FIN_THREADS == 0 && FIN_ITEMS % 32 == 0 && TB_BINS % FIN_BIG_THREADS == 0, "finalize tiling");
 
 struct FinShared {
     unsigned hist[TB_BINS + 1];  // bucket starts (sorted positions)
     unsigned fill[TB_BINS];      // fill cursors, then kept rows per bucket, then kept rows in the later buckets
-    unsigned warp[FIN_THREADS / 32];
-    unsigned keys;
+    unsigned warp[32];
+    unsigned keys, next;
 };
 
 // Exclusive scan, in place, of a[at(0)], a[at(1)], ..., a[at(TB_BINS - 1)]; every thread of the CTA calls it after a
 // barrier that completed `a`; returns the total; ends with a barrier.
-template <typename Map>
+template <int T, typename Map>
 __device__ __forceinline__ unsigned scan_bins(unsigned* a, Map at, unsigned* s_warp) {
-    constexpr int PER = TB_BINS / FIN_THREADS;
+    constexpr int PER = TB_BINS / T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned local[PER], sum = 0;
 #pragma unroll
@@ -1894,7 +1902,7 @@ __device__ __forceinline__ unsigned scan_bins(unsigned* a, Map at, unsigned* s_w
     __syncthreads();
     unsigned base = incl - sum, total = 0;
 #pragma unroll
-    for (int w = 0; w < FIN_THREADS / 32; ++w) {
+    for (int w = 0; w < T / 32; ++w) {
         const unsigned v = s_warp[w];
         if (w < warp) base += v;
         total += v;
@@ -1909,6 +1917,7 @@ __device__ __forceinline__ unsigned scan_bins(unsigned* a, Map at, unsigned* s_w
 }
 
 // Exclusive scan of one value per thread; returns the thread's prefix, `total` for everybody; two barriers.
+template <int T>
 __device__ __forceinline__ unsigned scan_threads(unsigned v, unsigned& total, unsigned* s_warp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned incl = v;
@@ -1923,7 +1932,7 @@ __device__ __forceinline__ unsigned scan_threads(unsigned v, unsigned& total, un
     unsigned base = incl - v;
     total = 0;
 #pragma unroll
-    for (int w = 0; w < FIN_THREADS / 32; ++w) {
+    for (int w = 0; w < T / 32; ++w) {
         const unsigned t = s_warp[w];
         if (w < warp) base += t;
         total += t;
@@ -1931,7 +1940,7 @@ __device__ __forceinline__ unsigned scan_threads(unsigned v, unsigned& total, un
     return base;
 }
 
-template <typename Item, bool SMEM>
+template <typename Item, bool SMEM, int T>
 __device__ __forceinline__ void order_event(const SimParams& P, const FinalizeArgs& fa, const GroupView& chunk,
                                                Counters* ctr, FinShared& sh, const int L, const int limit,
                                                const HashEntry* __restrict__ tab, Item* A, Item* B, uint32_t* C,
@@ -1955,16 +1964,16 @@ __device__ __forceinline__ void order_event(const SimParams& P, const FinalizeAr
 
     // 1: histogram over the time bucket
     unsigned occupied = 0;
-    for (int i0 = tid; i0 < limit; i0 += 4 * FIN_THREADS) {  // four loads in flight per thread
+    for (int i0 = tid; i0 < limit; i0 += 4 * T) {  // four loads in flight per thread
         unsigned k[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * FIN_THREADS;
+            const int i = i0 + u * T;
             k[u] = i < limit ? tab[i].key1 : 0u;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * FIN_THREADS;
+            const int i = i0 + u * T;
             if (i >= limit) break;
             unsigned key1 = k[u];
             if (key1) {
@@ -1978,15 +1987,15 @@ __device__ __forceinline__ void order_event(const SimParams& P, const FinalizeAr
     if (occupied) atomicAdd(&sh.keys, occupied);
     __syncthreads();
     // 2: bucket starts
-    const int n = (int)scan_bins(sh.hist, [](int b) { return b; }, sh.warp);
-    for (int b = tid; b < TB_BINS; b += FIN_THREADS) sh.fill[b] = sh.hist[b];
+    const int n = (int)scan_bins<T>(sh.hist, [](int b) { return b; }, sh.warp);
+    for (int b = tid; b < TB_BINS; b += T) sh.fill[b] = sh.hist[b];
     if (tid == 0) {
         sh.hist[TB_BINS] = (unsigned)n;
         if (sh.keys) atomicAdd(&ctr->keys, (unsigned long long)sh.keys);
     }
     __syncthreads();
     // 3: entries into their buckets
-    for (int i = tid; i < limit; i += FIN_THREADS) {
+    for (int i = tid; i < limit; i += T) {
         unsigned key1 = SMEM ? C[i] : tab[i].key1;
         if (!SMEM && key1) key1 = masked(key1);
         if (key1) A[atomicAdd(&sh.fill[bin_of(key1)], 1u)] = ((Item)((key1 - 1u) & 0x7FFFu) << SH) | (Item)(unsigned)i;
@@ -1994,7 +2003,7 @@ __device__ __forceinline__ void order_event(const SimParams& P, const FinalizeAr
     __syncthreads();
     // 4: order every bucket: one thread per item counts the smaller items of its bucket (a bucket holds the pads hit in
     // one time bucket, a handful for most tracks; neighbouring threads walk the same items, the reads are broadcasts)
-    for (int i = tid; i < n; i += FIN_THREADS) {
+    for (int i = tid; i < n; i += T) {
         const Item v = A[i];
         const unsigned kv = key_of((unsigned)(v & IDX_MASK));
         const unsigned bin = bin_of(kv);
@@ -2012,12 +2021,12 @@ __device__ __forceinline__ void order_event(const SimParams& P, const FinalizeAr
         }
         B[lo + rank] = v;
     }
-    for (int b = tid; b < TB_BINS; b += FIN_THREADS) sh.fill[b] = 0u;  // (kept rows per bucket, step 7)
+    for (int b = tid; b < TB_BINS; b += T) sh.fill[b] = 0u;  // (kept rows per bucket, step 7)
     __syncthreads();
     // 5: rows = first copies
     int n_rows = n;
     if (dup) {
-        for (int p = tid; p - lane < n; p += FIN_THREADS) {  // (warp-uniform trip count)
+        for (int p = tid; p - lane < n; p += T) {  // (warp-uniform trip count)
             bool head = false;
             if (p < n) head = p == 0 || key_of((unsigned)(B[p] & IDX_MASK)) != key_of((unsigned)(B[p - 1] & IDX_MASK));
             const unsigned m = __ballot_sync(FULL, head);
@@ -2026,10 +2035,10 @@ __device__ __forceinline__ void order_event(const SimParams& P, const FinalizeAr
         __syncthreads();
         const int n_words = (n + 31) >> 5;
         unsigned done = 0;
-        for (int w0 = 0; w0 < n_words; w0 += FIN_THREADS) {
+        for (int w0 = 0; w0 < n_words; w0 += T) {
             const int w = w0 + tid;
             unsigned total;
-            const unsigned before = scan_threads(w < n_words ? (unsigned)__popc(H[w]) : 0u, total, sh.warp);
+            const unsigned before = scan_threads<T>(w < n_words ? (unsigned)__popc(H[w]) : 0u, total, sh.warp);
             if (w < n_words) HP[w] = done + before;
             done += total;
         }
@@ -2044,7 +2053,7 @@ __device__ __forceinline__ void order_event(const SimParams& P, const FinalizeAr
     uint4* staged = fa.staged + (int64_t)L * chunk.hash_cap;
     const bool spy = fa.spyral != 0u;
     const bool draw = fa.replay.offsets == nullptr;  // (replayed uniforms have 53 bits: emit_kernel looks them up)
-    for (int p = tid; p < n; p += FIN_THREADS) {
+    for (int p = tid; p < n; p += T) {
         Item w_out = 0;
         if (is_row(p)) {
             const uint4 en = __ldg(reinterpret_cast<const uint4*>(tab + (unsigned)(B[p] & IDX_MASK)));
@@ -2076,9 +2085,9 @@ __device__ __forceinline__ void order_event(const SimParams& P, const FinalizeAr
     // 7: place of every kept row in z order.  z falls as the time bucket rises (detector/writer.py:101-103, 236):
     //   (kept rows of the later buckets) + (kept rows of its bucket with a larger wiggle, or the same and a lower position)
     __syncthreads();
-    const unsigned n_kept = scan_bins(sh.fill, [](int b) { return TB_BINS - 1 - b; }, sh.warp);
+    const unsigned n_kept = scan_bins<T>(sh.fill, [](int b) { return TB_BINS - 1 - b; }, sh.warp);
     if (tid == 0) fa.row_kept[slot_event] = n_kept;
-    for (int p = tid; p < n; p += FIN_THREADS) {
+    for (int p = tid; p < n; p += T) {
         const unsigned w = (unsigned)A[p];
         if (!((w >> 16) & 1u)) continue;  // below the ADC threshold, or not a row
         const unsigned bin = (w >> 17) & 0x3FFu, wp = w & 0x1FFFFu;
@@ -2095,31 +2104,64 @@ __device__ __forceinline__ void order_event(const SimParams& P, const FinalizeAr
 }
 
 // Kernel A of finalize: order the entry list of every event of the chunk (one CTA per event, no event waits for
-// another) and stage its rows.
+// another) and stage its rows.  Lists that do not fit this kernel's shared memory are queued for order_big_kernel
+// (or, beyond that kernel's capacity too, ordered here in global scratch).
 __global__ void __launch_bounds__(FIN_THREADS, ATTPC_FIN_MIN_CTAS)
 order_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa,
              const __grid_constant__ GroupView chunk, Counters* ctr) {
     extern __shared__ __align__(16) uint32_t s_fin[];
     __shared__ FinShared sh;
     const int tid = threadIdx.x;
-    if (tid == 0) sh.keys = 0;
-    for (int b = tid; b <= TB_BINS; b += FIN_THREADS) sh.hist[b] = 0;
-    __syncthreads();
     const int L = (int)blockIdx.x;
     const int slot_event = chunk.first_slot + L;
     // an attempt that overflowed a buffer is void (the host redoes the launch)
     const bool void_attempt = (ctr->overflow_points | ctr->overflow_hash) != 0;
     const int limit = void_attempt ? 0 : (int)min(chunk.n_entries[slot_event], (unsigned)chunk.hash_cap);
+    const bool narrow = chunk.hash_cap <= (1 << 17);  // list indices fit the 32-bit items
+    if (limit > FIN_ITEMS && limit <= FIN_BIG_ITEMS && narrow) {
+        if (tid == 0) fa.big_list[atomicAdd(fa.big_count_list, 1u)] = (unsigned)L;
+        return;
+    }
+    if (tid == 0) sh.keys = 0;
+    for (int b = tid; b <= TB_BINS; b += FIN_THREADS) sh.hist[b] = 0;
+    __syncthreads();
     const HashEntry* tab = chunk.tables + (int64_t)L * chunk.hash_cap;
-    if (limit <= FIN_ITEMS && chunk.hash_cap <= (1 << 17)) {
+    if (limit <= FIN_ITEMS && narrow) {
         uint32_t* H = s_fin + 3 * FIN_ITEMS;
-        order_event<uint32_t, true>(P, fa, chunk, ctr, sh, L, limit, tab, s_fin, s_fin + FIN_ITEMS,
-                                    s_fin + 2 * FIN_ITEMS, H, H + FIN_ITEMS / 32);
+        order_event<uint32_t, true, FIN_THREADS>(P, fa, chunk, ctr, sh, L, limit, tab, s_fin, s_fin + FIN_ITEMS,
+                                                 s_fin + 2 * FIN_ITEMS, H, H + FIN_ITEMS / 32);
     } else {
         uint64_t* scratch = fa.sort_items + (int64_t)L * fa.scratch_stride;
         unsigned* H = reinterpret_cast<unsigned*>(scratch + 2 * (int64_t)chunk.hash_cap);
-        order_event<uint64_t, false>(P, fa, chunk, ctr, sh, L, limit, tab, scratch, scratch + chunk.hash_cap, nullptr,
-                                     H, H + chunk.hash_cap / 32 + 1);
+        order_event<uint64_t, false, FIN_THREADS>(P, fa, chunk, ctr, sh, L, limit, tab, scratch, scratch + chunk.hash_cap,
+                                                  nullptr, H, H + chunk.hash_cap / 32 + 1);
+    }
+}
+
+// The queued long lists (dense events): persistent CTAs, one per SM, 1024 threads, 197 KB of shared memory each.
+__global__ void __launch_bounds__(FIN_BIG_THREADS, 1)
+order_big_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa,
+                 const __grid_constant__ GroupView chunk, Counters* ctr) {
+    extern __shared__ __align__(16) uint32_t s_fin[];
+    __shared__ FinShared sh;
+    const int tid = threadIdx.x;
+    const unsigned n_queued = *fa.big_count_list;
+    for (;;) {
+        __syncthreads();  // (the previous event is done with the shared memory)
+        if (tid == 0) {
+            sh.next = atomicAdd(fa.big_cursor, 1u);
+            sh.keys = 0;
+        }
+        for (int b = tid; b <= TB_BINS; b += FIN_BIG_THREADS) sh.hist[b] = 0;
+        __syncthreads();
+        if (sh.next >= n_queued) return;
+        const int L = (int)fa.big_list[sh.next];
+        const int slot_event = chunk.first_slot + L;
+        const int limit = (int)min(chunk.n_entries[slot_event], (unsigned)chunk.hash_cap);
+        const HashEntry* tab = chunk.tables + (int64_t)L * chunk.hash_cap;
+        uint32_t* H = s_fin + 3 * FIN_BIG_ITEMS;
+        order_event<uint32_t, true, FIN_BIG_THREADS>(P, fa, chunk, ctr, sh, L, limit, tab, s_fin, s_fin + FIN_BIG_ITEMS,
+                                                     s_fin + 2 * FIN_BIG_ITEMS, H, H + FIN_BIG_ITEMS / 32);
     }
 }
 
