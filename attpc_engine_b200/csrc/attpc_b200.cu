@@ -376,7 +376,12 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
     fa.scratch_stride = scratch_stride(sim->hash_cap);
     fa.staged = sim->staged.p;
     fa.csr_total = sim->csr_total.p;
-    fa.big_list = sim->big_list.p;
+    // order_big_kernel takes whole SMs (197 KB of shared memory per CTA).  Alone on the GPU that pays (device-resident
+    // calls); beside the kernels of other engines and chunks (calls that copy to the host, pipelined) its CTAs wait for
+    // SMs to drain and stall the others: measured 2.25 -> 1.69 M events/s end to end.  Such calls keep long lists in the
+    // global-memory tier of order_kernel.
+    const bool use_big = fences == nullptr;
+    fa.big_list = use_big ? sim->big_list.p : nullptr;
     fa.big_count_list = sim->big_list.p + sim->big_list_events;
     fa.big_cursor = fa.big_count_list + 1;
     CU(cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM_BYTES));
@@ -411,10 +416,11 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         cudaEvent_t d1 = sim->mark();
         CU(cudaMemsetAsync(fa.big_count_list, 0, 2 * sizeof(unsigned), sim->stream));
         order_kernel<<<(unsigned)gv.n_events, FIN_THREADS, FIN_SMEM_BYTES, sim->stream>>>(sim->P, fa, gv, ctr);
-        order_big_kernel<<<(unsigned)sim->sm_count, FIN_BIG_THREADS, FIN_BIG_SMEM_BYTES, sim->stream>>>(sim->P, fa, gv, ctr);
+        if (use_big)
+            order_big_kernel<<<(unsigned)sim->sm_count, FIN_BIG_THREADS, FIN_BIG_SMEM_BYTES, sim->stream>>>(sim->P, fa, gv, ctr);
         offsets_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, ctr);
         emit_kernel<<<(unsigned)gv.n_events, EMIT_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
-        sim->launches += 7;
+        sim->launches += use_big ? 7 : 6;
         if (spyral) {  // replayed uniforms have 53 bits: the Spyral passes read the float64 cloud instead (parity tests)
             int rc = launch_spyral(sim, spyral_args(sim, launch_first_event + gv.first_slot, gv.n_events, spyral->typed, false, ctr));
             if (rc) return rc;

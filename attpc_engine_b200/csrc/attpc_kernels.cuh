@@ -1585,7 +1585,7 @@ struct FinalizeArgs {
                               //   x = time bucket << 16 | wiggle (16 bit);  y = electrons, low 32 bits;
                               //   z = electrons bits 32..47 | pad << 16 | above-ADC-threshold << 31;  w = track rank | z-order place << 4
     int64_t scratch_stride;   // 64-bit words of sort_items per event
-    unsigned* big_list;       // [chunk events] events queued for order_big_kernel; big_count_list, big_cursor: zeroed per chunk
+    unsigned* big_list;       // [chunk events] events queued for order_big_kernel (null: none are); big_count_list, big_cursor: zeroed per chunk
     unsigned* big_count_list;
     unsigned* big_cursor;
     // Spyral rows of the same events (detector/writer.py:61-112, 232-238), thresholded and in z order: 0 = none,
@@ -1847,9 +1847,9 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
 // ---------------------------------------------------------------------------------------------------- finalize
 // detector/simulator.py:19-49 (dict_to_points), :104-115 (time-bucket wiggle and mask) and, when asked for,
 // detector/response.py:35-57 + detector/writer.py:232-238 (amplitude, ADC threshold, z order) on the entry lists that
-// deposit_kernel left, in three launches per chunk of events:
+// deposit_kernel left, in four launches per chunk of events:
 //
-// order_kernel, one CTA per event, no event waits for another:
+// order_kernel / order_big_kernel, one CTA per event at a time, no event waits for another:
 //   1  histogram of the entries over the integer time bucket (mask applied), keys staged in shared memory
 //   2  exclusive scan -> bucket starts;  3  entries into their buckets (items = pad | list index)
 //   4  rank by counting inside each bucket -> canonical order, ascending (time bucket, pad); copies of a key that sit
@@ -1860,8 +1860,10 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
 //      wiggle -> place of every kept row in z order, stored with the staged row
 // offsets_kernel: running CSR offsets from the row counts.   emit_kernel: streams the staged rows to the sinks.
 //
-// Everything an event needs stays in shared memory when its list has at most FIN_ITEMS entries; longer lists (dense
-// events) run the same code on a scratch region in global memory with 64-bit items.
+// Everything an event needs stays in shared memory: lists of up to FIN_ITEMS entries in order_kernel (two CTAs per SM),
+// longer ones, up to FIN_BIG_ITEMS, in order_big_kernel (queued by order_kernel; persistent CTAs, one per SM); beyond that
+// (or with more than 2^17 entries per list allowed) the same code runs on a scratch region in global memory with
+// 64-bit items.
 constexpr int FIN_THREADS = ATTPC_FIN_THREADS;
 constexpr int FIN_ITEMS = ATTPC_FIN_ITEMS;
 constexpr size_t FIN_SMEM_BYTES = (size_t)(3 * FIN_ITEMS + 2 * (FIN_ITEMS / 32)) * sizeof(uint32_t);
@@ -2118,7 +2120,7 @@ order_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finali
     const bool void_attempt = (ctr->overflow_points | ctr->overflow_hash) != 0;
     const int limit = void_attempt ? 0 : (int)min(chunk.n_entries[slot_event], (unsigned)chunk.hash_cap);
     const bool narrow = chunk.hash_cap <= (1 << 17);  // list indices fit the 32-bit items
-    if (limit > FIN_ITEMS && limit <= FIN_BIG_ITEMS && narrow) {
+    if (fa.big_list && limit > FIN_ITEMS && limit <= FIN_BIG_ITEMS && narrow) {
         if (tid == 0) fa.big_list[atomicAdd(fa.big_count_list, 1u)] = (unsigned)L;
         return;
     }
