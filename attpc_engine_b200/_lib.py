@@ -177,6 +177,7 @@ SIGNATURES = {
         [C.c_void_p, _P_I64, _P_D, _P_I64, C.c_int64, C.c_uint32, C.POINTER(AttpcResult)],
     ),
     "attpc_lookup_pads": (C.c_int, [C.c_void_p, _P_D, C.c_int64, _P_I32]),
+    "attpc_read_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
 }
 
 _lib = None

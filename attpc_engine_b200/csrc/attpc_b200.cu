@@ -1582,6 +1582,16 @@ int attpc_convert_to_spyral(AttpcSim* sim, const int64_t* offsets, const double*
     return rc;
 }
 
+int attpc_read_device(AttpcSim* sim, const void* dev, void* host, int64_t n_bytes) {
+    if (!sim) return ATTPC_E_BADARG;
+    if (n_bytes < 0 || (n_bytes > 0 && (!dev || !host))) return sim->fail(ATTPC_E_BADARG, "attpc_read_device: bad arguments");
+    if (n_bytes == 0) return ATTPC_OK;
+    CU(cudaSetDevice(sim->device));
+    CU(cudaStreamSynchronize(sim->stream));
+    CU(cudaMemcpy(host, dev, (size_t)n_bytes, cudaMemcpyDeviceToHost));
+    return ATTPC_OK;
+}
+
 int attpc_lookup_pads(AttpcSim* sim, const double* xy, int64_t n, int32_t* pads_out) {
     if (!sim) return ATTPC_E_BADARG;
     if (n < 0 || (n > 0 && (!xy || !pads_out))) return sim->fail(ATTPC_E_BADARG, "attpc_lookup_pads: bad arguments");

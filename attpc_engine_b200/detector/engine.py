@@ -92,6 +92,7 @@ class SimBatch:
         #: packed wire form of the same columns: dict(pad_rank uint16, wiggle uint16, tb_counts uint16 [B, 512],
         #: labels_of_rank int8 [4], rank_shift, and the electron columns) or None
         self.packed = packed
+        self.device = None  # device pointers of a call made with host_copy=False (`Engine.read_device_result`)
         #: Spyral rows (after ADC threshold, z-sorted) as typed columns: dict(pad int16, tb_q16 uint32, e_lo uint32,
         #: e_hi uint16, label8 int8) -- 13 B/row over PCIe instead of 72; ``rows`` / ``row_labels`` / ``event_rows`` rebuild
         #: the float64 arrays from them on demand, bit for bit (`Engine.rows_from_columns`)
@@ -358,9 +359,11 @@ class Engine:
     def _collect(self, res: _lib.AttpcResult, first_event: int, copy: bool, rows: bool, track_labels=()) -> SimBatch:
         n_ev, n_pts = int(res.n_events), int(res.n_points)
         stats = {k: getattr(res, k) for k in _STAT_FIELDS}
-        if not res.offsets:  # SKIP_HOST_COPY
-            return SimBatch(first_event, np.zeros(n_ev + 1, np.int64), np.zeros((0, 3)), np.zeros(0, np.int64),
-                            stats=dict(stats, n_points=n_pts))  # fmt: skip
+        if not res.offsets:  # SKIP_HOST_COPY: the rows stay on the device (`read_device_result` fetches them)
+            out = SimBatch(first_event, np.zeros(n_ev + 1, np.int64), np.zeros((0, 3)), np.zeros(0, np.int64),
+                           stats=dict(stats, n_points=n_pts))  # fmt: skip
+            out.device = dict(offsets=res.offsets_dev, cloud=res.cloud_dev, labels=res.labels_dev, n_events=n_ev, n_points=n_pts)
+            return out
         grab = (lambda a: a.copy()) if copy else (lambda a: a)
         offsets = grab(np.ctypeslib.as_array(res.offsets, shape=(n_ev + 1,)))
         columns = packed = None
@@ -418,6 +421,19 @@ class Engine:
                 out.rows, out.row_labels = np.zeros((0, 8)), np.zeros(0, np.int64)
             out.stats["n_rows"] = n_rows
         return out
+
+    def read_device_result(self, batch: SimBatch) -> SimBatch:
+        """The rows of a device-resident call (`host_copy=False`), copied to fresh host arrays.  Valid until the next
+        call on this engine reuses the device buffers."""
+        dev = batch.device
+        n_ev, n_pts = dev["n_events"], dev["n_points"]
+        offsets = np.empty(n_ev + 1, dtype=np.int64)
+        cloud = np.empty((n_pts, 3), dtype=np.float64)
+        labels = np.empty(n_pts, dtype=np.int64)
+        for arr, ptr in ((offsets, dev["offsets"]), (cloud, dev["cloud"]), (labels, dev["labels"])):
+            if arr.nbytes:
+                _lib.check(self.lib.attpc_read_device(self.handle, ptr, arr.ctypes.data_as(C.c_void_p), arr.nbytes), self.handle)
+        return SimBatch(batch.first_event, offsets, cloud, labels, stats=dict(batch.stats))
 
     def rows_from_columns(self, cols: dict) -> tuple[np.ndarray, np.ndarray]:
         """The eight Spyral columns (`writer.py:61-112`) from the typed columns of ``ATTPC_SPYRAL_COLUMNS``.

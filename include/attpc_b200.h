@@ -253,6 +253,10 @@ int attpc_convert_to_spyral(AttpcSim* sim, const int64_t* offsets, const double*
 /* Pad lookup of detector/transporter.py:78-120 + the veto of :165,237 for n positions (metres). */
 int attpc_lookup_pads(AttpcSim* sim, const double* xy, int64_t n, int32_t* pads_out);
 
+/* Copy n_bytes from one of the *_dev arrays of the handle's last result into host memory (results of a call made with
+ * ATTPC_SKIP_HOST_COPY stay on the device; this is how a caller without a CUDA binding of its own reads them). */
+int attpc_read_device(AttpcSim* sim, const void* dev, void* host, int64_t n_bytes);
+
 #ifdef __cplusplus
 }
 #endif

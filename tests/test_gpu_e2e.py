@@ -430,3 +430,26 @@ def test_mesh_weight_table_equals_reference_expression(name, n_events):
     assert fast.stats["n_deposits"] == exact.stats["n_deposits"] > 0
     assert np.array_equal(fast.offsets, exact.offsets) and np.array_equal(fast.labels, exact.labels)
     assert np.array_equal(fast.cloud, exact.cloud)
+
+
+@pytest.mark.parametrize("name", ["c16dd", "c12aa"])
+def test_device_resident_call_holds_the_same_rows(name):
+    """`host_copy=False` (what `bench.py` times as `value`) takes other code paths than a call that copies to the host:
+    all groups of a launch in one chunk, long entry lists through `order_big_kernel` (15 % of the 16C(d,d') events,
+    nearly all of 12C(a,a')3a), float64 rows written on the device.  Its rows, read back from the device, equal the
+    rows of the copying call."""
+    import bench
+    from attpc_engine_b200 import nuclear_map
+    from attpc_engine_b200.detector.engine import engine_for
+    from attpc_engine_b200.detector.simulator import _nuclei_for
+
+    n = 6000 if name == "c16dd" else 1500
+    cfg, momenta, vertices, zs, as_, indices = bench.build_workload(name, n, seed_offset=5)
+    eng = engine_for(cfg, _nuclei_for(zs, as_, indices, nuclear_map))
+    host = eng.simulate_batch(momenta, vertices, zs, as_, indices, seed=11, first_event=70000)
+    there = eng.simulate_batch(momenta, vertices, zs, as_, indices, seed=11, first_event=70000, host_copy=False)
+    assert there.device is not None and there.stats["n_points"] == host.stats["n_points"] > 0
+    back = eng.read_device_result(there)
+    assert np.array_equal(back.offsets, host.offsets)
+    assert np.array_equal(back.cloud, host.cloud) and np.array_equal(back.labels, host.labels)
+    assert (np.diff(host.offsets) > 5120).any()  # some lists were long enough for the second tier
