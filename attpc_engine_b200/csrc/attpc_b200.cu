@@ -140,7 +140,7 @@ struct AttpcSim {
     DevArray<HashEntry> hash;
     DevArray<uint64_t> sort_items;
     DevArray<uint4> staged;  // ordered rows of the chunk's events between order_kernel and emit_kernel
-    DevArray<unsigned> big_list;  // events queued for order_big_kernel: [chunk events] + {count, cursor}
+    DevArray<unsigned> big_list;  // events queued for order_queue_kernel: two lists of [chunk events] + 2 x {count, cursor}
     int64_t big_list_events = 0;
     DevArray<unsigned> kept;
     DevArray<double> in_momenta, in_vertices;
@@ -269,7 +269,7 @@ int ensure_work_buffers(AttpcSim* sim, int64_t launch_events, int32_t ranks, int
     CU(sim->sort_items.reserve(table_groups * sim->group_events * scratch_stride(sim->hash_cap)));
     CU(sim->staged.reserve(table_groups * sim->group_events * sim->hash_cap));
     sim->big_list_events = std::max<int64_t>(sim->big_list_events, table_groups * sim->group_events);
-    CU(sim->big_list.reserve(sim->big_list_events + 2));
+    CU(sim->big_list.reserve(2 * sim->big_list_events + 4));
     CU(sim->csr_total.reserve(3));  // cloud rows, electron counts >= 2^32, Spyral rows
     CU(sim->csr_host.reserve(3));
     CU(sim->chunk_totals.reserve(2 * (n_groups + 1)));
@@ -376,16 +376,20 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
     fa.scratch_stride = scratch_stride(sim->hash_cap);
     fa.staged = sim->staged.p;
     fa.csr_total = sim->csr_total.p;
-    // order_big_kernel takes whole SMs (197 KB of shared memory per CTA).  Alone on the GPU that pays (device-resident
-    // calls); beside the kernels of other engines and chunks (calls that copy to the host, pipelined) its CTAs wait for
-    // SMs to drain and stall the others: measured 2.25 -> 1.69 M events/s end to end.  Such calls keep long lists in the
-    // global-memory tier of order_kernel.
+    // The second tier is persistent CTAs with 197 KB of shared memory.  Alone on the GPU they pay (device-resident
+    // calls).  Beside the kernels of other engines and chunks (calls that copy to the host, pipelined) every one of
+    // them, even with an empty queue, waits for an SM whose deposit CTAs have drained and holds up the stream behind
+    // it: measured 2.25 -> 1.69 M events/s end to end (a two-per-SM, 98 KB variant: 2.25 -> 2.10 M, 0.54 -> 0.44 M
+    // for 12C(a,a')3a).  Such calls order the lists beyond order_kernel's 8192 entries in global scratch (the third tier:
+    // persistent CTAs again, but without dynamic shared memory - they fit beside anything and keep the whole L1).
     const bool use_big = fences == nullptr;
-    fa.big_list = use_big ? sim->big_list.p : nullptr;
-    fa.big_count_list = sim->big_list.p + sim->big_list_events;
-    fa.big_cursor = fa.big_count_list + 1;
+    unsigned* qbase = sim->big_list.p + 2 * sim->big_list_events;  // {big count, big cursor, far count, far cursor}
+    fa.big = {use_big ? sim->big_list.p : nullptr, qbase, qbase + 1};
+    fa.far = {sim->big_list.p + sim->big_list_events, qbase + 2, qbase + 3};
+    auto big_kernel = order_queue_kernel<FIN_BIG_THREADS, FIN_BIG_ITEMS, 1>;
+    auto far_kernel = order_queue_kernel<FIN_THREADS, 0, 2>;
+    CU(cudaFuncSetAttribute(big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_BIG_SMEM_BYTES));
     CU(cudaFuncSetAttribute(order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_SMEM_BYTES));
-    CU(cudaFuncSetAttribute(order_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FIN_BIG_SMEM_BYTES));
     CU(cudaFuncSetAttribute(deposit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DEPOSIT_SMEM_BYTES));
     // Groups are processed in chunks: every kernel is launched once per chunk with one grid row per group, so the
     // ramp-up and tail of a launch are paid once per chunk.  When rows go to the host a chunk is what is copied while
@@ -414,13 +418,14 @@ int run_groups(AttpcSim* sim, int64_t launch_events, FinalizeArgs fa, int which,
         deposit_kernel<<<dim3((unsigned)sim->max_units, (unsigned)ng), DEPOSIT_THREADS, DEPOSIT_SMEM_BYTES,
                          sim->stream>>>(sim->P, pb, gv, ctr);
         cudaEvent_t d1 = sim->mark();
-        CU(cudaMemsetAsync(fa.big_count_list, 0, 2 * sizeof(unsigned), sim->stream));
+        CU(cudaMemsetAsync(qbase, 0, 4 * sizeof(unsigned), sim->stream));
         order_kernel<<<(unsigned)gv.n_events, FIN_THREADS, FIN_SMEM_BYTES, sim->stream>>>(sim->P, fa, gv, ctr);
+        far_kernel<<<(unsigned)(2 * sim->sm_count), FIN_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr, fa.far);
         if (use_big)
-            order_big_kernel<<<(unsigned)sim->sm_count, FIN_BIG_THREADS, FIN_BIG_SMEM_BYTES, sim->stream>>>(sim->P, fa, gv, ctr);
+            big_kernel<<<(unsigned)sim->sm_count, FIN_BIG_THREADS, FIN_BIG_SMEM_BYTES, sim->stream>>>(sim->P, fa, gv, ctr, fa.big);
         offsets_kernel<<<1, 1024, 0, sim->stream>>>(fa, gv, ctr);
         emit_kernel<<<(unsigned)gv.n_events, EMIT_THREADS, 0, sim->stream>>>(sim->P, fa, gv, ctr);
-        sim->launches += use_big ? 7 : 6;
+        sim->launches += use_big ? 8 : 7;
         if (spyral) {  // replayed uniforms have 53 bits: the Spyral passes read the float64 cloud instead (parity tests)
             int rc = launch_spyral(sim, spyral_args(sim, launch_first_event + gv.first_slot, gv.n_events, spyral->typed, false, ctr));
             if (rc) return rc;

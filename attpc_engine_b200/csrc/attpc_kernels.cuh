@@ -31,7 +31,7 @@
 #define ATTPC_FIN_MIN_CTAS 2   // CTAs per SM the register allocation of order_kernel aims at
 #endif
 #ifndef ATTPC_FIN_ITEMS
-#define ATTPC_FIN_ITEMS 5120   // longest entry list ordered in shared memory (12 B per entry)
+#define ATTPC_FIN_ITEMS 8192   // longest entry list order_kernel orders in shared memory (12 B per entry; two CTAs per SM)
 #endif
 
 namespace attpc {
@@ -1585,9 +1585,13 @@ struct FinalizeArgs {
                               //   x = time bucket << 16 | wiggle (16 bit);  y = electrons, low 32 bits;
                               //   z = electrons bits 32..47 | pad << 16 | above-ADC-threshold << 31;  w = track rank | z-order place << 4
     int64_t scratch_stride;   // 64-bit words of sort_items per event
-    unsigned* big_list;       // [chunk events] events queued for order_big_kernel (null: none are); big_count_list, big_cursor: zeroed per chunk
-    unsigned* big_count_list;
-    unsigned* big_cursor;
+    // events queued by order_kernel for the kernels with more shared memory per event (list == null: tier not in use);
+    // count and cursor are zeroed per chunk
+    struct Queue {
+        unsigned* list;   // [chunk events]
+        unsigned* count;
+        unsigned* cursor;
+    } big, far;  // big: second shared-memory tier; far: lists ordered in global scratch
     // Spyral rows of the same events (detector/writer.py:61-112, 232-238), thresholded and in z order: 0 = none,
     // 1 = typed columns (rcol_*), 2 = float64 rows
     uint32_t spyral, pad_;
@@ -1849,7 +1853,7 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
 // detector/response.py:35-57 + detector/writer.py:232-238 (amplitude, ADC threshold, z order) on the entry lists that
 // deposit_kernel left, in four launches per chunk of events:
 //
-// order_kernel / order_big_kernel, one CTA per event at a time, no event waits for another:
+// order_kernel / order_queue_kernel, one CTA per event at a time, no event waits for another:
 //   1  histogram of the entries over the integer time bucket (mask applied), keys staged in shared memory
 //   2  exclusive scan -> bucket starts;  3  entries into their buckets (items = pad | list index)
 //   4  rank by counting inside each bucket -> canonical order, ascending (time bucket, pad); copies of a key that sit
@@ -1861,14 +1865,15 @@ spyral_rows_kernel(const __grid_constant__ SimParams P, SpyralArgs sa) {
 // offsets_kernel: running CSR offsets from the row counts.   emit_kernel: streams the staged rows to the sinks.
 //
 // Everything an event needs stays in shared memory: lists of up to FIN_ITEMS entries in order_kernel (two CTAs per SM),
-// longer ones, up to FIN_BIG_ITEMS, in order_big_kernel (queued by order_kernel; persistent CTAs, one per SM); beyond that
+// longer ones, up to FIN_BIG_ITEMS, in order_queue_kernel (queued by order_kernel; persistent CTAs, one per SM);
+// beyond that
 // (or with more than 2^17 entries per list allowed) the same code runs on a scratch region in global memory with
 // 64-bit items.
 constexpr int FIN_THREADS = ATTPC_FIN_THREADS;
 constexpr int FIN_ITEMS = ATTPC_FIN_ITEMS;
 constexpr size_t FIN_SMEM_BYTES = (size_t)(3 * FIN_ITEMS + 2 * (FIN_ITEMS / 32)) * sizeof(uint32_t);
-// second shared-memory tier: the events whose lists exceed FIN_ITEMS are queued by order_kernel and taken, one CTA per
-// SM with (nearly) all of its shared memory, by order_big_kernel
+// second shared-memory tier: the events whose lists exceed FIN_ITEMS are queued by order_kernel and taken by persistent
+// CTAs of order_queue_kernel, one per SM with (nearly) all of its shared memory, up to 16384 entries
 constexpr int FIN_BIG_THREADS = 1024;
 constexpr int FIN_BIG_ITEMS = 16384;
 constexpr size_t FIN_BIG_SMEM_BYTES = (size_t)(3 * FIN_BIG_ITEMS + 2 * (FIN_BIG_ITEMS / 32)) * sizeof(uint32_t);
@@ -2106,8 +2111,8 @@ __device__ __forceinline__ void order_event(const SimParams& P, const FinalizeAr
 }
 
 // Kernel A of finalize: order the entry list of every event of the chunk (one CTA per event, no event waits for
-// another) and stage its rows.  Lists that do not fit this kernel's shared memory are queued for order_big_kernel
-// (or, beyond that kernel's capacity too, ordered here in global scratch).
+// another) and stage its rows.  Lists that do not fit this kernel's shared memory are queued for order_queue_kernel:
+// for its second shared-memory tier when the call uses it and the list fits, for its global-scratch tier otherwise.
 __global__ void __launch_bounds__(FIN_THREADS, ATTPC_FIN_MIN_CTAS)
 order_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa,
              const __grid_constant__ GroupView chunk, Counters* ctr) {
@@ -2120,50 +2125,52 @@ order_kernel(const __grid_constant__ SimParams P, const __grid_constant__ Finali
     const bool void_attempt = (ctr->overflow_points | ctr->overflow_hash) != 0;
     const int limit = void_attempt ? 0 : (int)min(chunk.n_entries[slot_event], (unsigned)chunk.hash_cap);
     const bool narrow = chunk.hash_cap <= (1 << 17);  // list indices fit the 32-bit items
-    if (fa.big_list && limit > FIN_ITEMS && limit <= FIN_BIG_ITEMS && narrow) {
-        if (tid == 0) fa.big_list[atomicAdd(fa.big_count_list, 1u)] = (unsigned)L;
+    if (limit > FIN_ITEMS || !narrow) {  // not for this kernel's shared memory: queue the event
+        const FinalizeArgs::Queue& q = narrow && fa.big.list && limit <= FIN_BIG_ITEMS ? fa.big : fa.far;
+        if (tid == 0) q.list[atomicAdd(q.count, 1u)] = (unsigned)L;
         return;
     }
     if (tid == 0) sh.keys = 0;
     for (int b = tid; b <= TB_BINS; b += FIN_THREADS) sh.hist[b] = 0;
     __syncthreads();
     const HashEntry* tab = chunk.tables + (int64_t)L * chunk.hash_cap;
-    if (limit <= FIN_ITEMS && narrow) {
-        uint32_t* H = s_fin + 3 * FIN_ITEMS;
-        order_event<uint32_t, true, FIN_THREADS>(P, fa, chunk, ctr, sh, L, limit, tab, s_fin, s_fin + FIN_ITEMS,
-                                                 s_fin + 2 * FIN_ITEMS, H, H + FIN_ITEMS / 32);
-    } else {
-        uint64_t* scratch = fa.sort_items + (int64_t)L * fa.scratch_stride;
-        unsigned* H = reinterpret_cast<unsigned*>(scratch + 2 * (int64_t)chunk.hash_cap);
-        order_event<uint64_t, false, FIN_THREADS>(P, fa, chunk, ctr, sh, L, limit, tab, scratch, scratch + chunk.hash_cap,
-                                                  nullptr, H, H + chunk.hash_cap / 32 + 1);
-    }
+    uint32_t* H = s_fin + 3 * FIN_ITEMS;
+    order_event<uint32_t, true, FIN_THREADS>(P, fa, chunk, ctr, sh, L, limit, tab, s_fin, s_fin + FIN_ITEMS,
+                                             s_fin + 2 * FIN_ITEMS, H, H + FIN_ITEMS / 32);
 }
 
-// The queued long lists (dense events): persistent CTAs, one per SM, 1024 threads, 197 KB of shared memory each.
-__global__ void __launch_bounds__(FIN_BIG_THREADS, 1)
-order_big_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa,
-                 const __grid_constant__ GroupView chunk, Counters* ctr) {
+// The queued long lists (dense events): persistent CTAs that take events from the queue until it is empty.
+template <int T, int ITEMS, int MIN_CTAS>
+__global__ void __launch_bounds__(T, MIN_CTAS)
+order_queue_kernel(const __grid_constant__ SimParams P, const __grid_constant__ FinalizeArgs fa,
+                   const __grid_constant__ GroupView chunk, Counters* ctr, const FinalizeArgs::Queue q) {
     extern __shared__ __align__(16) uint32_t s_fin[];
     __shared__ FinShared sh;
     const int tid = threadIdx.x;
-    const unsigned n_queued = *fa.big_count_list;
+    const unsigned n_queued = *q.count;
     for (;;) {
         __syncthreads();  // (the previous event is done with the shared memory)
         if (tid == 0) {
-            sh.next = atomicAdd(fa.big_cursor, 1u);
+            sh.next = atomicAdd(q.cursor, 1u);
             sh.keys = 0;
         }
-        for (int b = tid; b <= TB_BINS; b += FIN_BIG_THREADS) sh.hist[b] = 0;
+        for (int b = tid; b <= TB_BINS; b += T) sh.hist[b] = 0;
         __syncthreads();
         if (sh.next >= n_queued) return;
-        const int L = (int)fa.big_list[sh.next];
+        const int L = (int)q.list[sh.next];
         const int slot_event = chunk.first_slot + L;
         const int limit = (int)min(chunk.n_entries[slot_event], (unsigned)chunk.hash_cap);
         const HashEntry* tab = chunk.tables + (int64_t)L * chunk.hash_cap;
-        uint32_t* H = s_fin + 3 * FIN_BIG_ITEMS;
-        order_event<uint32_t, true, FIN_BIG_THREADS>(P, fa, chunk, ctr, sh, L, limit, tab, s_fin, s_fin + FIN_BIG_ITEMS,
-                                                     s_fin + 2 * FIN_BIG_ITEMS, H, H + FIN_BIG_ITEMS / 32);
+        if (ITEMS > 0) {  // shared-memory tier
+            uint32_t* H = s_fin + 3 * ITEMS;
+            order_event<uint32_t, true, T>(P, fa, chunk, ctr, sh, L, limit, tab, s_fin, s_fin + ITEMS, s_fin + 2 * ITEMS,
+                                           H, H + ITEMS / 32);
+        } else {  // global scratch, 64-bit items: no dynamic shared memory, the L1 cache keeps its full size
+            uint64_t* scratch = fa.sort_items + (int64_t)L * fa.scratch_stride;
+            unsigned* H = reinterpret_cast<unsigned*>(scratch + 2 * (int64_t)chunk.hash_cap);
+            order_event<uint64_t, false, T>(P, fa, chunk, ctr, sh, L, limit, tab, scratch, scratch + chunk.hash_cap,
+                                            nullptr, H, H + chunk.hash_cap / 32 + 1);
+        }
     }
 }
 

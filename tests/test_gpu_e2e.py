@@ -435,8 +435,8 @@ def test_mesh_weight_table_equals_reference_expression(name, n_events):
 @pytest.mark.parametrize("name", ["c16dd", "c12aa"])
 def test_device_resident_call_holds_the_same_rows(name):
     """`host_copy=False` (what `bench.py` times as `value`) takes other code paths than a call that copies to the host:
-    all groups of a launch in one chunk, long entry lists through `order_big_kernel` (15 % of the 16C(d,d') events,
-    nearly all of 12C(a,a')3a), float64 rows written on the device.  Its rows, read back from the device, equal the
+    all groups of a launch in one chunk, entry lists beyond 8192 entries through `order_queue_kernel` (a few 16C(d,d')
+    events, most of 12C(a,a')3a), float64 rows written on the device.  Its rows, read back from the device, equal the
     rows of the copying call."""
     import bench
     from attpc_engine_b200 import nuclear_map
@@ -452,4 +452,5 @@ def test_device_resident_call_holds_the_same_rows(name):
     back = eng.read_device_result(there)
     assert np.array_equal(back.offsets, host.offsets)
     assert np.array_equal(back.cloud, host.cloud) and np.array_equal(back.labels, host.labels)
-    assert (np.diff(host.offsets) > 5120).any()  # some lists were long enough for the second tier
+    if name == "c12aa":
+        assert (np.diff(host.offsets) > 8192).any()  # lists long enough for the second tier (order_queue_kernel)

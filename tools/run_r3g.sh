@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out
 T=${TAG:-r3g}
 timeout 1500 python -m pytest tests -m gpu -q --timeout 900 --timeout-method=thread 2>&1 | tail -6 > gpurun_out/${T}_tests.log; tail -1 gpurun_out/${T}_tests.log
-TAG=$T KERNELS="deposit_kernel ^order_kernel ^order_big_kernel ^emit_kernel track_kernel point_order_kernel" BENCH_ARGS="" bash tools/profile_r2.sh
+TAG=$T KERNELS="deposit_kernel ^order_kernel order_queue_kernel ^emit_kernel track_kernel point_order_kernel" BENCH_ARGS="" bash tools/profile_r2.sh
 python bench.py --steps 20 --warmup 5 > gpurun_out/${T}_bench_c16dd.log 2>&1; echo "c16dd rc=$?"; tail -1 gpurun_out/${T}_bench_c16dd.log | cut -c1-160
 timeout 600 python bench.py --spyral --steps 20 --warmup 5 --no-cpu > gpurun_out/${T}_bench_c16dd_spyral.log 2>&1; echo "spyral rc=$?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_reference.log 2>&1; echo "reference rc=$?"
