@@ -98,7 +98,7 @@ struct AttpcSim {
 
     // sizing
     int32_t launch_events = 32768;
-    int32_t copy_launch_events = 4096;  // rows go to the host in chunks of this many events (measured optimum, tools/run_r2y.sh)
+    int32_t copy_launch_events = 4096;  // rows go to the host in chunks of this many events (measured optimum, tools/run_r2_e2e_sweep.sh)
     int32_t group_events = 2048;
     int32_t chunk_groups = 16;  // groups per kernel launch when the rows stay on the device
     int32_t unit_points = UNIT_POINTS;     // test knobs (AttpcConfig.unit_points / table_spill_keys)

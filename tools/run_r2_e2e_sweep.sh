@@ -2,7 +2,7 @@
 # pipelined e2e (simulate_stream): engines per GPU x copy chunk, raw typed cloud and Spyral typed rows; e2e GPU tests
 set -u
 mkdir -p gpurun_out
-T=${TAG:-r2y}
+T=${TAG:-r2e2e}
 timeout 900 python -m pytest tests/test_gpu_e2e.py -x -q --timeout 600 --timeout-method=thread 2>&1 | tail -5 > gpurun_out/${T}_tests.log; tail -1 gpurun_out/${T}_tests.log
 for eng in 2 3; do
  for ce in 2048 4096 8192; do
