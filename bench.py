@@ -7,10 +7,17 @@ A *step* is one pass of the whole hot path (`simulate` of detector/simulator.py:
 batch of B synthetic kinematics events per GPU.  Prints ONE JSON line (rank 0).
 
 * value      events/s with the inputs resident in HBM and the results left in HBM (device time, CUDA events
-             recorded by the library on its own stream, max over ranks).
-* e2e        the same metric through the public Python API `simulate_batch` with pinned HOST inputs and the
-             full point clouds copied back to HOST inside the timed region.
-* roofline   dominant kernel (by device time) against the measured HBM peak, algorithmic bytes of SURVEY.md 8(d).
+             recorded by the library on its own stream, max over ranks; L2 flushed between steps).
+* e2e        the same metric through the public Python API `simulate_stream` (the pipelined `simulate_batch` that
+             `run_simulation` is built on, `--e2e-engines` engines per GPU): pinned HOST inputs copied in and the full
+             point clouds copied back to pinned HOST memory every step, as packed typed columns (8 B/row + 1 KB per
+             event, lossless).  e2e_sync: one synchronous `simulate_batch` call per step.  e2e_float64: the pipelined
+             call returning the reference's own float64 / int64 arrays (32 B/row).  e2e_decoded: one step plus the
+             numpy decode of the columns on one host thread.
+* roofline   dominant kernel (by device time): its issue-slot roofline (warp instructions per launch from the committed
+             ncu capture over the launch time measured live, against SMs x 4 schedulers x clock), the HBM fraction of
+             the whole step (algorithmic bytes of SURVEY.md 8(d) against the measured copy peak) beside it, and the
+             kernel's DRAM traffic from the same capture (profiles/traffic.json).
 * cpu_baseline / --impl reference
              the CPU oracle port of the reference (oracle/attpc_oracle.py: scipy Radau + numba, the reference's
              own tool chain) on all host cores, on a bounded sample of the same events.
