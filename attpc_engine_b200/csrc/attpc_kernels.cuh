@@ -2159,7 +2159,9 @@ order_queue_kernel(const __grid_constant__ SimParams P, const __grid_constant__ 
         if (sh.next >= n_queued) return;
         const int L = (int)q.list[sh.next];
         const int slot_event = chunk.first_slot + L;
-        const int limit = (int)min(chunk.n_entries[slot_event], (unsigned)chunk.hash_cap);
+        // (an attempt that overflowed a buffer is void: its lists may be incomplete, the host redoes the launch)
+        const bool void_attempt = (ctr->overflow_points | ctr->overflow_hash) != 0;
+        const int limit = void_attempt ? 0 : (int)min(chunk.n_entries[slot_event], (unsigned)chunk.hash_cap);
         const HashEntry* tab = chunk.tables + (int64_t)L * chunk.hash_cap;
         if (ITEMS > 0) {  // shared-memory tier
             uint32_t* H = s_fin + 3 * ITEMS;

@@ -248,8 +248,9 @@ def simulate_stream(
     """Pipelined `simulate_batch` over a sequence of batches: yields ``(k, SimBatch)`` in ascending ``k``.
 
     ``batches[k]`` is ``(momenta [B, K, 4], vertices [B, 3], first_event)`` or a callable returning that (called in
-    the worker, e.g. to read a chunk of a file; one at a time unless it has a true ``thread_safe`` attribute).  Batch ``k`` goes to worker ``k mod W``, ``W = len(devices) *
-    engines_per_device`` workers, each a host thread with its own engine (its own streams and pinned buffers).  Two
+    the worker, e.g. to read a chunk of a file; one at a time unless it has a true ``thread_safe`` attribute).
+    Batch ``k`` goes to worker ``k mod W``, ``W = len(devices) * engines_per_device`` workers, each a host thread
+    with its own engine (its own streams and pinned buffers).  Two
     engines on one GPU overlap the device-to-host copy of one batch with the kernels of the next: the end-to-end
     rate of a single GPU is otherwise bounded by ``compute + copy`` of one batch at a time.  A yielded batch is valid
     until the consumer asks for the next one (its worker starts on batch ``k + W`` only then), so ``copy=False``
