@@ -165,8 +165,22 @@ class SimBatch:
             out[rows[lo:hi] - a] = c["big_electrons"][lo:hi]
         return out
 
+    def _decode_packed(self) -> bool:
+        """Cloud and labels straight from the packed columns in one multi-threaded pass (`_decode.py`), when possible."""
+        if self.packed is None or self._cloud is not None:
+            return False
+        from ._decode import decode_packed
+
+        out = decode_packed(self.packed, self.offsets)
+        if out is None:
+            return False
+        self._cloud, self._labels = out
+        return True
+
     @property
     def cloud(self) -> np.ndarray:
+        if self._cloud is None and self._decode_packed():
+            return self._cloud
         if self._cloud is None and self.columns is not None:
             c = self.columns
             out = np.empty((len(c["pad"]), 3), dtype=np.float64)
@@ -179,6 +193,8 @@ class SimBatch:
 
     @property
     def labels(self) -> np.ndarray:
+        if self._labels is None and self._decode_packed():
+            return self._labels
         if self._labels is None and self.columns is not None:
             self._labels = self.columns["label8"].astype(np.int64)
         return self._labels

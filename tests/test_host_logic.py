@@ -451,6 +451,19 @@ def test_packed_columns_decode():
         assert np.array_equal(cloud[:, 0], pad[a:b]) and np.array_equal(cloud[:, 1], tb[a:b] + wiggle[a:b] / 65536.0)
         assert np.array_equal(cloud[:, 2], electrons[a:b])
         assert np.array_equal(labels, np.array([2, 3, 5])[rank[a:b]]) and labels.dtype == np.int64
+    from attpc_engine_b200.detector import _decode
+
+    if _decode.HAVE_NUMBA:  # the one-pass decoder and the numpy route give the same arrays
+        fast = SimBatch(100, offsets, packed=packed)
+        assert fast._decode_packed() and fast._columns is None
+        saved, _decode.HAVE_NUMBA = _decode.HAVE_NUMBA, False
+        try:
+            slow = SimBatch(100, offsets, packed=packed)
+            assert not slow._decode_packed()
+            assert np.array_equal(fast.cloud, slow.cloud) and np.array_equal(fast.labels, slow.labels)
+            assert fast.cloud.dtype == slow.cloud.dtype == np.float64 and fast.labels.dtype == slow.labels.dtype == np.int64
+        finally:
+            _decode.HAVE_NUMBA = saved
     cols = batch.columns
     assert cols["pad"].dtype == np.int16 and cols["tb_q16"].dtype == np.uint32 and cols["label8"].dtype == np.int8
     assert np.array_equal(cols["pad"], pad) and np.array_equal(cols["tb_q16"], (tb.astype(np.uint32) << 16) | wiggle)
