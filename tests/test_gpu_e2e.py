@@ -242,6 +242,29 @@ def test_spyral_writer_layout_through_h5py_stand_in(dist, monkeypatch, tmp_path)
     rows, labels = batch.event_rows(7)
     assert np.array_equal(d.data, rows) and np.array_equal(files[1]["cloud"]["labels_7"].data, labels)
     assert d.attrs["orig_run"] == 1 and d.attrs["orig_event"] == 7 and d.attrs["ic_amplitude"] == -1.0
+    # what the downstream consumer (Spyral's point-cloud phase; docs/user_guide/detector/index.md:176-196, writer.py:97-110,
+    # 240-251) reads: events min_event..max_event of every file, columns x, y, z, amplitude, integral, pad, tb, scale
+    win, mm = float(cfg.elec_params.windows_edge), float(cfg.elec_params.micromegas_edge)
+    seen = 0
+    for f in files:
+        group = f["cloud"]
+        for e in range(group.attrs["min_event"], group.attrs["max_event"] + 1):
+            if f"cloud_{e}" not in group:  # (an event without points is not written, simulator.py:204)
+                continue
+            c, lab = group[f"cloud_{e}"].data, group[f"labels_{e}"].data
+            assert c.ndim == 2 and c.shape[1] == 8 and c.dtype == np.float64 and len(lab) == len(c)
+            if len(c) == 0:  # (every point below the ADC threshold: the reference writes the empty dataset too)
+                continue
+            pad = c[:, 5].astype(np.int64)
+            assert np.array_equal(c[:, 5], pad) and pad.min() >= 0 and pad.max() < len(cfg.pad_sizes)
+            assert np.array_equal(c[:, 0], cfg.pad_centers[pad, 0]) and np.array_equal(c[:, 1], cfg.pad_centers[pad, 1])
+            assert np.array_equal(c[:, 7], cfg.pad_sizes[pad])
+            assert np.array_equal(c[:, 2], (win - c[:, 6]) / (win - mm) * cfg.det_params.length * 1000.0)
+            assert np.all(np.diff(c[:, 2]) >= 0.0) and c[:, 6].min() >= 0.0 and c[:, 6].max() < 512.0  # z-sorted, tb masked
+            assert np.all(c[:, 3] > cfg.elec_params.adc_threshold) and np.all(c[:, 3] <= 4095.0) and np.all(c[:, 4] >= c[:, 3])
+            assert set(np.unique(lab)) <= set(idx)
+            seen += 1
+    assert seen >= 10
 
 
 @pytest.mark.parametrize("name", ["c16dd", "c12aa"])
