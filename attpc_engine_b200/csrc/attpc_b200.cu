@@ -228,7 +228,7 @@ int next_pow2(int64_t v) {
     return (int)p;
 }
 
-// 64-bit words of scratch per event for the entry lists that finalize_kernel cannot order in shared memory: two item
+// 64-bit words of scratch per event for the entry lists that the ordering kernels cannot keep in shared memory: two item
 // arrays and two bit-mask / running-count arrays
 int64_t scratch_stride(int64_t hash_cap) { return 2 * hash_cap + hash_cap / 32 + 2; }
 
